@@ -1,0 +1,124 @@
+/*
+ * lepton_b200.h -- C ABI of the B200-native Lepton arithmetic-coding path.
+ *
+ * This is the drop-in boundary for the reference's BaseEncoder / BaseDecoder plug-in interface
+ * (/root/reference/src/lepton/base_coders.hh:26-65):
+ *
+ *   lepb200_encode_images  replaces  BaseEncoder::encode_chunk(const UncompressedComponents*, FileWriter*,
+ *                                    const ThreadHandoff* selected_splits, unsigned num_selected_splits)
+ *                          (base_coders.hh:59-62, called from write_ujpg, src/lepton/jpgcoder.cc:4079-4081),
+ *                          i.e. VP8ComponentEncoder::vp8_full_encoder up to -- not including -- the MuxWriter
+ *                          interleave (src/lepton/vp8_encoder.cc:521-573): it returns one bool-coder byte
+ *                          stream per thread-segment.  Batched over images.
+ *   lepb200_decode_images  replaces  BaseDecoder::decode_chunk(UncompressedComponents*) /
+ *                          BaseDecoder::decode_row (base_coders.hh:31,38-44; src/lepton/vp8_decoder.cc:387-490,
+ *                          src/lepton/lepton_codec.cc:266-309): demuxed per-segment streams in, full
+ *                          coefficient planes out.
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All hot-path compute runs in hand-written sm_100a
+ * CUDA kernels; there is no CPU fallback: without a CUDA device every entry point that needs one fails
+ * with LEPB200_ERR_NO_DEVICE.
+ *
+ * Data layout at the boundary is the reference's: a component plane is a row-major array of AlignedBlock
+ * (64 x int16, 128 bytes; order: 49 "7x7" coefficients in zig-zag order, DC, 7 row-0 ACs, 7 column-0 ACs;
+ * src/vp8/util/aligned_block.hh:32-44,98-161), `bch` blocks per row, `bcv` rows
+ * (src/lepton/uncompressed_components.hh:24-302).
+ */
+#ifndef LEPTON_B200_H_
+#define LEPTON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEPB200_MAX_SEGMENTS 16 /* MuxReader::MAX_STREAM_ID, src/io/MuxReader.hh:201 */
+
+/* return codes of the API itself (per-segment coding status uses the reference's ExitCode values) */
+enum {
+    LEPB200_OK = 0,
+    LEPB200_ERR_NO_DEVICE = -1,
+    LEPB200_ERR_CUDA = -2,
+    LEPB200_ERR_INVALID = -3,
+    LEPB200_ERR_NOMEM = -4
+};
+
+/* per-segment status: reference ExitCode values (src/vp8/util/memory.hh:13-39) */
+enum {
+    LEPB200_ST_SUCCESS = 0,
+    LEPB200_ST_ASSERTION_FAILURE = 1,
+    LEPB200_ST_COEFFICIENT_OUT_OF_RANGE = 6,
+    LEPB200_ST_STREAM_INCONSISTENT = 7,
+    LEPB200_ST_UNSUPPORTED_JPEG_WITH_ZERO_IDCT_0 = 43,
+    LEPB200_ST_OUTPUT_OVERFLOW = 100 /* not a reference code: the caller-independent output arena was too small */
+};
+
+typedef struct lepb200_ctx lepb200_ctx;
+
+/* One image = what UncompressedComponents + the selected ThreadHandoff splits carry across the boundary. */
+typedef struct lepb200_image {
+    int32_t ncmp;                    /* 1..3 colour components (get_num_components) */
+    int32_t mcuv;                    /* MCU rows (get_mcu_count_vertical) */
+    int32_t bch[3];                  /* blocks per row of each component plane (block_width) */
+    int32_t bcv[3];                  /* allocated block rows (original_height) */
+    int32_t trunc_bcv[3];            /* rows actually coded (get_max_coded_heights); == bcv unless truncated */
+    int32_t trunc_bc[3];             /* blocks actually coded (component_size_in_blocks); == bch*bcv unless truncated */
+    uint16_t qtable_zigzag[3][64];   /* get_quantization_tables(cmp): DQT entries in zig-zag order */
+    int16_t* planes[3];              /* HOST memory, bch*bcv AlignedBlocks each; input for encode, output for decode */
+    int32_t nseg;                    /* number of thread-segments, 1..16 (selected_splits) */
+    int32_t luma_y_start[LEPB200_MAX_SEGMENTS]; /* ThreadHandoff::luma_y_start of each segment; segment i ends
+                                                    where i+1 starts, the last one runs to the end of the image */
+} lepb200_image;
+
+/* One thread-segment's bool-coder stream. */
+typedef struct lepb200_stream {
+    const uint8_t* data;             /* encode: points into memory owned by the context, valid until the next call */
+    uint64_t len;
+    int32_t status;                  /* LEPB200_ST_* */
+    uint32_t reserved;
+    uint64_t ndecisions;             /* binary decisions coded (VPXBoolWriter::put / VPXBoolReader::get calls) */
+} lepb200_stream;
+
+/* Creates a context on CUDA device `device` (one context per GPU / per host thread). */
+int lepb200_create(lepb200_ctx** out, int device);
+void lepb200_destroy(lepb200_ctx* ctx);
+const char* lepb200_last_error(const lepb200_ctx* ctx);
+
+/* Page-locked host memory for planes / streams handed to the calls below (pageable memory works too, slower). */
+void* lepb200_pinned_alloc(size_t bytes);
+void lepb200_pinned_free(void* p);
+
+/* ---- one-call forms (host buffers in, host buffers out; H2D + kernel + D2H) ---- */
+/* out must have room for sum(images[i].nseg) entries, filled image-major. */
+int lepb200_encode_images(lepb200_ctx* ctx, const lepb200_image* images, int nimages, lepb200_stream* out);
+/* in has sum(images[i].nseg) entries (data/len used); decoded planes are written to images[i].planes.
+ * status_out (optional) receives one LEPB200_ST_* per segment. */
+int lepb200_decode_images(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in,
+                          int32_t* status_out);
+
+/* ---- staged forms (for pipelining and for timing the kernel with inputs resident in HBM) ---- */
+int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages); /* H2D planes + job tables */
+int lepb200_encode_launch(lepb200_ctx* ctx);                                           /* kernel only (async) */
+int lepb200_encode_fetch(lepb200_ctx* ctx, lepb200_stream* out);                       /* sync + D2H streams */
+int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in);
+int lepb200_decode_launch(lepb200_ctx* ctx);
+int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, int32_t* status_out);
+
+/* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */
+float lepb200_last_kernel_ms(lepb200_ctx* ctx);
+/* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
+uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx);
+/* Sum over the last uploaded batch of 128 * coded blocks + stream bytes (SURVEY.md section 8(d) algorithmic bytes);
+ * valid after *_fetch. */
+uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx);
+/* Size in bytes of one per-warp probability model (informational). */
+size_t lepb200_model_bytes(void);
+/* 1 if a CUDA device is usable from this process. */
+int lepb200_device_available(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEPTON_B200_H_ */

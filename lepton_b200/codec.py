@@ -1,0 +1,266 @@
+"""ctypes binding of include/lepton_b200.h -- the host-side mirror of the reference's plug-in boundary.
+
+Reference interface mirrored (file:line in /root/reference):
+  * ``BaseEncoder::encode_chunk(const UncompressedComponents*, FileWriter*, const ThreadHandoff*, unsigned)``
+    (src/lepton/base_coders.hh:59-62)  ->  :meth:`LeptonB200Codec.encode_images`
+  * ``BaseDecoder::decode_chunk(UncompressedComponents*)`` (src/lepton/base_coders.hh:31)
+    ->  :meth:`LeptonB200Codec.decode_images`
+A :class:`CoefImage` carries what ``UncompressedComponents`` + the selected ``ThreadHandoff`` splits carry:
+component geometry, quantisation tables (zig-zag order), coefficient planes in AlignedBlock order, segment starts.
+Per-segment results use the reference's ExitCode values (src/vp8/util/memory.hh:13-39).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_SEGMENTS = 16
+
+
+class LeptonB200Error(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "liblepton_b200.so")
+
+
+class _Image(ctypes.Structure):
+    _fields_ = [
+        ("ncmp", ctypes.c_int32), ("mcuv", ctypes.c_int32),
+        ("bch", ctypes.c_int32 * 3), ("bcv", ctypes.c_int32 * 3),
+        ("trunc_bcv", ctypes.c_int32 * 3), ("trunc_bc", ctypes.c_int32 * 3),
+        ("qtable_zigzag", (ctypes.c_uint16 * 64) * 3),
+        ("planes", ctypes.c_void_p * 3),
+        ("nseg", ctypes.c_int32),
+        ("luma_y_start", ctypes.c_int32 * MAX_SEGMENTS),
+    ]
+
+
+class _Stream(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("len", ctypes.c_uint64), ("status", ctypes.c_int32),
+                ("reserved", ctypes.c_uint32), ("ndecisions", ctypes.c_uint64)]
+
+
+_LIB = None
+
+_EXPORTS = [
+    "lepb200_create", "lepb200_destroy", "lepb200_last_error", "lepb200_pinned_alloc", "lepb200_pinned_free",
+    "lepb200_encode_images", "lepb200_decode_images", "lepb200_encode_upload", "lepb200_encode_launch",
+    "lepb200_encode_fetch", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
+    "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
+    "lepb200_device_available",
+]
+
+
+def lib():
+    """Load the C-ABI library; raises (never falls back) if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LeptonB200Error("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)" % path)
+    L = ctypes.CDLL(path)
+    for name in _EXPORTS:
+        if not hasattr(L, name):
+            raise LeptonB200Error("liblepton_b200.so does not export %s" % name)
+    vp, ip = ctypes.c_void_p, ctypes.POINTER(_Image)
+    sp = ctypes.POINTER(_Stream)
+    L.lepb200_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    L.lepb200_create.restype = ctypes.c_int
+    L.lepb200_destroy.argtypes = [vp]
+    L.lepb200_destroy.restype = None
+    L.lepb200_last_error.argtypes = [vp]
+    L.lepb200_last_error.restype = ctypes.c_char_p
+    L.lepb200_pinned_alloc.argtypes = [ctypes.c_size_t]
+    L.lepb200_pinned_alloc.restype = vp
+    L.lepb200_pinned_free.argtypes = [vp]
+    L.lepb200_pinned_free.restype = None
+    L.lepb200_encode_images.argtypes = [vp, ip, ctypes.c_int, sp]
+    L.lepb200_encode_upload.argtypes = [vp, ip, ctypes.c_int]
+    L.lepb200_encode_launch.argtypes = [vp]
+    L.lepb200_encode_fetch.argtypes = [vp, sp]
+    L.lepb200_decode_images.argtypes = [vp, ip, ctypes.c_int, sp, ctypes.POINTER(ctypes.c_int32)]
+    L.lepb200_decode_upload.argtypes = [vp, ip, ctypes.c_int, sp]
+    L.lepb200_decode_launch.argtypes = [vp]
+    L.lepb200_decode_fetch.argtypes = [vp, ip, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
+    for f in ("lepb200_encode_images", "lepb200_encode_upload", "lepb200_encode_launch", "lepb200_encode_fetch",
+              "lepb200_decode_images", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
+              "lepb200_device_available"):
+        getattr(L, f).restype = ctypes.c_int
+    L.lepb200_last_kernel_ms.argtypes = [vp]
+    L.lepb200_last_kernel_ms.restype = ctypes.c_float
+    L.lepb200_kernel_launches.argtypes = [vp]
+    L.lepb200_kernel_launches.restype = ctypes.c_uint64
+    L.lepb200_last_algorithmic_bytes.argtypes = [vp]
+    L.lepb200_last_algorithmic_bytes.restype = ctypes.c_uint64
+    L.lepb200_model_bytes.restype = ctypes.c_size_t
+    _LIB = L
+    return L
+
+
+@dataclass
+class CoefImage:
+    """Quantised DCT coefficients of one JPEG plus the thread-segment split chosen for it."""
+    ncmp: int
+    mcuv: int
+    bch: Sequence[int]
+    bcv: Sequence[int]
+    qtables_zigzag: Sequence[Sequence[int]]
+    planes: List[np.ndarray]                 # per component int16 [bch*bcv, 64], AlignedBlock order
+    luma_y_start: Sequence[int] = (0,)
+    trunc_bcv: Optional[Sequence[int]] = None
+    trunc_bc: Optional[Sequence[int]] = None
+    jpeg_bytes: int = 0                       # size of the source JPEG (for MB/s accounting only)
+    _keep: list = field(default_factory=list, repr=False)
+
+    @property
+    def nseg(self) -> int:
+        return len(self.luma_y_start)
+
+    def blocks(self) -> int:
+        return int(sum(self.bch[c] * self.bcv[c] for c in range(self.ncmp)))
+
+    def to_c(self) -> _Image:
+        im = _Image()
+        im.ncmp, im.mcuv, im.nseg = self.ncmp, self.mcuv, self.nseg
+        if not (1 <= self.nseg <= MAX_SEGMENTS):
+            raise LeptonB200Error("nseg out of range")
+        for c in range(self.ncmp):
+            p = self.planes[c]
+            if p.dtype != np.int16 or not p.flags["C_CONTIGUOUS"] or p.size != self.bch[c] * self.bcv[c] * 64:
+                raise LeptonB200Error("plane %d must be C-contiguous int16 of bch*bcv*64 elements" % c)
+            im.bch[c], im.bcv[c] = self.bch[c], self.bcv[c]
+            im.trunc_bcv[c] = self.trunc_bcv[c] if self.trunc_bcv is not None else self.bcv[c]
+            im.trunc_bc[c] = self.trunc_bc[c] if self.trunc_bc is not None else self.bch[c] * self.bcv[c]
+            for i in range(64):
+                im.qtable_zigzag[c][i] = int(self.qtables_zigzag[c][i])
+            im.planes[c] = p.ctypes.data
+        for s, y in enumerate(self.luma_y_start):
+            im.luma_y_start[s] = int(y)
+        return im
+
+
+@dataclass
+class SegmentResult:
+    data: bytes
+    status: int
+    ndecisions: int
+
+
+class LeptonB200Codec:
+    """One context per GPU.  ``encode_images`` / ``decode_images`` are the whole-batch equivalents of the
+    reference's per-file ``encode_chunk`` / ``decode_chunk``."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        self._ctx = ctypes.c_void_p()
+        rc = self._L.lepb200_create(ctypes.byref(self._ctx), device)
+        if rc != 0:
+            raise LeptonB200Error("lepb200_create(device=%d) failed with %d (no CUDA device? there is no CPU fallback)"
+                                  % (device, rc))
+        self.device = device
+
+    def close(self):
+        if self._ctx:
+            self._L.lepb200_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise LeptonB200Error("%s failed (%d): %s" % (what, rc, self._L.lepb200_last_error(self._ctx).decode()))
+
+    # ---- staged API -------------------------------------------------------------------------------
+    def _c_images(self, images):
+        arr = (_Image * len(images))()
+        for i, im in enumerate(images):
+            arr[i] = im.to_c()
+        return arr
+
+    def encode_upload(self, images):
+        self._enc_imgs = images
+        self._enc_c = self._c_images(images)
+        self._check(self._L.lepb200_encode_upload(self._ctx, self._enc_c, len(images)), "encode_upload")
+
+    def encode_launch(self):
+        self._check(self._L.lepb200_encode_launch(self._ctx), "encode_launch")
+
+    def encode_fetch(self, copy=True):
+        n = sum(im.nseg for im in self._enc_imgs)
+        out = (_Stream * n)()
+        self._check(self._L.lepb200_encode_fetch(self._ctx, out), "encode_fetch")
+        res, k = [], 0
+        for im in self._enc_imgs:
+            segs = []
+            for _ in range(im.nseg):
+                s = out[k]
+                data = ctypes.string_at(s.data, s.len) if (copy and s.len) else b""
+                segs.append(SegmentResult(data, s.status, s.ndecisions))
+                k += 1
+            res.append(segs)
+        self.last_lens = [out[i].len for i in range(n)]
+        return res
+
+    def encode_images(self, images, copy=True):
+        self.encode_upload(images)
+        self.encode_launch()
+        return self.encode_fetch(copy=copy)
+
+    def decode_upload(self, images, streams):
+        """streams: per image, a list of per-segment byte strings"""
+        n = sum(im.nseg for im in images)
+        arr = (_Stream * n)()
+        keep, k = [], 0
+        for im, segs in zip(images, streams):
+            if len(segs) != im.nseg:
+                raise LeptonB200Error("stream count != nseg")
+            for s in segs:
+                buf = np.frombuffer(s, dtype=np.uint8)
+                keep.append(buf)
+                arr[k].data = buf.ctypes.data if len(buf) else None
+                arr[k].len = len(buf)
+                k += 1
+        self._dec_imgs, self._dec_keep = images, keep
+        self._dec_c = self._c_images(images)
+        self._check(self._L.lepb200_decode_upload(self._ctx, self._dec_c, len(images), arr), "decode_upload")
+
+    def decode_launch(self):
+        self._check(self._L.lepb200_decode_launch(self._ctx), "decode_launch")
+
+    def decode_fetch(self):
+        n = sum(im.nseg for im in self._dec_imgs)
+        st = (ctypes.c_int32 * n)()
+        self._check(self._L.lepb200_decode_fetch(self._ctx, self._dec_c, len(self._dec_imgs), st), "decode_fetch")
+        return list(st)
+
+    def decode_images(self, images, streams):
+        """Decodes into ``images[i].planes`` (pre-allocated).  Returns per-segment status codes."""
+        self.decode_upload(images, streams)
+        self.decode_launch()
+        return self.decode_fetch()
+
+    # ---- introspection ----------------------------------------------------------------------------
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self._L.lepb200_last_kernel_ms(self._ctx))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.lepb200_kernel_launches(self._ctx))
+
+    @property
+    def last_algorithmic_bytes(self) -> int:
+        return int(self._L.lepb200_last_algorithmic_bytes(self._ctx))

@@ -1,0 +1,453 @@
+// lep_capi.cu -- context, device memory management and the C ABI declared in include/lepton_b200.h.
+// Single translation unit: the kernels are included so that nvcc sees one module (no -rdc needed).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lepton_b200.h"
+#include "lep_common.cuh"
+#include "lep_predict.cuh"
+#include "lep_encode.cu"
+#include "lep_decode.cu"
+
+using namespace lepb200;
+
+namespace {
+
+// zig-zag position of each raster index (reference src/vp8/model/jpeg_meta.hh:13-23)
+const uint8_t k_zigzag[64] = {
+    0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42, 3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44, 53,
+    10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+// first column of icos_base_8192_scaled (src/vp8/model/jpeg_meta.hh:48-58): entries [i*8]
+const int k_icos_base_col0[8] = {8192, 11363, 10703, 9633, 8192, 6436, 4433, 2260};
+// src/vp8/model/model.hh:264-274
+const uint16_t k_freqmax[64] = {
+    1024, 931, 985, 968, 1020, 968, 1020, 1020, 932, 858, 884, 840, 932, 838, 854, 854,
+    985, 884, 871, 875, 985, 878, 871, 854, 967, 841, 876, 844, 967, 886, 870, 837,
+    1020, 932, 985, 967, 1020, 969, 1020, 1020, 969, 838, 878, 886, 969, 838, 969, 838,
+    1020, 854, 871, 870, 1010, 969, 1020, 1020, 1020, 854, 854, 838, 1020, 838, 1020, 838};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct lepb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    DevBuf d_planes, d_streams, d_dense, d_images, d_segs, d_order, d_counter, d_models, d_rows;
+    HostBuf h_segs, h_dense, h_stage;
+    std::vector<ImageDesc> images;
+    std::vector<SegDesc> segs;
+    std::vector<int> order;
+    std::vector<size_t> seg_blocks;
+    std::vector<size_t> plane_bytes;      // per image*3
+    size_t row_stride = 0;
+    int grid = 0;
+    bool have_batch = false, launched = false, is_encode = true;
+    float last_ms = -1.f;
+    uint64_t launches = 0;
+    uint64_t alg_bytes = 0;
+    uint64_t coded_blocks = 0;
+};
+
+#define CK(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return e_ == cudaErrorMemoryAllocation ? LEPB200_ERR_NOMEM : LEPB200_ERR_CUDA;  \
+        }                                                                                   \
+    } while (0)
+
+namespace {
+
+// ProbabilityTablesBase::set_quantization_table (src/vp8/model/model.hh:247-290)
+int fill_quant(ImageDesc& d, int c, const uint16_t zz[64], bool check_zero) {
+    uint16_t* q = d.q[c];
+    for (int i = 0; i < 64; ++i) q[i] = zz[k_zigzag[i]];
+    for (int r = 0; r < 8; ++r) {
+        for (int i = 0; i < 8; ++i) {
+            d.icos_x[c][r * 8 + i] = k_icos_base_col0[i] * (int)q[i * 8 + r];
+            d.icos_y[c][r * 8 + i] = k_icos_base_col0[i] * (int)q[r * 8 + i];
+        }
+        if (d.icos_x[c][r * 8] == 0 || d.icos_y[c][r * 8] == 0) {
+            if (check_zero) return LEPB200_ST_UNSUPPORTED_JPEG_WITH_ZERO_IDCT_0;
+            // decode side (filetype == LEPTON, model.hh:257): the reference goes on and would divide by zero; refuse.
+            return LEPB200_ST_UNSUPPORTED_JPEG_WITH_ZERO_IDCT_0;
+        }
+    }
+    for (int k = 0; k < 64; ++k) {
+        uint16_t fm = (uint16_t)(k_freqmax[k] + q[k] - 1);
+        if (q[k]) fm = (uint16_t)(fm / q[k]);
+        int len = 0;
+        for (uint32_t v = fm; v; v >>= 1) ++len;
+        d.min_thr[c][k] = (uint8_t)(len > 7 ? len - 7 : 0);
+    }
+    return 0;
+}
+
+// Rows of component c coded by a segment [min_y, max_y) (row iteration of lepton_codec.hh:41-100).
+size_t segment_blocks(const lepb200_image& im, int min_y, int max_y, bool last) {
+    size_t n = 0;
+    int v0 = im.bcv[0] / im.mcuv;
+    for (int c = 0; c < im.ncmp; ++c) {
+        int mult = im.bcv[c] / im.mcuv;
+        long y0 = (long)(min_y / std::max(v0, 1)) * mult, y1 = last ? im.trunc_bcv[c] : (long)((max_y + v0 - 1) / std::max(v0, 1)) * mult;
+        y1 = std::min<long>(y1, im.trunc_bcv[c]);
+        if (y1 > y0) n += (size_t)(y1 - y0) * im.bch[c];
+    }
+    return n;
+}
+
+int validate_image(lepb200_ctx* ctx, const lepb200_image& im) {
+    if (im.ncmp < 1 || im.ncmp > 3 || im.mcuv <= 0 || im.nseg < 1 || im.nseg > LEPB200_MAX_SEGMENTS) {
+        ctx->err = "invalid image descriptor (ncmp/mcuv/nseg)";
+        return LEPB200_ERR_INVALID;
+    }
+    for (int c = 0; c < im.ncmp; ++c) {
+        if (im.bch[c] <= 0 || im.bcv[c] <= 0 || im.bcv[c] % im.mcuv || im.trunc_bcv[c] < 0 || im.trunc_bcv[c] > im.bcv[c] ||
+            im.trunc_bc[c] < 0 || (long long)im.trunc_bc[c] > (long long)im.bch[c] * im.bcv[c] || !im.planes[c]) {
+            ctx->err = "invalid component geometry";
+            return LEPB200_ERR_INVALID;
+        }
+    }
+    for (int s = 0; s + 1 < im.nseg; ++s)
+        if (im.luma_y_start[s] > im.luma_y_start[s + 1]) { ctx->err = "segment starts must be non-decreasing"; return LEPB200_ERR_INVALID; }
+    return 0;
+}
+
+// Common part of encode/decode upload: job tables, pools, plane arena layout.
+int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool encode, const lepb200_stream* in) {
+    ctx->have_batch = false; ctx->launched = false; ctx->is_encode = encode;
+    if (nimages <= 0 || !images) { ctx->err = "empty batch"; return LEPB200_ERR_INVALID; }
+    ctx->images.assign(nimages, ImageDesc());
+    ctx->segs.clear(); ctx->seg_blocks.clear(); ctx->plane_bytes.assign((size_t)nimages * 3, 0);
+    size_t plane_total = 0, stream_total = 0, row_stride = 0;
+    int sidx = 0;
+    for (int i = 0; i < nimages; ++i) {
+        const lepb200_image& im = images[i];
+        int v = validate_image(ctx, im);
+        if (v) return v;
+        ImageDesc& d = ctx->images[i];
+        memset(&d, 0, sizeof(d));
+        d.ncmp = im.ncmp; d.mcuv = im.mcuv;
+        int qstatus = 0;
+        size_t rs = 0;
+        for (int c = 0; c < im.ncmp; ++c) {
+            d.bch[c] = im.bch[c]; d.bcv[c] = im.bcv[c]; d.trunc_bcv[c] = im.trunc_bcv[c]; d.trunc_bc[c] = im.trunc_bc[c];
+            d.mult[c] = im.bcv[c] / im.mcuv;
+            int qs = fill_quant(d, c, im.qtable_zigzag[c], encode);
+            if (qs) qstatus = qs;
+            size_t pb = (size_t)im.bch[c] * im.bcv[c] * 128;
+            ctx->plane_bytes[(size_t)i * 3 + c] = pb;
+            d.plane[c] = plane_total;                     // offset for now; rebased below
+            plane_total += align_up(pb, 256);
+            rs += (size_t)im.bch[c] * 16 + align_up((size_t)im.bch[c], 16);
+        }
+        row_stride = std::max(row_stride, align_up(rs, 256));
+        for (int s = 0; s < im.nseg; ++s, ++sidx) {
+            SegDesc sd;
+            memset(&sd, 0, sizeof(sd));
+            sd.image = i;
+            sd.min_y = im.luma_y_start[s];
+            sd.is_last = s + 1 == im.nseg;
+            sd.max_y = sd.is_last ? im.bcv[0] : im.luma_y_start[s + 1];
+            sd.status = qstatus;
+            size_t nb = segment_blocks(im, sd.min_y, sd.max_y, sd.is_last);
+            ctx->seg_blocks.push_back(nb);
+            if (encode) {
+                size_t cap = align_up(nb * 128 + 4096, 256);
+                sd.stream = stream_total; sd.cap = (uint32_t)cap;
+                stream_total += cap;
+            } else {
+                sd.stream = stream_total; sd.cap = (uint32_t)in[sidx].len;
+                stream_total += align_up((size_t)in[sidx].len + 16, 16);
+            }
+            ctx->segs.push_back(sd);
+        }
+    }
+    const int nseg = (int)ctx->segs.size();
+    // largest segments first (longest-processing-time-first on the persistent warps)
+    ctx->order.resize(nseg);
+    for (int i = 0; i < nseg; ++i) ctx->order[i] = i;
+    std::stable_sort(ctx->order.begin(), ctx->order.end(), [&](int a, int b) { return ctx->seg_blocks[a] > ctx->seg_blocks[b]; });
+
+    // persistent grid: as many CTAs as can be resident, but no more warps than segments
+    int per_sm = 0;
+    if (encode) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lep_encode_kernel, ENC_WARPS_PER_CTA * 32, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lep_decode_kernel, DEC_WARPS_PER_CTA * 32, 0));
+    const int wpc = encode ? ENC_WARPS_PER_CTA : DEC_WARPS_PER_CTA;
+    int grid = std::max(1, std::min(per_sm * ctx->sm_count, (nseg + wpc - 1) / wpc));
+    ctx->grid = grid;
+    ctx->row_stride = row_stride;
+
+    CK(ctx->d_planes.reserve(plane_total));
+    CK(ctx->d_streams.reserve(stream_total + 256));
+    CK(ctx->d_images.reserve(sizeof(ImageDesc) * nimages));
+    CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
+    CK(ctx->d_order.reserve(sizeof(int) * nseg));
+    CK(ctx->d_counter.reserve(256));
+    CK(ctx->d_models.reserve((size_t)grid * wpc * MODEL_BYTES));
+    CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
+    for (int i = 0; i < nimages; ++i)
+        for (int c = 0; c < ctx->images[i].ncmp; ++c) ctx->images[i].plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
+    for (auto& sd : ctx->segs) sd.stream += (unsigned long long)(uintptr_t)ctx->d_streams.p;
+    CK(cudaMemcpyAsync(ctx->d_images.p, ctx->images.data(), sizeof(ImageDesc) * nimages, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_segs.p, ctx->segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_order.p, ctx->order.data(), sizeof(int) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+__global__ void lep_compact_kernel(const SegDesc* __restrict__ segs, const unsigned long long* __restrict__ dst_off, uint8_t* __restrict__ dense, int nseg) {
+    // one CTA per segment: copy the produced stream bytes into the dense output buffer (16-byte body, byte tails)
+    const int s = blockIdx.x;
+    if (s >= nseg) return;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(segs[s].stream);
+    uint8_t* dst = dense + dst_off[s];
+    const uint32_t n = segs[s].status == 0 ? segs[s].len : 0;
+    const uint32_t n16 = n / 16;           // src is 256-byte aligned, dst offsets are 16-byte aligned
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = s4[i];
+    for (uint32_t i = n16 * 16 + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int lepb200_device_available(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+size_t lepb200_model_bytes(void) { return MODEL_BYTES; }
+
+int lepb200_create(lepb200_ctx** out, int device) {
+    if (!out) return LEPB200_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return LEPB200_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return LEPB200_ERR_INVALID;
+    lepb200_ctx* ctx = new lepb200_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LEPB200_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return LEPB200_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return LEPB200_ERR_CUDA;
+    }
+    *out = ctx;
+    return LEPB200_OK;
+}
+
+void lepb200_destroy(lepb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->d_planes, &ctx->d_streams, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
+        b->release();
+    for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage}) b->release();
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* lepb200_last_error(const lepb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+float lepb200_last_kernel_ms(lepb200_ctx* ctx) { return ctx ? ctx->last_ms : -1.f; }
+uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx) { return ctx ? ctx->alg_bytes : 0; }
+
+void* lepb200_pinned_alloc(size_t bytes) {
+    void* p = nullptr;
+    return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr;
+}
+void lepb200_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------ encode
+int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages) {
+    if (!ctx) return LEPB200_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int r = build_batch(ctx, images, nimages, true, nullptr);
+    if (r) return r;
+    for (int i = 0; i < nimages; ++i)
+        for (int c = 0; c < images[i].ncmp; ++c)
+            CK(cudaMemcpyAsync(reinterpret_cast<void*>(ctx->images[i].plane[c]), images[i].planes[c], ctx->plane_bytes[(size_t)i * 3 + c],
+                               cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_batch = true;
+    return LEPB200_OK;
+}
+
+int lepb200_encode_launch(lepb200_ctx* ctx) {
+    if (!ctx || !ctx->have_batch || !ctx->is_encode) { if (ctx) ctx->err = "encode_launch without encode_upload"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size();
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    lep_encode_kernel<<<ctx->grid, ENC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
+        static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
+        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    ctx->launched = true;
+    return LEPB200_OK;
+}
+
+int lepb200_encode_fetch(lepb200_ctx* ctx, lepb200_stream* out) {
+    if (!ctx || !ctx->launched || !ctx->is_encode || !out) { if (ctx) ctx->err = "encode_fetch without encode_launch"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size();
+    CK(ctx->h_segs.reserve(sizeof(SegDesc) * nseg + sizeof(unsigned long long) * nseg));
+    SegDesc* hs = static_cast<SegDesc*>(ctx->h_segs.p);
+    CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    // dense layout of the produced streams
+    unsigned long long* offs = reinterpret_cast<unsigned long long*>(hs + nseg);
+    size_t total = 0;
+    uint64_t alg = 0;
+    for (int s = 0; s < nseg; ++s) {
+        offs[s] = total;
+        size_t n = hs[s].status == 0 ? hs[s].len : 0;
+        total += align_up(n, 16);
+        alg += (uint64_t)ctx->seg_blocks[s] * 128 + n;
+    }
+    ctx->alg_bytes = alg;
+    const size_t dense_bytes = align_up(total, 256);
+    CK(ctx->d_dense.reserve(dense_bytes + sizeof(unsigned long long) * nseg));
+    CK(ctx->h_dense.reserve(total + 16));
+    unsigned long long* d_offs = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_dense.p) + dense_bytes);
+    CK(cudaMemcpyAsync(d_offs, offs, sizeof(unsigned long long) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+    lep_compact_kernel<<<nseg, 256, 0, ctx->stream>>>(static_cast<const SegDesc*>(ctx->d_segs.p), d_offs, static_cast<uint8_t*>(ctx->d_dense.p), nseg);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    if (total) CK(cudaMemcpyAsync(ctx->h_dense.p, ctx->d_dense.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < nseg; ++s) {
+        out[s].data = static_cast<const uint8_t*>(ctx->h_dense.p) + offs[s];
+        out[s].len = hs[s].status == 0 ? hs[s].len : 0;
+        out[s].status = hs[s].status;
+        out[s].reserved = 0;
+        out[s].ndecisions = (uint64_t)hs[s].ndecisions_lo | ((uint64_t)hs[s].ndecisions_hi << 32);
+    }
+    return LEPB200_OK;
+}
+
+int lepb200_encode_images(lepb200_ctx* ctx, const lepb200_image* images, int nimages, lepb200_stream* out) {
+    int r = lepb200_encode_upload(ctx, images, nimages);
+    if (r) return r;
+    r = lepb200_encode_launch(ctx);
+    if (r) return r;
+    return lepb200_encode_fetch(ctx, out);
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in) {
+    if (!ctx || !in) return LEPB200_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int r = build_batch(ctx, images, nimages, false, in);
+    if (r) return r;
+    const int nseg = (int)ctx->segs.size();
+    // pack the streams into one pinned staging buffer -> one H2D copy
+    size_t total = 0;
+    for (int s = 0; s < nseg; ++s) total = std::max(total, (size_t)(ctx->segs[s].stream - (unsigned long long)(uintptr_t)ctx->d_streams.p) + in[s].len);
+    CK(ctx->h_stage.reserve(total + 16));
+    for (int s = 0; s < nseg; ++s)
+        if (in[s].len) memcpy(static_cast<uint8_t*>(ctx->h_stage.p) + (ctx->segs[s].stream - (unsigned long long)(uintptr_t)ctx->d_streams.p), in[s].data, in[s].len);
+    if (total) CK(cudaMemcpyAsync(ctx->d_streams.p, ctx->h_stage.p, total, cudaMemcpyHostToDevice, ctx->stream));
+    // planes start zeroed: blocks outside the coded range (truncated images) stay zero like the reference's calloc
+    size_t plane_total = 0;
+    for (int i = 0; i < nimages; ++i)
+        for (int c = 0; c < images[i].ncmp; ++c) plane_total = std::max(plane_total, (size_t)(ctx->images[i].plane[c] - (unsigned long long)(uintptr_t)ctx->d_planes.p) + ctx->plane_bytes[(size_t)i * 3 + c]);
+    CK(cudaMemsetAsync(ctx->d_planes.p, 0, plane_total, ctx->stream));
+    ctx->have_batch = true;
+    return LEPB200_OK;
+}
+
+int lepb200_decode_launch(lepb200_ctx* ctx) {
+    if (!ctx || !ctx->have_batch || ctx->is_encode) { if (ctx) ctx->err = "decode_launch without decode_upload"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size();
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
+        static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
+        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    ctx->launched = true;
+    return LEPB200_OK;
+}
+
+int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, int32_t* status_out) {
+    if (!ctx || !ctx->launched || ctx->is_encode) { if (ctx) ctx->err = "decode_fetch without decode_launch"; return LEPB200_ERR_INVALID; }
+    if (nimages != (int)ctx->images.size()) { ctx->err = "decode_fetch: batch size mismatch"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size();
+    CK(ctx->h_segs.reserve(sizeof(SegDesc) * nseg));
+    SegDesc* hs = static_cast<SegDesc*>(ctx->h_segs.p);
+    CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int i = 0; i < nimages; ++i)
+        for (int c = 0; c < images[i].ncmp; ++c)
+            CK(cudaMemcpyAsync(images[i].planes[c], reinterpret_cast<const void*>(ctx->images[i].plane[c]), ctx->plane_bytes[(size_t)i * 3 + c],
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    uint64_t alg = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (status_out) status_out[s] = hs[s].status;
+        alg += (uint64_t)ctx->seg_blocks[s] * 128 + ctx->segs[s].cap;
+    }
+    ctx->alg_bytes = alg;
+    return LEPB200_OK;
+}
+
+int lepb200_decode_images(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in, int32_t* status_out) {
+    int r = lepb200_decode_upload(ctx, images, nimages, in);
+    if (r) return r;
+    r = lepb200_decode_launch(ctx);
+    if (r) return r;
+    return lepb200_decode_fetch(ctx, images, nimages, status_out);
+}
+
+}  // extern "C"

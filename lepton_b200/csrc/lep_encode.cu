@@ -1,0 +1,411 @@
+// lep_encode.cu -- sm_100a encode kernel: coefficient planes -> per-segment VP8 bool-coder streams.
+//
+// Work decomposition (new; the reference runs one CPU thread per segment, src/lepton/vp8_encoder.cc:239-445):
+//   * persistent grid, one WARP per Lepton thread-segment, segments pulled from a global work queue
+//     (largest first), the warp's 1.5 MB probability model zero-filled by the warp itself;
+//   * per 8x8 block the warp works in three phases
+//       1. lane-parallel SYMBOLISATION: each lane owns two coefficients (one 32-bit word of the 128-byte
+//          AlignedBlock), computes their neighbour priors / context bins and appends their binary
+//          decisions (model index, bit) to a shared-memory queue at a prefix-sum offset.  Nothing in the
+//          encoder's context computation depends on coder state (hard part 1);
+//       2. batched MODEL UPDATE: 32 queued decisions at a time, one per lane -- parallel 16-bit loads of
+//          the adaptive counts, same-address conflicts resolved in queue order with __match_any_sync,
+//          probabilities computed per lane, counts written back;
+//       3. the RANGE CODER chain (vpx_write, src/vp8/encoder/boolwriter.hh:48-118) runs warp-uniform over
+//          the 32 (probability, bit) pairs broadcast by shuffle; bytes leave through lane 0.
+//
+// Bit-exactness notes follow the oracle (oracle/lepton_oracle.c), which is pinned against the reference.
+#include "lep_common.cuh"
+#include "lep_predict.cuh"
+
+namespace lepb200 {
+
+constexpr int ENC_WARPS_PER_CTA = 4;
+constexpr int QCAP = 1472;   // worst case decisions per block: 6 + 49*22 + 2*(3 + 7*22) + 22 = 1420
+
+struct EncWarpSmem {
+    uint32_t queue[QCAP];     // (bit << 31) | model index
+    int16_t rast[3][64];      // raster-order copies: [0]=cur/left ping, [1]=left/cur pong, [2]=above
+    int32_t tmp[64];          // IDCT intermediate
+    int16_t pix[64];          // IDCT output (pixels sans DC)
+};
+
+struct EncShared {
+    uint32_t rcp[512];
+    EncWarpSmem w[ENC_WARPS_PER_CTA];
+};
+
+// ---- bool writer state (warp-uniform) ------------------------------------------------------------
+struct BoolWriter {
+    uint32_t low, range;
+    int count;
+    uint32_t pos, cap;
+    uint8_t* buf;
+    bool overflow;
+};
+
+// vpx_write (boolwriter.hh:48-118). All lanes run it with identical state; lane 0 touches memory.
+__device__ __forceinline__ void bw_put(BoolWriter& w, uint32_t bit, uint32_t prob, int lane) {
+    uint32_t split = 1 + (((w.range - 1) * prob) >> 8);
+    uint32_t range = bit ? w.range - split : split;
+    uint32_t low = w.low + (bit ? split : 0);
+    int shift = __clz(range) - 24;
+    range <<= shift;
+    int count = w.count + shift;
+    if (count >= 0) {
+        int offset = shift - count;
+        if (lane == 0) {
+            if ((low << (offset - 1)) & 0x80000000u) {      // carry: walk back over 0xff bytes (boolwriter.hh:96-105)
+                int x = (int)w.pos - 1;
+                while (x >= 0 && w.buf[x] == 0xff) { w.buf[x] = 0; --x; }
+                if (x >= 0) w.buf[x] += 1;
+            }
+            if (w.pos < w.cap) w.buf[w.pos] = (uint8_t)(low >> (24 - offset));
+        }
+        if (w.pos >= w.cap) w.overflow = true;
+        w.pos++;
+        low = (low << offset) & 0xffffff;
+        shift = count;
+        count -= 8;
+    }
+    w.low = low << shift;
+    w.count = count;
+    w.range = range;
+}
+
+// ---- queue flush: batched model update + range-coder chain ------------------------------------------
+__device__ __forceinline__ void flush_queue(const uint32_t* __restrict__ queue, int n, uint16_t* __restrict__ model,
+                                            const uint32_t* __restrict__ s_rcp, BoolWriter& bw, int lane) {
+    const uint32_t lt_mask = (1u << lane) - 1;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        bool active = i < n;
+        uint32_t e = active ? queue[i] : 0;
+        uint32_t addr = e & 0xfffffu, bit = e >> 31;
+        uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
+        int rank = __popc(peers & lt_mask);
+        int npeers = __popc(peers);
+        uint32_t w = active ? (uint32_t)model[addr] : 0u;
+        int maxrank = __reduce_max_sync(FULL, npeers - 1);
+        // apply, in queue order, the updates of earlier decisions that hit the same branch
+        for (int r = 0; r < maxrank; ++r) {
+            int src = (r < npeers) ? (int)__fns(peers, 0, r + 1) : lane;   // lane holding the r-th earlier decision
+            uint32_t sbit = __shfl_sync(FULL, bit, src);
+            if (rank > r) w = branch_update(w, sbit);
+        }
+        uint32_t prob = branch_prob(w, s_rcp);
+        if (active && rank == npeers - 1) model[addr] = (uint16_t)branch_update(w, bit);
+        int cnt = min(32, n - base);
+        for (int j = 0; j < cnt; ++j) {
+            uint32_t p = __shfl_sync(FULL, prob, j);
+            uint32_t b = __shfl_sync(FULL, bit, j);
+            bw_put(bw, b, p, lane);
+        }
+    }
+    __syncwarp();
+}
+
+// ---- helpers for symbolisation ------------------------------------------------------------------------
+// number of queue entries for one coefficient coded with (exponent unary, sign, len-1 residual bits)
+__device__ __forceinline__ int coef_entries(int len) { return len == 0 ? 1 : min(len + 1, 11) + len; }
+
+// ---- the kernel ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
+lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
+                  int* __restrict__ work_counter, uint16_t* __restrict__ model_pool, uint8_t* __restrict__ row_pool,
+                  size_t row_pool_stride) {
+    __shared__ EncShared sm;
+    const int lane = lane_id();
+    const int warp_in_cta = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * ENC_WARPS_PER_CTA + warp_in_cta;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sm.rcp[i] = i < 2 ? 0u : (uint32_t)((0x100000000ull + i - 1) / i);
+    __syncthreads();
+    EncWarpSmem& ws = sm.w[warp_in_cta];
+    uint16_t* model = model_pool + (size_t)gwarp * M_TOTAL;
+    uint8_t* rowbuf = row_pool + (size_t)gwarp * row_pool_stride;
+    const uint32_t lt_mask = (1u << lane) - 1;
+
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(work_counter, 1);
+        job = __shfl_sync(FULL, job, 0);
+        if (job >= nseg) break;
+        const int sidx = order[job];
+        SegDesc& sd = segs[sidx];
+        const ImageDesc& g = images[sd.image];
+        if (sd.status != ST_OK) continue;          // rejected on the host (e.g. zero quantiser, model.hh:257-262)
+
+        // reset the model to the identity prior: zero fill (16-byte stores, coalesced)
+        {
+            uint4* m4 = reinterpret_cast<uint4*>(model);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = lane; i < M_TOTAL / 8; i += 32) m4[i] = z;
+        }
+        __syncwarp();
+
+        BoolWriter bw;
+        bw.low = 0; bw.range = 255; bw.count = -24; bw.pos = 0; bw.cap = sd.cap; bw.buf = reinterpret_cast<uint8_t*>(sd.stream); bw.overflow = false;
+        bw_put(bw, 0, 128, lane);                                    // vpx_start_encode marker bit (boolwriter.cc:17-24)
+
+        // per-component row buffers: bottom-edge prediction (8 x int16) and 7x7 nonzero count of the row above
+        int16_t* row_edge[3]; uint8_t* row_nz[3];
+        {
+            size_t off = 0;
+            for (int c = 0; c < 3; ++c) {
+                int w = c < g.ncmp ? g.bch[c] : 0;
+                row_edge[c] = reinterpret_cast<int16_t*>(rowbuf + off); off += (size_t)w * 16;
+            }
+            for (int c = 0; c < 3; ++c) {
+                int w = c < g.ncmp ? g.bch[c] : 0;
+                row_nz[c] = rowbuf + off; off += (size_t)((w + 15) & ~15);
+            }
+        }
+
+        int status = ST_OK;
+        unsigned long long ndec = 0;
+        bool top[3] = {true, true, true};
+        uint32_t index = 0;
+        for (;;) {
+            RowSpec rs = row_spec_from_index(index++, g);
+            if (rs.done) break;
+            if (rs.luma_y >= sd.max_y && !sd.is_last) break;
+            if (rs.skip) continue;
+            if (rs.luma_y < sd.min_y) continue;
+            const int c = rs.component, y = rs.curr_y;
+            const bool has_above = !top[c];
+            top[c] = false;
+            const int ci = c == 0 ? 0 : 1;
+            const int w = g.bch[c];
+            const uint32_t* plane = reinterpret_cast<const uint32_t*>(g.plane[c]);
+            const uint32_t* rowp = plane + (size_t)y * w * 32;
+            const uint32_t* abovep = rowp - (size_t)w * 32;
+            const uint16_t* q = g.q[c];
+            const int q0 = q[0];
+            int16_t* redge = row_edge[c];
+            uint8_t* rnz = row_nz[c];
+
+            uint32_t cur = rowp[lane];
+            uint32_t abv = has_above ? abovep[lane] : 0u;
+            uint32_t left = 0, aleft = 0;
+            int left_v = 0;          // lanes 0..7: left block's right-column edge prediction
+            int nz_left = 0;
+            int pp = 0;              // ping-pong index of the raster copy of `cur`
+            for (int x = 0; x < w; ++x) {
+                const bool has_left = x > 0;
+                // prefetch the next block of this row and of the row above
+                uint32_t ncur = 0, nabv = 0;
+                if (x + 1 < w) { ncur = rowp[(size_t)(x + 1) * 32 + lane]; if (has_above) nabv = abovep[(size_t)(x + 1) * 32 + lane]; }
+
+                // ---------------- raster copies for the gathers (IDCT, Lakhani edge predictor)
+                {
+                    int r0 = c_aligned_to_raster[2 * lane], r1 = c_aligned_to_raster[2 * lane + 1];
+                    ws.rast[pp][r0] = (int16_t)h_lo(cur); ws.rast[pp][r1] = (int16_t)h_hi(cur);
+                    ws.rast[2][r0] = (int16_t)h_lo(abv); ws.rast[2][r1] = (int16_t)h_hi(abv);
+                }
+                __syncwarp();
+                const int16_t* rcur = ws.rast[pp];
+                const int16_t* rleft = ws.rast[pp ^ 1];
+                const int16_t* rabove = ws.rast[2];
+
+                int qn = 0;   // queue length (warp-uniform)
+                // ---------------- (i) number of non-zeros in the 7x7 block (aligned_block.hh:132-148), context model.hh:463-485
+                const int c0v = h_lo(cur), c1v = h_hi(cur);
+                const bool in0 = 2 * lane < 49, in1 = 2 * lane + 1 < 49;
+                const bool e0 = in0 && c0v != 0, e1 = in1 && c1v != 0;
+                const uint32_t m0 = __ballot_sync(FULL, e0), m1 = __ballot_sync(FULL, e1);
+                const int nz = __popc(m0) + __popc(m1);
+                const int nz_above = has_above ? (int)rnz[x] : 0;
+                {
+                    int ctx = 0;
+                    if (has_above && !has_left) ctx = (nz_above + 1) / 2;
+                    else if (has_left && !has_above) ctx = (nz_left + 1) / 2;
+                    else if (has_left && has_above) ctx = (nz_above + nz_left + 2) / 4;
+                    int bin = c_nonzero_to_bin[ctx];
+                    if (lane < 6) {
+                        int idx = 5 - lane;                               // bit index, MSB first
+                        int prefix = nz >> (idx + 1);
+                        ws.queue[lane] = m_nz7(ci, bin, idx, prefix) | ((uint32_t)((nz >> idx) & 1) << 31);
+                    }
+                    qn = 6;
+                }
+                // ---------------- (ii) 7x7 coefficients in zig-zag (== aligned) order (encoder.cc:219-285)
+                int eobx = 0, eoby = 0;
+                {
+                    const int before0 = __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
+                    const int before1 = before0 + (e0 ? 1 : 0);
+                    const bool coded0 = in0 && before0 < nz, coded1 = in1 && before1 < nz;
+                    const int a0 = iabs(c0v), a1 = iabs(c1v);
+                    const int len0 = bitlen(a0 & 0xffff), len1 = bitlen(a1 & 0xffff);
+                    if ((coded0 && len0 > 11) || (coded1 && len1 > 11)) status = ST_COEF_RANGE;
+                    int cnt0 = coded0 ? coef_entries(min(len0, 11)) : 0;
+                    int cnt1 = coded1 ? coef_entries(min(len1, 11)) : 0;
+                    int total;
+                    int off = qn + warp_excl_scan(cnt0 + cnt1, lane, total);
+                    // priors
+                    const int pr0 = aavrg16(h_lo(left), h_lo(abv), h_lo(aleft), has_left, has_above);
+                    const int pr1 = aavrg16(h_hi(left), h_hi(abv), h_hi(aleft), has_left, has_above);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const bool coded = h ? coded1 : coded0;
+                        if (coded) {
+                            const int zz = 2 * lane + h;
+                            const int v = h ? c1v : c0v, av = h ? a1 : a0, len = min(h ? len1 : len0, 11);
+                            const int prior = h ? pr1 : pr0;
+                            const int left_nz = nz - (h ? before1 : before0);
+                            const int bin = c_nonzero_to_bin[left_nz];
+                            const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
+                            const int coord = c_aligned_to_raster[zz];
+                            uint32_t ea = m_exp7(ci, bin, zz, bsr);
+                            int o = off;
+                            const int nexp = min(len + 1, 11);
+                            for (int i = 0; i < nexp; ++i) ws.queue[o++] = (ea + i) | ((uint32_t)(len != i) << 31);
+                            if (len) {
+                                ws.queue[o++] = m_sign(ci, 0, 0) | ((uint32_t)(v >= 0) << 31);
+                                uint32_t ra = m_resn(ci, coord, bin);
+                                for (int i = len - 2; i >= 0; --i) ws.queue[o++] = (ra + i) | ((uint32_t)((av >> i) & 1) << 31);
+                            }
+                            off = o;
+                        }
+                    }
+                    // a lane's two coefficients: keep the max of both for eob
+                    {
+                        int ex = 0, ey = 0;
+                        if (e0) { int co = c_aligned_to_raster[2 * lane]; ex = co & 7; ey = co >> 3; }
+                        if (e1) { int co = c_aligned_to_raster[2 * lane + 1]; ex = max(ex, co & 7); ey = max(ey, co >> 3); }
+                        eobx = __reduce_max_sync(FULL, ex);
+                        eoby = __reduce_max_sync(FULL, ey);
+                    }
+                    qn += total;
+                }
+                // ---------------- (iii) edges: horizontal (raster 1..7) then vertical (raster 8..56) (encoder.cc:39-184)
+                {
+                    // lanes 0..6: horizontal coefficient k = lane+1; lanes 8..14: vertical coefficient k = lane-7;
+                    // lane 7 carries the vertical count bits, the horizontal count bits sit in front of lane 0.
+                    const bool is_h = lane < 7, is_v = lane >= 8 && lane < 15;
+                    const int k = is_h ? lane + 1 : lane - 7;
+                    const int coord = is_h ? k : 8 * k;
+                    int v = 0;
+                    if (is_h || is_v) v = rcur[coord];
+                    const uint32_t nzmask = __ballot_sync(FULL, v != 0);
+                    const uint32_t hm = nzmask & 0x7f, vm = (nzmask >> 8) & 0x7f;
+                    const int ne_h = __popc(hm), ne_v = __popc(vm);
+                    int prior = 0;
+                    if (is_h && has_above) prior = lak_pred(rcur, rabove, g.icos_x[c] + k * 8, k, 8);
+                    if (is_v && has_left) prior = lak_pred(rcur, rleft, g.icos_y[c] + k * 8, 8 * k, 1);
+                    const int ne_rem = is_h ? ne_h - __popc(hm & lt_mask) : ne_v - __popc(vm & ((lt_mask >> 8) & 0x7f));
+                    const bool coded = (is_h || is_v) && ne_rem > 0;
+                    const int av = iabs(v) & 0xffff;
+                    const int len_raw = bitlen(av);
+                    if (coded && len_raw > 11) status = ST_COEF_RANGE;
+                    const int len = min(len_raw, 11);
+                    int cnt = coded ? coef_entries(len) : 0;
+                    if (lane == 7) cnt = 3;
+                    int total;
+                    int off = qn + 3 + warp_excl_scan(cnt, lane, total);
+                    if (lane == 15 || lane == 7) {
+                        const bool vert = lane == 7;
+                        const int ne = vert ? ne_v : ne_h;
+                        const int eob = vert ? eoby : eobx;
+                        int o = vert ? off : qn;
+                        for (int i = 2; i >= 0; --i)
+                            ws.queue[o++] = m_nze(vert, ci, eob, (nz + 3) / 7, i, ne >> (i + 1)) | ((uint32_t)((ne >> i) & 1) << 31);
+                    }
+                    if (coded) {
+                        const int zig15 = is_h ? k - 1 : 6 + k;
+                        const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
+                        uint32_t ea = m_expx(ci, ne_rem, zig15, bsr);
+                        int o = off;
+                        const int nexp = min(len + 1, 11);
+                        for (int i = 0; i < nexp; ++i) ws.queue[o++] = (ea + i) | ((uint32_t)(len != i) << 31);
+                        if (len) {
+                            const int p16 = (int)(int16_t)prior;                       // sign_array_8: int16 truncation (model.hh:1116)
+                            const int sctx = p16 == 0 ? 0 : (p16 > 0 ? 1 : 2);
+                            ws.queue[o++] = m_sign(ci, sctx, bsr) | ((uint32_t)(v >= 0) << 31);
+                            if (len > 1) {
+                                const int min_thr = g.min_thr[c][coord];
+                                int i = len - 2;
+                                if (i >= min_thr) {
+                                    const int ctx_abs = iabs(prior) & 0xffff;          // uint16_t ctx_abs (model.hh:1079)
+                                    uint32_t ta = m_thr(ci, min(ctx_abs >> min_thr, 255), min(len - min_thr, 7));
+                                    uint32_t so = 1;
+                                    for (; i >= min_thr; --i) {
+                                        uint32_t b = (av >> i) & 1;
+                                        ws.queue[o++] = (ta + so) | (b << 31);
+                                        so = min((so << 1) | b, 127u);
+                                    }
+                                }
+                                uint32_t ra = m_resn(ci, coord, ne_rem);
+                                for (; i >= 0; --i) ws.queue[o++] = (ra + i) | ((uint32_t)((av >> i) & 1) << 31);
+                            }
+                        }
+                    }
+                    qn += 3 + total;
+                }
+                // ---------------- (iv) DC (encoder.cc:293-364)
+                warp_idct_sans_dc(rcur, q, ws.tmp, ws.pix, lane);
+                const int dc = h_hi(__shfl_sync(FULL, cur, 24));          // aligned index 49
+                int above_h = 0;
+                if (has_above && lane >= 8 && lane < 16) above_h = redge[(size_t)x * 8 + (lane - 8)];
+                DcPred dp = warp_predict_dc(ws.pix, left_v, above_h, has_left, has_above, q0, lane);
+                {
+                    const int adv = adv_unpredict(dc, false, dp.pred);
+                    if (dc != adv_unpredict((int)(int16_t)adv, true, dp.pred)) status = ST_COEF_RANGE;
+                    const int v = (int)(int16_t)adv, av = iabs(v) & 0xffff, len = min(bitlen(av), 11);
+                    const int lm = min(bitlen((uint32_t)iabs(dp.unc) & 0xffff), 11), lo = min(bitlen((uint32_t)iabs(dp.unc2) & 0xffff), 16);
+                    const int nexp = min(len + 1, 11);
+                    const int n = coef_entries(len);
+                    if (lane < n) {
+                        uint32_t e;
+                        if (lane < nexp) e = (m_expdc(lm, lo) + lane) | ((uint32_t)(len != lane) << 31);
+                        else if (lane == nexp) {
+                            const int sctx = dp.unc2 >= 0 ? (dp.unc2 == 0 ? 3 : 2) : 1;
+                            e = m_sign(ci, 0, sctx) | ((uint32_t)(v >= 0) << 31);
+                        } else {
+                            const int i = len - 2 - (lane - nexp - 1);
+                            e = (m_resdc(lm) + i) | ((uint32_t)((av >> i) & 1) << 31);
+                        }
+                        ws.queue[qn + lane] = e;
+                    }
+                    qn += n;
+                }
+                __syncwarp();
+                // ---------------- (v) neighbour summary of this block (block_context.hh:44-78)
+                const int edge = edge_pixel(ws.pix, q0, dc, lane);
+                if (lane >= 8 && lane < 16) redge[(size_t)x * 8 + (lane - 8)] = (int16_t)edge;
+                if (lane == 0) rnz[x] = (uint8_t)nz;
+                left_v = edge;            // lanes 0..7
+                nz_left = nz;
+
+                // ---------------- code the queued decisions
+                status = __reduce_max_sync(FULL, status);
+                if (status != ST_OK) break;
+                flush_queue(ws.queue, qn, model, sm.rcp, bw, lane);
+                ndec += (unsigned long long)qn;
+
+                // early-out on truncated images (vp8_encoder.cc:110-113,133-135): not after the right-most block
+                if (x + 1 < w && (uint32_t)((size_t)y * w + x + 1) >= (uint32_t)g.trunc_bc[c]) break;
+
+                aleft = abv; left = cur; cur = ncur; abv = nabv; pp ^= 1;
+            }
+            if (status != ST_OK) break;
+        }
+        if (status == ST_OK) {
+            for (int i = 0; i < 32; ++i) bw_put(bw, 0, 128, lane);                      // vpx_stop_encode (boolwriter.cc:26-35)
+            if (lane == 0 && bw.pos > 0 && bw.pos < bw.cap && (bw.buf[bw.pos - 1] & 0xe0) == 0xc0) bw.buf[bw.pos] = 0;
+            uint32_t last = 0;
+            if (lane == 0 && bw.pos > 0 && bw.pos <= bw.cap) last = bw.buf[bw.pos - 1];
+            last = __shfl_sync(FULL, last, 0);
+            if ((last & 0xe0) == 0xc0) bw.pos++;
+            if (bw.overflow || bw.pos > bw.cap) status = ST_OUT_OVERFLOW;
+        }
+        if (lane == 0) {
+            sd.len = bw.pos;
+            sd.status = status;
+            sd.ndecisions_lo = (uint32_t)ndec;
+            sd.ndecisions_hi = (uint32_t)(ndec >> 32);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace lepb200

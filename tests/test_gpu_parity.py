@@ -1,0 +1,123 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI, against the pinned oracle and the reference's own
+.lep files.  Bit-exact (integer / byte work): streams must be identical, decoded planes identical."""
+import numpy as np
+import pytest
+
+import lepfmt
+from helpers import (coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image,
+                     random_coef_image)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    from lepton_b200 import LeptonB200Codec
+    c = LeptonB200Codec(0)
+    yield c
+    c.close()
+
+
+def test_golden_batch_encode_matches_reference_streams(codec):
+    """All committed reference-written .lep files in ONE batch: GPU streams == the reference's streams."""
+    imgs, want = [], []
+    for name in golden_leps():
+        lf = load_lep(name)
+        planes, streams = oracle_decode_planes(lf)
+        imgs.append(coef_image_from_lep(lf, planes))
+        want.append(streams[:lf.nseg])
+    got = codec.encode_images(imgs)
+    for name, g, w in zip(golden_leps(), got, want):
+        for i, (seg, ref) in enumerate(zip(g, w)):
+            assert seg.status == 0, (name, i, seg.status)
+            assert seg.data == ref, "%s segment %d differs from the reference stream" % (name, i)
+
+
+def test_golden_batch_decode_matches_reference_planes(codec):
+    imgs, streams_all, want = [], [], []
+    for name in golden_leps():
+        lf = load_lep(name)
+        planes, streams = oracle_decode_planes(lf)
+        img = coef_image_from_lep(lf, [np.full_like(p, 77) for p in planes])
+        imgs.append(img)
+        streams_all.append(streams[:lf.nseg])
+        want.append((lf, planes))
+    st = codec.decode_images(imgs, streams_all)
+    assert all(s == 0 for s in st), st
+    for name, img, (lf, planes) in zip(golden_leps(), imgs, want):
+        for c in range(img.ncmp):
+            assert np.array_equal(img.planes[c], planes[c]), "%s component %d" % (name, c)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(ncmp=3, mcuh=5, mcuv=4, sf=((2, 2), (1, 1), (1, 1)), nseg=1),
+    dict(ncmp=3, mcuh=7, mcuv=6, sf=((2, 2), (1, 1), (1, 1)), nseg=3),
+    dict(ncmp=3, mcuh=9, mcuv=5, sf=((1, 1), (1, 1), (1, 1)), nseg=2),
+    dict(ncmp=3, mcuh=6, mcuv=4, sf=((2, 1), (1, 1), (1, 1)), nseg=2),
+    dict(ncmp=1, mcuh=11, mcuv=7, sf=((1, 1),), nseg=4),
+    dict(ncmp=1, mcuh=1, mcuv=1, sf=((1, 1),), nseg=1),        # single block
+    dict(ncmp=1, mcuh=1, mcuv=9, sf=((1, 1),), nseg=2),        # one block wide (width_one model)
+    dict(ncmp=3, mcuh=1, mcuv=3, sf=((2, 2), (1, 1), (1, 1)), nseg=1),
+    dict(ncmp=3, mcuh=12, mcuv=8, sf=((2, 2), (1, 1), (1, 1)), nseg=8, density=0.9, amp=100, qscale=0.3),   # dense, large coefficients
+    dict(ncmp=3, mcuh=8, mcuv=8, sf=((2, 2), (1, 1), (1, 1)), nseg=1, density=0.0, amp=1),     # (almost) empty blocks
+])
+def test_random_planes_encode_decode_vs_oracle(codec, cfg):
+    rng = np.random.default_rng(1234)
+    img = random_coef_image(rng, **cfg)
+    ref = oracle_encode_image(img)
+    got = codec.encode_images([img])[0]
+    assert len(got) == len(ref)
+    for i, (g, (rc, s, nd)) in enumerate(zip(got, ref)):
+        assert g.status == rc == 0
+        assert g.data == s, "segment %d" % i
+        assert g.ndecisions == nd
+    # decode what we encoded
+    from lepton_b200 import CoefImage
+    out = CoefImage(ncmp=img.ncmp, mcuv=img.mcuv, bch=img.bch, bcv=img.bcv, qtables_zigzag=img.qtables_zigzag,
+                    planes=[np.full_like(p, -5) for p in img.planes], luma_y_start=img.luma_y_start)
+    st = codec.decode_images([out], [[g.data for g in got]])
+    assert all(s == 0 for s in st)
+    for c in range(img.ncmp):
+        assert np.array_equal(out.planes[c], img.planes[c])
+
+
+def test_out_of_range_coefficient_status(codec):
+    """COEFFICIENT_OUT_OF_RANGE (reference exit code 6, src/vp8/encoder/encoder.cc:124,265,343)."""
+    rng = np.random.default_rng(5)
+    img = random_coef_image(rng, ncmp=1, mcuh=4, mcuv=4, sf=((1, 1),), nseg=2)
+    img.planes[0][3, 7] = 4096          # 13-bit magnitude in the first segment only
+    ref = oracle_encode_image(img)
+    got = codec.encode_images([img])[0]
+    assert [g.status for g in got] == [r[0] for r in ref] == [6, 0]
+    assert got[1].data == ref[1][1]
+
+
+def test_branch_saturation_long_run(codec):
+    """Long constant runs drive branch counts through the 255 overflow / 'neverseen' paths (branch.hh:82-100)."""
+    from lepton_b200 import CoefImage
+    n = 40 * 40
+    p = np.zeros((n, 64), dtype=np.int16)
+    p[:, 0] = 1
+    p[::7, 1] = -3
+    p[:, 49] = 5
+    img = CoefImage(ncmp=1, mcuv=40, bch=[40], bcv=[40], qtables_zigzag=[[8] * 64], planes=[p], luma_y_start=[0])
+    (rc, s, nd), = oracle_encode_image(img)
+    got = codec.encode_images([img])[0][0]
+    assert rc == 0 and got.status == 0 and got.data == s and got.ndecisions == nd
+    out = CoefImage(ncmp=1, mcuv=40, bch=[40], bcv=[40], qtables_zigzag=[[8] * 64], planes=[np.zeros_like(p)], luma_y_start=[0])
+    assert codec.decode_images([out], [[got.data]]) == [0]
+    assert np.array_equal(out.planes[0], p)
+
+
+def test_mixed_batch_many_images(codec):
+    """A batch of different geometries in one launch: per-image results must not depend on batching."""
+    rng = np.random.default_rng(99)
+    imgs = []
+    for k in range(24):
+        ncmp = 1 if k % 5 == 0 else 3
+        sf = ((1, 1),) if ncmp == 1 else (((2, 2), (1, 1), (1, 1)) if k % 2 else ((1, 1), (1, 1), (1, 1)))
+        imgs.append(random_coef_image(rng, ncmp=ncmp, mcuh=2 + k % 7, mcuv=2 + (k * 3) % 5, sf=sf, nseg=1 + k % 3))
+    got = codec.encode_images(imgs)
+    for img, g in zip(imgs, got):
+        ref = oracle_encode_image(img)
+        assert [x.data for x in g] == [r[1] for r in ref]
