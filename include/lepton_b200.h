@@ -118,6 +118,39 @@ size_t lepb200_model_bytes(void);
 /* 1 if a CUDA device is usable from this process. */
 int lepb200_device_available(void);
 
+
+/* ------------------------------------------------------------------------------------------------------------
+ * File-level drop-in (host front/back end + GPU coder): what `lepton in.jpg out.lep` / `lepton in.lep out.jpg`
+ * do (src/lepton/jpgcoder.cc process_file :1528), batched over files.  Outputs are byte-identical to the
+ * reference CLI with default options.  status is a reference ExitCode (0 ok) or LEPB200_ST_NOT_HANDLED for
+ * inputs whose host-side handling this build does not cover yet (such files are refused, never mis-coded).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define LEPB200_ST_NOT_HANDLED 200
+
+typedef struct lepb200_codec lepb200_codec;
+typedef struct lepb200_buffer { const uint8_t* data; size_t len; } lepb200_buffer;
+typedef struct lepb200_result { const uint8_t* data; size_t len; int32_t status; } lepb200_result; /* data owned by the codec */
+
+int lepb200_codec_create(lepb200_codec** out, int device, int host_threads /* 0 = all cores */);
+void lepb200_codec_destroy(lepb200_codec* codec);
+const char* lepb200_codec_last_error(const lepb200_codec* codec);
+lepb200_ctx* lepb200_codec_ctx(lepb200_codec* codec);
+/* seconds spent by the last call in: JPEG parse + Huffman decode | H2D + kernel + D2H | container writing */
+void lepb200_codec_last_timing(const lepb200_codec* codec, double* front_s, double* gpu_s, double* back_s);
+/* n JPEG files in, n .lep files out */
+int lepb200_compress_jpegs(lepb200_codec* codec, const lepb200_buffer* jpegs, int n, lepb200_result* out);
+
+/* ---- the host stages on their own (no GPU): JPEG front end and .lep assembly around an external coder.
+ * lepb200_host_jpeg_open parses + Huffman-decodes one JPEG (read_jpeg + decode_jpeg, jpgcoder.cc:2270,2799) and
+ * selects the thread-segments (write_ujpg :3860-3934); *_image exposes planes/geometry/splits as a lepb200_image
+ * (pointers stay valid until *_close); *_write_lep assembles the container around nseg coded streams. */
+typedef struct lepb200_jpeg lepb200_jpeg;
+int lepb200_host_jpeg_open(const uint8_t* data, size_t len, lepb200_jpeg** out, int32_t* status);
+const char* lepb200_host_jpeg_error(const lepb200_jpeg* h);
+int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img);
+int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, int nseg, const uint8_t** data, size_t* len);
+void lepb200_host_jpeg_close(lepb200_jpeg* h);
+
 #ifdef __cplusplus
 }
 #endif

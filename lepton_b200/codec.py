@@ -54,7 +54,9 @@ _EXPORTS = [
     "lepb200_encode_images", "lepb200_decode_images", "lepb200_encode_upload", "lepb200_encode_launch",
     "lepb200_encode_fetch", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
-    "lepb200_device_available",
+    "lepb200_device_available", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
+    "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
+    "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
 ]
 
 
@@ -264,3 +266,150 @@ class LeptonB200Codec:
     @property
     def last_algorithmic_bytes(self) -> int:
         return int(self._L.lepb200_last_algorithmic_bytes(self._ctx))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# File-level drop-in: what the reference CLI does per file (`lepton in.jpg out.lep`), batched.
+# ---------------------------------------------------------------------------------------------------------
+class _Buffer(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("len", ctypes.c_size_t)]
+
+
+class _Result(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("len", ctypes.c_size_t), ("status", ctypes.c_int32)]
+
+
+def _bind_file_api(L):
+    if getattr(L, "_file_api_bound", False):
+        return
+    vp = ctypes.c_void_p
+    L.lepb200_codec_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int]
+    L.lepb200_codec_create.restype = ctypes.c_int
+    L.lepb200_codec_destroy.argtypes = [vp]
+    L.lepb200_codec_destroy.restype = None
+    L.lepb200_codec_last_error.argtypes = [vp]
+    L.lepb200_codec_last_error.restype = ctypes.c_char_p
+    L.lepb200_codec_ctx.argtypes = [vp]
+    L.lepb200_codec_ctx.restype = vp
+    L.lepb200_codec_last_timing.argtypes = [vp] + [ctypes.POINTER(ctypes.c_double)] * 3
+    L.lepb200_codec_last_timing.restype = None
+    L.lepb200_compress_jpegs.argtypes = [vp, ctypes.POINTER(_Buffer), ctypes.c_int, ctypes.POINTER(_Result)]
+    L.lepb200_compress_jpegs.restype = ctypes.c_int
+    L.lepb200_host_jpeg_open.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
+    L.lepb200_host_jpeg_open.restype = ctypes.c_int
+    L.lepb200_host_jpeg_error.argtypes = [vp]
+    L.lepb200_host_jpeg_error.restype = ctypes.c_char_p
+    L.lepb200_host_jpeg_image.argtypes = [vp, ctypes.POINTER(_Image)]
+    L.lepb200_host_jpeg_image.restype = ctypes.c_int
+    L.lepb200_host_jpeg_write_lep.argtypes = [vp, ctypes.POINTER(_Stream), ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.lepb200_host_jpeg_write_lep.restype = ctypes.c_int
+    L.lepb200_host_jpeg_close.argtypes = [vp]
+    L.lepb200_host_jpeg_close.restype = None
+    L._file_api_bound = True
+
+
+class HostJpeg:
+    """Host stages only (no GPU): parse + Huffman-decode a JPEG, expose it as a CoefImage, assemble a .lep."""
+
+    def __init__(self, data: bytes):
+        self._L = lib()
+        _bind_file_api(self._L)
+        self._h = ctypes.c_void_p()
+        st = ctypes.c_int32()
+        self._data = data
+        self._L.lepb200_host_jpeg_open(data, len(data), ctypes.byref(self._h), ctypes.byref(st))
+        self.status = st.value
+        self.error = self._L.lepb200_host_jpeg_error(self._h).decode()
+
+    def close(self):
+        if self._h:
+            self._L.lepb200_host_jpeg_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def coef_image(self) -> CoefImage:
+        if self.status:
+            raise LeptonB200Error("JPEG front end refused the file: status %d (%s)" % (self.status, self.error))
+        im = _Image()
+        if self._L.lepb200_host_jpeg_image(self._h, ctypes.byref(im)) != 0:
+            raise LeptonB200Error("host_jpeg_image failed")
+        planes = []
+        for c in range(im.ncmp):
+            n = im.bch[c] * im.bcv[c]
+            arr = np.ctypeslib.as_array(ctypes.cast(im.planes[c], ctypes.POINTER(ctypes.c_int16)), shape=(n, 64))
+            planes.append(arr)          # view into memory owned by this HostJpeg
+        return CoefImage(ncmp=im.ncmp, mcuv=im.mcuv, bch=[im.bch[c] for c in range(im.ncmp)],
+                         bcv=[im.bcv[c] for c in range(im.ncmp)],
+                         qtables_zigzag=[[im.qtable_zigzag[c][i] for i in range(64)] for c in range(im.ncmp)],
+                         planes=planes, luma_y_start=[im.luma_y_start[s] for s in range(im.nseg)],
+                         jpeg_bytes=len(self._data), _keep=[self])
+
+    def write_lep(self, streams: Sequence[bytes]) -> bytes:
+        arr = (_Stream * len(streams))()
+        keep = []
+        for i, s in enumerate(streams):
+            b = np.frombuffer(s, dtype=np.uint8)
+            keep.append(b)
+            arr[i].data = b.ctypes.data if len(b) else None
+            arr[i].len = len(b)
+        d, n = ctypes.c_void_p(), ctypes.c_size_t()
+        if self._L.lepb200_host_jpeg_write_lep(self._h, arr, len(streams), ctypes.byref(d), ctypes.byref(n)) != 0:
+            raise LeptonB200Error("write_lep failed: %s" % self._L.lepb200_host_jpeg_error(self._h).decode())
+        return ctypes.string_at(d, n.value)
+
+
+class LeptonB200FileCodec:
+    """JPEG bytes -> .lep bytes for a batch of files; host threads + one GPU."""
+
+    def __init__(self, device: int = 0, host_threads: int = 0):
+        self._L = lib()
+        _bind_file_api(self._L)
+        self._c = ctypes.c_void_p()
+        rc = self._L.lepb200_codec_create(ctypes.byref(self._c), device, host_threads)
+        if rc != 0:
+            raise LeptonB200Error("lepb200_codec_create(device=%d) failed with %d (no CUDA device? there is no CPU fallback)" % (device, rc))
+
+    def close(self):
+        if self._c:
+            self._L.lepb200_codec_destroy(self._c)
+            self._c = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress(self, jpegs: Sequence[bytes], copy: bool = True):
+        """-> list of (status, lep_bytes).  With copy=False only lengths are materialised (benchmarking)."""
+        n = len(jpegs)
+        bufs = (_Buffer * n)()
+        keep = []
+        for i, j in enumerate(jpegs):
+            b = np.frombuffer(j, dtype=np.uint8)
+            keep.append(b)
+            bufs[i].data = b.ctypes.data
+            bufs[i].len = len(b)
+        res = (_Result * n)()
+        rc = self._L.lepb200_compress_jpegs(self._c, bufs, n, res)
+        if rc != 0:
+            raise LeptonB200Error("compress_jpegs failed (%d): %s" % (rc, self._L.lepb200_codec_last_error(self._c).decode()))
+        out = []
+        for i in range(n):
+            r = res[i]
+            out.append((r.status, ctypes.string_at(r.data, r.len) if (copy and r.len) else (b"" if copy else r.len)))
+        return out
+
+    def last_timing(self):
+        a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self._L.lepb200_codec_last_timing(self._c, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"front_s": a.value, "gpu_s": b.value, "back_s": c.value}
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.lepb200_kernel_launches(self._L.lepb200_codec_ctx(self._c)))

@@ -1,0 +1,123 @@
+// lep_host.h -- host-side (CPU, C++) halves of the drop-in: JPEG front end, .lep container, mux.
+//
+// These are the callers on either side of the GPU hot path (SURVEY.md section 8(f) "next" rows, host versions):
+//   JPEG bytes --parse_jpeg/decode_scans--> coefficient planes + per-MCU-row handoffs
+//              --select_splits------------> thread-segments          (reference write_ujpg, jpgcoder.cc:3860-3934)
+//              --[GPU: lepb200_encode_*]--> per-segment bool-coder streams
+//              --write_lep----------------> .lep bytes               (reference write_ujpg + vp8_full_encoder tail)
+// and the inverse for decode.  Everything here must be byte-exact with the reference; citations are to
+// /root/reference/src/lepton/jpgcoder.cc unless stated otherwise.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace lephost {
+
+// reference ExitCode values used as status (src/vp8/util/memory.hh:13-39) + local "not handled by this build" codes
+enum Status : int32_t {
+    OK = 0,
+    ASSERTION_FAILURE = 1,
+    SHORT_READ = 3,
+    UNSUPPORTED_4_COLORS = 4,
+    COEFFICIENT_OUT_OF_RANGE = 6,
+    STREAM_INCONSISTENT = 7,
+    PROGRESSIVE_UNSUPPORTED = 8,
+    SAMPLING_BEYOND_TWO_UNSUPPORTED = 10,
+    VERSION_UNSUPPORTED = 13,
+    UNSUPPORTED_JPEG = 42,
+    UNSUPPORTED_JPEG_WITH_ZERO_IDCT_0 = 43,
+    NOT_HANDLED = 200   // feature of the reference this build does not cover yet (never a silent wrong answer)
+};
+
+// ThreadHandoff (src/lepton/thread_handoff.hh:8-39)
+struct Handoff {
+    uint16_t luma_y_start = 0, luma_y_end = 0;
+    uint32_t segment_size = 0;
+    uint8_t overhang_byte = 0, num_overhang_bits = 0;
+    int16_t last_dc[4] = {0, 0, 0, 0};
+};
+
+struct Component {
+    int jid = 0, H = 0, V = 0, tq = 0, td = 0, ta = 0;   // H = horizontal sampling (reference "sfv"), V = vertical ("sfh")
+    int bch = 0, bcv = 0, bc = 0, nch = 0, ncv = 0, mbs = 0;
+};
+
+struct HuffTable {
+    bool set = false;
+    uint8_t bits[17] = {0};
+    uint8_t vals[256] = {0};
+    // decode acceleration
+    uint16_t fast[512];        // (len << 8) | symbol for codes of <= 9 bits, 0 = slow path
+    int32_t maxcode[18];       // canonical decode
+    int32_t valoff[18];
+    // encode side
+    uint16_t ecode[256];
+    uint8_t elen[256];
+    bool build();
+};
+
+struct Jpeg {
+    // ---- read_jpeg products (jpgcoder.cc:2270-2466)
+    std::vector<uint8_t> hdr;        // every marker segment after SOI, in file order ("hdrdata")
+    std::vector<uint8_t> huff;       // entropy-coded bytes of all scans, de-stuffed, RST markers removed ("huffdata")
+    std::vector<uint8_t> grb;        // bytes from EOI on ("grbgdata"); empty when exactly FF D9
+    std::vector<std::pair<uint32_t, uint32_t>> offs;   // (position in huff, position in file) ("huff_input_offsets")
+    std::vector<uint32_t> rst_cnt;   // restart markers seen per scan
+    std::vector<uint8_t> rst_err;    // trailing bogus restart markers per scan
+    bool early_eof = false;
+    uint32_t filesize = 0;
+    // ---- frame (setup_imginfo_jpg, jpgcoder.cc:4450-4540)
+    int jpegtype = 0;                // 1 sequential, 2 progressive
+    int width = 0, height = 0, ncmp = 0;
+    Component cmp[4];
+    uint16_t qtables[4][64];         // zig-zag order as stored in DQT
+    bool qt_set[4] = {false, false, false, false};
+    int mcuh = 0, mcuv = 0, mcuc = 0;
+    // ---- decode products (decode_jpeg, jpgcoder.cc:2799-3302)
+    int8_t padbit = -1;
+    std::vector<Handoff> rows;       // one per MCU row + the final one ("luma_row_offset_return")
+    int status = OK;
+    std::string error;
+};
+
+// Parse the container level of a JPEG file (everything except Huffman decoding).  `data` starts at SOI.
+bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j);
+// Bytes of coefficient plane c (AlignedBlock order).
+inline size_t plane_bytes(const Jpeg& j, int c) { return (size_t)j.cmp[c].bc * 128; }
+// Huffman-decode all scans into planes (pre-zeroed, AlignedBlock order) and record the per-row handoffs.
+bool decode_scans(Jpeg& j, int16_t* const planes[4]);
+
+// ---- container ----------------------------------------------------------------------------------
+struct Splits {
+    std::vector<Handoff> selected;   // what gets serialised into the header ('H' 'H' nseg ...)
+};
+// Thread-segment selection of write_ujpg (jpgcoder.cc:3860-3934) with the reference's default options.
+Splits select_splits(const Jpeg& j);
+
+// MuxWriter + vp8_full_encoder interleave schedule (src/io/MuxReader.hh:336-522, src/lepton/vp8_encoder.cc:573-600).
+void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, std::vector<uint8_t>& out);
+
+// Whole .lep file: fixed header, zlib'd header blob, "CMP", muxed streams, LE32 size trailer.
+bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<const uint8_t*, size_t>>& streams,
+               std::vector<uint8_t>& out, std::string& err);
+
+// ---- decode side --------------------------------------------------------------------------------------
+struct LepFile {
+    uint8_t version = 0, flag = 0;
+    int nseg = 0;
+    uint32_t jpeg_size = 0;
+    Jpeg j;                          // hdr, grb, rst_cnt/rst_err, padbit, frame filled from the header blob
+    std::vector<Handoff> handoffs;   // as serialised (luma_y_start, segment_size, overhang, last_dc)
+    bool has_eee = false;
+    uint32_t eee[7] = {0};
+    std::vector<std::vector<uint8_t>> streams;   // demuxed per-segment bool-coder streams
+    int status = OK;
+    std::string error;
+};
+bool read_lep(const uint8_t* data, size_t n, LepFile& lf);
+// Re-create the JPEG bytes from decoded coefficient planes (recode_baseline_jpeg, src/lepton/recoder.cc:694-889).
+bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err);
+
+}  // namespace lephost

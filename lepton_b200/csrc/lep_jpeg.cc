@@ -1,0 +1,479 @@
+// lep_jpeg.cc -- JPEG front end: marker-level parse, de-stuffing, baseline Huffman decode to coefficient
+// planes in the reference's AlignedBlock order, per-MCU-row ThreadHandoff capture.
+//
+// Behavioural model: read_jpeg (jpgcoder.cc:2270-2466), setup_imginfo_jpg (:4450-4540), parse_jfif_jpg
+// (:4545-4800), decode_jpeg (:2799-3302), decode_block_seq (:4893-4961), next_mcupos (recoder.cc:190-243),
+// crystallize_thread_handoff (jpgcoder.cc:2520-2560).  The implementation is new (table-driven Huffman decoder
+// over a 64-bit window on the de-stuffed stream); files the reference would refuse are refused with the same
+// ExitCode, and reference features not covered yet return NOT_HANDLED rather than guessing.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "lep_host.h"
+
+namespace lephost {
+
+namespace {
+
+// zig-zag position -> AlignedBlock index (src/vp8/util/aligned_block.hh:56-65)
+const uint8_t k_zigzag_to_aligned[64] = {
+    49, 50, 57, 58, 0, 51, 52, 1, 2, 59, 60, 3, 4, 5, 53, 54, 6, 7, 8, 9, 61, 62, 10, 11,
+    12, 13, 14, 55, 56, 15, 16, 17, 18, 19, 20, 63, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32,
+    33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48};
+
+inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+bool fail(Jpeg& j, int status, const char* msg) {
+    j.status = status;
+    j.error = msg;
+    return false;
+}
+
+}  // namespace
+
+bool HuffTable::build() {
+    // canonical code assignment (ITU T.81 Annex C); also the encode-side code/length arrays
+    int code = 0, k = 0;
+    memset(fast, 0, sizeof(fast));
+    memset(elen, 0, sizeof(elen));
+    memset(ecode, 0, sizeof(ecode));
+    for (int len = 1; len <= 16; ++len) {
+        valoff[len] = k - code;
+        for (int i = 0; i < bits[len]; ++i, ++k, ++code) {
+            if (k >= 256) return false;
+            const uint8_t sym = vals[k];
+            ecode[sym] = (uint16_t)code;
+            elen[sym] = (uint8_t)len;
+            if (len <= 9) {
+                const int shift = 9 - len;
+                for (int f = 0; f < (1 << shift); ++f) fast[(code << shift) | f] = (uint16_t)((len << 8) | sym);
+            }
+        }
+        maxcode[len] = bits[len] ? code - 1 : -1;
+        if (code > (1 << len)) return false;
+        code <<= 1;
+    }
+    maxcode[17] = 0x7fffffff;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// read_jpeg: split the file into header segments / de-stuffed entropy data / trailing garbage
+// ------------------------------------------------------------------------------------------------
+static bool parse_frame(Jpeg& j);
+
+bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j) {
+    if (n < 4 || data[0] != 0xFF || data[1] != 0xD8) return fail(j, UNSUPPORTED_JPEG, "not a JPEG (no SOI)");
+    size_t pos = 2;                       // jpg_ident_offset (jpgcoder.cc:1809)
+    uint8_t type = 0, seg0 = 0, seg1 = 0;
+    bool eof_called = false;
+    int scnc = 0;
+    j.huff.reserve(n);
+    j.hdr.reserve(4096);
+    while (true) {
+        if (type == 0xDA) {
+            unsigned cpos = 0, crst = 0;
+            bool scan_done = false;
+            while (!scan_done) {
+                j.offs.emplace_back((uint32_t)j.huff.size(), (uint32_t)pos);
+                if (pos >= n) { j.early_eof = true; eof_called = true; scan_done = true; seg0 = 0; break; }
+                uint8_t tmp = data[pos++];
+                if (tmp != 0xFF) {
+                    crst = 0;
+                    // bulk copy of the run of non-FF bytes
+                    const uint8_t* run = data + pos - 1;
+                    const uint8_t* ff = (const uint8_t*)memchr(run, 0xFF, n - (pos - 1));
+                    size_t len = ff ? (size_t)(ff - run) : n - (pos - 1);
+                    j.huff.insert(j.huff.end(), run, run + len);
+                    pos = (pos - 1) + len;
+                    if (!ff) { j.early_eof = true; eof_called = true; tmp = run[len - 1]; }
+                    else { tmp = 0xFF; pos++; }
+                }
+                if (tmp == 0xFF) {
+                    if (pos >= n) { j.early_eof = true; eof_called = true; scan_done = true; seg0 = 0; break; }
+                    tmp = data[pos++];
+                    if (tmp == 0x00) {
+                        crst = 0;
+                        j.huff.push_back(0xFF);
+                    } else if (tmp == 0xD0 + (cpos & 7)) {
+                        cpos++; crst++;
+                        while (j.rst_cnt.size() <= (size_t)scnc) j.rst_cnt.push_back(0);
+                        ++j.rst_cnt[scnc];
+                    } else {
+                        if ((int)j.rst_err.size() < scnc) j.rst_err.insert(j.rst_err.end(), scnc - j.rst_err.size(), 0);
+                        j.rst_err.push_back((uint8_t)crst);
+                        scnc++;
+                        seg0 = 0xFF; seg1 = tmp;
+                        scan_done = true;
+                    }
+                } else {
+                    scan_done = true;      // end of file inside the scan
+                    seg0 = 0;
+                }
+            }
+            if (j.early_eof) break;
+        } else {
+            if (pos + 2 > n) break;
+            seg0 = data[pos]; seg1 = data[pos + 1];
+            pos += 2;
+            if (seg0 != 0xFF) return fail(j, UNSUPPORTED_JPEG, "size mismatch in marker segment");
+        }
+        type = seg1;
+        if (type == 0xD9) { eof_called = true; break; }
+        if (pos + 2 > n) break;
+        const unsigned len = 2 + be16(data + pos);
+        if (len < 4) break;
+        if (pos + (len - 2) > n) break;
+        // segment = FF type len_hi len_lo payload
+        j.hdr.push_back(0xFF); j.hdr.push_back(type);
+        j.hdr.insert(j.hdr.end(), data + pos, data + pos + (len - 2));
+        pos += len - 2;
+    }
+    if (!eof_called || j.hdr.empty()) return fail(j, UNSUPPORTED_JPEG, "unexpected end of data encountered in header");
+    if (j.huff.empty()) return fail(j, UNSUPPORTED_JPEG, "unexpected end of data encountered in huffman");
+    // garbage: the last two bytes read, then the rest of the file (jpgcoder.cc:2429-2447)
+    {
+        uint8_t g0 = pos >= 2 ? data[pos - 2] : 0, g1 = pos >= 1 ? data[pos - 1] : 0;
+        j.grb.push_back(g0); j.grb.push_back(g1);
+        j.grb.insert(j.grb.end(), data + pos, data + n);
+        if (j.grb.size() == 2 && j.grb[0] == 0xFF && j.grb[1] == 0xD9) j.grb.clear();
+    }
+    j.filesize = (uint32_t)n;
+    return parse_frame(j);
+}
+
+// setup_imginfo_jpg + the SOF/DQT cases of parse_jfif_jpg
+static bool parse_frame(Jpeg& j) {
+    size_t hpos = 0;
+    const std::vector<uint8_t>& h = j.hdr;
+    while (hpos + 4 <= h.size()) {
+        const uint8_t type = h[hpos + 1];
+        const size_t len = 2 + be16(&h[hpos + 2]);
+        const uint8_t* seg = &h[hpos];
+        if (type == 0xDB) {
+            size_t p = 4;
+            while (p < len) {
+                const int pq = seg[p] >> 4, tq = seg[p] & 15;
+                if (pq >= 2 || tq >= 4) break;
+                ++p;
+                if (pq == 0) {
+                    for (int i = 0; i < 64; ++i) {
+                        j.qtables[tq][i] = p + i < len ? seg[p + i] : 0;
+                        if (j.qtables[tq][i] == 0) break;          // reference quirk: stops at the first zero (jpgcoder.cc:4602)
+                    }
+                    p += 64;
+                } else {
+                    for (int i = 0; i < 64; ++i) {
+                        j.qtables[tq][i] = p + 2 * i + 1 < len ? (uint16_t)be16(seg + p + 2 * i) : 0;
+                        if (j.qtables[tq][i] == 0) break;
+                    }
+                    p += 128;
+                }
+                j.qt_set[tq] = true;
+            }
+            if (p != len) return fail(j, UNSUPPORTED_JPEG, "size mismatch in dqt marker");
+        } else if (type == 0xC0 || type == 0xC1 || type == 0xC2) {
+            j.jpegtype = type == 0xC2 ? 2 : 1;
+            if (len < 10) return fail(j, UNSUPPORTED_JPEG, "short SOF");
+            if (seg[4] != 8) return fail(j, UNSUPPORTED_JPEG, "data precision not supported");
+            j.height = be16(seg + 5);
+            j.width = be16(seg + 7);
+            j.ncmp = seg[9];
+            if (j.ncmp > 4) return fail(j, UNSUPPORTED_JPEG, "too many components");
+            if (len < (size_t)(10 + 3 * j.ncmp)) return fail(j, UNSUPPORTED_JPEG, "short SOF");
+            for (int c = 0; c < j.ncmp; ++c) {
+                Component& k = j.cmp[c];
+                k.jid = seg[10 + 3 * c];
+                k.H = seg[11 + 3 * c] >> 4;
+                k.V = seg[11 + 3 * c] & 15;
+                if (k.H > 4 || k.V > 4) return fail(j, 11 /*SAMPLING_BEYOND_FOUR_UNSUPPORTED*/, "sampling factor > 4");
+                if (k.H > 2 || k.V > 2) return fail(j, SAMPLING_BEYOND_TWO_UNSUPPORTED, "sampling factor > 2");
+                k.tq = seg[12 + 3 * c];
+                if (k.tq >= 4) return fail(j, UNSUPPORTED_JPEG, "bad quantisation table id");
+            }
+        } else if (type == 0xC3 || (type >= 0xC5 && type <= 0xC7) || (type >= 0xC9 && type <= 0xCB) || (type >= 0xCD && type <= 0xCF)) {
+            return fail(j, UNSUPPORTED_JPEG, "unsupported SOF type (lossless / differential / arithmetic)");
+        }
+        hpos += len;
+    }
+    if (j.ncmp == 0 || j.jpegtype == 0) return fail(j, UNSUPPORTED_JPEG, "header contains incomplete information");
+    if (j.ncmp > 3) return fail(j, UNSUPPORTED_4_COLORS, "4 colour channels");
+    int hm = 0, vm = 0;
+    for (int c = 0; c < j.ncmp; ++c) {
+        const Component& k = j.cmp[c];
+        if (k.H == 0 || k.V == 0 || !j.qt_set[k.tq] || j.qtables[k.tq][0] == 0) return fail(j, UNSUPPORTED_JPEG, "header information is incomplete");
+        hm = std::max(hm, k.H); vm = std::max(vm, k.V);
+    }
+    j.mcuv = (int)std::ceil((float)j.height / (float)(8 * vm));
+    j.mcuh = (int)std::ceil((float)j.width / (float)(8 * hm));
+    j.mcuc = j.mcuv * j.mcuh;
+    if (j.mcuc <= 0) return fail(j, UNSUPPORTED_JPEG, "empty image");
+    for (int c = 0; c < j.ncmp; ++c) {
+        Component& k = j.cmp[c];
+        k.mbs = k.H * k.V;
+        k.bcv = j.mcuv * k.V;
+        k.bch = j.mcuh * k.H;
+        k.bc = k.bcv * k.bch;
+        k.ncv = (int)std::ceil((float)j.height * ((float)k.V / (8.0 * vm)));
+        k.nch = (int)std::ceil((float)j.width * ((float)k.H / (8.0 * hm)));
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Huffman decoding
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct BitReader {
+    const uint8_t* d;
+    size_t n;          // bytes
+    uint64_t bitpos;   // bits consumed
+    inline bool eof() const { return bitpos >= n * 8; }
+    // peek 32 bits at the current position (zero beyond the end)
+    inline uint32_t peek32() const {
+        size_t byte = (size_t)(bitpos >> 3);
+        uint64_t v = 0;
+        if (byte + 8 <= n) {
+            uint64_t raw;
+            memcpy(&raw, d + byte, 8);
+            v = __builtin_bswap64(raw);
+        } else {
+            for (int i = 0; i < 8; ++i) v = (v << 8) | (byte + i < n ? d[byte + i] : 0);
+        }
+        return (uint32_t)((v << (bitpos & 7)) >> 32);
+    }
+    inline void skip(int k) { bitpos += (uint64_t)k; }
+};
+
+// one Huffman symbol; -1 on invalid code / read past the end
+inline int decode_symbol(BitReader& br, const HuffTable& t) {
+    const uint32_t w = br.peek32();
+    const uint16_t f = t.fast[w >> 23];
+    if (f) {
+        br.skip(f >> 8);
+        return f & 0xff;
+    }
+    int code = (int)(w >> 22);   // 10 bits
+    int len = 10;
+    while (len <= 16 && code > t.maxcode[len]) { ++len; code = (int)(w >> (32 - len)); }
+    if (len > 16) return -1;
+    br.skip(len);
+    return t.vals[code + t.valoff[len]];
+}
+
+inline int devli(int s, int n) { return s == 0 ? n : (n >= (1 << (s - 1)) ? n : n + 1 - (1 << s)); }
+
+struct ScanInfo {
+    int ncomp = 0;
+    int cmp[4] = {0, 0, 0, 0};
+    int from = 0, to = 0, sah = 0, sal = 0;
+};
+
+// crystallize_thread_handoff (jpgcoder.cc:2520-2560).  abitreader::getpos() == (bits consumed >> 3) + 1.
+Handoff crystallize(const Jpeg& j, const BitReader& br, int mcu_y, const int lastdc[4], int luma_mul) {
+    const uint32_t gp = (uint32_t)(br.bitpos >> 3) + 1;
+    const auto& offs = j.offs;
+    auto it = std::lower_bound(offs.begin(), offs.end(), std::pair<uint32_t, uint32_t>(gp, gp));
+    if (it != offs.begin()) --it;
+    uint32_t mapped = 0;
+    if (it != offs.end()) mapped = it->second + (gp - it->first);
+    Handoff h;
+    h.segment_size = mapped;
+    for (int i = 0; i < 3; ++i) h.last_dc[i] = (int16_t)lastdc[i];
+    h.luma_y_start = (uint16_t)(luma_mul * mcu_y);
+    h.luma_y_end = (uint16_t)(luma_mul * (mcu_y + 1));
+    const int rem = (int)(br.bitpos & 7);
+    h.num_overhang_bits = (uint8_t)rem;
+    uint8_t cur = (size_t)(br.bitpos >> 3) < br.n ? br.d[br.bitpos >> 3] : 0;
+    h.overhang_byte = (uint8_t)(cur & (((1 << rem) - 1) << (8 - rem)));
+    return h;
+}
+
+// abitreader::unpad (bitops.hh:316-332)
+int8_t unpad(BitReader& br, int8_t fillbit) {
+    if ((br.bitpos & 7) == 0 || br.eof()) return fillbit;
+    auto rd = [&]() { int b = (br.d[br.bitpos >> 3] >> (7 - (br.bitpos & 7))) & 1; br.bitpos++; return b; };
+    int last = rd();
+    int fb = last, offset = 1;
+    while (br.bitpos & 7) { last = rd(); fb |= last << offset; ++offset; }
+    while (offset < 7) { fb |= last << offset; ++offset; }
+    return (int8_t)fb;
+}
+
+}  // namespace
+
+bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
+    HuffTable dc_t[4], ac_t[4];
+    BitReader br{j.huff.data(), j.huff.size(), 0};
+    int rsti = 0;
+    int lastdc[4] = {0, 0, 0, 0};
+    size_t hpos = 0;
+    const std::vector<uint8_t>& h = j.hdr;
+    const int luma_mul = j.cmp[0].bcv / j.mcuv;
+    int mcu = 0;
+    int scans = 0;
+    j.padbit = -1;
+    if (j.jpegtype != 1) return fail(j, NOT_HANDLED, "progressive JPEG: host front end not implemented yet");
+    if (j.early_eof) return fail(j, NOT_HANDLED, "truncated JPEG: host front end not implemented yet");
+    while (true) {
+        ScanInfo sc;
+        uint8_t type = 0;
+        while (type != 0xDA) {
+            if (hpos + 3 >= h.size()) break;
+            type = h[hpos + 1];
+            const size_t len = 2 + be16(&h[hpos + 2]);
+            const uint8_t* seg = &h[hpos];
+            if (hpos + len > h.size()) return fail(j, UNSUPPORTED_JPEG, "truncated header segment");
+            if (type == 0xC4) {
+                size_t p = 4;
+                while (p < len) {
+                    const int tc = seg[p] >> 4, th = seg[p] & 15;
+                    if (tc >= 2 || th >= 4) break;
+                    ++p;
+                    if (p + 16 > len) return fail(j, UNSUPPORTED_JPEG, "size mismatch in dht marker");
+                    HuffTable& t = tc ? ac_t[th] : dc_t[th];
+                    int total = 0;
+                    t.bits[0] = 0;
+                    for (int i = 0; i < 16; ++i) { t.bits[i + 1] = seg[p + i]; total += seg[p + i]; }
+                    if (total > 256 || p + 16 + total > len) return fail(j, UNSUPPORTED_JPEG, "size mismatch in dht marker");
+                    memcpy(t.vals, seg + p + 16, total);
+                    if (!t.build()) return fail(j, UNSUPPORTED_JPEG, "bad huffman table");
+                    t.set = true;
+                    p += 16 + total;
+                }
+                if (p != len) return fail(j, UNSUPPORTED_JPEG, "size mismatch in dht marker");
+            } else if (type == 0xDD) {
+                rsti = be16(seg + 4);
+            } else if (type == 0xDA) {
+                sc.ncomp = seg[4];
+                if (sc.ncomp > j.ncmp || sc.ncomp < 1 || len < (size_t)(8 + 2 * sc.ncomp)) return fail(j, UNSUPPORTED_JPEG, "bad SOS");
+                for (int i = 0; i < sc.ncomp; ++i) {
+                    int c = 0;
+                    while (c < j.ncmp && j.cmp[c].jid != seg[5 + 2 * i]) ++c;
+                    if (c == j.ncmp) return fail(j, UNSUPPORTED_JPEG, "component id mismatch in start-of-scan");
+                    sc.cmp[i] = c;
+                    j.cmp[c].td = seg[6 + 2 * i] >> 4;
+                    j.cmp[c].ta = seg[6 + 2 * i] & 15;
+                    if (j.cmp[c].td >= 4 || j.cmp[c].ta >= 4) return fail(j, UNSUPPORTED_JPEG, "huffman table number mismatch");
+                }
+                const uint8_t* t = seg + 5 + 2 * sc.ncomp;
+                sc.from = t[0]; sc.to = t[1]; sc.sah = t[2] >> 4; sc.sal = t[2] & 15;
+                if (sc.from > sc.to || sc.to > 63) return fail(j, UNSUPPORTED_JPEG, "spectral selection parameter out of range");
+            }
+            hpos += len;
+        }
+        if (type != 0xDA) break;
+        for (int i = 0; i < sc.ncomp; ++i) {
+            const Component& k = j.cmp[sc.cmp[i]];
+            if (!dc_t[k.td].set || !ac_t[k.ta].set) return fail(j, UNSUPPORTED_JPEG, "huffman table missing in scan");
+        }
+        if (sc.ncomp != j.ncmp) return fail(j, PROGRESSIVE_UNSUPPORTED, "non-interleaved multi-scan JPEG (treated as progressive by the reference)");
+
+        int cmp = sc.cmp[0], csc = 0, sub = 0, dpos = 0;
+        mcu = 0;
+        bool handoff_due = true;
+        int sta = 0;
+        const int hmul = j.cmp[0].bch / j.mcuh, vmul = j.cmp[0].bcv / j.mcuv;
+        while (true) {
+            lastdc[0] = lastdc[1] = lastdc[2] = lastdc[3] = 0;
+            sta = 0;
+            int rstw = rsti;
+            while (sta == 0) {
+                if (handoff_due) {
+                    const int mcu_y = sc.ncomp > 1 ? mcu / j.mcuh : (dpos / (hmul * vmul)) / j.mcuh;
+                    j.rows.push_back(crystallize(j, br, mcu_y, lastdc, luma_mul));
+                    handoff_due = false;
+                }
+                // ---- decode_block_seq
+                const Component& k = j.cmp[cmp];
+                const HuffTable& dct = dc_t[k.td];
+                const HuffTable& act = ac_t[k.ta];
+                int16_t* blk = planes[cmp] + (size_t)dpos * 64;
+                int s = decode_symbol(br, dct);
+                if (s < 0 || s > 16) return fail(j, UNSUPPORTED_JPEG, "decode error in scan (dc)");
+                uint32_t nbits = s ? (br.peek32() >> (32 - s)) : 0;
+                br.skip(s);
+                int16_t dcv = (int16_t)(devli(s, (int)nbits) + lastdc[cmp]);
+                lastdc[cmp] = dcv;
+                blk[k_zigzag_to_aligned[0]] = dcv;
+                int bpos = 1, eob = 64;
+                int last_nonzero_written = 1;   // whether block[eob-1] != 0 (reference check :2953)
+                while (bpos < 64) {
+                    int hc = decode_symbol(br, act);
+                    if (hc < 0) return fail(j, UNSUPPORTED_JPEG, "decode error in scan (ac)");
+                    if (hc > 0) {
+                        int z = hc >> 4;
+                        s = hc & 15;
+                        nbits = s ? (br.peek32() >> (32 - s)) : 0;
+                        br.skip(s);
+                        if (z + bpos >= 64) return fail(j, NOT_HANDLED, "zero run past the end of the block (truncated-file fix-up)");
+                        bpos += z;
+                        int v = devli(s, (int)nbits);
+                        blk[k_zigzag_to_aligned[bpos++]] = (int16_t)v;
+                        last_nonzero_written = v != 0;
+                    } else {
+                        eob = bpos;
+                        break;
+                    }
+                }
+                if (eob > 1 && !last_nonzero_written) return fail(j, UNSUPPORTED_JPEG, "cannot encode image with eob after last 0");
+                if (br.bitpos > (uint64_t)br.n * 8) return fail(j, NOT_HANDLED, "entropy data ends inside a block (truncated file)");
+                // ---- next position
+                if (sc.ncomp > 1) {
+                    const int old_mcu = mcu;
+                    // next_mcupos (recoder.cc:190-243)
+                    if (++sub >= j.cmp[cmp].mbs) {
+                        sub = 0;
+                        if (++csc >= sc.ncomp) {
+                            csc = 0;
+                            cmp = sc.cmp[0];
+                            ++mcu;
+                            if (mcu >= j.mcuc) sta = 2;
+                            else if (rsti > 0 && --rstw == 0) sta = 1;
+                        } else {
+                            cmp = sc.cmp[csc];
+                        }
+                    }
+                    const Component& kk = j.cmp[cmp];
+                    if (kk.V > 1) {
+                        const int my = mcu / j.mcuh, mx = mcu - my * j.mcuh, sy = sub / kk.H, sx = sub - sy * kk.H;
+                        dpos = (my * kk.V + sy) * kk.bch + mx * kk.H + sx;
+                    } else if (kk.H > 1) {
+                        dpos = mcu * kk.mbs + sub;
+                    } else {
+                        dpos = mcu;
+                    }
+                    if (mcu % j.mcuh == 0 && old_mcu != mcu) handoff_due = true;
+                } else {
+                    // next_mcuposn (jpgcoder.cc:5432-5456)
+                    const Component& kk = j.cmp[cmp];
+                    dpos++;
+                    if (kk.bch != kk.nch && dpos % kk.bch == kk.nch) dpos += kk.bch - kk.nch;
+                    if (kk.bcv != kk.ncv && dpos / kk.bch == kk.ncv) dpos = kk.bc;
+                    if (dpos >= kk.bc) sta = 2;
+                    else if (rsti > 0 && --rstw == 0) sta = 1;
+                    mcu = dpos / (hmul * vmul);
+                    if (cmp == 0 && (mcu % j.mcuh == 0) && (dpos % (hmul * vmul) == 0)) handoff_due = true;
+                }
+                if (br.eof()) { sta = 2; break; }
+            }
+            // padbit bookkeeping (jpgcoder.cc:3260-3271)
+            if (j.padbit != -1) {
+                if (j.padbit != unpad(br, j.padbit)) return fail(j, UNSUPPORTED_JPEG, "inconsistent use of padbits");
+            } else {
+                j.padbit = unpad(br, j.padbit);
+            }
+            if (sta == 2) { ++scans; break; }
+        }
+    }
+    if (scans == 0) return fail(j, UNSUPPORTED_JPEG, "no scan found");
+    j.rows.push_back(crystallize(j, br, (uint16_t)(mcu / j.mcuh), lastdc, luma_mul));
+    for (size_t i = 1; i < j.rows.size(); ++i)
+        if (j.rows[i].luma_y_start < j.rows[i - 1].luma_y_end) j.rows[i].luma_y_start = j.rows[i - 1].luma_y_end;
+    if (!br.eof()) return fail(j, UNSUPPORTED_JPEG, "unneeded data found after coded image data");
+    return true;
+}
+
+}  // namespace lephost

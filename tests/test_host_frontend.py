@@ -1,0 +1,61 @@
+"""Host (CPU) halves of the drop-in, no GPU needed: the JPEG front end must reproduce the reference's coefficient
+planes and thread-segment splits, and the container writer must reproduce the reference's .lep bytes when fed the
+reference's own segment streams (so header blob, zlib stream, handoffs, mux packets and trailer are all pinned)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import lepfmt
+from helpers import GOLDEN, MANIFEST, load_lep
+
+BASELINE_COMPLETE = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "colorswap.jpg",
+                     "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg"]
+
+
+@pytest.mark.parametrize("name", BASELINE_COMPLETE)
+def test_jpeg_front_end_and_container_match_reference(name):
+    from lepton_b200 import HostJpeg
+    data = open(os.path.join(GOLDEN, name), "rb").read()
+    hj = HostJpeg(data)
+    assert hj.status == 0, hj.error
+    img = hj.coef_image()
+    m = MANIFEST[name]
+    got = [hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in img.planes]
+    assert got == m["plane_sha256"], "Huffman-decoded planes differ from the reference's -ujg dump"
+    assert list(img.luma_y_start) == m["splits"]
+    lf = load_lep(name[:-4] + ".lep")
+    streams = lepfmt.demux(lf.payload)[:lf.nseg]
+    lep = hj.write_lep(streams)
+    ref = open(os.path.join(GOLDEN, name[:-4] + ".lep"), "rb").read()
+    assert lep == ref, "assembled .lep differs from the reference's file"
+
+
+@pytest.mark.parametrize("name,status", [("androidprogressive.jpg", 200), ("gray2sf.jpg", 200), ("narrowrst.jpg", 200)])
+def test_unhandled_inputs_are_refused_not_miscoded(name, status):
+    from lepton_b200 import HostJpeg
+    hj = HostJpeg(open(os.path.join(GOLDEN, name), "rb").read())
+    assert hj.status == status and hj.error
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """Every function declared in include/lepton_b200.h must be exported by the built library."""
+    import re
+    import ctypes
+    from lepton_b200 import library_path
+    hdr = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "lepton_b200.h")).read()
+    names = set(re.findall(r"\b(lepb200_[a-z0-9_]+)\s*\(", hdr))
+    L = ctypes.CDLL(library_path())
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert len(names) >= 25
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from lepton_b200 import LeptonB200Codec, LeptonB200Error
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(LeptonB200Error):
+        LeptonB200Codec(0)
