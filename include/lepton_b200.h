@@ -106,6 +106,8 @@ int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
 int lepb200_decode_launch(lepb200_ctx* ctx);
 int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, int32_t* status_out);
 
+/* Wait for everything queued on the context's stream. */
+int lepb200_sync(lepb200_ctx* ctx);
 /* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */
 float lepb200_last_kernel_ms(lepb200_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */

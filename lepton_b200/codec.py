@@ -54,7 +54,7 @@ _EXPORTS = [
     "lepb200_encode_images", "lepb200_decode_images", "lepb200_encode_upload", "lepb200_encode_launch",
     "lepb200_encode_fetch", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
-    "lepb200_device_available", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
+    "lepb200_device_available", "lepb200_sync", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
     "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
 ]
@@ -97,6 +97,8 @@ def lib():
               "lepb200_decode_images", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
               "lepb200_device_available"):
         getattr(L, f).restype = ctypes.c_int
+    L.lepb200_sync.argtypes = [vp]
+    L.lepb200_sync.restype = ctypes.c_int
     L.lepb200_last_kernel_ms.argtypes = [vp]
     L.lepb200_last_kernel_ms.restype = ctypes.c_float
     L.lepb200_kernel_launches.argtypes = [vp]
@@ -253,6 +255,9 @@ class LeptonB200Codec:
         self.decode_upload(images, streams)
         self.decode_launch()
         return self.decode_fetch()
+
+    def sync(self):
+        self._check(self._L.lepb200_sync(self._ctx), "sync")
 
     # ---- introspection ----------------------------------------------------------------------------
     @property

@@ -190,7 +190,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
             size_t nb = segment_blocks(im, sd.min_y, sd.max_y, sd.is_last);
             ctx->seg_blocks.push_back(nb);
             if (encode) {
-                size_t cap = align_up(nb * 128 + 4096, 256);
+                size_t cap = align_up(nb * 64 + 4096, 256);   // 64 B/block is > 1.5x what q=100 photos need; overflow is reported, never silent
                 sd.stream = stream_total; sd.cap = (uint32_t)cap;
                 stream_total += cap;
             } else {
@@ -292,7 +292,21 @@ void lepb200_destroy(lepb200_ctx* ctx) {
 }
 
 const char* lepb200_last_error(const lepb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-float lepb200_last_kernel_ms(lepb200_ctx* ctx) { return ctx ? ctx->last_ms : -1.f; }
+int lepb200_sync(lepb200_ctx* ctx) {
+    if (!ctx) return LEPB200_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return LEPB200_OK;
+}
+float lepb200_last_kernel_ms(lepb200_ctx* ctx) {
+    if (!ctx) return -1.f;
+    if (ctx->launched) {
+        cudaSetDevice(ctx->device);
+        float ms = -1.f;
+        if (cudaEventSynchronize(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    }
+    return ctx->last_ms;
+}
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx) { return ctx ? ctx->alg_bytes : 0; }
 
