@@ -110,6 +110,9 @@ int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nima
 int lepb200_sync(lepb200_ctx* ctx);
 /* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */
 float lepb200_last_kernel_ms(lepb200_ctx* ctx);
+/* Encode only: device time of kernel A (symbolisation + model update) within the last launch; the rest of
+ * lepb200_last_kernel_ms is kernel B (range coder). */
+float lepb200_last_symbolise_ms(lepb200_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx);
 /* Sum over the last uploaded batch of 128 * coded blocks + stream bytes (SURVEY.md section 8(d) algorithmic bytes);

@@ -54,7 +54,7 @@ _EXPORTS = [
     "lepb200_encode_images", "lepb200_decode_images", "lepb200_encode_upload", "lepb200_encode_launch",
     "lepb200_encode_fetch", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
-    "lepb200_device_available", "lepb200_sync", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
+    "lepb200_device_available", "lepb200_sync", "lepb200_last_symbolise_ms", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
     "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
 ]
@@ -101,6 +101,8 @@ def lib():
     L.lepb200_sync.restype = ctypes.c_int
     L.lepb200_last_kernel_ms.argtypes = [vp]
     L.lepb200_last_kernel_ms.restype = ctypes.c_float
+    L.lepb200_last_symbolise_ms.argtypes = [vp]
+    L.lepb200_last_symbolise_ms.restype = ctypes.c_float
     L.lepb200_kernel_launches.argtypes = [vp]
     L.lepb200_kernel_launches.restype = ctypes.c_uint64
     L.lepb200_last_algorithmic_bytes.argtypes = [vp]
@@ -263,6 +265,10 @@ class LeptonB200Codec:
     @property
     def last_kernel_ms(self) -> float:
         return float(self._L.lepb200_last_kernel_ms(self._ctx))
+
+    @property
+    def last_symbolise_ms(self) -> float:
+        return float(self._L.lepb200_last_symbolise_ms(self._ctx))
 
     @property
     def kernel_launches(self) -> int:

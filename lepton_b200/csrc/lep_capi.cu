@@ -66,9 +66,9 @@ struct lepb200_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     std::string err;
-    DevBuf d_planes, d_streams, d_dense, d_images, d_segs, d_order, d_counter, d_models, d_rows;
+    DevBuf d_planes, d_streams, d_tokens, d_dense, d_images, d_segs, d_order, d_counter, d_models, d_rows;
     HostBuf h_segs, h_dense, h_stage;
     std::vector<ImageDesc> images;
     std::vector<SegDesc> segs;
@@ -78,7 +78,8 @@ struct lepb200_ctx {
     size_t row_stride = 0;
     int grid = 0;
     bool have_batch = false, launched = false, is_encode = true;
-    float last_ms = -1.f;
+    float last_ms = -1.f, last_ms_a = -1.f;
+    uint32_t tokens_per_block = 128;     // token-stream capacity per coded block (worst case is 1420; overflow is reported)
     uint64_t launches = 0;
     uint64_t alg_bytes = 0;
     uint64_t coded_blocks = 0;
@@ -156,7 +157,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     if (nimages <= 0 || !images) { ctx->err = "empty batch"; return LEPB200_ERR_INVALID; }
     ctx->images.assign(nimages, ImageDesc());
     ctx->segs.clear(); ctx->seg_blocks.clear(); ctx->plane_bytes.assign((size_t)nimages * 3, 0);
-    size_t plane_total = 0, stream_total = 0, row_stride = 0;
+    size_t plane_total = 0, stream_total = 0, token_total = 0, row_stride = 0;
     int sidx = 0;
     for (int i = 0; i < nimages; ++i) {
         const lepb200_image& im = images[i];
@@ -193,6 +194,9 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
                 size_t cap = align_up(nb * 64 + 4096, 256);   // 64 B/block is > 1.5x what q=100 photos need; overflow is reported, never silent
                 sd.stream = stream_total; sd.cap = (uint32_t)cap;
                 stream_total += cap;
+                size_t tcap = align_up(nb * ctx->tokens_per_block + 64, 64);
+                sd.tokens = token_total; sd.tok_cap = (uint32_t)std::min<size_t>(tcap, 0xffffff00u);
+                token_total += tcap * 2;
             } else {
                 sd.stream = stream_total; sd.cap = (uint32_t)in[sidx].len;
                 stream_total += align_up((size_t)in[sidx].len + 16, 16);
@@ -217,6 +221,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
 
     CK(ctx->d_planes.reserve(plane_total));
     CK(ctx->d_streams.reserve(stream_total + 256));
+    if (encode) CK(ctx->d_tokens.reserve(token_total + 256));
     CK(ctx->d_images.reserve(sizeof(ImageDesc) * nimages));
     CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
@@ -225,7 +230,10 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < ctx->images[i].ncmp; ++c) ctx->images[i].plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
-    for (auto& sd : ctx->segs) sd.stream += (unsigned long long)(uintptr_t)ctx->d_streams.p;
+    for (auto& sd : ctx->segs) {
+        sd.stream += (unsigned long long)(uintptr_t)ctx->d_streams.p;
+        if (encode) sd.tokens += (unsigned long long)(uintptr_t)ctx->d_tokens.p;
+    }
     CK(cudaMemcpyAsync(ctx->d_images.p, ctx->images.data(), sizeof(ImageDesc) * nimages, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_segs.p, ctx->segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_order.p, ctx->order.data(), sizeof(int) * nseg, cudaMemcpyHostToDevice, ctx->stream));
@@ -270,7 +278,7 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return LEPB200_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev_mid) != cudaSuccess) {
         delete ctx;
         return LEPB200_ERR_CUDA;
     }
@@ -282,11 +290,12 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_planes, &ctx->d_streams, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
+    for (DevBuf* b : {&ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
         b->release();
     for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage}) b->release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_mid);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -304,8 +313,14 @@ float lepb200_last_kernel_ms(lepb200_ctx* ctx) {
         cudaSetDevice(ctx->device);
         float ms = -1.f;
         if (cudaEventSynchronize(ctx->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+        if (ctx->is_encode && cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev_mid) == cudaSuccess) ctx->last_ms_a = ms;
     }
     return ctx->last_ms;
+}
+float lepb200_last_symbolise_ms(lepb200_ctx* ctx) {
+    if (!ctx) return -1.f;
+    lepb200_last_kernel_ms(ctx);
+    return ctx->last_ms_a;
 }
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx) { return ctx ? ctx->alg_bytes : 0; }
@@ -340,8 +355,12 @@ int lepb200_encode_launch(lepb200_ctx* ctx) {
         static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
         static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
+    lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(static_cast<SegDesc*>(ctx->d_segs.p), nseg,
+                                                                                              static_cast<const int*>(ctx->d_order.p));
+    CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches += 1;
+    ctx->launches += 2;
     ctx->launched = true;
     return LEPB200_OK;
 }

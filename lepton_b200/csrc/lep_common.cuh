@@ -90,7 +90,9 @@ struct SegDesc {
     uint32_t len;                    // encode: bytes produced
     int32_t status;                  // reference ExitCode value (0 ok, 6 COEFFICIENT_OUT_OF_RANGE, 7 STREAM_INCONSISTENT, ...)
     uint32_t ndecisions_lo, ndecisions_hi;
-    uint32_t pad_;
+    uint32_t ntok;                   // encode: (probability, bit) tokens produced by kernel A
+    unsigned long long tokens;       // encode: device address of the segment's token stream (uint16 each)
+    uint32_t tok_cap, pad_;
 };
 
 enum : int32_t { ST_OK = 0, ST_ASSERT = 1, ST_COEF_RANGE = 6, ST_STREAM_INCONSISTENT = 7, ST_OUT_OVERFLOW = 100 };

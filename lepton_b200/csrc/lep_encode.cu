@@ -3,16 +3,18 @@
 // Work decomposition (new; the reference runs one CPU thread per segment, src/lepton/vp8_encoder.cc:239-445):
 //   * persistent grid, one WARP per Lepton thread-segment, segments pulled from a global work queue
 //     (largest first), the warp's 1.5 MB probability model zero-filled by the warp itself;
-//   * per 8x8 block the warp works in three phases
+//   * kernel A (lep_encode_kernel), per 8x8 block the warp works in two phases
 //       1. lane-parallel SYMBOLISATION: each lane owns two coefficients (one 32-bit word of the 128-byte
 //          AlignedBlock), computes their neighbour priors / context bins and appends their binary
 //          decisions (model index, bit) to a shared-memory queue at a prefix-sum offset.  Nothing in the
 //          encoder's context computation depends on coder state (hard part 1);
 //       2. batched MODEL UPDATE: 32 queued decisions at a time, one per lane -- parallel 16-bit loads of
 //          the adaptive counts, same-address conflicts resolved in queue order with __match_any_sync,
-//          probabilities computed per lane, counts written back;
-//       3. the RANGE CODER chain (vpx_write, src/vp8/encoder/boolwriter.hh:48-118) runs warp-uniform over
-//          the 32 (probability, bit) pairs broadcast by shuffle; bytes leave through lane 0.
+//          probabilities computed per lane, counts written back; the resulting (probability, bit) TOKENS
+//          (16 bits each) are appended to the segment's token stream in HBM with coalesced 64-byte stores;
+//   * kernel B (lep_rangecode_kernel) runs the serial RANGE CODER chain (vpx_write,
+//     src/vp8/encoder/boolwriter.hh:48-118) with one THREAD per segment: the chain needs no memory-dependent
+//     loads any more, so 32 segments advance per warp instruction instead of one.
 //
 // Bit-exactness notes follow the oracle (oracle/lepton_oracle.c), which is pinned against the reference.
 #include "lep_common.cuh"
@@ -35,73 +37,34 @@ struct EncShared {
     EncWarpSmem w[ENC_WARPS_PER_CTA];
 };
 
-// ---- bool writer state (warp-uniform) ------------------------------------------------------------
-struct BoolWriter {
-    uint32_t low, range;
-    int count;
-    uint32_t pos, cap;
-    uint8_t* buf;
-    bool overflow;
-};
-
-// vpx_write (boolwriter.hh:48-118). All lanes run it with identical state; lane 0 touches memory.
-__device__ __forceinline__ void bw_put(BoolWriter& w, uint32_t bit, uint32_t prob, int lane) {
-    uint32_t split = 1 + (((w.range - 1) * prob) >> 8);
-    uint32_t range = bit ? w.range - split : split;
-    uint32_t low = w.low + (bit ? split : 0);
-    int shift = __clz(range) - 24;
-    range <<= shift;
-    int count = w.count + shift;
-    if (count >= 0) {
-        int offset = shift - count;
-        if (lane == 0) {
-            if ((low << (offset - 1)) & 0x80000000u) {      // carry: walk back over 0xff bytes (boolwriter.hh:96-105)
-                int x = (int)w.pos - 1;
-                while (x >= 0 && w.buf[x] == 0xff) { w.buf[x] = 0; --x; }
-                if (x >= 0) w.buf[x] += 1;
-            }
-            if (w.pos < w.cap) w.buf[w.pos] = (uint8_t)(low >> (24 - offset));
-        }
-        if (w.pos >= w.cap) w.overflow = true;
-        w.pos++;
-        low = (low << offset) & 0xffffff;
-        shift = count;
-        count -= 8;
-    }
-    w.low = low << shift;
-    w.count = count;
-    w.range = range;
-}
-
 // ---- queue flush: batched model update + range-coder chain ------------------------------------------
 __device__ __forceinline__ void flush_queue(const uint32_t* __restrict__ queue, int n, uint16_t* __restrict__ model,
-                                            const uint32_t* __restrict__ s_rcp, BoolWriter& bw, int lane) {
+                                            const uint32_t* __restrict__ s_rcp, uint16_t* __restrict__ tokens, uint32_t& ntok,
+                                            uint32_t tok_cap, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1;
     for (int base = 0; base < n; base += 32) {
-        int i = base + lane;
-        bool active = i < n;
-        uint32_t e = active ? queue[i] : 0;
-        uint32_t addr = e & 0xfffffu, bit = e >> 31;
-        uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
-        int rank = __popc(peers & lt_mask);
-        int npeers = __popc(peers);
+        const int i = base + lane;
+        const bool active = i < n;
+        const uint32_t e = active ? queue[i] : 0;
+        const uint32_t addr = e & 0xfffffu, bit = e >> 31;
+        const uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
+        const uint32_t earlier = peers & lt_mask;
+        const int rank = __popc(earlier);
+        const int pred = earlier ? 31 - __clz(earlier) : lane;     // previous decision on the same branch
         uint32_t w = active ? (uint32_t)model[addr] : 0u;
-        int maxrank = __reduce_max_sync(FULL, npeers - 1);
-        // apply, in queue order, the updates of earlier decisions that hit the same branch
-        for (int r = 0; r < maxrank; ++r) {
-            int src = (r < npeers) ? (int)__fns(peers, 0, r + 1) : lane;   // lane holding the r-th earlier decision
-            uint32_t sbit = __shfl_sync(FULL, bit, src);
-            if (rank > r) w = branch_update(w, sbit);
+        const int maxrank = __reduce_max_sync(FULL, rank);
+        // Resolve same-branch conflicts in queue order: in round r the lanes of rank r take over the state their
+        // predecessor (rank r-1, already resolved) leaves behind after its own update.
+        for (int r = 1; r <= maxrank; ++r) {
+            const uint32_t after = branch_update(w, bit);
+            const uint32_t from_pred = __shfl_sync(FULL, after, pred);
+            if (rank == r) w = from_pred;
         }
-        uint32_t prob = branch_prob(w, s_rcp);
-        if (active && rank == npeers - 1) model[addr] = (uint16_t)branch_update(w, bit);
-        int cnt = min(32, n - base);
-        for (int j = 0; j < cnt; ++j) {
-            uint32_t p = __shfl_sync(FULL, prob, j);
-            uint32_t b = __shfl_sync(FULL, bit, j);
-            bw_put(bw, b, p, lane);
-        }
+        const uint32_t pb = branch_prob(w, s_rcp) | (bit << 8);
+        if (active && (peers >> lane) == 1u) model[addr] = (uint16_t)branch_update(w, bit);   // last decision of its branch
+        if (active && ntok + i < tok_cap) tokens[ntok + i] = (uint16_t)pb;                    // coalesced 2-byte stores
     }
+    ntok += (uint32_t)n;
     __syncwarp();
 }
 
@@ -143,9 +106,9 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
         }
         __syncwarp();
 
-        BoolWriter bw;
-        bw.low = 0; bw.range = 255; bw.count = -24; bw.pos = 0; bw.cap = sd.cap; bw.buf = reinterpret_cast<uint8_t*>(sd.stream); bw.overflow = false;
-        bw_put(bw, 0, 128, lane);                                    // vpx_start_encode marker bit (boolwriter.cc:17-24)
+        uint16_t* tokens = reinterpret_cast<uint16_t*>(sd.tokens);
+        const uint32_t tok_cap = sd.tok_cap;
+        uint32_t ntok = 0;
 
         // per-component row buffers: bottom-edge prediction (8 x int16) and 7x7 nonzero count of the row above
         int16_t* row_edge[3]; uint8_t* row_nz[3];
@@ -379,7 +342,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 // ---------------- code the queued decisions
                 status = __reduce_max_sync(FULL, status);
                 if (status != ST_OK) break;
-                flush_queue(ws.queue, qn, model, sm.rcp, bw, lane);
+                flush_queue(ws.queue, qn, model, sm.rcp, tokens, ntok, tok_cap, lane);
                 ndec += (unsigned long long)qn;
 
                 // early-out on truncated images (vp8_encoder.cc:110-113,133-135): not after the right-most block
@@ -389,23 +352,80 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             }
             if (status != ST_OK) break;
         }
-        if (status == ST_OK) {
-            for (int i = 0; i < 32; ++i) bw_put(bw, 0, 128, lane);                      // vpx_stop_encode (boolwriter.cc:26-35)
-            if (lane == 0 && bw.pos > 0 && bw.pos < bw.cap && (bw.buf[bw.pos - 1] & 0xe0) == 0xc0) bw.buf[bw.pos] = 0;
-            uint32_t last = 0;
-            if (lane == 0 && bw.pos > 0 && bw.pos <= bw.cap) last = bw.buf[bw.pos - 1];
-            last = __shfl_sync(FULL, last, 0);
-            if ((last & 0xe0) == 0xc0) bw.pos++;
-            if (bw.overflow || bw.pos > bw.cap) status = ST_OUT_OVERFLOW;
-        }
+        if (status == ST_OK && ntok > tok_cap) status = ST_OUT_OVERFLOW;
         if (lane == 0) {
-            sd.len = bw.pos;
+            sd.ntok = ntok;
+            sd.len = 0;
             sd.status = status;
             sd.ndecisions_lo = (uint32_t)ndec;
             sd.ndecisions_hi = (uint32_t)(ndec >> 32);
         }
         __syncwarp();
     }
+}
+
+// ---- kernel B: the range coder, one thread per segment ------------------------------------------------
+// vpx_start_encode / vpx_write / vpx_stop_encode (src/vp8/encoder/boolwriter.cc:17-35, boolwriter.hh:48-118)
+// over the (probability, bit) tokens produced by kernel A.  Per-thread state; bytes go straight to the segment's
+// stream, the carry walks back over already written 0xff bytes exactly like the reference.
+struct RcState { uint32_t low, range; int count; uint32_t pos, cap; uint8_t* buf; };
+
+__device__ __forceinline__ void rc_put(RcState& w, uint32_t bit, uint32_t prob) {
+    const uint32_t split = 1 + (((w.range - 1) * prob) >> 8);
+    uint32_t range = bit ? w.range - split : split;
+    uint32_t low = w.low + (bit ? split : 0);
+    int shift = __clz(range) - 24;
+    range <<= shift;
+    int count = w.count + shift;
+    if (count >= 0) {
+        const int offset = shift - count;
+        if ((low << (offset - 1)) & 0x80000000u) {
+            int x = (int)w.pos - 1;
+            while (x >= 0 && w.buf[x] == 0xff) { w.buf[x] = 0; --x; }
+            if (x >= 0) w.buf[x] += 1;
+        }
+        if (w.pos < w.cap) w.buf[w.pos] = (uint8_t)(low >> (24 - offset));
+        w.pos++;
+        low = (low << offset) & 0xffffff;
+        shift = count;
+        count -= 8;
+    }
+    w.low = low << shift;
+    w.count = count;
+    w.range = range;
+}
+
+constexpr int RC_THREADS = 64;
+
+__global__ void __launch_bounds__(RC_THREADS)
+lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order) {
+    const int t = blockIdx.x * RC_THREADS + threadIdx.x;
+    if (t >= nseg) return;
+    SegDesc& sd = segs[order[t]];
+    if (sd.status != ST_OK) return;
+    RcState w;
+    w.low = 0; w.range = 255; w.count = -24; w.pos = 0; w.cap = sd.cap; w.buf = reinterpret_cast<uint8_t*>(sd.stream);
+    rc_put(w, 0, 128);                                               // marker bit
+    const uint4* tok4 = reinterpret_cast<const uint4*>(sd.tokens);
+    const uint32_t ntok = sd.ntok;
+    const uint32_t nfull = ntok / 8;
+    uint4 nxt = nfull ? __ldg(tok4) : make_uint4(0, 0, 0, 0);
+    for (uint32_t i = 0; i < nfull; ++i) {
+        const uint4 cur = nxt;
+        if (i + 1 < nfull) nxt = __ldg(tok4 + i + 1);                // prefetch the next 8 tokens
+        const uint32_t v[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            rc_put(w, (v[k] >> 8) & 1, v[k] & 0xff);
+            rc_put(w, (v[k] >> 24) & 1, (v[k] >> 16) & 0xff);
+        }
+    }
+    const uint16_t* tok = reinterpret_cast<const uint16_t*>(sd.tokens);
+    for (uint32_t i = nfull * 8; i < ntok; ++i) { const uint32_t v = tok[i]; rc_put(w, (v >> 8) & 1, v & 0xff); }
+    for (int i = 0; i < 32; ++i) rc_put(w, 0, 128);                  // vpx_stop_encode
+    if (w.pos > 0 && w.pos < w.cap && (w.buf[w.pos - 1] & 0xe0) == 0xc0) { w.buf[w.pos] = 0; w.pos++; }
+    sd.len = w.pos;
+    if (w.pos >= w.cap) sd.status = ST_OUT_OVERFLOW;
 }
 
 }  // namespace lepb200
