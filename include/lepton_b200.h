@@ -155,6 +155,8 @@ const char* lepb200_host_jpeg_error(const lepb200_jpeg* h);
 int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img);
 int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, int nseg, const uint8_t** data, size_t* len);
 void lepb200_host_jpeg_close(lepb200_jpeg* h);
+/* diagnostic: wall-clock seconds of the host front end alone over a batch with `threads` workers */
+double lepb200_host_frontend_seconds(const lepb200_buffer* jpegs, int n, int threads, int32_t* first_error);
 
 #ifdef __cplusplus
 }

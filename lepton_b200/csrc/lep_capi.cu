@@ -79,7 +79,6 @@ struct lepb200_ctx {
     int grid = 0;
     bool have_batch = false, launched = false, is_encode = true;
     float last_ms = -1.f, last_ms_a = -1.f;
-    uint32_t tokens_per_block = 128;     // token-stream capacity per coded block (worst case is 1420; overflow is reported)
     uint64_t launches = 0;
     uint64_t alg_bytes = 0;
     uint64_t coded_blocks = 0;
@@ -157,7 +156,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     if (nimages <= 0 || !images) { ctx->err = "empty batch"; return LEPB200_ERR_INVALID; }
     ctx->images.assign(nimages, ImageDesc());
     ctx->segs.clear(); ctx->seg_blocks.clear(); ctx->plane_bytes.assign((size_t)nimages * 3, 0);
-    size_t plane_total = 0, stream_total = 0, token_total = 0, row_stride = 0;
+    size_t plane_total = 0, stream_total = 0, row_stride = 0;
     int sidx = 0;
     for (int i = 0; i < nimages; ++i) {
         const lepb200_image& im = images[i];
@@ -194,9 +193,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
                 size_t cap = align_up(nb * 64 + 4096, 256);   // 64 B/block is > 1.5x what q=100 photos need; overflow is reported, never silent
                 sd.stream = stream_total; sd.cap = (uint32_t)cap;
                 stream_total += cap;
-                size_t tcap = align_up(nb * ctx->tokens_per_block + 64, 64);
-                sd.tokens = token_total; sd.tok_cap = (uint32_t)std::min<size_t>(tcap, 0xffffff00u);
-                token_total += tcap * 2;
+                sd.tokens = 0; sd.tok_cap = 0;                    // assigned on the device by the counting pre-pass
             } else {
                 sd.stream = stream_total; sd.cap = (uint32_t)in[sidx].len;
                 stream_total += align_up((size_t)in[sidx].len + 16, 16);
@@ -221,7 +218,6 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
 
     CK(ctx->d_planes.reserve(plane_total));
     CK(ctx->d_streams.reserve(stream_total + 256));
-    if (encode) CK(ctx->d_tokens.reserve(token_total + 256));
     CK(ctx->d_images.reserve(sizeof(ImageDesc) * nimages));
     CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
@@ -230,10 +226,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < ctx->images[i].ncmp; ++c) ctx->images[i].plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
-    for (auto& sd : ctx->segs) {
-        sd.stream += (unsigned long long)(uintptr_t)ctx->d_streams.p;
-        if (encode) sd.tokens += (unsigned long long)(uintptr_t)ctx->d_tokens.p;
-    }
+    for (auto& sd : ctx->segs) sd.stream += (unsigned long long)(uintptr_t)ctx->d_streams.p;
     CK(cudaMemcpyAsync(ctx->d_images.p, ctx->images.data(), sizeof(ImageDesc) * nimages, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_segs.p, ctx->segs.data(), sizeof(SegDesc) * nseg, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_order.p, ctx->order.data(), sizeof(int) * nseg, cudaMemcpyHostToDevice, ctx->stream));
@@ -341,6 +334,18 @@ int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
         for (int c = 0; c < images[i].ncmp; ++c)
             CK(cudaMemcpyAsync(reinterpret_cast<void*>(ctx->images[i].plane[c]), images[i].planes[c], ctx->plane_bytes[(size_t)i * 3 + c],
                                cudaMemcpyHostToDevice, ctx->stream));
+    // pre-pass: per-segment token upper bounds -> exact-fit token arena (sizes depend on the data, so one sync here)
+    const int nseg = (int)ctx->segs.size();
+    lep_count_kernel<<<nseg, CNT_THREADS, 0, ctx->stream>>>(static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg);
+    CK(cudaGetLastError());
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_counter.p) + 64);
+    lep_token_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(static_cast<SegDesc*>(ctx->d_segs.p), nseg, d_total);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    unsigned long long total_tokens = 0;
+    CK(cudaMemcpyAsync(&total_tokens, d_total, sizeof(total_tokens), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->d_tokens.reserve((size_t)total_tokens * 2 + 256));
     ctx->have_batch = true;
     return LEPB200_OK;
 }
@@ -353,11 +358,12 @@ int lepb200_encode_launch(lepb200_ctx* ctx) {
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     lep_encode_kernel<<<ctx->grid, ENC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
         static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
-        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
+        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride,
+        static_cast<uint16_t*>(ctx->d_tokens.p));
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
-    lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(static_cast<SegDesc*>(ctx->d_segs.p), nseg,
-                                                                                              static_cast<const int*>(ctx->d_order.p));
+    lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(
+        static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p), static_cast<const uint16_t*>(ctx->d_tokens.p));
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 2;

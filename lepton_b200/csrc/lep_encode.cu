@@ -76,7 +76,7 @@ __device__ __forceinline__ int coef_entries(int len) { return len == 0 ? 1 : min
 __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
 lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
                   int* __restrict__ work_counter, uint16_t* __restrict__ model_pool, uint8_t* __restrict__ row_pool,
-                  size_t row_pool_stride) {
+                  size_t row_pool_stride, uint16_t* __restrict__ token_base) {
     __shared__ EncShared sm;
     const int lane = lane_id();
     const int warp_in_cta = threadIdx.x >> 5;
@@ -106,7 +106,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
         }
         __syncwarp();
 
-        uint16_t* tokens = reinterpret_cast<uint16_t*>(sd.tokens);
+        uint16_t* tokens = token_base + sd.tokens;               // sd.tokens = offset (in tokens) assigned by the pre-pass
         const uint32_t tok_cap = sd.tok_cap;
         uint32_t ntok = 0;
 
@@ -395,10 +395,10 @@ __device__ __forceinline__ void rc_put(RcState& w, uint32_t bit, uint32_t prob) 
     w.range = range;
 }
 
-constexpr int RC_THREADS = 64;
+constexpr int RC_THREADS = 32;
 
 __global__ void __launch_bounds__(RC_THREADS)
-lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order) {
+lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order, const uint16_t* __restrict__ token_base) {
     const int t = blockIdx.x * RC_THREADS + threadIdx.x;
     if (t >= nseg) return;
     SegDesc& sd = segs[order[t]];
@@ -406,26 +406,112 @@ lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     RcState w;
     w.low = 0; w.range = 255; w.count = -24; w.pos = 0; w.cap = sd.cap; w.buf = reinterpret_cast<uint8_t*>(sd.stream);
     rc_put(w, 0, 128);                                               // marker bit
-    const uint4* tok4 = reinterpret_cast<const uint4*>(sd.tokens);
+    const uint16_t* tok = token_base + sd.tokens;
+    const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
     const uint32_t nfull = ntok / 8;
-    uint4 nxt = nfull ? __ldg(tok4) : make_uint4(0, 0, 0, 0);
-    for (uint32_t i = 0; i < nfull; ++i) {
-        const uint4 cur = nxt;
-        if (i + 1 < nfull) nxt = __ldg(tok4 + i + 1);                // prefetch the next 8 tokens
-        const uint32_t v[4] = {cur.x, cur.y, cur.z, cur.w};
+    // 4-deep software prefetch ring (64 tokens ahead): the chain itself never waits on memory
+    uint4 ring[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ring[k] = (uint32_t)k < nfull ? __ldg(tok4 + k) : make_uint4(0, 0, 0, 0);
+    for (uint32_t i = 0; i < nfull; i += 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            rc_put(w, (v[k] >> 8) & 1, v[k] & 0xff);
-            rc_put(w, (v[k] >> 24) & 1, (v[k] >> 16) & 0xff);
+            if (i + k < nfull) {
+                const uint4 cur = ring[k];
+                if (i + k + 4 < nfull) ring[k] = __ldg(tok4 + i + k + 4);
+                const uint32_t v[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    rc_put(w, (v[m] >> 8) & 1, v[m] & 0xff);
+                    rc_put(w, (v[m] >> 24) & 1, (v[m] >> 16) & 0xff);
+                }
+            }
         }
     }
-    const uint16_t* tok = reinterpret_cast<const uint16_t*>(sd.tokens);
     for (uint32_t i = nfull * 8; i < ntok; ++i) { const uint32_t v = tok[i]; rc_put(w, (v >> 8) & 1, v & 0xff); }
     for (int i = 0; i < 32; ++i) rc_put(w, 0, 128);                  // vpx_stop_encode
     if (w.pos > 0 && w.pos < w.cap && (w.buf[w.pos - 1] & 0xe0) == 0xc0) { w.buf[w.pos] = 0; w.pos++; }
     sd.len = w.pos;
     if (w.pos >= w.cap) sd.status = ST_OUT_OVERFLOW;
+}
+
+// ---- pre-pass: upper bound of the number of tokens each segment will produce -------------------------------
+// Exact for the 7x7 and edge coefficients (their decision counts depend only on the block itself), 22 for the DC
+// (its value depends on the prediction), 12 for the three count fields.  One CTA per segment, one warp per block.
+constexpr int CNT_THREADS = 256;
+
+__global__ void __launch_bounds__(CNT_THREADS)
+lep_count_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg) {
+    const int s = blockIdx.x;
+    if (s >= nseg) return;
+    SegDesc& sd = segs[s];
+    const ImageDesc& g = images[sd.image];
+    const int lane = lane_id(), wid = threadIdx.x >> 5, nw = CNT_THREADS / 32;
+    const uint32_t lt_mask = (1u << lane) - 1;
+    unsigned long long acc = 0;
+    if (sd.status == ST_OK) {
+        uint32_t index = 0;
+        for (;;) {
+            RowSpec rs = row_spec_from_index(index++, g);
+            if (rs.done) break;
+            if (rs.luma_y >= sd.max_y && !sd.is_last) break;
+            if (rs.skip) continue;
+            if (rs.luma_y < sd.min_y) continue;
+            const int c = rs.component, w = g.bch[c];
+            const uint32_t* rowp = reinterpret_cast<const uint32_t*>(g.plane[c]) + (size_t)rs.curr_y * w * 32;
+            for (int x = wid; x < w; x += nw) {
+                const uint32_t cur = rowp[(size_t)x * 32 + lane];
+                const int v0 = h_lo(cur), v1 = h_hi(cur);
+                const int l0 = min(bitlen((uint32_t)iabs(v0) & 0xffff), 11), l1 = min(bitlen((uint32_t)iabs(v1) & 0xffff), 11);
+                // region of each half: 0 = 7x7 (idx < 49), 1 = DC (49), 2 = horizontal edge (50..56), 3 = vertical edge (57..63)
+                const int i0 = 2 * lane, i1 = 2 * lane + 1;
+                const int r0 = i0 < 49 ? 0 : (i0 == 49 ? 1 : (i0 < 57 ? 2 : 3)), r1 = i1 < 49 ? 0 : (i1 == 49 ? 1 : (i1 < 57 ? 2 : 3));
+                int cnt = 0;
+#pragma unroll
+                for (int reg = 0; reg < 4; ++reg) {
+                    if (reg == 1) continue;
+                    const bool n0 = r0 == reg && v0 != 0, n1 = r1 == reg && v1 != 0;
+                    const uint32_t m0 = __ballot_sync(FULL, n0), m1 = __ballot_sync(FULL, n1);
+                    // a coefficient is coded while non-zeros remain at or after it (in index order within its region)
+                    const bool later0 = ((m0 | m1) & ~lt_mask) != 0;                 // this lane or later lanes hold a non-zero
+                    const bool later1 = (m1 >> lane) != 0 || ((m0 >> lane) >> 1) != 0;
+                    if (r0 == reg && later0) cnt += coef_entries(l0);
+                    if (r1 == reg && later1) cnt += coef_entries(l1);
+                }
+                cnt = __reduce_add_sync(FULL, cnt);
+                if (lane == 0) acc += (unsigned long long)cnt + 12 + 22;
+            }
+        }
+    }
+    __shared__ unsigned long long part[CNT_THREADS / 32];
+    if (lane == 0) part[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < nw; ++i) t += part[i];
+        t = (t + 64 + 63) & ~63ull;                              // 128-byte aligned token streams
+        sd.tok_cap = t > 0xffffff00ull ? 0xffffff00u : (uint32_t)t;
+    }
+}
+
+// exclusive scan of tok_cap -> token stream offsets (in tokens); total in *total_out.  Single CTA.
+__global__ void lep_token_offsets_kernel(SegDesc* __restrict__ segs, int nseg, unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long sums[1024];
+    const int t = threadIdx.x, per = (nseg + 1023) / 1024;
+    const int b = t * per, e = min(nseg, b + per);
+    unsigned long long s = 0;
+    for (int i = b; i < e; ++i) s += segs[i].tok_cap;
+    sums[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) { unsigned long long v = sums[i]; sums[i] = run; run += v; }
+        *total_out = run;
+    }
+    __syncthreads();
+    unsigned long long off = sums[t];
+    for (int i = b; i < e; ++i) { segs[i].tokens = off; off += segs[i].tok_cap; }
 }
 
 }  // namespace lepb200

@@ -190,6 +190,29 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     return LEPB200_OK;
 }
 
+// Host front end only (parse + Huffman decode + split selection) over a batch with `threads` workers; returns the
+// wall-clock seconds.  Diagnostic: lets the host stage be profiled without a GPU.
+double lepb200_host_frontend_seconds(const lepb200_buffer* jpegs, int n, int threads, int32_t* first_error) {
+    std::vector<std::unique_ptr<Jpeg>> js(n);
+    std::vector<std::vector<int16_t>> store(n);
+    double t0 = now_s();
+    parallel_for(n, threads, [&](int i) {
+        js[i].reset(new Jpeg());
+        Jpeg& j = *js[i];
+        if (!parse_jpeg(jpegs[i].data, jpegs[i].len, j)) return;
+        size_t total = 0;
+        for (int k = 0; k < j.ncmp; ++k) total += (size_t)j.cmp[k].bc * 64;
+        store[i].assign(total, 0);
+        int16_t* planes[4] = {nullptr, nullptr, nullptr, nullptr};
+        size_t off = 0;
+        for (int k = 0; k < j.ncmp; ++k) { planes[k] = store[i].data() + off; off += (size_t)j.cmp[k].bc * 64; }
+        if (decode_scans(j, planes)) select_splits(j);
+    });
+    double dt = now_s() - t0;
+    if (first_error) { *first_error = 0; for (int i = 0; i < n; ++i) if (js[i]->status) { *first_error = js[i]->status; break; } }
+    return dt;
+}
+
 // ---- staged host-only entry points (no GPU involved): parse + Huffman-decode one JPEG, expose its planes and
 // thread-segment split as a lepb200_image, and assemble the .lep from externally coded segment streams.
 struct lepb200_jpeg {
