@@ -117,34 +117,43 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     c->err.clear();
     double t0 = now_s();
     std::vector<std::unique_ptr<Jpeg>> js(n);
-    parallel_for(n, c->nthreads, [&](int i) {
-        js[i].reset(new Jpeg());
-        parse_jpeg(jpegs[i].data, jpegs[i].len, *js[i]);
-    });
-    // plane arena layout
-    std::vector<size_t> base(n, 0);
+    // plane arena layout from a header-only peek (so that the big per-image buffers are never malloc'ed)
+    std::vector<size_t> base(n, 0), need(n, 0);
     size_t total = 0;
     for (int i = 0; i < n; ++i) {
-        if (js[i]->status) continue;
+        need[i] = peek_plane_bytes(jpegs[i].data, jpegs[i].len);
         base[i] = total;
-        for (int k = 0; k < js[i]->ncmp; ++k) total += (plane_bytes(*js[i], k) + 255) & ~size_t(255);
+        total += need[i];
     }
     if (!reserve_arena(c, total + 256)) { c->err = "pinned host allocation failed"; return LEPB200_ERR_NOMEM; }
     std::vector<std::array<int16_t*, 4>> planes(n);
     std::vector<Splits> splits(n);
     parallel_for(n, c->nthreads, [&](int i) {
+        // the de-stuffed entropy buffer is the only large per-image allocation: recycle it per thread
+        static thread_local std::vector<uint8_t> huff_scratch;
+        static thread_local std::vector<std::pair<uint32_t, uint32_t>> offs_scratch;
+        js[i].reset(new Jpeg());
         Jpeg& j = *js[i];
-        if (j.status) return;
-        uint8_t* p = static_cast<uint8_t*>(c->arena) + base[i];
-        for (int k = 0; k < 4; ++k) planes[i][k] = nullptr;
-        for (int k = 0; k < j.ncmp; ++k) {
-            planes[i][k] = reinterpret_cast<int16_t*>(p);
-            size_t pb = plane_bytes(j, k);
-            memset(p, 0, pb);
-            p += (pb + 255) & ~size_t(255);
+        huff_scratch.clear(); offs_scratch.clear();
+        j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);
+        bool ok = parse_jpeg(jpegs[i].data, jpegs[i].len, j);
+        if (ok) {
+            size_t want = 0;
+            for (int k = 0; k < j.ncmp; ++k) want += (plane_bytes(j, k) + 255) & ~size_t(255);
+            if (want != need[i]) { j.status = NOT_HANDLED; j.error = "plane size peek mismatch"; ok = false; }
         }
-        if (!decode_scans(j, planes[i].data())) return;
-        splits[i] = select_splits(j);
+        if (ok) {
+            uint8_t* p = static_cast<uint8_t*>(c->arena) + base[i];
+            for (int k = 0; k < 4; ++k) planes[i][k] = nullptr;
+            for (int k = 0; k < j.ncmp; ++k) {
+                planes[i][k] = reinterpret_cast<int16_t*>(p);
+                size_t pb = plane_bytes(j, k);
+                memset(p, 0, pb);
+                p += (pb + 255) & ~size_t(255);
+            }
+            if (decode_scans(j, planes[i].data())) splits[i] = select_splits(j);
+        }
+        j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);     // keep the capacity with the thread
     });
     double t1 = now_s();
     // GPU: one batch over all images that survived the front end

@@ -72,7 +72,7 @@ struct Jpeg {
     int jpegtype = 0;                // 1 sequential, 2 progressive
     int width = 0, height = 0, ncmp = 0;
     Component cmp[4];
-    uint16_t qtables[4][64];         // zig-zag order as stored in DQT
+    uint16_t qtables[4][64] = {};    // zig-zag order as stored in DQT
     bool qt_set[4] = {false, false, false, false};
     int mcuh = 0, mcuv = 0, mcuc = 0;
     // ---- decode products (decode_jpeg, jpgcoder.cc:2799-3302)
@@ -84,6 +84,8 @@ struct Jpeg {
 
 // Parse the container level of a JPEG file (everything except Huffman decoding).  `data` starts at SOI.
 bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j);
+// Header-only peek: total (256-byte padded) bytes of all coefficient planes, 0 if unknown.
+size_t peek_plane_bytes(const uint8_t* data, size_t n);
 // Bytes of coefficient plane c (AlignedBlock order).
 inline size_t plane_bytes(const Jpeg& j, int c) { return (size_t)j.cmp[c].bc * 128; }
 // Huffman-decode all scans into planes (pre-zeroed, AlignedBlock order) and record the per-row handoffs.

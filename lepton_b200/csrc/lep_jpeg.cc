@@ -221,6 +221,37 @@ static bool parse_frame(Jpeg& j) {
     return true;
 }
 
+// Quick marker walk up to the first SOF: total bytes of the coefficient planes (0 if not determinable here;
+// the full parse then reports the precise error).  Used to lay out the pinned plane arena before decoding.
+size_t peek_plane_bytes(const uint8_t* data, size_t n) {
+    if (n < 4 || data[0] != 0xFF || data[1] != 0xD8) return 0;
+    size_t pos = 2;
+    while (pos + 4 <= n) {
+        if (data[pos] != 0xFF) return 0;
+        const uint8_t type = data[pos + 1];
+        if (type == 0xD9 || type == 0xDA) return 0;
+        const size_t len = 2 + be16(data + pos + 2);
+        if (type == 0xC0 || type == 0xC1 || type == 0xC2) {
+            if (pos + len > n || len < 10) return 0;
+            const uint8_t* seg = data + pos;
+            const int height = be16(seg + 5), width = be16(seg + 7), nc = seg[9];
+            if (nc < 1 || nc > 4 || len < (size_t)(10 + 3 * nc)) return 0;
+            int hm = 0, vm = 0;
+            for (int c = 0; c < nc; ++c) { hm = std::max(hm, seg[11 + 3 * c] >> 4); vm = std::max(vm, seg[11 + 3 * c] & 15); }
+            if (!hm || !vm) return 0;
+            const size_t mcuv = (size_t)std::ceil((float)height / (float)(8 * vm)), mcuh = (size_t)std::ceil((float)width / (float)(8 * hm));
+            size_t total = 0;
+            for (int c = 0; c < nc; ++c) {
+                const size_t pb = mcuv * (seg[11 + 3 * c] & 15) * mcuh * (seg[11 + 3 * c] >> 4) * 128;
+                total += (pb + 255) & ~size_t(255);
+            }
+            return total;
+        }
+        pos += len;
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Huffman decoding
 // ------------------------------------------------------------------------------------------------
