@@ -140,7 +140,11 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads /* 0 
 void lepb200_codec_destroy(lepb200_codec* codec);
 const char* lepb200_codec_last_error(const lepb200_codec* codec);
 lepb200_ctx* lepb200_codec_ctx(lepb200_codec* codec);
-/* seconds spent by the last call in: JPEG parse + Huffman decode | H2D + kernel + D2H | container writing */
+/* kernel launches issued so far by the codec's contexts */
+uint64_t lepb200_codec_kernel_launches(const lepb200_codec* codec);
+/* files per pipeline chunk (default 512): chunk k+1 is Huffman-decoded while chunk k is on the GPU */
+void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
+/* summed seconds spent by the last call's stages (they overlap): JPEG parse + Huffman decode | H2D + kernel + D2H | container writing */
 void lepb200_codec_last_timing(const lepb200_codec* codec, double* front_s, double* gpu_s, double* back_s);
 /* n JPEG files in, n .lep files out */
 int lepb200_compress_jpegs(lepb200_codec* codec, const lepb200_buffer* jpegs, int n, lepb200_result* out);

@@ -55,7 +55,7 @@ _EXPORTS = [
     "lepb200_encode_fetch", "lepb200_decode_upload", "lepb200_decode_launch", "lepb200_decode_fetch",
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
     "lepb200_device_available", "lepb200_sync", "lepb200_last_symbolise_ms", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
-    "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
+    "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_codec_kernel_launches", "lepb200_codec_set_chunk_images", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
 ]
 
@@ -304,6 +304,10 @@ def _bind_file_api(L):
     L.lepb200_codec_ctx.restype = vp
     L.lepb200_codec_last_timing.argtypes = [vp] + [ctypes.POINTER(ctypes.c_double)] * 3
     L.lepb200_codec_last_timing.restype = None
+    L.lepb200_codec_kernel_launches.argtypes = [vp]
+    L.lepb200_codec_kernel_launches.restype = ctypes.c_uint64
+    L.lepb200_codec_set_chunk_images.argtypes = [vp, ctypes.c_int]
+    L.lepb200_codec_set_chunk_images.restype = None
     L.lepb200_compress_jpegs.argtypes = [vp, ctypes.POINTER(_Buffer), ctypes.c_int, ctypes.POINTER(_Result)]
     L.lepb200_compress_jpegs.restype = ctypes.c_int
     L.lepb200_host_jpeg_open.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
@@ -377,13 +381,15 @@ class HostJpeg:
 class LeptonB200FileCodec:
     """JPEG bytes -> .lep bytes for a batch of files; host threads + one GPU."""
 
-    def __init__(self, device: int = 0, host_threads: int = 0):
+    def __init__(self, device: int = 0, host_threads: int = 0, chunk_images: int = 0):
         self._L = lib()
         _bind_file_api(self._L)
         self._c = ctypes.c_void_p()
         rc = self._L.lepb200_codec_create(ctypes.byref(self._c), device, host_threads)
         if rc != 0:
             raise LeptonB200Error("lepb200_codec_create(device=%d) failed with %d (no CUDA device? there is no CPU fallback)" % (device, rc))
+        if chunk_images > 0:
+            self._L.lepb200_codec_set_chunk_images(self._c, chunk_images)
 
     def close(self):
         if self._c:
@@ -423,4 +429,4 @@ class LeptonB200FileCodec:
 
     @property
     def kernel_launches(self) -> int:
-        return int(self._L.lepb200_kernel_launches(self._L.lepb200_codec_ctx(self._c)))
+        return int(self._L.lepb200_codec_kernel_launches(self._c))

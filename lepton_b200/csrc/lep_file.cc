@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <array>
 #include <algorithm>
@@ -19,10 +20,12 @@
 using namespace lephost;
 
 struct lepb200_codec {
-    lepb200_ctx* ctx = nullptr;
+    lepb200_ctx* ctx = nullptr;     // == ctx2[0]
+    lepb200_ctx* ctx2[2] = {nullptr, nullptr};   // ping-pong contexts: chunk k on ctx2[k & 1]
     int nthreads = 1;
-    void* arena = nullptr;          // pinned host memory for coefficient planes
-    size_t arena_cap = 0;
+    int chunk_images = 512;
+    void* arena[2] = {nullptr, nullptr};          // pinned host memory for coefficient planes, one per in-flight chunk
+    size_t arena_cap[2] = {0, 0};
     std::vector<std::vector<uint8_t>> outputs;
     std::string err;
     // timing of the last call (seconds): parse+huffman, gpu (upload+kernel+fetch), container
@@ -49,14 +52,14 @@ double now_s() {
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
-bool reserve_arena(lepb200_codec* c, size_t bytes) {
-    if (bytes <= c->arena_cap) return true;
-    if (c->arena) lepb200_pinned_free(c->arena);
-    c->arena = nullptr; c->arena_cap = 0;
+bool reserve_arena(lepb200_codec* c, int slot, size_t bytes) {
+    if (bytes <= c->arena_cap[slot]) return true;
+    if (c->arena[slot]) lepb200_pinned_free(c->arena[slot]);
+    c->arena[slot] = nullptr; c->arena_cap[slot] = 0;
     size_t want = bytes + bytes / 8 + 4096;
-    c->arena = lepb200_pinned_alloc(want);
-    if (!c->arena) return false;
-    c->arena_cap = want;
+    c->arena[slot] = lepb200_pinned_alloc(want);
+    if (!c->arena[slot]) return false;
+    c->arena_cap[slot] = want;
     return true;
 }
 
@@ -83,8 +86,12 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
     lepb200_ctx* ctx = nullptr;
     int r = lepb200_create(&ctx, device);
     if (r) return r;
+    lepb200_ctx* ctxb = nullptr;
+    r = lepb200_create(&ctxb, device);
+    if (r) { lepb200_destroy(ctx); return r; }
     lepb200_codec* c = new lepb200_codec();
     c->ctx = ctx;
+    c->ctx2[0] = ctx; c->ctx2[1] = ctxb;
     c->nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     *out = c;
     return LEPB200_OK;
@@ -92,8 +99,9 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
 
 void lepb200_codec_destroy(lepb200_codec* c) {
     if (!c) return;
-    if (c->arena) lepb200_pinned_free(c->arena);
-    lepb200_destroy(c->ctx);
+    for (int s = 0; s < 2; ++s) if (c->arena[s]) lepb200_pinned_free(c->arena[s]);
+    lepb200_destroy(c->ctx2[0]);
+    lepb200_destroy(c->ctx2[1]);
     delete c;
 }
 
@@ -103,6 +111,8 @@ const char* lepb200_codec_last_error(const lepb200_codec* c) {
 }
 
 lepb200_ctx* lepb200_codec_ctx(lepb200_codec* c) { return c ? c->ctx : nullptr; }
+uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) { return c ? lepb200_kernel_launches(c->ctx2[0]) + lepb200_kernel_launches(c->ctx2[1]) : 0; }
+void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 
 void lepb200_codec_last_timing(const lepb200_codec* c, double* front_s, double* gpu_s, double* back_s) {
     if (!c) return;
@@ -112,91 +122,143 @@ void lepb200_codec_last_timing(const lepb200_codec* c, double* front_s, double* 
 }
 
 // JPEG files -> .lep files.  out[i].data points into codec-owned memory, valid until the next call.
+//
+// The batch is processed as a 3-stage software pipeline over chunks of `chunk_images` files:
+//   front (host threads: parse, de-stuff, Huffman decode into a pinned arena, split selection)
+//   gpu   (H2D planes, token pre-pass, kernel A, kernel B, compaction, D2H streams)        -- alternating contexts
+//   back  (host threads: mux + container)
+// so that chunk k+1 is being Huffman-decoded while chunk k is on the GPU and chunk k-1 is being written out.
+namespace {
+
+struct ChunkState {
+    int begin = 0, end = 0;
+    std::vector<std::unique_ptr<Jpeg>> js;
+    std::vector<std::array<int16_t*, 4>> planes;
+    std::vector<Splits> splits;
+    std::vector<lepb200_image> imgs;
+    std::vector<int> idx;                 // image index (relative to begin) of imgs[k]
+    std::vector<int> seg_base;
+    std::vector<lepb200_stream> streams;
+    int gpu_rc = 0;
+};
+
+}  // namespace
+
 int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n, lepb200_result* out) {
     if (!c || !jpegs || !out || n <= 0) return LEPB200_ERR_INVALID;
     c->err.clear();
-    double t0 = now_s();
-    std::vector<std::unique_ptr<Jpeg>> js(n);
-    // plane arena layout from a header-only peek (so that the big per-image buffers are never malloc'ed)
-    std::vector<size_t> base(n, 0), need(n, 0);
-    size_t total = 0;
-    for (int i = 0; i < n; ++i) {
-        need[i] = peek_plane_bytes(jpegs[i].data, jpegs[i].len);
-        base[i] = total;
-        total += need[i];
-    }
-    if (!reserve_arena(c, total + 256)) { c->err = "pinned host allocation failed"; return LEPB200_ERR_NOMEM; }
-    std::vector<std::array<int16_t*, 4>> planes(n);
-    std::vector<Splits> splits(n);
-    parallel_for(n, c->nthreads, [&](int i) {
-        // the de-stuffed entropy buffer is the only large per-image allocation: recycle it per thread
-        static thread_local std::vector<uint8_t> huff_scratch;
-        static thread_local std::vector<std::pair<uint32_t, uint32_t>> offs_scratch;
-        js[i].reset(new Jpeg());
-        Jpeg& j = *js[i];
-        huff_scratch.clear(); offs_scratch.clear();
-        j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);
-        bool ok = parse_jpeg(jpegs[i].data, jpegs[i].len, j);
-        if (ok) {
-            size_t want = 0;
-            for (int k = 0; k < j.ncmp; ++k) want += (plane_bytes(j, k) + 255) & ~size_t(255);
-            if (want != need[i]) { j.status = NOT_HANDLED; j.error = "plane size peek mismatch"; ok = false; }
-        }
-        if (ok) {
-            uint8_t* p = static_cast<uint8_t*>(c->arena) + base[i];
-            for (int k = 0; k < 4; ++k) planes[i][k] = nullptr;
-            for (int k = 0; k < j.ncmp; ++k) {
-                planes[i][k] = reinterpret_cast<int16_t*>(p);
-                size_t pb = plane_bytes(j, k);
-                memset(p, 0, pb);
-                p += (pb + 255) & ~size_t(255);
-            }
-            if (decode_scans(j, planes[i].data())) splits[i] = select_splits(j);
-        }
-        j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);     // keep the capacity with the thread
-    });
-    double t1 = now_s();
-    // GPU: one batch over all images that survived the front end
-    std::vector<lepb200_image> imgs;
-    std::vector<int> idx;
-    int nseg_total = 0;
-    for (int i = 0; i < n; ++i) {
-        if (js[i]->status) continue;
-        lepb200_image im;
-        fill_image(im, *js[i], planes[i].data(), splits[i].selected);
-        imgs.push_back(im);
-        idx.push_back(i);
-        nseg_total += im.nseg;
-    }
-    std::vector<lepb200_stream> streams(nseg_total);
-    if (!imgs.empty()) {
-        int r = lepb200_encode_images(c->ctx, imgs.data(), (int)imgs.size(), streams.data());
-        if (r) return r;
-    }
-    double t2 = now_s();
+    c->t_front = c->t_gpu = c->t_back = 0;
+    const int chunk = std::max(1, c->chunk_images);
+    const int nchunks = (n + chunk - 1) / chunk;
     c->outputs.assign(n, std::vector<uint8_t>());
-    std::vector<int> seg_base(imgs.size() + 1, 0);
-    for (size_t k = 0; k < imgs.size(); ++k) seg_base[k + 1] = seg_base[k] + imgs[k].nseg;
     std::vector<int> status(n, 0);
-    for (int i = 0; i < n; ++i) status[i] = js[i]->status;
-    parallel_for((int)imgs.size(), c->nthreads, [&](int k) {
-        const int i = idx[k];
-        std::vector<std::pair<const uint8_t*, size_t>> ss;
-        for (int s = seg_base[k]; s < seg_base[k + 1]; ++s) {
-            if (streams[s].status) { status[i] = streams[s].status; return; }
-            ss.emplace_back(streams[s].data, (size_t)streams[s].len);
+    std::vector<ChunkState> cs(nchunks);
+    std::mutex tmu;
+
+    auto front = [&](int k) {
+        double t0 = now_s();
+        ChunkState& s = cs[k];
+        s.begin = k * chunk; s.end = std::min(n, s.begin + chunk);
+        const int m = s.end - s.begin;
+        s.js.resize(m); s.planes.resize(m); s.splits.resize(m);
+        std::vector<size_t> base(m, 0), need(m, 0);
+        size_t total = 0;
+        for (int i = 0; i < m; ++i) {
+            need[i] = peek_plane_bytes(jpegs[s.begin + i].data, jpegs[s.begin + i].len);
+            base[i] = total;
+            total += need[i];
         }
-        std::string err;
-        if (!write_lep(*js[i], splits[i], ss, c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
-    });
-    double t3 = now_s();
+        const int slot = k & 1;
+        if (!reserve_arena(c, slot, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+        uint8_t* arena = static_cast<uint8_t*>(c->arena[slot]);
+        parallel_for(m, c->nthreads, [&](int i) {
+            // the de-stuffed entropy buffer is the only large per-image allocation: recycle it per thread
+            static thread_local std::vector<uint8_t> huff_scratch;
+            static thread_local std::vector<std::pair<uint32_t, uint32_t>> offs_scratch;
+            s.js[i].reset(new Jpeg());
+            Jpeg& j = *s.js[i];
+            huff_scratch.clear(); offs_scratch.clear();
+            j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);
+            const lepb200_buffer& in = jpegs[s.begin + i];
+            bool ok = parse_jpeg(in.data, in.len, j);
+            if (ok) {
+                size_t want = 0;
+                for (int q = 0; q < j.ncmp; ++q) want += (plane_bytes(j, q) + 255) & ~size_t(255);
+                if (want != need[i]) { j.status = NOT_HANDLED; j.error = "plane size peek mismatch"; ok = false; }
+            }
+            if (ok) {
+                uint8_t* p = arena + base[i];
+                for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
+                for (int q = 0; q < j.ncmp; ++q) {
+                    s.planes[i][q] = reinterpret_cast<int16_t*>(p);
+                    size_t pb = plane_bytes(j, q);
+                    memset(p, 0, pb);
+                    p += (pb + 255) & ~size_t(255);
+                }
+                if (decode_scans(j, s.planes[i].data())) s.splits[i] = select_splits(j);
+            }
+            j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);     // keep the capacity with the thread
+        });
+        int nseg_total = 0;
+        for (int i = 0; i < m; ++i) {
+            status[s.begin + i] = s.js[i]->status;
+            if (s.js[i]->status) continue;
+            lepb200_image im;
+            fill_image(im, *s.js[i], s.planes[i].data(), s.splits[i].selected);
+            s.imgs.push_back(im);
+            s.idx.push_back(i);
+            nseg_total += im.nseg;
+        }
+        s.streams.resize(nseg_total);
+        s.seg_base.assign(s.imgs.size() + 1, 0);
+        for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_front += now_s() - t0;
+    };
+    auto gpu = [&](int k) {
+        double t0 = now_s();
+        ChunkState& s = cs[k];
+        if (s.gpu_rc == 0 && !s.imgs.empty()) s.gpu_rc = lepb200_encode_images(c->ctx2[k & 1], s.imgs.data(), (int)s.imgs.size(), s.streams.data());
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_gpu += now_s() - t0;
+    };
+    auto back = [&](int k) {
+        double t0 = now_s();
+        ChunkState& s = cs[k];
+        if (s.gpu_rc == 0) {
+            parallel_for((int)s.imgs.size(), std::max(1, c->nthreads / 4), [&](int q) {
+                const int i = s.begin + s.idx[q];
+                std::vector<std::pair<const uint8_t*, size_t>> ss;
+                for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t) {
+                    if (s.streams[t].status) { status[i] = s.streams[t].status; return; }
+                    ss.emplace_back(s.streams[t].data, (size_t)s.streams[t].len);
+                }
+                std::string err;
+                if (!write_lep(*s.js[s.idx[q]], s.splits[s.idx[q]], ss, c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
+            });
+        }
+        s.js.clear(); s.planes.clear(); s.splits.clear();          // release per-chunk host state early
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_back += now_s() - t0;
+    };
+
+    for (int step = 0; step < nchunks + 2; ++step) {
+        std::thread tf, tg, tb;
+        if (step < nchunks) tf = std::thread(front, step);
+        if (step - 1 >= 0 && step - 1 < nchunks) tg = std::thread(gpu, step - 1);
+        if (step - 2 >= 0 && step - 2 < nchunks) tb = std::thread(back, step - 2);
+        if (tf.joinable()) tf.join();
+        if (tg.joinable()) tg.join();
+        if (tb.joinable()) tb.join();
+    }
+    int rc = LEPB200_OK;
+    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k & 1]); }
     for (int i = 0; i < n; ++i) {
         out[i].status = status[i];
         out[i].data = status[i] ? nullptr : c->outputs[i].data();
         out[i].len = status[i] ? 0 : c->outputs[i].size();
     }
-    c->t_front = t1 - t0; c->t_gpu = t2 - t1; c->t_back = t3 - t2;
-    return LEPB200_OK;
+    return rc;
 }
 
 // Host front end only (parse + Huffman decode + split selection) over a batch with `threads` workers; returns the
