@@ -66,6 +66,18 @@ def make_corpus(distinct, seed0=0):
         return list(ex.map(synth_jpeg, range(seed0, seed0 + distinct)))
 
 
+def effective_cores():
+    """CPU cores this process may actually use: affinity mask and cgroup quota, whichever is smaller."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 # ---------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     def __init__(self, gpu_index):
@@ -141,7 +153,7 @@ def run_reference_sample(jpegs, workers):
 
 
 def cpu_baseline(distinct_jpegs, sample_files):
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     jp = [distinct_jpegs[i % len(distinct_jpegs)] for i in range(sample_files)]
     dt, nbytes = run_reference_sample(jp, cores)
     return {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
@@ -160,6 +172,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic images replicated to --images")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads for the e2e stage (0 = effective cores / ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=512)
     args = ap.parse_args()
@@ -183,7 +197,7 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/lepton not built (run __graft_entry__.build() where /root/reference exists)"}))
             return 0
         distinct = make_corpus(min(args.distinct, 32))
-        cores = os.cpu_count() or 1
+        cores = effective_cores()
         sample = [distinct[i % len(distinct)] for i in range(args.cpu_sample)]
         for _ in range(max(args.warmup, 0)):
             run_reference_sample(sample[:max(8, cores // 4)], cores)
@@ -271,12 +285,47 @@ def main():
     total_jpeg = jpeg_bytes * max(world, 1)
     value = total_jpeg * args.steps / dev_s_max / 1e6
 
+    # ---------------------------------------------------------------- decode direction + round trip (same batch)
+    decode = None
+    if not args.no_decode:
+        res = codec.encode_fetch(copy=True)                       # streams of the last launch, on the host
+        streams = [[s.data for s in r] for r in res]
+        # round trip on the distinct images: GPU decode of the GPU-coded streams must give back the input planes
+        from lepton_b200 import CoefImage
+        outs = [CoefImage(ncmp=im.ncmp, mcuv=im.mcuv, bch=im.bch, bcv=im.bcv, qtables_zigzag=im.qtables_zigzag,
+                          planes=[np.full_like(p, 1) for p in im.planes], luma_y_start=im.luma_y_start) for im in base_imgs]
+        st = codec.decode_images(outs, streams[:len(outs)])
+        ok = 0
+        k = 0
+        for im, o in zip(base_imgs, outs):
+            good = all(s == 0 for s in st[k:k + im.nseg]) and all(np.array_equal(a, b) for a, b in zip(im.planes, o.planes))
+            ok += int(good)
+            k += im.nseg
+        # timing: whole batch, streams resident in HBM
+        codec.decode_upload(imgs, streams)
+        for _ in range(max(args.warmup - 1, 1)):
+            codec.decode_launch()
+            codec.sync()
+        barrier()
+        dms = []
+        for _ in range(args.steps):
+            codec.decode_launch()
+            codec.sync()
+            dms.append(codec.last_kernel_ms)
+        barrier()
+        td = torch.tensor([sum(dms) / 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        decode = {"value": jpeg_bytes * max(world, 1) * args.steps / float(td[0]) / 1e6, "unit": "MB/s", "ms_per_step": 1e3 * float(td[0]) / args.steps,
+                  "kernel": "lep_decode_kernel", "roundtrip_pass_rate": ok / len(base_imgs), "roundtrip_images": len(base_imgs),
+                  "decisions_per_s": ndecisions / (sum(dms) / len(dms) / 1e3)}
+
     # ---------------------------------------------------------------- e2e through the file-level C ABI (host buffers)
     e2e = None
     if not args.no_e2e:
         codec.close()
         codec = None
-        threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+        threads = args.host_threads or max(1, effective_cores() // max(world, 1))
         fc = LeptonB200FileCodec(local_rank, host_threads=threads)
         r = fc.compress(jpegs, copy=False)          # warm-up (allocates pinned arenas)
         assert all(st == 0 for st, _ in r)
@@ -331,6 +380,8 @@ def main():
         "wall_ms_per_step": 1e3 * wall_max / args.steps,
         "batch": {"jpeg_bytes": int(jpeg_bytes), "segments": int(nseg), "blocks": int(blocks), "stream_bytes": int(stream_bytes)},
     }
+    if decode:
+        line["decode"] = decode
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and os.path.exists(REF_LEPTON):

@@ -368,7 +368,40 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
 // vpx_start_encode / vpx_write / vpx_stop_encode (src/vp8/encoder/boolwriter.cc:17-35, boolwriter.hh:48-118)
 // over the (probability, bit) tokens produced by kernel A.  Per-thread state; bytes go straight to the segment's
 // stream, the carry walks back over already written 0xff bytes exactly like the reference.
-struct RcState { uint32_t low, range; int count; uint32_t pos, cap; uint8_t* buf; };
+// Output staging: the logical stream is  M[0..mpos) ++ [cache] ++ [0xff]*run  where only M is in memory.  A carry
+// then never has to read memory back in the common case: it increments `cache` and turns the pending 0xff run into
+// zeros.  (The reference walks back over memory, boolwriter.hh:96-105; the byte sequence produced is identical.)
+struct RcState { uint32_t low, range; int count; uint32_t mpos, cap; uint8_t* buf; int cache; uint32_t run; };
+
+__device__ __forceinline__ void rc_store(RcState& w, uint32_t byte) {
+    if (w.mpos < w.cap) asm volatile("st.global.u8 [%0], %1;" ::"l"(w.buf + w.mpos), "r"(byte) : "memory");
+    w.mpos++;
+}
+// rare path: pending 0xff run, a 0xff byte arriving, or a carry into a pending 0xff
+__device__ __forceinline__ void rc_emit_slow(RcState& w, uint32_t b, bool carry) {
+    if (carry) {
+        if (w.cache == 0xff || w.cache < 0) {
+            // carry has to travel into bytes already in memory: same walk as the reference
+            long x = (long)w.mpos - 1;
+            while (x >= 0 && w.buf[x] == 0xff) { w.buf[x] = 0; --x; }
+            if (x >= 0) w.buf[x] += 1;
+            if (w.cache == 0xff) w.cache = 0;
+        } else {
+            w.cache += 1;
+        }
+        if (w.run > 0) {                    // the 0xff run overflows to zeros; the last zero stays pending
+            rc_store(w, (uint32_t)w.cache);
+            for (uint32_t i = 1; i < w.run; ++i) rc_store(w, 0);
+            w.cache = 0;
+            w.run = 0;
+        }
+    }
+    if (b == 0xff) { w.run++; return; }
+    if (w.cache >= 0) rc_store(w, (uint32_t)w.cache);
+    for (uint32_t i = 0; i < w.run; ++i) rc_store(w, 0xff);
+    w.cache = (int)b;
+    w.run = 0;
+}
 
 __device__ __forceinline__ void rc_put(RcState& w, uint32_t bit, uint32_t prob) {
     const uint32_t split = 1 + (((w.range - 1) * prob) >> 8);
@@ -377,19 +410,22 @@ __device__ __forceinline__ void rc_put(RcState& w, uint32_t bit, uint32_t prob) 
     int shift = __clz(range) - 24;
     range <<= shift;
     int count = w.count + shift;
-    if (count >= 0) {
-        const int offset = shift - count;
-        if ((low << (offset - 1)) & 0x80000000u) {
-            int x = (int)w.pos - 1;
-            while (x >= 0 && w.buf[x] == 0xff) { w.buf[x] = 0; --x; }
-            if (x >= 0) w.buf[x] += 1;
-        }
-        if (w.pos < w.cap) w.buf[w.pos] = (uint8_t)(low >> (24 - offset));
-        w.pos++;
-        low = (low << offset) & 0xffffff;
-        shift = count;
-        count -= 8;
+    // byte emission, written so that the common case is straight-line predicated code (lanes of a warp hit it at
+    // different decisions; a real branch here would diverge on almost every decision)
+    const bool emit = count >= 0;
+    const int offset = shift - count;
+    const bool carry = emit && (((low << ((offset - 1) & 31)) & 0x80000000u) != 0);
+    const uint32_t b = (low >> ((24 - offset) & 31)) & 0xff;
+    const bool fast = emit && w.run == 0 && b != 0xff && w.cache >= 0 && !(carry && w.cache == 0xff);
+    if (fast) {
+        if (w.mpos < w.cap) asm volatile("st.global.u8 [%0], %1;" ::"l"(w.buf + w.mpos), "r"((uint32_t)w.cache + (carry ? 1u : 0u)) : "memory");
+        w.mpos++;
+        w.cache = (int)b;
     }
+    if (emit && !fast) rc_emit_slow(w, b, carry);
+    low = emit ? ((low << (offset & 31)) & 0xffffff) : low;
+    shift = emit ? count : shift;
+    count = emit ? count - 8 : count;
     w.low = low << shift;
     w.count = count;
     w.range = range;
@@ -404,36 +440,40 @@ lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     SegDesc& sd = segs[order[t]];
     if (sd.status != ST_OK) return;
     RcState w;
-    w.low = 0; w.range = 255; w.count = -24; w.pos = 0; w.cap = sd.cap; w.buf = reinterpret_cast<uint8_t*>(sd.stream);
+    w.low = 0; w.range = 255; w.count = -24; w.mpos = 0; w.cap = sd.cap; w.buf = reinterpret_cast<uint8_t*>(sd.stream);
+    w.cache = -1; w.run = 0;
     rc_put(w, 0, 128);                                               // marker bit
     const uint16_t* tok = token_base + sd.tokens;
     const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
     const uint32_t nfull = ntok / 8;
-    // 4-deep software prefetch ring (64 tokens ahead): the chain itself never waits on memory
-    uint4 ring[4];
+    // 4-deep software prefetch (32 tokens ahead) so that the chain never waits on memory
+    uint4 r0 = nfull > 0 ? __ldg(tok4 + 0) : make_uint4(0, 0, 0, 0);
+    uint4 r1 = nfull > 1 ? __ldg(tok4 + 1) : make_uint4(0, 0, 0, 0);
+    uint4 r2 = nfull > 2 ? __ldg(tok4 + 2) : make_uint4(0, 0, 0, 0);
+    uint4 r3 = nfull > 3 ? __ldg(tok4 + 3) : make_uint4(0, 0, 0, 0);
+    for (uint32_t i = 0; i < nfull; ++i) {
+        const uint4 cur = r0;
+        r0 = r1; r1 = r2; r2 = r3;
+        r3 = i + 4 < nfull ? __ldg(tok4 + i + 4) : make_uint4(0, 0, 0, 0);
+        const uint32_t v[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ring[k] = (uint32_t)k < nfull ? __ldg(tok4 + k) : make_uint4(0, 0, 0, 0);
-    for (uint32_t i = 0; i < nfull; i += 4) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < nfull) {
-                const uint4 cur = ring[k];
-                if (i + k + 4 < nfull) ring[k] = __ldg(tok4 + i + k + 4);
-                const uint32_t v[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    rc_put(w, (v[m] >> 8) & 1, v[m] & 0xff);
-                    rc_put(w, (v[m] >> 24) & 1, (v[m] >> 16) & 0xff);
-                }
-            }
+        for (int m = 0; m < 4; ++m) {
+            rc_put(w, (v[m] >> 8) & 1, v[m] & 0xff);
+            rc_put(w, (v[m] >> 24) & 1, (v[m] >> 16) & 0xff);
         }
     }
+#pragma unroll 1
     for (uint32_t i = nfull * 8; i < ntok; ++i) { const uint32_t v = tok[i]; rc_put(w, (v >> 8) & 1, v & 0xff); }
+#pragma unroll 1
     for (int i = 0; i < 32; ++i) rc_put(w, 0, 128);                  // vpx_stop_encode
-    if (w.pos > 0 && w.pos < w.cap && (w.buf[w.pos - 1] & 0xe0) == 0xc0) { w.buf[w.pos] = 0; w.pos++; }
-    sd.len = w.pos;
-    if (w.pos >= w.cap) sd.status = ST_OUT_OVERFLOW;
+    // drain the staging, then the trailing-marker rule of vpx_stop_encode (boolwriter.cc:32-34)
+    uint32_t last = 0;
+    if (w.cache >= 0) { rc_store(w, (uint32_t)w.cache); last = (uint32_t)w.cache; }
+    for (uint32_t i = 0; i < w.run; ++i) { rc_store(w, 0xff); last = 0xff; }
+    if (w.mpos > 0 && (last & 0xe0) == 0xc0) rc_store(w, 0);
+    sd.len = w.mpos;
+    if (w.mpos >= w.cap) sd.status = ST_OUT_OVERFLOW;
 }
 
 // ---- pre-pass: upper bound of the number of tokens each segment will produce -------------------------------

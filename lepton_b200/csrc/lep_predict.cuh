@@ -5,6 +5,17 @@
 
 namespace lepb200 {
 
+// Truncating signed division n / d for |n| < 2^24, 1 <= d < 2^16 without the ~40-instruction integer divide:
+// float reciprocal estimate + one-step correction (exact: the estimate is off by at most one).
+__device__ __forceinline__ int div_trunc_small(int n, int d) {
+    const uint32_t a = (uint32_t)(n < 0 ? -n : n);
+    uint32_t q = (uint32_t)(__uint2float_rz(a) * __frcp_rn(__uint2float_rz((uint32_t)d)));
+    int rem = (int)a - (int)(q * (uint32_t)d);
+    if (rem < 0) { --q; rem += d; }
+    if (rem >= d) { ++q; }
+    return n < 0 ? -(int)q : (int)q;
+}
+
 // 8-point row pass of the reference IDCT (src/lepton/idct.cc:41-111), int32 wrap-around arithmetic.
 __device__ __forceinline__ void idct_row(const int32_t in[8], int32_t out[8]) {
     const int32_t w1 = 2841, w2 = 2676, w3 = 2408, w5 = 1609, w6 = 1108, w7 = 565, r2 = 181;
@@ -142,7 +153,7 @@ __device__ __forceinline__ DcPred warp_predict_dc(const int16_t* pix, int left_v
         if (iabs(a0) < iabs(a1)) far_afield = a0;
         r.unc2 = far_afield >> 3;
     }
-    r.pred = ((avgmed / q0) + 4) >> 3;
+    r.pred = (div_trunc_small(avgmed, q0) + 4) >> 3;            // |avgmed| < 2^20
     return r;
 }
 
@@ -176,7 +187,10 @@ __device__ __forceinline__ int lak_pred(const int16_t* cur, const int16_t* nb, c
         int32_t t = (int32_t)cur[first + i * step] + ((i & 1) ? (int32_t)nb[first + i * step] : -(int32_t)nb[first + i * step]);
         pred -= (uint32_t)icos[i] * (uint32_t)t;
     }
-    return (int32_t)pred / icos[0];
+    // C division by icos[0] = 8192 * q (model.hh:957,1064): trunc(trunc(p / 8192) / q) == trunc(p / (8192 q))
+    const int32_t p = (int32_t)pred;
+    const int32_t t = (p + ((p >> 31) & 8191)) >> 13;
+    return div_trunc_small(t, icos[0] >> 13);
 }
 
 }  // namespace lepb200
