@@ -148,6 +148,8 @@ void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
 void lepb200_codec_last_timing(const lepb200_codec* codec, double* front_s, double* gpu_s, double* back_s);
 /* n JPEG files in, n .lep files out */
 int lepb200_compress_jpegs(lepb200_codec* codec, const lepb200_buffer* jpegs, int n, lepb200_result* out);
+/* n .lep files in, n JPEG files out (byte-identical to the originals) */
+int lepb200_decompress_leps(lepb200_codec* codec, const lepb200_buffer* leps, int n, lepb200_result* out);
 
 /* ---- the host stages on their own (no GPU): JPEG front end and .lep assembly around an external coder.
  * lepb200_host_jpeg_open parses + Huffman-decodes one JPEG (read_jpeg + decode_jpeg, jpgcoder.cc:2270,2799) and
@@ -159,6 +161,15 @@ const char* lepb200_host_jpeg_error(const lepb200_jpeg* h);
 int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img);
 int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, int nseg, const uint8_t** data, size_t* len);
 void lepb200_host_jpeg_close(lepb200_jpeg* h);
+/* decode-side host stages: container parse + demux (read_ujpg, jpgcoder.cc:4117), geometry/splits, segment streams, and
+ * JPEG re-creation from caller-provided planes (recode_baseline_jpeg, recoder.cc:694) */
+typedef struct lepb200_lep lepb200_lep;
+int lepb200_host_lep_open(const uint8_t* data, size_t len, lepb200_lep** out, int32_t* status);
+const char* lepb200_host_lep_error(const lepb200_lep* h);
+int lepb200_host_lep_image(lepb200_lep* h, lepb200_image* img);
+int lepb200_host_lep_stream(lepb200_lep* h, int seg, const uint8_t** data, size_t* len);
+int lepb200_host_lep_recode(lepb200_lep* h, const int16_t* const planes[3], const uint8_t** data, size_t* len);
+void lepb200_host_lep_close(lepb200_lep* h);
 /* diagnostic: wall-clock seconds of the host front end alone over a batch with `threads` workers */
 double lepb200_host_frontend_seconds(const lepb200_buffer* jpegs, int n, int threads, int32_t* first_error);
 

@@ -57,6 +57,8 @@ _EXPORTS = [
     "lepb200_device_available", "lepb200_sync", "lepb200_last_symbolise_ms", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
     "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_codec_kernel_launches", "lepb200_codec_set_chunk_images", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
+    "lepb200_decompress_leps", "lepb200_host_lep_open", "lepb200_host_lep_error", "lepb200_host_lep_image",
+    "lepb200_host_lep_stream", "lepb200_host_lep_recode", "lepb200_host_lep_close", "lepb200_host_frontend_seconds",
 ]
 
 
@@ -320,6 +322,20 @@ def _bind_file_api(L):
     L.lepb200_host_jpeg_write_lep.restype = ctypes.c_int
     L.lepb200_host_jpeg_close.argtypes = [vp]
     L.lepb200_host_jpeg_close.restype = None
+    L.lepb200_decompress_leps.argtypes = [vp, ctypes.POINTER(_Buffer), ctypes.c_int, ctypes.POINTER(_Result)]
+    L.lepb200_decompress_leps.restype = ctypes.c_int
+    L.lepb200_host_lep_open.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
+    L.lepb200_host_lep_open.restype = ctypes.c_int
+    L.lepb200_host_lep_error.argtypes = [vp]
+    L.lepb200_host_lep_error.restype = ctypes.c_char_p
+    L.lepb200_host_lep_image.argtypes = [vp, ctypes.POINTER(_Image)]
+    L.lepb200_host_lep_image.restype = ctypes.c_int
+    L.lepb200_host_lep_stream.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.lepb200_host_lep_stream.restype = ctypes.c_int
+    L.lepb200_host_lep_recode.argtypes = [vp, ctypes.c_void_p * 3, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.lepb200_host_lep_recode.restype = ctypes.c_int
+    L.lepb200_host_lep_close.argtypes = [vp]
+    L.lepb200_host_lep_close.restype = None
     L._file_api_bound = True
 
 
@@ -378,6 +394,66 @@ class HostJpeg:
         return ctypes.string_at(d, n.value)
 
 
+class HostLep:
+    """Decode-side host stages only (no GPU): parse a .lep, expose geometry / splits / segment streams, and
+    re-create the JPEG bytes from coefficient planes."""
+
+    def __init__(self, data: bytes):
+        self._L = lib()
+        _bind_file_api(self._L)
+        self._h = ctypes.c_void_p()
+        st = ctypes.c_int32()
+        self._data = data
+        self._L.lepb200_host_lep_open(data, len(data), ctypes.byref(self._h), ctypes.byref(st))
+        self.status = st.value
+        self.error = self._L.lepb200_host_lep_error(self._h).decode()
+
+    def close(self):
+        if self._h:
+            self._L.lepb200_host_lep_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def coef_image(self) -> CoefImage:
+        """Geometry + splits with freshly allocated (zero) planes to decode into."""
+        if self.status:
+            raise LeptonB200Error(".lep reader refused the file: status %d (%s)" % (self.status, self.error))
+        im = _Image()
+        if self._L.lepb200_host_lep_image(self._h, ctypes.byref(im)) != 0:
+            raise LeptonB200Error("host_lep_image failed")
+        planes = [np.zeros((im.bch[c] * im.bcv[c], 64), dtype=np.int16) for c in range(im.ncmp)]
+        return CoefImage(ncmp=im.ncmp, mcuv=im.mcuv, bch=[im.bch[c] for c in range(im.ncmp)],
+                         bcv=[im.bcv[c] for c in range(im.ncmp)],
+                         qtables_zigzag=[[im.qtable_zigzag[c][i] for i in range(64)] for c in range(im.ncmp)],
+                         planes=planes, luma_y_start=[im.luma_y_start[s] for s in range(im.nseg)])
+
+    def streams(self, nseg: int):
+        out = []
+        for s in range(nseg):
+            d, n = ctypes.c_void_p(), ctypes.c_size_t()
+            if self._L.lepb200_host_lep_stream(self._h, s, ctypes.byref(d), ctypes.byref(n)) != 0:
+                raise LeptonB200Error("host_lep_stream failed")
+            out.append(ctypes.string_at(d, n.value))
+        return out
+
+    def recode(self, planes) -> bytes:
+        arr = (ctypes.c_void_p * 3)()
+        keep = []
+        for i, p in enumerate(planes):
+            q = np.ascontiguousarray(p, dtype=np.int16)
+            keep.append(q)
+            arr[i] = q.ctypes.data
+        d, n = ctypes.c_void_p(), ctypes.c_size_t()
+        if self._L.lepb200_host_lep_recode(self._h, arr, ctypes.byref(d), ctypes.byref(n)) != 0:
+            raise LeptonB200Error("recode failed: %s" % self._L.lepb200_host_lep_error(self._h).decode())
+        return ctypes.string_at(d, n.value)
+
+
 class LeptonB200FileCodec:
     """JPEG bytes -> .lep bytes for a batch of files; host threads + one GPU."""
 
@@ -416,6 +492,26 @@ class LeptonB200FileCodec:
         rc = self._L.lepb200_compress_jpegs(self._c, bufs, n, res)
         if rc != 0:
             raise LeptonB200Error("compress_jpegs failed (%d): %s" % (rc, self._L.lepb200_codec_last_error(self._c).decode()))
+        out = []
+        for i in range(n):
+            r = res[i]
+            out.append((r.status, ctypes.string_at(r.data, r.len) if (copy and r.len) else (b"" if copy else r.len)))
+        return out
+
+    def decompress(self, leps: Sequence[bytes], copy: bool = True):
+        """.lep bytes -> JPEG bytes; -> list of (status, jpeg_bytes)."""
+        n = len(leps)
+        bufs = (_Buffer * n)()
+        keep = []
+        for i, j in enumerate(leps):
+            b = np.frombuffer(j, dtype=np.uint8)
+            keep.append(b)
+            bufs[i].data = b.ctypes.data
+            bufs[i].len = len(b)
+        res = (_Result * n)()
+        rc = self._L.lepb200_decompress_leps(self._c, bufs, n, res)
+        if rc != 0:
+            raise LeptonB200Error("decompress_leps failed (%d): %s" % (rc, self._L.lepb200_codec_last_error(self._c).decode()))
         out = []
         for i in range(n):
             r = res[i]

@@ -261,6 +261,158 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     return rc;
 }
 
+// .lep files -> JPEG files (inverse of lepb200_compress_jpegs), same 3-stage chunk pipeline:
+//   front (host: container parse, zlib inflate, demux)  |  gpu (H2D streams, decode kernel, D2H planes)  |
+//   back (host: Huffman re-encode + byte stuffing + header/garbage re-assembly)
+int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n, lepb200_result* out) {
+    if (!c || !leps || !out || n <= 0) return LEPB200_ERR_INVALID;
+    c->err.clear();
+    c->t_front = c->t_gpu = c->t_back = 0;
+    const int chunk = std::max(1, c->chunk_images);
+    const int nchunks = (n + chunk - 1) / chunk;
+    c->outputs.assign(n, std::vector<uint8_t>());
+    std::vector<int> status(n, 0);
+    struct DChunk {
+        int begin = 0, end = 0;
+        std::vector<std::unique_ptr<LepFile>> lf;
+        std::vector<std::array<int16_t*, 4>> planes;
+        std::vector<lepb200_image> imgs;
+        std::vector<int> idx;
+        std::vector<lepb200_stream> streams;
+        std::vector<int32_t> seg_status;
+        std::vector<int> seg_base;
+        int gpu_rc = 0;
+    };
+    std::vector<DChunk> cs(nchunks);
+    std::mutex tmu;
+    auto front = [&](int k) {
+        double t0 = now_s();
+        DChunk& s = cs[k];
+        s.begin = k * chunk; s.end = std::min(n, s.begin + chunk);
+        const int m = s.end - s.begin;
+        s.lf.resize(m); s.planes.resize(m);
+        parallel_for(m, c->nthreads, [&](int i) {
+            s.lf[i].reset(new LepFile());
+            read_lep(leps[s.begin + i].data, leps[s.begin + i].len, *s.lf[i]);
+        });
+        size_t total = 0;
+        std::vector<size_t> base(m, 0);
+        for (int i = 0; i < m; ++i) {
+            status[s.begin + i] = s.lf[i]->status;
+            if (s.lf[i]->status) continue;
+            base[i] = total;
+            for (int q = 0; q < s.lf[i]->j.ncmp; ++q) total += (plane_bytes(s.lf[i]->j, q) + 255) & ~size_t(255);
+        }
+        if (!reserve_arena(c, k & 1, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+        uint8_t* arena = static_cast<uint8_t*>(c->arena[k & 1]);
+        int nseg_total = 0;
+        for (int i = 0; i < m; ++i) {
+            LepFile& lf = *s.lf[i];
+            if (lf.status) continue;
+            const Jpeg& j = lf.j;
+            uint8_t* p = arena + base[i];
+            for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
+            for (int q = 0; q < j.ncmp; ++q) { s.planes[i][q] = reinterpret_cast<int16_t*>(p); p += (plane_bytes(j, q) + 255) & ~size_t(255); }
+            lepb200_image im;
+            fill_image(im, j, s.planes[i].data(), lf.handoffs);
+            s.imgs.push_back(im);
+            s.idx.push_back(i);
+            for (int t = 0; t < lf.nseg; ++t) {
+                lepb200_stream st;
+                memset(&st, 0, sizeof(st));
+                st.data = lf.streams[t].data();
+                st.len = lf.streams[t].size();
+                s.streams.push_back(st);
+            }
+            nseg_total += lf.nseg;
+        }
+        s.seg_status.assign(nseg_total, 0);
+        s.seg_base.assign(s.imgs.size() + 1, 0);
+        for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_front += now_s() - t0;
+    };
+    auto gpu = [&](int k) {
+        double t0 = now_s();
+        DChunk& s = cs[k];
+        if (s.gpu_rc == 0 && !s.imgs.empty())
+            s.gpu_rc = lepb200_decode_images(c->ctx2[k & 1], s.imgs.data(), (int)s.imgs.size(), s.streams.data(), s.seg_status.data());
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_gpu += now_s() - t0;
+    };
+    auto back = [&](int k) {
+        double t0 = now_s();
+        DChunk& s = cs[k];
+        if (s.gpu_rc == 0) {
+            parallel_for((int)s.imgs.size(), c->nthreads, [&](int q) {
+                const int li = s.idx[q], i = s.begin + li;
+                for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t)
+                    if (s.seg_status[t]) { status[i] = s.seg_status[t]; return; }
+                std::string err;
+                if (!recode_baseline(*s.lf[li], s.planes[li].data(), c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
+            });
+        }
+        s.lf.clear();
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_back += now_s() - t0;
+    };
+    for (int step = 0; step < nchunks + 2; ++step) {
+        std::thread tf, tg, tb;
+        if (step < nchunks) tf = std::thread(front, step);
+        if (step - 1 >= 0 && step - 1 < nchunks) tg = std::thread(gpu, step - 1);
+        if (step - 2 >= 0 && step - 2 < nchunks) tb = std::thread(back, step - 2);
+        if (tf.joinable()) tf.join();
+        if (tg.joinable()) tg.join();
+        if (tb.joinable()) tb.join();
+    }
+    int rc = LEPB200_OK;
+    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k & 1]); }
+    for (int i = 0; i < n; ++i) {
+        out[i].status = status[i];
+        out[i].data = status[i] ? nullptr : c->outputs[i].data();
+        out[i].len = status[i] ? 0 : c->outputs[i].size();
+    }
+    return rc;
+}
+
+// ---- host-only decode-side stages (no GPU): parse a .lep, expose geometry/streams, re-create the JPEG from planes
+struct lepb200_lep {
+    LepFile lf;
+    std::vector<uint8_t> out;
+};
+int lepb200_host_lep_open(const uint8_t* data, size_t len, lepb200_lep** out, int32_t* status) {
+    if (!out || !data) return LEPB200_ERR_INVALID;
+    lepb200_lep* h = new lepb200_lep();
+    *out = h;
+    read_lep(data, len, h->lf);
+    if (status) *status = h->lf.status;
+    return LEPB200_OK;
+}
+const char* lepb200_host_lep_error(const lepb200_lep* h) { return h ? h->lf.error.c_str() : "null"; }
+// geometry + splits (planes pointers are left null: the caller provides the planes)
+int lepb200_host_lep_image(lepb200_lep* h, lepb200_image* img) {
+    if (!h || !img || h->lf.status) return LEPB200_ERR_INVALID;
+    int16_t* none[4] = {nullptr, nullptr, nullptr, nullptr};
+    fill_image(*img, h->lf.j, none, h->lf.handoffs);
+    return LEPB200_OK;
+}
+int lepb200_host_lep_stream(lepb200_lep* h, int seg, const uint8_t** data, size_t* len) {
+    if (!h || h->lf.status || seg < 0 || seg >= h->lf.nseg) return LEPB200_ERR_INVALID;
+    *data = h->lf.streams[seg].data();
+    *len = h->lf.streams[seg].size();
+    return LEPB200_OK;
+}
+int lepb200_host_lep_recode(lepb200_lep* h, const int16_t* const planes[3], const uint8_t** data, size_t* len) {
+    if (!h || h->lf.status) return LEPB200_ERR_INVALID;
+    const int16_t* p4[4] = {planes[0], planes[1], planes[2], nullptr};
+    std::string err;
+    if (!recode_baseline(h->lf, p4, h->out, err)) { h->lf.error = err; return LEPB200_ERR_INVALID; }
+    *data = h->out.data();
+    *len = h->out.size();
+    return LEPB200_OK;
+}
+void lepb200_host_lep_close(lepb200_lep* h) { delete h; }
+
 // Host front end only (parse + Huffman decode + split selection) over a batch with `threads` workers; returns the
 // wall-clock seconds.  Diagnostic: lets the host stage be profiled without a GPU.
 double lepb200_host_frontend_seconds(const lepb200_buffer* jpegs, int n, int threads, int32_t* first_error) {

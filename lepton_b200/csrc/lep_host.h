@@ -84,6 +84,8 @@ struct Jpeg {
 
 // Parse the container level of a JPEG file (everything except Huffman decoding).  `data` starts at SOI.
 bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j);
+// Frame geometry + quantisation tables from j.hdr (setup_imginfo_jpg); used by both directions.
+bool parse_frame(Jpeg& j);
 // Header-only peek: total (256-byte padded) bytes of all coefficient planes, 0 if unknown.
 size_t peek_plane_bytes(const uint8_t* data, size_t n);
 // Bytes of coefficient plane c (AlignedBlock order).
@@ -113,6 +115,7 @@ struct LepFile {
     Jpeg j;                          // hdr, grb, rst_cnt/rst_err, padbit, frame filled from the header blob
     std::vector<Handoff> handoffs;   // as serialised (luma_y_start, segment_size, overhang, last_dc)
     bool has_eee = false;
+    bool rst_cnt_set = false;        // CRS section present (jpgcoder.cc:4241)
     uint32_t eee[7] = {0};
     std::vector<std::vector<uint8_t>> streams;   // demuxed per-segment bool-coder streams
     int status = OK;

@@ -61,7 +61,7 @@ bool HuffTable::build() {
 // ------------------------------------------------------------------------------------------------
 // read_jpeg: split the file into header segments / de-stuffed entropy data / trailing garbage
 // ------------------------------------------------------------------------------------------------
-static bool parse_frame(Jpeg& j);
+bool parse_frame(Jpeg& j);
 
 bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j) {
     if (n < 4 || data[0] != 0xFF || data[1] != 0xD8) return fail(j, UNSUPPORTED_JPEG, "not a JPEG (no SOI)");
@@ -144,7 +144,7 @@ bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j) {
 }
 
 // setup_imginfo_jpg + the SOF/DQT cases of parse_jfif_jpg
-static bool parse_frame(Jpeg& j) {
+bool parse_frame(Jpeg& j) {
     size_t hpos = 0;
     const std::vector<uint8_t>& h = j.hdr;
     while (hpos + 4 <= h.size()) {

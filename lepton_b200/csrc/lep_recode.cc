@@ -1,0 +1,315 @@
+// lep_recode.cc -- decode-side host halves: .lep container reader (read_ujpg, jpgcoder.cc:4117-4362; fixed header
+// :2140-2176; MuxReader, src/io/MuxReader.hh:230-283; ThreadHandoff::deserialize, thread_handoff.cc:4-39) and the
+// baseline JPEG re-creation from coefficient planes (recode_baseline_jpeg, src/lepton/recoder.cc:694-889;
+// recode_one_mcu_row :316-410; encode_block_seq :245-313; 0xff stuffing :144-185).
+//
+// The reference re-encodes every thread-segment independently from its handoff (overhang bits + last DCs) and
+// concatenates; encoding the scan front to back from the complete planes yields the same bytes, so that is what
+// is done here (one host thread per file; files are processed in parallel by the caller).
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "lep_host.h"
+
+namespace lephost {
+
+namespace {
+inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+bool lfail(LepFile& lf, int st, const char* msg) { lf.status = st; lf.error = msg; return false; }
+
+// AlignedBlock index of each zig-zag position (src/vp8/util/aligned_block.hh:56-65)
+const uint8_t k_zigzag_to_aligned[64] = {
+    49, 50, 57, 58, 0, 51, 52, 1, 2, 59, 60, 3, 4, 5, 53, 54, 6, 7, 8, 9, 61, 62, 10, 11,
+    12, 13, 14, 55, 56, 15, 16, 17, 18, 19, 20, 63, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32,
+    33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48};
+}  // namespace
+
+bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
+    if (n < 28 + 3 + 4 || d[0] != 0xCF || d[1] != 0x84) return lfail(lf, VERSION_UNSUPPORTED, "not a .lep file");
+    lf.version = d[2]; lf.flag = d[3]; lf.nseg = d[4];
+    if (lf.version != 1) return lfail(lf, NOT_HANDLED, "only version 1 (zlib header) containers are handled");
+    if (lf.flag == 'Y') return lfail(lf, NOT_HANDLED, "-startbyte slices are not handled");
+    lf.jpeg_size = rd32(d + 20);
+    const uint32_t zlen = rd32(d + 24);
+    if ((size_t)28 + zlen + 3 + 4 > n) return lfail(lf, SHORT_READ, "truncated .lep");
+    // inflate the header blob
+    std::vector<uint8_t> blob;
+    {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit(&zs) != Z_OK) return lfail(lf, ASSERTION_FAILURE, "inflateInit failed");
+        zs.next_in = const_cast<uint8_t*>(d + 28); zs.avail_in = zlen;
+        blob.resize(std::max<size_t>(4096, (size_t)zlen * 4));
+        size_t have = 0;
+        int ret;
+        do {
+            if (have == blob.size()) blob.resize(blob.size() * 2);
+            zs.next_out = blob.data() + have; zs.avail_out = (uInt)(blob.size() - have);
+            ret = inflate(&zs, Z_NO_FLUSH);
+            have = blob.size() - zs.avail_out;
+        } while (ret == Z_OK);
+        inflateEnd(&zs);
+        if (ret != Z_STREAM_END) return lfail(lf, ASSERTION_FAILURE, "Data not properly zlib coded");
+        blob.resize(have);
+    }
+    size_t p = 0;
+    auto need = [&](size_t k) { return p + k <= blob.size(); };
+    if (!need(7) || memcmp(&blob[p], "HDR", 3)) return lfail(lf, UNSUPPORTED_JPEG, "HDR marker not found");
+    const uint32_t hdrs = rd32(&blob[p + 3]);
+    p += 7;
+    if (!need(hdrs)) return lfail(lf, SHORT_READ, "short HDR");
+    Jpeg& j = lf.j;
+    j.hdr.assign(blob.begin() + p, blob.begin() + p + hdrs);
+    p += hdrs;
+    if (!parse_frame(j)) { lf.status = j.status; lf.error = j.error; return false; }
+    if (!need(4) || memcmp(&blob[p], "P0D", 3)) return lfail(lf, NOT_HANDLED, "P0D marker not found (legacy PAD not handled)");
+    j.padbit = (int8_t)blob[p + 3];
+    p += 4;
+    j.grb.clear();
+    bool have_grb = false;
+    while (need(3)) {
+        const uint8_t* m = &blob[p];
+        if (!memcmp(m, "CRS", 3)) {
+            if (!need(7)) return lfail(lf, SHORT_READ, "short CRS");
+            uint32_t k = rd32(m + 3);
+            if (!need(7 + 4 * (size_t)k)) return lfail(lf, SHORT_READ, "short CRS");
+            j.rst_cnt.resize(k);
+            for (uint32_t i = 0; i < k; ++i) j.rst_cnt[i] = rd32(m + 7 + 4 * i);
+            lf.rst_cnt_set = true;
+            p += 7 + 4 * (size_t)k;
+        } else if (m[0] == 'H' && m[1] == 'H') {
+            const int k = m[2];
+            if (!need(3 + 16 * (size_t)k)) return lfail(lf, VERSION_UNSUPPORTED, "short handoff table");
+            for (int i = 0; i < k; ++i) {
+                const uint8_t* r = m + 3 + 16 * i;
+                Handoff h;
+                h.luma_y_start = (uint16_t)(r[0] | (r[1] << 8));
+                h.segment_size = rd32(r + 2);
+                h.overhang_byte = r[6]; h.num_overhang_bits = r[7];
+                for (int q = 0; q < 4; ++q) h.last_dc[q] = (int16_t)(r[8 + 2 * q] | (r[9 + 2 * q] << 8));
+                lf.handoffs.push_back(h);
+            }
+            for (size_t i = 1; i < lf.handoffs.size(); ++i) lf.handoffs[i - 1].luma_y_end = lf.handoffs[i].luma_y_start;
+            p += 3 + 16 * (size_t)k;
+        } else if (!memcmp(m, "FRS", 3)) {
+            if (!need(7)) return lfail(lf, SHORT_READ, "short FRS");
+            uint32_t k = rd32(m + 3);
+            if (!need(7 + (size_t)k)) return lfail(lf, SHORT_READ, "short FRS");
+            j.rst_err.assign(m + 7, m + 7 + k);
+            p += 7 + (size_t)k;
+        } else if (!memcmp(m, "GRB", 3)) {
+            if (!need(7)) return lfail(lf, SHORT_READ, "short GRB");
+            uint32_t k = rd32(m + 3);
+            if (!need(7 + (size_t)k)) return lfail(lf, SHORT_READ, "short GRB");
+            j.grb.assign(m + 7, m + 7 + k);
+            have_grb = true;
+            p += 7 + (size_t)k;
+        } else if (!memcmp(m, "EEE", 3)) {
+            if (!need(31)) return lfail(lf, SHORT_READ, "short EEE");
+            lf.has_eee = true;
+            for (int i = 0; i < 7; ++i) lf.eee[i] = rd32(m + 3 + 4 * i);
+            p += 31;
+        } else if (!memcmp(m, "PGR", 3) || !memcmp(m, "PGE", 3) || !memcmp(m, "SIZ", 3)) {
+            return lfail(lf, NOT_HANDLED, "prefix garbage / embedded JPEG sections are not handled");
+        } else {
+            return lfail(lf, UNSUPPORTED_JPEG, "unknown data found in header blob");
+        }
+    }
+    if (!have_grb) { j.grb = {0xFF, 0xD9}; }          // "if we don't have any garbage, assume FFD9 EOI" (jpgcoder.cc:4194)
+    if (lf.handoffs.empty() || (int)lf.handoffs.size() != lf.nseg) return lfail(lf, VERSION_UNSUPPORTED, "handoff table missing or inconsistent");
+    if (lf.handoffs[0].num_overhang_bits == 0xff) return lfail(lf, NOT_HANDLED, "legacy single-thread container");
+    // demux (src/io/MuxReader.hh:230-283); the last 4 bytes are the file-size trailer
+    size_t q = 28 + (size_t)zlen;
+    if (memcmp(d + q, "CMP", 3)) return lfail(lf, UNSUPPORTED_JPEG, "CMP marker missing");
+    q += 3;
+    const size_t end = n - 4;
+    lf.streams.assign(16, std::vector<uint8_t>());
+    while (q + 3 <= end) {
+        const uint8_t hd = d[q];
+        const int sid = hd & 15, flags = (hd >> 4) & 3;
+        size_t len, skip;
+        if (flags == 0) { len = (size_t)d[q + 1] + 256 * (size_t)d[q + 2] + 1; skip = 3; }
+        else { len = (size_t)1024 << (2 * flags); skip = 1; }
+        if (q + skip + len > end) return lfail(lf, SHORT_READ, "mux packet runs past the end of the file");
+        lf.streams[sid].insert(lf.streams[sid].end(), d + q + skip, d + q + skip + len);
+        q += skip + len;
+    }
+    lf.streams.resize(lf.nseg);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Huffman re-encoding of the (single, interleaved or single-component) baseline scan
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct BitWriter {
+    std::vector<uint8_t>& out;
+    uint64_t acc = 0;
+    int nbits = 0;
+    explicit BitWriter(std::vector<uint8_t>& o) : out(o) {}
+    inline void put(uint32_t v, int n) {          // n <= 32
+        if (!n) return;
+        acc = (acc << n) | (v & ((n == 32) ? 0xffffffffu : ((1u << n) - 1)));
+        nbits += n;
+        while (nbits >= 8) {
+            const uint8_t b = (uint8_t)(acc >> (nbits - 8));
+            out.push_back(b);
+            if (b == 0xFF) out.push_back(0x00);   // byte stuffing (recoder.cc:144-185)
+            nbits -= 8;
+        }
+    }
+    // abitwriter::pad (bitops.hh:168-175): successive bits of `fill`, LSB first
+    inline void pad(uint8_t fill) {
+        int offset = 1;
+        while (nbits & 7) { put((fill & offset) ? 1 : 0, 1); offset <<= 1; }
+    }
+};
+
+inline int bitlen16(int v) { return v ? 32 - __builtin_clz((unsigned)v) : 0; }
+
+}  // namespace
+
+bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err) {
+    const Jpeg& j = lf.j;
+    if (j.jpegtype != 1) { err = "progressive re-encode not implemented"; return false; }
+    if (lf.has_eee) { err = "truncated-file re-encode not implemented"; return false; }
+    const std::vector<uint8_t>& h = j.hdr;
+    HuffTable dc_t[4], ac_t[4];
+    int rsti = 0;
+    size_t hpos = 0;
+    int ncomp = 0, scmp[4] = {0, 0, 0, 0}, td[4] = {0}, ta[4] = {0};
+    // handle_initial_segments (recoder.cc:412-461): everything up to and including the first SOS
+    bool found = false;
+    while (hpos + 4 <= h.size()) {
+        const uint8_t type = h[hpos + 1];
+        const size_t len = 2 + be16(&h[hpos + 2]);
+        if (hpos + len > h.size()) { err = "truncated header segment"; return false; }
+        const uint8_t* seg = &h[hpos];
+        if (type == 0xC4) {
+            size_t p = 4;
+            while (p < len) {
+                const int tc = seg[p] >> 4, th = seg[p] & 15;
+                if (tc >= 2 || th >= 4) break;
+                ++p;
+                HuffTable& t = tc ? ac_t[th] : dc_t[th];
+                int total = 0;
+                t.bits[0] = 0;
+                for (int i = 0; i < 16; ++i) { t.bits[i + 1] = seg[p + i]; total += seg[p + i]; }
+                if (total > 256 || p + 16 + total > len) { err = "bad DHT"; return false; }
+                memcpy(t.vals, seg + p + 16, total);
+                if (!t.build()) { err = "bad huffman table"; return false; }
+                t.set = true;
+                p += 16 + total;
+            }
+        } else if (type == 0xDD) {
+            rsti = be16(seg + 4);
+        } else if (type == 0xDA) {
+            ncomp = seg[4];
+            if (ncomp < 1 || ncomp > j.ncmp) { err = "bad SOS"; return false; }
+            for (int i = 0; i < ncomp; ++i) {
+                int c = 0;
+                while (c < j.ncmp && j.cmp[c].jid != seg[5 + 2 * i]) ++c;
+                if (c == j.ncmp) { err = "component id mismatch"; return false; }
+                scmp[i] = c; td[c] = seg[6 + 2 * i] >> 4; ta[c] = seg[6 + 2 * i] & 15;
+            }
+            hpos += len;
+            found = true;
+            break;
+        }
+        hpos += len;
+    }
+    if (!found) { err = "overran headers"; return false; }
+    if (ncomp != j.ncmp) { err = "non-interleaved multi-scan baseline not handled"; return false; }
+    out.clear();
+    out.reserve((size_t)lf.jpeg_size + 64);
+    out.push_back(0xFF); out.push_back(0xD8);
+    out.insert(out.end(), h.begin(), h.begin() + hpos);
+
+    BitWriter bw(out);
+    int lastdc[4] = {0, 0, 0, 0};
+    const int mcuc = j.mcuc;
+    unsigned rst_written = 0;
+    const bool rst_limited = lf.rst_cnt_set && !j.rst_cnt.empty();
+    int rstw = rsti;
+    auto encode_block = [&](int c, int dpos) {
+        const int16_t* blk = planes[c] + (size_t)dpos * 64;
+        const HuffTable& dct = dc_t[td[c]];
+        const HuffTable& act = ac_t[ta[c]];
+        // DC (encode_block_seq, recoder.cc:245-262)
+        const int16_t dc = blk[49];
+        const int16_t diff = (int16_t)(dc - (int16_t)lastdc[c]);
+        lastdc[c] = dc;
+        int s = bitlen16(diff > 0 ? diff : -diff);
+        int nb = diff > 0 ? diff : (diff - 1) + (1 << s);
+        bw.put(dct.ecode[s], dct.elen[s]);
+        bw.put((uint32_t)nb, s);
+        // AC
+        int end = 63;
+        while (end > 0 && blk[k_zigzag_to_aligned[end]] == 0) --end;
+        int z = 0;
+        for (int bpos = 1; bpos <= end; ++bpos) {
+            const int v = blk[k_zigzag_to_aligned[bpos]];
+            if (v == 0) { ++z; continue; }
+            while (z & 0xf0) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
+            s = bitlen16(v > 0 ? v : -v);
+            nb = v > 0 ? v : (v - 1) + (1 << s);
+            const int hc = ((z & 0xf) << 4) + s;
+            bw.put(act.ecode[hc], act.elen[hc]);
+            bw.put((uint32_t)nb, s);
+            z = 0;
+        }
+        if (end != 63) bw.put(act.ecode[0x00], act.elen[0x00]);
+    };
+    auto restart = [&]() {      // recoder.cc:381-397
+        bw.pad((uint8_t)j.padbit);
+        if (!rst_limited || rst_written < j.rst_cnt[0]) {
+            out.push_back(0xFF);
+            out.push_back((uint8_t)(0xD0 + (rst_written & 7)));
+            rst_written++;
+        }
+        rstw = rsti;
+        lastdc[0] = lastdc[1] = lastdc[2] = lastdc[3] = 0;
+    };
+    if (j.ncmp > 1) {
+        for (int mcu = 0; mcu < mcuc; ++mcu) {
+            const int my = mcu / j.mcuh, mx = mcu - my * j.mcuh;
+            for (int ci = 0; ci < ncomp; ++ci) {
+                const int c = scmp[ci];
+                const Component& k = j.cmp[c];
+                for (int sub = 0; sub < k.mbs; ++sub) {
+                    const int sy = sub / k.H, sx = sub - sy * k.H;
+                    encode_block(c, (my * k.V + sy) * k.bch + mx * k.H + sx);
+                }
+            }
+            if (mcu + 1 < mcuc && rsti > 0 && --rstw == 0) restart();
+        }
+    } else {
+        // single component: next_mcuposn order (jpgcoder.cc:5432-5456)
+        const Component& k = j.cmp[0];
+        int dpos = 0;
+        while (true) {
+            encode_block(0, dpos);
+            dpos++;
+            if (k.bch != k.nch && dpos % k.bch == k.nch) dpos += k.bch - k.nch;
+            if (k.bcv != k.ncv && dpos / k.bch == k.ncv) dpos = k.bc;
+            if (dpos >= k.bc) break;
+            if (rsti > 0 && --rstw == 0) restart();
+        }
+    }
+    bw.pad((uint8_t)j.padbit);
+    // trailing bogus restart markers of the (only) scan (recoder.cc:839-848)
+    if (!j.rst_err.empty()) {
+        const unsigned cum = rsti ? (unsigned)(j.mcuh * j.mcuv - 1) / rsti : 0;
+        for (unsigned i = 0; i < j.rst_err[0]; ++i) { out.push_back(0xFF); out.push_back((uint8_t)(0xD0 + ((cum + i) & 7))); }
+    }
+    out.insert(out.end(), h.begin() + hpos, h.end());      // header data after the first SOS, if any
+    out.insert(out.end(), j.grb.begin(), j.grb.end());
+    if (out.size() != lf.jpeg_size) { err = "re-created JPEG has the wrong size"; return false; }
+    return true;
+}
+
+}  // namespace lephost

@@ -59,3 +59,23 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("GPU present")
     with pytest.raises(LeptonB200Error):
         LeptonB200Codec(0)
+
+
+@pytest.mark.parametrize("name", BASELINE_COMPLETE + ["android_t4.lep", "iphonecrop2_t8.lep", "androidcrop_t2.lep"])
+def test_lep_reader_and_jpeg_recode_match_original(name):
+    """Decode-side host halves without a GPU: our .lep reader must demux exactly the reference's streams, and the
+    Huffman re-encoder must re-create the original JPEG byte for byte from the (oracle-decoded) coefficient planes."""
+    from lepton_b200 import HostLep
+    from helpers import oracle_decode_planes
+    lep_name = name if name.endswith(".lep") else name[:-4] + ".lep"
+    src_jpg = MANIFEST[lep_name]["source"] if lep_name in MANIFEST else name
+    data = open(os.path.join(GOLDEN, lep_name), "rb").read()
+    hl = HostLep(data)
+    assert hl.status == 0, hl.error
+    lf = load_lep(lep_name)
+    img = hl.coef_image()
+    assert list(img.luma_y_start) == [h.luma_y_start for h in lf.handoffs]
+    assert hl.streams(img.nseg) == lepfmt.demux(lf.payload)[:lf.nseg]
+    planes, _ = oracle_decode_planes(lf)
+    jpg = hl.recode(planes)
+    assert jpg == open(os.path.join(GOLDEN, src_jpg), "rb").read(), "re-created JPEG differs from the original"
