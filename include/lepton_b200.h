@@ -108,6 +108,32 @@ int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nima
 
 /* Wait for everything queued on the context's stream. */
 int lepb200_sync(lepb200_ctx* ctx);
+/* ---- GPU Huffman decode: baseline JPEG scan -> coefficient planes directly in HBM.
+ * Replaces the Huffman half of decode_jpeg (src/lepton/jpgcoder.cc:2799-3302, decode_block_seq :4893-4961); the caller
+ * still parses markers and de-stuffs the entropy-coded bytes (read_jpeg, :2270-2466).  One thread per image. */
+typedef struct lepb200_hufftable { uint8_t bits[17]; uint8_t vals[256]; } lepb200_hufftable;   /* DHT form: counts per length (bits[1..16]) + symbols */
+typedef struct lepb200_huffrow { uint32_t bitpos; int16_t lastdc[3]; int16_t mcu_y; } lepb200_huffrow; /* Huffman state at an MCU-row start */
+typedef struct lepb200_jpeg_scan {
+    const uint8_t* entropy;          /* HOST: de-stuffed entropy-coded bytes of the (single) scan, RST markers removed */
+    uint32_t nbytes;
+    int32_t ncmp, mcuh, mcuv, rsti;  /* components (frame order == scan order), MCUs per row / rows, restart interval */
+    int32_t H[3], V[3];              /* sampling factors */
+    int32_t nch[3], ncv[3];          /* non-interleaved block counts (single-component scans) */
+    lepb200_hufftable dc[3], ac[3];  /* tables selected by the SOS for each component */
+    /* outputs */
+    int32_t status;                  /* 0 ok, 42 UNSUPPORTED_JPEG (decode error, inconsistent padding, trailing data), 200 not handled */
+    int32_t padbit;                  /* as written to the P0D section */
+    uint32_t end_bitpos;
+    int32_t nrows;
+    lepb200_huffrow* rows;           /* HOST array with room for mcuv + 1 entries */
+} lepb200_jpeg_scan;
+/* Uploads the entropy bytes, Huffman-decodes every scan into the context's device plane arena (laid out exactly as a
+ * following lepb200_encode_upload_resident expects) and returns per-row states + status on the host. */
+int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans, int nimages);
+/* Like lepb200_encode_upload, but the planes are the ones just produced on the device by
+ * lepb200_huffman_decode_to_device (images[i].planes is ignored; geometry must match scan i). */
+int lepb200_encode_upload_resident(lepb200_ctx* ctx, const lepb200_image* images, int nimages);
+
 /* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */
 float lepb200_last_kernel_ms(lepb200_ctx* ctx);
 /* Encode only: device time of kernel A (symbolisation + model update) within the last launch; the rest of
@@ -144,6 +170,9 @@ lepb200_ctx* lepb200_codec_ctx(lepb200_codec* codec);
 uint64_t lepb200_codec_kernel_launches(const lepb200_codec* codec);
 /* files per pipeline chunk (default 512): chunk k+1 is Huffman-decoded while chunk k is on the GPU */
 void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
+/* 1 (default): Huffman-decode on the GPU when every file of a chunk is a complete single-scan baseline JPEG;
+ * 0: always Huffman-decode on host threads */
+void lepb200_codec_set_gpu_huffman(lepb200_codec* codec, int on);
 /* summed seconds spent by the last call's stages (they overlap): JPEG parse + Huffman decode | H2D + kernel + D2H | container writing */
 void lepb200_codec_last_timing(const lepb200_codec* codec, double* front_s, double* gpu_s, double* back_s);
 /* n JPEG files in, n .lep files out */

@@ -11,6 +11,7 @@
 #include "lep_predict.cuh"
 #include "lep_encode.cu"
 #include "lep_decode.cu"
+#include "lep_huff.cu"
 
 using namespace lepb200;
 
@@ -68,8 +69,10 @@ struct lepb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     std::string err;
-    DevBuf d_planes, d_streams, d_tokens, d_dense, d_images, d_segs, d_order, d_counter, d_models, d_rows;
-    HostBuf h_segs, h_dense, h_stage;
+    DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_images, d_segs, d_order, d_counter, d_models, d_rows;
+    HostBuf h_segs, h_dense, h_stage, h_hjobs;
+    size_t resident_plane_total = 0;
+    int resident_images = 0;
     std::vector<ImageDesc> images;
     std::vector<SegDesc> segs;
     std::vector<int> order;
@@ -251,6 +254,8 @@ __global__ void lep_compact_kernel(const SegDesc* __restrict__ segs, const unsig
 
 extern "C" {
 
+static int encode_prepass(lepb200_ctx* ctx);
+
 int lepb200_device_available(void) {
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
@@ -283,9 +288,9 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
+    for (DevBuf* b : {&ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
         b->release();
-    for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage}) b->release();
+    for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs}) b->release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_mid);
@@ -334,6 +339,10 @@ int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
         for (int c = 0; c < images[i].ncmp; ++c)
             CK(cudaMemcpyAsync(reinterpret_cast<void*>(ctx->images[i].plane[c]), images[i].planes[c], ctx->plane_bytes[(size_t)i * 3 + c],
                                cudaMemcpyHostToDevice, ctx->stream));
+    return encode_prepass(ctx);
+}
+
+static int encode_prepass(lepb200_ctx* ctx) {
     // pre-pass: per-segment token upper bounds -> exact-fit token arena (sizes depend on the data, so one sync here)
     const int nseg = (int)ctx->segs.size();
     lep_count_kernel<<<nseg, CNT_THREADS, 0, ctx->stream>>>(static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg);
@@ -348,6 +357,124 @@ int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
     CK(ctx->d_tokens.reserve((size_t)total_tokens * 2 + 256));
     ctx->have_batch = true;
     return LEPB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GPU Huffman decode
+static bool build_table_dev(const lepb200_hufftable& in, HuffTableDev& t) {
+    memset(&t, 0, sizeof(t));
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        t.valoff[len] = k - code;
+        for (int i = 0; i < in.bits[len]; ++i, ++k, ++code) {
+            if (k >= 256) return false;
+            t.vals[k] = in.vals[k];
+            if (len <= 9) {
+                const int shift = 9 - len;
+                for (int f = 0; f < (1 << shift); ++f) t.fast[(code << shift) | f] = (uint16_t)((len << 8) | in.vals[k]);
+            }
+        }
+        t.maxcode[len] = in.bits[len] ? code - 1 : -1;
+        if (code > (1 << len)) return false;
+        code <<= 1;
+    }
+    t.maxcode[17] = 0x7fffffff;
+    return true;
+}
+
+int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans, int n) {
+    if (!ctx || !scans || n <= 0) return LEPB200_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_batch = false; ctx->launched = false; ctx->resident_images = 0;
+    std::vector<HuffJob> jobs(n);
+    std::vector<HuffTableDev> tabs;
+    std::vector<std::pair<const lepb200_hufftable*, int>> seen;     // dedupe identical tables (most files share the standard ones)
+    auto table_index = [&](const lepb200_hufftable& t, bool& ok) -> int {
+        for (auto& s : seen) if (!memcmp(s.first, &t, sizeof(t))) return s.second;
+        HuffTableDev d;
+        ok = build_table_dev(t, d);
+        tabs.push_back(d);
+        seen.emplace_back(&t, (int)tabs.size() - 1);
+        return (int)tabs.size() - 1;
+    };
+    size_t plane_total = 0, huff_total = 0, rows_total = 0;
+    for (int i = 0; i < n; ++i) {
+        lepb200_jpeg_scan& sc = scans[i];
+        HuffJob& jb = jobs[i];
+        memset(&jb, 0, sizeof(jb));
+        bool ok = sc.ncmp >= 1 && sc.ncmp <= 3 && sc.mcuh > 0 && sc.mcuv > 0 && sc.entropy && sc.rows;
+        jb.ncmp = sc.ncmp; jb.mcuh = sc.mcuh; jb.mcuv = sc.mcuv; jb.rsti = sc.rsti; jb.nbytes = sc.nbytes;
+        for (int c = 0; ok && c < sc.ncmp; ++c) {
+            jb.H[c] = sc.H[c]; jb.V[c] = sc.V[c];
+            ok = ok && sc.H[c] >= 1 && sc.H[c] <= 2 && sc.V[c] >= 1 && sc.V[c] <= 2;
+            jb.bch[c] = sc.mcuh * sc.H[c]; jb.bcv[c] = sc.mcuv * sc.V[c];
+            jb.nch[c] = sc.nch[c]; jb.ncv[c] = sc.ncv[c];
+            jb.dc_tab[c] = table_index(sc.dc[c], ok);
+            jb.ac_tab[c] = table_index(sc.ac[c], ok);
+            jb.plane[c] = plane_total;
+            plane_total += align_up((size_t)jb.bch[c] * jb.bcv[c] * 128, 256);
+        }
+        jb.status = ok ? 0 : LEPB200_ST_NOT_HANDLED;
+        jb.huff = huff_total;
+        huff_total += align_up((size_t)sc.nbytes + 16, 16);
+        jb.rows = rows_total;
+        rows_total += (size_t)(sc.mcuv + 1) * sizeof(HuffRow);
+    }
+    CK(ctx->d_planes.reserve(plane_total + 256));
+    CK(ctx->d_huff.reserve(huff_total + 256));
+    CK(ctx->d_hrows.reserve(rows_total + 256));
+    CK(ctx->d_hjobs.reserve(sizeof(HuffJob) * n));
+    CK(ctx->d_htabs.reserve(sizeof(HuffTableDev) * std::max<size_t>(1, tabs.size())));
+    CK(ctx->h_stage.reserve(huff_total + 256));
+    uint8_t* hs = static_cast<uint8_t*>(ctx->h_stage.p);
+    for (int i = 0; i < n; ++i) {
+        HuffJob& jb = jobs[i];
+        memcpy(hs + jb.huff, scans[i].entropy, scans[i].nbytes);
+        memset(hs + jb.huff + scans[i].nbytes, 0, align_up((size_t)scans[i].nbytes + 16, 16) - scans[i].nbytes);
+        jb.huff += (unsigned long long)(uintptr_t)ctx->d_huff.p;
+        jb.rows += (unsigned long long)(uintptr_t)ctx->d_hrows.p;
+        for (int c = 0; c < jb.ncmp; ++c) jb.plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
+    }
+    CK(cudaMemsetAsync(ctx->d_planes.p, 0, plane_total, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_huff.p, hs, huff_total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hjobs.p, jobs.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    lep_huffdecode_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, ctx->stream>>>(
+        static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p));
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(ctx->h_hjobs.reserve(sizeof(HuffJob) * n + rows_total));
+    HuffJob* hj = static_cast<HuffJob*>(ctx->h_hjobs.p);
+    uint8_t* hrows = reinterpret_cast<uint8_t*>(hj + n);
+    CK(cudaMemcpyAsync(hj, ctx->d_hjobs.p, sizeof(HuffJob) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hrows, ctx->d_hrows.p, rows_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        scans[i].status = hj[i].status;
+        scans[i].padbit = hj[i].padbit;
+        scans[i].end_bitpos = hj[i].end_bitpos;
+        scans[i].nrows = hj[i].nrows;
+        const size_t off = (size_t)(jobs[i].rows - (unsigned long long)(uintptr_t)ctx->d_hrows.p);
+        static_assert(sizeof(HuffRow) == sizeof(lepb200_huffrow), "row record layout");
+        if (hj[i].nrows > 0) memcpy(scans[i].rows, hrows + off, sizeof(HuffRow) * (size_t)std::min(hj[i].nrows, scans[i].mcuv + 1));
+    }
+    ctx->resident_plane_total = plane_total;
+    ctx->resident_images = n;
+    return LEPB200_OK;
+}
+
+int lepb200_encode_upload_resident(lepb200_ctx* ctx, const lepb200_image* images, int nimages) {
+    if (!ctx) return LEPB200_ERR_INVALID;
+    if (ctx->resident_images != nimages) { ctx->err = "encode_upload_resident: no matching huffman_decode_to_device batch"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    // planes pointers are not dereferenced on this path, but validate_image wants them non-null
+    std::vector<lepb200_image> tmp(images, images + nimages);
+    for (auto& im : tmp) for (int c = 0; c < im.ncmp && c < 3; ++c) if (!im.planes[c]) im.planes[c] = reinterpret_cast<int16_t*>(uintptr_t(1));
+    void* const planes_before = ctx->d_planes.p;
+    int r = build_batch(ctx, tmp.data(), nimages, true, nullptr);
+    if (r) return r;
+    if (ctx->d_planes.p != planes_before) { ctx->err = "encode_upload_resident: plane arena moved (geometry mismatch)"; return LEPB200_ERR_INVALID; }
+    ctx->resident_images = 0;
+    return encode_prepass(ctx);
 }
 
 int lepb200_encode_launch(lepb200_ctx* ctx) {

@@ -24,6 +24,7 @@ struct lepb200_codec {
     lepb200_ctx* ctx2[2] = {nullptr, nullptr};   // ping-pong contexts: chunk k on ctx2[k & 1]
     int nthreads = 1;
     int chunk_images = 512;
+    bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
     void* arena[2] = {nullptr, nullptr};          // pinned host memory for coefficient planes, one per in-flight chunk
     size_t arena_cap[2] = {0, 0};
     std::vector<std::vector<uint8_t>> outputs;
@@ -113,6 +114,7 @@ const char* lepb200_codec_last_error(const lepb200_codec* c) {
 lepb200_ctx* lepb200_codec_ctx(lepb200_codec* c) { return c ? c->ctx : nullptr; }
 uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) { return c ? lepb200_kernel_launches(c->ctx2[0]) + lepb200_kernel_launches(c->ctx2[1]) : 0; }
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
+void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
 
 void lepb200_codec_last_timing(const lepb200_codec* c, double* front_s, double* gpu_s, double* back_s) {
     if (!c) return;
@@ -140,6 +142,10 @@ struct ChunkState {
     std::vector<int> seg_base;
     std::vector<lepb200_stream> streams;
     int gpu_rc = 0;
+    // GPU Huffman path
+    bool on_gpu = false;
+    std::vector<lepb200_jpeg_scan> scans;
+    std::vector<std::vector<lepb200_huffrow>> rowbuf;
 };
 
 }  // namespace
@@ -167,6 +173,39 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             need[i] = peek_plane_bytes(jpegs[s.begin + i].data, jpegs[s.begin + i].len);
             base[i] = total;
             total += need[i];
+        }
+        if (c->gpu_huffman) {
+            // GPU Huffman path: the host only parses markers and de-stuffs; eligible if EVERY file of the chunk is a
+            // complete single-scan baseline JPEG (otherwise the whole chunk takes the host Huffman path below)
+            s.scans.assign(m, lepb200_jpeg_scan());
+            s.rowbuf.resize(m);
+            std::atomic<int> ineligible(0);
+            parallel_for(m, c->nthreads, [&](int i) {
+                s.js[i].reset(new Jpeg());
+                Jpeg& j = *s.js[i];
+                const lepb200_buffer& in = jpegs[s.begin + i];
+                GpuScanSetup gs;
+                if (!parse_jpeg(in.data, in.len, j) || !gpu_scan_setup(j, gs)) { ineligible++; return; }
+                lepb200_jpeg_scan& sc = s.scans[i];
+                memset(&sc, 0, sizeof(sc));
+                sc.entropy = j.huff.data(); sc.nbytes = (uint32_t)j.huff.size();
+                sc.ncmp = j.ncmp; sc.mcuh = j.mcuh; sc.mcuv = j.mcuv; sc.rsti = gs.rsti;
+                for (int q = 0; q < j.ncmp; ++q) {
+                    sc.H[q] = j.cmp[q].H; sc.V[q] = j.cmp[q].V; sc.nch[q] = j.cmp[q].nch; sc.ncv[q] = j.cmp[q].ncv;
+                    memcpy(sc.dc[q].bits, gs.dc_bits[q], 17); memcpy(sc.dc[q].vals, gs.dc_vals[q], 256);
+                    memcpy(sc.ac[q].bits, gs.ac_bits[q], 17); memcpy(sc.ac[q].vals, gs.ac_vals[q], 256);
+                }
+                s.rowbuf[i].resize((size_t)j.mcuv + 1);
+                sc.rows = s.rowbuf[i].data();
+            });
+            if (ineligible.load() == 0) {
+                s.on_gpu = true;
+                std::lock_guard<std::mutex> g(tmu);
+                c->t_front += now_s() - t0;
+                return;
+            }
+            for (auto& u : s.js) u.reset();      // fall through to the host Huffman path for this chunk
+            s.scans.clear(); s.rowbuf.clear();
         }
         const int slot = k & 1;
         if (!reserve_arena(c, slot, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
@@ -218,7 +257,44 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     auto gpu = [&](int k) {
         double t0 = now_s();
         ChunkState& s = cs[k];
-        if (s.gpu_rc == 0 && !s.imgs.empty()) s.gpu_rc = lepb200_encode_images(c->ctx2[k & 1], s.imgs.data(), (int)s.imgs.size(), s.streams.data());
+        if (s.on_gpu && s.gpu_rc == 0) {
+            lepb200_ctx* ctx = c->ctx2[k & 1];
+            const int m = s.end - s.begin;
+            s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), m);
+            if (s.gpu_rc == 0) {
+                int nseg_total = 0;
+                int16_t* none[4] = {nullptr, nullptr, nullptr, nullptr};
+                for (int i = 0; i < m; ++i) {
+                    Jpeg& j = *s.js[i];
+                    const lepb200_jpeg_scan& sc = s.scans[i];
+                    if (sc.status == 0 && sc.nrows >= 2) {
+                        j.padbit = (int8_t)sc.padbit;
+                        j.rows.clear();
+                        for (int r = 0; r < sc.nrows; ++r) j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
+                        for (size_t r = 1; r < j.rows.size(); ++r)
+                            if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
+                        s.splits[i] = select_splits(j);
+                    } else {
+                        j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
+                        j.error = "GPU Huffman decoder refused the scan";
+                        Handoff h0;                       // placeholder single segment so that the batch layout stays intact
+                        s.splits[i].selected.assign(1, h0);
+                    }
+                    status[s.begin + i] = j.status;
+                    lepb200_image im;
+                    fill_image(im, j, none, s.splits[i].selected);
+                    s.imgs.push_back(im);
+                    s.idx.push_back(i);
+                    nseg_total += im.nseg;
+                }
+                s.streams.resize(nseg_total);
+                s.seg_base.assign(s.imgs.size() + 1, 0);
+                for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+                s.gpu_rc = lepb200_encode_upload_resident(ctx, s.imgs.data(), m);
+                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(ctx);
+                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
+            }
+        } else if (s.gpu_rc == 0 && !s.imgs.empty()) s.gpu_rc = lepb200_encode_images(c->ctx2[k & 1], s.imgs.data(), (int)s.imgs.size(), s.streams.data());
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -228,6 +304,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         if (s.gpu_rc == 0) {
             parallel_for((int)s.imgs.size(), std::max(1, c->nthreads / 4), [&](int q) {
                 const int i = s.begin + s.idx[q];
+                if (status[i]) return;
                 std::vector<std::pair<const uint8_t*, size_t>> ss;
                 for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t) {
                     if (s.streams[t].status) { status[i] = s.streams[t].status; return; }

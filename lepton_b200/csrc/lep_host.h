@@ -93,6 +93,14 @@ inline size_t plane_bytes(const Jpeg& j, int c) { return (size_t)j.cmp[c].bc * 1
 // Huffman-decode all scans into planes (pre-zeroed, AlignedBlock order) and record the per-row handoffs.
 bool decode_scans(Jpeg& j, int16_t* const planes[4]);
 
+// ---- GPU Huffman path helpers
+struct GpuScanSetup {
+    int rsti = 0;
+    uint8_t dc_bits[3][17], dc_vals[3][256], ac_bits[3][17], ac_vals[3][256];
+};
+bool gpu_scan_setup(const Jpeg& j, GpuScanSetup& out);
+Handoff handoff_from_state(const Jpeg& j, uint32_t bitpos, int mcu_y, const int16_t lastdc[3]);
+
 // ---- container ----------------------------------------------------------------------------------
 struct Splits {
     std::vector<Handoff> selected;   // what gets serialised into the header ('H' 'H' nseg ...)

@@ -1,0 +1,210 @@
+// lep_huff.cu -- baseline JPEG Huffman decode on the GPU.
+//
+// Moves the 16x data expansion (JPEG bytes -> 128 B/block coefficient planes) onto the device: the host only
+// splits the file into header / de-stuffed entropy bytes (lep_jpeg.cc parse_jpeg) and uploads the entropy bytes;
+// this kernel produces the coefficient planes in AlignedBlock order directly in HBM, plus, per MCU row, the
+// resumable Huffman state the reference calls a ThreadHandoff (bit position, last DCs;
+// crystallize_thread_handoff, src/lepton/jpgcoder.cc:2520-2560).
+//
+// A baseline scan without restart markers is one serial bit stream, so the unit of parallelism is the image:
+// ONE THREAD PER IMAGE (a batch of thousands of files keeps the chip busy; the kernel is latency-bound per thread,
+// its duration is that of the largest file).  Semantics follow decode_jpeg / decode_block_seq
+// (jpgcoder.cc:2799-3302, :4893-4961) exactly like the host decoder in lep_jpeg.cc, against which it is tested.
+#include "lep_common.cuh"
+
+namespace lepb200 {
+
+struct HuffTableDev {
+    uint16_t fast[512];      // (len << 8) | symbol for codes of <= 9 bits, 0 = longer code
+    int32_t maxcode[18];
+    int32_t valoff[18];
+    uint8_t vals[256];
+};
+
+struct HuffRow {             // state at the start of an MCU row
+    uint32_t bitpos;         // bits consumed of the de-stuffed entropy stream
+    int16_t lastdc[3];
+    int16_t mcu_y;
+};
+
+struct HuffJob {
+    unsigned long long huff;         // device address of the de-stuffed entropy bytes (4-byte aligned, zero padded by 8)
+    unsigned long long plane[3];     // coefficient planes (pre-zeroed)
+    unsigned long long rows;         // HuffRow[mcuv + 1]
+    uint32_t nbytes;
+    int32_t ncmp, mcuh, mcuv, rsti;
+    int32_t H[3], V[3], bch[3], bcv[3], nch[3], ncv[3];
+    int32_t dc_tab[3], ac_tab[3];    // indices into the table array
+    // outputs
+    int32_t status;                  // 0 ok; 42 UNSUPPORTED_JPEG (decode error / eob after last 0 / unneeded data); 200 not handled
+    int32_t padbit;
+    uint32_t end_bitpos;
+    int32_t nrows;
+};
+
+static __constant__ uint8_t c_zigzag_to_aligned[64] = {
+    49, 50, 57, 58, 0, 51, 52, 1, 2, 59, 60, 3, 4, 5, 53, 54, 6, 7, 8, 9, 61, 62, 10, 11,
+    12, 13, 14, 55, 56, 15, 16, 17, 18, 19, 20, 63, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32,
+    33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48};
+
+struct HBits {
+    const uint32_t* w;       // big-endian words of the stream
+    unsigned long long acc;  // next bits, MSB first, in the top `n` bits
+    int n;
+    uint32_t wi, nwords;
+    unsigned long long bitpos;
+};
+__device__ __forceinline__ void hb_fill(HBits& b) {
+    if (b.n <= 32) {
+        uint32_t v = b.wi < b.nwords ? __ldg(b.w + b.wi) : 0u;
+        b.wi++;
+        v = __byte_perm(v, 0, 0x0123);
+        b.acc |= (unsigned long long)v << (32 - b.n);
+        b.n += 32;
+    }
+}
+__device__ __forceinline__ uint32_t hb_peek(const HBits& b, int k) { return (uint32_t)(b.acc >> (64 - k)); }   // 1 <= k <= 32
+__device__ __forceinline__ void hb_skip(HBits& b, int k) { b.acc <<= k; b.n -= k; b.bitpos += (unsigned)k; }
+
+__device__ __forceinline__ int huff_symbol(HBits& b, const HuffTableDev* __restrict__ t) {
+    hb_fill(b);
+    const uint32_t top = hb_peek(b, 16);
+    const uint32_t f = __ldg(&t->fast[top >> 7]);
+    if (f) { hb_skip(b, (int)(f >> 8)); return (int)(f & 0xff); }
+    int len = 10;
+    int code = (int)(top >> 6);
+    while (len <= 16 && code > __ldg(&t->maxcode[len])) { ++len; code = (int)(top >> (16 - len)); }
+    if (len > 16) return -1;
+    hb_skip(b, len);
+    return __ldg(&t->vals[code + __ldg(&t->valoff[len])]);
+}
+__device__ __forceinline__ int huff_extend(HBits& b, int s) {      // DEVLI (jpgcoder.cc:117)
+    if (s == 0) return 0;
+    hb_fill(b);
+    const int n = (int)hb_peek(b, s);
+    hb_skip(b, s);
+    return n >= (1 << (s - 1)) ? n : n + 1 - (1 << s);
+}
+
+constexpr int HUFF_THREADS = 32;
+
+__global__ void __launch_bounds__(HUFF_THREADS)
+lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables) {
+    const int t = blockIdx.x * HUFF_THREADS + threadIdx.x;
+    if (t >= njobs) return;
+    HuffJob& jb = jobs[t];
+    if (jb.status != 0) return;
+    HBits b;
+    b.w = reinterpret_cast<const uint32_t*>(jb.huff);
+    b.acc = 0; b.n = 0; b.wi = 0; b.nwords = (jb.nbytes + 3) / 4; b.bitpos = 0;
+    const unsigned long long total_bits = (unsigned long long)jb.nbytes * 8;
+    HuffRow* rows = reinterpret_cast<HuffRow*>(jb.rows);
+    const int ncmp = jb.ncmp, mcuh = jb.mcuh, mcuc = jb.mcuh * jb.mcuv, rsti = jb.rsti;
+    int lastdc[3] = {0, 0, 0};
+    int cmp = 0, csc = 0, sub = 0, dpos = 0, mcu = 0;
+    int nrows = 0, status = 0, padbit = -1;
+    bool handoff_due = true;
+    const int hmul = jb.bch[0] / jb.mcuh, vmul = jb.bcv[0] / jb.mcuv;
+    int rstw = rsti;
+    int sta = 0;
+    while (true) {                       // one iteration = one block (flattened decode_jpeg loops)
+        if (handoff_due) {
+            const int mcu_y = ncmp > 1 ? mcu / mcuh : (dpos / (hmul * vmul)) / mcuh;
+            HuffRow r;
+            r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)mcu_y;
+            r.lastdc[0] = (int16_t)lastdc[0]; r.lastdc[1] = (int16_t)lastdc[1]; r.lastdc[2] = (int16_t)lastdc[2];
+            rows[nrows++] = r;
+            handoff_due = false;
+        }
+        // ---- decode_block_seq
+        const HuffTableDev* dct = tables + jb.dc_tab[cmp];
+        const HuffTableDev* act = tables + jb.ac_tab[cmp];
+        int16_t* blk = reinterpret_cast<int16_t*>(jb.plane[cmp]) + (size_t)dpos * 64;
+        int s = huff_symbol(b, dct);
+        if (s < 0 || s > 16) { status = 42; break; }
+        const int16_t dcv = (int16_t)(huff_extend(b, s) + lastdc[cmp]);
+        lastdc[cmp] = dcv;
+        blk[49] = dcv;
+        int bpos = 1;
+        bool last_nonzero = true, eob_seen = false;
+        while (bpos < 64) {
+            const int hc = huff_symbol(b, act);
+            if (hc < 0) { status = 42; break; }
+            if (hc == 0) { eob_seen = true; break; }
+            const int z = hc >> 4;
+            s = hc & 15;
+            const int v = huff_extend(b, s);
+            if (z + bpos >= 64) { status = 200; break; }           // truncated-file fix-up path: not handled here
+            bpos += z;
+            blk[c_zigzag_to_aligned[bpos++]] = (int16_t)v;
+            last_nonzero = v != 0;
+        }
+        if (status) break;
+        if (eob_seen && bpos > 1 && !last_nonzero) { status = 42; break; }   // "eob after last 0" (jpgcoder.cc:2953)
+        if (b.bitpos > total_bits) { status = 200; break; }         // entropy data ends inside a block
+        // ---- next position
+        sta = 0;
+        if (ncmp > 1) {
+            const int old_mcu = mcu;
+            if (++sub >= jb.H[cmp] * jb.V[cmp]) {
+                sub = 0;
+                if (++csc >= ncmp) {
+                    csc = 0; cmp = 0; ++mcu;
+                    if (mcu >= mcuc) sta = 2;
+                    else if (rsti > 0 && --rstw == 0) sta = 1;
+                } else {
+                    cmp = csc;
+                }
+            }
+            const int H = jb.H[cmp], V = jb.V[cmp];
+            if (V > 1) {
+                const int my = mcu / mcuh, mx = mcu - my * mcuh, sy = sub / H, sx = sub - sy * H;
+                dpos = (my * V + sy) * jb.bch[cmp] + mx * H + sx;
+            } else if (H > 1) {
+                dpos = mcu * (H * V) + sub;
+            } else {
+                dpos = mcu;
+            }
+            if (mcu % mcuh == 0 && old_mcu != mcu) handoff_due = true;
+        } else {
+            dpos++;
+            if (jb.bch[0] != jb.nch[0] && dpos % jb.bch[0] == jb.nch[0]) dpos += jb.bch[0] - jb.nch[0];
+            if (jb.bcv[0] != jb.ncv[0] && dpos / jb.bch[0] == jb.ncv[0]) dpos = jb.bch[0] * jb.bcv[0];
+            if (dpos >= jb.bch[0] * jb.bcv[0]) sta = 2;
+            else if (rsti > 0 && --rstw == 0) sta = 1;
+            mcu = dpos / (hmul * vmul);
+            if ((mcu % mcuh == 0) && (dpos % (hmul * vmul) == 0)) handoff_due = true;
+        }
+        if (b.bitpos >= total_bits) sta = 2;                          // huffr->eof
+        if (sta != 0) {
+            // abitreader::unpad (bitops.hh:316-332) + padbit bookkeeping (jpgcoder.cc:3260-3271)
+            int fb = padbit;
+            if ((b.bitpos & 7) != 0 && b.bitpos < total_bits) {
+                hb_fill(b);
+                int last = (int)hb_peek(b, 1); hb_skip(b, 1);
+                fb = last;
+                int offset = 1;
+                while (b.bitpos & 7) { hb_fill(b); last = (int)hb_peek(b, 1); hb_skip(b, 1); fb |= last << offset; ++offset; }
+                while (offset < 7) { fb |= last << offset; ++offset; }
+            }
+            if (padbit != -1) { if (padbit != fb) { status = 42; break; } }
+            else padbit = fb;
+            if (sta == 2) break;
+            lastdc[0] = lastdc[1] = lastdc[2] = 0;                    // restart interval
+            rstw = rsti;
+        }
+    }
+    if (status == 0) {
+        HuffRow r;
+        r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)(mcu / mcuh);
+        r.lastdc[0] = (int16_t)lastdc[0]; r.lastdc[1] = (int16_t)lastdc[1]; r.lastdc[2] = (int16_t)lastdc[2];
+        rows[nrows++] = r;
+        if (b.bitpos < total_bits) status = 42;                      // "unneeded data found after coded image data"
+    }
+    jb.status = status;
+    jb.padbit = padbit;
+    jb.end_bitpos = (uint32_t)b.bitpos;
+    jb.nrows = nrows;
+}
+
+}  // namespace lepb200

@@ -335,6 +335,67 @@ int8_t unpad(BitReader& br, int8_t fillbit) {
 
 }  // namespace
 
+// ThreadHandoff for a Huffman state captured elsewhere (the GPU decoder): same mapping as crystallize().
+Handoff handoff_from_state(const Jpeg& j, uint32_t bitpos, int mcu_y, const int16_t lastdc[3]) {
+    BitReader br{j.huff.data(), j.huff.size(), bitpos};
+    int ldc[4] = {lastdc[0], lastdc[1], lastdc[2], 0};
+    return crystallize(j, br, mcu_y, ldc, j.cmp[0].bcv / j.mcuv);
+}
+
+// Single-scan baseline set-up for the GPU Huffman decoder: tables chosen by the SOS, restart interval.  Returns false
+// (without touching j.status) when the file needs the general host path (progressive, truncated, several scans, scan
+// order != frame order).
+bool gpu_scan_setup(const Jpeg& j, GpuScanSetup& out) {
+    if (j.jpegtype != 1 || j.early_eof || j.ncmp < 1 || j.ncmp > 3) return false;
+    const std::vector<uint8_t>& h = j.hdr;
+    struct Raw { bool set = false; uint8_t bits[17]; uint8_t vals[256]; } dc[4], ac[4];
+    size_t hpos = 0;
+    int nsos = 0;
+    out.rsti = 0;
+    while (hpos + 4 <= h.size()) {
+        const uint8_t type = h[hpos + 1];
+        const size_t len = 2 + be16(&h[hpos + 2]);
+        if (hpos + len > h.size()) return false;
+        const uint8_t* seg = &h[hpos];
+        if (type == 0xC4) {
+            if (nsos) return false;                    // tables after the scan started: general path
+            size_t p = 4;
+            while (p < len) {
+                const int tc = seg[p] >> 4, th = seg[p] & 15;
+                if (tc >= 2 || th >= 4) return false;
+                ++p;
+                if (p + 16 > len) return false;
+                Raw& t = tc ? ac[th] : dc[th];
+                int total = 0;
+                t.bits[0] = 0;
+                for (int i = 0; i < 16; ++i) { t.bits[i + 1] = seg[p + i]; total += seg[p + i]; }
+                if (total > 256 || p + 16 + total > len) return false;
+                memset(t.vals, 0, 256);
+                memcpy(t.vals, seg + p + 16, total);
+                t.set = true;
+                p += 16 + total;
+            }
+            if (p != len) return false;
+        } else if (type == 0xDD) {
+            if (nsos) return false;
+            out.rsti = be16(seg + 4);
+        } else if (type == 0xDA) {
+            if (++nsos > 1) return false;
+            const int nc = seg[4];
+            if (nc != j.ncmp || len < (size_t)(8 + 2 * nc)) return false;
+            for (int i = 0; i < nc; ++i) {
+                if (seg[5 + 2 * i] != j.cmp[i].jid) return false;       // scan order must be frame order
+                const int td = seg[6 + 2 * i] >> 4, ta = seg[6 + 2 * i] & 15;
+                if (td >= 4 || ta >= 4 || !dc[td].set || !ac[ta].set) return false;
+                memcpy(out.dc_bits[i], dc[td].bits, 17); memcpy(out.dc_vals[i], dc[td].vals, 256);
+                memcpy(out.ac_bits[i], ac[ta].bits, 17); memcpy(out.ac_vals[i], ac[ta].vals, 256);
+            }
+        }
+        hpos += len;
+    }
+    return nsos == 1;
+}
+
 bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
     HuffTable dc_t[4], ac_t[4];
     BitReader br{j.huff.data(), j.huff.size(), 0};

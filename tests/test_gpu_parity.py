@@ -163,3 +163,22 @@ def test_file_level_roundtrip_jpeg_lep_jpeg():
     for n, (st, out) in zip(ref, back):
         assert st == 0 and out == open(os.path.join(GOLDEN, MANIFEST[n]["source"]), "rb").read(), n
     fc.close()
+
+
+@pytest.mark.parametrize("gpu_huffman", [True, False])
+def test_file_level_compress_both_huffman_paths(gpu_huffman):
+    """Huffman decode on the GPU (one thread per image) and on host threads must give the same, reference-identical
+    .lep files (restart markers, grey, 4:2:0 and multi-segment images included)."""
+    import os
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200FileCodec
+    names = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "colorswap.jpg",
+             "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg"]
+    jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names] * 3
+    fc = LeptonB200FileCodec(0, host_threads=4, chunk_images=8, gpu_huffman=gpu_huffman)
+    res = fc.compress(jpegs)
+    for k, (st, lep) in enumerate(res):
+        n = names[k % len(names)]
+        assert st == 0, (n, st)
+        assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
+    fc.close()
