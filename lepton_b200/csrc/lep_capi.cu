@@ -439,7 +439,7 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(cudaMemcpyAsync(ctx->d_hjobs.p, jobs.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
     lep_huffdecode_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, ctx->stream>>>(
-        static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p));
+        static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
     CK(cudaGetLastError());
     ctx->launches += 1;
     CK(ctx->h_hjobs.reserve(sizeof(HuffJob) * n + rows_total));

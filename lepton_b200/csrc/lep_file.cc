@@ -21,12 +21,12 @@ using namespace lephost;
 
 struct lepb200_codec {
     lepb200_ctx* ctx = nullptr;     // == ctx2[0]
-    lepb200_ctx* ctx2[2] = {nullptr, nullptr};   // ping-pong contexts: chunk k on ctx2[k & 1]
+    lepb200_ctx* ctx2[3] = {nullptr, nullptr, nullptr};   // rotating contexts: chunk k on ctx2[k % 3]
     int nthreads = 1;
     int chunk_images = 512;
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
-    void* arena[2] = {nullptr, nullptr};          // pinned host memory for coefficient planes, one per in-flight chunk
-    size_t arena_cap[2] = {0, 0};
+    void* arena[3] = {nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
+    size_t arena_cap[3] = {0, 0, 0};
     std::vector<std::vector<uint8_t>> outputs;
     std::string err;
     // timing of the last call (seconds): parse+huffman, gpu (upload+kernel+fetch), container
@@ -87,12 +87,14 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
     lepb200_ctx* ctx = nullptr;
     int r = lepb200_create(&ctx, device);
     if (r) return r;
-    lepb200_ctx* ctxb = nullptr;
+    lepb200_ctx *ctxb = nullptr, *ctxc = nullptr;
     r = lepb200_create(&ctxb, device);
     if (r) { lepb200_destroy(ctx); return r; }
+    r = lepb200_create(&ctxc, device);
+    if (r) { lepb200_destroy(ctx); lepb200_destroy(ctxb); return r; }
     lepb200_codec* c = new lepb200_codec();
     c->ctx = ctx;
-    c->ctx2[0] = ctx; c->ctx2[1] = ctxb;
+    c->ctx2[0] = ctx; c->ctx2[1] = ctxb; c->ctx2[2] = ctxc;
     c->nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     *out = c;
     return LEPB200_OK;
@@ -100,9 +102,8 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
 
 void lepb200_codec_destroy(lepb200_codec* c) {
     if (!c) return;
-    for (int s = 0; s < 2; ++s) if (c->arena[s]) lepb200_pinned_free(c->arena[s]);
-    lepb200_destroy(c->ctx2[0]);
-    lepb200_destroy(c->ctx2[1]);
+    for (int s = 0; s < 3; ++s) if (c->arena[s]) lepb200_pinned_free(c->arena[s]);
+    for (int s = 0; s < 3; ++s) lepb200_destroy(c->ctx2[s]);
     delete c;
 }
 
@@ -112,7 +113,9 @@ const char* lepb200_codec_last_error(const lepb200_codec* c) {
 }
 
 lepb200_ctx* lepb200_codec_ctx(lepb200_codec* c) { return c ? c->ctx : nullptr; }
-uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) { return c ? lepb200_kernel_launches(c->ctx2[0]) + lepb200_kernel_launches(c->ctx2[1]) : 0; }
+uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
+    return c ? lepb200_kernel_launches(c->ctx2[0]) + lepb200_kernel_launches(c->ctx2[1]) + lepb200_kernel_launches(c->ctx2[2]) : 0;
+}
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
 
@@ -207,7 +210,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             for (auto& u : s.js) u.reset();      // fall through to the host Huffman path for this chunk
             s.scans.clear(); s.rowbuf.clear();
         }
-        const int slot = k & 1;
+        const int slot = k % 3;
         if (!reserve_arena(c, slot, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
         uint8_t* arena = static_cast<uint8_t*>(c->arena[slot]);
         parallel_for(m, c->nthreads, [&](int i) {
@@ -258,7 +261,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         double t0 = now_s();
         ChunkState& s = cs[k];
         if (s.on_gpu && s.gpu_rc == 0) {
-            lepb200_ctx* ctx = c->ctx2[k & 1];
+            lepb200_ctx* ctx = c->ctx2[k % 3];
             const int m = s.end - s.begin;
             s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), m);
             if (s.gpu_rc == 0) {
@@ -291,10 +294,19 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 s.seg_base.assign(s.imgs.size() + 1, 0);
                 for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
                 s.gpu_rc = lepb200_encode_upload_resident(ctx, s.imgs.data(), m);
-                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(ctx);
-                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
+                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(ctx);         // kernels A and B queued; fetched by the next stage
             }
-        } else if (s.gpu_rc == 0 && !s.imgs.empty()) s.gpu_rc = lepb200_encode_images(c->ctx2[k & 1], s.imgs.data(), (int)s.imgs.size(), s.streams.data());
+        } else if (s.gpu_rc == 0 && !s.imgs.empty()) {
+            s.gpu_rc = lepb200_encode_upload(c->ctx2[k % 3], s.imgs.data(), (int)s.imgs.size());
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(c->ctx2[k % 3]);
+        }
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_gpu += now_s() - t0;
+    };
+    auto gpu2 = [&](int k) {              // wait for the chunk's kernels, compact, D2H the streams
+        double t0 = now_s();
+        ChunkState& s = cs[k];
+        if (s.gpu_rc == 0 && !s.imgs.empty()) s.gpu_rc = lepb200_encode_fetch(c->ctx2[k % 3], s.streams.data());
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -319,17 +331,21 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         c->t_back += now_s() - t0;
     };
 
-    for (int step = 0; step < nchunks + 2; ++step) {
-        std::thread tf, tg, tb;
+    // 4-stage lock-step pipeline; chunk k lives on context k % 3, so Huffman decode / kernel A of chunk k+1 overlap
+    // on the device with kernel B / compaction / D2H of chunk k (different streams)
+    for (int step = 0; step < nchunks + 3; ++step) {
+        std::thread tf, tg, tg2, tb;
         if (step < nchunks) tf = std::thread(front, step);
         if (step - 1 >= 0 && step - 1 < nchunks) tg = std::thread(gpu, step - 1);
-        if (step - 2 >= 0 && step - 2 < nchunks) tb = std::thread(back, step - 2);
+        if (step - 2 >= 0 && step - 2 < nchunks) tg2 = std::thread(gpu2, step - 2);
+        if (step - 3 >= 0 && step - 3 < nchunks) tb = std::thread(back, step - 3);
         if (tf.joinable()) tf.join();
         if (tg.joinable()) tg.join();
+        if (tg2.joinable()) tg2.join();
         if (tb.joinable()) tb.join();
     }
     int rc = LEPB200_OK;
-    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k & 1]); }
+    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
     for (int i = 0; i < n; ++i) {
         out[i].status = status[i];
         out[i].data = status[i] ? nullptr : c->outputs[i].data();

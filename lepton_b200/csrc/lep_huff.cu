@@ -87,9 +87,22 @@ __device__ __forceinline__ int huff_extend(HBits& b, int s) {      // DEVLI (jpg
 }
 
 constexpr int HUFF_THREADS = 32;
+constexpr int HUFF_SMEM_TABLES = 8;      // tables staged in shared memory when the batch uses few distinct ones
 
+// One symbol per loop iteration (flat state machine): lanes of a warp decode different images, and a nested
+// "for each block / while AC" loop would make every lane wait for the slowest block of the warp at each block end.
 __global__ void __launch_bounds__(HUFF_THREADS)
-lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables) {
+lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables, int ntables) {
+    __shared__ HuffTableDev s_tab[HUFF_SMEM_TABLES];
+    const bool use_smem = ntables <= HUFF_SMEM_TABLES;
+    if (use_smem) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_tab);
+        const int nw = ntables * (int)(sizeof(HuffTableDev) / 4);
+        for (int i = threadIdx.x; i < nw; i += HUFF_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const HuffTableDev* tb = use_smem ? s_tab : tables;
     const int t = blockIdx.x * HUFF_THREADS + threadIdx.x;
     if (t >= njobs) return;
     HuffJob& jb = jobs[t];
@@ -103,47 +116,62 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
     int lastdc[3] = {0, 0, 0};
     int cmp = 0, csc = 0, sub = 0, dpos = 0, mcu = 0;
     int nrows = 0, status = 0, padbit = -1;
-    bool handoff_due = true;
     const int hmul = jb.bch[0] / jb.mcuh, vmul = jb.bcv[0] / jb.mcuv;
     int rstw = rsti;
-    int sta = 0;
-    while (true) {                       // one iteration = one block (flattened decode_jpeg loops)
-        if (handoff_due) {
-            const int mcu_y = ncmp > 1 ? mcu / mcuh : (dpos / (hmul * vmul)) / mcuh;
-            HuffRow r;
-            r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)mcu_y;
-            r.lastdc[0] = (int16_t)lastdc[0]; r.lastdc[1] = (int16_t)lastdc[1]; r.lastdc[2] = (int16_t)lastdc[2];
-            rows[nrows++] = r;
-            handoff_due = false;
+    int bpos = 0;                        // 0: next symbol is the block's DC; 1..63: next AC position
+    bool last_nonzero = true;
+    int16_t* blk = reinterpret_cast<int16_t*>(jb.plane[0]);
+    const HuffTableDev* dct = tb + jb.dc_tab[0];
+    const HuffTableDev* act = tb + jb.ac_tab[0];
+    // first handoff
+    {
+        HuffRow r;
+        r.bitpos = 0; r.mcu_y = 0; r.lastdc[0] = r.lastdc[1] = r.lastdc[2] = 0;
+        rows[nrows++] = r;
+    }
+    bool done = false;
+    while (!done) {
+        // ---- one Huffman symbol (+ its magnitude bits)
+        hb_fill(b);
+        const HuffTableDev* tab = bpos == 0 ? dct : act;
+        const uint32_t top = hb_peek(b, 16);
+        int sym;
+        {
+            const uint32_t f = tab->fast[top >> 7];
+            if (f) { hb_skip(b, (int)(f >> 8)); sym = (int)(f & 0xff); }
+            else {
+                int len = 10, code = (int)(top >> 6);
+                while (len <= 16 && code > tab->maxcode[len]) { ++len; code = (int)(top >> (16 - len)); }
+                if (len > 16) { status = 42; break; }
+                hb_skip(b, len);
+                sym = tab->vals[code + tab->valoff[len]];
+            }
         }
-        // ---- decode_block_seq
-        const HuffTableDev* dct = tables + jb.dc_tab[cmp];
-        const HuffTableDev* act = tables + jb.ac_tab[cmp];
-        int16_t* blk = reinterpret_cast<int16_t*>(jb.plane[cmp]) + (size_t)dpos * 64;
-        int s = huff_symbol(b, dct);
-        if (s < 0 || s > 16) { status = 42; break; }
-        const int16_t dcv = (int16_t)(huff_extend(b, s) + lastdc[cmp]);
-        lastdc[cmp] = dcv;
-        blk[49] = dcv;
-        int bpos = 1;
-        bool last_nonzero = true, eob_seen = false;
-        while (bpos < 64) {
-            const int hc = huff_symbol(b, act);
-            if (hc < 0) { status = 42; break; }
-            if (hc == 0) { eob_seen = true; break; }
-            const int z = hc >> 4;
-            s = hc & 15;
-            const int v = huff_extend(b, s);
+        bool block_done = false;
+        if (bpos == 0) {
+            if (sym > 16) { status = 42; break; }
+            const int16_t dcv = (int16_t)(huff_extend(b, sym) + lastdc[cmp]);
+            lastdc[cmp] = dcv;
+            blk[49] = dcv;
+            bpos = 1;
+            last_nonzero = true;
+        } else if (sym == 0) {                                    // EOB
+            if (bpos > 1 && !last_nonzero) { status = 42; break; }   // "eob after last 0" (jpgcoder.cc:2953)
+            block_done = true;
+        } else {
+            const int z = sym >> 4, sz = sym & 15;
+            const int v = huff_extend(b, sz);
             if (z + bpos >= 64) { status = 200; break; }           // truncated-file fix-up path: not handled here
             bpos += z;
             blk[c_zigzag_to_aligned[bpos++]] = (int16_t)v;
             last_nonzero = v != 0;
+            block_done = bpos >= 64;
         }
-        if (status) break;
-        if (eob_seen && bpos > 1 && !last_nonzero) { status = 42; break; }   // "eob after last 0" (jpgcoder.cc:2953)
+        if (!block_done) continue;
         if (b.bitpos > total_bits) { status = 200; break; }         // entropy data ends inside a block
-        // ---- next position
-        sta = 0;
+        // ---- next block position (next_mcupos / next_mcuposn)
+        int sta = 0;
+        bool handoff_due = false;
         if (ncmp > 1) {
             const int old_mcu = mcu;
             if (++sub >= jb.H[cmp] * jb.V[cmp]) {
@@ -155,6 +183,8 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
                 } else {
                     cmp = csc;
                 }
+                dct = tb + jb.dc_tab[cmp];
+                act = tb + jb.ac_tab[cmp];
             }
             const int H = jb.H[cmp], V = jb.V[cmp];
             if (V > 1) {
@@ -175,6 +205,8 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
             mcu = dpos / (hmul * vmul);
             if ((mcu % mcuh == 0) && (dpos % (hmul * vmul) == 0)) handoff_due = true;
         }
+        blk = reinterpret_cast<int16_t*>(jb.plane[cmp]) + (size_t)dpos * 64;
+        bpos = 0;
         if (b.bitpos >= total_bits) sta = 2;                          // huffr->eof
         if (sta != 0) {
             // abitreader::unpad (bitops.hh:316-332) + padbit bookkeeping (jpgcoder.cc:3260-3271)
@@ -189,9 +221,16 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
             }
             if (padbit != -1) { if (padbit != fb) { status = 42; break; } }
             else padbit = fb;
-            if (sta == 2) break;
+            if (sta == 2) { done = true; break; }
             lastdc[0] = lastdc[1] = lastdc[2] = 0;                    // restart interval
             rstw = rsti;
+        }
+        if (handoff_due) {
+            const int mcu_y = ncmp > 1 ? mcu / mcuh : (dpos / (hmul * vmul)) / mcuh;
+            HuffRow r;
+            r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)mcu_y;
+            r.lastdc[0] = (int16_t)lastdc[0]; r.lastdc[1] = (int16_t)lastdc[1]; r.lastdc[2] = (int16_t)lastdc[2];
+            rows[nrows++] = r;
         }
     }
     if (status == 0) {
