@@ -112,25 +112,34 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
     b.acc = 0; b.n = 0; b.wi = 0; b.nwords = (jb.nbytes + 3) / 4; b.bitpos = 0;
     const unsigned long long total_bits = (unsigned long long)jb.nbytes * 8;
     HuffRow* rows = reinterpret_cast<HuffRow*>(jb.rows);
-    const int ncmp = jb.ncmp, mcuh = jb.mcuh, mcuc = jb.mcuh * jb.mcuv, rsti = jb.rsti;
-    int lastdc[3] = {0, 0, 0};
-    int cmp = 0, csc = 0, sub = 0, dpos = 0, mcu = 0;
+    // everything the per-block bookkeeping needs lives in registers; positions are tracked incrementally so that the
+    // block-end path (which some lane of the warp takes on almost every iteration) has no divisions and no loads
+    const int ncmp = jb.ncmp, mcuh = jb.mcuh, mcuv = jb.mcuv, rsti = jb.rsti;
+    const int H0 = jb.H[0], V0 = jb.V[0], H1 = ncmp > 1 ? jb.H[1] : 1, V1 = ncmp > 1 ? jb.V[1] : 1, H2 = ncmp > 2 ? jb.H[2] : 1, V2 = ncmp > 2 ? jb.V[2] : 1;
+    const int W0 = jb.bch[0], W1 = ncmp > 1 ? jb.bch[1] : 0, W2 = ncmp > 2 ? jb.bch[2] : 0;
+    int16_t* const P0 = reinterpret_cast<int16_t*>(jb.plane[0]);
+    int16_t* const P1 = reinterpret_cast<int16_t*>(jb.plane[1]);
+    int16_t* const P2 = reinterpret_cast<int16_t*>(jb.plane[2]);
+    const HuffTableDev* const D0 = tb + jb.dc_tab[0]; const HuffTableDev* const A0 = tb + jb.ac_tab[0];
+    const HuffTableDev* const D1 = tb + jb.dc_tab[1]; const HuffTableDev* const A1 = tb + jb.ac_tab[1];
+    const HuffTableDev* const D2 = tb + jb.dc_tab[2]; const HuffTableDev* const A2 = tb + jb.ac_tab[2];
+    const int nch0 = jb.nch[0], ncv0 = jb.ncv[0];
+    int dc0 = 0, dc1 = 0, dc2 = 0;                   // last DCs
+    int cmp = 0, sx = 0, sy = 0, mx = 0, my = 0;     // component, block within MCU, MCU position
+    int bx = 0, by = 0;                              // single-component scans: block position in the plane
     int nrows = 0, status = 0, padbit = -1;
-    const int hmul = jb.bch[0] / jb.mcuh, vmul = jb.bcv[0] / jb.mcuv;
     int rstw = rsti;
-    int bpos = 0;                        // 0: next symbol is the block's DC; 1..63: next AC position
+    int bpos = 0;                                    // 0: next symbol is the block's DC; 1..63: next AC position
     bool last_nonzero = true;
-    int16_t* blk = reinterpret_cast<int16_t*>(jb.plane[0]);
-    const HuffTableDev* dct = tb + jb.dc_tab[0];
-    const HuffTableDev* act = tb + jb.ac_tab[0];
-    // first handoff
+    int16_t* blk = P0;
+    const HuffTableDev* dct = D0;
+    const HuffTableDev* act = A0;
     {
         HuffRow r;
         r.bitpos = 0; r.mcu_y = 0; r.lastdc[0] = r.lastdc[1] = r.lastdc[2] = 0;
         rows[nrows++] = r;
     }
-    bool done = false;
-    while (!done) {
+    while (true) {
         // ---- one Huffman symbol (+ its magnitude bits)
         hb_fill(b);
         const HuffTableDev* tab = bpos == 0 ? dct : act;
@@ -150,8 +159,9 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
         bool block_done = false;
         if (bpos == 0) {
             if (sym > 16) { status = 42; break; }
-            const int16_t dcv = (int16_t)(huff_extend(b, sym) + lastdc[cmp]);
-            lastdc[cmp] = dcv;
+            const int last = cmp == 0 ? dc0 : (cmp == 1 ? dc1 : dc2);
+            const int16_t dcv = (int16_t)(huff_extend(b, sym) + last);
+            if (cmp == 0) dc0 = dcv; else if (cmp == 1) dc1 = dcv; else dc2 = dcv;
             blk[49] = dcv;
             bpos = 1;
             last_nonzero = true;
@@ -169,43 +179,40 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
         }
         if (!block_done) continue;
         if (b.bitpos > total_bits) { status = 200; break; }         // entropy data ends inside a block
-        // ---- next block position (next_mcupos / next_mcuposn)
+        // ---- next block position (next_mcupos / next_mcuposn), incremental
         int sta = 0;
         bool handoff_due = false;
         if (ncmp > 1) {
-            const int old_mcu = mcu;
-            if (++sub >= jb.H[cmp] * jb.V[cmp]) {
-                sub = 0;
-                if (++csc >= ncmp) {
-                    csc = 0; cmp = 0; ++mcu;
-                    if (mcu >= mcuc) sta = 2;
+            const int H = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), V = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
+            if (++sx >= H) { sx = 0; ++sy; }
+            if (sy >= V) {                                          // component done within this MCU
+                sy = 0;
+                if (++cmp >= ncmp) {
+                    cmp = 0;
+                    if (++mx >= mcuh) { mx = 0; ++my; handoff_due = true; }
+                    if (my >= mcuv) sta = 2;
                     else if (rsti > 0 && --rstw == 0) sta = 1;
-                } else {
-                    cmp = csc;
                 }
-                dct = tb + jb.dc_tab[cmp];
-                act = tb + jb.ac_tab[cmp];
+                dct = cmp == 0 ? D0 : (cmp == 1 ? D1 : D2);
+                act = cmp == 0 ? A0 : (cmp == 1 ? A1 : A2);
             }
-            const int H = jb.H[cmp], V = jb.V[cmp];
-            if (V > 1) {
-                const int my = mcu / mcuh, mx = mcu - my * mcuh, sy = sub / H, sx = sub - sy * H;
-                dpos = (my * V + sy) * jb.bch[cmp] + mx * H + sx;
-            } else if (H > 1) {
-                dpos = mcu * (H * V) + sub;
-            } else {
-                dpos = mcu;
-            }
-            if (mcu % mcuh == 0 && old_mcu != mcu) handoff_due = true;
+            const int Hn = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), Vn = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
+            const int Wn = cmp == 0 ? W0 : (cmp == 1 ? W1 : W2);
+            int16_t* Pn = cmp == 0 ? P0 : (cmp == 1 ? P1 : P2);
+            const int dpos = (my * Vn + sy) * Wn + mx * Hn + sx;
+            blk = Pn + (size_t)dpos * 64;
         } else {
-            dpos++;
-            if (jb.bch[0] != jb.nch[0] && dpos % jb.bch[0] == jb.nch[0]) dpos += jb.bch[0] - jb.nch[0];
-            if (jb.bcv[0] != jb.ncv[0] && dpos / jb.bch[0] == jb.ncv[0]) dpos = jb.bch[0] * jb.bcv[0];
-            if (dpos >= jb.bch[0] * jb.bcv[0]) sta = 2;
+            // next_mcuposn (jpgcoder.cc:5432-5456): row-major over the nch x ncv coded blocks of the bch x bcv plane
+            if (++bx >= nch0) { bx = 0; ++by; }
+            if (by >= ncv0) sta = 2;
             else if (rsti > 0 && --rstw == 0) sta = 1;
-            mcu = dpos / (hmul * vmul);
-            if ((mcu % mcuh == 0) && (dpos % (hmul * vmul) == 0)) handoff_due = true;
+            const int dpos = by * W0 + bx;
+            blk = P0 + (size_t)dpos * 64;
+            // handoff when the block index is a multiple of one "MCU row" worth of blocks (jpgcoder.cc:3084-3087)
+            const int per_mcu = H0 * V0;
+            if (sta != 2 && (dpos % per_mcu) == 0 && ((dpos / per_mcu) % mcuh) == 0) handoff_due = true;
+            if (sta != 2) { my = (dpos / per_mcu) / mcuh; }
         }
-        blk = reinterpret_cast<int16_t*>(jb.plane[cmp]) + (size_t)dpos * 64;
         bpos = 0;
         if (b.bitpos >= total_bits) sta = 2;                          // huffr->eof
         if (sta != 0) {
@@ -221,22 +228,22 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
             }
             if (padbit != -1) { if (padbit != fb) { status = 42; break; } }
             else padbit = fb;
-            if (sta == 2) { done = true; break; }
-            lastdc[0] = lastdc[1] = lastdc[2] = 0;                    // restart interval
+            if (sta == 2) break;
+            dc0 = dc1 = dc2 = 0;                                      // restart interval
             rstw = rsti;
         }
         if (handoff_due) {
-            const int mcu_y = ncmp > 1 ? mcu / mcuh : (dpos / (hmul * vmul)) / mcuh;
             HuffRow r;
-            r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)mcu_y;
-            r.lastdc[0] = (int16_t)lastdc[0]; r.lastdc[1] = (int16_t)lastdc[1]; r.lastdc[2] = (int16_t)lastdc[2];
+            r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)my;
+            r.lastdc[0] = (int16_t)dc0; r.lastdc[1] = (int16_t)dc1; r.lastdc[2] = (int16_t)dc2;
             rows[nrows++] = r;
         }
     }
+    const int final_mcu_y = ncmp > 1 ? my : (by >= ncv0 ? mcuv : my);
     if (status == 0) {
         HuffRow r;
-        r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)(mcu / mcuh);
-        r.lastdc[0] = (int16_t)lastdc[0]; r.lastdc[1] = (int16_t)lastdc[1]; r.lastdc[2] = (int16_t)lastdc[2];
+        r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)final_mcu_y;
+        r.lastdc[0] = (int16_t)dc0; r.lastdc[1] = (int16_t)dc1; r.lastdc[2] = (int16_t)dc2;
         rows[nrows++] = r;
         if (b.bitpos < total_bits) status = 42;                      // "unneeded data found after coded image data"
     }
