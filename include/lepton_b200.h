@@ -139,6 +139,8 @@ float lepb200_last_kernel_ms(lepb200_ctx* ctx);
 /* Encode only: device time of kernel A (symbolisation + model update) within the last launch; the rest of
  * lepb200_last_kernel_ms is kernel B (range coder). */
 float lepb200_last_symbolise_ms(lepb200_ctx* ctx);
+/* Device time of the Huffman-decode kernel of the last lepb200_huffman_decode_to_device call, milliseconds. */
+float lepb200_last_huffman_ms(lepb200_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx);
 /* Sum over the last uploaded batch of 128 * coded blocks + stream bytes (SURVEY.md section 8(d) algorithmic bytes);
@@ -173,6 +175,8 @@ void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
 /* 1 (default): Huffman-decode on the GPU when every file of a chunk is a complete single-scan baseline JPEG;
  * 0: always Huffman-decode on host threads */
 void lepb200_codec_set_gpu_huffman(lepb200_codec* codec, int on);
+/* device milliseconds of the last chunk's GPU Huffman-decode kernel (diagnostic) */
+double lepb200_codec_last_huffman_ms(const lepb200_codec* codec);
 /* summed seconds spent by the last call's stages (they overlap): JPEG parse + Huffman decode | H2D + kernel + D2H | container writing */
 void lepb200_codec_last_timing(const lepb200_codec* codec, double* front_s, double* gpu_s, double* back_s);
 /* n JPEG files in, n .lep files out */

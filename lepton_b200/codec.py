@@ -313,6 +313,8 @@ def _bind_file_api(L):
     L.lepb200_codec_set_chunk_images.restype = None
     L.lepb200_codec_set_gpu_huffman.argtypes = [vp, ctypes.c_int]
     L.lepb200_codec_set_gpu_huffman.restype = None
+    L.lepb200_codec_last_huffman_ms.argtypes = [vp]
+    L.lepb200_codec_last_huffman_ms.restype = ctypes.c_double
     L.lepb200_compress_jpegs.argtypes = [vp, ctypes.POINTER(_Buffer), ctypes.c_int, ctypes.POINTER(_Result)]
     L.lepb200_compress_jpegs.restype = ctypes.c_int
     L.lepb200_host_jpeg_open.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
@@ -525,7 +527,8 @@ class LeptonB200FileCodec:
     def last_timing(self):
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         self._L.lepb200_codec_last_timing(self._c, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-        return {"front_s": a.value, "gpu_s": b.value, "back_s": c.value}
+        return {"front_s": a.value, "gpu_s": b.value, "back_s": c.value,
+                "huffman_kernel_ms_last_chunk": float(self._L.lepb200_codec_last_huffman_ms(self._c))}
 
     @property
     def kernel_launches(self) -> int:

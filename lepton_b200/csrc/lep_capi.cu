@@ -81,7 +81,7 @@ struct lepb200_ctx {
     size_t row_stride = 0;
     int grid = 0;
     bool have_batch = false, launched = false, is_encode = true;
-    float last_ms = -1.f, last_ms_a = -1.f;
+    float last_ms = -1.f, last_ms_a = -1.f, last_ms_huff = -1.f;
     uint64_t launches = 0;
     uint64_t alg_bytes = 0;
     uint64_t coded_blocks = 0;
@@ -320,6 +320,7 @@ float lepb200_last_symbolise_ms(lepb200_ctx* ctx) {
     lepb200_last_kernel_ms(ctx);
     return ctx->last_ms_a;
 }
+float lepb200_last_huffman_ms(lepb200_ctx* ctx) { return ctx ? ctx->last_ms_huff : -1.f; }
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx) { return ctx ? ctx->alg_bytes : 0; }
 
@@ -438,9 +439,11 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(cudaMemcpyAsync(ctx->d_huff.p, hs, huff_total, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_hjobs.p, jobs.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
     lep_huffdecode_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, ctx->stream>>>(
         static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
     ctx->launches += 1;
     CK(ctx->h_hjobs.reserve(sizeof(HuffJob) * n + rows_total));
     HuffJob* hj = static_cast<HuffJob*>(ctx->h_hjobs.p);
@@ -448,6 +451,7 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(cudaMemcpyAsync(hj, ctx->d_hjobs.p, sizeof(HuffJob) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hrows, ctx->d_hrows.p, rows_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_ms_huff, ctx->ev0, ctx->ev_mid);
     for (int i = 0; i < n; ++i) {
         scans[i].status = hj[i].status;
         scans[i].padbit = hj[i].padbit;

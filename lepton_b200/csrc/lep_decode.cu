@@ -94,6 +94,7 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sm.rcp[i] = i < 2 ? 0u : (uint32_t)((0x100000000ull + i - 1) / i);
     __syncthreads();
     DecWarpSmem& ws = sm.w[warp_in_cta];
+    const int r0 = c_aligned_to_raster[2 * lane], r1 = c_aligned_to_raster[2 * lane + 1];   // once: per-lane constant-memory indices serialise
     uint16_t* model = model_pool + (size_t)gwarp * M_TOTAL;
     uint8_t* rowbuf = row_pool + (size_t)gwarp * row_pool_stride;
 
@@ -165,7 +166,6 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 const bool has_left = x > 0;
                 uint32_t nabv = 0;
                 if (has_above && x + 1 < w) nabv = abovep[(size_t)(x + 1) * 32 + lane];
-                const int r0 = c_aligned_to_raster[2 * lane], r1 = c_aligned_to_raster[2 * lane + 1];
                 ws.rast[2][r0] = (int16_t)h_lo(abv); ws.rast[2][r1] = (int16_t)h_hi(abv);
                 int16_t* rcur = ws.rast[pp];
                 const int16_t* rleft = ws.rast[pp ^ 1];

@@ -34,6 +34,8 @@ struct EncWarpSmem {
 
 struct EncShared {
     uint32_t rcp[512];
+    uint8_t a2r[64];          // aligned -> raster and nz -> bin tables: per-lane indices, so not in constant memory
+    uint8_t nzbin[64];
     EncWarpSmem w[ENC_WARPS_PER_CTA];
 };
 
@@ -82,7 +84,9 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
     const int warp_in_cta = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * ENC_WARPS_PER_CTA + warp_in_cta;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sm.rcp[i] = i < 2 ? 0u : (uint32_t)((0x100000000ull + i - 1) / i);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { sm.a2r[i] = c_aligned_to_raster[i]; sm.nzbin[i] = i < 50 ? c_nonzero_to_bin[i] : 0; }
     __syncthreads();
+    const int r0 = sm.a2r[2 * lane], r1 = sm.a2r[2 * lane + 1];      // raster positions of this lane's two coefficients
     EncWarpSmem& ws = sm.w[warp_in_cta];
     uint16_t* model = model_pool + (size_t)gwarp * M_TOTAL;
     uint8_t* rowbuf = row_pool + (size_t)gwarp * row_pool_stride;
@@ -161,7 +165,6 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
 
                 // ---------------- raster copies for the gathers (IDCT, Lakhani edge predictor)
                 {
-                    int r0 = c_aligned_to_raster[2 * lane], r1 = c_aligned_to_raster[2 * lane + 1];
                     ws.rast[pp][r0] = (int16_t)h_lo(cur); ws.rast[pp][r1] = (int16_t)h_hi(cur);
                     ws.rast[2][r0] = (int16_t)h_lo(abv); ws.rast[2][r1] = (int16_t)h_hi(abv);
                 }
@@ -215,9 +218,9 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                             const int v = h ? c1v : c0v, av = h ? a1 : a0, len = min(h ? len1 : len0, 11);
                             const int prior = h ? pr1 : pr0;
                             const int left_nz = nz - (h ? before1 : before0);
-                            const int bin = c_nonzero_to_bin[left_nz];
+                            const int bin = sm.nzbin[left_nz];
                             const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
-                            const int coord = c_aligned_to_raster[zz];
+                            const int coord = h ? r1 : r0;
                             uint32_t ea = m_exp7(ci, bin, zz, bsr);
                             int o = off;
                             const int nexp = min(len + 1, 11);
@@ -233,8 +236,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                     // a lane's two coefficients: keep the max of both for eob
                     {
                         int ex = 0, ey = 0;
-                        if (e0) { int co = c_aligned_to_raster[2 * lane]; ex = co & 7; ey = co >> 3; }
-                        if (e1) { int co = c_aligned_to_raster[2 * lane + 1]; ex = max(ex, co & 7); ey = max(ey, co >> 3); }
+                        if (e0) { ex = r0 & 7; ey = r0 >> 3; }
+                        if (e1) { ex = max(ex, r1 & 7); ey = max(ey, r1 >> 3); }
                         eobx = __reduce_max_sync(FULL, ex);
                         eoby = __reduce_max_sync(FULL, ey);
                     }
@@ -368,10 +371,14 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
 // vpx_start_encode / vpx_write / vpx_stop_encode (src/vp8/encoder/boolwriter.cc:17-35, boolwriter.hh:48-118)
 // over the (probability, bit) tokens produced by kernel A.  Per-thread state; bytes go straight to the segment's
 // stream, the carry walks back over already written 0xff bytes exactly like the reference.
-// Output staging: the logical stream is  M[0..mpos) ++ [cache] ++ [0xff]*run  where only M is in memory.  A carry
-// then never has to read memory back in the common case: it increments `cache` and turns the pending 0xff run into
-// zeros.  (The reference walks back over memory, boolwriter.hh:96-105; the byte sequence produced is identical.)
-struct RcState { uint32_t low, range; int count; uint32_t mpos, cap; uint8_t* buf; int cache; uint32_t run; };
+// The coder state is kept as a 64-bit window `acc` over the not-yet-emitted low end of the code value and the count
+// `U` of bits in it (the reference keeps 24+8 bits and emits a byte as soon as one is complete, boolwriter.hh:88-112;
+// here up to four decisions are absorbed before complete bytes are peeled off, so the per-decision chain is
+// split/select/normalise only).  A byte leaves through a small staging state -- the last byte not yet written plus a
+// run of pending 0xff bytes -- so a carry (bit U of acc) normally needs no memory access: it increments the staged byte
+// and turns the 0xff run into zeros.  The byte sequence is identical to the reference's walk-back over memory
+// (boolwriter.hh:96-105); the rare carry into a staged 0xff falls back to exactly that walk.
+struct RcState { unsigned long long acc; uint32_t range; int U; uint32_t mpos, cap; uint8_t* buf; int cache; uint32_t run; };
 
 __device__ __forceinline__ void rc_store(RcState& w, uint32_t byte) {
     if (w.mpos < w.cap) asm volatile("st.global.u8 [%0], %1;" ::"l"(w.buf + w.mpos), "r"(byte) : "memory");
@@ -381,7 +388,6 @@ __device__ __forceinline__ void rc_store(RcState& w, uint32_t byte) {
 __device__ __forceinline__ void rc_emit_slow(RcState& w, uint32_t b, bool carry) {
     if (carry) {
         if (w.cache == 0xff || w.cache < 0) {
-            // carry has to travel into bytes already in memory: same walk as the reference
             long x = (long)w.mpos - 1;
             while (x >= 0 && w.buf[x] == 0xff) { w.buf[x] = 0; --x; }
             if (x >= 0) w.buf[x] += 1;
@@ -402,33 +408,33 @@ __device__ __forceinline__ void rc_emit_slow(RcState& w, uint32_t b, bool carry)
     w.cache = (int)b;
     w.run = 0;
 }
-
+__device__ __forceinline__ void rc_emit(RcState& w, uint32_t b, bool carry) {
+    const bool fast = w.run == 0 && b != 0xff && w.cache >= 0 && !(carry && w.cache == 0xff);
+    if (fast) {
+        rc_store(w, (uint32_t)w.cache + (carry ? 1u : 0u));
+        w.cache = (int)b;
+    } else {
+        rc_emit_slow(w, b, carry);
+    }
+}
+// peel complete bytes off the top of the window (a byte is complete once 32 bits are pending, boolwriter.hh:88)
+__device__ __forceinline__ void rc_drain(RcState& w) {
+    while (w.U >= 32) {
+        const uint32_t top = (uint32_t)(w.acc >> (w.U - 8));          // 8 bits + the carry above them
+        w.acc &= (1ull << (w.U - 8)) - 1;
+        w.U -= 8;
+        rc_emit(w, top & 0xff, (top >> 8) != 0);
+    }
+}
+// vpx_write minus the byte emission: 4 of these fit between two drains (U <= 31 + 4*7 + carry bit < 64)
 __device__ __forceinline__ void rc_put(RcState& w, uint32_t bit, uint32_t prob) {
     const uint32_t split = 1 + (((w.range - 1) * prob) >> 8);
     uint32_t range = bit ? w.range - split : split;
-    uint32_t low = w.low + (bit ? split : 0);
-    int shift = __clz(range) - 24;
-    range <<= shift;
-    int count = w.count + shift;
-    // byte emission, written so that the common case is straight-line predicated code (lanes of a warp hit it at
-    // different decisions; a real branch here would diverge on almost every decision)
-    const bool emit = count >= 0;
-    const int offset = shift - count;
-    const bool carry = emit && (((low << ((offset - 1) & 31)) & 0x80000000u) != 0);
-    const uint32_t b = (low >> ((24 - offset) & 31)) & 0xff;
-    const bool fast = emit && w.run == 0 && b != 0xff && w.cache >= 0 && !(carry && w.cache == 0xff);
-    if (fast) {
-        if (w.mpos < w.cap) asm volatile("st.global.u8 [%0], %1;" ::"l"(w.buf + w.mpos), "r"((uint32_t)w.cache + (carry ? 1u : 0u)) : "memory");
-        w.mpos++;
-        w.cache = (int)b;
-    }
-    if (emit && !fast) rc_emit_slow(w, b, carry);
-    low = emit ? ((low << (offset & 31)) & 0xffffff) : low;
-    shift = emit ? count : shift;
-    count = emit ? count - 8 : count;
-    w.low = low << shift;
-    w.count = count;
-    w.range = range;
+    w.acc += bit ? split : 0u;
+    const int shift = __clz(range) - 24;
+    w.range = range << shift;
+    w.acc <<= shift;
+    w.U += shift;
 }
 
 constexpr int RC_THREADS = 32;
@@ -440,9 +446,9 @@ lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     SegDesc& sd = segs[order[t]];
     if (sd.status != ST_OK) return;
     RcState w;
-    w.low = 0; w.range = 255; w.count = -24; w.mpos = 0; w.cap = sd.cap; w.buf = reinterpret_cast<uint8_t*>(sd.stream);
+    w.acc = 0; w.range = 255; w.U = 8; w.mpos = 0; w.cap = sd.cap; w.buf = reinterpret_cast<uint8_t*>(sd.stream);
     w.cache = -1; w.run = 0;
-    rc_put(w, 0, 128);                                               // marker bit
+    rc_put(w, 0, 128);                                               // vpx_start_encode marker bit (boolwriter.cc:17-24)
     const uint16_t* tok = token_base + sd.tokens;
     const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
@@ -456,17 +462,22 @@ lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
         const uint4 cur = r0;
         r0 = r1; r1 = r2; r2 = r3;
         r3 = i + 4 < nfull ? __ldg(tok4 + i + 4) : make_uint4(0, 0, 0, 0);
-        const uint32_t v[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            rc_put(w, (v[m] >> 8) & 1, v[m] & 0xff);
-            rc_put(w, (v[m] >> 24) & 1, (v[m] >> 16) & 0xff);
-        }
+        rc_drain(w);
+        rc_put(w, (cur.x >> 8) & 1, cur.x & 0xff);
+        rc_put(w, (cur.x >> 24) & 1, (cur.x >> 16) & 0xff);
+        rc_put(w, (cur.y >> 8) & 1, cur.y & 0xff);
+        rc_put(w, (cur.y >> 24) & 1, (cur.y >> 16) & 0xff);
+        rc_drain(w);
+        rc_put(w, (cur.z >> 8) & 1, cur.z & 0xff);
+        rc_put(w, (cur.z >> 24) & 1, (cur.z >> 16) & 0xff);
+        rc_put(w, (cur.w >> 8) & 1, cur.w & 0xff);
+        rc_put(w, (cur.w >> 24) & 1, (cur.w >> 16) & 0xff);
     }
 #pragma unroll 1
-    for (uint32_t i = nfull * 8; i < ntok; ++i) { const uint32_t v = tok[i]; rc_put(w, (v >> 8) & 1, v & 0xff); }
+    for (uint32_t i = nfull * 8; i < ntok; ++i) { const uint32_t v = tok[i]; rc_drain(w); rc_put(w, (v >> 8) & 1, v & 0xff); }
 #pragma unroll 1
-    for (int i = 0; i < 32; ++i) rc_put(w, 0, 128);                  // vpx_stop_encode
+    for (int i = 0; i < 32; ++i) { rc_drain(w); rc_put(w, 0, 128); }   // vpx_stop_encode (boolwriter.cc:26-35)
+    rc_drain(w);
     // drain the staging, then the trailing-marker rule of vpx_stop_encode (boolwriter.cc:32-34)
     uint32_t last = 0;
     if (w.cache >= 0) { rc_store(w, (uint32_t)w.cache); last = (uint32_t)w.cache; }

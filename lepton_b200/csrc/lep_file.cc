@@ -30,7 +30,7 @@ struct lepb200_codec {
     std::vector<std::vector<uint8_t>> outputs;
     std::string err;
     // timing of the last call (seconds): parse+huffman, gpu (upload+kernel+fetch), container
-    double t_front = 0, t_gpu = 0, t_back = 0;
+    double t_front = 0, t_gpu = 0, t_back = 0, t_huff_ms = 0;
 };
 
 namespace {
@@ -118,6 +118,7 @@ uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
 }
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
+double lepb200_codec_last_huffman_ms(const lepb200_codec* c) { return c ? c->t_huff_ms : -1.0; }
 
 void lepb200_codec_last_timing(const lepb200_codec* c, double* front_s, double* gpu_s, double* back_s) {
     if (!c) return;
@@ -264,6 +265,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             lepb200_ctx* ctx = c->ctx2[k % 3];
             const int m = s.end - s.begin;
             s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), m);
+            c->t_huff_ms = lepb200_last_huffman_ms(ctx);
             if (s.gpu_rc == 0) {
                 int nseg_total = 0;
                 int16_t* none[4] = {nullptr, nullptr, nullptr, nullptr};

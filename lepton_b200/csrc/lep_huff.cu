@@ -94,6 +94,8 @@ constexpr int HUFF_SMEM_TABLES = 8;      // tables staged in shared memory when 
 __global__ void __launch_bounds__(HUFF_THREADS)
 lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables, int ntables) {
     __shared__ HuffTableDev s_tab[HUFF_SMEM_TABLES];
+    __shared__ uint8_t s_zz[64];          // per-lane indices differ: constant memory would serialise the lookups
+    for (int i = threadIdx.x; i < 64; i += HUFF_THREADS) s_zz[i] = c_zigzag_to_aligned[i];
     const bool use_smem = ntables <= HUFF_SMEM_TABLES;
     if (use_smem) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
@@ -173,7 +175,7 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
             const int v = huff_extend(b, sz);
             if (z + bpos >= 64) { status = 200; break; }           // truncated-file fix-up path: not handled here
             bpos += z;
-            blk[c_zigzag_to_aligned[bpos++]] = (int16_t)v;
+            blk[s_zz[bpos++]] = (int16_t)v;
             last_nonzero = v != 0;
             block_done = bpos >= 64;
         }
