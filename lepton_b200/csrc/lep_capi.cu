@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/lepton_b200.h"
@@ -423,7 +424,6 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(ctx->d_planes.reserve(plane_total + 256));
     CK(ctx->d_huff.reserve(huff_total + 256));
     CK(ctx->d_hrows.reserve(rows_total + 256));
-    CK(ctx->d_hjobs.reserve(sizeof(HuffJob) * n));
     CK(ctx->d_htabs.reserve(sizeof(HuffTableDev) * std::max<size_t>(1, tabs.size())));
     CK(ctx->h_stage.reserve(huff_total + 256));
     uint8_t* hs = static_cast<uint8_t*>(ctx->h_stage.p);
@@ -435,13 +435,36 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         jb.rows += (unsigned long long)(uintptr_t)ctx->d_hrows.p;
         for (int c = 0; c < jb.ncmp; ++c) jb.plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
     }
+    // sort job indices by geometry; the device job array is stored in that order (perm[k] = caller index)
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    auto geom_key = [&](int i) {
+        const HuffJob& j = jobs[i];
+        return std::make_tuple(j.ncmp, j.mcuh, j.mcuv, j.rsti, j.H[0], j.V[0], j.H[1], j.V[1], j.H[2], j.V[2], j.nch[0], j.ncv[0]);
+    };
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return geom_key(a) < geom_key(b); });
+    std::vector<HuffJob> sorted(n);
+    for (int k = 0; k < n; ++k) sorted[k] = jobs[perm[k]];
+    std::vector<int2> groups;
+    for (int k = 0; k < n;) {
+        int e = k + 1;
+        while (e < n && e - k < 32 && geom_key(perm[e]) == geom_key(perm[k])) ++e;
+        groups.push_back(make_int2(k, e - k));
+        k = e;
+    }
+    CK(ctx->d_hjobs.reserve(align_up(sizeof(HuffJob) * n, 256) + sizeof(int2) * groups.size()));
     CK(cudaMemsetAsync(ctx->d_planes.p, 0, plane_total, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_huff.p, hs, huff_total, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_hjobs.p, jobs.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hjobs.p, sorted.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_hjobs.p) + align_up(sizeof(HuffJob) * n, 256), groups.data(), sizeof(int2) * groups.size(),
+                       cudaMemcpyHostToDevice, ctx->stream));
     if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    // group images of identical geometry, up to 32 per warp (jobs stay in caller order; groups index into them through
+    // a permutation applied to the uploaded job array)
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    lep_huffdecode_kernel<<<(n + HUFF_THREADS - 1) / HUFF_THREADS, HUFF_THREADS, 0, ctx->stream>>>(
-        static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
+    lep_huffdecode_kernel<<<(int)groups.size(), HUFF_THREADS, 0, ctx->stream>>>(
+        static_cast<HuffJob*>(ctx->d_hjobs.p), reinterpret_cast<const int2*>(static_cast<uint8_t*>(ctx->d_hjobs.p) + align_up(sizeof(HuffJob) * n, 256)),
+        (int)groups.size(), static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
     ctx->launches += 1;
@@ -452,14 +475,15 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(cudaMemcpyAsync(hrows, ctx->d_hrows.p, rows_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_ms_huff, ctx->ev0, ctx->ev_mid);
-    for (int i = 0; i < n; ++i) {
-        scans[i].status = hj[i].status;
-        scans[i].padbit = hj[i].padbit;
-        scans[i].end_bitpos = hj[i].end_bitpos;
-        scans[i].nrows = hj[i].nrows;
+    for (int k = 0; k < n; ++k) {
+        const int i = perm[k];
+        scans[i].status = hj[k].status;
+        scans[i].padbit = hj[k].padbit;
+        scans[i].end_bitpos = hj[k].end_bitpos;
+        scans[i].nrows = hj[k].nrows;
         const size_t off = (size_t)(jobs[i].rows - (unsigned long long)(uintptr_t)ctx->d_hrows.p);
         static_assert(sizeof(HuffRow) == sizeof(lepb200_huffrow), "row record layout");
-        if (hj[i].nrows > 0) memcpy(scans[i].rows, hrows + off, sizeof(HuffRow) * (size_t)std::min(hj[i].nrows, scans[i].mcuv + 1));
+        if (hj[k].nrows > 0) memcpy(scans[i].rows, hrows + off, sizeof(HuffRow) * (size_t)std::min(hj[k].nrows, scans[i].mcuv + 1));
     }
     ctx->resident_plane_total = plane_total;
     ctx->resident_images = n;
