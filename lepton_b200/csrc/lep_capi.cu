@@ -435,36 +435,18 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         jb.rows += (unsigned long long)(uintptr_t)ctx->d_hrows.p;
         for (int c = 0; c < jb.ncmp; ++c) jb.plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
     }
-    // sort job indices by geometry; the device job array is stored in that order (perm[k] = caller index)
     std::vector<int> perm(n);
-    for (int i = 0; i < n; ++i) perm[i] = i;
-    auto geom_key = [&](int i) {
-        const HuffJob& j = jobs[i];
-        return std::make_tuple(j.ncmp, j.mcuh, j.mcuv, j.rsti, j.H[0], j.V[0], j.H[1], j.V[1], j.H[2], j.V[2], j.nch[0], j.ncv[0]);
-    };
-    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return geom_key(a) < geom_key(b); });
-    std::vector<HuffJob> sorted(n);
-    for (int k = 0; k < n; ++k) sorted[k] = jobs[perm[k]];
-    std::vector<int2> groups;
-    for (int k = 0; k < n;) {
-        int e = k + 1;
-        while (e < n && e - k < 32 && geom_key(perm[e]) == geom_key(perm[k])) ++e;
-        groups.push_back(make_int2(k, e - k));
-        k = e;
-    }
-    CK(ctx->d_hjobs.reserve(align_up(sizeof(HuffJob) * n, 256) + sizeof(int2) * groups.size()));
+    for (int i = 0; i < n; ++i) perm[i] = i;          // one warp per image: no geometry grouping needed
+    const std::vector<HuffJob>& sorted = jobs;
+    CK(ctx->d_hjobs.reserve(align_up(sizeof(HuffJob) * n, 256)));
     CK(cudaMemsetAsync(ctx->d_planes.p, 0, plane_total, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_huff.p, hs, huff_total, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_hjobs.p, sorted.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_hjobs.p) + align_up(sizeof(HuffJob) * n, 256), groups.data(), sizeof(int2) * groups.size(),
-                       cudaMemcpyHostToDevice, ctx->stream));
+
     if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
-    // group images of identical geometry, up to 32 per warp (jobs stay in caller order; groups index into them through
-    // a permutation applied to the uploaded job array)
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    lep_huffdecode_kernel<<<(int)groups.size(), HUFF_THREADS, 0, ctx->stream>>>(
-        static_cast<HuffJob*>(ctx->d_hjobs.p), reinterpret_cast<const int2*>(static_cast<uint8_t*>(ctx->d_hjobs.p) + align_up(sizeof(HuffJob) * n, 256)),
-        (int)groups.size(), static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
+    lep_huffdecode_kernel<<<(n + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_THREADS, 0, ctx->stream>>>(
+        static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
     ctx->launches += 1;

@@ -86,18 +86,25 @@ __device__ __forceinline__ int huff_extend(HBits& b, int s) {      // DEVLI (jpg
     return n >= (1 << (s - 1)) ? n : n + 1 - (1 << s);
 }
 
-constexpr int HUFF_THREADS = 32;
+constexpr int HUFF_WARPS = 4;
+constexpr int HUFF_THREADS = HUFF_WARPS * 32;
 constexpr int HUFF_SMEM_TABLES = 8;      // tables staged in shared memory when the batch uses few distinct ones
 
-// One WARP per group of up to 32 images WITH IDENTICAL GEOMETRY (the host sorts the batch): the walk over MCUs /
-// components / blocks is then warp-uniform and costs a handful of instructions per block, and only the symbol loop
-// inside a block is per-lane (lanes wait for the longest block of the group).  With per-lane geometry every branch of
-// the bookkeeping is taken by some lane on almost every iteration and the warp executes all of it all the time.
+// ONE WARP PER IMAGE, window-parallel Huffman decode.  A single thread walking the bit stream pays ~500 cycles per
+// symbol on this machine (in-order issue, every step a dependent load).  Instead the 32 lanes decode, in parallel, the
+// codeword that WOULD start at each of the next 32 bit offsets (table lookup + magnitude bits from a private 64-bit
+// window); the true symbol sequence is then recovered by a warp-uniform walk that costs one shuffle per symbol:
+// start at offset 0, jump by each symbol's total length, stop at the end of the block or of the 32-offset window.
+// Only the first symbol of a block uses the DC table, and windows are re-based at every block start, so lane 0 alone
+// ever needs it.
+__device__ __forceinline__ uint32_t be_word(const uint32_t* __restrict__ w, uint32_t k, uint32_t nwords) {
+    return k < nwords ? __byte_perm(__ldg(w + k), 0, 0x0123) : 0u;
+}
+
 __global__ void __launch_bounds__(HUFF_THREADS)
-lep_huffdecode_kernel(HuffJob* __restrict__ jobs, const int2* __restrict__ groups, int ngroups,
-                      const HuffTableDev* __restrict__ tables, int ntables) {
+lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables, int ntables) {
     __shared__ HuffTableDev s_tab[HUFF_SMEM_TABLES];
-    __shared__ uint8_t s_zz[64];          // per-lane indices differ: constant memory would serialise the lookups
+    __shared__ uint8_t s_zz[64];
     for (int i = threadIdx.x; i < 64; i += HUFF_THREADS) s_zz[i] = c_zigzag_to_aligned[i];
     const bool use_smem = ntables <= HUFF_SMEM_TABLES;
     if (use_smem) {
@@ -108,172 +115,185 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, const int2* __restrict__ group
     }
     __syncthreads();
     const HuffTableDev* tb = use_smem ? s_tab : tables;
-    if ((int)blockIdx.x >= ngroups) return;
-    const int2 grp = groups[blockIdx.x];                 // (first job, count <= 32)
-    const int lane = threadIdx.x;
-    const bool have = lane < grp.y;
-    HuffJob& jb = jobs[grp.x + (have ? lane : 0)];       // idle lanes shadow lane 0's geometry, never write
-    bool live = have && jb.status == 0;
+    const int job = blockIdx.x * HUFF_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (job >= njobs) return;
+    HuffJob& jb = jobs[job];
+    if (jb.status != 0) return;
 
-    HBits b;
-    b.w = reinterpret_cast<const uint32_t*>(jb.huff);
-    b.acc = 0; b.n = 0; b.wi = 0; b.nwords = (jb.nbytes + 3) / 4; b.bitpos = 0;
-    const unsigned long long total_bits = (unsigned long long)jb.nbytes * 8;
+    const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(jb.huff);
+    const uint32_t nwords = (jb.nbytes + 3) / 4;
+    const uint32_t total_bits = jb.nbytes * 8u;
     HuffRow* rows = reinterpret_cast<HuffRow*>(jb.rows);
-    // geometry: identical for every lane of the group (taken from the group's first job)
-    const HuffJob& g0 = jobs[grp.x];
-    const int ncmp = g0.ncmp, mcuh = g0.mcuh, mcuv = g0.mcuv, rsti = g0.rsti;
-    const int H0 = g0.H[0], V0 = g0.V[0], H1 = ncmp > 1 ? g0.H[1] : 1, V1 = ncmp > 1 ? g0.V[1] : 1, H2 = ncmp > 2 ? g0.H[2] : 1, V2 = ncmp > 2 ? g0.V[2] : 1;
-    const int W0 = g0.bch[0], W1 = ncmp > 1 ? g0.bch[1] : 0, W2 = ncmp > 2 ? g0.bch[2] : 0;
-    const int nch0 = g0.nch[0], ncv0 = g0.ncv[0];
-    // per-lane: planes and tables
+    const int ncmp = jb.ncmp, mcuh = jb.mcuh, mcuv = jb.mcuv, rsti = jb.rsti;
+    const int H0 = jb.H[0], V0 = jb.V[0], H1 = ncmp > 1 ? jb.H[1] : 1, V1 = ncmp > 1 ? jb.V[1] : 1, H2 = ncmp > 2 ? jb.H[2] : 1, V2 = ncmp > 2 ? jb.V[2] : 1;
+    const int W0 = jb.bch[0], W1 = ncmp > 1 ? jb.bch[1] : 0, W2 = ncmp > 2 ? jb.bch[2] : 0;
+    const int nch0 = jb.nch[0], ncv0 = jb.ncv[0];
     int16_t* const P0 = reinterpret_cast<int16_t*>(jb.plane[0]);
     int16_t* const P1 = reinterpret_cast<int16_t*>(jb.plane[1]);
     int16_t* const P2 = reinterpret_cast<int16_t*>(jb.plane[2]);
     const HuffTableDev* const D0 = tb + jb.dc_tab[0]; const HuffTableDev* const A0 = tb + jb.ac_tab[0];
     const HuffTableDev* const D1 = tb + jb.dc_tab[1]; const HuffTableDev* const A1 = tb + jb.ac_tab[1];
     const HuffTableDev* const D2 = tb + jb.dc_tab[2]; const HuffTableDev* const A2 = tb + jb.ac_tab[2];
+
+    // warp-uniform decoder state
+    uint32_t p = 0;                                  // bit position of the next symbol
     int dc0 = 0, dc1 = 0, dc2 = 0;
+    int cmp = 0, sx = 0, sy = 0, mx = 0, my = 0, bx = 0, by = 0;
     int nrows = 0, status = 0, padbit = -1, final_y = 0;
     int rstw = rsti;
-    bool finished = false;                    // this lane reached the end of its scan (sta == 2)
-
-    // state shared by both scan shapes: called at the end of a restart interval / of the scan
-    auto unpad_and_check = [&]() {
-        int fb = padbit;
-        if ((b.bitpos & 7) != 0 && b.bitpos < total_bits) {
-            hb_fill(b);
-            int last = (int)hb_peek(b, 1); hb_skip(b, 1);
-            fb = last;
-            int offset = 1;
-            while (b.bitpos & 7) { hb_fill(b); last = (int)hb_peek(b, 1); hb_skip(b, 1); fb |= last << offset; ++offset; }
-            while (offset < 7) { fb |= last << offset; ++offset; }
-        }
-        if (padbit != -1) { if (padbit != fb) status = 42; }
-        else padbit = fb;
-    };
+    int bpos = 0;
+    bool last_nonzero = true;
+    int16_t* blk = P0;
+    const HuffTableDev* dct = D0;
+    const HuffTableDev* act = A0;
     auto push_row = [&](int mcu_y) {
-        HuffRow r;
-        r.bitpos = (uint32_t)b.bitpos; r.mcu_y = (int16_t)mcu_y;
-        r.lastdc[0] = (int16_t)dc0; r.lastdc[1] = (int16_t)dc1; r.lastdc[2] = (int16_t)dc2;
-        rows[nrows++] = r;
+        if (lane == 0) {
+            HuffRow r;
+            r.bitpos = p; r.mcu_y = (int16_t)mcu_y;
+            r.lastdc[0] = (int16_t)dc0; r.lastdc[1] = (int16_t)dc1; r.lastdc[2] = (int16_t)dc2;
+            rows[nrows] = r;
+        }
+        nrows++;
     };
-    // one block for this lane: DC symbol, AC symbols until EOB / 63 (decode_block_seq, jpgcoder.cc:4893-4961)
-    auto decode_block = [&](int cmp, int16_t* blk) {
-        const HuffTableDev* dct = cmp == 0 ? D0 : (cmp == 1 ? D1 : D2);
-        const HuffTableDev* act = cmp == 0 ? A0 : (cmp == 1 ? A1 : A2);
-        int bpos = 0;
-        bool last_nonzero = true;
-        bool active = live && !finished && status == 0;
-        while (__any_sync(FULL, active)) {
-            if (active) {
-                hb_fill(b);                                   // >= 33 bits: enough for one code (<= 16) + magnitude (<= 16)
-                const HuffTableDev* tab = bpos == 0 ? dct : act;
-                const uint32_t top = hb_peek(b, 16);
-                int sym = -1;
-                const uint32_t f = tab->fast[top >> 7];
-                if (f) { hb_skip(b, (int)(f >> 8)); sym = (int)(f & 0xff); }
-                else {
-                    int len = 10, code = (int)(top >> 6);
-                    while (len <= 16 && code > tab->maxcode[len]) { ++len; code = (int)(top >> (16 - len)); }
-                    if (len <= 16) { hb_skip(b, len); sym = tab->vals[code + tab->valoff[len]]; }
-                }
-                if (sym < 0 || (bpos == 0 && sym > 16)) { status = 42; active = false; }
-                else if (bpos == 0) {
-                    int v = 0;
-                    if (sym) { const int n = (int)hb_peek(b, sym); hb_skip(b, sym); v = n >= (1 << (sym - 1)) ? n : n + 1 - (1 << sym); }
-                    const int last = cmp == 0 ? dc0 : (cmp == 1 ? dc1 : dc2);
-                    const int16_t dcv = (int16_t)(v + last);
-                    if (cmp == 0) dc0 = dcv; else if (cmp == 1) dc1 = dcv; else dc2 = dcv;
-                    blk[49] = dcv;
-                    bpos = 1;
-                } else if (sym == 0) {                                        // EOB
-                    if (bpos > 1 && !last_nonzero) status = 42;               // "eob after last 0" (jpgcoder.cc:2953)
-                    active = false;
-                } else {
-                    const int z = sym >> 4, sz = sym & 15;
-                    int v = 0;
-                    if (sz) { const int n = (int)hb_peek(b, sz); hb_skip(b, sz); v = n >= (1 << (sz - 1)) ? n : n + 1 - (1 << sz); }
-                    if (z + bpos >= 64) { status = 200; active = false; }     // truncated-file fix-up path: not handled here
-                    else {
-                        bpos += z;
-                        blk[s_zz[bpos++]] = (int16_t)v;
-                        last_nonzero = v != 0;
-                        if (bpos >= 64) active = false;
-                    }
-                }
+    auto bit_at = [&](uint32_t pos) -> int {         // uniform single-bit read (padding bits)
+        const uint32_t wv = be_word(words, pos >> 5, nwords);
+        return (int)((wv >> (31 - (pos & 31))) & 1u);
+    };
+    push_row(0);
+    bool done = false;
+    while (!done) {
+        // ---- every lane: the symbol that would start at bit offset p + lane
+        const uint32_t off = p + (uint32_t)lane;
+        const uint32_t k = off >> 5, sh = off & 31;
+        const uint32_t w0 = be_word(words, k, nwords), w1 = be_word(words, k + 1, nwords), w2 = be_word(words, k + 2, nwords);
+        const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);    // 64 bits from `off`, MSB first
+        const bool is_dc = lane == 0 && bpos == 0;
+        const HuffTableDev* tab = is_dc ? dct : act;
+        int len = 0, sym = 0;
+        {
+            const uint32_t f = tab->fast[hi >> 23];
+            if (f) { len = (int)(f >> 8); sym = (int)(f & 0xff); }
+            else {
+                const uint32_t top = hi >> 16;
+                int l = 10, code = (int)(top >> 6);
+                while (l <= 16 && code > tab->maxcode[l]) { ++l; code = (int)(top >> (16 - l)); }
+                if (l <= 16) { len = l; sym = tab->vals[code + tab->valoff[l]]; }
             }
         }
-        if (live && !finished && status == 0 && b.bitpos > total_bits) status = 200;   // entropy data ends inside a block
-    };
-    // after a block: end of data / restart interval / end of scan handling for this lane
-    auto after_block = [&](bool scan_done, bool restart_due, int mcu_y_now) {
-        if (!live || finished || status) return;
-        int sta = scan_done ? 2 : (restart_due ? 1 : 0);
-        if (b.bitpos >= total_bits) sta = 2;                                  // huffr->eof
-        if (sta == 0) return;
-        unpad_and_check();
-        if (status) return;
-        if (sta == 2) { finished = true; final_y = mcu_y_now; return; }
-        dc0 = dc1 = dc2 = 0;                                                  // restart interval
-    };
-
-    if (live) push_row(0);
-    if (ncmp > 1) {
-        for (int my = 0; my < mcuv; ++my) {
-            for (int mx = 0; mx < mcuh; ++mx) {
-                for (int cmp = 0; cmp < ncmp; ++cmp) {
-                    const int H = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), V = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
-                    const int W = cmp == 0 ? W0 : (cmp == 1 ? W1 : W2);
-                    int16_t* P = cmp == 0 ? P0 : (cmp == 1 ? P1 : P2);
-                    for (int sy = 0; sy < V; ++sy)
-                        for (int sx = 0; sx < H; ++sx) {
-                            const bool last_in_mcu = cmp == ncmp - 1 && sy == V - 1 && sx == H - 1;
-                            decode_block(cmp, P + ((size_t)(my * V + sy) * W + mx * H + sx) * 64);
-                            if (!last_in_mcu) {
-                                // the reference checks eof after every block (jpgcoder.cc:2975)
-                                if (live && !finished && !status && b.bitpos >= total_bits) { unpad_and_check(); finished = true; final_y = my; }
-                            }
-                        }
+        const int sz = is_dc ? sym : (sym & 15);
+        const int run = is_dc ? 0 : (sym >> 4);
+        int val = 0;
+        bool bad = len == 0 || sz > 16;
+        if (!bad && sz) {
+            // sz magnitude bits follow the code: bits [len, len+sz) of the 64-bit window
+            const unsigned long long win = ((unsigned long long)hi << 32) | lo;
+            const int nb = (int)((win << len) >> (64 - sz));
+            val = nb >= (1 << (sz - 1)) ? nb : nb + 1 - (1 << sz);
+        }
+        // info: [0,6) total length (0 = invalid) | [6,10) run | [10,15) size | [16,32) value
+        const uint32_t info = bad ? 0u : ((uint32_t)(len + sz) | ((uint32_t)run << 6) | ((uint32_t)sz << 10) | ((uint32_t)(val & 0xffff) << 16));
+        // ---- warp-uniform walk along the true symbol sequence inside this window
+        int cur = 0;
+        bool block_done = false;
+        while (cur < 32) {
+            const uint32_t inf = __shfl_sync(FULL, info, cur);
+            const int tot = (int)(inf & 63);
+            if (tot == 0) { status = 42; break; }
+            const int r = (int)((inf >> 6) & 15), z = (int)((inf >> 10) & 31);
+            const int v = (int)(int16_t)(inf >> 16);
+            if (bpos == 0) {
+                const int last = cmp == 0 ? dc0 : (cmp == 1 ? dc1 : dc2);
+                const int16_t dcv = (int16_t)(v + last);
+                if (cmp == 0) dc0 = dcv; else if (cmp == 1) dc1 = dcv; else dc2 = dcv;
+                if (lane == 0) blk[49] = dcv;
+                bpos = 1;
+                last_nonzero = true;
+                cur += tot;
+                // the following symbols use the AC table, but lanes > 0 already assumed that; lane 0's own AC
+                // candidate at offset 0 is never needed again
+                continue;
+            }
+            cur += tot;
+            if (r == 0 && z == 0) {                                           // EOB
+                if (bpos > 1 && !last_nonzero) status = 42;                   // "eob after last 0" (jpgcoder.cc:2953)
+                block_done = true;
+                break;
+            }
+            if (r + bpos >= 64) { status = 200; break; }                      // truncated-file fix-up path: not handled here
+            bpos += r;
+            if (lane == 0) blk[s_zz[bpos]] = (int16_t)v;
+            ++bpos;
+            last_nonzero = v != 0;
+            if (bpos >= 64) { block_done = true; break; }
+        }
+        if (status) break;
+        p += (uint32_t)cur;
+        if (!block_done) continue;
+        if (p > total_bits) { status = 200; break; }                          // entropy data ends inside a block
+        // ---- next block position (next_mcupos / next_mcuposn), warp-uniform
+        int sta = 0;
+        bool handoff_due = false;
+        if (ncmp > 1) {
+            const int H = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), V = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
+            if (++sx >= H) { sx = 0; ++sy; }
+            if (sy >= V) {
+                sy = 0;
+                if (++cmp >= ncmp) {
+                    cmp = 0;
+                    if (++mx >= mcuh) { mx = 0; ++my; handoff_due = true; }
+                    if (my >= mcuv) sta = 2;
+                    else if (rsti > 0 && --rstw == 0) sta = 1;
                 }
-                // MCU complete (next_mcupos, recoder.cc:190-243)
-                const bool scan_done = my == mcuv - 1 && mx == mcuh - 1;
-                bool restart_due = false;
-                if (!scan_done && rsti > 0 && --rstw == 0) { restart_due = true; rstw = rsti; }
-                const int next_y = mx == mcuh - 1 ? my + 1 : my;
-                after_block(scan_done, restart_due, next_y);
-                if (mx == mcuh - 1 && !scan_done && live && !finished && !status) push_row(my + 1);
+                dct = cmp == 0 ? D0 : (cmp == 1 ? D1 : D2);
+                act = cmp == 0 ? A0 : (cmp == 1 ? A1 : A2);
             }
-            if (!__any_sync(FULL, live && !finished && status == 0)) break;
-        }
-    } else {
-        // single component: row-major over the nch x ncv coded blocks (next_mcuposn, jpgcoder.cc:5432-5456)
-        const int per_mcu = H0 * V0;
-        for (int by = 0; by < ncv0; ++by) {
-            for (int bx = 0; bx < nch0; ++bx) {
-                decode_block(0, P0 + ((size_t)by * W0 + bx) * 64);
-                const bool scan_done = by == ncv0 - 1 && bx == nch0 - 1;
-                bool restart_due = false;
-                if (!scan_done && rsti > 0 && --rstw == 0) { restart_due = true; rstw = rsti; }
-                // position of the NEXT block decides the handoff (jpgcoder.cc:3084-3087)
-                const int nbx = bx + 1 < nch0 ? bx + 1 : 0, nby = bx + 1 < nch0 ? by : by + 1;
-                const int ndpos = nby * W0 + nbx;
-                const int nmcu_y = (ndpos / per_mcu) / mcuh;
-                after_block(scan_done, restart_due, scan_done ? mcuv : nmcu_y);
-                if (!scan_done && (ndpos % per_mcu) == 0 && ((ndpos / per_mcu) % mcuh) == 0 && live && !finished && !status) push_row(nmcu_y);
+            const int Hn = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), Vn = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
+            const int Wn = cmp == 0 ? W0 : (cmp == 1 ? W1 : W2);
+            int16_t* Pn = cmp == 0 ? P0 : (cmp == 1 ? P1 : P2);
+            blk = Pn + ((size_t)(my * Vn + sy) * Wn + mx * Hn + sx) * 64;
+        } else {
+            if (++bx >= nch0) { bx = 0; ++by; }
+            if (by >= ncv0) sta = 2;
+            else if (rsti > 0 && --rstw == 0) sta = 1;
+            const int dpos = by * W0 + bx;
+            blk = P0 + (size_t)dpos * 64;
+            const int per_mcu = H0 * V0;
+            if (sta != 2) {
+                my = (dpos / per_mcu) / mcuh;
+                if ((dpos % per_mcu) == 0 && ((dpos / per_mcu) % mcuh) == 0) handoff_due = true;
+            } else {
+                my = mcuv;
             }
-            if (!__any_sync(FULL, live && !finished && status == 0)) break;
         }
+        bpos = 0;
+        if (p >= total_bits) sta = 2;                                         // huffr->eof
+        if (sta != 0) {
+            // abitreader::unpad (bitops.hh:316-332) + padbit bookkeeping (jpgcoder.cc:3260-3271)
+            int fb = padbit;
+            if ((p & 7) != 0 && p < total_bits) {
+                int last = bit_at(p); ++p;
+                fb = last;
+                int offset = 1;
+                while (p & 7) { last = bit_at(p); ++p; fb |= last << offset; ++offset; }
+                while (offset < 7) { fb |= last << offset; ++offset; }
+            }
+            if (padbit != -1) { if (padbit != fb) { status = 42; break; } }
+            else padbit = fb;
+            if (sta == 2) { final_y = my; done = true; break; }
+            dc0 = dc1 = dc2 = 0;                                              // restart interval
+            rstw = rsti;
+        }
+        if (handoff_due) push_row(my);
     }
-    if (have) {
-        if (live && status == 0) {
-            if (!finished) final_y = mcuv;
-            push_row(final_y);
-            if (b.bitpos < total_bits) status = 42;                      // "unneeded data found after coded image data"
-        }
-        if (jb.status == 0) jb.status = status;
+    if (status == 0) {
+        push_row(final_y);
+        if (p < total_bits) status = 42;                                      // "unneeded data found after coded image data"
+    }
+    if (lane == 0) {
+        jb.status = status;
         jb.padbit = padbit;
-        jb.end_bitpos = (uint32_t)b.bitpos;
+        jb.end_bitpos = p;
         jb.nrows = nrows;
     }
 }

@@ -276,7 +276,46 @@ struct BitReader {
         return (uint32_t)((v << (bitpos & 7)) >> 32);
     }
     inline void skip(int k) { bitpos += (uint64_t)k; }
+    // >= 57 valid bits at the current position, MSB first (zero beyond the end)
+    inline uint64_t peek57() const {
+        size_t byte = (size_t)(bitpos >> 3);
+        uint64_t v = 0;
+        if (byte + 8 <= n) {
+            uint64_t raw;
+            memcpy(&raw, d + byte, 8);
+            v = __builtin_bswap64(raw);
+        } else {
+            for (int i = 0; i < 8; ++i) v = (v << 8) | (byte + i < n ? d[byte + i] : 0);
+        }
+        return v << (bitpos & 7);
+    }
 };
+
+// One Huffman symbol plus its magnitude bits from a single 57-bit window (code <= 16 bits, magnitude <= 16 bits).
+// Returns the symbol (-1 on an invalid code); *value receives DEVLI(size, bits) where size = symbol & mask.
+inline int decode_symbol_value(BitReader& br, const HuffTable& t, int size_mask, int* value) {
+    const uint64_t win = br.peek57();
+    const uint16_t f = t.fast[win >> 55];
+    int len, sym;
+    if (f) { len = f >> 8; sym = f & 0xff; }
+    else {
+        const uint32_t w = (uint32_t)(win >> 32);
+        int code = (int)(w >> 22);
+        len = 10;
+        while (len <= 16 && code > t.maxcode[len]) { ++len; code = (int)(w >> (32 - len)); }
+        if (len > 16) return -1;
+        sym = t.vals[code + t.valoff[len]];
+    }
+    const int s = sym & size_mask;
+    int v = 0;
+    if (s) {
+        const int nb = (int)((win << len) >> (64 - s));
+        v = nb >= (1 << (s - 1)) ? nb : nb + 1 - (1 << s);
+    }
+    *value = v;
+    br.skip(len + s);
+    return sym;
+}
 
 // one Huffman symbol; -1 on invalid code / read past the end
 inline int decode_symbol(BitReader& br, const HuffTable& t) {
@@ -483,26 +522,22 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
                 const HuffTable& dct = dc_t[k.td];
                 const HuffTable& act = ac_t[k.ta];
                 int16_t* blk = planes[cmp] + (size_t)dpos * 64;
-                int s = decode_symbol(br, dct);
+                int dcdiff = 0;
+                int s = decode_symbol_value(br, dct, 0x1f, &dcdiff);
                 if (s < 0 || s > 16) return fail(j, UNSUPPORTED_JPEG, "decode error in scan (dc)");
-                uint32_t nbits = s ? (br.peek32() >> (32 - s)) : 0;
-                br.skip(s);
-                int16_t dcv = (int16_t)(devli(s, (int)nbits) + lastdc[cmp]);
+                int16_t dcv = (int16_t)(dcdiff + lastdc[cmp]);
                 lastdc[cmp] = dcv;
                 blk[k_zigzag_to_aligned[0]] = dcv;
                 int bpos = 1, eob = 64;
                 int last_nonzero_written = 1;   // whether block[eob-1] != 0 (reference check :2953)
                 while (bpos < 64) {
-                    int hc = decode_symbol(br, act);
+                    int v = 0;
+                    int hc = decode_symbol_value(br, act, 15, &v);
                     if (hc < 0) return fail(j, UNSUPPORTED_JPEG, "decode error in scan (ac)");
                     if (hc > 0) {
                         int z = hc >> 4;
-                        s = hc & 15;
-                        nbits = s ? (br.peek32() >> (32 - s)) : 0;
-                        br.skip(s);
                         if (z + bpos >= 64) return fail(j, NOT_HANDLED, "zero run past the end of the block (truncated-file fix-up)");
                         bpos += z;
-                        int v = devli(s, (int)nbits);
                         blk[k_zigzag_to_aligned[bpos++]] = (int16_t)v;
                         last_nonzero_written = v != 0;
                     } else {
