@@ -170,7 +170,7 @@ const char* lepb200_codec_last_error(const lepb200_codec* codec);
 lepb200_ctx* lepb200_codec_ctx(lepb200_codec* codec);
 /* kernel launches issued so far by the codec's contexts */
 uint64_t lepb200_codec_kernel_launches(const lepb200_codec* codec);
-/* files per pipeline chunk (default 512): chunk k+1 is Huffman-decoded while chunk k is on the GPU */
+/* files per pipeline chunk (default 1024): chunk k+1 is Huffman-decoded while chunk k is on the GPU */
 void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
 /* 1 (default): Huffman-decode on the GPU when every file of a chunk is a complete single-scan baseline JPEG;
  * 0: always Huffman-decode on host threads */

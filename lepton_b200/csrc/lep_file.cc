@@ -23,7 +23,7 @@ struct lepb200_codec {
     lepb200_ctx* ctx = nullptr;     // == ctx2[0]
     lepb200_ctx* ctx2[3] = {nullptr, nullptr, nullptr};   // rotating contexts: chunk k on ctx2[k % 3]
     int nthreads = 1;
-    int chunk_images = 512;
+    int chunk_images = 1024;
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
     void* arena[3] = {nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
     size_t arena_cap[3] = {0, 0, 0};
