@@ -83,7 +83,10 @@ __device__ __forceinline__ int dec_coef_plain(Decoder& d, uint32_t exp_addr, uin
     return neg ? -val : val;
 }
 
-__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32)
+#ifndef LEPB200_DEC_MINBLOCKS
+#define LEPB200_DEC_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, LEPB200_DEC_MINBLOCKS)
 lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
                   int* __restrict__ work_counter, uint16_t* __restrict__ model_pool, uint8_t* __restrict__ row_pool,
                   size_t row_pool_stride) {

@@ -75,7 +75,10 @@ __device__ __forceinline__ void flush_queue(const uint32_t* __restrict__ queue, 
 __device__ __forceinline__ int coef_entries(int len) { return len == 0 ? 1 : min(len + 1, 11) + len; }
 
 // ---- the kernel ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32)
+#ifndef LEPB200_ENC_MINBLOCKS
+#define LEPB200_ENC_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32, LEPB200_ENC_MINBLOCKS)
 lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
                   int* __restrict__ work_counter, uint16_t* __restrict__ model_pool, uint8_t* __restrict__ row_pool,
                   size_t row_pool_stride, uint16_t* __restrict__ token_base) {
