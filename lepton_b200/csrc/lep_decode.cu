@@ -84,7 +84,7 @@ __device__ __forceinline__ int dec_coef_plain(Decoder& d, uint32_t exp_addr, uin
 }
 
 #ifndef LEPB200_DEC_MINBLOCKS
-#define LEPB200_DEC_MINBLOCKS 6
+#define LEPB200_DEC_MINBLOCKS 5
 #endif
 __global__ void __launch_bounds__(DEC_WARPS_PER_CTA * 32, LEPB200_DEC_MINBLOCKS)
 lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,

@@ -76,7 +76,7 @@ __device__ __forceinline__ int coef_entries(int len) { return len == 0 ? 1 : min
 
 // ---- the kernel ---------------------------------------------------------------------------------------
 #ifndef LEPB200_ENC_MINBLOCKS
-#define LEPB200_ENC_MINBLOCKS 6
+#define LEPB200_ENC_MINBLOCKS 7
 #endif
 __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32, LEPB200_ENC_MINBLOCKS)
 lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
