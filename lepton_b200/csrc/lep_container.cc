@@ -201,7 +201,11 @@ bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<cons
         le32(blob, (uint32_t)j.rst_err.size());
         blob.insert(blob.end(), j.rst_err.begin(), j.rst_err.end());
     }
-    if (j.early_eof) { err = "truncated JPEG (EEE section) not handled"; return false; }
+    if (j.early_eof) {                                     // jpgcoder.cc:3996-4007
+        put(blob, "EEE", 3);
+        le32(blob, (uint32_t)j.max_cmp); le32(blob, (uint32_t)j.max_bpos); le32(blob, (uint32_t)j.max_sah);
+        for (int i = 0; i < 4; ++i) le32(blob, (uint32_t)j.max_dpos[i]);
+    }
     if (!j.grb.empty()) {
         put(blob, "GRB", 3);
         le32(blob, (uint32_t)j.grb.size());

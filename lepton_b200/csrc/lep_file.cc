@@ -69,7 +69,8 @@ void fill_image(lepb200_image& im, const Jpeg& j, int16_t* const planes[4], cons
     im.ncmp = j.ncmp; im.mcuv = j.mcuv;
     for (int c = 0; c < j.ncmp; ++c) {
         im.bch[c] = j.cmp[c].bch; im.bcv[c] = j.cmp[c].bcv;
-        im.trunc_bcv[c] = j.cmp[c].bcv; im.trunc_bc[c] = j.cmp[c].bc;
+        im.trunc_bcv[c] = j.trunc_bcv[c] ? j.trunc_bcv[c] : j.cmp[c].bcv;
+        im.trunc_bc[c] = j.trunc_bc[c] ? j.trunc_bc[c] : j.cmp[c].bc;
         memcpy(im.qtable_zigzag[c], j.qtables[j.cmp[c].tq], 128);
         im.planes[c] = planes[c];
     }

@@ -77,6 +77,8 @@ struct Jpeg {
     int mcuh = 0, mcuv = 0, mcuc = 0;
     // ---- decode products (decode_jpeg, jpgcoder.cc:2799-3302)
     int8_t padbit = -1;
+    int max_cmp = 0, max_bpos = 0, max_sah = 0, max_dpos[4] = {0, 0, 0, 0};   // truncation bookkeeping (EEE section)
+    int trunc_bcv[4] = {0, 0, 0, 0}, trunc_bc[4] = {0, 0, 0, 0};             // coded rows / blocks per component
     std::vector<Handoff> rows;       // one per MCU row + the final one ("luma_row_offset_return")
     int status = OK;
     std::string error;

@@ -261,7 +261,8 @@ struct BitReader {
     const uint8_t* d;
     size_t n;          // bytes
     uint64_t bitpos;   // bits consumed
-    inline bool eof() const { return bitpos >= n * 8; }
+    bool at_eof = false;   // abitreader::eof (bitops.hh:262-306): set by the read that consumes the last bit (or tries to go past it)
+    inline bool eof() const { return at_eof; }
     // peek 32 bits at the current position (zero beyond the end)
     inline uint32_t peek32() const {
         size_t byte = (size_t)(bitpos >> 3);
@@ -275,7 +276,11 @@ struct BitReader {
         }
         return (uint32_t)((v << (bitpos & 7)) >> 32);
     }
-    inline void skip(int k) { bitpos += (uint64_t)k; }
+    inline void skip(int k) {
+        if (!k) return;
+        if (bitpos + (uint64_t)k >= (uint64_t)n * 8) { at_eof = true; bitpos = (uint64_t)n * 8; }
+        else bitpos += (uint64_t)k;
+    }
     // >= 57 valid bits at the current position, MSB first (zero beyond the end)
     inline uint64_t peek57() const {
         size_t byte = (size_t)(bitpos >> 3);
@@ -364,7 +369,7 @@ Handoff crystallize(const Jpeg& j, const BitReader& br, int mcu_y, const int las
 // abitreader::unpad (bitops.hh:316-332)
 int8_t unpad(BitReader& br, int8_t fillbit) {
     if ((br.bitpos & 7) == 0 || br.eof()) return fillbit;
-    auto rd = [&]() { int b = (br.d[br.bitpos >> 3] >> (7 - (br.bitpos & 7))) & 1; br.bitpos++; return b; };
+    auto rd = [&]() { int b = br.eof() ? 0 : (br.d[br.bitpos >> 3] >> (7 - (br.bitpos & 7))) & 1; br.skip(1); return b; };
     int last = rd();
     int fb = last, offset = 1;
     while (br.bitpos & 7) { last = rd(); fb |= last << offset; ++offset; }
@@ -376,7 +381,7 @@ int8_t unpad(BitReader& br, int8_t fillbit) {
 
 // ThreadHandoff for a Huffman state captured elsewhere (the GPU decoder): same mapping as crystallize().
 Handoff handoff_from_state(const Jpeg& j, uint32_t bitpos, int mcu_y, const int16_t lastdc[3]) {
-    BitReader br{j.huff.data(), j.huff.size(), bitpos};
+    BitReader br{j.huff.data(), j.huff.size(), bitpos, false};
     int ldc[4] = {lastdc[0], lastdc[1], lastdc[2], 0};
     return crystallize(j, br, mcu_y, ldc, j.cmp[0].bcv / j.mcuv);
 }
@@ -385,7 +390,7 @@ Handoff handoff_from_state(const Jpeg& j, uint32_t bitpos, int mcu_y, const int1
 // (without touching j.status) when the file needs the general host path (progressive, truncated, several scans, scan
 // order != frame order).
 bool gpu_scan_setup(const Jpeg& j, GpuScanSetup& out) {
-    if (j.jpegtype != 1 || j.early_eof || j.ncmp < 1 || j.ncmp > 3) return false;
+    if (j.jpegtype != 1 || j.early_eof || j.ncmp < 1 || j.ncmp > 3) return false;   // truncated files take the host path
     const std::vector<uint8_t>& h = j.hdr;
     struct Raw { bool set = false; uint8_t bits[17]; uint8_t vals[256]; } dc[4], ac[4];
     size_t hpos = 0;
@@ -437,7 +442,7 @@ bool gpu_scan_setup(const Jpeg& j, GpuScanSetup& out) {
 
 bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
     HuffTable dc_t[4], ac_t[4];
-    BitReader br{j.huff.data(), j.huff.size(), 0};
+    BitReader br{j.huff.data(), j.huff.size(), 0, false};
     int rsti = 0;
     int lastdc[4] = {0, 0, 0, 0};
     size_t hpos = 0;
@@ -447,7 +452,6 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
     int scans = 0;
     j.padbit = -1;
     if (j.jpegtype != 1) return fail(j, NOT_HANDLED, "progressive JPEG: host front end not implemented yet");
-    if (j.early_eof) return fail(j, NOT_HANDLED, "truncated JPEG: host front end not implemented yet");
     while (true) {
         ScanInfo sc;
         uint8_t type = 0;
@@ -504,6 +508,11 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
 
         int cmp = sc.cmp[0], csc = 0, sub = 0, dpos = 0;
         mcu = 0;
+        if (!br.eof()) {                              // jpgcoder.cc:2879-2886
+            j.max_bpos = std::max(j.max_bpos, sc.to);
+            j.max_sah = std::max(j.max_sah, std::max(sc.sal, sc.sah));
+            for (int i = 0; i < sc.ncomp; ++i) j.max_cmp = std::max(j.max_cmp, sc.cmp[i]);
+        }
         bool handoff_due = true;
         int sta = 0;
         const int hmul = j.cmp[0].bch / j.mcuh, vmul = j.cmp[0].bcv / j.mcuv;
@@ -517,6 +526,7 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
                     j.rows.push_back(crystallize(j, br, mcu_y, lastdc, luma_mul));
                     handoff_due = false;
                 }
+                if (!br.eof()) j.max_dpos[cmp] = std::max(j.max_dpos[cmp], dpos);     // jpgcoder.cc:2941-2943
                 // ---- decode_block_seq
                 const Component& k = j.cmp[cmp];
                 const HuffTable& dct = dc_t[k.td];
@@ -536,7 +546,16 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
                     if (hc < 0) return fail(j, UNSUPPORTED_JPEG, "decode error in scan (ac)");
                     if (hc > 0) {
                         int z = hc >> 4;
-                        if (z + bpos >= 64) return fail(j, NOT_HANDLED, "zero run past the end of the block (truncated-file fix-up)");
+                        if (z + bpos >= 64) {
+                            // eof_fixup (jpgcoder.cc:4930-4958): only legal when the data ran out; the rest of the block
+                            // is zero and the last coefficient is set to 1 so that the block has no trailing zero run
+                            if (!br.eof()) return fail(j, ASSERTION_FAILURE, "zero run longer than the block in complete data");
+                            for (int q = bpos; q < 64; ++q) blk[k_zigzag_to_aligned[q]] = 0;
+                            blk[k_zigzag_to_aligned[63]] = 1;
+                            last_nonzero_written = 1;
+                            eob = 64;
+                            break;
+                        }
                         bpos += z;
                         blk[k_zigzag_to_aligned[bpos++]] = (int16_t)v;
                         last_nonzero_written = v != 0;
@@ -546,7 +565,6 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
                     }
                 }
                 if (eob > 1 && !last_nonzero_written) return fail(j, UNSUPPORTED_JPEG, "cannot encode image with eob after last 0");
-                if (br.bitpos > (uint64_t)br.n * 8) return fail(j, NOT_HANDLED, "entropy data ends inside a block (truncated file)");
                 // ---- next position
                 if (sc.ncomp > 1) {
                     const int old_mcu = mcu;
@@ -596,6 +614,19 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
         }
     }
     if (scans == 0) return fail(j, UNSUPPORTED_JPEG, "no scan found");
+    for (int c = 0; c < j.ncmp; ++c) { j.trunc_bcv[c] = j.cmp[c].bcv; j.trunc_bc[c] = j.cmp[c].bc; }
+    if (j.early_eof) {
+        // UncompressedComponents::set_truncation_bounds / set_block_count_dpos (uncompressed_components.hh:166-188)
+        for (int c = 0; c < j.ncmp; ++c) {
+            const Component& k = j.cmp[c];
+            const int tbc = j.max_dpos[c] + 1;
+            int vs = std::min(tbc / k.bch + (tbc % k.bch ? 1 : 0), k.bcv);
+            const int ratio = k.bcv / j.mcuv;
+            while (vs % ratio != 0 && vs + 1 <= k.bcv) ++vs;
+            j.trunc_bcv[c] = vs;
+            j.trunc_bc[c] = tbc;
+        }
+    }
     j.rows.push_back(crystallize(j, br, (uint16_t)(mcu / j.mcuh), lastdc, luma_mul));
     for (size_t i = 1; i < j.rows.size(); ++i)
         if (j.rows[i].luma_y_start < j.rows[i - 1].luma_y_end) j.rows[i].luma_y_start = j.rows[i - 1].luma_y_end;

@@ -111,6 +111,20 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
             if (!need(31)) return lfail(lf, SHORT_READ, "short EEE");
             lf.has_eee = true;
             for (int i = 0; i < 7; ++i) lf.eee[i] = rd32(m + 3 + 4 * i);
+            // UncompressedComponents::set_truncation_bounds (uncompressed_components.hh:166-188)
+            j.early_eof = true;
+            j.max_cmp = (int)lf.eee[0]; j.max_bpos = (int)lf.eee[1]; j.max_sah = (int)lf.eee[2];
+            for (int c = 0; c < j.ncmp; ++c) {
+                const Component& k = j.cmp[c];
+                j.max_dpos[c] = (int)lf.eee[3 + c];
+                const long tbc = (long)lf.eee[3 + c] + 1;
+                if (tbc > k.bc) return lfail(lf, STREAM_INCONSISTENT, "truncation bound beyond the component");
+                int vs = (int)std::min<long>(tbc / k.bch + (tbc % k.bch ? 1 : 0), k.bcv);
+                const int ratio = k.bcv / j.mcuv;
+                while (vs % ratio != 0 && vs + 1 <= k.bcv) ++vs;
+                j.trunc_bcv[c] = vs;
+                j.trunc_bc[c] = (int)tbc;
+            }
             p += 31;
         } else if (!memcmp(m, "PGR", 3) || !memcmp(m, "PGE", 3) || !memcmp(m, "SIZ", 3)) {
             return lfail(lf, NOT_HANDLED, "prefix garbage / embedded JPEG sections are not handled");
@@ -176,7 +190,6 @@ inline int bitlen16(int v) { return v ? 32 - __builtin_clz((unsigned)v) : 0; }
 bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err) {
     const Jpeg& j = lf.j;
     if (j.jpegtype != 1) { err = "progressive re-encode not implemented"; return false; }
-    if (lf.has_eee) { err = "truncated-file re-encode not implemented"; return false; }
     const std::vector<uint8_t>& h = j.hdr;
     HuffTable dc_t[4], ac_t[4];
     int rsti = 0;
@@ -307,6 +320,9 @@ bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vec
         for (unsigned i = 0; i < j.rst_err[0]; ++i) { out.push_back(0xFF); out.push_back((uint8_t)(0xD0 + ((cum + i) & 7))); }
     }
     out.insert(out.end(), h.begin() + hpos, h.end());      // header data after the first SOS, if any
+    // everything before the garbage is bounded to (original size - garbage size): for truncated originals the scan is
+    // cut exactly where the file ended (str_out->set_bound, recoder.cc:699-700, 880-886)
+    if (lf.jpeg_size >= j.grb.size() && out.size() > lf.jpeg_size - j.grb.size()) out.resize(lf.jpeg_size - j.grb.size());
     out.insert(out.end(), j.grb.begin(), j.grb.end());
     if (out.size() != lf.jpeg_size) { err = "re-created JPEG has the wrong size"; return false; }
     return true;

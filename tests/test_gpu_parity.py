@@ -150,11 +150,14 @@ def test_file_level_roundtrip_jpeg_lep_jpeg():
     from helpers import GOLDEN, MANIFEST
     from lepton_b200 import LeptonB200FileCodec
     names = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "colorswap.jpg",
-             "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg"]
+             "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg",
+             "gray2sf.jpg", "narrowrst.jpg", "nofsync.jpg", "singlerowtrunc.jpg", "truncatedzerorun.jpg"]   # incl. truncated files
     jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
     fc = LeptonB200FileCodec(0, host_threads=4, chunk_images=4)
     leps = fc.compress(jpegs)
     assert all(st == 0 for st, _ in leps)
+    for n, (_, lep) in zip(names, leps):
+        assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
     back = fc.decompress([l for _, l in leps])
     for n, j, (st, out) in zip(names, jpegs, back):
         assert st == 0 and out == j, n
