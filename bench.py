@@ -277,13 +277,13 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     launches = codec.kernel_launches - launches0
     clocks = sampler.stop()
+    from lepton_b200.sharding import reduce_job_throughput
     dev_s = sum(kernel_ms) / 1e3
-    t = torch.tensor([dev_s, t_wall], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s_max, wall_max = float(t[0]), float(t[1])
-    total_jpeg = jpeg_bytes * max(world, 1)
-    value = total_jpeg * args.steps / dev_s_max / 1e6
+    # whole-job throughput: bytes of ALL ranks / max over ranks of the device time (same helper the gloo test covers)
+    thr, total_units, dev_s_max = reduce_job_throughput(jpeg_bytes * args.steps, dev_s, dist, "cuda")
+    _, _, wall_max = reduce_job_throughput(0.0, t_wall, dist, "cuda")
+    total_jpeg = total_units / args.steps
+    value = thr / 1e6
 
     # ---------------------------------------------------------------- decode direction + round trip (same batch)
     decode = None

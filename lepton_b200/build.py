@@ -25,7 +25,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     cu = [os.path.join(SRC, "lep_capi.cu")]
-    cc = sorted(os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith(".cc"))
+    cc = sorted(os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith(".cc") and f != "lepton_cli.cc")
     defs = ["-D%s=%s" % (k, os.environ[k]) for k in ("LEPB200_ENC_MINBLOCKS", "LEPB200_DEC_MINBLOCKS") if k in os.environ]
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared"] + defs + [
            "-Xcompiler", "-fPIC,-O3,-pthread", "-o", OUT] + cu + cc + ["-lz", "-lpthread"]
@@ -33,6 +33,11 @@ def build(force=False, verbose=False):
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    # the `lepton`-compatible CLI over the library
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", os.path.join(bindir, "lepton-b200"), os.path.join(SRC, "lepton_cli.cc"),
+                           "-L" + HERE, "-llepton_b200", "-Wl,-rpath,$ORIGIN/.."])
     return OUT
 
 
