@@ -233,7 +233,7 @@ bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<cons
     out.reserve(28 + z.size() + 3 + total_stream + total_stream / 1024 + 64);
     out.push_back(0xCF); out.push_back(0x84);              // lepton_header (jpgcoder.cc:551)
     out.push_back(1);                                      // ujgversion
-    out.push_back('Z');                                    // baseline only (g_allow_progressive cleared, :3298-3300)
+    out.push_back(j.is_baseline ? 'Z' : 'X');              // 'Z': g_allow_progressive cleared for baseline files (:3298-3300, :4044-4052)
     out.push_back((uint8_t)sp.selected.size());
     out.push_back(0); out.push_back(0); out.push_back(0);
     for (int i = 0; i < 12; ++i) out.push_back(0);         // GIT_REVISION "" (:4058-4060)

@@ -55,6 +55,7 @@ struct HuffTable {
     // encode side
     uint16_t ecode[256];
     uint8_t elen[256];
+    int max_eobrun = 0;        // progressive: longest end-of-band run with a code in this table
     bool build();
 };
 
@@ -77,6 +78,7 @@ struct Jpeg {
     int mcuh = 0, mcuv = 0, mcuc = 0;
     // ---- decode products (decode_jpeg, jpgcoder.cc:2799-3302)
     int8_t padbit = -1;
+    bool is_baseline = true;         // false: progressive, or scans that do not interleave all components (flag 'X')
     int max_cmp = 0, max_bpos = 0, max_sah = 0, max_dpos[4] = {0, 0, 0, 0};   // truncation bookkeeping (EEE section)
     int trunc_bcv[4] = {0, 0, 0, 0}, trunc_bc[4] = {0, 0, 0, 0};             // coded rows / blocks per component
     std::vector<Handoff> rows;       // one per MCU row + the final one ("luma_row_offset_return")

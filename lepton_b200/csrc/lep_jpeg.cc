@@ -55,6 +55,10 @@ bool HuffTable::build() {
         code <<= 1;
     }
     maxcode[17] = 0x7fffffff;
+    // largest end-of-band run this table can express (build_huffcodes, jpgcoder.cc:5542-5549)
+    max_eobrun = 0;
+    for (int i = 14; i >= 0; --i)
+        if (elen[i << 4] > 0) { max_eobrun = (2 << i) - 1; break; }
     return true;
 }
 
@@ -377,6 +381,221 @@ int8_t unpad(BitReader& br, int8_t fillbit) {
     return (int8_t)fb;
 }
 
+// read k (<= 16) raw bits, MSB first; zero past the end (abitreader::read, bitops.hh:262-306)
+inline int read_bits(BitReader& br, int k) {
+    if (!k) return 0;
+    const int v = (int)(br.peek32() >> (32 - k));
+    br.skip(k);
+    return v;
+}
+
+struct ScanPos {               // position bookkeeping shared by the scan decoders
+    int cmp = 0, csc = 0, mcu = 0, sub = 0, dpos = 0, rstw = 0;
+};
+
+// next_mcupos (recoder.cc:190-243): interleaved order.  Returns 0 go on, 1 restart interval done, 2 scan done.
+inline int next_mcupos(const Jpeg& j, const ScanInfo& sc, int rsti, ScanPos& p) {
+    int sta = 0;
+    if (++p.sub >= j.cmp[p.cmp].mbs) {
+        p.sub = 0;
+        if (++p.csc >= sc.ncomp) {
+            p.csc = 0;
+            p.cmp = sc.cmp[0];
+            ++p.mcu;
+            if (p.mcu >= j.mcuc) sta = 2;
+            else if (rsti > 0 && --p.rstw == 0) sta = 1;
+        } else {
+            p.cmp = sc.cmp[p.csc];
+        }
+    }
+    const Component& k = j.cmp[p.cmp];
+    if (k.V > 1) {
+        const int my = p.mcu / j.mcuh, mx = p.mcu - my * j.mcuh, sy = p.sub / k.H, sx = p.sub - sy * k.H;
+        p.dpos = (my * k.V + sy) * k.bch + mx * k.H + sx;
+    } else if (k.H > 1) {
+        p.dpos = p.mcu * k.mbs + p.sub;
+    } else {
+        p.dpos = p.mcu;
+    }
+    return sta;
+}
+
+// next_mcuposn (jpgcoder.cc:5432-5456): single-component scan order over the non-padded blocks
+inline int next_mcuposn(const Jpeg& j, int rsti, ScanPos& p) {
+    const Component& k = j.cmp[p.cmp];
+    p.dpos++;
+    if (k.bch != k.nch && p.dpos % k.bch == k.nch) p.dpos += k.bch - k.nch;
+    if (k.bcv != k.ncv && p.dpos / k.bch == k.ncv) p.dpos = k.bc;
+    if (p.dpos >= k.bc) return 2;
+    if (rsti > 0 && --p.rstw == 0) return 1;
+    return 0;
+}
+
+// skip_eobrun (jpgcoder.cc:5462-5503): jump over the blocks an end-of-band run covers
+inline int skip_eobrun(const Jpeg& j, int rsti, ScanPos& p, unsigned& eobrun) {
+    if (eobrun == 0) return 0;
+    const Component& k = j.cmp[p.cmp];
+    if (rsti > 0) {
+        if ((int)eobrun > p.rstw) return -1;
+        p.rstw -= (int)eobrun;
+    }
+    if (k.bch != k.nch) p.dpos += (int)(((unsigned)(p.dpos % k.bch) + eobrun) / (unsigned)k.nch) * (k.bch - k.nch);
+    if (k.bcv != k.ncv && p.dpos / k.bch >= k.ncv) p.dpos += (k.bcv - k.ncv) * k.bch;
+    p.dpos += (int)eobrun;
+    eobrun = 0;
+    if (p.dpos == k.bc) return 2;
+    if (p.dpos > k.bc) return -1;
+    if (rsti > 0 && p.rstw == 0) return 1;
+    return 0;
+}
+
+// One restart interval of a progressive scan (decode_jpeg, jpgcoder.cc:2985-3258; block routines :4968-5340).
+// Returns the reference's `sta` (1 restart, 2 scan done, -1 error); handoffs are recorded only by first-stage DC scans.
+int decode_progressive_interval(Jpeg& j, BitReader& br, const ScanInfo& sc, int rsti, const HuffTable* dc_t, const HuffTable* ac_t,
+                                int16_t* const planes[4], ScanPos& p, int lastdc[4], bool& handoff_due, int luma_mul) {
+    int sta = 0;
+    unsigned eobrun = 0, peobrun = 0;
+    auto track = [&]() { if (!br.eof()) j.max_dpos[p.cmp] = std::max(j.max_dpos[p.cmp], p.dpos); };
+    auto coef = [&](int bpos) -> int16_t& { return planes[p.cmp][(size_t)p.dpos * 64 + k_zigzag_to_aligned[bpos]]; };
+    if (sc.ncomp > 1 || sc.to == 0) {
+        const bool inter = sc.ncomp > 1;
+        if (sc.sah == 0) {
+            // ---- DC, first stage (decode_dc_prg_fs :4968)
+            while (sta == 0) {
+                if (handoff_due) {
+                    j.rows.push_back(crystallize(j, br, inter ? p.mcu / j.mcuh : p.dpos / j.cmp[p.cmp].bch, lastdc, luma_mul));
+                    handoff_due = false;
+                }
+                track();
+                int diff = 0;
+                const int s = decode_symbol_value(br, dc_t[j.cmp[p.cmp].td], 0x1f, &diff);
+                if (s < 0 || s > 16) { sta = -1; diff = 0; }
+                const int16_t v = (int16_t)(diff + lastdc[p.cmp]);
+                lastdc[p.cmp] = v;
+                coef(0) = (int16_t)((uint16_t)v << sc.sal);
+                if (inter) {
+                    const int old_mcu = p.mcu;
+                    if (sta != -1) sta = next_mcupos(j, sc, rsti, p);
+                    if (p.mcu % j.mcuh == 0 && old_mcu != p.mcu) handoff_due = true;
+                } else {
+                    if (sta != -1) sta = next_mcuposn(j, rsti, p);
+                    if (p.cmp == 0 && p.dpos % j.cmp[p.cmp].bch == 0) handoff_due = true;
+                }
+                if (br.eof()) { sta = 2; break; }
+            }
+        } else {
+            // ---- DC refinement: one bit per block (decode_dc_prg_sa :5124)
+            while (sta == 0) {
+                track();
+                const int bit = read_bits(br, 1);
+                coef(0) = (int16_t)(coef(0) + (bit << sc.sal));
+                sta = inter ? next_mcupos(j, sc, rsti, p) : next_mcuposn(j, rsti, p);
+                if (br.eof()) { sta = 2; break; }
+            }
+        }
+        return sta;
+    }
+    const HuffTable& act = ac_t[j.cmp[p.cmp].ta];
+    if (sc.sah == 0) {
+        // ---- AC, first stage (decode_ac_prg_fs :5014)
+        while (sta == 0) {
+            track();
+            int eob = sc.to + 1;
+            if (eobrun > 0) {
+                --eobrun;                                  // the block stays as it is (copy loop :3178 is empty)
+                eob = sc.from;
+            } else {
+                int bpos = sc.from;
+                while (bpos <= sc.to) {
+                    int v = 0;
+                    const int hc = decode_symbol_value(br, act, 0, &v);     // magnitude bits read below (depends on the symbol class)
+                    if (hc < 0) { eob = -1; break; }
+                    const int l = hc >> 4, r = hc & 15;
+                    if (l == 15 || r > 0) {
+                        const int n = read_bits(br, r);
+                        if (l + bpos > sc.to) { eob = -1; break; }
+                        for (int z = 0; z < l; ++z) coef(bpos++) = 0;
+                        coef(bpos++) = (int16_t)((uint16_t)(int16_t)devli(r, n) << sc.sal);
+                    } else {
+                        eob = bpos;
+                        const int n = read_bits(br, l);
+                        eobrun = (unsigned)(n + (1 << l));
+                        --eobrun;
+                        break;
+                    }
+                }
+            }
+            if (eob == sc.from && eobrun > 0 && peobrun > 0 && peobrun < (unsigned)act.max_eobrun - 1) {
+                j.status = ASSERTION_FAILURE; j.error = "reconstruction of non optimal coding not supported";   // errorlevel 1
+            }
+            if (eob < 0) sta = -1;
+            else sta = skip_eobrun(j, rsti, p, eobrun);
+            if (sta == 0) sta = next_mcuposn(j, rsti, p);
+            if (br.eof()) { sta = 2; break; }
+        }
+        return sta;
+    }
+    // ---- AC refinement (decode_ac_prg_sa :5150, decode_eobrun_sa :5322)
+    while (sta == 0) {
+        int16_t blk[64];
+        for (int b = sc.from; b <= sc.to; ++b) blk[b] = coef(b);
+        int eob = sc.to;
+        track();
+        if (eobrun == 0) {
+            int bpos = sc.from;
+            bool err = false;
+            while (bpos <= sc.to) {
+                int dummy = 0;
+                const int hc = decode_symbol_value(br, act, 0, &dummy);
+                if (hc < 0) { err = true; break; }
+                const int l = hc >> 4, r = hc & 15;
+                if (l == 15 || r > 0) {
+                    int z = l, v = 0;
+                    if (r == 1) v = read_bits(br, 1) ? 1 : -1;
+                    else if (r != 0) { err = true; break; }
+                    while (true) {
+                        if (blk[bpos] == 0) {
+                            if (z > 0) --z;
+                            else { blk[bpos++] = (int16_t)v; break; }
+                        } else {
+                            const int n = read_bits(br, 1);
+                            blk[bpos] = (int16_t)(blk[bpos] > 0 ? n : -n);
+                        }
+                        if (bpos++ >= sc.to) { err = true; break; }
+                    }
+                    if (err) break;
+                } else {
+                    eob = bpos;
+                    const int n = read_bits(br, l);
+                    eobrun = (unsigned)(n + (1 << l));
+                    break;
+                }
+            }
+            if (err) eob = -1;
+            else if (eobrun > 0) {
+                for (; bpos <= sc.to; ++bpos)
+                    if (blk[bpos] != 0) { const int n = read_bits(br, 1); blk[bpos] = (int16_t)(blk[bpos] > 0 ? n : -n); }
+                --eobrun;
+            }
+            if (eob == sc.from && eobrun > 0 && peobrun > 0 && peobrun < (unsigned)act.max_eobrun - 1) {
+                j.status = ASSERTION_FAILURE; j.error = "reconstruction of non optimal coding not supported";
+            }
+        } else {
+            for (int b = sc.from; b <= sc.to; ++b)
+                if (blk[b] != 0) { const int n = read_bits(br, 1); blk[b] = (int16_t)(blk[b] > 0 ? n : -n); }
+            --eobrun;
+            eob = 0;
+        }
+        peobrun = eobrun;
+        if (eob >= 0)
+            for (int b = sc.from; b <= sc.to; ++b) coef(b) = (int16_t)(coef(b) + (int16_t)((uint16_t)blk[b] << sc.sal));
+        if (eob < 0) sta = -1;
+        else sta = next_mcuposn(j, rsti, p);
+        if (br.eof()) { sta = 2; break; }
+    }
+    return sta;
+}
+
 }  // namespace
 
 // ThreadHandoff for a Huffman state captured elsewhere (the GPU decoder): same mapping as crystallize().
@@ -451,7 +670,7 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
     int mcu = 0;
     int scans = 0;
     j.padbit = -1;
-    if (j.jpegtype != 1) return fail(j, NOT_HANDLED, "progressive JPEG: host front end not implemented yet");
+    j.is_baseline = true;
     while (true) {
         ScanInfo sc;
         uint8_t type = 0;
@@ -500,11 +719,39 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
             hpos += len;
         }
         if (type != 0xDA) break;
-        for (int i = 0; i < sc.ncomp; ++i) {
+        for (int i = 0; i < sc.ncomp; ++i) {                      // jpgcoder.cc:2858-2868
             const Component& k = j.cmp[sc.cmp[i]];
-            if (!dc_t[k.td].set || !ac_t[k.ta].set) return fail(j, UNSUPPORTED_JPEG, "huffman table missing in scan");
+            const bool need_dc = j.jpegtype == 1 || ((sc.ncomp > 1 || sc.to == 0) && sc.sah == 0);
+            const bool need_ac = j.jpegtype == 1 || (sc.ncomp == 1 && sc.to > 0);
+            if ((need_dc && !dc_t[k.td].set) || (need_ac && !ac_t[k.ta].set)) return fail(j, UNSUPPORTED_JPEG, "huffman table missing in scan");
         }
-        if (sc.ncomp != j.ncmp) return fail(j, PROGRESSIVE_UNSUPPORTED, "non-interleaved multi-scan JPEG (treated as progressive by the reference)");
+        if (sc.ncomp != j.ncmp || j.jpegtype != 1) j.is_baseline = false;     // jpgcoder.cc:2912-2926: written with flag 'X'
+        if (j.jpegtype != 1) {
+            ScanPos p;
+            p.cmp = sc.cmp[0];
+            mcu = 0;
+            if (!br.eof()) {
+                j.max_bpos = std::max(j.max_bpos, sc.to);
+                j.max_sah = std::max(j.max_sah, std::max(sc.sal, sc.sah));
+                for (int i = 0; i < sc.ncomp; ++i) j.max_cmp = std::max(j.max_cmp, sc.cmp[i]);
+            }
+            bool handoff_due = true;
+            while (true) {
+                lastdc[0] = lastdc[1] = lastdc[2] = lastdc[3] = 0;
+                p.rstw = rsti;
+                const int sta = decode_progressive_interval(j, br, sc, rsti, dc_t, ac_t, planes, p, lastdc, handoff_due, luma_mul);
+                if (j.status != OK) return false;
+                if (j.padbit != -1) {
+                    if (j.padbit != unpad(br, j.padbit)) return fail(j, UNSUPPORTED_JPEG, "inconsistent use of padbits");
+                } else {
+                    j.padbit = unpad(br, j.padbit);
+                }
+                if (sta == -1) return fail(j, UNSUPPORTED_JPEG, "decode error in progressive scan");
+                if (sta == 2) { ++scans; break; }
+            }
+            if (sc.ncomp > 1) mcu = p.mcu;              // the last handoff is taken at mcu / mcuh (jpgcoder.cc:3278)
+            continue;
+        }
 
         int cmp = sc.cmp[0], csc = 0, sub = 0, dpos = 0;
         mcu = 0;

@@ -187,9 +187,11 @@ inline int bitlen16(int v) { return v ? 32 - __builtin_clz((unsigned)v) : 0; }
 
 }  // namespace
 
+bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err);
+
 bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err) {
     const Jpeg& j = lf.j;
-    if (j.jpegtype != 1) { err = "progressive re-encode not implemented"; return false; }
+    if (lf.flag != 'Z' || j.jpegtype != 1) return recode_scans(lf, planes, out, err);     // multi-scan / progressive files
     const std::vector<uint8_t>& h = j.hdr;
     HuffTable dc_t[4], ac_t[4];
     int rsti = 0;
@@ -322,6 +324,287 @@ bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vec
     out.insert(out.end(), h.begin() + hpos, h.end());      // header data after the first SOS, if any
     // everything before the garbage is bounded to (original size - garbage size): for truncated originals the scan is
     // cut exactly where the file ended (str_out->set_bound, recoder.cc:699-700, 880-886)
+    if (lf.jpeg_size >= j.grb.size() && out.size() > lf.jpeg_size - j.grb.size()) out.resize(lf.jpeg_size - j.grb.size());
+    out.insert(out.end(), j.grb.begin(), j.grb.end());
+    if (out.size() != lf.jpeg_size) { err = "re-created JPEG has the wrong size"; return false; }
+    return true;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// General (multi-scan) re-encoder for containers flagged 'X': progressive JPEGs and sequential files whose scans do
+// not interleave every component.  Restates recode_jpeg (jpgcoder.cc:3309-3724) + the block routines
+// (encode_dc_prg_fs :4993, encode_ac_prg_fs :5078, encode_dc_prg_sa :5137, encode_ac_prg_sa :5247, encode_eobrun :5346,
+// encode_crbits :5379) and the marker/stuffing pass merge_jpeg_streaming (:2562-2740), fused into one front-to-back walk.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct ScanHdr { int ncomp = 0, cmp[4] = {0, 0, 0, 0}, from = 0, to = 0, sah = 0, sal = 0; };
+
+inline int fdiv2(int v, int p) { return v < 0 ? -((-v) >> p) : (v >> p); }
+
+struct ProgWriter {
+    BitWriter& bw;
+    std::vector<uint8_t> crbits;          // stored correction bits (abytewriter "storw")
+    unsigned eobrun = 0;
+    explicit ProgWriter(BitWriter& b) : bw(b) {}
+    void flush_crbits() { for (uint8_t b : crbits) bw.put(b, 1); crbits.clear(); }
+    void flush_eobrun(const HuffTable& t) {
+        if (eobrun == 0) return;
+        while (eobrun > (unsigned)t.max_eobrun) {
+            bw.put(t.ecode[0xE0], t.elen[0xE0]);
+            bw.put(32767 - (1 << 14), 14);
+            eobrun -= (unsigned)t.max_eobrun;
+        }
+        int s = bitlen16((int)eobrun);
+        if (s) --s;
+        bw.put(t.ecode[s << 4], t.elen[s << 4]);
+        bw.put(eobrun - (1u << s), s);
+        eobrun = 0;
+    }
+};
+
+}  // namespace
+
+bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err) {
+    const Jpeg& j = lf.j;
+    const std::vector<uint8_t>& h = j.hdr;
+    HuffTable dc_t[4], ac_t[4];
+    int td[4] = {0, 0, 0, 0}, ta[4] = {0, 0, 0, 0};
+    int rsti = 0;
+    size_t hpos = 0;
+    out.clear();
+    out.reserve((size_t)lf.jpeg_size + 64);
+    out.push_back(0xFF); out.push_back(0xD8);
+    BitWriter bw(out);
+    ProgWriter pw(bw);
+    bool rst_stuck = false;                // a refused marker is never retried (rpos stops advancing, :2640-2650)
+    int scan = 0;
+    while (true) {
+        // ---- header segments up to and including the next SOS; DHT / DRI / SOS are interpreted on the way
+        ScanHdr sc;
+        uint8_t type = 0;
+        const size_t seg_begin = hpos;
+        while (type != 0xDA) {
+            if (hpos + 3 >= h.size()) break;
+            type = h[hpos + 1];
+            const size_t len = 2 + be16(&h[hpos + 2]);
+            if (hpos + len > h.size()) { err = "truncated header segment"; return false; }
+            const uint8_t* seg = &h[hpos];
+            if (type == 0xC4) {
+                size_t p = 4;
+                while (p < len) {
+                    const int tc = seg[p] >> 4, th = seg[p] & 15;
+                    if (tc >= 2 || th >= 4) break;
+                    ++p;
+                    HuffTable& t = tc ? ac_t[th] : dc_t[th];
+                    int total = 0;
+                    t.bits[0] = 0;
+                    for (int i = 0; i < 16; ++i) { t.bits[i + 1] = seg[p + i]; total += seg[p + i]; }
+                    if (total > 256 || p + 16 + total > len) { err = "bad DHT"; return false; }
+                    memcpy(t.vals, seg + p + 16, total);
+                    if (!t.build()) { err = "bad huffman table"; return false; }
+                    t.set = true;
+                    p += 16 + total;
+                }
+            } else if (type == 0xDD) {
+                rsti = be16(seg + 4);
+            } else if (type == 0xDA) {
+                sc.ncomp = seg[4];
+                if (sc.ncomp < 1 || sc.ncomp > j.ncmp || len < (size_t)(8 + 2 * sc.ncomp)) { err = "bad SOS"; return false; }
+                for (int i = 0; i < sc.ncomp; ++i) {
+                    int c = 0;
+                    while (c < j.ncmp && j.cmp[c].jid != seg[5 + 2 * i]) ++c;
+                    if (c == j.ncmp) { err = "component id mismatch"; return false; }
+                    sc.cmp[i] = c; td[c] = seg[6 + 2 * i] >> 4; ta[c] = seg[6 + 2 * i] & 15;
+                    if (td[c] >= 4 || ta[c] >= 4) { err = "huffman table number mismatch"; return false; }
+                }
+                const uint8_t* t = seg + 5 + 2 * sc.ncomp;
+                sc.from = t[0]; sc.to = t[1]; sc.sah = t[2] >> 4; sc.sal = t[2] & 15;
+                if (sc.from > sc.to || sc.to > 63 || sc.sah >= 12 || sc.sal >= 12) { err = "scan parameters out of range"; return false; }
+            }
+            hpos += len;
+        }
+        out.insert(out.end(), h.begin() + seg_begin, h.begin() + std::min(hpos, h.size()));
+        if (type != 0xDA) break;
+        ++scan;
+        // ---- one scan
+        unsigned cpos = 0, rst_this_scan = 0;
+        auto rst_ok = [&]() {              // rst_cnt_ok (:2509-2517)
+            if (rsti == 0 || rst_stuck) return false;
+            if (!lf.rst_cnt_set) return true;
+            return j.rst_cnt.size() > (size_t)scan - 1 && rst_this_scan < j.rst_cnt[scan - 1];
+        };
+        int cmp = sc.cmp[0], csc = 0, mcu = 0, sub = 0, dpos = 0;
+        const bool inter = sc.ncomp > 1;
+        auto coef = [&](int bpos) -> int { return planes[cmp][(size_t)dpos * 64 + k_zigzag_to_aligned[bpos]]; };
+        auto advance = [&](int& rstw) -> int {
+            if (inter) {                   // next_mcupos (recoder.cc:190-243)
+                int sta = 0;
+                if (++sub >= j.cmp[cmp].mbs) {
+                    sub = 0;
+                    if (++csc >= sc.ncomp) {
+                        csc = 0; cmp = sc.cmp[0]; ++mcu;
+                        if (mcu >= j.mcuc) sta = 2;
+                        else if (rsti > 0 && --rstw == 0) sta = 1;
+                    } else cmp = sc.cmp[csc];
+                }
+                const Component& k = j.cmp[cmp];
+                if (k.V > 1) {
+                    const int my = mcu / j.mcuh, mx = mcu - my * j.mcuh, sy = sub / k.H, sx = sub - sy * k.H;
+                    dpos = (my * k.V + sy) * k.bch + mx * k.H + sx;
+                } else if (k.H > 1) dpos = mcu * k.mbs + sub;
+                else dpos = mcu;
+                return sta;
+            }
+            const Component& k = j.cmp[cmp];          // next_mcuposn (jpgcoder.cc:5432-5456)
+            dpos++;
+            if (k.bch != k.nch && dpos % k.bch == k.nch) dpos += k.bch - k.nch;
+            if (k.bcv != k.ncv && dpos / k.bch == k.ncv) dpos = k.bc;
+            if (dpos >= k.bc) return 2;
+            if (rsti > 0 && --rstw == 0) return 1;
+            return 0;
+        };
+        for (int i = 0; i < sc.ncomp; ++i) {
+            const int c = sc.cmp[i];
+            const bool need_dc = j.jpegtype == 1 || ((inter || sc.to == 0) && sc.sah == 0);
+            const bool need_ac = j.jpegtype == 1 || (!inter && sc.to > 0);
+            if ((need_dc && !dc_t[td[c]].set) || (need_ac && !ac_t[ta[c]].set)) { err = "huffman table missing in scan"; return false; }
+        }
+        while (true) {
+            int lastdc[4] = {0, 0, 0, 0};
+            int sta = 0, rstw = rsti;
+            pw.eobrun = 0;
+            if (j.jpegtype == 1) {
+                // ---- sequential scan (encode_block_seq, recoder.cc:245-313)
+                while (sta == 0) {
+                    const HuffTable& dct = dc_t[td[cmp]];
+                    const HuffTable& act = ac_t[ta[cmp]];
+                    const int16_t dc = (int16_t)coef(0);
+                    const int16_t diff = (int16_t)(dc - (int16_t)lastdc[cmp]);
+                    lastdc[cmp] = dc;
+                    int s = bitlen16(diff > 0 ? diff : -diff);
+                    int nb = diff > 0 ? diff : (diff - 1) + (1 << s);
+                    bw.put(dct.ecode[s], dct.elen[s]);
+                    bw.put((uint32_t)nb, s);
+                    int end = 63;
+                    while (end > 0 && coef(end) == 0) --end;
+                    int z = 0;
+                    for (int bpos = 1; bpos <= end; ++bpos) {
+                        const int v = coef(bpos);
+                        if (v == 0) { ++z; continue; }
+                        while (z & 0xf0) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
+                        s = bitlen16(v > 0 ? v : -v);
+                        nb = v > 0 ? v : (v - 1) + (1 << s);
+                        const int hc = ((z & 0xf) << 4) + s;
+                        bw.put(act.ecode[hc], act.elen[hc]);
+                        bw.put((uint32_t)nb, s);
+                        z = 0;
+                    }
+                    if (end != 63) bw.put(act.ecode[0x00], act.elen[0x00]);
+                    sta = advance(rstw);
+                }
+            } else if (inter || sc.to == 0) {
+                if (sc.sah == 0) {
+                    // ---- DC first stage
+                    while (sta == 0) {
+                        const HuffTable& dct = dc_t[td[cmp]];
+                        const int tmp = coef(0) >> sc.sal;
+                        const int16_t diff = (int16_t)(tmp - lastdc[cmp]);
+                        lastdc[cmp] = tmp;
+                        const int s = bitlen16(diff > 0 ? diff : -diff);
+                        const int nb = diff > 0 ? diff : (diff - 1) + (1 << s);
+                        bw.put(dct.ecode[s], dct.elen[s]);
+                        bw.put((uint32_t)nb, s);
+                        sta = advance(rstw);
+                    }
+                } else {
+                    // ---- DC refinement bit
+                    while (sta == 0) {
+                        bw.put((uint32_t)((coef(0) >> sc.sal) & 1), 1);
+                        sta = advance(rstw);
+                    }
+                }
+            } else if (sc.sah == 0) {
+                // ---- AC first stage
+                const HuffTable& act = ac_t[ta[cmp]];
+                while (sta == 0) {
+                    int z = 0;
+                    for (int bpos = sc.from; bpos <= sc.to; ++bpos) {
+                        const int tmp = fdiv2(coef(bpos), sc.sal);
+                        if (tmp != 0) {
+                            pw.flush_eobrun(act);
+                            while (z >= 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
+                            const int a = tmp > 0 ? tmp : -tmp;
+                            const int s = bitlen16(a);
+                            const int nb = tmp > 0 ? tmp : (tmp - 1) + (1 << s);
+                            const int hc = (z << 4) + s;
+                            bw.put(act.ecode[hc], act.elen[hc]);
+                            bw.put((uint32_t)nb, s);
+                            z = 0;
+                        } else ++z;
+                    }
+                    if (z > 0) {
+                        ++pw.eobrun;
+                        if (pw.eobrun == (unsigned)act.max_eobrun) pw.flush_eobrun(act);
+                    }
+                    sta = advance(rstw);
+                }
+                pw.flush_eobrun(act);
+            } else {
+                // ---- AC refinement
+                const HuffTable& act = ac_t[ta[cmp]];
+                while (sta == 0) {
+                    int blk[64];
+                    for (int bpos = sc.from; bpos <= sc.to; ++bpos) blk[bpos] = fdiv2(coef(bpos), sc.sal);
+                    int eob = sc.from;
+                    for (int bpos = sc.to; bpos >= sc.from; --bpos)
+                        if (blk[bpos] == 1 || blk[bpos] == -1) { eob = bpos + 1; break; }
+                    if (eob > sc.from && pw.eobrun > 0) { pw.flush_eobrun(act); pw.flush_crbits(); }
+                    int z = 0, bpos = sc.from;
+                    for (; bpos < eob; ++bpos) {
+                        const int tmp = blk[bpos];
+                        if (tmp == 0) {
+                            if (++z == 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); pw.flush_crbits(); z = 0; }
+                        } else if (tmp == 1 || tmp == -1) {
+                            const int hc = (z << 4) + 1;
+                            bw.put(act.ecode[hc], act.elen[hc]);
+                            bw.put(tmp > 0 ? 1u : 0u, 1);
+                            pw.flush_crbits();
+                            z = 0;
+                        } else {
+                            pw.crbits.push_back((uint8_t)(tmp & 1));
+                        }
+                    }
+                    for (; bpos <= sc.to; ++bpos)
+                        if (blk[bpos] != 0) pw.crbits.push_back((uint8_t)(blk[bpos] & 1));
+                    if (eob <= sc.to) {
+                        ++pw.eobrun;
+                        if (pw.eobrun == (unsigned)act.max_eobrun) { pw.flush_eobrun(act); pw.flush_crbits(); }
+                    }
+                    sta = advance(rstw);
+                }
+                pw.flush_eobrun(act);
+                pw.flush_crbits();
+            }
+            bw.pad((uint8_t)j.padbit);
+            if (sta == 2) break;
+            // restart: marker after the padded byte when the scan's marker budget allows (:2640-2650)
+            if (rsti > 0) {
+                if (rst_ok()) {
+                    out.push_back(0xFF);
+                    out.push_back((uint8_t)(0xD0 + (cpos & 7)));
+                    ++cpos; ++rst_this_scan;
+                } else {
+                    rst_stuck = true;
+                }
+            }
+        }
+        // bogus trailing restart markers of this scan (:2711-2719)
+        if ((size_t)scan - 1 < j.rst_err.size())
+            for (unsigned i = 0; i < j.rst_err[scan - 1]; ++i) { out.push_back(0xFF); out.push_back((uint8_t)(0xD0 + (cpos & 7))); ++cpos; }
+    }
+    if (scan == 0) { err = "no scan found"; return false; }
     if (lf.jpeg_size >= j.grb.size() && out.size() > lf.jpeg_size - j.grb.size()) out.resize(lf.jpeg_size - j.grb.size());
     out.insert(out.end(), j.grb.begin(), j.grb.end());
     if (out.size() != lf.jpeg_size) { err = "re-created JPEG has the wrong size"; return false; }

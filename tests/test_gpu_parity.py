@@ -130,14 +130,12 @@ def test_file_level_compress_matches_reference_lep_bytes():
     from helpers import GOLDEN
     from lepton_b200 import LeptonB200FileCodec
     names = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "colorswap.jpg",
-             "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg", "androidprogressive.jpg"]
+             "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg",
+             "androidprogressive.jpg", "iphoneprogressive.jpg", "iphoneprogressive2.jpg"]     # incl. progressive (flag 'X')
     jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
     fc = LeptonB200FileCodec(0, host_threads=4)
     res = fc.compress(jpegs)
     for n, (st, lep) in zip(names, res):
-        if n == "androidprogressive.jpg":
-            assert st == 200            # refused (progressive host front end not built yet), never mis-coded
-            continue
         assert st == 0, (n, st)
         assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
     fc.close()
@@ -151,7 +149,8 @@ def test_file_level_roundtrip_jpeg_lep_jpeg():
     from lepton_b200 import LeptonB200FileCodec
     names = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "colorswap.jpg",
              "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "trailingrst2.jpg",
-             "gray2sf.jpg", "narrowrst.jpg", "nofsync.jpg", "singlerowtrunc.jpg", "truncatedzerorun.jpg"]   # incl. truncated files
+             "gray2sf.jpg", "narrowrst.jpg", "nofsync.jpg", "singlerowtrunc.jpg", "truncatedzerorun.jpg",     # truncated files
+             "androidprogressive.jpg", "iphoneprogressive.jpg", "iphoneprogressive2.jpg"]                        # progressive
     jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
     fc = LeptonB200FileCodec(0, host_threads=4, chunk_images=4)
     leps = fc.compress(jpegs)
