@@ -101,6 +101,10 @@ int lepb200_decode_images(lepb200_ctx* ctx, const lepb200_image* images, int nim
 /* ---- staged forms (for pipelining and for timing the kernel with inputs resident in HBM) ---- */
 int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages); /* H2D planes + job tables */
 int lepb200_encode_launch(lepb200_ctx* ctx);                                           /* kernel only (async) */
+/* the two halves of lepb200_encode_launch, for callers that pipeline them over different batches: symbolisation +
+ * model update (the heavy, throughput-bound kernel) and the serial range-coder chains (latency-bound, a few warps) */
+int lepb200_encode_launch_symbolise(lepb200_ctx* ctx);
+int lepb200_encode_launch_rangecode(lepb200_ctx* ctx);
 int lepb200_encode_fetch(lepb200_ctx* ctx, lepb200_stream* out);                       /* sync + D2H streams */
 int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in);
 int lepb200_decode_launch(lepb200_ctx* ctx);
@@ -148,6 +152,12 @@ uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx);
 uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx);
 /* Size in bytes of one per-warp probability model (informational). */
 size_t lepb200_model_bytes(void);
+/* Co-scheduling knobs (no reference counterpart): cap the persistent encode grid at n CTAs per SM (0 = fill the SM) and
+ * set how many images one CTA of the Huffman kernel decodes, so that the Huffman decode of the next chunk runs NEXT TO
+ * the encode kernel of the current one instead of behind it.  Environment LEPB200_ENC_CTA_CAP / LEPB200_HUFF_WARPS override. */
+void lepb200_set_encode_ctas_per_sm(lepb200_ctx* ctx, int n);
+void lepb200_set_host_threads(lepb200_ctx* ctx, int n);   /* host threads the context may use for staging copies (default 1) */
+void lepb200_set_huffman_warps_per_cta(lepb200_ctx* ctx, int n);
 /* 1 if a CUDA device is usable from this process. */
 int lepb200_device_available(void);
 

@@ -1,9 +1,11 @@
 // lep_capi.cu -- context, device memory management and the C ABI declared in include/lepton_b200.h.
 // Single translation unit: the kernels are included so that nvcc sees one module (no -rdc needed).
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -81,11 +83,14 @@ struct lepb200_ctx {
     std::vector<size_t> plane_bytes;      // per image*3
     size_t row_stride = 0;
     int grid = 0;
-    bool have_batch = false, launched = false, is_encode = true;
+    bool have_batch = false, launched = false, symbolised = false, is_encode = true;
     float last_ms = -1.f, last_ms_a = -1.f, last_ms_huff = -1.f;
     uint64_t launches = 0;
     uint64_t alg_bytes = 0;
     uint64_t coded_blocks = 0;
+    int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
+    int huff_warps = 4;                   // images per CTA of the Huffman kernel
+    int host_threads = 1;                 // host threads this context may use for staging copies
 };
 
 #define CK(call)                                                                            \
@@ -215,6 +220,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     int per_sm = 0;
     if (encode) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lep_encode_kernel, ENC_WARPS_PER_CTA * 32, 0));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lep_decode_kernel, DEC_WARPS_PER_CTA * 32, 0));
+    if (encode && ctx->enc_cta_cap > 0) per_sm = std::min(per_sm, ctx->enc_cta_cap);
     const int wpc = encode ? ENC_WARPS_PER_CTA : DEC_WARPS_PER_CTA;
     int grid = std::max(1, std::min(per_sm * ctx->sm_count, (nseg + wpc - 1) / wpc));
     ctx->grid = grid;
@@ -281,9 +287,15 @@ int lepb200_create(lepb200_ctx** out, int device) {
         delete ctx;
         return LEPB200_ERR_CUDA;
     }
+    if (const char* e = getenv("LEPB200_ENC_CTA_CAP")) ctx->enc_cta_cap = atoi(e);          // tuning overrides
+    if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
     *out = ctx;
     return LEPB200_OK;
 }
+
+void lepb200_set_encode_ctas_per_sm(lepb200_ctx* ctx, int n) { if (ctx && !getenv("LEPB200_ENC_CTA_CAP")) ctx->enc_cta_cap = n; }
+void lepb200_set_host_threads(lepb200_ctx* ctx, int n) { if (ctx && n > 0) ctx->host_threads = n; }
+void lepb200_set_huffman_warps_per_cta(lepb200_ctx* ctx, int n) { if (ctx && !getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = n; }
 
 void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
@@ -427,10 +439,25 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(ctx->d_htabs.reserve(sizeof(HuffTableDev) * std::max<size_t>(1, tabs.size())));
     CK(ctx->h_stage.reserve(huff_total + 256));
     uint8_t* hs = static_cast<uint8_t*>(ctx->h_stage.p);
+    {
+        // gather the de-stuffed scans into the pinned staging buffer (hundreds of MB per chunk): split over host threads
+        const int nt = std::max(1, std::min(ctx->host_threads, n));
+        auto copy_range = [&](int t) {
+            for (int i = t; i < n; i += nt) {
+                const HuffJob& jb = jobs[i];
+                memcpy(hs + jb.huff, scans[i].entropy, scans[i].nbytes);
+                memset(hs + jb.huff + scans[i].nbytes, 0, align_up((size_t)scans[i].nbytes + 16, 16) - scans[i].nbytes);
+            }
+        };
+        if (nt == 1) copy_range(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(copy_range, t);
+            for (auto& t : th) t.join();
+        }
+    }
     for (int i = 0; i < n; ++i) {
         HuffJob& jb = jobs[i];
-        memcpy(hs + jb.huff, scans[i].entropy, scans[i].nbytes);
-        memset(hs + jb.huff + scans[i].nbytes, 0, align_up((size_t)scans[i].nbytes + 16, 16) - scans[i].nbytes);
         jb.huff += (unsigned long long)(uintptr_t)ctx->d_huff.p;
         jb.rows += (unsigned long long)(uintptr_t)ctx->d_hrows.p;
         for (int c = 0; c < jb.ncmp; ++c) jb.plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
@@ -445,7 +472,10 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
 
     if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    lep_huffdecode_kernel<<<(n + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_THREADS, 0, ctx->stream>>>(
+    // CTA width: 7 images per CTA puts a 1024-image chunk on one CTA per SM, whose registers fit next to the encode
+    // kernel of the previous chunk when that one is capped (lepb200_set_encode_ctas_per_sm), so the two overlap
+    const int hw = std::max(1, std::min(HUFF_MAX_WARPS, ctx->huff_warps));
+    lep_huffdecode_kernel<<<(n + hw - 1) / hw, hw * 32, 0, ctx->stream>>>(
         static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
@@ -487,7 +517,7 @@ int lepb200_encode_upload_resident(lepb200_ctx* ctx, const lepb200_image* images
     return encode_prepass(ctx);
 }
 
-int lepb200_encode_launch(lepb200_ctx* ctx) {
+int lepb200_encode_launch_symbolise(lepb200_ctx* ctx) {
     if (!ctx || !ctx->have_batch || !ctx->is_encode) { if (ctx) ctx->err = "encode_launch without encode_upload"; return LEPB200_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     const int nseg = (int)ctx->segs.size();
@@ -499,13 +529,28 @@ int lepb200_encode_launch(lepb200_ctx* ctx) {
         static_cast<uint16_t*>(ctx->d_tokens.p));
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
+    ctx->launches += 1;
+    ctx->symbolised = true;
+    return LEPB200_OK;
+}
+
+int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
+    if (!ctx || !ctx->symbolised || !ctx->is_encode) { if (ctx) ctx->err = "encode_launch_rangecode without encode_launch_symbolise"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size();
     lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(
         static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p), static_cast<const uint16_t*>(ctx->d_tokens.p));
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches += 2;
+    ctx->launches += 1;
+    ctx->symbolised = false;
     ctx->launched = true;
     return LEPB200_OK;
+}
+
+int lepb200_encode_launch(lepb200_ctx* ctx) {
+    const int r = lepb200_encode_launch_symbolise(ctx);
+    return r ? r : lepb200_encode_launch_rangecode(ctx);
 }
 
 int lepb200_encode_fetch(lepb200_ctx* ctx, lepb200_stream* out) {

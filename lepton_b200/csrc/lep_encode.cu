@@ -25,8 +25,20 @@ namespace lepb200 {
 constexpr int ENC_WARPS_PER_CTA = 4;
 constexpr int QCAP = 1472;   // worst case decisions per block: 6 + 49*22 + 2*(3 + 7*22) + 22 = 1420
 
+// Decision items.  Symbolisation does not write the binary decisions one by one: every coded coefficient leaves ONE
+// 16-byte descriptor (exponent / sign / residual / threshold branch bases, magnitude, sign, first queue position) and
+// one byte in `mark` at its first queue position; the flush expands positions to (branch index, bit) pairs 32 at a time.
+//   coefficient: w0 = exp base | len << 20 | sign << 24          w1 = sign branch | |v| << 20
+//                w2 = residual base | first position << 20       w3 = threshold base | min_threshold << 20 (15 = none)
+//   single decision ("raw"): w0 = 1 << 31, w1 = (bit << 31) | branch
+// Item ids are fixed: 0..5 7x7 count bits, 6..54 7x7 coefficients (zig-zag), 55..57 / 65..67 edge counts, 58..64 /
+// 68..74 edge coefficients, 75..96 DC decisions.
+constexpr int N_ITEMS = 100;
+constexpr int IT_NZ = 0, IT_77 = 6, IT_HCNT = 55, IT_H = 58, IT_VCNT = 65, IT_V = 68, IT_DC = 75;
+
 struct EncWarpSmem {
-    uint32_t queue[QCAP];     // (bit << 31) | model index
+    uint4 desc[N_ITEMS];
+    uint8_t mark[QCAP];       // item id + 1 at the first queue position of each item, 0 elsewhere (kept zero between blocks)
     int16_t rast[3][64];      // raster-order copies: [0]=cur/left ping, [1]=left/cur pong, [2]=above
     int32_t tmp[64];          // IDCT intermediate
     int16_t pix[64];          // IDCT output (pixels sans DC)
@@ -39,32 +51,65 @@ struct EncShared {
     EncWarpSmem w[ENC_WARPS_PER_CTA];
 };
 
-// ---- queue flush: batched model update + range-coder chain ------------------------------------------
-__device__ __forceinline__ void flush_queue(const uint32_t* __restrict__ queue, int n, uint16_t* __restrict__ model,
+// ---- queue flush: expansion of the items + batched model update ---------------------------------------
+__device__ __forceinline__ uint32_t expand_item(const uint4 d, int pos) {
+    if (d.x >> 31) return d.y;
+    const int len = (int)((d.x >> 20) & 15u), nexp = min(len + 1, 11);
+    const int k = pos - (int)(d.z >> 20);
+    if (k < nexp) return ((d.x & 0xfffffu) + (uint32_t)k) | ((uint32_t)(len != k) << 31);
+    if (k == nexp) return (d.y & 0xfffffu) | (((d.x >> 24) & 1u) << 31);
+    const int ib = len - 2 - (k - nexp - 1);                  // residual bit index, MSB first
+    const uint32_t av = d.y >> 20;
+    const uint32_t bit = (av >> ib) & 1u;
+    // threshold-coded bits (edges): branch chosen by the bits already sent, i.e. the magnitude's prefix (model.hh:1085-1100)
+    const uint32_t addr = ib >= (int)((d.w >> 20) & 15u) ? (d.w & 0xfffffu) + min(av >> (ib + 1), 127u) : (d.z & 0xfffffu) + (uint32_t)ib;
+    return addr | (bit << 31);
+}
+
+__device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, uint16_t* __restrict__ model,
                                             const uint32_t* __restrict__ s_rcp, uint16_t* __restrict__ tokens, uint32_t& ntok,
                                             uint32_t tok_cap, int lane) {
-    const uint32_t lt_mask = (1u << lane) - 1;
+    const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
+    uint32_t carry = 0;                                        // item covering the last position of the previous batch
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
         const bool active = i < n;
-        const uint32_t e = active ? queue[i] : 0;
+        // which item covers queue position i: nearest start mark at or below it
+        const uint32_t mk = ws.mark[i];
+        ws.mark[i] = 0;
+        const uint32_t starts = __ballot_sync(FULL, mk != 0) & le_mask;
+        const uint32_t from_lane = __shfl_sync(FULL, mk, starts ? 31 - __clz(starts) : 0);
+        const uint32_t item = starts ? from_lane : carry;
+        carry = __shfl_sync(FULL, item, 31);
+        const uint32_t e = active ? expand_item(ws.desc[item - 1], i) : 0u;
         const uint32_t addr = e & 0xfffffu, bit = e >> 31;
         const uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
         const uint32_t earlier = peers & lt_mask;
         const int rank = __popc(earlier);
         const int pred = earlier ? 31 - __clz(earlier) : lane;     // previous decision on the same branch
         uint32_t w = active ? (uint32_t)model[addr] : 0u;
-        const int maxrank = __reduce_max_sync(FULL, rank);
-        // Resolve same-branch conflicts in queue order: in round r the lanes of rank r take over the state their
-        // predecessor (rank r-1, already resolved) leaves behind after its own update.
-        for (int r = 1; r <= maxrank; ++r) {
-            const uint32_t after = branch_update(w, bit);
-            const uint32_t from_pred = __shfl_sync(FULL, after, pred);
-            if (rank == r) w = from_pred;
+        // Resolve same-branch conflicts in queue order.  While no count of the group can saturate inside this batch
+        // (the common case) record_obs_and_update is a plain increment, so the state a lane sees is the loaded word
+        // plus the number of zeros / ones its predecessors on the same branch observed: closed form, no rounds.
+        const uint32_t ones = __ballot_sync(FULL, bit != 0);
+        const uint32_t n1_all = __popc(peers & ones), n0_all = __popc(peers & ~ones);
+        const bool plain = !active || ((w & 0xff) + n0_all <= 254u && (w >> 8) + n1_all <= 254u);   // low byte 0xff (special state) never passes
+        if (__all_sync(FULL, plain)) {
+            w += __popc(earlier & ~ones) + (__popc(earlier & ones) << 8);
+        } else {
+            // general path: in round r the lanes of rank r take over the state their predecessor (rank r-1, already
+            // resolved) leaves behind after its own update.
+            const int maxrank = __reduce_max_sync(FULL, rank);
+            for (int r = 1; r <= maxrank; ++r) {
+                const uint32_t after = branch_update(w, bit);
+                const uint32_t from_pred = __shfl_sync(FULL, after, pred);
+                if (rank == r) w = from_pred;
+            }
         }
         const uint32_t pb = branch_prob(w, s_rcp) | (bit << 8);
         if (active && (peers >> lane) == 1u) model[addr] = (uint16_t)branch_update(w, bit);   // last decision of its branch
         if (active && ntok + i < tok_cap) tokens[ntok + i] = (uint16_t)pb;                    // coalesced 2-byte stores
+        __syncwarp();                                                                         // order this batch's model stores before the next batch's loads
     }
     ntok += (uint32_t)n;
     __syncwarp();
@@ -110,6 +155,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             uint4* m4 = reinterpret_cast<uint4*>(model);
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (uint32_t i = lane; i < M_TOTAL / 8; i += 32) m4[i] = z;
+            uint32_t* mk4 = reinterpret_cast<uint32_t*>(ws.mark);        // the flush leaves the marks zero; a segment that ended on an error does not
+            for (int i = lane; i < QCAP / 4; i += 32) mk4[i] = 0u;
         }
         __syncwarp();
 
@@ -118,22 +165,14 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
         uint32_t ntok = 0;
 
         // per-component row buffers: bottom-edge prediction (8 x int16) and 7x7 nonzero count of the row above
-        int16_t* row_edge[3]; uint8_t* row_nz[3];
-        {
-            size_t off = 0;
-            for (int c = 0; c < 3; ++c) {
-                int w = c < g.ncmp ? g.bch[c] : 0;
-                row_edge[c] = reinterpret_cast<int16_t*>(rowbuf + off); off += (size_t)w * 16;
-            }
-            for (int c = 0; c < 3; ++c) {
-                int w = c < g.ncmp ? g.bch[c] : 0;
-                row_nz[c] = rowbuf + off; off += (size_t)((w + 15) & ~15);
-            }
-        }
+        // (offsets kept as scalars: arrays indexed by the component would live in local memory)
+        const int bw0 = g.bch[0], bw1 = g.ncmp > 1 ? g.bch[1] : 0, bw2 = g.ncmp > 2 ? g.bch[2] : 0;
+        const size_t nz_base = (size_t)(bw0 + bw1 + bw2) * 16;
+        const int nzs0 = (bw0 + 15) & ~15, nzs1 = (bw1 + 15) & ~15;
 
         int status = ST_OK;
         unsigned long long ndec = 0;
-        bool top[3] = {true, true, true};
+        uint32_t top_mask = 7u;                 // bit c set: no row of component c coded yet in this segment
         uint32_t index = 0;
         for (;;) {
             RowSpec rs = row_spec_from_index(index++, g);
@@ -142,8 +181,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             if (rs.skip) continue;
             if (rs.luma_y < sd.min_y) continue;
             const int c = rs.component, y = rs.curr_y;
-            const bool has_above = !top[c];
-            top[c] = false;
+            const bool has_above = !((top_mask >> c) & 1u);
+            top_mask &= ~(1u << c);
             const int ci = c == 0 ? 0 : 1;
             const int w = g.bch[c];
             const uint32_t* plane = reinterpret_cast<const uint32_t*>(g.plane[c]);
@@ -151,8 +190,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             const uint32_t* abovep = rowp - (size_t)w * 32;
             const uint16_t* q = g.q[c];
             const int q0 = q[0];
-            int16_t* redge = row_edge[c];
-            uint8_t* rnz = row_nz[c];
+            int16_t* redge = reinterpret_cast<int16_t*>(rowbuf + (size_t)(c == 0 ? 0 : (c == 1 ? bw0 : bw0 + bw1)) * 16);
+            uint8_t* rnz = rowbuf + nz_base + (c == 0 ? 0 : (c == 1 ? nzs0 : nzs0 + nzs1));
 
             uint32_t cur = rowp[lane];
             uint32_t abv = has_above ? abovep[lane] : 0u;
@@ -193,7 +232,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                     if (lane < 6) {
                         int idx = 5 - lane;                               // bit index, MSB first
                         int prefix = nz >> (idx + 1);
-                        ws.queue[lane] = m_nz7(ci, bin, idx, prefix) | ((uint32_t)((nz >> idx) & 1) << 31);
+                        ws.desc[IT_NZ + lane] = make_uint4(0x80000000u, m_nz7(ci, bin, idx, prefix) | ((uint32_t)((nz >> idx) & 1) << 31), 0u, 0u);
+                        ws.mark[lane] = (uint8_t)(IT_NZ + lane + 1);
                     }
                     qn = 6;
                 }
@@ -224,16 +264,11 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                             const int bin = sm.nzbin[left_nz];
                             const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
                             const int coord = h ? r1 : r0;
-                            uint32_t ea = m_exp7(ci, bin, zz, bsr);
-                            int o = off;
-                            const int nexp = min(len + 1, 11);
-                            for (int i = 0; i < nexp; ++i) ws.queue[o++] = (ea + i) | ((uint32_t)(len != i) << 31);
-                            if (len) {
-                                ws.queue[o++] = m_sign(ci, 0, 0) | ((uint32_t)(v >= 0) << 31);
-                                uint32_t ra = m_resn(ci, coord, bin);
-                                for (int i = len - 2; i >= 0; --i) ws.queue[o++] = (ra + i) | ((uint32_t)((av >> i) & 1) << 31);
-                            }
-                            off = o;
+                            ws.desc[IT_77 + zz] = make_uint4(m_exp7(ci, bin, zz, bsr) | ((uint32_t)len << 20) | ((uint32_t)(v >= 0) << 24),
+                                                             m_sign(ci, 0, 0) | ((uint32_t)(av & 0x7ff) << 20),
+                                                             m_resn(ci, coord, bin) | ((uint32_t)off << 20), 15u << 20);
+                            ws.mark[off] = (uint8_t)(IT_77 + zz + 1);
+                            off += coef_entries(len);
                         }
                     }
                     // a lane's two coefficients: keep the max of both for eob
@@ -259,8 +294,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                     const uint32_t hm = nzmask & 0x7f, vm = (nzmask >> 8) & 0x7f;
                     const int ne_h = __popc(hm), ne_v = __popc(vm);
                     int prior = 0;
-                    if (is_h && has_above) prior = lak_pred(rcur, rabove, g.icos_x[c] + k * 8, k, 8);
-                    if (is_v && has_left) prior = lak_pred(rcur, rleft, g.icos_y[c] + k * 8, 8 * k, 1);
+                    if ((is_h && has_above) || (is_v && has_left))        // one pass for both edges: per-lane neighbour / stride / table
+                        prior = lak_pred(rcur, is_h ? rabove : rleft, (is_h ? g.icos_x[c] : g.icos_y[c]) + k * 8, coord, is_h ? 8 : 1);
                     const int ne_rem = is_h ? ne_h - __popc(hm & lt_mask) : ne_v - __popc(vm & ((lt_mask >> 8) & 0x7f));
                     const bool coded = (is_h || is_v) && ne_rem > 0;
                     const int av = iabs(v) & 0xffff;
@@ -276,37 +311,28 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                         const int ne = vert ? ne_v : ne_h;
                         const int eob = vert ? eoby : eobx;
                         int o = vert ? off : qn;
-                        for (int i = 2; i >= 0; --i)
-                            ws.queue[o++] = m_nze(vert, ci, eob, (nz + 3) / 7, i, ne >> (i + 1)) | ((uint32_t)((ne >> i) & 1) << 31);
+                        const int it = vert ? IT_VCNT : IT_HCNT;
+                        for (int i = 2; i >= 0; --i) {
+                            ws.desc[it + 2 - i] = make_uint4(0x80000000u, m_nze(vert, ci, eob, (nz + 3) / 7, i, ne >> (i + 1)) | ((uint32_t)((ne >> i) & 1) << 31), 0u, 0u);
+                            ws.mark[o++] = (uint8_t)(it + 2 - i + 1);
+                        }
                     }
                     if (coded) {
                         const int zig15 = is_h ? k - 1 : 6 + k;
                         const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
-                        uint32_t ea = m_expx(ci, ne_rem, zig15, bsr);
-                        int o = off;
-                        const int nexp = min(len + 1, 11);
-                        for (int i = 0; i < nexp; ++i) ws.queue[o++] = (ea + i) | ((uint32_t)(len != i) << 31);
-                        if (len) {
-                            const int p16 = (int)(int16_t)prior;                       // sign_array_8: int16 truncation (model.hh:1116)
-                            const int sctx = p16 == 0 ? 0 : (p16 > 0 ? 1 : 2);
-                            ws.queue[o++] = m_sign(ci, sctx, bsr) | ((uint32_t)(v >= 0) << 31);
-                            if (len > 1) {
-                                const int min_thr = g.min_thr[c][coord];
-                                int i = len - 2;
-                                if (i >= min_thr) {
-                                    const int ctx_abs = iabs(prior) & 0xffff;          // uint16_t ctx_abs (model.hh:1079)
-                                    uint32_t ta = m_thr(ci, min(ctx_abs >> min_thr, 255), min(len - min_thr, 7));
-                                    uint32_t so = 1;
-                                    for (; i >= min_thr; --i) {
-                                        uint32_t b = (av >> i) & 1;
-                                        ws.queue[o++] = (ta + so) | (b << 31);
-                                        so = min((so << 1) | b, 127u);
-                                    }
-                                }
-                                uint32_t ra = m_resn(ci, coord, ne_rem);
-                                for (; i >= 0; --i) ws.queue[o++] = (ra + i) | ((uint32_t)((av >> i) & 1) << 31);
-                            }
+                        const int p16 = (int)(int16_t)prior;                           // sign_array_8: int16 truncation (model.hh:1116)
+                        const int sctx = p16 == 0 ? 0 : (p16 > 0 ? 1 : 2);
+                        const int min_thr = g.min_thr[c][coord];
+                        uint32_t w3 = 15u << 20;
+                        if (len - 2 >= min_thr) {
+                            const int ctx_abs = iabs(prior) & 0xffff;                  // uint16_t ctx_abs (model.hh:1079)
+                            w3 = m_thr(ci, min(ctx_abs >> min_thr, 255), min(len - min_thr, 7)) | ((uint32_t)min_thr << 20);
                         }
+                        const int it = (is_h ? IT_H : IT_V) + k - 1;
+                        ws.desc[it] = make_uint4(m_expx(ci, ne_rem, zig15, bsr) | ((uint32_t)len << 20) | ((uint32_t)(v >= 0) << 24),
+                                                 m_sign(ci, sctx, bsr) | ((uint32_t)(av & 0x7ff) << 20),
+                                                 m_resn(ci, coord, ne_rem) | ((uint32_t)off << 20), w3);
+                        ws.mark[off] = (uint8_t)(it + 1);
                     }
                     qn += 3 + total;
                 }
@@ -333,7 +359,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                             const int i = len - 2 - (lane - nexp - 1);
                             e = (m_resdc(lm) + i) | ((uint32_t)((av >> i) & 1) << 31);
                         }
-                        ws.queue[qn + lane] = e;
+                        ws.desc[IT_DC + lane] = make_uint4(0x80000000u, e, 0u, 0u);
+                        ws.mark[qn + lane] = (uint8_t)(IT_DC + lane + 1);
                     }
                     qn += n;
                 }
@@ -348,7 +375,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 // ---------------- code the queued decisions
                 status = __reduce_max_sync(FULL, status);
                 if (status != ST_OK) break;
-                flush_queue(ws.queue, qn, model, sm.rcp, tokens, ntok, tok_cap, lane);
+                flush_queue(ws, qn, model, sm.rcp, tokens, ntok, tok_cap, lane);
                 ndec += (unsigned long long)qn;
 
                 // early-out on truncated images (vp8_encoder.cc:110-113,133-135): not after the right-most block

@@ -4,6 +4,8 @@
 // write_ujpg on the way in, read_ujpg / recode_baseline_jpeg on the way out); the arithmetic coding itself goes
 // through the C ABI of lep_capi.cu to the sm_100a kernels.  No CPU coder exists in this library.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -97,6 +99,7 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
     c->ctx = ctx;
     c->ctx2[0] = ctx; c->ctx2[1] = ctxb; c->ctx2[2] = ctxc;
     c->nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    for (int s = 0; s < 3; ++s) lepb200_set_host_threads(c->ctx2[s], c->nthreads);
     *out = c;
     return LEPB200_OK;
 }
@@ -147,6 +150,7 @@ struct ChunkState {
     std::vector<int> seg_base;
     std::vector<lepb200_stream> streams;
     int gpu_rc = 0;
+    bool enc_done = false;                // kernel A finished for this chunk
     // GPU Huffman path
     bool on_gpu = false;
     std::vector<lepb200_jpeg_scan> scans;
@@ -157,6 +161,11 @@ struct ChunkState {
 
 int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n, lepb200_result* out) {
     if (!c || !jpegs || !out || n <= 0) return LEPB200_ERR_INVALID;
+    const bool trace = getenv("LEPB200_TRACE") != nullptr;           // stage timeline on stderr (diagnostics)
+    const double t_origin = now_s();
+    auto mark = [&](const char* what, int k, double t_begin) {
+        if (trace) fprintf(stderr, "[trace] %-14s chunk %d  %8.1f -> %8.1f ms\n", what, k, (t_begin - t_origin) * 1e3, (now_s() - t_origin) * 1e3);
+    };
     c->err.clear();
     c->t_front = c->t_gpu = c->t_back = 0;
     const int chunk = std::max(1, c->chunk_images);
@@ -205,6 +214,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             });
             if (ineligible.load() == 0) {
                 s.on_gpu = true;
+                mark("front", k, t0);
                 std::lock_guard<std::mutex> g(tmu);
                 c->t_front += now_s() - t0;
                 return;
@@ -259,57 +269,76 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         std::lock_guard<std::mutex> g(tmu);
         c->t_front += now_s() - t0;
     };
-    auto gpu = [&](int k) {
+    auto huff = [&](int k) {              // GPU Huffman decode of the chunk (H2D of the entropy-coded bytes, one kernel)
         double t0 = now_s();
         ChunkState& s = cs[k];
         if (s.on_gpu && s.gpu_rc == 0) {
             lepb200_ctx* ctx = c->ctx2[k % 3];
-            const int m = s.end - s.begin;
-            s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), m);
+            s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), s.end - s.begin);
             c->t_huff_ms = lepb200_last_huffman_ms(ctx);
-            if (s.gpu_rc == 0) {
-                int nseg_total = 0;
-                int16_t* none[4] = {nullptr, nullptr, nullptr, nullptr};
-                for (int i = 0; i < m; ++i) {
-                    Jpeg& j = *s.js[i];
-                    const lepb200_jpeg_scan& sc = s.scans[i];
-                    if (sc.status == 0 && sc.nrows >= 2) {
-                        j.padbit = (int8_t)sc.padbit;
-                        j.rows.clear();
-                        for (int r = 0; r < sc.nrows; ++r) j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
-                        for (size_t r = 1; r < j.rows.size(); ++r)
-                            if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
-                        s.splits[i] = select_splits(j);
-                    } else {
-                        j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
-                        j.error = "GPU Huffman decoder refused the scan";
-                        Handoff h0;                       // placeholder single segment so that the batch layout stays intact
-                        s.splits[i].selected.assign(1, h0);
-                    }
-                    status[s.begin + i] = j.status;
-                    lepb200_image im;
-                    fill_image(im, j, none, s.splits[i].selected);
-                    s.imgs.push_back(im);
-                    s.idx.push_back(i);
-                    nseg_total += im.nseg;
-                }
-                s.streams.resize(nseg_total);
-                s.seg_base.assign(s.imgs.size() + 1, 0);
-                for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
-                s.gpu_rc = lepb200_encode_upload_resident(ctx, s.imgs.data(), m);
-                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(ctx);         // kernels A and B queued; fetched by the next stage
-            }
-        } else if (s.gpu_rc == 0 && !s.imgs.empty()) {
-            s.gpu_rc = lepb200_encode_upload(c->ctx2[k % 3], s.imgs.data(), (int)s.imgs.size());
-            if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(c->ctx2[k % 3]);
+            mark("huffman", k, t0);
+            if (trace) fprintf(stderr, "[trace]   huffman kernel %.1f ms\n", c->t_huff_ms);
         }
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
-    auto gpu2 = [&](int k) {              // wait for the chunk's kernels, compact, D2H the streams
+    auto enc = [&](int k) {               // thread-segment selection, token pre-pass, kernel A (symbolise + model update)
         double t0 = now_s();
         ChunkState& s = cs[k];
-        if (s.gpu_rc == 0 && !s.imgs.empty()) s.gpu_rc = lepb200_encode_fetch(c->ctx2[k % 3], s.streams.data());
+        lepb200_ctx* ctx = c->ctx2[k % 3];
+        if (s.on_gpu && s.gpu_rc == 0) {
+            const int m = s.end - s.begin;
+            int nseg_total = 0;
+            int16_t* none[4] = {nullptr, nullptr, nullptr, nullptr};
+            s.imgs.resize(m); s.idx.resize(m);
+            parallel_for(m, c->nthreads, [&](int i) {
+                Jpeg& j = *s.js[i];
+                const lepb200_jpeg_scan& sc = s.scans[i];
+                if (sc.status == 0 && sc.nrows >= 2) {
+                    j.padbit = (int8_t)sc.padbit;
+                    j.rows.clear();
+                    for (int r = 0; r < sc.nrows; ++r) j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
+                    for (size_t r = 1; r < j.rows.size(); ++r)
+                        if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
+                    s.splits[i] = select_splits(j);
+                } else {
+                    j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
+                    j.error = "GPU Huffman decoder refused the scan";
+                    Handoff h0;                       // placeholder single segment so that the batch layout stays intact
+                    s.splits[i].selected.assign(1, h0);
+                }
+                status[s.begin + i] = j.status;
+                fill_image(s.imgs[i], j, none, s.splits[i].selected);
+                s.idx[i] = i;
+            });
+            for (int i = 0; i < m; ++i) nseg_total += s.imgs[i].nseg;
+            s.streams.resize(nseg_total);
+            s.seg_base.assign(s.imgs.size() + 1, 0);
+            for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+            mark("handoffs", k, t0);
+            double t1 = now_s();
+            s.gpu_rc = lepb200_encode_upload_resident(ctx, s.imgs.data(), m);
+            mark("prepass", k, t1);
+        } else if (s.gpu_rc == 0 && !s.imgs.empty()) {
+            s.gpu_rc = lepb200_encode_upload(ctx, s.imgs.data(), (int)s.imgs.size());
+        }
+        if (s.gpu_rc == 0 && !s.imgs.empty()) {
+            s.gpu_rc = lepb200_encode_launch_symbolise(ctx);
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_sync(ctx);
+            s.enc_done = s.gpu_rc == 0;
+        }
+        mark("symbolise", k, t0);
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_gpu += now_s() - t0;
+    };
+    auto rc = [&](int k) {                // kernel B (range coder chains), compaction, D2H of the streams
+        double t0 = now_s();
+        ChunkState& s = cs[k];
+        lepb200_ctx* ctx = c->ctx2[k % 3];
+        if (s.gpu_rc == 0 && s.enc_done) s.gpu_rc = lepb200_encode_launch_rangecode(ctx);
+        if (s.gpu_rc == 0 && s.enc_done) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
+        mark("rangecode+fetch", k, t0);
+        if (trace) fprintf(stderr, "[trace]   kernel A %.1f ms, A+B span %.1f ms\n", lepb200_last_symbolise_ms(ctx), lepb200_last_kernel_ms(ctx));
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -330,31 +359,32 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             });
         }
         s.js.clear(); s.planes.clear(); s.splits.clear();          // release per-chunk host state early
+        mark("back", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_back += now_s() - t0;
     };
 
-    // 4-stage lock-step pipeline; chunk k lives on context k % 3, so Huffman decode / kernel A of chunk k+1 overlap
-    // on the device with kernel B / compaction / D2H of chunk k (different streams)
-    for (int step = 0; step < nchunks + 3; ++step) {
-        std::thread tf, tg, tg2, tb;
-        if (step < nchunks) tf = std::thread(front, step);
-        if (step - 1 >= 0 && step - 1 < nchunks) tg = std::thread(gpu, step - 1);
-        if (step - 2 >= 0 && step - 2 < nchunks) tg2 = std::thread(gpu2, step - 2);
-        if (step - 3 >= 0 && step - 3 < nchunks) tb = std::thread(back, step - 3);
-        if (tf.joinable()) tf.join();
-        if (tg.joinable()) tg.join();
-        if (tg2.joinable()) tg2.join();
-        if (tb.joinable()) tb.join();
+    // 5-stage lock-step pipeline; chunk k lives on context k % 3 from its Huffman stage to its range-coder stage, so
+    // on the device the Huffman decode of chunk k+2, kernel A of chunk k+1 and kernel B / compaction / D2H of chunk k
+    // run side by side (three streams) while host threads parse chunk k+3 and write the containers of chunk k-1.
+    for (int step = 0; step < nchunks + 4; ++step) {
+        std::thread th[5];
+        auto in = [&](int k) { return k >= 0 && k < nchunks; };
+        if (in(step)) th[0] = std::thread(front, step);
+        if (in(step - 1)) th[1] = std::thread(huff, step - 1);
+        if (in(step - 2)) th[2] = std::thread(enc, step - 2);
+        if (in(step - 3)) th[3] = std::thread(rc, step - 3);
+        if (in(step - 4)) th[4] = std::thread(back, step - 4);
+        for (auto& t : th) if (t.joinable()) t.join();
     }
-    int rc = LEPB200_OK;
-    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
+    int ret = LEPB200_OK;
+    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
     for (int i = 0; i < n; ++i) {
         out[i].status = status[i];
         out[i].data = status[i] ? nullptr : c->outputs[i].data();
         out[i].len = status[i] ? 0 : c->outputs[i].size();
     }
-    return rc;
+    return ret;
 }
 
 // .lep files -> JPEG files (inverse of lepb200_compress_jpegs), same 3-stage chunk pipeline:

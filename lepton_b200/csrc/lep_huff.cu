@@ -86,8 +86,7 @@ __device__ __forceinline__ int huff_extend(HBits& b, int s) {      // DEVLI (jpg
     return n >= (1 << (s - 1)) ? n : n + 1 - (1 << s);
 }
 
-constexpr int HUFF_WARPS = 4;
-constexpr int HUFF_THREADS = HUFF_WARPS * 32;
+constexpr int HUFF_MAX_WARPS = 8;         // warps (= images) per CTA is a launch parameter (blockDim.x / 32)
 constexpr int HUFF_SMEM_TABLES = 8;      // tables staged in shared memory when the batch uses few distinct ones
 
 // ONE WARP PER IMAGE, window-parallel Huffman decode.  A single thread walking the bit stream pays ~500 cycles per
@@ -101,21 +100,24 @@ __device__ __forceinline__ uint32_t be_word(const uint32_t* __restrict__ w, uint
     return k < nwords ? __byte_perm(__ldg(w + k), 0, 0x0123) : 0u;
 }
 
-__global__ void __launch_bounds__(HUFF_THREADS)
+#ifndef LEPB200_HUFF_MINBLOCKS
+#define LEPB200_HUFF_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(HUFF_MAX_WARPS * 32, LEPB200_HUFF_MINBLOCKS)
 lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables, int ntables) {
     __shared__ HuffTableDev s_tab[HUFF_SMEM_TABLES];
     __shared__ uint8_t s_zz[64];
-    for (int i = threadIdx.x; i < 64; i += HUFF_THREADS) s_zz[i] = c_zigzag_to_aligned[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_zz[i] = c_zigzag_to_aligned[i];
     const bool use_smem = ntables <= HUFF_SMEM_TABLES;
     if (use_smem) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_tab);
         const int nw = ntables * (int)(sizeof(HuffTableDev) / 4);
-        for (int i = threadIdx.x; i < nw; i += HUFF_THREADS) dst[i] = src[i];
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
     const HuffTableDev* tb = use_smem ? s_tab : tables;
-    const int job = blockIdx.x * HUFF_WARPS + (threadIdx.x >> 5);
+    const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (job >= njobs) return;
     HuffJob& jb = jobs[job];
