@@ -118,7 +118,9 @@ int lepb200_sync(lepb200_ctx* ctx);
 typedef struct lepb200_hufftable { uint8_t bits[17]; uint8_t vals[256]; } lepb200_hufftable;   /* DHT form: counts per length (bits[1..16]) + symbols */
 typedef struct lepb200_huffrow { uint32_t bitpos; int16_t lastdc[3]; int16_t mcu_y; } lepb200_huffrow; /* Huffman state at an MCU-row start */
 typedef struct lepb200_jpeg_scan {
-    const uint8_t* entropy;          /* HOST: de-stuffed entropy-coded bytes of the (single) scan, RST markers removed */
+    const uint8_t* entropy;          /* HOST: de-stuffed entropy-coded bytes of the (single) scan, RST markers removed.
+                                      * NULL = placeholder: the image only gets its (zeroed) plane slot in the device arena and is
+                                      * filled from host planes by lepb200_encode_upload_resident (files the host had to decode) */
     uint32_t nbytes;
     int32_t ncmp, mcuh, mcuv, rsti;  /* components (frame order == scan order), MCUs per row / rows, restart interval */
     int32_t H[3], V[3];              /* sampling factors */
@@ -134,8 +136,12 @@ typedef struct lepb200_jpeg_scan {
 /* Uploads the entropy bytes, Huffman-decodes every scan into the context's device plane arena (laid out exactly as a
  * following lepb200_encode_upload_resident expects) and returns per-row states + status on the host. */
 int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans, int nimages);
+/* Pinned staging buffer of the context (>= bytes): scans whose `entropy` pointers lie inside it, 16-byte aligned and with
+ * >= 16 spare bytes behind each, are uploaded by lepb200_huffman_decode_to_device without the gather copy. */
+uint8_t* lepb200_huffman_stage_reserve(lepb200_ctx* ctx, size_t bytes);
 /* Like lepb200_encode_upload, but the planes are the ones just produced on the device by
- * lepb200_huffman_decode_to_device (images[i].planes is ignored; geometry must match scan i). */
+ * lepb200_huffman_decode_to_device (geometry must match scan i).  images[i].planes == NULL: use the resident planes;
+ * non-NULL (placeholder scans): copy these host planes into the image's slot first. */
 int lepb200_encode_upload_resident(lepb200_ctx* ctx, const lepb200_image* images, int nimages);
 
 /* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */

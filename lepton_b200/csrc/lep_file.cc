@@ -25,7 +25,8 @@ struct lepb200_codec {
     lepb200_ctx* ctx = nullptr;     // == ctx2[0]
     lepb200_ctx* ctx2[3] = {nullptr, nullptr, nullptr};   // rotating contexts: chunk k on ctx2[k % 3]
     int nthreads = 1;
-    int chunk_images = 1024;
+    int chunk_images = 4096;
+    size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk (device memory budget: two contexts in flight)
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
     void* arena[3] = {nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
     size_t arena_cap[3] = {0, 0, 0};
@@ -133,28 +134,32 @@ void lepb200_codec_last_timing(const lepb200_codec* c, double* front_s, double* 
 
 // JPEG files -> .lep files.  out[i].data points into codec-owned memory, valid until the next call.
 //
-// The batch is processed as a 3-stage software pipeline over chunks of `chunk_images` files:
-//   front (host threads: parse, de-stuff, Huffman decode into a pinned arena, split selection)
-//   gpu   (H2D planes, token pre-pass, kernel A, kernel B, compaction, D2H streams)        -- alternating contexts
-//   back  (host threads: mux + container)
-// so that chunk k+1 is being Huffman-decoded while chunk k is on the GPU and chunk k-1 is being written out.
+// The batch is cut into LARGE chunks (up to `chunk_images` files and `plane_cap` bytes of coefficient planes): the
+// Huffman-decode and range-coder kernels are latency-bound chains whose duration hardly depends on how many images they
+// cover, so a launch should cover as many as device memory allows.  Chunks run through a 3-stage lock-step pipeline on
+// two alternating contexts:
+//   front (host threads) parse + de-stuff every file straight into the context's pinned staging buffer; files the GPU
+//                        Huffman decoder cannot take (progressive, truncated, several scans) are Huffman-decoded here
+//                        into a pinned plane arena instead
+//   gpu                  H2D -> Huffman kernel -> thread-segment selection (host) -> token pre-pass -> kernel A ->
+//                        kernel B -> compaction -> D2H
+//   back  (host threads) mux + container of every file
 namespace {
 
 struct ChunkState {
     int begin = 0, end = 0;
-    std::vector<std::unique_ptr<Jpeg>> js;
-    std::vector<std::array<int16_t*, 4>> planes;
+    std::vector<std::unique_ptr<Jpeg>> js;              // per file of the chunk
+    std::vector<std::array<int16_t*, 4>> planes;        // host planes of host-decoded files (else null)
     std::vector<Splits> splits;
-    std::vector<lepb200_image> imgs;
-    std::vector<int> idx;                 // image index (relative to begin) of imgs[k]
+    std::vector<uint8_t> host_decoded;                  // 1: planes came from the host Huffman decoder
+    std::vector<lepb200_image> imgs;                    // batch order == idx order
+    std::vector<int> idx;                               // file index (relative to begin) of imgs[q]
     std::vector<int> seg_base;
     std::vector<lepb200_stream> streams;
-    int gpu_rc = 0;
-    bool enc_done = false;                // kernel A finished for this chunk
-    // GPU Huffman path
-    bool on_gpu = false;
-    std::vector<lepb200_jpeg_scan> scans;
+    std::vector<lepb200_jpeg_scan> scans;               // per batch image
     std::vector<std::vector<lepb200_huffrow>> rowbuf;
+    int gpu_rc = 0;
+    bool any_gpu_huffman = false;
 };
 
 }  // namespace
@@ -164,13 +169,26 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     const bool trace = getenv("LEPB200_TRACE") != nullptr;           // stage timeline on stderr (diagnostics)
     const double t_origin = now_s();
     auto mark = [&](const char* what, int k, double t_begin) {
-        if (trace) fprintf(stderr, "[trace] %-14s chunk %d  %8.1f -> %8.1f ms\n", what, k, (t_begin - t_origin) * 1e3, (now_s() - t_origin) * 1e3);
+        if (trace) fprintf(stderr, "[trace] %-16s chunk %d  %8.1f -> %8.1f ms\n", what, k, (t_begin - t_origin) * 1e3, (now_s() - t_origin) * 1e3);
     };
     c->err.clear();
     c->t_front = c->t_gpu = c->t_back = 0;
-    const int chunk = std::max(1, c->chunk_images);
-    const int nchunks = (n + chunk - 1) / chunk;
-    c->outputs.assign(n, std::vector<uint8_t>());
+    // ---- chunk boundaries
+    std::vector<size_t> need(n);
+    parallel_for(n, c->nthreads, [&](int i) { need[i] = peek_plane_bytes(jpegs[i].data, jpegs[i].len); });
+    std::vector<std::pair<int, int>> ranges;
+    {
+        const int chunk = std::max(1, c->chunk_images);
+        int b = 0;
+        size_t acc = 0;
+        for (int i = 0; i < n; ++i) {
+            if (i > b && (i - b >= chunk || acc + need[i] > c->plane_cap)) { ranges.emplace_back(b, i); b = i; acc = 0; }
+            acc += need[i];
+        }
+        ranges.emplace_back(b, n);
+    }
+    const int nchunks = (int)ranges.size();
+    c->outputs.resize(n);
     std::vector<int> status(n, 0);
     std::vector<ChunkState> cs(nchunks);
     std::mutex tmu;
@@ -178,175 +196,158 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     auto front = [&](int k) {
         double t0 = now_s();
         ChunkState& s = cs[k];
-        s.begin = k * chunk; s.end = std::min(n, s.begin + chunk);
+        s.begin = ranges[k].first; s.end = ranges[k].second;
         const int m = s.end - s.begin;
-        s.js.resize(m); s.planes.resize(m); s.splits.resize(m);
-        std::vector<size_t> base(m, 0), need(m, 0);
-        size_t total = 0;
+        lepb200_ctx* ctx = c->ctx2[k % 2];
+        s.js.resize(m); s.planes.resize(m); s.splits.resize(m); s.host_decoded.assign(m, 0);
+        // staging layout for the de-stuffed scans (a scan is never longer than its file) and arena layout for planes
+        // of files that turn out to need the host decoder
+        std::vector<size_t> soff(m + 1, 0), poff(m + 1, 0);
         for (int i = 0; i < m; ++i) {
-            need[i] = peek_plane_bytes(jpegs[s.begin + i].data, jpegs[s.begin + i].len);
-            base[i] = total;
-            total += need[i];
+            soff[i + 1] = soff[i] + ((jpegs[s.begin + i].len + 32 + 15) & ~size_t(15));
+            poff[i + 1] = poff[i] + need[s.begin + i];
         }
-        if (c->gpu_huffman) {
-            // GPU Huffman path: the host only parses markers and de-stuffs; eligible if EVERY file of the chunk is a
-            // complete single-scan baseline JPEG (otherwise the whole chunk takes the host Huffman path below)
-            s.scans.assign(m, lepb200_jpeg_scan());
-            s.rowbuf.resize(m);
-            std::atomic<int> ineligible(0);
-            parallel_for(m, c->nthreads, [&](int i) {
-                s.js[i].reset(new Jpeg());
-                Jpeg& j = *s.js[i];
-                const lepb200_buffer& in = jpegs[s.begin + i];
-                GpuScanSetup gs;
-                if (!parse_jpeg(in.data, in.len, j) || !gpu_scan_setup(j, gs)) { ineligible++; return; }
-                lepb200_jpeg_scan& sc = s.scans[i];
-                memset(&sc, 0, sizeof(sc));
-                sc.entropy = j.huff.data(); sc.nbytes = (uint32_t)j.huff.size();
-                sc.ncmp = j.ncmp; sc.mcuh = j.mcuh; sc.mcuv = j.mcuv; sc.rsti = gs.rsti;
-                for (int q = 0; q < j.ncmp; ++q) {
-                    sc.H[q] = j.cmp[q].H; sc.V[q] = j.cmp[q].V; sc.nch[q] = j.cmp[q].nch; sc.ncv[q] = j.cmp[q].ncv;
-                    memcpy(sc.dc[q].bits, gs.dc_bits[q], 17); memcpy(sc.dc[q].vals, gs.dc_vals[q], 256);
-                    memcpy(sc.ac[q].bits, gs.ac_bits[q], 17); memcpy(sc.ac[q].vals, gs.ac_vals[q], 256);
-                }
-                s.rowbuf[i].resize((size_t)j.mcuv + 1);
-                sc.rows = s.rowbuf[i].data();
-            });
-            if (ineligible.load() == 0) {
-                s.on_gpu = true;
-                mark("front", k, t0);
-                std::lock_guard<std::mutex> g(tmu);
-                c->t_front += now_s() - t0;
-                return;
-            }
-            for (auto& u : s.js) u.reset();      // fall through to the host Huffman path for this chunk
-            s.scans.clear(); s.rowbuf.clear();
+        uint8_t* stage = c->gpu_huffman ? lepb200_huffman_stage_reserve(ctx, soff[m]) : nullptr;
+        if (c->gpu_huffman && !stage) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+        const int slot = k % 2;
+        uint8_t* arena = nullptr;
+        if (!c->gpu_huffman) {                       // every file takes the host decoder: one arena for the chunk
+            if (!reserve_arena(c, slot, poff[m] + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+            arena = static_cast<uint8_t*>(c->arena[slot]);
         }
-        const int slot = k % 3;
-        if (!reserve_arena(c, slot, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
-        uint8_t* arena = static_cast<uint8_t*>(c->arena[slot]);
+        std::vector<uint8_t> eligible(m, 0);
+        std::vector<GpuScanSetup> setups(c->gpu_huffman ? m : 0);
+        // pass 1: parse + de-stuff (into the staging buffer on the GPU path)
         parallel_for(m, c->nthreads, [&](int i) {
-            // the de-stuffed entropy buffer is the only large per-image allocation: recycle it per thread
-            static thread_local std::vector<uint8_t> huff_scratch;
-            static thread_local std::vector<std::pair<uint32_t, uint32_t>> offs_scratch;
             s.js[i].reset(new Jpeg());
             Jpeg& j = *s.js[i];
-            huff_scratch.clear(); offs_scratch.clear();
-            j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);
             const lepb200_buffer& in = jpegs[s.begin + i];
-            bool ok = parse_jpeg(in.data, in.len, j);
-            if (ok) {
-                size_t want = 0;
-                for (int q = 0; q < j.ncmp; ++q) want += (plane_bytes(j, q) + 255) & ~size_t(255);
-                if (want != need[i]) { j.status = NOT_HANDLED; j.error = "plane size peek mismatch"; ok = false; }
-            }
-            if (ok) {
-                uint8_t* p = arena + base[i];
-                for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
-                for (int q = 0; q < j.ncmp; ++q) {
-                    s.planes[i][q] = reinterpret_cast<int16_t*>(p);
-                    size_t pb = plane_bytes(j, q);
-                    memset(p, 0, pb);
-                    p += (pb + 255) & ~size_t(255);
-                }
-                if (decode_scans(j, s.planes[i].data())) s.splits[i] = select_splits(j);
-            }
-            j.huff.swap(huff_scratch); j.offs.swap(offs_scratch);     // keep the capacity with the thread
+            if (stage) j.huff.attach(stage + soff[i], soff[i + 1] - soff[i] - 16);
+            if (!parse_jpeg(in.data, in.len, j)) return;
+            if (stage && gpu_scan_setup(j, setups[i])) eligible[i] = 1;
         });
-        int nseg_total = 0;
+        // host-decoded files of a GPU chunk share one arena sized for just them
+        if (c->gpu_huffman) {
+            size_t tot = 0;
+            std::vector<size_t> off(m, 0);
+            for (int i = 0; i < m; ++i) if (!eligible[i] && s.js[i]->status == 0) { off[i] = tot; tot += need[s.begin + i]; }
+            if (tot) {
+                if (!reserve_arena(c, slot, tot + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+                arena = static_cast<uint8_t*>(c->arena[slot]);
+            }
+            for (int i = 0; i < m; ++i) poff[i] = off[i];
+        }
+        // pass 2: host Huffman decode where needed
+        parallel_for(m, c->nthreads, [&](int i) {
+            Jpeg& j = *s.js[i];
+            for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
+            if (j.status || eligible[i]) return;
+            size_t want = 0;
+            for (int q = 0; q < j.ncmp; ++q) want += (plane_bytes(j, q) + 255) & ~size_t(255);
+            if (want != need[s.begin + i]) { j.status = NOT_HANDLED; j.error = "plane size peek mismatch"; return; }
+            uint8_t* p = arena + poff[i];
+            for (int q = 0; q < j.ncmp; ++q) {
+                s.planes[i][q] = reinterpret_cast<int16_t*>(p);
+                const size_t pb = plane_bytes(j, q);
+                memset(p, 0, pb);
+                p += (pb + 255) & ~size_t(255);
+            }
+            if (decode_scans(j, s.planes[i].data())) { s.splits[i] = select_splits(j); s.host_decoded[i] = 1; }
+        });
+        // batch = every file that is still fine, in file order
         for (int i = 0; i < m; ++i) {
             status[s.begin + i] = s.js[i]->status;
-            if (s.js[i]->status) continue;
-            lepb200_image im;
-            fill_image(im, *s.js[i], s.planes[i].data(), s.splits[i].selected);
-            s.imgs.push_back(im);
-            s.idx.push_back(i);
-            nseg_total += im.nseg;
+            if (s.js[i]->status == 0) s.idx.push_back(i);
         }
-        s.streams.resize(nseg_total);
-        s.seg_base.assign(s.imgs.size() + 1, 0);
-        for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+        const int nb = (int)s.idx.size();
+        s.scans.assign(nb, lepb200_jpeg_scan());
+        s.rowbuf.resize(nb);
+        for (int q = 0; q < nb; ++q) {
+            const int i = s.idx[q];
+            const Jpeg& j = *s.js[i];
+            lepb200_jpeg_scan& sc = s.scans[q];
+            memset(&sc, 0, sizeof(sc));
+            sc.ncmp = j.ncmp; sc.mcuh = j.mcuh; sc.mcuv = j.mcuv;
+            for (int t = 0; t < j.ncmp && t < 3; ++t) { sc.H[t] = j.cmp[t].H; sc.V[t] = j.cmp[t].V; sc.nch[t] = j.cmp[t].nch; sc.ncv[t] = j.cmp[t].ncv; }
+            if (!eligible[i]) continue;              // placeholder: plane slot only
+            const GpuScanSetup& gs = setups[i];
+            sc.entropy = j.huff.data(); sc.nbytes = (uint32_t)j.huff.size(); sc.rsti = gs.rsti;
+            for (int t = 0; t < j.ncmp; ++t) {
+                memcpy(sc.dc[t].bits, gs.dc_bits[t], 17); memcpy(sc.dc[t].vals, gs.dc_vals[t], 256);
+                memcpy(sc.ac[t].bits, gs.ac_bits[t], 17); memcpy(sc.ac[t].vals, gs.ac_vals[t], 256);
+            }
+            s.rowbuf[q].resize((size_t)j.mcuv + 1);
+            sc.rows = s.rowbuf[q].data();
+            s.any_gpu_huffman = true;
+        }
+        mark("front", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_front += now_s() - t0;
     };
-    auto huff = [&](int k) {              // GPU Huffman decode of the chunk (H2D of the entropy-coded bytes, one kernel)
+
+    auto gpu = [&](int k) {
         double t0 = now_s();
         ChunkState& s = cs[k];
-        if (s.on_gpu && s.gpu_rc == 0) {
-            lepb200_ctx* ctx = c->ctx2[k % 3];
-            s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), s.end - s.begin);
-            c->t_huff_ms = lepb200_last_huffman_ms(ctx);
-            mark("huffman", k, t0);
-            if (trace) fprintf(stderr, "[trace]   huffman kernel %.1f ms\n", c->t_huff_ms);
-        }
-        std::lock_guard<std::mutex> g(tmu);
-        c->t_gpu += now_s() - t0;
-    };
-    auto enc = [&](int k) {               // thread-segment selection, token pre-pass, kernel A (symbolise + model update)
-        double t0 = now_s();
-        ChunkState& s = cs[k];
-        lepb200_ctx* ctx = c->ctx2[k % 3];
-        if (s.on_gpu && s.gpu_rc == 0) {
-            const int m = s.end - s.begin;
-            int nseg_total = 0;
-            int16_t* none[4] = {nullptr, nullptr, nullptr, nullptr};
-            s.imgs.resize(m); s.idx.resize(m);
-            parallel_for(m, c->nthreads, [&](int i) {
-                Jpeg& j = *s.js[i];
-                const lepb200_jpeg_scan& sc = s.scans[i];
-                if (sc.status == 0 && sc.nrows >= 2) {
-                    j.padbit = (int8_t)sc.padbit;
-                    j.rows.clear();
-                    for (int r = 0; r < sc.nrows; ++r) j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
-                    for (size_t r = 1; r < j.rows.size(); ++r)
-                        if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
-                    s.splits[i] = select_splits(j);
-                } else {
-                    j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
-                    j.error = "GPU Huffman decoder refused the scan";
-                    Handoff h0;                       // placeholder single segment so that the batch layout stays intact
-                    s.splits[i].selected.assign(1, h0);
-                }
-                status[s.begin + i] = j.status;
-                fill_image(s.imgs[i], j, none, s.splits[i].selected);
-                s.idx[i] = i;
-            });
-            for (int i = 0; i < m; ++i) nseg_total += s.imgs[i].nseg;
-            s.streams.resize(nseg_total);
-            s.seg_base.assign(s.imgs.size() + 1, 0);
-            for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
-            mark("handoffs", k, t0);
+        lepb200_ctx* ctx = c->ctx2[k % 2];
+        const int nb = (int)s.idx.size();
+        if (s.gpu_rc == 0 && nb > 0) {
+            if (s.any_gpu_huffman) {
+                s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), nb);
+                c->t_huff_ms = lepb200_last_huffman_ms(ctx);
+                mark("huffman", k, t0);
+                if (trace) fprintf(stderr, "[trace]   huffman kernel %.1f ms\n", c->t_huff_ms);
+            }
             double t1 = now_s();
-            s.gpu_rc = lepb200_encode_upload_resident(ctx, s.imgs.data(), m);
-            mark("prepass", k, t1);
-        } else if (s.gpu_rc == 0 && !s.imgs.empty()) {
-            s.gpu_rc = lepb200_encode_upload(ctx, s.imgs.data(), (int)s.imgs.size());
+            s.imgs.resize(nb);
+            if (s.gpu_rc == 0) {
+                // thread-segment selection from the Huffman states at the MCU-row starts (write_ujpg, jpgcoder.cc:3860-3934)
+                parallel_for(nb, c->nthreads, [&](int q) {
+                    const int i = s.idx[q];
+                    Jpeg& j = *s.js[i];
+                    const lepb200_jpeg_scan& sc = s.scans[q];
+                    if (!s.host_decoded[i]) {
+                        if (sc.status == 0 && sc.nrows >= 2) {
+                            j.padbit = (int8_t)sc.padbit;
+                            j.rows.clear();
+                            for (int r = 0; r < sc.nrows; ++r) j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
+                            for (size_t r = 1; r < j.rows.size(); ++r)
+                                if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
+                            for (int t = 0; t < j.ncmp; ++t) { j.trunc_bcv[t] = j.cmp[t].bcv; j.trunc_bc[t] = j.cmp[t].bc; }
+                            s.splits[i] = select_splits(j);
+                        } else {
+                            j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
+                            j.error = "GPU Huffman decoder refused the scan";
+                            Handoff h0;                       // placeholder single segment so that the batch layout stays intact
+                            s.splits[i].selected.assign(1, h0);
+                        }
+                        status[s.begin + i] = j.status;
+                    }
+                    fill_image(s.imgs[q], j, s.planes[i].data(), s.splits[i].selected);
+                });
+                int nseg_total = 0;
+                s.seg_base.assign(nb + 1, 0);
+                for (int q = 0; q < nb; ++q) { s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg; nseg_total += s.imgs[q].nseg; }
+                s.streams.resize(nseg_total);
+                mark("segments", k, t1);
+                t1 = now_s();
+                s.gpu_rc = s.any_gpu_huffman ? lepb200_encode_upload_resident(ctx, s.imgs.data(), nb) : lepb200_encode_upload(ctx, s.imgs.data(), nb);
+                mark("upload+prepass", k, t1);
+                t1 = now_s();
+                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(ctx);
+                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
+                mark("encode+fetch", k, t1);
+                if (trace) fprintf(stderr, "[trace]   kernel A %.1f ms, A+B %.1f ms\n", lepb200_last_symbolise_ms(ctx), lepb200_last_kernel_ms(ctx));
+            }
         }
-        if (s.gpu_rc == 0 && !s.imgs.empty()) {
-            s.gpu_rc = lepb200_encode_launch_symbolise(ctx);
-            if (s.gpu_rc == 0) s.gpu_rc = lepb200_sync(ctx);
-            s.enc_done = s.gpu_rc == 0;
-        }
-        mark("symbolise", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
-    auto rc = [&](int k) {                // kernel B (range coder chains), compaction, D2H of the streams
-        double t0 = now_s();
-        ChunkState& s = cs[k];
-        lepb200_ctx* ctx = c->ctx2[k % 3];
-        if (s.gpu_rc == 0 && s.enc_done) s.gpu_rc = lepb200_encode_launch_rangecode(ctx);
-        if (s.gpu_rc == 0 && s.enc_done) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
-        mark("rangecode+fetch", k, t0);
-        if (trace) fprintf(stderr, "[trace]   kernel A %.1f ms, A+B span %.1f ms\n", lepb200_last_symbolise_ms(ctx), lepb200_last_kernel_ms(ctx));
-        std::lock_guard<std::mutex> g(tmu);
-        c->t_gpu += now_s() - t0;
-    };
+
     auto back = [&](int k) {
         double t0 = now_s();
         ChunkState& s = cs[k];
         if (s.gpu_rc == 0) {
-            parallel_for((int)s.imgs.size(), std::max(1, c->nthreads / 4), [&](int q) {
+            parallel_for((int)s.idx.size(), c->nthreads, [&](int q) {
                 const int i = s.begin + s.idx[q];
                 if (status[i]) return;
                 std::vector<std::pair<const uint8_t*, size_t>> ss;
@@ -355,31 +356,30 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                     ss.emplace_back(s.streams[t].data, (size_t)s.streams[t].len);
                 }
                 std::string err;
+                c->outputs[i].clear();
                 if (!write_lep(*s.js[s.idx[q]], s.splits[s.idx[q]], ss, c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
             });
         }
-        s.js.clear(); s.planes.clear(); s.splits.clear();          // release per-chunk host state early
+        parallel_for((int)s.js.size(), c->nthreads, [&](int i) { s.js[i].reset(); });     // release per-chunk host state early
+        s.js.clear(); s.planes.clear(); s.splits.clear();
         mark("back", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_back += now_s() - t0;
     };
 
-    // 5-stage lock-step pipeline; chunk k lives on context k % 3 from its Huffman stage to its range-coder stage, so
-    // on the device the Huffman decode of chunk k+2, kernel A of chunk k+1 and kernel B / compaction / D2H of chunk k
-    // run side by side (three streams) while host threads parse chunk k+3 and write the containers of chunk k-1.
-    for (int step = 0; step < nchunks + 4; ++step) {
-        std::thread th[5];
+    // 3-stage lock-step pipeline, chunk k on context k % 2
+    for (int step = 0; step < nchunks + 2; ++step) {
+        std::thread th[3];
         auto in = [&](int k) { return k >= 0 && k < nchunks; };
         if (in(step)) th[0] = std::thread(front, step);
-        if (in(step - 1)) th[1] = std::thread(huff, step - 1);
-        if (in(step - 2)) th[2] = std::thread(enc, step - 2);
-        if (in(step - 3)) th[3] = std::thread(rc, step - 3);
-        if (in(step - 4)) th[4] = std::thread(back, step - 4);
+        if (in(step - 1)) th[1] = std::thread(gpu, step - 1);
+        if (in(step - 2)) th[2] = std::thread(back, step - 2);
         for (auto& t : th) if (t.joinable()) t.join();
     }
     int ret = LEPB200_OK;
-    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
+    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 2]); }
     for (int i = 0; i < n; ++i) {
+        if (status[i]) c->outputs[i].clear();
         out[i].status = status[i];
         out[i].data = status[i] ? nullptr : c->outputs[i].data();
         out[i].len = status[i] ? 0 : c->outputs[i].size();

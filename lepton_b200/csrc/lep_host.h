@@ -9,6 +9,7 @@
 // /root/reference/src/lepton/jpgcoder.cc unless stated otherwise.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <utility>
 #include <vector>
@@ -59,10 +60,35 @@ struct HuffTable {
     bool build();
 };
 
+// De-stuffed entropy-coded bytes of all scans.  Owns its storage by default; attach() makes it write into caller-provided
+// memory instead (the file pipeline points it at the pinned staging buffer the GPU Huffman decoder uploads from, so the
+// bytes are written exactly once).
+struct HuffBuf {
+    std::vector<uint8_t> own;
+    uint8_t* ext = nullptr;
+    size_t ext_cap = 0, ext_n = 0;
+    bool overflow = false;
+    void attach(uint8_t* p, size_t cap) { ext = p; ext_cap = cap; ext_n = 0; overflow = false; }
+    const uint8_t* data() const { return ext ? ext : own.data(); }
+    size_t size() const { return ext ? ext_n : own.size(); }
+    bool empty() const { return size() == 0; }
+    void reserve(size_t n) { if (!ext) own.reserve(n); }
+    void clear() { if (ext) ext_n = 0; else own.clear(); }
+    void push_back(uint8_t b) {
+        if (!ext) { own.push_back(b); return; }
+        if (ext_n < ext_cap) ext[ext_n++] = b; else overflow = true;
+    }
+    void append(const uint8_t* p, size_t n) {
+        if (!ext) { own.insert(own.end(), p, p + n); return; }
+        if (ext_n + n <= ext_cap) { memcpy(ext + ext_n, p, n); ext_n += n; } else overflow = true;
+    }
+    void swap(std::vector<uint8_t>& v) { own.swap(v); }     // storage recycling of the owned mode
+};
+
 struct Jpeg {
     // ---- read_jpeg products (jpgcoder.cc:2270-2466)
     std::vector<uint8_t> hdr;        // every marker segment after SOI, in file order ("hdrdata")
-    std::vector<uint8_t> huff;       // entropy-coded bytes of all scans, de-stuffed, RST markers removed ("huffdata")
+    HuffBuf huff;                    // entropy-coded bytes of all scans, de-stuffed, RST markers removed ("huffdata")
     std::vector<uint8_t> grb;        // bytes from EOI on ("grbgdata"); empty when exactly FF D9
     std::vector<std::pair<uint32_t, uint32_t>> offs;   // (position in huff, position in file) ("huff_input_offsets")
     std::vector<uint32_t> rst_cnt;   // restart markers seen per scan

@@ -27,6 +27,8 @@ struct HuffRow {             // state at the start of an MCU row
     int16_t mcu_y;
 };
 
+constexpr int HUFF_JOB_SKIP = -1;        // HuffJob::status of a placeholder (plane slot only, nothing to decode)
+
 struct HuffJob {
     unsigned long long huff;         // device address of the de-stuffed entropy bytes (4-byte aligned, zero padded by 8)
     unsigned long long plane[3];     // coefficient planes (pre-zeroed)

@@ -89,7 +89,7 @@ bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j) {
                     const uint8_t* run = data + pos - 1;
                     const uint8_t* ff = (const uint8_t*)memchr(run, 0xFF, n - (pos - 1));
                     size_t len = ff ? (size_t)(ff - run) : n - (pos - 1);
-                    j.huff.insert(j.huff.end(), run, run + len);
+                    j.huff.append(run, len);
                     pos = (pos - 1) + len;
                     if (!ff) { j.early_eof = true; eof_called = true; tmp = run[len - 1]; }
                     else { tmp = 0xFF; pos++; }
@@ -136,6 +136,7 @@ bool parse_jpeg(const uint8_t* data, size_t n, Jpeg& j) {
     }
     if (!eof_called || j.hdr.empty()) return fail(j, UNSUPPORTED_JPEG, "unexpected end of data encountered in header");
     if (j.huff.empty()) return fail(j, UNSUPPORTED_JPEG, "unexpected end of data encountered in huffman");
+    if (j.huff.overflow) return fail(j, ASSERTION_FAILURE, "entropy staging buffer too small");
     // garbage: the last two bytes read, then the rest of the file (jpgcoder.cc:2429-2447)
     {
         uint8_t g0 = pos >= 2 ? data[pos - 2] : 0, g1 = pos >= 1 ? data[pos - 1] : 0;
