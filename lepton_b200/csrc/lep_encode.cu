@@ -23,7 +23,7 @@
 namespace lepb200 {
 
 constexpr int ENC_WARPS_PER_CTA = 4;
-constexpr int QCAP = 1472;   // worst case decisions per block: 6 + 49*22 + 2*(3 + 7*22) + 22 = 1420
+constexpr int QCAP = 2944;   // two blocks in flight; worst case decisions per block: 6 + 49*22 + 2*(3 + 7*22) + 22 = 1420
 
 // Decision items.  Symbolisation does not write the binary decisions one by one: every coded coefficient leaves ONE
 // 16-byte descriptor (exponent / sign / residual / threshold branch bases, magnitude, sign, first queue position) and
@@ -32,16 +32,16 @@ constexpr int QCAP = 1472;   // worst case decisions per block: 6 + 49*22 + 2*(3
 //                w2 = residual base | first position << 20       w3 = threshold base | min_threshold << 20 (15 = none)
 //   single decision ("raw"): w0 = 1 << 31, w1 = (bit << 31) | branch
 // Item ids are fixed: 0..5 7x7 count bits, 6..54 7x7 coefficients (zig-zag), 55..57 / 65..67 edge counts, 58..64 /
-// 68..74 edge coefficients, 75..96 DC decisions.
-constexpr int N_ITEMS = 100;
+// 68..74 edge coefficients, 75 the DC.
+constexpr int N_ITEMS = 76;
 constexpr int IT_NZ = 0, IT_77 = 6, IT_HCNT = 55, IT_H = 58, IT_VCNT = 65, IT_V = 68, IT_DC = 75;
 
 struct EncWarpSmem {
-    uint4 desc[N_ITEMS];
-    uint8_t mark[QCAP];       // item id + 1 at the first queue position of each item, 0 elsewhere (kept zero between blocks)
-    int16_t rast[3][64];      // raster-order copies: [0]=cur/left ping, [1]=left/cur pong, [2]=above
-    int32_t tmp[64];          // IDCT intermediate
-    int16_t pix[64];          // IDCT output (pixels sans DC)
+    uint4 desc[2 * N_ITEMS];  // items of block A (ids 0..99) and block B (100..199) of the pair in flight
+    uint8_t mark[QCAP];       // item id + 1 at the first queue position of each item, 0 elsewhere (kept zero between flushes)
+    int16_t rast[5][64];      // raster-order copies: three rotating buffers (A, B, left neighbour of A) + above A, above B
+    int32_t tmp[2][64];       // IDCT intermediates of A and B
+    int16_t pix[2][64];       // IDCT outputs (pixels sans DC) of A and B
 };
 
 struct EncShared {
@@ -52,7 +52,7 @@ struct EncShared {
 };
 
 // ---- queue flush: expansion of the items + batched model update ---------------------------------------
-__device__ __forceinline__ uint32_t expand_item(const uint4 d, int pos) {
+__device__ __forceinline__ uint32_t expand_item(const uint4 d, int pos) {      // pos: position relative to the item's block
     if (d.x >> 31) return d.y;
     const int len = (int)((d.x >> 20) & 15u), nexp = min(len + 1, 11);
     const int k = pos - (int)(d.z >> 20);
@@ -66,7 +66,8 @@ __device__ __forceinline__ uint32_t expand_item(const uint4 d, int pos) {
     return addr | (bit << 31);
 }
 
-__device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, uint16_t* __restrict__ model,
+// n queued positions; the items of block B (ids >= N_ITEMS) are positioned relative to base_b
+__device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, int base_b, uint16_t* __restrict__ model,
                                             const uint32_t* __restrict__ s_rcp, uint16_t* __restrict__ tokens, uint32_t& ntok,
                                             uint32_t tok_cap, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
@@ -81,7 +82,7 @@ __device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, uint16_t* __
         const uint32_t from_lane = __shfl_sync(FULL, mk, starts ? 31 - __clz(starts) : 0);
         const uint32_t item = starts ? from_lane : carry;
         carry = __shfl_sync(FULL, item, 31);
-        const uint32_t e = active ? expand_item(ws.desc[item - 1], i) : 0u;
+        const uint32_t e = active ? expand_item(ws.desc[item - 1], item > (uint32_t)N_ITEMS ? i - base_b : i) : 0u;
         const uint32_t addr = e & 0xfffffu, bit = e >> 31;
         const uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
         const uint32_t earlier = peers & lt_mask;
@@ -118,6 +119,74 @@ __device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, uint16_t* __
 // ---- helpers for symbolisation ------------------------------------------------------------------------
 // number of queue entries for one coefficient coded with (exponent unary, sign, len-1 residual bits)
 __device__ __forceinline__ int coef_entries(int len) { return len == 0 ? 1 : min(len + 1, 11) + len; }
+
+// ---- two blocks per warp: lanes 0..15 serve block A (x), lanes 16..31 block B (x + 1) in the lane-sparse sections ----
+// Lane-parallel 8x8 IDCT (DC forced to zero) of A on lanes 0..7 and of B on lanes 8..15.
+__device__ __forceinline__ void warp_idct_pair(const int16_t* rA, const int16_t* rB, const uint16_t* __restrict__ q, int32_t (*tmp)[64],
+                                               int16_t (*pix)[64], int lane, bool has_b) {
+    const int b = (lane >> 3) & 1, r = lane & 7;
+    const bool act = lane < (has_b ? 16 : 8);
+    if (act) {
+        const int16_t* rast = b ? rB : rA;
+        int32_t in[8], out[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) in[k] = (int32_t)rast[r * 8 + k] * (int32_t)q[r * 8 + k];
+        if (r == 0) in[0] = 0;
+        idct_row(in, out);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tmp[b][r * 8 + k] = out[k];
+    }
+    __syncwarp();
+    if (act) {
+        int32_t in[8], out[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) in[k] = tmp[b][k * 8 + r];
+        idct_col(in, out);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pix[b][k * 8 + r] = (int16_t)out[k];
+    }
+    __syncwarp();
+}
+
+// adv_predict_dc_pix for both halves at once (see warp_predict_dc): within a half, lanes 0..7 hold the left estimate,
+// lanes 8..15 the above one.  pix / has_left are per half; the result is uniform within a half.
+__device__ __forceinline__ DcPred warp_predict_dc_pair(const int16_t* pix, int left_v, int above_h, bool has_left, bool has_above, int q0, int lane) {
+    int est = 0;
+    const int i = lane & 7, hb = lane & 16;
+    if ((lane & 8) == 0) {
+        if (has_left) {
+            int16_t p0 = pix[i * 8], p1 = pix[i * 8 + 1];
+            int16_t delta = (int16_t)(p0 - p1);
+            est = (int16_t)((int16_t)((int16_t)left_v - half_rz16(delta)) - (int16_t)(p0 + 1024));
+        }
+    } else {
+        if (has_above) {
+            int16_t p0 = pix[i], p1 = pix[8 + i];
+            int16_t delta = (int16_t)(p0 - p1);
+            est = (int16_t)((int16_t)((int16_t)above_h - half_rz16(delta)) - (int16_t)(p0 + 1024));
+        }
+    }
+    int s = grp8_sum(est), mn = grp8_min(est), mx = grp8_max(est);
+    int sl = __shfl_sync(FULL, s, hb), sa = __shfl_sync(FULL, s, hb + 8);
+    int mnl = __shfl_sync(FULL, mn, hb), mna = __shfl_sync(FULL, mn, hb + 8);
+    int mxl = __shfl_sync(FULL, mx, hb), mxa = __shfl_sync(FULL, mx, hb + 8);
+    DcPred r; r.pred = 0; r.unc = 0; r.unc2 = 0;
+    int avgmed = 0;
+    if (has_left || has_above) {
+        int a0, a1, mn_all, mx_all;
+        if (has_left && has_above) { a0 = sl; a1 = sa; mn_all = min(mnl, mna); mx_all = max(mxl, mxa); }
+        else if (has_left) { a0 = a1 = sl; mn_all = mnl; mx_all = mxl; }
+        else { a0 = a1 = sa; mn_all = mna; mx_all = mxa; }
+        avgmed = (a0 + a1) >> 1;
+        r.unc = (mx_all - mn_all) >> 3;
+        a0 -= avgmed; a1 -= avgmed;
+        int far_afield = a1;
+        if (iabs(a0) < iabs(a1)) far_afield = a0;
+        r.unc2 = far_afield >> 3;
+    }
+    r.pred = (div_trunc_small(avgmed, q0) + 4) >> 3;            // |avgmed| < 2^20
+    return r;
+}
 
 // ---- the kernel ---------------------------------------------------------------------------------------
 #ifndef LEPB200_ENC_MINBLOCKS
@@ -193,195 +262,233 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             int16_t* redge = reinterpret_cast<int16_t*>(rowbuf + (size_t)(c == 0 ? 0 : (c == 1 ? bw0 : bw0 + bw1)) * 16);
             uint8_t* rnz = rowbuf + nz_base + (c == 0 ? 0 : (c == 1 ? nzs0 : nzs0 + nzs1));
 
-            uint32_t cur = rowp[lane];
-            uint32_t abv = has_above ? abovep[lane] : 0u;
-            uint32_t left = 0, aleft = 0;
-            int left_v = 0;          // lanes 0..7: left block's right-column edge prediction
+            // ---- the row, two blocks (A = x, B = x + 1) per iteration
+            const bool hiB = lane >= 16;                     // this lane serves block B in the packed sections
+            const int l = lane & 15;
+            const uint32_t trunc_bc = (uint32_t)g.trunc_bc[c];
+            uint32_t curA = rowp[lane], curB = w > 1 ? rowp[32 + lane] : 0u;
+            uint32_t abvA = has_above ? abovep[lane] : 0u, abvB = (has_above && w > 1) ? abovep[32 + lane] : 0u;
+            uint32_t left = 0, aleft = 0;                    // left / above-left neighbours of A
+            int left_v = 0;                                  // lanes 0..7: right-column edge prediction of A's left neighbour
             int nz_left = 0;
-            int pp = 0;              // ping-pong index of the raster copy of `cur`
-            for (int x = 0; x < w; ++x) {
-                const bool has_left = x > 0;
-                // prefetch the next block of this row and of the row above
-                uint32_t ncur = 0, nabv = 0;
-                if (x + 1 < w) { ncur = rowp[(size_t)(x + 1) * 32 + lane]; if (has_above) nabv = abovep[(size_t)(x + 1) * 32 + lane]; }
-
+            int ra = 0, rb = 1, rl = 2;                      // roles of the three rotating raster buffers
+            for (int x = 0; x < w; x += 2) {
+                // a block at or past the truncation bound is not coded unless it is the first of its row
+                // (vp8_encoder.cc:110-113,133-135)
+                const bool has_b = x + 1 < w && (uint32_t)((size_t)y * w + x + 1) < trunc_bc;
+                const bool more = has_b && x + 2 < w && (uint32_t)((size_t)y * w + x + 2) < trunc_bc;
+                // prefetch the next pair of this row and of the row above
+                uint32_t ncurA = 0, ncurB = 0, nabvA = 0, nabvB = 0;
+                if (x + 2 < w) { ncurA = rowp[(size_t)(x + 2) * 32 + lane]; if (has_above) nabvA = abovep[(size_t)(x + 2) * 32 + lane]; }
+                if (x + 3 < w) { ncurB = rowp[(size_t)(x + 3) * 32 + lane]; if (has_above) nabvB = abovep[(size_t)(x + 3) * 32 + lane]; }
                 // ---------------- raster copies for the gathers (IDCT, Lakhani edge predictor)
-                {
-                    ws.rast[pp][r0] = (int16_t)h_lo(cur); ws.rast[pp][r1] = (int16_t)h_hi(cur);
-                    ws.rast[2][r0] = (int16_t)h_lo(abv); ws.rast[2][r1] = (int16_t)h_hi(abv);
+                ws.rast[ra][r0] = (int16_t)h_lo(curA); ws.rast[ra][r1] = (int16_t)h_hi(curA);
+                ws.rast[3][r0] = (int16_t)h_lo(abvA); ws.rast[3][r1] = (int16_t)h_hi(abvA);
+                if (has_b) {
+                    ws.rast[rb][r0] = (int16_t)h_lo(curB); ws.rast[rb][r1] = (int16_t)h_hi(curB);
+                    ws.rast[4][r0] = (int16_t)h_lo(abvB); ws.rast[4][r1] = (int16_t)h_hi(abvB);
                 }
                 __syncwarp();
-                const int16_t* rcur = ws.rast[pp];
-                const int16_t* rleft = ws.rast[pp ^ 1];
-                const int16_t* rabove = ws.rast[2];
+                const bool act_h = !hiB || has_b;                           // this half has a block
+                const bool has_left_h = hiB ? true : x > 0;
+                const int16_t* rcur = ws.rast[hiB ? rb : ra];
+                const int16_t* rabove = ws.rast[hiB ? 4 : 3];
+                const int16_t* rleft = ws.rast[hiB ? ra : rl];
 
-                int qn = 0;   // queue length (warp-uniform)
-                // ---------------- (i) number of non-zeros in the 7x7 block (aligned_block.hh:132-148), context model.hh:463-485
-                const int c0v = h_lo(cur), c1v = h_hi(cur);
+                // ---------------- number of non-zeros in the 7x7 areas (aligned_block.hh:132-148)
                 const bool in0 = 2 * lane < 49, in1 = 2 * lane + 1 < 49;
-                const bool e0 = in0 && c0v != 0, e1 = in1 && c1v != 0;
-                const uint32_t m0 = __ballot_sync(FULL, e0), m1 = __ballot_sync(FULL, e1);
-                const int nz = __popc(m0) + __popc(m1);
-                const int nz_above = has_above ? (int)rnz[x] : 0;
+                const uint32_t mA0 = __ballot_sync(FULL, in0 && h_lo(curA) != 0), mA1 = __ballot_sync(FULL, in1 && h_hi(curA) != 0);
+                const uint32_t mB0 = __ballot_sync(FULL, has_b && in0 && h_lo(curB) != 0), mB1 = __ballot_sync(FULL, has_b && in1 && h_hi(curB) != 0);
+                const int nzA = __popc(mA0) + __popc(mA1), nzB = __popc(mB0) + __popc(mB1);
+                const int nz_h = hiB ? nzB : nzA;
+
+                // ---------------- pixels, DC prediction (encoder.cc:293-364) and neighbour summaries (block_context.hh:44-78)
+                warp_idct_pair(ws.rast[ra], ws.rast[rb], q, ws.tmp, ws.pix, lane, has_b);
+                const int dcA = h_hi(__shfl_sync(FULL, curA, 24)), dcB = h_hi(__shfl_sync(FULL, curB, 24));     // aligned index 49
+                const int dc_h = hiB ? dcB : dcA;
+                const int16_t* pix_h = ws.pix[hiB ? 1 : 0];
+                const int edge = act_h ? edge_pixel(pix_h, q0, dc_h, l) : 0;          // l < 8: right column, l >= 8: bottom row
+                const int edge_from_a = __shfl_sync(FULL, edge, lane & 7);           // A's right column -> B's left neighbour
+                const int left_v_h = hiB ? edge_from_a : left_v;
+                int above_h = 0;
+                if (has_above && act_h && l >= 8) above_h = redge[(size_t)(x + (hiB ? 1 : 0)) * 8 + (l - 8)];
+                DcPred dp = warp_predict_dc_pair(pix_h, left_v_h, above_h, has_left_h, has_above, q0, lane);
+                int dc_len, dc_v;
                 {
-                    int ctx = 0;
-                    if (has_above && !has_left) ctx = (nz_above + 1) / 2;
-                    else if (has_left && !has_above) ctx = (nz_left + 1) / 2;
-                    else if (has_left && has_above) ctx = (nz_above + nz_left + 2) / 4;
-                    int bin = c_nonzero_to_bin[ctx];
-                    if (lane < 6) {
-                        int idx = 5 - lane;                               // bit index, MSB first
-                        int prefix = nz >> (idx + 1);
-                        ws.desc[IT_NZ + lane] = make_uint4(0x80000000u, m_nz7(ci, bin, idx, prefix) | ((uint32_t)((nz >> idx) & 1) << 31), 0u, 0u);
-                        ws.mark[lane] = (uint8_t)(IT_NZ + lane + 1);
-                    }
-                    qn = 6;
+                    const int adv = adv_unpredict(dc_h, false, dp.pred);
+                    if (act_h && dc_h != adv_unpredict((int)(int16_t)adv, true, dp.pred)) status = ST_COEF_RANGE;
+                    dc_v = (int)(int16_t)adv;
+                    dc_len = min(bitlen(iabs(dc_v) & 0xffff), 11);
                 }
-                // ---------------- (ii) 7x7 coefficients in zig-zag (== aligned) order (encoder.cc:219-285)
-                int eobx = 0, eoby = 0;
+                const int n_dc = coef_entries(dc_len);
+
+                // ---------------- 7x7 coefficients: which are coded and how many decisions each takes (encoder.cc:219-285)
+                const int bA0 = __popc(mA0 & lt_mask) + __popc(mA1 & lt_mask), bA1 = bA0 + ((mA0 >> lane) & 1);
+                const int bB0 = __popc(mB0 & lt_mask) + __popc(mB1 & lt_mask), bB1 = bB0 + ((mB0 >> lane) & 1);
+                const bool cA0 = in0 && bA0 < nzA, cA1 = in1 && bA1 < nzA, cB0 = in0 && bB0 < nzB, cB1 = in1 && bB1 < nzB;
+                const int lA0 = bitlen(iabs(h_lo(curA)) & 0xffff), lA1 = bitlen(iabs(h_hi(curA)) & 0xffff);
+                const int lB0 = bitlen(iabs(h_lo(curB)) & 0xffff), lB1 = bitlen(iabs(h_hi(curB)) & 0xffff);
+                if ((cA0 && lA0 > 11) || (cA1 && lA1 > 11) || (cB0 && lB0 > 11) || (cB1 && lB1 > 11)) status = ST_COEF_RANGE;
+                const int nA0 = cA0 ? coef_entries(min(lA0, 11)) : 0, nA1 = cA1 ? coef_entries(min(lA1, 11)) : 0;
+                const int nB0 = cB0 ? coef_entries(min(lB0, 11)) : 0, nB1 = cB1 ? coef_entries(min(lB1, 11)) : 0;
+                int tot7;
+                const int sc7 = warp_excl_scan((nA0 + nA1) | ((nB0 + nB1) << 16), lane, tot7);      // both blocks in one scan
+                const int tot7A = tot7 & 0xffff, tot7B = tot7 >> 16;
+
+                // ---------------- edges (encoder.cc:39-184): within a half, lanes 0..6 horizontal coefficient k = l + 1,
+                // lanes 8..14 vertical k = l - 7; lane 7 carries the vertical count bits, lane 15 the horizontal ones
+                const bool is_h = l < 7, is_v = l >= 8 && l < 15;
+                const int ek = is_h ? l + 1 : l - 7;
+                const int ecoord = is_h ? ek : 8 * ek;
+                int ev = 0;
+                if ((is_h || is_v) && act_h) ev = rcur[ecoord];
+                const uint32_t nzmask = __ballot_sync(FULL, ev != 0);
+                const uint32_t hm = (nzmask >> (lane & 16)) & 0x7f, vm = (nzmask >> ((lane & 16) + 8)) & 0x7f;
+                const int ne_h = __popc(hm), ne_v = __popc(vm);
+                int eprior = 0;
+                if (act_h && ((is_h && has_above) || (is_v && has_left_h)))        // one pass for both edges of both blocks
+                    eprior = lak_pred(rcur, is_h ? rabove : rleft, (is_h ? g.icos_x[c] : g.icos_y[c]) + ek * 8, ecoord, is_h ? 8 : 1);
+                const uint32_t lt16 = (1u << l) - 1;
+                const int ne_rem = is_h ? ne_h - __popc(hm & lt16) : ne_v - __popc(vm & ((lt16 >> 8) & 0x7f));
+                const bool ecoded = (is_h || is_v) && ne_rem > 0;
+                const int eav = iabs(ev) & 0xffff;
+                const int elen_raw = bitlen(eav);
+                if (ecoded && elen_raw > 11) status = ST_COEF_RANGE;
+                const int elen = min(elen_raw, 11);
+                int ecnt = ecoded ? coef_entries(elen) : 0;
+                if (l == 7) ecnt = 3;                                               // vertical count bits sit between the two edges
+                int etot_all;
+                const int esc_all = warp_excl_scan(ecnt, lane, etot_all);
+                const int etotA = __shfl_sync(FULL, esc_all, 16);                  // exclusive prefix at lane 16 == total of half A
+                const int esc = hiB ? esc_all - etotA : esc_all;
+                const int etot_h = hiB ? etot_all - etotA : etotA;
+                // eob of the 7x7 area per block (for the edge-count contexts)
+                int eobx, eoby;
                 {
-                    const int before0 = __popc(m0 & lt_mask) + __popc(m1 & lt_mask);
-                    const int before1 = before0 + (e0 ? 1 : 0);
-                    const bool coded0 = in0 && before0 < nz, coded1 = in1 && before1 < nz;
-                    const int a0 = iabs(c0v), a1 = iabs(c1v);
-                    const int len0 = bitlen(a0 & 0xffff), len1 = bitlen(a1 & 0xffff);
-                    if ((coded0 && len0 > 11) || (coded1 && len1 > 11)) status = ST_COEF_RANGE;
-                    int cnt0 = coded0 ? coef_entries(min(len0, 11)) : 0;
-                    int cnt1 = coded1 ? coef_entries(min(len1, 11)) : 0;
-                    int total;
-                    int off = qn + warp_excl_scan(cnt0 + cnt1, lane, total);
-                    // priors
-                    const int pr0 = aavrg16(h_lo(left), h_lo(abv), h_lo(aleft), has_left, has_above);
-                    const int pr1 = aavrg16(h_hi(left), h_hi(abv), h_hi(aleft), has_left, has_above);
+                    const bool eA0 = (mA0 >> lane) & 1, eA1 = (mA1 >> lane) & 1, eB0 = (mB0 >> lane) & 1, eB1 = (mB1 >> lane) & 1;
+                    int ax = 0, ay = 0, bx = 0, by = 0;
+                    if (eA0) { ax = r0 & 7; ay = r0 >> 3; }
+                    if (eA1) { ax = max(ax, r1 & 7); ay = max(ay, r1 >> 3); }
+                    if (eB0) { bx = r0 & 7; by = r0 >> 3; }
+                    if (eB1) { bx = max(bx, r1 & 7); by = max(by, r1 >> 3); }
+                    const int packed = __reduce_max_sync(FULL, ax) | (__reduce_max_sync(FULL, ay) << 4) | (__reduce_max_sync(FULL, bx) << 8) | (__reduce_max_sync(FULL, by) << 12);
+                    eobx = (packed >> (hiB ? 8 : 0)) & 15; eoby = (packed >> (hiB ? 12 : 4)) & 15;
+                }
+
+                // ---------------- queue layout: [6 count bits][7x7][3 h-count][h coefs][3 v-count][v coefs][DC] per block
+                const int n_dcA = __shfl_sync(FULL, n_dc, 0), n_dcB = __shfl_sync(FULL, n_dc, 16);
+                const int qnA = 6 + tot7A + 3 + etotA + n_dcA;
+                const int qnB = has_b ? 6 + tot7B + 3 + (etot_all - etotA) + n_dcB : 0;
+                const int base_b = qnA;
+                const int base_h = hiB ? base_b : 0;                                // queue position of this half's block
+                const int tot7_h = hiB ? tot7B : tot7A;
+                const int it0 = hiB ? N_ITEMS : 0;                                  // item ids of this half's block
+
+                // ---------------- items: count bits of the 7x7 area (context model.hh:463-485)
+                {
+                    const int nz_above = (has_above && act_h) ? (int)rnz[x + (hiB ? 1 : 0)] : 0;
+                    const int nzl = hiB ? nzA : nz_left;
+                    int ctx = 0;
+                    if (has_above && !has_left_h) ctx = (nz_above + 1) / 2;
+                    else if (has_left_h && !has_above) ctx = (nzl + 1) / 2;
+                    else if (has_left_h && has_above) ctx = (nz_above + nzl + 2) / 4;
+                    if (l < 6 && act_h) {
+                        const int bin = sm.nzbin[ctx];
+                        const int idx = 5 - l;                                      // bit index, MSB first
+                        ws.desc[it0 + IT_NZ + l] = make_uint4(0x80000000u, m_nz7(ci, bin, idx, nz_h >> (idx + 1)) | ((uint32_t)((nz_h >> idx) & 1) << 31), 0u, 0u);
+                        ws.mark[base_h + l] = (uint8_t)(it0 + IT_NZ + l + 1);
+                    }
+                }
+                // ---------------- items: 7x7 coefficients, block A then block B (all lanes, two coefficients each)
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    if (blk == 1 && !has_b) break;
+                    const uint32_t cur = blk ? curB : curA, lf = blk ? curA : left, ab = blk ? abvB : abvA, al = blk ? abvA : aleft;
+                    const bool hl = blk ? true : x > 0;
+                    const int nz = blk ? nzB : nzA;
+                    int off = (blk ? base_b : 0) + 6 + (blk ? (sc7 >> 16) : (sc7 & 0xffff));
+                    const int pr0 = aavrg16(h_lo(lf), h_lo(ab), h_lo(al), hl, has_above);
+                    const int pr1 = aavrg16(h_hi(lf), h_hi(ab), h_hi(al), hl, has_above);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const bool coded = h ? coded1 : coded0;
+                        const bool coded = blk ? (h ? cB1 : cB0) : (h ? cA1 : cA0);
                         if (coded) {
                             const int zz = 2 * lane + h;
-                            const int v = h ? c1v : c0v, av = h ? a1 : a0, len = min(h ? len1 : len0, 11);
+                            const int v = h ? h_hi(cur) : h_lo(cur), av = iabs(v);
+                            const int len = min(blk ? (h ? lB1 : lB0) : (h ? lA1 : lA0), 11);
                             const int prior = h ? pr1 : pr0;
-                            const int left_nz = nz - (h ? before1 : before0);
+                            const int left_nz = nz - (blk ? (h ? bB1 : bB0) : (h ? bA1 : bA0));
                             const int bin = sm.nzbin[left_nz];
                             const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
                             const int coord = h ? r1 : r0;
-                            ws.desc[IT_77 + zz] = make_uint4(m_exp7(ci, bin, zz, bsr) | ((uint32_t)len << 20) | ((uint32_t)(v >= 0) << 24),
-                                                             m_sign(ci, 0, 0) | ((uint32_t)(av & 0x7ff) << 20),
-                                                             m_resn(ci, coord, bin) | ((uint32_t)off << 20), 15u << 20);
-                            ws.mark[off] = (uint8_t)(IT_77 + zz + 1);
+                            const int it = blk * N_ITEMS + IT_77 + zz;
+                            ws.desc[it] = make_uint4(m_exp7(ci, bin, zz, bsr) | ((uint32_t)len << 20) | ((uint32_t)(v >= 0) << 24),
+                                                     m_sign(ci, 0, 0) | ((uint32_t)(av & 0x7ff) << 20),
+                                                     m_resn(ci, coord, bin) | ((uint32_t)(off - (blk ? base_b : 0)) << 20), 15u << 20);
+                            ws.mark[off] = (uint8_t)(it + 1);
                             off += coef_entries(len);
                         }
                     }
-                    // a lane's two coefficients: keep the max of both for eob
-                    {
-                        int ex = 0, ey = 0;
-                        if (e0) { ex = r0 & 7; ey = r0 >> 3; }
-                        if (e1) { ex = max(ex, r1 & 7); ey = max(ey, r1 >> 3); }
-                        eobx = __reduce_max_sync(FULL, ex);
-                        eoby = __reduce_max_sync(FULL, ey);
-                    }
-                    qn += total;
                 }
-                // ---------------- (iii) edges: horizontal (raster 1..7) then vertical (raster 8..56) (encoder.cc:39-184)
+                // ---------------- items: edge counts and edge coefficients (both blocks at once)
                 {
-                    // lanes 0..6: horizontal coefficient k = lane+1; lanes 8..14: vertical coefficient k = lane-7;
-                    // lane 7 carries the vertical count bits, the horizontal count bits sit in front of lane 0.
-                    const bool is_h = lane < 7, is_v = lane >= 8 && lane < 15;
-                    const int k = is_h ? lane + 1 : lane - 7;
-                    const int coord = is_h ? k : 8 * k;
-                    int v = 0;
-                    if (is_h || is_v) v = rcur[coord];
-                    const uint32_t nzmask = __ballot_sync(FULL, v != 0);
-                    const uint32_t hm = nzmask & 0x7f, vm = (nzmask >> 8) & 0x7f;
-                    const int ne_h = __popc(hm), ne_v = __popc(vm);
-                    int prior = 0;
-                    if ((is_h && has_above) || (is_v && has_left))        // one pass for both edges: per-lane neighbour / stride / table
-                        prior = lak_pred(rcur, is_h ? rabove : rleft, (is_h ? g.icos_x[c] : g.icos_y[c]) + k * 8, coord, is_h ? 8 : 1);
-                    const int ne_rem = is_h ? ne_h - __popc(hm & lt_mask) : ne_v - __popc(vm & ((lt_mask >> 8) & 0x7f));
-                    const bool coded = (is_h || is_v) && ne_rem > 0;
-                    const int av = iabs(v) & 0xffff;
-                    const int len_raw = bitlen(av);
-                    if (coded && len_raw > 11) status = ST_COEF_RANGE;
-                    const int len = min(len_raw, 11);
-                    int cnt = coded ? coef_entries(len) : 0;
-                    if (lane == 7) cnt = 3;
-                    int total;
-                    int off = qn + 3 + warp_excl_scan(cnt, lane, total);
-                    if (lane == 15 || lane == 7) {
-                        const bool vert = lane == 7;
+                    const int ebase = base_h + 6 + tot7_h;                          // first of the three h-count bits
+                    if ((l == 15 || l == 7) && act_h) {
+                        const bool vert = l == 7;
                         const int ne = vert ? ne_v : ne_h;
                         const int eob = vert ? eoby : eobx;
-                        int o = vert ? off : qn;
-                        const int it = vert ? IT_VCNT : IT_HCNT;
+                        int o = vert ? ebase + 3 + esc : ebase;
+                        const int it = it0 + (vert ? IT_VCNT : IT_HCNT);
                         for (int i = 2; i >= 0; --i) {
-                            ws.desc[it + 2 - i] = make_uint4(0x80000000u, m_nze(vert, ci, eob, (nz + 3) / 7, i, ne >> (i + 1)) | ((uint32_t)((ne >> i) & 1) << 31), 0u, 0u);
+                            ws.desc[it + 2 - i] = make_uint4(0x80000000u, m_nze(vert, ci, eob, (nz_h + 3) / 7, i, ne >> (i + 1)) | ((uint32_t)((ne >> i) & 1) << 31), 0u, 0u);
                             ws.mark[o++] = (uint8_t)(it + 2 - i + 1);
                         }
                     }
-                    if (coded) {
-                        const int zig15 = is_h ? k - 1 : 6 + k;
-                        const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
-                        const int p16 = (int)(int16_t)prior;                           // sign_array_8: int16 truncation (model.hh:1116)
+                    if (ecoded) {
+                        const int off = ebase + 3 + esc;
+                        const int zig15 = is_h ? ek - 1 : 6 + ek;
+                        const int bsr = bitlen((uint32_t)min(iabs(eprior), 1023));
+                        const int p16 = (int)(int16_t)eprior;                           // sign_array_8: int16 truncation (model.hh:1116)
                         const int sctx = p16 == 0 ? 0 : (p16 > 0 ? 1 : 2);
-                        const int min_thr = g.min_thr[c][coord];
+                        const int min_thr = g.min_thr[c][ecoord];
                         uint32_t w3 = 15u << 20;
-                        if (len - 2 >= min_thr) {
-                            const int ctx_abs = iabs(prior) & 0xffff;                  // uint16_t ctx_abs (model.hh:1079)
-                            w3 = m_thr(ci, min(ctx_abs >> min_thr, 255), min(len - min_thr, 7)) | ((uint32_t)min_thr << 20);
+                        if (elen - 2 >= min_thr) {
+                            const int ctx_abs = iabs(eprior) & 0xffff;                  // uint16_t ctx_abs (model.hh:1079)
+                            w3 = m_thr(ci, min(ctx_abs >> min_thr, 255), min(elen - min_thr, 7)) | ((uint32_t)min_thr << 20);
                         }
-                        const int it = (is_h ? IT_H : IT_V) + k - 1;
-                        ws.desc[it] = make_uint4(m_expx(ci, ne_rem, zig15, bsr) | ((uint32_t)len << 20) | ((uint32_t)(v >= 0) << 24),
-                                                 m_sign(ci, sctx, bsr) | ((uint32_t)(av & 0x7ff) << 20),
-                                                 m_resn(ci, coord, ne_rem) | ((uint32_t)off << 20), w3);
+                        const int it = it0 + (is_h ? IT_H : IT_V) + ek - 1;
+                        ws.desc[it] = make_uint4(m_expx(ci, ne_rem, zig15, bsr) | ((uint32_t)elen << 20) | ((uint32_t)(ev >= 0) << 24),
+                                                 m_sign(ci, sctx, bsr) | ((uint32_t)(eav & 0x7ff) << 20),
+                                                 m_resn(ci, ecoord, ne_rem) | ((uint32_t)(off - base_h) << 20), w3);
                         ws.mark[off] = (uint8_t)(it + 1);
                     }
-                    qn += 3 + total;
-                }
-                // ---------------- (iv) DC (encoder.cc:293-364)
-                warp_idct_sans_dc(rcur, q, ws.tmp, ws.pix, lane);
-                const int dc = h_hi(__shfl_sync(FULL, cur, 24));          // aligned index 49
-                int above_h = 0;
-                if (has_above && lane >= 8 && lane < 16) above_h = redge[(size_t)x * 8 + (lane - 8)];
-                DcPred dp = warp_predict_dc(ws.pix, left_v, above_h, has_left, has_above, q0, lane);
-                {
-                    const int adv = adv_unpredict(dc, false, dp.pred);
-                    if (dc != adv_unpredict((int)(int16_t)adv, true, dp.pred)) status = ST_COEF_RANGE;
-                    const int v = (int)(int16_t)adv, av = iabs(v) & 0xffff, len = min(bitlen(av), 11);
-                    const int lm = min(bitlen((uint32_t)iabs(dp.unc) & 0xffff), 11), lo = min(bitlen((uint32_t)iabs(dp.unc2) & 0xffff), 16);
-                    const int nexp = min(len + 1, 11);
-                    const int n = coef_entries(len);
-                    if (lane < n) {
-                        uint32_t e;
-                        if (lane < nexp) e = (m_expdc(lm, lo) + lane) | ((uint32_t)(len != lane) << 31);
-                        else if (lane == nexp) {
-                            const int sctx = dp.unc2 >= 0 ? (dp.unc2 == 0 ? 3 : 2) : 1;
-                            e = m_sign(ci, 0, sctx) | ((uint32_t)(v >= 0) << 31);
-                        } else {
-                            const int i = len - 2 - (lane - nexp - 1);
-                            e = (m_resdc(lm) + i) | ((uint32_t)((av >> i) & 1) << 31);
-                        }
-                        ws.desc[IT_DC + lane] = make_uint4(0x80000000u, e, 0u, 0u);
-                        ws.mark[qn + lane] = (uint8_t)(IT_DC + lane + 1);
+                    // ---------------- item: DC (exponent / sign / residual like a coefficient, own branches; model.hh:560-640)
+                    if (l == 0 && act_h) {
+                        const int off = ebase + 3 + etot_h;
+                        const int lm = min(bitlen((uint32_t)iabs(dp.unc) & 0xffff), 11), lo = min(bitlen((uint32_t)iabs(dp.unc2) & 0xffff), 16);
+                        const int sctx = dp.unc2 >= 0 ? (dp.unc2 == 0 ? 3 : 2) : 1;
+                        ws.desc[it0 + IT_DC] = make_uint4(m_expdc(lm, lo) | ((uint32_t)dc_len << 20) | ((uint32_t)(dc_v >= 0) << 24),
+                                                          m_sign(ci, 0, sctx) | ((uint32_t)(iabs(dc_v) & 0x7ff) << 20),
+                                                          m_resdc(lm) | ((uint32_t)(off - base_h) << 20), 15u << 20);
+                        ws.mark[off] = (uint8_t)(it0 + IT_DC + 1);
                     }
-                    qn += n;
                 }
                 __syncwarp();
-                // ---------------- (v) neighbour summary of this block (block_context.hh:44-78)
-                const int edge = edge_pixel(ws.pix, q0, dc, lane);
-                if (lane >= 8 && lane < 16) redge[(size_t)x * 8 + (lane - 8)] = (int16_t)edge;
-                if (lane == 0) rnz[x] = (uint8_t)nz;
-                left_v = edge;            // lanes 0..7
-                nz_left = nz;
+                // ---------------- neighbour summaries for the row below and the next pair
+                if (act_h && l >= 8) redge[(size_t)(x + (hiB ? 1 : 0)) * 8 + (l - 8)] = (int16_t)edge;
+                if (l == 0 && act_h) rnz[x + (hiB ? 1 : 0)] = (uint8_t)nz_h;
+                left_v = __shfl_sync(FULL, edge, (has_b ? 16 : 0) + (lane & 7));       // lanes 0..7: right column of the last block coded
+                nz_left = has_b ? nzB : nzA;
 
                 // ---------------- code the queued decisions
                 status = __reduce_max_sync(FULL, status);
                 if (status != ST_OK) break;
-                flush_queue(ws, qn, model, sm.rcp, tokens, ntok, tok_cap, lane);
-                ndec += (unsigned long long)qn;
-
-                // early-out on truncated images (vp8_encoder.cc:110-113,133-135): not after the right-most block
-                if (x + 1 < w && (uint32_t)((size_t)y * w + x + 1) >= (uint32_t)g.trunc_bc[c]) break;
-
-                aleft = abv; left = cur; cur = ncur; abv = nabv; pp ^= 1;
+                flush_queue(ws, qnA + qnB, base_b, model, sm.rcp, tokens, ntok, tok_cap, lane);
+                ndec += (unsigned long long)(qnA + qnB);
+                if (!more) break;
+                aleft = abvB; left = curB;
+                curA = ncurA; curB = ncurB; abvA = nabvA; abvB = nabvB;
+                { const int t = rl; rl = rb; rb = ra; ra = t; }
             }
             if (status != ST_OK) break;
         }

@@ -103,12 +103,15 @@ __device__ __forceinline__ uint32_t be_word(const uint32_t* __restrict__ w, uint
 }
 
 #ifndef LEPB200_HUFF_MINBLOCKS
-#define LEPB200_HUFF_MINBLOCKS 3
+#define LEPB200_HUFF_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(HUFF_MAX_WARPS * 32, LEPB200_HUFF_MINBLOCKS)
 lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev* __restrict__ tables, int ntables) {
     __shared__ HuffTableDev s_tab[HUFF_SMEM_TABLES];
     __shared__ uint8_t s_zz[64];
+    // per-component constants of each warp's image: read once per block, so they live in shared memory, not registers
+    struct CmpInfo { unsigned long long plane; const HuffTableDev* dct; const HuffTableDev* act; int H, V, W, pad; };
+    __shared__ CmpInfo s_cmp[HUFF_MAX_WARPS][3];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) s_zz[i] = c_zigzag_to_aligned[i];
     const bool use_smem = ntables <= HUFF_SMEM_TABLES;
     if (use_smem) {
@@ -130,15 +133,18 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
     const uint32_t total_bits = jb.nbytes * 8u;
     HuffRow* rows = reinterpret_cast<HuffRow*>(jb.rows);
     const int ncmp = jb.ncmp, mcuh = jb.mcuh, mcuv = jb.mcuv, rsti = jb.rsti;
-    const int H0 = jb.H[0], V0 = jb.V[0], H1 = ncmp > 1 ? jb.H[1] : 1, V1 = ncmp > 1 ? jb.V[1] : 1, H2 = ncmp > 2 ? jb.H[2] : 1, V2 = ncmp > 2 ? jb.V[2] : 1;
-    const int W0 = jb.bch[0], W1 = ncmp > 1 ? jb.bch[1] : 0, W2 = ncmp > 2 ? jb.bch[2] : 0;
+    CmpInfo* const ci = s_cmp[threadIdx.x >> 5];
+    if (lane < 3) {
+        const int q = lane < ncmp ? lane : 0;
+        CmpInfo t;
+        t.plane = jb.plane[q]; t.dct = tb + jb.dc_tab[q]; t.act = tb + jb.ac_tab[q];
+        t.H = lane < ncmp ? jb.H[q] : 1; t.V = lane < ncmp ? jb.V[q] : 1; t.W = lane < ncmp ? jb.bch[q] : 0; t.pad = 0;
+        ci[lane] = t;
+    }
+    __syncwarp();
+    const int H0 = ci[0].H, V0 = ci[0].V, W0 = ci[0].W;
     const int nch0 = jb.nch[0], ncv0 = jb.ncv[0];
-    int16_t* const P0 = reinterpret_cast<int16_t*>(jb.plane[0]);
-    int16_t* const P1 = reinterpret_cast<int16_t*>(jb.plane[1]);
-    int16_t* const P2 = reinterpret_cast<int16_t*>(jb.plane[2]);
-    const HuffTableDev* const D0 = tb + jb.dc_tab[0]; const HuffTableDev* const A0 = tb + jb.ac_tab[0];
-    const HuffTableDev* const D1 = tb + jb.dc_tab[1]; const HuffTableDev* const A1 = tb + jb.ac_tab[1];
-    const HuffTableDev* const D2 = tb + jb.dc_tab[2]; const HuffTableDev* const A2 = tb + jb.ac_tab[2];
+    int16_t* const P0 = reinterpret_cast<int16_t*>(ci[0].plane);
 
     // warp-uniform decoder state
     uint32_t p = 0;                                  // bit position of the next symbol
@@ -149,8 +155,9 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
     int bpos = 0;
     bool last_nonzero = true;
     int16_t* blk = P0;
-    const HuffTableDev* dct = D0;
-    const HuffTableDev* act = A0;
+    const HuffTableDev* dct = ci[0].dct;
+    const HuffTableDev* act = ci[0].act;
+    int curH = H0, curV = V0;
     auto push_row = [&](int mcu_y) {
         if (lane == 0) {
             HuffRow r;
@@ -239,9 +246,8 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
         int sta = 0;
         bool handoff_due = false;
         if (ncmp > 1) {
-            const int H = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), V = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
-            if (++sx >= H) { sx = 0; ++sy; }
-            if (sy >= V) {
+            if (++sx >= curH) { sx = 0; ++sy; }
+            if (sy >= curV) {
                 sy = 0;
                 if (++cmp >= ncmp) {
                     cmp = 0;
@@ -249,13 +255,9 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
                     if (my >= mcuv) sta = 2;
                     else if (rsti > 0 && --rstw == 0) sta = 1;
                 }
-                dct = cmp == 0 ? D0 : (cmp == 1 ? D1 : D2);
-                act = cmp == 0 ? A0 : (cmp == 1 ? A1 : A2);
+                dct = ci[cmp].dct; act = ci[cmp].act; curH = ci[cmp].H; curV = ci[cmp].V;
             }
-            const int Hn = cmp == 0 ? H0 : (cmp == 1 ? H1 : H2), Vn = cmp == 0 ? V0 : (cmp == 1 ? V1 : V2);
-            const int Wn = cmp == 0 ? W0 : (cmp == 1 ? W1 : W2);
-            int16_t* Pn = cmp == 0 ? P0 : (cmp == 1 ? P1 : P2);
-            blk = Pn + ((size_t)(my * Vn + sy) * Wn + mx * Hn + sx) * 64;
+            blk = reinterpret_cast<int16_t*>(ci[cmp].plane) + ((size_t)(my * curV + sy) * ci[cmp].W + mx * curH + sx) * 64;
         } else {
             if (++bx >= nch0) { bx = 0; ++by; }
             if (by >= ncv0) sta = 2;
