@@ -139,6 +139,10 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
 /* Pinned staging buffer of the context (>= bytes): scans whose `entropy` pointers lie inside it, 16-byte aligned and with
  * >= 16 spare bytes behind each, are uploaded by lepb200_huffman_decode_to_device without the gather copy. */
 uint8_t* lepb200_huffman_stage_reserve(lepb200_ctx* ctx, size_t bytes);
+/* Optional: push staged bytes [offset, offset + bytes) to the device right away (asynchronous, thread-safe), e.g. from the
+ * thread that just parsed a file, so that the H2D copy overlaps the parsing of the other files.  The caller then uploads
+ * EVERY scan of the batch this way (with the 16 bytes behind each scan zeroed). */
+int lepb200_huffman_stage_upload(lepb200_ctx* ctx, size_t offset, size_t bytes);
 /* Like lepb200_encode_upload, but the planes are the ones just produced on the device by
  * lepb200_huffman_decode_to_device (geometry must match scan i).  images[i].planes == NULL: use the resident planes;
  * non-NULL (placeholder scans): copy these host planes into the image's slot first. */

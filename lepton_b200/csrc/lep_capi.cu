@@ -91,6 +91,7 @@ struct lepb200_ctx {
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
+    bool stage_preuploaded = false;       // the caller pushed the staged scans itself (lepb200_huffman_stage_upload)
 };
 
 #define CK(call)                                                                            \
@@ -399,7 +400,20 @@ uint8_t* lepb200_huffman_stage_reserve(lepb200_ctx* ctx, size_t bytes) {
     if (!ctx) return nullptr;
     if (cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
     if (ctx->h_stage.reserve(bytes + 256) != cudaSuccess) { ctx->err = "pinned staging allocation failed"; return nullptr; }
+    if (ctx->d_huff.reserve(bytes + 512) != cudaSuccess) { ctx->err = "device staging allocation failed"; return nullptr; }
+    ctx->stage_preuploaded = false;
     return static_cast<uint8_t*>(ctx->h_stage.p);
+}
+
+// Asynchronous H2D of one staged range (callable from several host threads while others are still parsing); once used,
+// the following lepb200_huffman_decode_to_device does not copy the staging buffer again, so ALL scans must be pushed.
+int lepb200_huffman_stage_upload(lepb200_ctx* ctx, size_t offset, size_t bytes) {
+    if (!ctx || !ctx->h_stage.p || offset + bytes > ctx->h_stage.cap || offset + bytes > ctx->d_huff.cap) return LEPB200_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return LEPB200_ERR_CUDA;
+    ctx->stage_preuploaded = true;
+    if (cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_huff.p) + offset, static_cast<uint8_t*>(ctx->h_stage.p) + offset, bytes,
+                        cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return LEPB200_ERR_CUDA;
+    return LEPB200_OK;
 }
 
 int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans, int n) {
@@ -464,7 +478,8 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     if (!in_place) CK(ctx->h_stage.reserve(huff_total + 256));
     uint8_t* hs = static_cast<uint8_t*>(ctx->h_stage.p);
     if (in_place) {
-        for (int i = 0; i < n; ++i) if (scans[i].entropy) memset(hs + jobs[i].huff + scans[i].nbytes, 0, 16);   // the decoder reads whole words past the end
+        if (!ctx->stage_preuploaded)          // (a caller that uploads itself has zeroed the 16 bytes behind each scan)
+            for (int i = 0; i < n; ++i) if (scans[i].entropy) memset(hs + jobs[i].huff + scans[i].nbytes, 0, 16);   // the decoder reads whole words past the end
     } else {
         // gather the de-stuffed scans into the pinned staging buffer (hundreds of MB per chunk): split over host threads
         const int nt = std::max(1, std::min(ctx->host_threads, n));
@@ -494,7 +509,8 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     const std::vector<HuffJob>& sorted = jobs;
     CK(ctx->d_hjobs.reserve(align_up(sizeof(HuffJob) * n, 256)));
     CK(cudaMemsetAsync(ctx->d_planes.p, 0, plane_total, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_huff.p, hs, huff_total, cudaMemcpyHostToDevice, ctx->stream));
+    if (!(in_place && ctx->stage_preuploaded)) CK(cudaMemcpyAsync(ctx->d_huff.p, hs, huff_total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stage_preuploaded = false;
     CK(cudaMemcpyAsync(ctx->d_hjobs.p, sorted.data(), sizeof(HuffJob) * n, cudaMemcpyHostToDevice, ctx->stream));
 
     if (!tabs.empty()) CK(cudaMemcpyAsync(ctx->d_htabs.p, tabs.data(), sizeof(HuffTableDev) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));

@@ -223,7 +223,13 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             Jpeg& j = *s.js[i];
             const lepb200_buffer& in = jpegs[s.begin + i];
             if (stage) j.huff.attach(stage + soff[i], soff[i + 1] - soff[i] - 16);
-            if (!parse_jpeg(in.data, in.len, j)) return;
+            const bool parsed = parse_jpeg(in.data, in.len, j);
+            if (stage) {                                   // push this file's scan now: the H2D overlaps the other files' parsing
+                const size_t nb = j.huff.size();
+                memset(stage + soff[i] + nb, 0, 16);
+                lepb200_huffman_stage_upload(ctx, soff[i], (nb + 16 + 15) & ~size_t(15));
+            }
+            if (!parsed) return;
             if (stage && gpu_scan_setup(j, setups[i])) eligible[i] = 1;
         });
         // host-decoded files of a GPU chunk share one arena sized for just them

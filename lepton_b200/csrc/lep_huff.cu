@@ -204,40 +204,45 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
         }
         // info: [0,6) total length (0 = invalid) | [6,10) run | [10,15) size | [16,32) value
         const uint32_t info = bad ? 0u : ((uint32_t)(len + sz) | ((uint32_t)run << 6) | ((uint32_t)sz << 10) | ((uint32_t)(val & 0xffff) << 16));
-        // ---- warp-uniform walk along the true symbol sequence inside this window
+        // ---- warp-uniform walk along the true symbol sequence inside this window: it only follows the chain of code
+        // lengths and tracks the zig-zag position; every visited lane then stores its own coefficient (parallel stores)
         int cur = 0;
         bool block_done = false;
+        int mypos = -1;                               // zig-zag position of this lane's AC symbol, if it is on the chain
+        if (bpos == 0) {                              // first symbol of a block: the DC difference, decoded by lane 0
+            const uint32_t inf = __shfl_sync(FULL, info, 0);
+            const int tot = (int)(inf & 63);
+            if (tot == 0) { status = 42; break; }
+            const int v = (int)(int16_t)(inf >> 16);
+            const int last = cmp == 0 ? dc0 : (cmp == 1 ? dc1 : dc2);
+            const int16_t dcv = (int16_t)(v + last);
+            if (cmp == 0) dc0 = dcv; else if (cmp == 1) dc1 = dcv; else dc2 = dcv;
+            if (lane == 0) blk[49] = dcv;
+            bpos = 1;
+            last_nonzero = true;
+            cur = tot;
+        }
         while (cur < 32) {
             const uint32_t inf = __shfl_sync(FULL, info, cur);
             const int tot = (int)(inf & 63);
             if (tot == 0) { status = 42; break; }
-            const int r = (int)((inf >> 6) & 15), z = (int)((inf >> 10) & 31);
-            const int v = (int)(int16_t)(inf >> 16);
-            if (bpos == 0) {
-                const int last = cmp == 0 ? dc0 : (cmp == 1 ? dc1 : dc2);
-                const int16_t dcv = (int16_t)(v + last);
-                if (cmp == 0) dc0 = dcv; else if (cmp == 1) dc1 = dcv; else dc2 = dcv;
-                if (lane == 0) blk[49] = dcv;
-                bpos = 1;
-                last_nonzero = true;
-                cur += tot;
-                // the following symbols use the AC table, but lanes > 0 already assumed that; lane 0's own AC
-                // candidate at offset 0 is never needed again
-                continue;
-            }
-            cur += tot;
-            if (r == 0 && z == 0) {                                           // EOB
+            const int rz = (int)((inf >> 6) & 0x1ff);                         // run | size << 4
+            if (rz == 0) {                                                    // EOB
                 if (bpos > 1 && !last_nonzero) status = 42;                   // "eob after last 0" (jpgcoder.cc:2953)
+                cur += tot;
                 block_done = true;
                 break;
             }
+            const int r = rz & 15;
             if (r + bpos >= 64) { status = 200; break; }                      // truncated-file fix-up path: not handled here
             bpos += r;
-            if (lane == 0) blk[s_zz[bpos]] = (int16_t)v;
+            if (lane == cur) mypos = bpos;
+            last_nonzero = (rz >> 4) != 0;                                    // size 0 here is ZRL, the only zero-valued AC symbol
             ++bpos;
-            last_nonzero = v != 0;
+            cur += tot;
             if (bpos >= 64) { block_done = true; break; }
         }
+        if (mypos >= 0) blk[s_zz[mypos]] = (int16_t)(info >> 16);
         if (status) break;
         p += (uint32_t)cur;
         if (!block_done) continue;
