@@ -70,6 +70,8 @@ typedef struct lepb200_image {
     int32_t nseg;                    /* number of thread-segments, 1..16 (selected_splits) */
     int32_t luma_y_start[LEPB200_MAX_SEGMENTS]; /* ThreadHandoff::luma_y_start of each segment; segment i ends
                                                     where i+1 starts, the last one runs to the end of the image */
+    uint32_t seg_token_bound[LEPB200_MAX_SEGMENTS]; /* encode, optional: upper bound of the binary decisions of each segment
+                                                    (from lepb200_huffrow.tokens); 0 = unknown, the library counts itself */
 } lepb200_image;
 
 /* One thread-segment's bool-coder stream. */
@@ -116,7 +118,8 @@ int lepb200_sync(lepb200_ctx* ctx);
  * Replaces the Huffman half of decode_jpeg (src/lepton/jpgcoder.cc:2799-3302, decode_block_seq :4893-4961); the caller
  * still parses markers and de-stuffs the entropy-coded bytes (read_jpeg, :2270-2466).  One thread per image. */
 typedef struct lepb200_hufftable { uint8_t bits[17]; uint8_t vals[256]; } lepb200_hufftable;   /* DHT form: counts per length (bits[1..16]) + symbols */
-typedef struct lepb200_huffrow { uint32_t bitpos; int16_t lastdc[3]; int16_t mcu_y; } lepb200_huffrow; /* Huffman state at an MCU-row start */
+typedef struct lepb200_huffrow { uint32_t bitpos; int16_t lastdc[3]; int16_t mcu_y; uint32_t tokens; } lepb200_huffrow; /* Huffman state at an MCU-row start;
+   tokens = upper bound of the coder's binary decisions for all blocks before the row */
 typedef struct lepb200_jpeg_scan {
     const uint8_t* entropy;          /* HOST: de-stuffed entropy-coded bytes of the (single) scan, RST markers removed.
                                       * NULL = placeholder: the image only gets its (zeroed) plane slot in the device arena and is

@@ -39,6 +39,7 @@ class _Image(ctypes.Structure):
         ("planes", ctypes.c_void_p * 3),
         ("nseg", ctypes.c_int32),
         ("luma_y_start", ctypes.c_int32 * MAX_SEGMENTS),
+        ("seg_token_bound", ctypes.c_uint32 * MAX_SEGMENTS),
     ]
 
 

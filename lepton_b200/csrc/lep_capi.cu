@@ -91,6 +91,8 @@ struct lepb200_ctx {
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
+    bool tokens_known = false;            // token streams laid out on the host from caller-supplied bounds (no counting pre-pass)
+    unsigned long long token_total = 0;
     bool stage_preuploaded = false;       // the caller pushed the staged scans itself (lepb200_huffman_stage_upload)
 };
 
@@ -167,6 +169,8 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     ctx->images.assign(nimages, ImageDesc());
     ctx->segs.clear(); ctx->seg_blocks.clear(); ctx->plane_bytes.assign((size_t)nimages * 3, 0);
     size_t plane_total = 0, stream_total = 0, row_stride = 0;
+    unsigned long long token_total = 0;   // token arena layout when every segment comes with a caller-supplied bound
+    bool tokens_known = encode;
     int sidx = 0;
     for (int i = 0; i < nimages; ++i) {
         const lepb200_image& im = images[i];
@@ -203,7 +207,15 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
                 size_t cap = align_up(nb * 64 + 4096, 256);   // 64 B/block is > 1.5x what q=100 photos need; overflow is reported, never silent
                 sd.stream = stream_total; sd.cap = (uint32_t)cap;
                 stream_total += cap;
-                sd.tokens = 0; sd.tok_cap = 0;                    // assigned on the device by the counting pre-pass
+                sd.tokens = 0; sd.tok_cap = 0;                    // assigned on the device by the counting pre-pass ...
+                if (im.seg_token_bound[s]) {                      // ... unless the caller knows a bound (GPU Huffman decoder)
+                    const unsigned long long tcap = ((unsigned long long)im.seg_token_bound[s] + 64 + 63) & ~63ull;
+                    sd.tok_cap = tcap > 0xffffff00ull ? 0xffffff00u : (uint32_t)tcap;
+                    sd.tokens = token_total;
+                    token_total += sd.tok_cap;
+                } else {
+                    tokens_known = false;
+                }
             } else {
                 sd.stream = stream_total; sd.cap = (uint32_t)in[sidx].len;
                 stream_total += align_up((size_t)in[sidx].len + 16, 16);
@@ -226,6 +238,8 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     int grid = std::max(1, std::min(per_sm * ctx->sm_count, (nseg + wpc - 1) / wpc));
     ctx->grid = grid;
     ctx->row_stride = row_stride;
+    ctx->tokens_known = tokens_known;
+    ctx->token_total = token_total;
 
     CK(ctx->d_planes.reserve(plane_total));
     CK(ctx->d_streams.reserve(stream_total + 256));
@@ -358,6 +372,11 @@ int lepb200_encode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
 }
 
 static int encode_prepass(lepb200_ctx* ctx) {
+    if (ctx->tokens_known) {              // bounds came with the images (GPU Huffman decoder): nothing to count, nothing to wait for
+        CK(ctx->d_tokens.reserve((size_t)ctx->token_total * 2 + 256));
+        ctx->have_batch = true;
+        return LEPB200_OK;
+    }
     // pre-pass: per-segment token upper bounds -> exact-fit token arena (sizes depend on the data, so one sync here)
     const int nseg = (int)ctx->segs.size();
     lep_count_kernel<<<nseg, CNT_THREADS, 0, ctx->stream>>>(static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg);

@@ -315,7 +315,10 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                         if (sc.status == 0 && sc.nrows >= 2) {
                             j.padbit = (int8_t)sc.padbit;
                             j.rows.clear();
-                            for (int r = 0; r < sc.nrows; ++r) j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
+                            for (int r = 0; r < sc.nrows; ++r) {
+                                j.rows.push_back(handoff_from_state(j, sc.rows[r].bitpos, sc.rows[r].mcu_y, sc.rows[r].lastdc));
+                                j.rows.back().tokens = sc.rows[r].tokens;
+                            }
                             for (size_t r = 1; r < j.rows.size(); ++r)
                                 if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
                             for (int t = 0; t < j.ncmp; ++t) { j.trunc_bcv[t] = j.cmp[t].bcv; j.trunc_bc[t] = j.cmp[t].bc; }
@@ -329,6 +332,18 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                         status[s.begin + i] = j.status;
                     }
                     fill_image(s.imgs[q], j, s.planes[i].data(), s.splits[i].selected);
+                    if (!s.host_decoded[i] && j.status == 0) {
+                        // decision-count bound of each thread-segment from the per-row counters of the Huffman kernel
+                        lepb200_image& im = s.imgs[q];
+                        size_t r = 0;
+                        uint32_t start_tok[LEPB200_MAX_SEGMENTS + 1];
+                        for (int t = 0; t < im.nseg; ++t) {
+                            while (r + 1 < j.rows.size() && (int)j.rows[r].luma_y_start < im.luma_y_start[t]) ++r;
+                            start_tok[t] = j.rows[r].tokens;
+                        }
+                        start_tok[im.nseg] = j.rows.back().tokens;
+                        for (int t = 0; t < im.nseg; ++t) im.seg_token_bound[t] = std::max<uint32_t>(1u, start_tok[t + 1] - start_tok[t]);
+                    }
                 });
                 int nseg_total = 0;
                 s.seg_base.assign(nb + 1, 0);

@@ -38,6 +38,7 @@ struct Handoff {
     uint32_t segment_size = 0;
     uint8_t overhang_byte = 0, num_overhang_bits = 0;
     int16_t last_dc[4] = {0, 0, 0, 0};
+    uint32_t tokens = 0;      // not part of the format: decision-count bound of everything before this row (GPU Huffman decoder)
 };
 
 struct Component {

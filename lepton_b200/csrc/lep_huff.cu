@@ -25,6 +25,7 @@ struct HuffRow {             // state at the start of an MCU row
     uint32_t bitpos;         // bits consumed of the de-stuffed entropy stream
     int16_t lastdc[3];
     int16_t mcu_y;
+    uint32_t tokens;         // upper bound of the binary decisions the Lepton coder takes for all blocks before this row
 };
 
 constexpr int HUFF_JOB_SKIP = -1;        // HuffJob::status of a placeholder (plane slot only, nothing to decode)
@@ -154,6 +155,11 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
     int rstw = rsti;
     int bpos = 0;
     bool last_nonzero = true;
+    // Bound of the coder's decision count, per block: 12 count bits + <= 22 for the DC + for every non-zero AC its
+    // exponent/sign/residual decisions + one decision per coded zero, of which there are at most (zig-zag index of the
+    // last non-zero) - (number of non-zeros).  Replaces a separate counting pass over the decoded planes.
+    uint32_t tokacc = 0;
+    int blk_sum = 0, blk_last = 0;
     int16_t* blk = P0;
     const HuffTableDev* dct = ci[0].dct;
     const HuffTableDev* act = ci[0].act;
@@ -163,6 +169,7 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
             HuffRow r;
             r.bitpos = p; r.mcu_y = (int16_t)mcu_y;
             r.lastdc[0] = (int16_t)dc0; r.lastdc[1] = (int16_t)dc1; r.lastdc[2] = (int16_t)dc2;
+            r.tokens = tokacc;
             rows[nrows] = r;
         }
         nrows++;
@@ -243,10 +250,18 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
             if (bpos >= 64) { block_done = true; break; }
         }
         if (mypos >= 0) blk[s_zz[mypos]] = (int16_t)(info >> 16);
+        {
+            const int z = (int)((info >> 10) & 31u);
+            const bool nzsym = mypos >= 0 && z > 0;
+            blk_sum += __reduce_add_sync(FULL, nzsym ? min(z + 1, 11) + z - 1 : 0);
+            blk_last = max(blk_last, (int)__reduce_max_sync(FULL, nzsym ? mypos : 0));
+        }
         if (status) break;
         p += (uint32_t)cur;
         if (!block_done) continue;
         if (p > total_bits) { status = 200; break; }                          // entropy data ends inside a block
+        tokacc += (uint32_t)(blk_sum + blk_last + 34);
+        blk_sum = 0; blk_last = 0;
         // ---- next block position (next_mcupos / next_mcuposn), warp-uniform
         int sta = 0;
         bool handoff_due = false;
