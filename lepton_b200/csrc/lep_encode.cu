@@ -72,22 +72,31 @@ __device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, int base_b, 
                                             uint32_t tok_cap, int lane) {
     const uint32_t lt_mask = (1u << lane) - 1, le_mask = lt_mask | (1u << lane);
     uint32_t carry = 0;                                        // item covering the last position of the previous batch
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        const bool active = i < n;
-        // which item covers queue position i: nearest start mark at or below it
-        const uint32_t mk = ws.mark[i];
-        ws.mark[i] = 0;
+    // decision (branch index, bit) of queue position `pos` for this lane; 0 past the end
+    auto decision_at = [&](int pos) -> uint32_t {
+        // which item covers the position: nearest start mark at or below it
+        const uint32_t mk = ws.mark[pos];
+        ws.mark[pos] = 0;
         const uint32_t starts = __ballot_sync(FULL, mk != 0) & le_mask;
         const uint32_t from_lane = __shfl_sync(FULL, mk, starts ? 31 - __clz(starts) : 0);
         const uint32_t item = starts ? from_lane : carry;
         carry = __shfl_sync(FULL, item, 31);
-        const uint32_t e = active ? expand_item(ws.desc[item - 1], item > (uint32_t)N_ITEMS ? i - base_b : i) : 0u;
+        return pos < n ? expand_item(ws.desc[item - 1], item > (uint32_t)N_ITEMS ? pos - base_b : pos) : 0u;
+    };
+    // software pipeline: the next batch is expanded and its model words are requested (L1 prefetch) before the current
+    // batch is resolved, so the adaptive-count loads of a batch overlap the arithmetic of the one before
+    uint32_t e_next = decision_at(lane);
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool active = i < n;
+        const uint32_t e = e_next;
+        if (base + 32 < n) {
+            e_next = decision_at(i + 32);
+            if (i + 32 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(model + (e_next & 0xfffffu)));
+        }
         const uint32_t addr = e & 0xfffffu, bit = e >> 31;
         const uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
         const uint32_t earlier = peers & lt_mask;
-        const int rank = __popc(earlier);
-        const int pred = earlier ? 31 - __clz(earlier) : lane;     // previous decision on the same branch
         uint32_t w = active ? (uint32_t)model[addr] : 0u;
         // Resolve same-branch conflicts in queue order.  While no count of the group can saturate inside this batch
         // (the common case) record_obs_and_update is a plain increment, so the state a lane sees is the loaded word
@@ -95,20 +104,28 @@ __device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, int base_b, 
         const uint32_t ones = __ballot_sync(FULL, bit != 0);
         const uint32_t n1_all = __popc(peers & ones), n0_all = __popc(peers & ~ones);
         const bool plain = !active || ((w & 0xff) + n0_all <= 254u && (w >> 8) + n1_all <= 254u);   // low byte 0xff (special state) never passes
-        if (__all_sync(FULL, plain)) {
-            w += __popc(earlier & ~ones) + (__popc(earlier & ones) << 8);
+        // the two absorbing states: (255,1) seeing only zeros and the "neverseen" (1,255) seeing only ones do not move
+        // (branch.hh:87-99); branches that always code the same bit sit there for good
+        const bool stuck = (w == 0x00feu && n1_all == 0) || ((w & 0xff) == 0xffu && n0_all == 0);
+        uint32_t neww;                                            // state after this lane's own observation
+        if (__all_sync(FULL, plain || stuck)) {
+            if (!stuck) w += __popc(earlier & ~ones) + (__popc(earlier & ones) << 8);
+            neww = stuck ? w : w + (bit ? 0x100u : 1u);
         } else {
             // general path: in round r the lanes of rank r take over the state their predecessor (rank r-1, already
             // resolved) leaves behind after its own update.
+            const int rank = __popc(earlier);
+            const int pred = earlier ? 31 - __clz(earlier) : lane;     // previous decision on the same branch
             const int maxrank = __reduce_max_sync(FULL, rank);
             for (int r = 1; r <= maxrank; ++r) {
                 const uint32_t after = branch_update(w, bit);
                 const uint32_t from_pred = __shfl_sync(FULL, after, pred);
                 if (rank == r) w = from_pred;
             }
+            neww = branch_update(w, bit);
         }
         const uint32_t pb = branch_prob(w, s_rcp) | (bit << 8);
-        if (active && (peers >> lane) == 1u) model[addr] = (uint16_t)branch_update(w, bit);   // last decision of its branch
+        if (active && (peers >> lane) == 1u) model[addr] = (uint16_t)neww;                    // last decision of its branch
         if (active && ntok + i < tok_cap) tokens[ntok + i] = (uint16_t)pb;                    // coalesced 2-byte stores
         __syncwarp();                                                                         // order this batch's model stores before the next batch's loads
     }
