@@ -14,6 +14,7 @@
 #include "lep_predict.cuh"
 #include "lep_encode.cu"
 #include "lep_decode.cu"
+#include "lep_decode_thread.cu"
 #include "lep_huff.cu"
 
 using namespace lepb200;
@@ -91,6 +92,10 @@ struct lepb200_ctx {
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
+    int dec_mode = 0;                     // decode kernel: 0 = one warp per segment (default), 1 = one thread per segment (wins only when
+                                          // tens of thousands of segments are in flight)
+    int dec_threads_max = 16384;          // thread mode: segments per launch (one 1.58 MB model each)
+    int dec_threads = 0;                  // thread mode: model / row-buffer slots of the current batch
     bool tokens_known = false;            // token streams laid out on the host from caller-supplied bounds (no counting pre-pass)
     unsigned long long token_total = 0;
     bool stage_preuploaded = false;       // the caller pushed the staged scans itself (lepb200_huffman_stage_upload)
@@ -247,8 +252,14 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
     CK(ctx->d_counter.reserve(256));
-    CK(ctx->d_models.reserve((size_t)grid * wpc * MODEL_BYTES));
-    CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
+    if (!encode && ctx->dec_mode == 1) {
+        ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
+        CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
+        CK(ctx->d_rows.reserve((size_t)ctx->dec_threads * row_stride));
+    } else {
+        CK(ctx->d_models.reserve((size_t)grid * wpc * MODEL_BYTES));
+        CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
+    }
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < ctx->images[i].ncmp; ++c) ctx->images[i].plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
     for (auto& sd : ctx->segs) sd.stream += (unsigned long long)(uintptr_t)ctx->d_streams.p;
@@ -304,6 +315,8 @@ int lepb200_create(lepb200_ctx** out, int device) {
     }
     if (const char* e = getenv("LEPB200_ENC_CTA_CAP")) ctx->enc_cta_cap = atoi(e);          // tuning overrides
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
+    if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
+    if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
     *out = ctx;
     return LEPB200_OK;
 }
@@ -697,10 +710,24 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
-        static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
-        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
-    CK(cudaGetLastError());
+    if (ctx->dec_mode == 1) {
+        // one thread per segment, largest segments first; a launch covers as many segments as there are model slots
+        for (int first = 0; first < nseg; first += ctx->dec_threads) {
+            const int count = std::min(ctx->dec_threads, nseg - first);
+            CK(cudaMemsetAsync(ctx->d_models.p, 0, (size_t)count * MODEL_BYTES, ctx->stream));       // identity prior = zero fill
+            lep_decode_thread_kernel<<<(count + DECT_THREADS - 1) / DECT_THREADS, DECT_THREADS, 0, ctx->stream>>>(
+                static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), first, count, static_cast<const int*>(ctx->d_order.p),
+                static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+        }
+        ctx->launches -= 1;
+    } else {
+        lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
+            static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
+            static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     ctx->launched = true;

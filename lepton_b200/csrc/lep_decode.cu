@@ -58,15 +58,16 @@ __device__ __forceinline__ uint32_t dec_get(Decoder& d, uint32_t addr) {
     BoolReader& r = d.br;
     uint32_t split = (r.range * prob + (256 - prob)) >> 8;
     if (r.count < 0) br_fill(r);
-    unsigned long long bigsplit = (unsigned long long)split << 56;
-    uint32_t bit = r.value >= bigsplit;
+    const uint32_t bit = (uint32_t)(r.value >> 56) >= split;          // value >= split << 56  <=>  top byte >= split
     uint32_t range = bit ? r.range - split : split;
-    if (bit) r.value -= bigsplit;
+    if (bit) r.value -= (unsigned long long)split << 56;
     int shift = __clz(range) - 24;
     r.range = range << shift;
     r.value <<= shift;
     r.count -= shift;
-    d.model[addr] = (uint16_t)branch_update(w, bit);      // every lane stores the same value (one transaction)
+    // record_obs_and_update: a plain increment unless a count is about to saturate (or the word is the special state)
+    const bool plain = (w & 0xffu) < 254u && (w >> 8) < 254u;
+    d.model[addr] = (uint16_t)(plain ? w + (bit ? 0x100u : 1u) : branch_update(w, bit));      // every lane stores the same value (one transaction)
     d.ndec++;
     return bit;
 }
@@ -133,15 +134,13 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             r.range = range << shift; r.value <<= shift; r.count -= shift;
         }
 
-        int16_t* row_edge[3]; uint8_t* row_nz[3];
-        {
-            size_t off = 0;
-            for (int c = 0; c < 3; ++c) { int w = c < g.ncmp ? g.bch[c] : 0; row_edge[c] = reinterpret_cast<int16_t*>(rowbuf + off); off += (size_t)w * 16; }
-            for (int c = 0; c < 3; ++c) { int w = c < g.ncmp ? g.bch[c] : 0; row_nz[c] = rowbuf + off; off += (size_t)((w + 15) & ~15); }
-        }
+        // per-component row buffers (offsets kept as scalars: arrays indexed by the component would live in local memory)
+        const int bw0 = g.bch[0], bw1 = g.ncmp > 1 ? g.bch[1] : 0, bw2 = g.ncmp > 2 ? g.bch[2] : 0;
+        const size_t nz_base = (size_t)(bw0 + bw1 + bw2) * 16;
+        const int nzs0 = (bw0 + 15) & ~15, nzs1 = (bw1 + 15) & ~15;
 
         int status = ST_OK;
-        bool top[3] = {true, true, true};
+        uint32_t top_mask = 7u;
         uint32_t index = 0;
         for (;;) {
             RowSpec rs = row_spec_from_index(index++, g);
@@ -150,8 +149,8 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             if (rs.skip) continue;
             if (rs.luma_y < sd.min_y) continue;
             const int c = rs.component, y = rs.curr_y;
-            const bool has_above = !top[c];
-            top[c] = false;
+            const bool has_above = !((top_mask >> c) & 1u);
+            top_mask &= ~(1u << c);
             const int ci = c == 0 ? 0 : 1;
             const int w = g.bch[c];
             uint32_t* plane = reinterpret_cast<uint32_t*>(g.plane[c]);
@@ -159,8 +158,8 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             const uint32_t* abovep = rowp - (size_t)w * 32;
             const uint16_t* q = g.q[c];
             const int q0 = q[0];
-            int16_t* redge = row_edge[c];
-            uint8_t* rnz = row_nz[c];
+            int16_t* redge = reinterpret_cast<int16_t*>(rowbuf + (size_t)(c == 0 ? 0 : (c == 1 ? bw0 : bw0 + bw1)) * 16);
+            uint8_t* rnz = rowbuf + nz_base + (c == 0 ? 0 : (c == 1 ? nzs0 : nzs0 + nzs1));
 
             uint32_t abv = has_above ? abovep[lane] : 0u;
             uint32_t left = 0, aleft = 0;

@@ -49,6 +49,17 @@ def test_golden_batch_decode_matches_reference_planes(codec):
             assert np.array_equal(img.planes[c], planes[c]), "%s component %d" % (name, c)
 
 
+def test_golden_batch_decode_thread_per_segment_kernel(monkeypatch):
+    """The alternative decode kernel (one thread per segment, LEPB200_DEC_MODE=1) must give the same planes."""
+    from lepton_b200 import LeptonB200Codec
+    monkeypatch.setenv("LEPB200_DEC_MODE", "1")
+    c = LeptonB200Codec(0)
+    try:
+        test_golden_batch_decode_matches_reference_planes(c)
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("cfg", [
     dict(ncmp=3, mcuh=5, mcuv=4, sf=((2, 2), (1, 1), (1, 1)), nseg=1),
     dict(ncmp=3, mcuh=7, mcuv=6, sf=((2, 2), (1, 1), (1, 1)), nseg=3),
