@@ -510,25 +510,15 @@ class LeptonB200FileCodec:
             return [(res[i].status, res[i].len) for i in range(n)]
         return [(res[i].status, ctypes.string_at(res[i].data, res[i].len) if res[i].len else b"") for i in range(n)]
 
-    def decompress(self, leps: Sequence[bytes], copy: bool = True):
-        """.lep bytes -> JPEG bytes; -> list of (status, jpeg_bytes)."""
-        n = len(leps)
-        bufs = (_Buffer * n)()
-        keep = []
-        for i, j in enumerate(leps):
-            b = np.frombuffer(j, dtype=np.uint8)
-            keep.append(b)
-            bufs[i].data = b.ctypes.data
-            bufs[i].len = len(b)
-        res = (_Result * n)()
+    def decompress(self, leps, copy: bool = True):
+        """.lep bytes -> JPEG bytes; -> list of (status, jpeg_bytes).  `leps`: bytes objects or a handle from prepare()."""
+        bufs, n, _keep, res = leps if isinstance(leps, tuple) else self.prepare(leps)
         rc = self._L.lepb200_decompress_leps(self._c, bufs, n, res)
         if rc != 0:
             raise LeptonB200Error("decompress_leps failed (%d): %s" % (rc, self._L.lepb200_codec_last_error(self._c).decode()))
-        out = []
-        for i in range(n):
-            r = res[i]
-            out.append((r.status, ctypes.string_at(r.data, r.len) if (copy and r.len) else (b"" if copy else r.len)))
-        return out
+        if not copy:
+            return [(res[i].status, res[i].len) for i in range(n)]
+        return [(res[i].status, ctypes.string_at(res[i].data, res[i].len) if res[i].len else b"") for i in range(n)]
 
     def last_timing(self):
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()

@@ -415,7 +415,9 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     if (!c || !leps || !out || n <= 0) return LEPB200_ERR_INVALID;
     c->err.clear();
     c->t_front = c->t_gpu = c->t_back = 0;
-    const int chunk = std::max(1, c->chunk_images);
+    // the way back moves the coefficient planes over PCIe (128 B per block) and re-encodes Huffman on host threads, so its
+    // chunks are smaller: three pinned plane arenas rotate through front / gpu / back
+    const int chunk = std::max(1, std::min(c->chunk_images, 1024));
     const int nchunks = (n + chunk - 1) / chunk;
     c->outputs.assign(n, std::vector<uint8_t>());
     std::vector<int> status(n, 0);
@@ -450,8 +452,8 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             base[i] = total;
             for (int q = 0; q < s.lf[i]->j.ncmp; ++q) total += (plane_bytes(s.lf[i]->j, q) + 255) & ~size_t(255);
         }
-        if (!reserve_arena(c, k & 1, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
-        uint8_t* arena = static_cast<uint8_t*>(c->arena[k & 1]);
+        if (!reserve_arena(c, k % 3, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+        uint8_t* arena = static_cast<uint8_t*>(c->arena[k % 3]);
         int nseg_total = 0;
         for (int i = 0; i < m; ++i) {
             LepFile& lf = *s.lf[i];
@@ -483,7 +485,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         double t0 = now_s();
         DChunk& s = cs[k];
         if (s.gpu_rc == 0 && !s.imgs.empty())
-            s.gpu_rc = lepb200_decode_images(c->ctx2[k & 1], s.imgs.data(), (int)s.imgs.size(), s.streams.data(), s.seg_status.data());
+            s.gpu_rc = lepb200_decode_images(c->ctx2[k % 3], s.imgs.data(), (int)s.imgs.size(), s.streams.data(), s.seg_status.data());
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -513,7 +515,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         if (tb.joinable()) tb.join();
     }
     int rc = LEPB200_OK;
-    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k & 1]); }
+    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
     for (int i = 0; i < n; ++i) {
         out[i].status = status[i];
         out[i].data = status[i] ? nullptr : c->outputs[i].data();
