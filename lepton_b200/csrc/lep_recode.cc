@@ -8,6 +8,8 @@
 // is done here (one host thread per file; files are processed in parallel by the caller).
 #include <zlib.h>
 
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -185,6 +187,94 @@ struct BitWriter {
 
 inline int bitlen16(int v) { return v ? 32 - __builtin_clz((unsigned)v) : 0; }
 
+// Bit writer of the baseline re-encoder (the hot loop of the .lep -> JPEG direction on the host): 64-bit accumulator,
+// four bytes leave at a time unless one of them is 0xFF and needs its stuffed zero (recoder.cc:144-185).
+struct FastWriter {
+    std::vector<uint8_t>& out;
+    uint8_t* p;
+    uint8_t* lim;
+    uint64_t acc = 0;
+    int nbits = 0;
+    explicit FastWriter(std::vector<uint8_t>& o, size_t expect) : out(o) {
+        const size_t used = out.size();
+        out.resize(used + expect + 4096);
+        p = out.data() + used; lim = out.data() + out.size();
+    }
+    inline void room(size_t n) {
+        if ((size_t)(lim - p) >= n) return;
+        const size_t used = (size_t)(p - out.data());
+        out.resize(out.size() * 2 + n + 4096);
+        p = out.data() + used; lim = out.data() + out.size();
+    }
+    inline void raw(uint8_t b) { room(1); *p++ = b; }
+    inline void put(uint32_t v, int n) {          // n <= 32, v < 2^n
+        acc = (acc << n) | v;
+        nbits += n;
+        if (nbits >= 32) {
+            const uint32_t w = (uint32_t)(acc >> (nbits - 32));
+            nbits -= 32;
+            room(8);
+            if (((w & 0x7f7f7f7fu) + 0x01010101u) & w & 0x80808080u) {          // some byte is 0xFF (exact test: b == 0xFF <=> (b & 0x7f) + 1 carries into a set top bit)
+                for (int sh = 24; sh >= 0; sh -= 8) {
+                    const uint8_t b = (uint8_t)(w >> sh);
+                    *p++ = b;
+                    if (b == 0xFF) *p++ = 0x00;
+                }
+            } else {
+                p[0] = (uint8_t)(w >> 24); p[1] = (uint8_t)(w >> 16); p[2] = (uint8_t)(w >> 8); p[3] = (uint8_t)w;
+                p += 4;
+            }
+        }
+    }
+    inline void flush_bytes() {
+        room(16);
+        while (nbits >= 8) {
+            const uint8_t b = (uint8_t)(acc >> (nbits - 8));
+            *p++ = b;
+            if (b == 0xFF) *p++ = 0x00;
+            nbits -= 8;
+        }
+    }
+    // abitwriter::pad (bitops.hh:168-175): successive bits of `fill`, LSB first
+    inline void pad(uint8_t fill) {
+        int offset = 1;
+        while (nbits & 7) { put((fill & offset) ? 1 : 0, 1); offset <<= 1; }
+        flush_bytes();
+    }
+    inline void finish() { out.resize((size_t)(p - out.data())); }
+};
+
+// zig-zag-ordered bit mask of the non-zero coefficients of an AlignedBlock: SSE2 compare + a fixed bit permutation
+struct ZzPerm {
+    uint64_t t[8][256];
+    ZzPerm() {
+        int al2zz[64];
+        for (int z = 0; z < 64; ++z) al2zz[k_zigzag_to_aligned[z]] = z;
+        for (int byte = 0; byte < 8; ++byte)
+            for (int v = 0; v < 256; ++v) {
+                uint64_t m = 0;
+                for (int b = 0; b < 8; ++b) if (v & (1 << b)) m |= 1ull << al2zz[byte * 8 + b];
+                t[byte][v] = m;
+            }
+    }
+};
+const ZzPerm g_zzperm;
+
+inline uint64_t nonzero_mask_zigzag(const int16_t* blk) {
+    const __m128i zero = _mm_setzero_si128();
+    uint64_t zmask = 0;                                   // bit a: coefficient a (aligned order) IS zero
+    for (int i = 0; i < 4; ++i) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i + 8));
+        const __m128i eq = _mm_packs_epi16(_mm_cmpeq_epi16(a, zero), _mm_cmpeq_epi16(b, zero));
+        zmask |= (uint64_t)(uint32_t)_mm_movemask_epi8(eq) << (16 * i);
+    }
+    const uint64_t nz = ~zmask;
+    uint64_t m = 0;
+    for (int byte = 0; byte < 8; ++byte) m |= g_zzperm.t[byte][(nz >> (8 * byte)) & 255];
+    return m;
+}
+
 }  // namespace
 
 bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err);
@@ -244,7 +334,7 @@ bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vec
     out.push_back(0xFF); out.push_back(0xD8);
     out.insert(out.end(), h.begin(), h.begin() + hpos);
 
-    BitWriter bw(out);
+    FastWriter bw(out, (size_t)lf.jpeg_size);
     int lastdc[4] = {0, 0, 0, 0};
     const int mcuc = j.mcuc;
     unsigned rst_written = 0;
@@ -260,30 +350,29 @@ bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vec
         lastdc[c] = dc;
         int s = bitlen16(diff > 0 ? diff : -diff);
         int nb = diff > 0 ? diff : (diff - 1) + (1 << s);
-        bw.put(dct.ecode[s], dct.elen[s]);
-        bw.put((uint32_t)nb, s);
-        // AC
-        int end = 63;
-        while (end > 0 && blk[k_zigzag_to_aligned[end]] == 0) --end;
-        int z = 0;
-        for (int bpos = 1; bpos <= end; ++bpos) {
-            const int v = blk[k_zigzag_to_aligned[bpos]];
-            if (v == 0) { ++z; continue; }
-            while (z & 0xf0) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
+        bw.put(((uint32_t)dct.ecode[s] << s) | (uint32_t)nb, dct.elen[s] + s);
+        // AC: walk the non-zero coefficients in zig-zag order
+        uint64_t m = nonzero_mask_zigzag(blk) >> 1;           // bit k: zig-zag position k + 1
+        int prev = 0;
+        while (m) {
+            const int z = __builtin_ctzll(m) + 1;
+            m &= m - 1;
+            int run = z - prev - 1;
+            prev = z;
+            while (run >= 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); run -= 16; }
+            const int v = blk[k_zigzag_to_aligned[z]];
             s = bitlen16(v > 0 ? v : -v);
             nb = v > 0 ? v : (v - 1) + (1 << s);
-            const int hc = ((z & 0xf) << 4) + s;
-            bw.put(act.ecode[hc], act.elen[hc]);
-            bw.put((uint32_t)nb, s);
-            z = 0;
+            const int hc = (run << 4) + s;
+            bw.put(((uint32_t)act.ecode[hc] << s) | (uint32_t)nb, act.elen[hc] + s);
         }
-        if (end != 63) bw.put(act.ecode[0x00], act.elen[0x00]);
+        if (prev != 63) bw.put(act.ecode[0x00], act.elen[0x00]);
     };
     auto restart = [&]() {      // recoder.cc:381-397
         bw.pad((uint8_t)j.padbit);
         if (!rst_limited || rst_written < j.rst_cnt[0]) {
-            out.push_back(0xFF);
-            out.push_back((uint8_t)(0xD0 + (rst_written & 7)));
+            bw.raw(0xFF);
+            bw.raw((uint8_t)(0xD0 + (rst_written & 7)));
             rst_written++;
         }
         rstw = rsti;
@@ -319,8 +408,9 @@ bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vec
     // trailing bogus restart markers of the (only) scan (recoder.cc:839-848)
     if (!j.rst_err.empty()) {
         const unsigned cum = rsti ? (unsigned)(j.mcuh * j.mcuv - 1) / rsti : 0;
-        for (unsigned i = 0; i < j.rst_err[0]; ++i) { out.push_back(0xFF); out.push_back((uint8_t)(0xD0 + ((cum + i) & 7))); }
+        for (unsigned i = 0; i < j.rst_err[0]; ++i) { bw.raw(0xFF); bw.raw((uint8_t)(0xD0 + ((cum + i) & 7))); }
     }
+    bw.finish();
     out.insert(out.end(), h.begin() + hpos, h.end());      // header data after the first SOS, if any
     // everything before the garbage is bounded to (original size - garbage size): for truncated originals the scan is
     // cut exactly where the file ended (str_out->set_bound, recoder.cc:699-700, 880-886)
