@@ -28,8 +28,8 @@ struct lepb200_codec {
     int chunk_images = 4096;
     size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk (device memory budget: two contexts in flight)
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
-    void* arena[3] = {nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
-    size_t arena_cap[3] = {0, 0, 0};
+    void* arena[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
+    size_t arena_cap[4] = {0, 0, 0, 0};
     std::vector<std::vector<uint8_t>> outputs;
     std::string err;
     // timing of the last call (seconds): parse+huffman, gpu (upload+kernel+fetch), container
@@ -107,7 +107,7 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
 
 void lepb200_codec_destroy(lepb200_codec* c) {
     if (!c) return;
-    for (int s = 0; s < 3; ++s) if (c->arena[s]) lepb200_pinned_free(c->arena[s]);
+    for (int s = 0; s < 4; ++s) if (c->arena[s]) lepb200_pinned_free(c->arena[s]);
     for (int s = 0; s < 3; ++s) lepb200_destroy(c->ctx2[s]);
     delete c;
 }
@@ -452,8 +452,8 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             base[i] = total;
             for (int q = 0; q < s.lf[i]->j.ncmp; ++q) total += (plane_bytes(s.lf[i]->j, q) + 255) & ~size_t(255);
         }
-        if (!reserve_arena(c, k % 3, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
-        uint8_t* arena = static_cast<uint8_t*>(c->arena[k % 3]);
+        if (!reserve_arena(c, k % 4, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+        uint8_t* arena = static_cast<uint8_t*>(c->arena[k % 4]);
         int nseg_total = 0;
         for (int i = 0; i < m; ++i) {
             LepFile& lf = *s.lf[i];
@@ -481,11 +481,23 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         std::lock_guard<std::mutex> g(tmu);
         c->t_front += now_s() - t0;
     };
-    auto gpu = [&](int k) {
+    auto gpu = [&](int k) {               // H2D of the streams + decode kernel
+        double t0 = now_s();
+        DChunk& s = cs[k];
+        lepb200_ctx* ctx = c->ctx2[k % 3];
+        if (s.gpu_rc == 0 && !s.imgs.empty()) {
+            s.gpu_rc = lepb200_decode_upload(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data());
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_launch(ctx);
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_sync(ctx);
+        }
+        std::lock_guard<std::mutex> g(tmu);
+        c->t_gpu += now_s() - t0;
+    };
+    auto fetch = [&](int k) {             // D2H of the planes (128 B per block), overlapping the next chunk's kernel
         double t0 = now_s();
         DChunk& s = cs[k];
         if (s.gpu_rc == 0 && !s.imgs.empty())
-            s.gpu_rc = lepb200_decode_images(c->ctx2[k % 3], s.imgs.data(), (int)s.imgs.size(), s.streams.data(), s.seg_status.data());
+            s.gpu_rc = lepb200_decode_fetch(c->ctx2[k % 3], s.imgs.data(), (int)s.imgs.size(), s.seg_status.data());
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -505,14 +517,15 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         std::lock_guard<std::mutex> g(tmu);
         c->t_back += now_s() - t0;
     };
-    for (int step = 0; step < nchunks + 2; ++step) {
-        std::thread tf, tg, tb;
-        if (step < nchunks) tf = std::thread(front, step);
-        if (step - 1 >= 0 && step - 1 < nchunks) tg = std::thread(gpu, step - 1);
-        if (step - 2 >= 0 && step - 2 < nchunks) tb = std::thread(back, step - 2);
-        if (tf.joinable()) tf.join();
-        if (tg.joinable()) tg.join();
-        if (tb.joinable()) tb.join();
+    // 4-stage lock-step pipeline: chunk k on context k % 3 (kernel, D2H) and pinned plane arena k % 4 (front .. back)
+    for (int step = 0; step < nchunks + 3; ++step) {
+        std::thread th[4];
+        auto in = [&](int k) { return k >= 0 && k < nchunks; };
+        if (in(step)) th[0] = std::thread(front, step);
+        if (in(step - 1)) th[1] = std::thread(gpu, step - 1);
+        if (in(step - 2)) th[2] = std::thread(fetch, step - 2);
+        if (in(step - 3)) th[3] = std::thread(back, step - 3);
+        for (auto& t : th) if (t.joinable()) t.join();
     }
     int rc = LEPB200_OK;
     for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
