@@ -184,8 +184,9 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
         // ---- every lane: the symbol that would start at bit offset p + lane
         const uint32_t off = p + (uint32_t)lane;
         const uint32_t k = off >> 5, sh = off & 31;
-        const uint32_t w0 = be_word(words, k, nwords), w1 = be_word(words, k + 1, nwords), w2 = be_word(words, k + 2, nwords);
-        const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);    // 64 bits from `off`, MSB first
+        const uint32_t w0 = be_word(words, k, nwords), w1 = be_word(words, k + 1, nwords);
+        const uint32_t hi = __funnelshift_l(w1, w0, sh);                     // 32 bits from `off`, MSB first: a code (<= 16 bits)
+                                                                             // and its magnitude bits (<= 16) always fit
         const bool is_dc = lane == 0 && bpos == 0;
         const HuffTableDev* tab = is_dc ? dct : act;
         int len = 0, sym = 0;
@@ -204,9 +205,8 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
         int val = 0;
         bool bad = len == 0 || sz > 16;
         if (!bad && sz) {
-            // sz magnitude bits follow the code: bits [len, len+sz) of the 64-bit window
-            const unsigned long long win = ((unsigned long long)hi << 32) | lo;
-            const int nb = (int)((win << len) >> (64 - sz));
+            // sz magnitude bits follow the code: bits [len, len+sz) of the window
+            const int nb = (int)((hi << len) >> (32 - sz));
             val = nb >= (1 << (sz - 1)) ? nb : nb + 1 - (1 << sz);
         }
         // info: [0,6) total length (0 = invalid) | [6,10) run | [10,15) size | [16,32) value
