@@ -195,3 +195,24 @@ def test_file_level_compress_both_huffman_paths(gpu_huffman):
         assert st == 0, (n, st)
         assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
     fc.close()
+
+
+def test_cli_jpg_to_lep_and_back(tmp_path):
+    """`lepton-b200 in.jpg out.lep` writes the reference CLI's bytes; `lepton-b200 out.lep back.jpg` restores the input
+    (the north_star's `lepton` command-line surface, src/lepton/jpgcoder.cc:988-1219,1528)."""
+    import os
+    import subprocess
+    from helpers import GOLDEN
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "lepton_b200", "bin", "lepton-b200")
+    assert os.path.exists(exe), "build() did not produce the CLI"
+    for name in ("androidcrop.jpg", "iphoneprogressive.jpg", "gray2sf.jpg"):
+        src = os.path.join(GOLDEN, name)
+        lep, back = str(tmp_path / "o.lep"), str(tmp_path / "o.jpg")
+        r = subprocess.run([exe, "-skipverify", src, lep], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert open(lep, "rb").read() == open(os.path.join(GOLDEN, name[:-4] + ".lep"), "rb").read(), name
+        r = subprocess.run([exe, lep, back], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert open(back, "rb").read() == open(src, "rb").read(), name
+    r = subprocess.run([exe, "-socket", os.path.join(GOLDEN, "androidcrop.jpg")], capture_output=True)
+    assert r.returncode == 13                     # service modes are outside this build: refused, not ignored
