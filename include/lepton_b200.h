@@ -151,6 +151,32 @@ int lepb200_huffman_stage_upload(lepb200_ctx* ctx, size_t offset, size_t bytes);
  * non-NULL (placeholder scans): copy these host planes into the image's slot first. */
 int lepb200_encode_upload_resident(lepb200_ctx* ctx, const lepb200_image* images, int nimages);
 
+/* ---- GPU baseline Huffman ENCODE for the decode direction (reference: recode_row_range /
+ * recode_one_mcu_row / encode_block_seq / escape_0xff_huffman_and_write, src/lepton/recoder.cc:472-545,316-410,245-313,
+ * 144-185).  After lepb200_decode_launch on the same context, image i of the batch (single interleaved or grey baseline
+ * scan, not truncated) gets the entropy-coded bytes of its scan -- stuffed, with restart markers -- produced on the
+ * device from the resident planes, one warp per thread-segment, so the D2H copy carries JPEG bytes, not 128 B per block.
+ * scan_bytes == 0 skips an image (the caller re-encodes it on the host from the fetched planes). */
+typedef struct lepb200_henc_segment {
+    int32_t mcu_row_start, mcu_row_end;   /* MCU rows [start, end) of the thread-segment */
+    int16_t last_dc[3];                   /* ThreadHandoff::last_dc */
+    uint8_t overhang_bits, overhang_byte; /* ThreadHandoff::num_overhang_bits / overhang_byte */
+    uint32_t expect_bytes;                /* ThreadHandoff::segment_size (file bytes the segment covers); ignored for the last one */
+} lepb200_henc_segment;
+typedef struct lepb200_henc_image {
+    int32_t rsti, padbit;
+    int32_t H[3], V[3];                   /* sampling factors (frame order == scan order) */
+    lepb200_hufftable dc[3], ac[3];       /* tables selected by the SOS for each component */
+    int32_t nseg;
+    lepb200_henc_segment seg[LEPB200_MAX_SEGMENTS];
+    uint32_t scan_bytes;                  /* bytes the scan must produce (file size - markers - trailer); 0 = skip this image */
+    /* outputs of lepb200_huffman_encode_fetch */
+    const uint8_t* data;                  /* HOST (pinned, owned by the context): scan_bytes bytes */
+    int32_t status;                       /* 0 ok; 1 a segment did not produce the byte count its handoff promises */
+} lepb200_henc_image;
+int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* images, int nimages);   /* queues the kernel (async) */
+int lepb200_huffman_encode_fetch(lepb200_ctx* ctx, lepb200_henc_image* images, int nimages);      /* waits, D2H of the scan bytes */
+
 /* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */
 float lepb200_last_kernel_ms(lepb200_ctx* ctx);
 /* Encode only: device time of kernel A (symbolisation + model update) within the last launch; the rest of
@@ -200,6 +226,8 @@ void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
 void lepb200_codec_set_gpu_huffman(lepb200_codec* codec, int on);
 /* device milliseconds of the last chunk's GPU Huffman-decode kernel (diagnostic) */
 double lepb200_codec_last_huffman_ms(const lepb200_codec* codec);
+/* files of the last lepb200_decompress_leps call whose scan was Huffman-encoded on the device (the rest went through the host re-encoder) */
+int lepb200_codec_last_gpu_recoded(const lepb200_codec* codec);
 /* summed seconds spent by the last call's stages (they overlap): JPEG parse + Huffman decode | H2D + kernel + D2H | container writing */
 void lepb200_codec_last_timing(const lepb200_codec* codec, double* front_s, double* gpu_s, double* back_s);
 /* n JPEG files in, n .lep files out */

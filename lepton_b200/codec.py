@@ -316,6 +316,8 @@ def _bind_file_api(L):
     L.lepb200_codec_set_gpu_huffman.restype = None
     L.lepb200_codec_last_huffman_ms.argtypes = [vp]
     L.lepb200_codec_last_huffman_ms.restype = ctypes.c_double
+    L.lepb200_codec_last_gpu_recoded.argtypes = [vp]
+    L.lepb200_codec_last_gpu_recoded.restype = ctypes.c_int
     L.lepb200_compress_jpegs.argtypes = [vp, ctypes.POINTER(_Buffer), ctypes.c_int, ctypes.POINTER(_Result)]
     L.lepb200_compress_jpegs.restype = ctypes.c_int
     L.lepb200_host_jpeg_open.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
@@ -519,6 +521,10 @@ class LeptonB200FileCodec:
         if not copy:
             return [(res[i].status, res[i].len) for i in range(n)]
         return [(res[i].status, ctypes.string_at(res[i].data, res[i].len) if res[i].len else b"") for i in range(n)]
+
+    @property
+    def last_gpu_recoded(self):
+        return int(self._L.lepb200_codec_last_gpu_recoded(self._c))
 
     def last_timing(self):
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()

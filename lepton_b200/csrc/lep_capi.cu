@@ -16,6 +16,7 @@
 #include "lep_decode.cu"
 #include "lep_decode_thread.cu"
 #include "lep_huff.cu"
+#include "lep_huffenc.cu"
 
 using namespace lepb200;
 
@@ -74,6 +75,11 @@ struct lepb200_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     std::string err;
     DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_images, d_segs, d_order, d_counter, d_models, d_rows;
+    DevBuf d_henc_out, d_henc_imgs, d_henc_segs, d_henc_tabs;
+    HostBuf h_henc_out, h_henc_segs;
+    std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
+    std::vector<int> henc_seg_first;      // per image: index of its first segment record
+    int henc_nseg = 0;
     HostBuf h_segs, h_dense, h_stage, h_hjobs;
     size_t resident_plane_total = 0;
     int resident_images = 0;
@@ -329,7 +335,7 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
+    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
         b->release();
     for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs}) b->release();
     cudaEventDestroy(ctx->ev0);
@@ -681,6 +687,116 @@ int lepb200_encode_images(lepb200_ctx* ctx, const lepb200_image* images, int nim
     return lepb200_encode_fetch(ctx, out);
 }
 
+// ------------------------------------------------------------------------------------------------ GPU Huffman encode
+static bool build_enc_table(const lepb200_hufftable& in, HEncTable& t) {
+    memset(&t, 0, sizeof(t));
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        for (int i = 0; i < in.bits[len]; ++i, ++k, ++code) {
+            if (k >= 256) return false;
+            t.code[in.vals[k]] = (uint16_t)code;
+            t.len[in.vals[k]] = (uint8_t)len;
+        }
+        if (code > (1 << len)) return false;
+        code <<= 1;
+    }
+    return true;
+}
+
+int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n) {
+    if (!ctx || !imgs || n <= 0) return LEPB200_ERR_INVALID;
+    if (!ctx->launched || ctx->is_encode || n != (int)ctx->images.size()) { ctx->err = "huffman_encode_resident: needs the decode batch just launched on this context"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    std::vector<HEncImage> hi(n);
+    std::vector<HEncSeg> hs;
+    std::vector<HEncTable> tabs;
+    std::vector<const lepb200_hufftable*> seen;
+    auto table_index = [&](const lepb200_hufftable& t, bool& ok) -> int {
+        for (size_t q = 0; q < seen.size(); ++q) if (!memcmp(seen[q], &t, sizeof(t))) return (int)q;
+        HEncTable e;
+        ok = build_enc_table(t, e) && ok;
+        tabs.push_back(e);
+        seen.push_back(&t);
+        return (int)tabs.size() - 1;
+    };
+    ctx->henc_off.assign(n, SIZE_MAX);
+    ctx->henc_seg_first.assign(n, -1);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        lepb200_henc_image& im = imgs[i];
+        im.data = nullptr; im.status = 0;
+        HEncImage& d = hi[i];
+        memset(&d, 0, sizeof(d));
+        if (im.scan_bytes == 0) continue;
+        const ImageDesc& g = ctx->images[i];
+        bool ok = im.nseg >= 1 && im.nseg <= LEPB200_MAX_SEGMENTS && g.ncmp >= 1 && g.ncmp <= 3;
+        d.ncmp = g.ncmp; d.mcuv = g.mcuv; d.rsti = im.rsti; d.padbit = im.padbit; d.scan_len = im.scan_bytes;
+        for (int c = 0; ok && c < g.ncmp; ++c) {
+            ok = im.H[c] >= 1 && im.H[c] <= 2 && im.V[c] >= 1 && im.V[c] <= 2 && g.bch[c] % im.H[c] == 0 && g.bcv[c] == g.mcuv * im.V[c];
+            d.H[c] = im.H[c]; d.V[c] = im.V[c]; d.bch[c] = g.bch[c]; d.plane[c] = g.plane[c];
+            if (ok) { d.dc_tab[c] = table_index(im.dc[c], ok); d.ac_tab[c] = table_index(im.ac[c], ok); }
+        }
+        if (ok) {
+            d.mcuh = g.bch[0] / im.H[0];
+            for (int c = 1; ok && c < g.ncmp; ++c) ok = g.bch[c] / im.H[c] == d.mcuh;
+        }
+        if (!ok) { im.status = LEPB200_ST_NOT_HANDLED; im.scan_bytes = 0; continue; }
+        ctx->henc_off[i] = total;
+        ctx->henc_seg_first[i] = (int)hs.size();
+        uint32_t off = 0;
+        for (int k = 0; k < im.nseg; ++k) {
+            HEncSeg sg;
+            memset(&sg, 0, sizeof(sg));
+            sg.image = i; sg.my0 = im.seg[k].mcu_row_start; sg.my1 = im.seg[k].mcu_row_end;
+            for (int c = 0; c < 3; ++c) sg.lastdc[c] = im.seg[k].last_dc[c];
+            sg.ov_bits = im.seg[k].overhang_bits; sg.ov_byte = im.seg[k].overhang_byte;
+            sg.out_off = off; sg.expect = im.seg[k].expect_bytes; sg.is_last = k + 1 == im.nseg;
+            off += im.seg[k].expect_bytes;
+            hs.push_back(sg);
+        }
+        total += align_up((size_t)im.scan_bytes + 16, 256);
+    }
+    ctx->henc_nseg = (int)hs.size();
+    if (hs.empty()) return LEPB200_OK;
+    CK(ctx->d_henc_out.reserve(total + 256));
+    CK(ctx->d_henc_imgs.reserve(sizeof(HEncImage) * n));
+    CK(ctx->d_henc_segs.reserve(sizeof(HEncSeg) * hs.size()));
+    CK(ctx->d_henc_tabs.reserve(sizeof(HEncTable) * std::max<size_t>(1, tabs.size())));
+    for (int i = 0; i < n; ++i) if (ctx->henc_off[i] != SIZE_MAX) hi[i].out = (unsigned long long)(uintptr_t)ctx->d_henc_out.p + ctx->henc_off[i];
+    // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may go out of scope
+    CK(cudaMemcpyAsync(ctx->d_henc_imgs.p, hi.data(), sizeof(HEncImage) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_henc_segs.p, hs.data(), sizeof(HEncSeg) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_henc_tabs.p, tabs.data(), sizeof(HEncTable) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const int nseg = (int)hs.size();
+    lep_huffencode_kernel<<<(nseg + HENC_WARPS - 1) / HENC_WARPS, HENC_WARPS * 32, 0, ctx->stream>>>(
+        static_cast<const HEncImage*>(ctx->d_henc_imgs.p), static_cast<HEncSeg*>(ctx->d_henc_segs.p), nseg, static_cast<const HEncTable*>(ctx->d_henc_tabs.p));
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    return LEPB200_OK;
+}
+
+int lepb200_huffman_encode_fetch(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n) {
+    if (!ctx || !imgs || n != (int)ctx->henc_off.size()) return LEPB200_ERR_INVALID;
+    if (ctx->henc_nseg == 0) return LEPB200_OK;
+    CK(cudaSetDevice(ctx->device));
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) if (ctx->henc_off[i] != SIZE_MAX) total = std::max(total, ctx->henc_off[i] + imgs[i].scan_bytes);
+    CK(ctx->h_henc_out.reserve(total + 256));
+    CK(ctx->h_henc_segs.reserve(sizeof(HEncSeg) * ctx->henc_nseg));
+    CK(cudaMemcpyAsync(ctx->h_henc_out.p, ctx->d_henc_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_henc_segs.p, ctx->d_henc_segs.p, sizeof(HEncSeg) * ctx->henc_nseg, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const HEncSeg* hs = static_cast<const HEncSeg*>(ctx->h_henc_segs.p);
+    for (int i = 0; i < n; ++i) {
+        if (ctx->henc_off[i] == SIZE_MAX) continue;
+        imgs[i].data = static_cast<const uint8_t*>(ctx->h_henc_out.p) + ctx->henc_off[i];
+        int st = 0;
+        for (int k = 0; k < imgs[i].nseg; ++k) if (hs[ctx->henc_seg_first[i] + k].status) st = 1;
+        imgs[i].status = st;
+    }
+    return LEPB200_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ decode
 int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in) {
     if (!ctx || !in) return LEPB200_ERR_INVALID;
@@ -744,8 +860,9 @@ int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nima
     CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->stream));
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < images[i].ncmp; ++c)
-            CK(cudaMemcpyAsync(images[i].planes[c], reinterpret_cast<const void*>(ctx->images[i].plane[c]), ctx->plane_bytes[(size_t)i * 3 + c],
-                               cudaMemcpyDeviceToHost, ctx->stream));
+            if (images[i].planes[c])        // NULL: the caller does not need this plane on the host (scan re-encoded on the device)
+                CK(cudaMemcpyAsync(images[i].planes[c], reinterpret_cast<const void*>(ctx->images[i].plane[c]), ctx->plane_bytes[(size_t)i * 3 + c],
+                                   cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     uint64_t alg = 0;

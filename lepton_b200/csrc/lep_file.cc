@@ -34,6 +34,7 @@ struct lepb200_codec {
     std::string err;
     // timing of the last call (seconds): parse+huffman, gpu (upload+kernel+fetch), container
     double t_front = 0, t_gpu = 0, t_back = 0, t_huff_ms = 0;
+    std::atomic<int> n_gpu_recoded{0};   // files of the last decompress call whose scan was Huffman-encoded on the device
 };
 
 namespace {
@@ -124,6 +125,7 @@ uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
 double lepb200_codec_last_huffman_ms(const lepb200_codec* c) { return c ? c->t_huff_ms : -1.0; }
+int lepb200_codec_last_gpu_recoded(const lepb200_codec* c) { return c ? c->n_gpu_recoded.load() : 0; }
 
 void lepb200_codec_last_timing(const lepb200_codec* c, double* front_s, double* gpu_s, double* back_s) {
     if (!c) return;
@@ -415,21 +417,46 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     if (!c || !leps || !out || n <= 0) return LEPB200_ERR_INVALID;
     c->err.clear();
     c->t_front = c->t_gpu = c->t_back = 0;
-    // the way back moves the coefficient planes over PCIe (128 B per block) and re-encodes Huffman on host threads, so its
-    // chunks are smaller: three pinned plane arenas rotate through front / gpu / back
-    const int chunk = std::max(1, std::min(c->chunk_images, 1024));
-    const int nchunks = (n + chunk - 1) / chunk;
+    c->n_gpu_recoded = 0;
+    // ---- containers: fixed header, zlib'd JPEG header, handoffs, demux of the segment streams (all files, host threads)
+    double t_parse = now_s();
+    std::vector<std::unique_ptr<LepFile>> all(n);
+    std::vector<size_t> pbytes(n, 0);
+    parallel_for(n, c->nthreads, [&](int i) {
+        all[i].reset(new LepFile());
+        if (read_lep(leps[i].data, leps[i].len, *all[i]))
+            for (int q = 0; q < all[i]->j.ncmp; ++q) pbytes[i] += (plane_bytes(all[i]->j, q) + 255) & ~size_t(255);
+    });
+    c->t_front += now_s() - t_parse;
+    // chunks of up to 14 GB of coefficient planes (device memory: three contexts in flight).  The planes stay on the device
+    // for every file whose scan the GPU can re-encode; only the others need a pinned host arena (128 B per block over PCIe)
+    std::vector<std::pair<int, int>> ranges;
+    {
+        const size_t cap = size_t(14) << 30;
+        const int chunk_max = std::max(1, c->chunk_images);
+        int b0 = 0;
+        size_t acc = 0;
+        for (int i = 0; i < n; ++i) {
+            if (i > b0 && (i - b0 >= chunk_max || acc + pbytes[i] > cap)) { ranges.emplace_back(b0, i); b0 = i; acc = 0; }
+            acc += pbytes[i];
+        }
+        ranges.emplace_back(b0, n);
+    }
+    const int nchunks = (int)ranges.size();
     c->outputs.assign(n, std::vector<uint8_t>());
     std::vector<int> status(n, 0);
     struct DChunk {
         int begin = 0, end = 0;
         std::vector<std::unique_ptr<LepFile>> lf;
-        std::vector<std::array<int16_t*, 4>> planes;
+        std::vector<std::array<int16_t*, 4>> planes;        // host planes of the files the host re-encodes (else null)
         std::vector<lepb200_image> imgs;
         std::vector<int> idx;
         std::vector<lepb200_stream> streams;
         std::vector<int32_t> seg_status;
         std::vector<int> seg_base;
+        std::vector<lepb200_henc_image> henc;       // per batch image: scan re-encoded on the device when scan_bytes != 0
+        std::vector<GpuRecodeSetup> gsetup;
+        std::vector<std::vector<int16_t>> fallback;  // planes of files whose device re-encode did not check out
         int gpu_rc = 0;
     };
     std::vector<DChunk> cs(nchunks);
@@ -437,35 +464,70 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     auto front = [&](int k) {
         double t0 = now_s();
         DChunk& s = cs[k];
-        s.begin = k * chunk; s.end = std::min(n, s.begin + chunk);
+        s.begin = ranges[k].first; s.end = ranges[k].second;
         const int m = s.end - s.begin;
         s.lf.resize(m); s.planes.resize(m);
-        parallel_for(m, c->nthreads, [&](int i) {
-            s.lf[i].reset(new LepFile());
-            read_lep(leps[s.begin + i].data, leps[s.begin + i].len, *s.lf[i]);
-        });
-        size_t total = 0;
-        std::vector<size_t> base(m, 0);
         for (int i = 0; i < m; ++i) {
+            s.lf[i] = std::move(all[s.begin + i]);
             status[s.begin + i] = s.lf[i]->status;
-            if (s.lf[i]->status) continue;
-            base[i] = total;
-            for (int q = 0; q < s.lf[i]->j.ncmp; ++q) total += (plane_bytes(s.lf[i]->j, q) + 255) & ~size_t(255);
-        }
-        if (!reserve_arena(c, k % 4, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
-        uint8_t* arena = static_cast<uint8_t*>(c->arena[k % 4]);
-        int nseg_total = 0;
-        for (int i = 0; i < m; ++i) {
-            LepFile& lf = *s.lf[i];
-            if (lf.status) continue;
-            const Jpeg& j = lf.j;
-            uint8_t* p = arena + base[i];
             for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
-            for (int q = 0; q < j.ncmp; ++q) { s.planes[i][q] = reinterpret_cast<int16_t*>(p); p += (plane_bytes(j, q) + 255) & ~size_t(255); }
-            lepb200_image im;
-            fill_image(im, j, s.planes[i].data(), lf.handoffs);
-            s.imgs.push_back(im);
-            s.idx.push_back(i);
+            if (s.lf[i]->status == 0) s.idx.push_back(i);
+        }
+        const int nb = (int)s.idx.size();
+        // GPU Huffman re-encode set-up for the files that allow it (complete single-scan baseline)
+        s.henc.assign(nb, lepb200_henc_image());
+        s.gsetup.assign(nb, GpuRecodeSetup());
+        s.fallback.resize(nb);
+        parallel_for(nb, c->nthreads, [&](int q) {
+            const LepFile& lf = *s.lf[s.idx[q]];
+            lepb200_henc_image& he = s.henc[q];
+            memset(&he, 0, sizeof(he));
+            GpuRecodeSetup& gs = s.gsetup[q];
+            if (!c->gpu_huffman || !gpu_recode_setup(lf, gs)) return;
+            const Jpeg& j = lf.j;
+            he.rsti = gs.rsti; he.padbit = (uint8_t)j.padbit;
+            for (int t = 0; t < j.ncmp; ++t) {
+                he.H[t] = j.cmp[t].H; he.V[t] = j.cmp[t].V;
+                memcpy(he.dc[t].bits, gs.dc_bits[t], 17); memcpy(he.dc[t].vals, gs.dc_vals[t], 256);
+                memcpy(he.ac[t].bits, gs.ac_bits[t], 17); memcpy(he.ac[t].vals, gs.ac_vals[t], 256);
+            }
+            const int luma_mul = j.cmp[0].bcv / j.mcuv;
+            he.nseg = lf.nseg;
+            bool ok = lf.nseg >= 1 && lf.nseg <= LEPB200_MAX_SEGMENTS;
+            for (int t = 0; ok && t < lf.nseg; ++t) {
+                const Handoff& hd = lf.handoffs[t];
+                lepb200_henc_segment& sg = he.seg[t];
+                ok = hd.luma_y_start % luma_mul == 0 && hd.num_overhang_bits < 8;
+                sg.mcu_row_start = hd.luma_y_start / luma_mul;
+                sg.mcu_row_end = t + 1 < lf.nseg ? lf.handoffs[t + 1].luma_y_start / luma_mul : j.mcuv;
+                for (int q3 = 0; q3 < 3; ++q3) sg.last_dc[q3] = hd.last_dc[q3];
+                sg.overhang_bits = hd.num_overhang_bits; sg.overhang_byte = hd.overhang_byte;
+                sg.expect_bytes = hd.segment_size;
+            }
+            if (ok) he.scan_bytes = gs.scan_bytes;
+        });
+        // pinned arena for the planes of the files the host re-encodes
+        size_t total = 0;
+        std::vector<size_t> base(nb, 0);
+        for (int q = 0; q < nb; ++q) if (s.henc[q].scan_bytes == 0) { base[q] = total; total += pbytes[s.begin + s.idx[q]]; }
+        uint8_t* arena = nullptr;
+        if (total) {
+            if (!reserve_arena(c, k % 4, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+            arena = static_cast<uint8_t*>(c->arena[k % 4]);
+        }
+        int nseg_total = 0;
+        s.imgs.resize(nb);
+        for (int q = 0; q < nb; ++q) {
+            const int i = s.idx[q];
+            LepFile& lf = *s.lf[i];
+            const Jpeg& j = lf.j;
+            if (s.henc[q].scan_bytes == 0) {
+                uint8_t* p = arena + base[q];
+                for (int t = 0; t < j.ncmp; ++t) { s.planes[i][t] = reinterpret_cast<int16_t*>(p); p += (plane_bytes(j, t) + 255) & ~size_t(255); }
+            }
+            fill_image(s.imgs[q], j, s.planes[i].data(), lf.handoffs);
+            // files that stay on the device have no host planes; the batch builder only wants the pointers non-null
+            for (int t = 0; t < j.ncmp; ++t) if (!s.imgs[q].planes[t]) s.imgs[q].planes[t] = reinterpret_cast<int16_t*>(uintptr_t(1));
             for (int t = 0; t < lf.nseg; ++t) {
                 lepb200_stream st;
                 memset(&st, 0, sizeof(st));
@@ -476,8 +538,8 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             nseg_total += lf.nseg;
         }
         s.seg_status.assign(nseg_total, 0);
-        s.seg_base.assign(s.imgs.size() + 1, 0);
-        for (size_t q = 0; q < s.imgs.size(); ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+        s.seg_base.assign(nb + 1, 0);
+        for (int q = 0; q < nb; ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
         std::lock_guard<std::mutex> g(tmu);
         c->t_front += now_s() - t0;
     };
@@ -488,6 +550,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         if (s.gpu_rc == 0 && !s.imgs.empty()) {
             s.gpu_rc = lepb200_decode_upload(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data());
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_launch(ctx);
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_huffman_encode_resident(ctx, s.henc.data(), (int)s.henc.size());   // scans re-encoded from the resident planes
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_sync(ctx);
         }
         std::lock_guard<std::mutex> g(tmu);
@@ -496,8 +559,26 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     auto fetch = [&](int k) {             // D2H of the planes (128 B per block), overlapping the next chunk's kernel
         double t0 = now_s();
         DChunk& s = cs[k];
-        if (s.gpu_rc == 0 && !s.imgs.empty())
-            s.gpu_rc = lepb200_decode_fetch(c->ctx2[k % 3], s.imgs.data(), (int)s.imgs.size(), s.seg_status.data());
+        if (s.gpu_rc == 0 && !s.imgs.empty()) {
+            lepb200_ctx* ctx = c->ctx2[k % 3];
+            s.gpu_rc = lepb200_huffman_encode_fetch(ctx, s.henc.data(), (int)s.henc.size());
+            // planes come back only for the files the host has to re-encode
+            std::vector<lepb200_image> need(s.imgs);
+            for (size_t q = 0; q < need.size(); ++q) {
+                const lepb200_henc_image& he = s.henc[q];
+                if (he.scan_bytes == 0) continue;                                  // planned for the host: arena pointers are in place
+                const int li = s.idx[q];
+                const Jpeg& j = s.lf[li]->j;
+                if (he.status == 0 && he.data) { for (int t = 0; t < 3; ++t) need[q].planes[t] = nullptr; continue; }
+                // the device re-encode did not produce the byte counts the handoffs promise: fetch the planes after all
+                size_t tot = 0;
+                for (int t = 0; t < j.ncmp; ++t) tot += plane_bytes(j, t) / 2;
+                s.fallback[q].assign(tot, 0);
+                int16_t* p = s.fallback[q].data();
+                for (int t = 0; t < j.ncmp; ++t) { s.planes[li][t] = p; need[q].planes[t] = p; p += plane_bytes(j, t) / 2; }
+            }
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_fetch(ctx, need.data(), (int)need.size(), s.seg_status.data());
+        }
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -510,7 +591,13 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
                 for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t)
                     if (s.seg_status[t]) { status[i] = s.seg_status[t]; return; }
                 std::string err;
-                if (!recode_baseline(*s.lf[li], s.planes[li].data(), c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
+                const lepb200_henc_image& he = s.henc[q];
+                const bool on_gpu = he.scan_bytes && he.status == 0 && he.data;
+                if (on_gpu) c->n_gpu_recoded++;
+                const bool ok = on_gpu
+                                    ? assemble_baseline(*s.lf[li], s.gsetup[q], he.data, c->outputs[i], err)
+                                    : recode_baseline(*s.lf[li], s.planes[li].data(), c->outputs[i], err);
+                if (!ok) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
             });
         }
         s.lf.clear();

@@ -161,6 +161,18 @@ struct LepFile {
     std::string error;
 };
 bool read_lep(const uint8_t* data, size_t n, LepFile& lf);
+// Set-up for re-encoding the scan on the GPU (lepb200_huffman_encode_resident): false when the file needs the host
+// re-encoder (progressive, truncated, several scans, scan order != frame order, restart-marker budget).
+struct GpuRecodeSetup {
+    int rsti = 0;
+    uint8_t dc_bits[3][17], dc_vals[3][256], ac_bits[3][17], ac_vals[3][256];
+    size_t hpos = 0;                 // end of the first SOS segment inside hdr
+    uint32_t scan_bytes = 0;         // entropy-coded bytes of the scan in the original file
+};
+bool gpu_recode_setup(const LepFile& lf, GpuRecodeSetup& out);
+// JPEG bytes around a scan produced elsewhere: SOI + header up to the SOS + scan + trailing restart markers + rest of the
+// header + garbage (the tail of recode_baseline_jpeg, recoder.cc:839-886).
+bool assemble_baseline(const LepFile& lf, const GpuRecodeSetup& gs, const uint8_t* scan, std::vector<uint8_t>& out, std::string& err);
 // Re-create the JPEG bytes from decoded coefficient planes (recode_baseline_jpeg, src/lepton/recoder.cc:694-889).
 bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err);
 

@@ -279,6 +279,86 @@ inline uint64_t nonzero_mask_zigzag(const int16_t* blk) {
 
 bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err);
 
+bool gpu_recode_setup(const LepFile& lf, GpuRecodeSetup& out) {
+    const Jpeg& j = lf.j;
+    if (lf.flag != 'Z' || j.jpegtype != 1 || lf.has_eee || j.early_eof || j.ncmp < 1 || j.ncmp > 3) return false;
+    const std::vector<uint8_t>& h = j.hdr;
+    struct Raw { bool set = false; uint8_t bits[17]; uint8_t vals[256]; } dc[4], ac[4];
+    size_t hpos = 0;
+    int nsos = 0;
+    out.rsti = 0; out.hpos = 0;
+    while (hpos + 4 <= h.size()) {
+        const uint8_t type = h[hpos + 1];
+        const size_t len = 2 + be16(&h[hpos + 2]);
+        if (hpos + len > h.size()) return false;
+        const uint8_t* seg = &h[hpos];
+        if (type == 0xC4) {
+            if (nsos) return false;                    // tables after the scan: general path
+            size_t p = 4;
+            while (p < len) {
+                const int tc = seg[p] >> 4, th = seg[p] & 15;
+                if (tc >= 2 || th >= 4) return false;
+                ++p;
+                if (p + 16 > len) return false;
+                Raw& t = tc ? ac[th] : dc[th];
+                int total = 0;
+                t.bits[0] = 0;
+                for (int i = 0; i < 16; ++i) { t.bits[i + 1] = seg[p + i]; total += seg[p + i]; }
+                if (total > 256 || p + 16 + total > len) return false;
+                memset(t.vals, 0, 256);
+                memcpy(t.vals, seg + p + 16, total);
+                t.set = true;
+                p += 16 + total;
+            }
+        } else if (type == 0xDD) {
+            if (nsos) return false;
+            out.rsti = be16(seg + 4);
+        } else if (type == 0xDA) {
+            if (++nsos > 1) return false;
+            const int nc = seg[4];
+            if (nc != j.ncmp || len < (size_t)(8 + 2 * nc)) return false;
+            for (int i = 0; i < nc; ++i) {
+                if (seg[5 + 2 * i] != j.cmp[i].jid) return false;       // scan order must be frame order
+                const int td = seg[6 + 2 * i] >> 4, ta = seg[6 + 2 * i] & 15;
+                if (td >= 4 || ta >= 4 || !dc[td].set || !ac[ta].set) return false;
+                memcpy(out.dc_bits[i], dc[td].bits, 17); memcpy(out.dc_vals[i], dc[td].vals, 256);
+                memcpy(out.ac_bits[i], ac[ta].bits, 17); memcpy(out.ac_vals[i], ac[ta].vals, 256);
+            }
+            out.hpos = hpos + len;
+        }
+        hpos += len;
+    }
+    if (nsos != 1) return false;
+    for (int c = 0; c < j.ncmp; ++c) if (j.cmp[c].H < 1 || j.cmp[c].H > 2 || j.cmp[c].V < 1 || j.cmp[c].V > 2) return false;
+    if (j.ncmp == 1 && (j.cmp[0].H != 1 || j.cmp[0].V != 1 || j.cmp[0].bch != j.cmp[0].nch || j.cmp[0].bcv != j.cmp[0].ncv)) return false;   // single-component scans walk nch x ncv blocks in raster order
+    // every restart marker of the scan must be wanted (truncated originals limit them, recoder.cc:381-397)
+    const unsigned nrst = out.rsti ? (unsigned)(j.mcuc - 1) / (unsigned)out.rsti : 0u;
+    if (lf.rst_cnt_set && !j.rst_cnt.empty() && j.rst_cnt[0] < nrst) return false;
+    const size_t trailing = j.rst_err.empty() ? 0 : 2 * (size_t)j.rst_err[0];
+    const size_t fixed = 2 + h.size() + j.grb.size() + trailing;
+    if ((size_t)lf.jpeg_size <= fixed) return false;
+    out.scan_bytes = (uint32_t)(lf.jpeg_size - fixed);
+    return true;
+}
+
+bool assemble_baseline(const LepFile& lf, const GpuRecodeSetup& gs, const uint8_t* scan, std::vector<uint8_t>& out, std::string& err) {
+    const Jpeg& j = lf.j;
+    const std::vector<uint8_t>& h = j.hdr;
+    out.clear();
+    out.reserve((size_t)lf.jpeg_size + 16);
+    out.push_back(0xFF); out.push_back(0xD8);
+    out.insert(out.end(), h.begin(), h.begin() + gs.hpos);
+    out.insert(out.end(), scan, scan + gs.scan_bytes);
+    if (!j.rst_err.empty()) {
+        const unsigned cum = gs.rsti ? (unsigned)(j.mcuh * j.mcuv - 1) / gs.rsti : 0;
+        for (unsigned i = 0; i < j.rst_err[0]; ++i) { out.push_back(0xFF); out.push_back((uint8_t)(0xD0 + ((cum + i) & 7))); }
+    }
+    out.insert(out.end(), h.begin() + gs.hpos, h.end());
+    out.insert(out.end(), j.grb.begin(), j.grb.end());
+    if (out.size() != lf.jpeg_size) { err = "re-created JPEG has the wrong size"; return false; }
+    return true;
+}
+
 bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err) {
     const Jpeg& j = lf.j;
     if (lf.flag != 'Z' || j.jpegtype != 1) return recode_scans(lf, planes, out, err);     // multi-scan / progressive files
