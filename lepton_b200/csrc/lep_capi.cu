@@ -801,6 +801,7 @@ int lepb200_huffman_encode_fetch(lepb200_ctx* ctx, lepb200_henc_image* imgs, int
 int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in) {
     if (!ctx || !in) return LEPB200_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    ctx->d_tokens.release();              // the encoder's token arena (the largest buffer of that direction) is not needed on the way back
     int r = build_batch(ctx, images, nimages, false, in);
     if (r) return r;
     const int nseg = (int)ctx->segs.size();
