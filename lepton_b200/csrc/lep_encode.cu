@@ -39,17 +39,15 @@ constexpr int IT_NZ = 0, IT_77 = 6, IT_HCNT = 55, IT_H = 58, IT_VCNT = 65, IT_V 
 struct EncWarpSmem {
     uint4 desc[2 * N_ITEMS];  // items of block A (ids 0..99) and block B (100..199) of the pair in flight
     uint8_t mark[QCAP];       // item id + 1 at the first queue position of each item, 0 elsewhere (kept zero between flushes)
-    int16_t rast[5][64];      // raster-order copies: three rotating buffers (A, B, left neighbour of A) + above A, above B
-    int32_t tmp[2][64];       // IDCT intermediates of A and B
-    int16_t pix[2][64];       // IDCT outputs (pixels sans DC) of A and B
+    // flat arrays addressed by integer offsets: per-lane SELECTED pointers into shared memory would be generic pointers
+    // (window base from a special register at every use)
+    int16_t rast[5 * 64];     // raster-order copies: three rotating buffers (A, B, left neighbour of A) + above A, above B
+    int32_t tmp[2 * 64];      // IDCT intermediates of A and B
+    int16_t pix[2 * 64];      // IDCT outputs (pixels sans DC) of A and B
 };
 
-struct EncShared {
-    uint32_t rcp[512];
-    uint8_t a2r[64];          // aligned -> raster and nz -> bin tables: per-lane indices, so not in constant memory
-    uint8_t nzbin[64];
-    EncWarpSmem w[ENC_WARPS_PER_CTA];
-};
+// (the CTA's shared memory is declared as separate arrays inside the kernel: members of one struct reached through a
+// reference made the compiler build generic addresses -- shared-window base from a special register -- at several uses)
 
 // ---- queue flush: expansion of the items + batched model update ---------------------------------------
 __device__ __forceinline__ uint32_t expand_item(const uint4 d, int pos) {      // pos: position relative to the item's block
@@ -139,46 +137,45 @@ __device__ __forceinline__ int coef_entries(int len) { return len == 0 ? 1 : min
 
 // ---- two blocks per warp: lanes 0..15 serve block A (x), lanes 16..31 block B (x + 1) in the lane-sparse sections ----
 // Lane-parallel 8x8 IDCT (DC forced to zero) of A on lanes 0..7 and of B on lanes 8..15.
-__device__ __forceinline__ void warp_idct_pair(const int16_t* rA, const int16_t* rB, const uint16_t* __restrict__ q, int32_t (*tmp)[64],
-                                               int16_t (*pix)[64], int lane, bool has_b) {
+__device__ __forceinline__ void warp_idct_pair(EncWarpSmem& ws, int offA, int offB, const uint16_t* __restrict__ q, int lane, bool has_b) {
     const int b = (lane >> 3) & 1, r = lane & 7;
     const bool act = lane < (has_b ? 16 : 8);
     if (act) {
-        const int16_t* rast = b ? rB : rA;
+        const int ro = b ? offB : offA;
         int32_t in[8], out[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) in[k] = (int32_t)rast[r * 8 + k] * (int32_t)q[r * 8 + k];
+        for (int k = 0; k < 8; ++k) in[k] = (int32_t)ws.rast[ro + r * 8 + k] * (int32_t)q[r * 8 + k];
         if (r == 0) in[0] = 0;
         idct_row(in, out);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tmp[b][r * 8 + k] = out[k];
+        for (int k = 0; k < 8; ++k) ws.tmp[b * 64 + r * 8 + k] = out[k];
     }
     __syncwarp();
     if (act) {
         int32_t in[8], out[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) in[k] = tmp[b][k * 8 + r];
+        for (int k = 0; k < 8; ++k) in[k] = ws.tmp[b * 64 + k * 8 + r];
         idct_col(in, out);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) pix[b][k * 8 + r] = (int16_t)out[k];
+        for (int k = 0; k < 8; ++k) ws.pix[b * 64 + k * 8 + r] = (int16_t)out[k];
     }
     __syncwarp();
 }
 
 // adv_predict_dc_pix for both halves at once (see warp_predict_dc): within a half, lanes 0..7 hold the left estimate,
-// lanes 8..15 the above one.  pix / has_left are per half; the result is uniform within a half.
-__device__ __forceinline__ DcPred warp_predict_dc_pair(const int16_t* pix, int left_v, int above_h, bool has_left, bool has_above, int q0, int lane) {
+// lanes 8..15 the above one.  po = offset of the half's pixels; has_left is per half; the result is uniform within a half.
+__device__ __forceinline__ DcPred warp_predict_dc_pair(const EncWarpSmem& ws, int po, int left_v, int above_h, bool has_left, bool has_above, int q0, int lane) {
     int est = 0;
     const int i = lane & 7, hb = lane & 16;
     if ((lane & 8) == 0) {
         if (has_left) {
-            int16_t p0 = pix[i * 8], p1 = pix[i * 8 + 1];
+            int16_t p0 = ws.pix[po + i * 8], p1 = ws.pix[po + i * 8 + 1];
             int16_t delta = (int16_t)(p0 - p1);
             est = (int16_t)((int16_t)((int16_t)left_v - half_rz16(delta)) - (int16_t)(p0 + 1024));
         }
     } else {
         if (has_above) {
-            int16_t p0 = pix[i], p1 = pix[8 + i];
+            int16_t p0 = ws.pix[po + i], p1 = ws.pix[po + 8 + i];
             int16_t delta = (int16_t)(p0 - p1);
             est = (int16_t)((int16_t)((int16_t)above_h - half_rz16(delta)) - (int16_t)(p0 + 1024));
         }
@@ -205,6 +202,31 @@ __device__ __forceinline__ DcPred warp_predict_dc_pair(const int16_t* pix, int l
     return r;
 }
 
+// NeighborSummary::set_horizontal / set_vertical on the half's pixels (see edge_pixel): l < 8 right column, else bottom row
+__device__ __forceinline__ int edge_pixel_at(const EncWarpSmem& ws, int po, int q0, int dc, int l) {
+    const int i = l & 7;
+    int16_t cur, prev;
+    if (l < 8) { cur = ws.pix[po + i * 8 + 7]; prev = ws.pix[po + i * 8 + 6]; }
+    else { cur = ws.pix[po + 56 + i]; prev = ws.pix[po + 48 + i]; }
+    const int16_t delta = (int16_t)(cur - prev);
+    const int16_t qdc = (int16_t)((uint32_t)q0 * (uint32_t)dc);
+    return (int16_t)(cur + half_rz16(delta) + 1024 + qdc);
+}
+
+// compute_lak (see lak_pred) with the blocks given as offsets into the raster buffers
+__device__ __forceinline__ int lak_pred_at(const EncWarpSmem& ws, int cur_off, int nb_off, const int32_t* __restrict__ icos, int first, int step) {
+    uint32_t pred = (uint32_t)(int32_t)ws.rast[nb_off + first] * (uint32_t)icos[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        const int32_t nbv = ws.rast[nb_off + first + i * step];
+        const int32_t t = (int32_t)ws.rast[cur_off + first + i * step] + ((i & 1) ? nbv : -nbv);
+        pred -= (uint32_t)icos[i] * (uint32_t)t;
+    }
+    const int32_t p = (int32_t)pred;
+    const int32_t t = (p + ((p >> 31) & 8191)) >> 13;
+    return div_trunc_small(t, icos[0] >> 13);
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------------
 #ifndef LEPB200_ENC_MINBLOCKS
 #define LEPB200_ENC_MINBLOCKS 7
@@ -213,15 +235,25 @@ __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32, LEPB200_ENC_MINBLOCKS)
 lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
                   int* __restrict__ work_counter, uint16_t* __restrict__ model_pool, uint8_t* __restrict__ row_pool,
                   size_t row_pool_stride, uint16_t* __restrict__ token_base) {
-    __shared__ EncShared sm;
-    const int lane = lane_id();
-    const int warp_in_cta = threadIdx.x >> 5;
+    __shared__ uint32_t s_rcp[512];
+    __shared__ uint8_t s_a2r[64];          // aligned -> raster and nz -> bin tables: per-lane indices, so not in constant memory
+    __shared__ uint8_t s_nzbin[64];
+    __shared__ EncWarpSmem s_w[ENC_WARPS_PER_CTA];
+    // read the special registers once: left to itself the compiler re-reads %tid.x / %laneid (S2R, slow) all over the
+    // block loop instead of keeping two registers
+    int lane, warp_in_cta;
+    {
+        unsigned l, t;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+        lane = (int)l; warp_in_cta = (int)(t >> 5);
+    }
     const int gwarp = blockIdx.x * ENC_WARPS_PER_CTA + warp_in_cta;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) sm.rcp[i] = i < 2 ? 0u : (uint32_t)((0x100000000ull + i - 1) / i);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) { sm.a2r[i] = c_aligned_to_raster[i]; sm.nzbin[i] = i < 50 ? c_nonzero_to_bin[i] : 0; }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_rcp[i] = i < 2 ? 0u : (uint32_t)((0x100000000ull + i - 1) / i);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { s_a2r[i] = c_aligned_to_raster[i]; s_nzbin[i] = i < 50 ? c_nonzero_to_bin[i] : 0; }
     __syncthreads();
-    const int r0 = sm.a2r[2 * lane], r1 = sm.a2r[2 * lane + 1];      // raster positions of this lane's two coefficients
-    EncWarpSmem& ws = sm.w[warp_in_cta];
+    const int r0 = s_a2r[2 * lane], r1 = s_a2r[2 * lane + 1];      // raster positions of this lane's two coefficients
+    EncWarpSmem& ws = s_w[warp_in_cta];
     uint16_t* model = model_pool + (size_t)gwarp * M_TOTAL;
     uint8_t* rowbuf = row_pool + (size_t)gwarp * row_pool_stride;
     const uint32_t lt_mask = (1u << lane) - 1;
@@ -299,18 +331,16 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 if (x + 2 < w) { ncurA = rowp[(size_t)(x + 2) * 32 + lane]; if (has_above) nabvA = abovep[(size_t)(x + 2) * 32 + lane]; }
                 if (x + 3 < w) { ncurB = rowp[(size_t)(x + 3) * 32 + lane]; if (has_above) nabvB = abovep[(size_t)(x + 3) * 32 + lane]; }
                 // ---------------- raster copies for the gathers (IDCT, Lakhani edge predictor)
-                ws.rast[ra][r0] = (int16_t)h_lo(curA); ws.rast[ra][r1] = (int16_t)h_hi(curA);
-                ws.rast[3][r0] = (int16_t)h_lo(abvA); ws.rast[3][r1] = (int16_t)h_hi(abvA);
+                ws.rast[ra * 64 + r0] = (int16_t)h_lo(curA); ws.rast[ra * 64 + r1] = (int16_t)h_hi(curA);
+                ws.rast[3 * 64 + r0] = (int16_t)h_lo(abvA); ws.rast[3 * 64 + r1] = (int16_t)h_hi(abvA);
                 if (has_b) {
-                    ws.rast[rb][r0] = (int16_t)h_lo(curB); ws.rast[rb][r1] = (int16_t)h_hi(curB);
-                    ws.rast[4][r0] = (int16_t)h_lo(abvB); ws.rast[4][r1] = (int16_t)h_hi(abvB);
+                    ws.rast[rb * 64 + r0] = (int16_t)h_lo(curB); ws.rast[rb * 64 + r1] = (int16_t)h_hi(curB);
+                    ws.rast[4 * 64 + r0] = (int16_t)h_lo(abvB); ws.rast[4 * 64 + r1] = (int16_t)h_hi(abvB);
                 }
                 __syncwarp();
                 const bool act_h = !hiB || has_b;                           // this half has a block
                 const bool has_left_h = hiB ? true : x > 0;
-                const int16_t* rcur = ws.rast[hiB ? rb : ra];
-                const int16_t* rabove = ws.rast[hiB ? 4 : 3];
-                const int16_t* rleft = ws.rast[hiB ? ra : rl];
+                const int rcur = (hiB ? rb : ra) * 64, rabove = (hiB ? 4 : 3) * 64, rleft = (hiB ? ra : rl) * 64;   // offsets into ws.rast
 
                 // ---------------- number of non-zeros in the 7x7 areas (aligned_block.hh:132-148)
                 const bool in0 = 2 * lane < 49, in1 = 2 * lane + 1 < 49;
@@ -320,16 +350,16 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 const int nz_h = hiB ? nzB : nzA;
 
                 // ---------------- pixels, DC prediction (encoder.cc:293-364) and neighbour summaries (block_context.hh:44-78)
-                warp_idct_pair(ws.rast[ra], ws.rast[rb], q, ws.tmp, ws.pix, lane, has_b);
+                warp_idct_pair(ws, ra * 64, rb * 64, q, lane, has_b);
                 const int dcA = h_hi(__shfl_sync(FULL, curA, 24)), dcB = h_hi(__shfl_sync(FULL, curB, 24));     // aligned index 49
                 const int dc_h = hiB ? dcB : dcA;
-                const int16_t* pix_h = ws.pix[hiB ? 1 : 0];
-                const int edge = act_h ? edge_pixel(pix_h, q0, dc_h, l) : 0;          // l < 8: right column, l >= 8: bottom row
+                const int pix_h = hiB ? 64 : 0;                                        // offset of this half's pixels in ws.pix
+                const int edge = act_h ? edge_pixel_at(ws, pix_h, q0, dc_h, l) : 0;    // l < 8: right column, l >= 8: bottom row
                 const int edge_from_a = __shfl_sync(FULL, edge, lane & 7);           // A's right column -> B's left neighbour
                 const int left_v_h = hiB ? edge_from_a : left_v;
                 int above_h = 0;
                 if (has_above && act_h && l >= 8) above_h = redge[(size_t)(x + (hiB ? 1 : 0)) * 8 + (l - 8)];
-                DcPred dp = warp_predict_dc_pair(pix_h, left_v_h, above_h, has_left_h, has_above, q0, lane);
+                DcPred dp = warp_predict_dc_pair(ws, pix_h, left_v_h, above_h, has_left_h, has_above, q0, lane);
                 int dc_len, dc_v;
                 {
                     const int adv = adv_unpredict(dc_h, false, dp.pred);
@@ -358,13 +388,13 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 const int ek = is_h ? l + 1 : l - 7;
                 const int ecoord = is_h ? ek : 8 * ek;
                 int ev = 0;
-                if ((is_h || is_v) && act_h) ev = rcur[ecoord];
+                if ((is_h || is_v) && act_h) ev = ws.rast[rcur + ecoord];
                 const uint32_t nzmask = __ballot_sync(FULL, ev != 0);
                 const uint32_t hm = (nzmask >> (lane & 16)) & 0x7f, vm = (nzmask >> ((lane & 16) + 8)) & 0x7f;
                 const int ne_h = __popc(hm), ne_v = __popc(vm);
                 int eprior = 0;
                 if (act_h && ((is_h && has_above) || (is_v && has_left_h)))        // one pass for both edges of both blocks
-                    eprior = lak_pred(rcur, is_h ? rabove : rleft, (is_h ? g.icos_x[c] : g.icos_y[c]) + ek * 8, ecoord, is_h ? 8 : 1);
+                    eprior = lak_pred_at(ws, rcur, is_h ? rabove : rleft, (is_h ? g.icos_x[c] : g.icos_y[c]) + ek * 8, ecoord, is_h ? 8 : 1);
                 const uint32_t lt16 = (1u << l) - 1;
                 const int ne_rem = is_h ? ne_h - __popc(hm & lt16) : ne_v - __popc(vm & ((lt16 >> 8) & 0x7f));
                 const bool ecoded = (is_h || is_v) && ne_rem > 0;
@@ -410,7 +440,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                     else if (has_left_h && !has_above) ctx = (nzl + 1) / 2;
                     else if (has_left_h && has_above) ctx = (nz_above + nzl + 2) / 4;
                     if (l < 6 && act_h) {
-                        const int bin = sm.nzbin[ctx];
+                        const int bin = s_nzbin[ctx];
                         const int idx = 5 - l;                                      // bit index, MSB first
                         ws.desc[it0 + IT_NZ + l] = make_uint4(0x80000000u, m_nz7(ci, bin, idx, nz_h >> (idx + 1)) | ((uint32_t)((nz_h >> idx) & 1) << 31), 0u, 0u);
                         ws.mark[base_h + l] = (uint8_t)(it0 + IT_NZ + l + 1);
@@ -435,7 +465,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                             const int len = min(blk ? (h ? lB1 : lB0) : (h ? lA1 : lA0), 11);
                             const int prior = h ? pr1 : pr0;
                             const int left_nz = nz - (blk ? (h ? bB1 : bB0) : (h ? bA1 : bA0));
-                            const int bin = sm.nzbin[left_nz];
+                            const int bin = s_nzbin[left_nz];
                             const int bsr = bitlen((uint32_t)min(iabs(prior), 1023));
                             const int coord = h ? r1 : r0;
                             const int it = blk * N_ITEMS + IT_77 + zz;
@@ -500,7 +530,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 // ---------------- code the queued decisions
                 status = __reduce_max_sync(FULL, status);
                 if (status != ST_OK) break;
-                flush_queue(ws, qnA + qnB, base_b, model, sm.rcp, tokens, ntok, tok_cap, lane);
+                flush_queue(ws, qnA + qnB, base_b, model, s_rcp, tokens, ntok, tok_cap, lane);
                 ndec += (unsigned long long)(qnA + qnB);
                 if (!more) break;
                 aleft = abvB; left = curB;
