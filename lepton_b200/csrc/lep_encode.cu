@@ -229,7 +229,7 @@ __device__ __forceinline__ int lak_pred_at(const EncWarpSmem& ws, int cur_off, i
 
 // ---- the kernel ---------------------------------------------------------------------------------------
 #ifndef LEPB200_ENC_MINBLOCKS
-#define LEPB200_ENC_MINBLOCKS 7
+#define LEPB200_ENC_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(ENC_WARPS_PER_CTA * 32, LEPB200_ENC_MINBLOCKS)
 lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order,
