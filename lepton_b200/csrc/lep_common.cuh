@@ -2,8 +2,8 @@
 //
 // This is a from-scratch sm_100a design of dropbox/lepton's arithmetic-coding hot path.  What is kept from
 // the reference is the *bitstream semantics* (so that .lep bytes are identical); the data layout, the work
-// decomposition (one warp per thread-segment, lane-parallel symbolisation, batched model update, uniform
-// range-coder chain) and the probability-table representation are new.
+// decomposition (one warp per thread-segment, lane-parallel symbolisation of two blocks at a time, batched model
+// update, one range-coder thread per segment) and the probability-table representation are new.
 //
 // Reference semantics cited below are relative to /root/reference.
 #pragma once

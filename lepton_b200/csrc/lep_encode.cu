@@ -1,20 +1,25 @@
-// lep_encode.cu -- sm_100a encode kernel: coefficient planes -> per-segment VP8 bool-coder streams.
+// lep_encode.cu -- sm_100a encode kernels: coefficient planes -> per-segment VP8 bool-coder streams.
 //
 // Work decomposition (new; the reference runs one CPU thread per segment, src/lepton/vp8_encoder.cc:239-445):
 //   * persistent grid, one WARP per Lepton thread-segment, segments pulled from a global work queue
-//     (largest first), the warp's 1.5 MB probability model zero-filled by the warp itself;
-//   * kernel A (lep_encode_kernel), per 8x8 block the warp works in two phases
-//       1. lane-parallel SYMBOLISATION: each lane owns two coefficients (one 32-bit word of the 128-byte
-//          AlignedBlock), computes their neighbour priors / context bins and appends their binary
-//          decisions (model index, bit) to a shared-memory queue at a prefix-sum offset.  Nothing in the
-//          encoder's context computation depends on coder state (hard part 1);
-//       2. batched MODEL UPDATE: 32 queued decisions at a time, one per lane -- parallel 16-bit loads of
-//          the adaptive counts, same-address conflicts resolved in queue order with __match_any_sync,
-//          probabilities computed per lane, counts written back; the resulting (probability, bit) TOKENS
-//          (16 bits each) are appended to the segment's token stream in HBM with coalesced 64-byte stores;
+//     (largest first), the warp's 1.58 MB probability model zero-filled by the warp itself;
+//   * kernel A (lep_encode_kernel) codes TWO blocks (x, x + 1) per iteration in two phases
+//       1. lane-parallel SYMBOLISATION.  Nothing in the encoder's context computation depends on coder state
+//          (hard part 1), so the warp computes, for both blocks, the neighbour priors /
+//          context bins of all coefficients (each lane owns two coefficients of each block: one 32-bit word of the
+//          128-byte AlignedBlock) and -- with lanes 0..15 serving block x and 16..31 block x + 1 -- the lane-sparse
+//          parts at double width: 8x8 IDCT (8 lanes per block), DC prediction (16), Lakhani edge predictors and
+//          edge counts (15).  Every coded coefficient leaves one 16-byte ITEM in shared memory;
+//       2. the FLUSH expands the items to (branch index, bit) decisions 32 at a time, one per lane: parallel 16-bit
+//          loads of the adaptive counts (next step's words prefetched), same-branch conflicts resolved in queue
+//          order in closed form (__match_any_sync + popcounts), probabilities computed per lane, counts written
+//          back; the resulting (probability, bit) TOKENS (16 bits each) go to the segment's token stream in HBM
+//          with coalesced 64-byte stores;
 //   * kernel B (lep_rangecode_kernel) runs the serial RANGE CODER chain (vpx_write,
 //     src/vp8/encoder/boolwriter.hh:48-118) with one THREAD per segment: the chain needs no memory-dependent
-//     loads any more, so 32 segments advance per warp instruction instead of one.
+//     loads any more, so 32 segments advance per warp instruction instead of one;
+//   * lep_count_kernel / lep_token_offsets_kernel size the token streams exactly when the planes came from the host
+//     (planes decoded by the GPU Huffman kernel arrive with a bound, see lep_huff.cu).
 //
 // Bit-exactness notes follow the oracle (oracle/lepton_oracle.c), which is pinned against the reference.
 #include "lep_common.cuh"

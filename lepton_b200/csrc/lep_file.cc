@@ -1,8 +1,9 @@
 // lep_file.cc -- file-level drop-in: JPEG bytes -> .lep bytes and back, batched.
 //
-// Host threads do what the reference's jpgcoder.cc does around the codec boundary (read_jpeg / decode_jpeg /
-// write_ujpg on the way in, read_ujpg / recode_baseline_jpeg on the way out); the arithmetic coding itself goes
-// through the C ABI of lep_capi.cu to the sm_100a kernels.  No CPU coder exists in this library.
+// Host threads do what the reference's jpgcoder.cc does around the codec boundary (read_jpeg / write_ujpg on the way in,
+// read_ujpg on the way out, plus decode_jpeg / recode_*_jpeg for the files the GPU Huffman kernels do not take:
+// progressive, truncated, several scans); Huffman decode / encode of complete baseline scans and the arithmetic coding
+// go through the C ABI of lep_capi.cu to the sm_100a kernels.  No CPU arithmetic coder exists in this library.
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>

@@ -6,10 +6,13 @@
 // resumable Huffman state the reference calls a ThreadHandoff (bit position, last DCs;
 // crystallize_thread_handoff, src/lepton/jpgcoder.cc:2520-2560).
 //
-// A baseline scan without restart markers is one serial bit stream, so the unit of parallelism is the image:
-// ONE THREAD PER IMAGE (a batch of thousands of files keeps the chip busy; the kernel is latency-bound per thread,
-// its duration is that of the largest file).  Semantics follow decode_jpeg / decode_block_seq
-// (jpgcoder.cc:2799-3302, :4893-4961) exactly like the host decoder in lep_jpeg.cc, against which it is tested.
+// A baseline scan without restart markers is one serial bit stream, so the unit of parallelism is the image: ONE WARP
+// PER IMAGE, whose 32 lanes decode the codewords that would start at the next 32 bit offsets while a warp-uniform walk
+// follows the true chain (see the kernel).  A batch of thousands of files keeps the chip busy: 4096 images are one wave
+// of 28 warps per SM.  Besides the Huffman state the kernel accumulates, per MCU row, an upper bound of the binary
+// decisions the Lepton coder will take, so the encoder's token streams can be laid out without a counting pass.
+// Semantics follow decode_jpeg / decode_block_seq (jpgcoder.cc:2799-3302, :4893-4961) exactly like the host decoder in
+// lep_jpeg.cc, against which it is tested.
 #include "lep_common.cuh"
 
 namespace lepb200 {
