@@ -219,3 +219,52 @@ def test_cli_jpg_to_lep_and_back(tmp_path):
         assert open(back, "rb").read() == open(src, "rb").read(), name
     r = subprocess.run([exe, "-socket", os.path.join(GOLDEN, "androidcrop.jpg")], capture_output=True)
     assert r.returncode == 13                     # service modes are outside this build: refused, not ignored
+
+
+def test_mixed_corpus_matches_reference_cli_and_round_trips(tmp_path):
+    """BASELINE config 3 in miniature: JPEGs of mixed size (incl. odd sizes), chroma subsampling, quality, with and without
+    restart markers, some progressive, some grey -- one batch through the file API.  Every .lep must equal what the
+    unmodified reference CLI (oracle/_ref/lepton, a checker) writes, and decompress must restore every input."""
+    import io
+    import os
+    import subprocess
+    from PIL import Image, ImageFile
+    from lepton_b200 import LeptonB200FileCodec
+    ImageFile.MAXBLOCK = 1 << 24
+    rng = np.random.default_rng(20240917)
+    jpegs = []
+    for k in range(36):
+        w, h = int(rng.integers(9, 700)), int(rng.integers(9, 500))
+        y, x = np.mgrid[0:h, 0:w]
+        base = (128 + 70 * np.sin(x / (5.0 + k)) + 50 * np.cos(y / (3.0 + 0.5 * k)))[..., None] + rng.normal(0, 6 + 3 * (k % 7), (h, w, 3))
+        im = Image.fromarray(np.clip(base, 0, 255).astype(np.uint8))
+        kw = dict(quality=[60, 75, 85, 95, 100][k % 5])
+        if k % 9 == 8:
+            im = im.convert("L")
+        else:
+            kw["subsampling"] = k % 3
+        if k % 4 == 3:
+            kw["restart_marker_blocks"] = 1 + k % 5
+        if k % 6 == 5:
+            kw["progressive"] = True
+        if k % 10 == 7:
+            kw["optimize"] = True
+        b = io.BytesIO()
+        im.save(b, "JPEG", **kw)
+        jpegs.append(b.getvalue())
+    fc = LeptonB200FileCodec(0, host_threads=4)
+    leps = fc.compress(jpegs)
+    assert all(st == 0 for st, _ in leps), [st for st, _ in leps]
+    ref_exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "_ref", "lepton")
+    if os.path.exists(ref_exe):
+        for k, (j, (_, lep)) in enumerate(zip(jpegs, leps)):
+            src, dst = str(tmp_path / ("i%d.jpg" % k)), str(tmp_path / ("i%d.lep" % k))
+            open(src, "wb").write(j)
+            r = subprocess.run([ref_exe, "-skipverify", "-allowprogressive", "-unjailed", src, dst], capture_output=True)
+            assert r.returncode == 0, (k, r.stderr[-200:])
+            assert lep == open(dst, "rb").read(), "file %d: .lep differs from the reference CLI's" % k
+    back = fc.decompress([l for _, l in leps])
+    for k, (j, (st, out)) in enumerate(zip(jpegs, back)):
+        assert st == 0 and out == j, k
+    assert fc.last_gpu_recoded >= 20          # the complete baseline files took the device Huffman encoder
+    fc.close()
