@@ -433,7 +433,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     // for every file whose scan the GPU can re-encode; only the others need a pinned host arena (128 B per block over PCIe)
     std::vector<std::pair<int, int>> ranges;
     {
-        const size_t cap = size_t(14) << 30;
+        const size_t cap = size_t(c->gpu_huffman ? 14 : 6) << 30;     // without the device re-encoder every plane needs pinned host memory too
         const int chunk_max = std::max(1, c->chunk_images);
         int b0 = 0;
         size_t acc = 0;
