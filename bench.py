@@ -419,6 +419,7 @@ def main():
     }
     if decode:
         line["decode"] = decode
+        line["roundtrip_pass_rate"] = decode["roundtrip_pass_rate"]       # BASELINE.json: "bit-exact round-trip pass rate"
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and os.path.exists(REF_LEPTON):
