@@ -253,6 +253,10 @@ const char* lepb200_host_lep_error(const lepb200_lep* h);
 int lepb200_host_lep_image(lepb200_lep* h, lepb200_image* img);
 int lepb200_host_lep_stream(lepb200_lep* h, int seg, const uint8_t** data, size_t* len);
 int lepb200_host_lep_recode(lepb200_lep* h, const int16_t* const planes[3], const uint8_t** data, size_t* len);
+/* host half of the device re-encode path (lepb200_huffman_encode_resident): offset and length of the scan in the original
+ * file (both 0 when the file needs the host re-encoder), and the JPEG assembled around scan bytes produced elsewhere */
+int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t* scan_bytes);
+int lepb200_host_lep_assemble(lepb200_lep* h, const uint8_t* scan, size_t scan_len, const uint8_t** data, size_t* len);
 void lepb200_host_lep_close(lepb200_lep* h);
 /* diagnostic: wall-clock seconds of the host front end alone over a batch with `threads` workers */
 double lepb200_host_frontend_seconds(const lepb200_buffer* jpegs, int n, int threads, int32_t* first_error);

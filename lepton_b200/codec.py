@@ -440,6 +440,20 @@ class HostLep:
                          qtables_zigzag=[[im.qtable_zigzag[c][i] for i in range(64)] for c in range(im.ncmp)],
                          planes=planes, luma_y_start=[im.luma_y_start[s] for s in range(im.nseg)])
 
+    def scan_layout(self):
+        """(offset, length) of the entropy-coded scan in the original JPEG, (0, 0) if the host has to re-encode it."""
+        off, n = ctypes.c_uint32(), ctypes.c_uint32()
+        if self._L.lepb200_host_lep_scan_layout(self._h, ctypes.byref(off), ctypes.byref(n)) != 0:
+            raise LeptonB200Error("host_lep_scan_layout failed")
+        return off.value, n.value
+
+    def assemble(self, scan: bytes) -> bytes:
+        """JPEG bytes around a scan that was Huffman-encoded elsewhere (the device)."""
+        d, n = ctypes.c_void_p(), ctypes.c_size_t()
+        if self._L.lepb200_host_lep_assemble(self._h, scan, len(scan), ctypes.byref(d), ctypes.byref(n)) != 0:
+            raise LeptonB200Error("host_lep_assemble failed: " + self._L.lepb200_host_lep_error(self._h).decode())
+        return ctypes.string_at(d, n.value)
+
     def streams(self, nseg: int):
         out = []
         for s in range(nseg):

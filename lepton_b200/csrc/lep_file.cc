@@ -661,6 +661,26 @@ int lepb200_host_lep_recode(lepb200_lep* h, const int16_t* const planes[3], cons
     *len = h->out.size();
     return LEPB200_OK;
 }
+// Host half of the device re-encode path: where the scan lies in the original file (0 = the file needs the host
+// re-encoder) and the assembly of the JPEG around scan bytes produced elsewhere.
+int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t* scan_bytes) {
+    if (!h || h->lf.status || !scan_offset || !scan_bytes) return LEPB200_ERR_INVALID;
+    GpuRecodeSetup gs;
+    if (!gpu_recode_setup(h->lf, gs)) { *scan_offset = 0; *scan_bytes = 0; return LEPB200_OK; }
+    *scan_offset = (uint32_t)(2 + gs.hpos);
+    *scan_bytes = gs.scan_bytes;
+    return LEPB200_OK;
+}
+int lepb200_host_lep_assemble(lepb200_lep* h, const uint8_t* scan, size_t scan_len, const uint8_t** data, size_t* len) {
+    if (!h || h->lf.status || !scan) return LEPB200_ERR_INVALID;
+    GpuRecodeSetup gs;
+    if (!gpu_recode_setup(h->lf, gs) || gs.scan_bytes != scan_len) return LEPB200_ERR_INVALID;
+    std::string err;
+    if (!assemble_baseline(h->lf, gs, scan, h->out, err)) { h->lf.error = err; return LEPB200_ERR_INVALID; }
+    *data = h->out.data();
+    *len = h->out.size();
+    return LEPB200_OK;
+}
 void lepb200_host_lep_close(lepb200_lep* h) { delete h; }
 
 // Host front end only (parse + Huffman decode + split selection) over a batch with `threads` workers; returns the

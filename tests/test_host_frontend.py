@@ -84,3 +84,24 @@ def test_lep_reader_and_jpeg_recode_match_original(name):
     planes, _ = oracle_decode_planes(lf)
     jpg = hl.recode(planes)
     assert jpg == open(os.path.join(GOLDEN, src_jpg), "rb").read(), "re-created JPEG differs from the original"
+
+
+@pytest.mark.parametrize("name", BASELINE_COMPLETE + BASELINE_TRUNCATED + PROGRESSIVE)
+def test_device_reencode_layout_and_assembly(name):
+    """Host half of the device Huffman re-encode path: for the files it accepts, the scan it asks the GPU for is exactly
+    the byte range of the original scan, and the JPEG assembled around those bytes is the original; truncated,
+    progressive and out-of-order scans are left to the host re-encoder."""
+    from lepton_b200 import HostLep
+    jpg = open(os.path.join(GOLDEN, name), "rb").read()
+    hl = HostLep(open(os.path.join(GOLDEN, name[:-4] + ".lep"), "rb").read())
+    assert hl.status == 0, hl.error
+    off, n = hl.scan_layout()
+    if name in BASELINE_TRUNCATED or name in PROGRESSIVE:
+        assert (off, n) == (0, 0)
+        return
+    if n == 0:
+        assert name == "colorswap.jpg"            # scan order differs from the frame's: host path
+        return
+    sos = jpg.rfind(b"\xff\xda", 0, off)
+    assert sos >= 0 and off == sos + 2 + int.from_bytes(jpg[sos + 2:sos + 4], "big")     # right behind the SOS segment
+    assert hl.assemble(jpg[off:off + n]) == jpg
