@@ -419,7 +419,7 @@ static bool build_table_dev(const lepb200_hufftable& in, HuffTableDev& t) {
     for (int len = 1; len <= 16; ++len) {
         t.valoff[len] = k - code;
         for (int i = 0; i < in.bits[len]; ++i, ++k, ++code) {
-            if (k >= 256) return false;
+            if (k >= 256 || code >= (1 << len)) return false;        // over-subscribed table
             t.vals[k] = in.vals[k];
             if (len <= 9) {
                 const int shift = 9 - len;
@@ -693,7 +693,7 @@ static bool build_enc_table(const lepb200_hufftable& in, HEncTable& t) {
     int code = 0, k = 0;
     for (int len = 1; len <= 16; ++len) {
         for (int i = 0; i < in.bits[len]; ++i, ++k, ++code) {
-            if (k >= 256) return false;
+            if (k >= 256 || code >= (1 << len)) return false;        // over-subscribed table
             t.code[in.vals[k]] = (uint16_t)code;
             t.len[in.vals[k]] = (uint8_t)len;
         }

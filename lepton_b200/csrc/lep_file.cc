@@ -226,6 +226,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             Jpeg& j = *s.js[i];
             const lepb200_buffer& in = jpegs[s.begin + i];
             if (stage) j.huff.attach(stage + soff[i], soff[i + 1] - soff[i] - 16);
+            if (need[s.begin + i] > c->plane_cap) { j.status = NOT_HANDLED; j.error = "image larger than the per-chunk device memory budget"; return; }
             const bool parsed = parse_jpeg(in.data, in.len, j);
             if (stage) {                                   // push this file's scan now: the H2D overlaps the other files' parsing
                 const size_t nb = j.huff.size();
@@ -401,7 +402,11 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         for (auto& t : th) if (t.joinable()) t.join();
     }
     int ret = LEPB200_OK;
-    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 2]); }
+    for (int k = 0; k < nchunks; ++k)
+        if (cs[k].gpu_rc) {               // the chunk's device work failed (e.g. out of memory): none of its files has an output
+            ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 2]);
+            for (int i = ranges[k].first; i < ranges[k].second; ++i) if (!status[i]) status[i] = 33;       // ExitCode::OS_ERROR
+        }
     for (int i = 0; i < n; ++i) {
         if (status[i]) c->outputs[i].clear();
         out[i].status = status[i];
@@ -425,8 +430,10 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     std::vector<size_t> pbytes(n, 0);
     parallel_for(n, c->nthreads, [&](int i) {
         all[i].reset(new LepFile());
-        if (read_lep(leps[i].data, leps[i].len, *all[i]))
+        if (read_lep(leps[i].data, leps[i].len, *all[i])) {
             for (int q = 0; q < all[i]->j.ncmp; ++q) pbytes[i] += (plane_bytes(all[i]->j, q) + 255) & ~size_t(255);
+            if (pbytes[i] > c->plane_cap) { all[i]->status = NOT_HANDLED; all[i]->error = "image larger than the per-chunk device memory budget"; pbytes[i] = 0; }
+        }
     });
     c->t_front += now_s() - t_parse;
     // chunks of up to 14 GB of coefficient planes (device memory: three contexts in flight).  The planes stay on the device
@@ -616,7 +623,11 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         for (auto& t : th) if (t.joinable()) t.join();
     }
     int rc = LEPB200_OK;
-    for (int k = 0; k < nchunks; ++k) if (cs[k].gpu_rc) { rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]); }
+    for (int k = 0; k < nchunks; ++k)
+        if (cs[k].gpu_rc) {
+            rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]);
+            for (int i = ranges[k].first; i < ranges[k].second; ++i) if (!status[i]) status[i] = 33;       // ExitCode::OS_ERROR
+        }
     for (int i = 0; i < n; ++i) {
         out[i].status = status[i];
         out[i].data = status[i] ? nullptr : c->outputs[i].data();

@@ -41,7 +41,7 @@ bool HuffTable::build() {
     for (int len = 1; len <= 16; ++len) {
         valoff[len] = k - code;
         for (int i = 0; i < bits[len]; ++i, ++k, ++code) {
-            if (k >= 256) return false;
+            if (k >= 256 || code >= (1 << len)) return false;        // more codes of this length than the code space holds
             const uint8_t sym = vals[k];
             ecode[sym] = (uint16_t)code;
             elen[sym] = (uint8_t)len;

@@ -136,6 +136,13 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
     }
     if (!have_grb) { j.grb = {0xFF, 0xD9}; }          // "if we don't have any garbage, assume FFD9 EOI" (jpgcoder.cc:4194)
     if (lf.handoffs.empty() || (int)lf.handoffs.size() != lf.nseg) return lfail(lf, VERSION_UNSUPPORTED, "handoff table missing or inconsistent");
+    if (lf.nseg > 16) return lfail(lf, NOT_HANDLED, "more than 16 thread-segments");             // MAX_NUM_THREADS of this build
+    // a corrupt handoff table must fail this file only, not the batch it travels in
+    if (lf.handoffs[0].luma_y_start != 0) return lfail(lf, STREAM_INCONSISTENT, "first thread-segment does not start at row 0");
+    for (int i = 0; i < lf.nseg; ++i) {
+        if ((int)lf.handoffs[i].luma_y_start > j.cmp[0].bcv || (i + 1 < lf.nseg && lf.handoffs[i].luma_y_start > lf.handoffs[i + 1].luma_y_start))
+            return lfail(lf, STREAM_INCONSISTENT, "thread-segment rows out of order or beyond the image");
+    }
     if (lf.handoffs[0].num_overhang_bits == 0xff) return lfail(lf, NOT_HANDLED, "legacy single-thread container");
     // demux (src/io/MuxReader.hh:230-283); the last 4 bytes are the file-size trailer
     size_t q = 28 + (size_t)zlen;
