@@ -268,3 +268,45 @@ def test_mixed_corpus_matches_reference_cli_and_round_trips(tmp_path):
         assert st == 0 and out == j, k
     assert fc.last_gpu_recoded >= 20          # the complete baseline files took the device Huffman encoder
     fc.close()
+
+
+def test_corrupt_files_fail_alone_inside_a_batch():
+    """Damaged inputs (scan bytes of a JPEG, coded payload / header bytes of a .lep) travel in one batch with intact files:
+    the kernels must stay inside their buffers, every damaged file ends with either a status or some output, and the
+    intact files of the batch still come out byte-exact."""
+    import os
+    import random
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200FileCodec
+    rnd = random.Random(99)
+    good = ["android.jpg", "grayscale.jpg", "trailingrst.jpg", "iphonecrop2.jpg"]
+    good_jpg = [open(os.path.join(GOLDEN, n), "rb").read() for n in good]
+    good_lep = [open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read() for n in good]
+    bad_jpg, bad_lep = [], []
+    for k in range(24):
+        j = bytearray(good_jpg[k % 4])
+        sos = j.rfind(b"\xff\xda")
+        for _ in range(1 + k % 5):
+            j[rnd.randrange(sos + 14, len(j) - 2)] = rnd.randrange(256)
+        bad_jpg.append(bytes(j))
+        l = bytearray(good_lep[k % 4])
+        lo = 28 if k % 3 == 0 else len(l) // 3                 # header blob (zlib) or the arithmetic-coded payload
+        for _ in range(1 + k % 4):
+            l[rnd.randrange(lo, len(l) - 4)] = rnd.randrange(256)
+        bad_lep.append(bytes(l))
+    fc = LeptonB200FileCodec(0, host_threads=4)
+    res = fc.compress(good_jpg + bad_jpg)
+    for n, (st, lep), ref in zip(good, res[:4], good_lep):
+        assert st == 0 and lep == ref, n
+    assert all(st != 0 or len(lep) > 0 for st, lep in res[4:])
+    back = fc.decompress(good_lep + bad_lep)
+    for n, (st, out), ref in zip(good, back[:4], good_jpg):
+        assert st == 0 and out == ref, n
+    assert all(st != 0 or len(out) > 0 for st, out in back[4:])
+    # files that still compress must also restore exactly (a damaged scan is just another JPEG to the coder)
+    again = [lep for st, lep in res[4:] if st == 0]
+    src = [j for j, (st, _) in zip(bad_jpg, res[4:]) if st == 0]
+    if again:
+        for j, (st, out) in zip(src, fc.decompress(again)):
+            assert st == 0 and out == j
+    fc.close()
