@@ -436,11 +436,13 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         }
     });
     c->t_front += now_s() - t_parse;
-    // chunks of up to 14 GB of coefficient planes (device memory: three contexts in flight).  The planes stay on the device
+    // chunks of up to `plane_cap` bytes of coefficient planes (device memory: three contexts in flight).  The planes stay on the device
     // for every file whose scan the GPU can re-encode; only the others need a pinned host arena (128 B per block over PCIe)
     std::vector<std::pair<int, int>> ranges;
     {
-        const size_t cap = size_t(c->gpu_huffman ? 14 : 6) << 30;     // without the device re-encoder every plane needs pinned host memory too
+        // one launch of the decode kernel should cover as many segments as possible (each chunk ends in a partly filled wave);
+        // without the device re-encoder every plane needs pinned host memory too, so those chunks stay small
+        const size_t cap = c->gpu_huffman ? c->plane_cap : (size_t(6) << 30);
         const int chunk_max = std::max(1, c->chunk_images);
         int b0 = 0;
         size_t acc = 0;
