@@ -8,7 +8,11 @@
 // ExitCode, and reference features not covered yet return NOT_HANDLED rather than guessing.
 #include <algorithm>
 #include <cmath>
+#include <emmintrin.h>
+
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 
 #include "lep_host.h"
 
@@ -345,6 +349,35 @@ inline int decode_symbol(BitReader& br, const HuffTable& t) {
 
 inline int devli(int s, int n) { return s == 0 ? n : (n >= (1 << (s - 1)) ? n : n + 1 - (1 << s)); }
 
+// zig-zag-ordered bit mask of the non-zero coefficients of an AlignedBlock (SSE2 compare + fixed bit permutation)
+struct ZzPermTable {
+    uint64_t t[8][256];
+    ZzPermTable() {
+        int al2zz[64];
+        for (int z = 0; z < 64; ++z) al2zz[k_zigzag_to_aligned[z]] = z;
+        for (int byte = 0; byte < 8; ++byte)
+            for (int v = 0; v < 256; ++v) {
+                uint64_t m = 0;
+                for (int bb = 0; bb < 8; ++bb) if (v & (1 << bb)) m |= 1ull << al2zz[byte * 8 + bb];
+                t[byte][v] = m;
+            }
+    }
+};
+const ZzPermTable g_zzperm_dec;
+inline uint64_t nonzero_mask_zigzag(const int16_t* blk) {
+    const __m128i zero = _mm_setzero_si128();
+    uint64_t zmask = 0;                                   // bit a: coefficient a (aligned order) IS zero
+    for (int i = 0; i < 4; ++i) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i + 8));
+        zmask |= (uint64_t)(uint32_t)_mm_movemask_epi8(_mm_packs_epi16(_mm_cmpeq_epi16(a, zero), _mm_cmpeq_epi16(b, zero))) << (16 * i);
+    }
+    const uint64_t nz = ~zmask;
+    uint64_t m = 0;
+    for (int byte = 0; byte < 8; ++byte) m |= g_zzperm_dec.t[byte][(nz >> (8 * byte)) & 255];
+    return m;
+}
+
 struct ScanInfo {
     int ncomp = 0;
     int cmp[4] = {0, 0, 0, 0};
@@ -536,10 +569,34 @@ int decode_progressive_interval(Jpeg& j, BitReader& br, const ScanInfo& sc, int 
         }
         return sta;
     }
-    // ---- AC refinement (decode_ac_prg_sa :5150, decode_eobrun_sa :5322)
+    // ---- AC refinement (decode_ac_prg_sa :5150, decode_eobrun_sa :5322), in place: the reference copies the band into a
+    // scratch block, replaces every already non-zero coefficient by its correction bit and adds the scratch block back
+    // shifted; here the same additions are applied directly, and the already non-zero coefficients of the block come
+    // from one vector compare (zig-zag-ordered bit mask) instead of 63 loads -- these scans visit every block of a
+    // component and dominate the decode time of progressive files.
+    const uint64_t band = (sc.to >= 63 ? ~0ull : ((1ull << (sc.to + 1)) - 1)) & ~((1ull << sc.from) - 1);
+    auto correct = [&](int z) {                    // one correction bit for the non-zero coefficient at zig-zag position z
+        if (read_bits(br, 1)) {
+            int16_t& cf = coef(z);
+            cf = (int16_t)(cf + (int16_t)((uint16_t)(int16_t)(cf > 0 ? 1 : -1) << sc.sal));
+        }
+    };
+    auto correct_all = [&](uint64_t m) {           // correction bits of all coefficients in m, ascending zig-zag order, read in batches
+        while (m) {
+            const int k = std::min(__builtin_popcountll(m), 24);
+            const uint32_t bits = (uint32_t)read_bits(br, k);          // first coefficient's bit on top
+            for (int i = k - 1; i >= 0; --i) {
+                const int z = __builtin_ctzll(m);
+                m &= m - 1;
+                if ((bits >> i) & 1u) {
+                    int16_t& cf = coef(z);
+                    cf = (int16_t)(cf + (int16_t)((uint16_t)(int16_t)(cf > 0 ? 1 : -1) << sc.sal));
+                }
+            }
+        }
+    };
     while (sta == 0) {
-        int16_t blk[64];
-        for (int b = sc.from; b <= sc.to; ++b) blk[b] = coef(b);
+        const uint64_t nzm = nonzero_mask_zigzag(planes[p.cmp] + (size_t)p.dpos * 64) & band;
         int eob = sc.to;
         track();
         if (eobrun == 0) {
@@ -555,12 +612,15 @@ int decode_progressive_interval(Jpeg& j, BitReader& br, const ScanInfo& sc, int 
                     if (r == 1) v = read_bits(br, 1) ? 1 : -1;
                     else if (r != 0) { err = true; break; }
                     while (true) {
-                        if (blk[bpos] == 0) {
+                        if (!((nzm >> bpos) & 1)) {
                             if (z > 0) --z;
-                            else { blk[bpos++] = (int16_t)v; break; }
+                            else {
+                                if (v) coef(bpos) = (int16_t)((uint16_t)(int16_t)v << sc.sal);
+                                ++bpos;
+                                break;
+                            }
                         } else {
-                            const int n = read_bits(br, 1);
-                            blk[bpos] = (int16_t)(blk[bpos] > 0 ? n : -n);
+                            correct(bpos);
                         }
                         if (bpos++ >= sc.to) { err = true; break; }
                     }
@@ -574,22 +634,18 @@ int decode_progressive_interval(Jpeg& j, BitReader& br, const ScanInfo& sc, int 
             }
             if (err) eob = -1;
             else if (eobrun > 0) {
-                for (; bpos <= sc.to; ++bpos)
-                    if (blk[bpos] != 0) { const int n = read_bits(br, 1); blk[bpos] = (int16_t)(blk[bpos] > 0 ? n : -n); }
+                correct_all(bpos <= 63 ? nzm & ~((1ull << bpos) - 1) : 0ull);
                 --eobrun;
             }
             if (eob == sc.from && eobrun > 0 && peobrun > 0 && peobrun < (unsigned)act.max_eobrun - 1) {
                 j.status = ASSERTION_FAILURE; j.error = "reconstruction of non optimal coding not supported";
             }
         } else {
-            for (int b = sc.from; b <= sc.to; ++b)
-                if (blk[b] != 0) { const int n = read_bits(br, 1); blk[b] = (int16_t)(blk[b] > 0 ? n : -n); }
+            correct_all(nzm);
             --eobrun;
             eob = 0;
         }
         peobrun = eobrun;
-        if (eob >= 0)
-            for (int b = sc.from; b <= sc.to; ++b) coef(b) = (int16_t)(coef(b) + (int16_t)((uint16_t)blk[b] << sc.sal));
         if (eob < 0) sta = -1;
         else sta = next_mcuposn(j, rsti, p);
         if (br.eof()) { sta = 2; break; }
@@ -728,6 +784,9 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
         }
         if (sc.ncomp != j.ncmp || j.jpegtype != 1) j.is_baseline = false;     // jpgcoder.cc:2912-2926: written with flag 'X'
         if (j.jpegtype != 1) {
+#ifdef LEPB200_SCAN_TIMING
+            timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+#endif
             ScanPos p;
             p.cmp = sc.cmp[0];
             mcu = 0;
@@ -751,6 +810,11 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
                 if (sta == 2) { ++scans; break; }
             }
             if (sc.ncomp > 1) mcu = p.mcu;              // the last handoff is taken at mcu / mcuh (jpgcoder.cc:3278)
+#ifdef LEPB200_SCAN_TIMING
+            { timespec ts1; clock_gettime(CLOCK_MONOTONIC, &ts1);
+              fprintf(stderr, "[scan] ncomp %d cmp %d Ss %d Se %d Ah %d Al %d  %.1f ms\n", sc.ncomp, sc.cmp[0], sc.from, sc.to, sc.sah, sc.sal,
+                      (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6); }
+#endif
             continue;
         }
 

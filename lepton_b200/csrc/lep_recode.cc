@@ -169,29 +169,6 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct BitWriter {
-    std::vector<uint8_t>& out;
-    uint64_t acc = 0;
-    int nbits = 0;
-    explicit BitWriter(std::vector<uint8_t>& o) : out(o) {}
-    inline void put(uint32_t v, int n) {          // n <= 32
-        if (!n) return;
-        acc = (acc << n) | (v & ((n == 32) ? 0xffffffffu : ((1u << n) - 1)));
-        nbits += n;
-        while (nbits >= 8) {
-            const uint8_t b = (uint8_t)(acc >> (nbits - 8));
-            out.push_back(b);
-            if (b == 0xFF) out.push_back(0x00);   // byte stuffing (recoder.cc:144-185)
-            nbits -= 8;
-        }
-    }
-    // abitwriter::pad (bitops.hh:168-175): successive bits of `fill`, LSB first
-    inline void pad(uint8_t fill) {
-        int offset = 1;
-        while (nbits & 7) { put((fill & offset) ? 1 : 0, 1); offset <<= 1; }
-    }
-};
-
 inline int bitlen16(int v) { return v ? 32 - __builtin_clz((unsigned)v) : 0; }
 
 // Bit writer of the baseline re-encoder (the hot loop of the .lep -> JPEG direction on the host): 64-bit accumulator,
@@ -214,6 +191,7 @@ struct FastWriter {
         p = out.data() + used; lim = out.data() + out.size();
     }
     inline void raw(uint8_t b) { room(1); *p++ = b; }
+    inline void raw_bytes(const uint8_t* src, size_t n) { room(n); memcpy(p, src, n); p += n; }
     inline void put(uint32_t v, int n) {          // n <= 32, v < 2^n
         acc = (acc << n) | v;
         nbits += n;
@@ -521,10 +499,10 @@ struct ScanHdr { int ncomp = 0, cmp[4] = {0, 0, 0, 0}, from = 0, to = 0, sah = 0
 inline int fdiv2(int v, int p) { return v < 0 ? -((-v) >> p) : (v >> p); }
 
 struct ProgWriter {
-    BitWriter& bw;
+    FastWriter& bw;
     std::vector<uint8_t> crbits;          // stored correction bits (abytewriter "storw")
     unsigned eobrun = 0;
-    explicit ProgWriter(BitWriter& b) : bw(b) {}
+    explicit ProgWriter(FastWriter& b) : bw(b) {}
     void flush_crbits() { for (uint8_t b : crbits) bw.put(b, 1); crbits.clear(); }
     void flush_eobrun(const HuffTable& t) {
         if (eobrun == 0) return;
@@ -553,7 +531,7 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
     out.clear();
     out.reserve((size_t)lf.jpeg_size + 64);
     out.push_back(0xFF); out.push_back(0xD8);
-    BitWriter bw(out);
+    FastWriter bw(out, (size_t)lf.jpeg_size);
     ProgWriter pw(bw);
     bool rst_stuck = false;                // a refused marker is never retried (rpos stops advancing, :2640-2650)
     int scan = 0;
@@ -602,7 +580,7 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
             }
             hpos += len;
         }
-        out.insert(out.end(), h.begin() + seg_begin, h.begin() + std::min(hpos, h.size()));
+        bw.raw_bytes(h.data() + seg_begin, std::min(hpos, h.size()) - seg_begin);
         if (type != 0xDA) break;
         ++scan;
         // ---- one scan
@@ -769,8 +747,8 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
             // restart: marker after the padded byte when the scan's marker budget allows (:2640-2650)
             if (rsti > 0) {
                 if (rst_ok()) {
-                    out.push_back(0xFF);
-                    out.push_back((uint8_t)(0xD0 + (cpos & 7)));
+                    bw.raw(0xFF);
+                    bw.raw((uint8_t)(0xD0 + (cpos & 7)));
                     ++cpos; ++rst_this_scan;
                 } else {
                     rst_stuck = true;
@@ -779,8 +757,9 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
         }
         // bogus trailing restart markers of this scan (:2711-2719)
         if ((size_t)scan - 1 < j.rst_err.size())
-            for (unsigned i = 0; i < j.rst_err[scan - 1]; ++i) { out.push_back(0xFF); out.push_back((uint8_t)(0xD0 + (cpos & 7))); ++cpos; }
+            for (unsigned i = 0; i < j.rst_err[scan - 1]; ++i) { bw.raw(0xFF); bw.raw((uint8_t)(0xD0 + (cpos & 7))); ++cpos; }
     }
+    bw.finish();
     if (scan == 0) { err = "no scan found"; return false; }
     if (lf.jpeg_size >= j.grb.size() && out.size() > lf.jpeg_size - j.grb.size()) out.resize(lf.jpeg_size - j.grb.size());
     out.insert(out.end(), j.grb.begin(), j.grb.end());
