@@ -37,7 +37,8 @@ struct HEncSeg {
 };
 
 constexpr int HENC_WARPS = 4;
-constexpr int HENC_WORDS = 80;       // bit buffer per warp: worst block = DC 27 + 63 * 27 + ZRLs << 80 * 32 bits
+constexpr int HENC_WORDS = 160;      // bit buffer per warp: flushed once it holds HENC_FLUSH_BITS; a block adds at most ~1800 bits
+constexpr uint32_t HENC_FLUSH_BITS = 2560;
 
 static __constant__ uint8_t c_zz2al[64] = {
     49, 50, 57, 58, 0, 51, 52, 1, 2, 59, 60, 3, 4, 5, 53, 54, 6, 7, 8, 9, 61, 62, 10, 11,
@@ -186,7 +187,7 @@ lep_huffencode_kernel(const HEncImage* __restrict__ images, HEncSeg* __restrict_
                         if (eobbits) put_bits(buf, pos, act.code[0x00], eobbits);
                         nbit += (uint32_t)total;
                         __syncwarp();
-                        flush();
+                        if (nbit >= HENC_FLUSH_BITS) flush();          // bytes leave in batches, not per block
                     }
             }
             // restart interval boundary (recoder.cc:381-397): pad, marker, predictors reset -- not after the last MCU
@@ -200,8 +201,8 @@ lep_huffencode_kernel(const HEncImage* __restrict__ images, HEncSeg* __restrict_
                     if (lane == 0) put_bits(buf, nbit, bits, need);
                     nbit += need;
                     __syncwarp();
-                    flush();
                 }
+                flush();                                                  // every pending byte goes out before the marker
                 if (lane == 0) {
                     if (opos < limit) out[opos] = 0xFF;
                     if (opos + 1 < limit) out[opos + 1] = (uint8_t)(0xD0 + (cpos & 7));
@@ -220,8 +221,8 @@ lep_huffencode_kernel(const HEncImage* __restrict__ images, HEncSeg* __restrict_
         if (lane == 0) put_bits(buf, nbit, bits, need);
         nbit += need;
         __syncwarp();
-        flush();
     }
+    flush();                                                              // complete bytes; a non-last segment drops its last bits (the next one starts with them)
     if (lane == 0) {
         const uint32_t produced = opos - sg.out_off;
         sg.produced = produced;
