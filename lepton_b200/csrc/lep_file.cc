@@ -220,21 +220,23 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         }
         std::vector<uint8_t> eligible(m, 0);
         std::vector<GpuScanSetup> setups(c->gpu_huffman ? m : 0);
-        // pass 1: parse + de-stuff (into the staging buffer on the GPU path)
-        parallel_for(m, c->nthreads, [&](int i) {
-            s.js[i].reset(new Jpeg());
-            Jpeg& j = *s.js[i];
-            const lepb200_buffer& in = jpegs[s.begin + i];
-            if (stage) j.huff.attach(stage + soff[i], soff[i + 1] - soff[i] - 16);
-            if (need[s.begin + i] > c->plane_cap) { j.status = NOT_HANDLED; j.error = "image larger than the per-chunk device memory budget"; return; }
-            const bool parsed = parse_jpeg(in.data, in.len, j);
-            if (stage) {                                   // push this file's scan now: the H2D overlaps the other files' parsing
-                const size_t nb = j.huff.size();
-                memset(stage + soff[i] + nb, 0, 16);
-                lepb200_huffman_stage_upload(ctx, soff[i], (nb + 16 + 15) & ~size_t(15));
+        // pass 1: parse + de-stuff (into the staging buffer on the GPU path), in groups of consecutive files: a group's
+        // staged bytes are contiguous, so one asynchronous H2D per group pushes them while other groups are still being
+        // parsed (a copy per file would spend more time in the CUDA runtime than in the parser)
+        const int group = 32, ngroups = (m + group - 1) / group;
+        parallel_for(ngroups, c->nthreads, [&](int gi) {
+            const int g0 = gi * group, g1 = std::min(m, g0 + group);
+            for (int i = g0; i < g1; ++i) {
+                s.js[i].reset(new Jpeg());
+                Jpeg& j = *s.js[i];
+                const lepb200_buffer& in = jpegs[s.begin + i];
+                if (stage) { j.huff.attach(stage + soff[i], soff[i + 1] - soff[i] - 16); memset(stage + soff[i], 0, 16); }
+                if (need[s.begin + i] > c->plane_cap) { j.status = NOT_HANDLED; j.error = "image larger than the per-chunk device memory budget"; continue; }
+                const bool parsed = parse_jpeg(in.data, in.len, j);
+                if (stage) memset(stage + soff[i] + j.huff.size(), 0, 16);          // the decoder reads whole words past the end
+                if (parsed && stage && gpu_scan_setup(j, setups[i])) eligible[i] = 1;
             }
-            if (!parsed) return;
-            if (stage && gpu_scan_setup(j, setups[i])) eligible[i] = 1;
+            if (stage) lepb200_huffman_stage_upload(ctx, soff[g0], soff[g1] - soff[g0]);
         });
         // host-decoded files of a GPU chunk share one arena sized for just them
         if (c->gpu_huffman) {
