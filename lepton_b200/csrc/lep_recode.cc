@@ -260,6 +260,28 @@ inline uint64_t nonzero_mask_zigzag(const int16_t* blk) {
     return m;
 }
 
+// bit z set when |coefficient at zig-zag position z| >= thr (thr in 1..32768): the positions a progressive
+// scan at successive-approximation bit `sal` sees as non-zero (thr = 1 << sal) or as already significant
+// (thr = 2 << sal)
+inline uint64_t magnitude_mask_zigzag(const int16_t* blk, int thr) {
+    const __m128i zero = _mm_setzero_si128();
+    const __m128i t1 = _mm_set1_epi16((short)(thr - 1));
+    uint64_t zmask = 0;                                   // bit a: |coefficient a| < thr
+    for (int i = 0; i < 4; ++i) {
+        __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i));
+        __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(blk + 16 * i + 8));
+        a = _mm_max_epi16(a, _mm_sub_epi16(zero, a));     // |x| as u16 (-32768 stays 0x8000 = 32768)
+        b = _mm_max_epi16(b, _mm_sub_epi16(zero, b));
+        const __m128i eq = _mm_packs_epi16(_mm_cmpeq_epi16(_mm_subs_epu16(a, t1), zero),
+                                           _mm_cmpeq_epi16(_mm_subs_epu16(b, t1), zero));
+        zmask |= (uint64_t)(uint32_t)_mm_movemask_epi8(eq) << (16 * i);
+    }
+    const uint64_t nz = ~zmask;
+    uint64_t m = 0;
+    for (int byte = 0; byte < 8; ++byte) m |= g_zzperm.t[byte][(nz >> (8 * byte)) & 255];
+    return m;
+}
+
 }  // namespace
 
 bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector<uint8_t>& out, std::string& err);
@@ -500,12 +522,24 @@ inline int fdiv2(int v, int p) { return v < 0 ? -((-v) >> p) : (v >> p); }
 
 struct ProgWriter {
     FastWriter& bw;
-    std::vector<uint8_t> crbits;          // stored correction bits (abytewriter "storw")
+    std::vector<uint32_t> crwords;        // stored correction bits (abytewriter "storw"), 32 to a word, oldest first
+    uint32_t crcur = 0;
+    int crn = 0;
     unsigned eobrun = 0;
+    bool bad = false;                      // coefficients the scan's tables cannot express (inconsistent .lep)
     explicit ProgWriter(FastWriter& b) : bw(b) {}
-    void flush_crbits() { for (uint8_t b : crbits) bw.put(b, 1); crbits.clear(); }
+    inline void push_crbit(uint32_t b) {
+        crcur = (crcur << 1) | b;
+        if (++crn == 32) { crwords.push_back(crcur); crcur = 0; crn = 0; }
+    }
+    void flush_crbits() {
+        for (uint32_t w : crwords) bw.put(w, 32);
+        crwords.clear();
+        if (crn) { bw.put(crcur, crn); crcur = 0; crn = 0; }
+    }
     void flush_eobrun(const HuffTable& t) {
         if (eobrun == 0) return;
+        if (t.max_eobrun <= 0) { bad = true; eobrun = 0; return; }      // the table has no end-of-band code at all
         while (eobrun > (unsigned)t.max_eobrun) {
             bw.put(t.ecode[0xE0], t.elen[0xE0]);
             bw.put(32767 - (1 << 14), 14);
@@ -642,19 +676,21 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
                     int nb = diff > 0 ? diff : (diff - 1) + (1 << s);
                     bw.put(dct.ecode[s], dct.elen[s]);
                     bw.put((uint32_t)nb, s);
-                    int end = 63;
-                    while (end > 0 && coef(end) == 0) --end;
-                    int z = 0;
-                    for (int bpos = 1; bpos <= end; ++bpos) {
+                    uint64_t m = nonzero_mask_zigzag(planes[cmp] + (size_t)dpos * 64) & ~1ull;
+                    const int end = m ? 63 - __builtin_clzll(m) : 0;
+                    int prev = 0;
+                    while (m) {
+                        const int bpos = __builtin_ctzll(m);
+                        m &= m - 1;
+                        int z = bpos - prev - 1;
+                        prev = bpos;
                         const int v = coef(bpos);
-                        if (v == 0) { ++z; continue; }
                         while (z & 0xf0) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
                         s = bitlen16(v > 0 ? v : -v);
                         nb = v > 0 ? v : (v - 1) + (1 << s);
                         const int hc = ((z & 0xf) << 4) + s;
                         bw.put(act.ecode[hc], act.elen[hc]);
                         bw.put((uint32_t)nb, s);
-                        z = 0;
                     }
                     if (end != 63) bw.put(act.ecode[0x00], act.elen[0x00]);
                     sta = advance(rstw);
@@ -683,23 +719,26 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
             } else if (sc.sah == 0) {
                 // ---- AC first stage
                 const HuffTable& act = ac_t[ta[cmp]];
+                const uint64_t band = (sc.to == 63 ? ~0ull : (1ull << (sc.to + 1)) - 1) & ~((1ull << sc.from) - 1);
                 while (sta == 0) {
-                    int z = 0;
-                    for (int bpos = sc.from; bpos <= sc.to; ++bpos) {
+                    uint64_t m = magnitude_mask_zigzag(planes[cmp] + (size_t)dpos * 64, 1 << sc.sal) & band;
+                    int prev = sc.from - 1;
+                    if (m) pw.flush_eobrun(act);
+                    while (m) {
+                        const int bpos = __builtin_ctzll(m);
+                        m &= m - 1;
+                        int z = bpos - prev - 1;
+                        prev = bpos;
                         const int tmp = fdiv2(coef(bpos), sc.sal);
-                        if (tmp != 0) {
-                            pw.flush_eobrun(act);
-                            while (z >= 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
-                            const int a = tmp > 0 ? tmp : -tmp;
-                            const int s = bitlen16(a);
-                            const int nb = tmp > 0 ? tmp : (tmp - 1) + (1 << s);
-                            const int hc = (z << 4) + s;
-                            bw.put(act.ecode[hc], act.elen[hc]);
-                            bw.put((uint32_t)nb, s);
-                            z = 0;
-                        } else ++z;
+                        while (z >= 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); z -= 16; }
+                        const int a = tmp > 0 ? tmp : -tmp;
+                        const int s = bitlen16(a);
+                        const int nb = tmp > 0 ? tmp : (tmp - 1) + (1 << s);
+                        const int hc = (z << 4) + s;
+                        bw.put(act.ecode[hc], act.elen[hc]);
+                        bw.put((uint32_t)nb, s);
                     }
-                    if (z > 0) {
+                    if (prev < sc.to) {
                         ++pw.eobrun;
                         if (pw.eobrun == (unsigned)act.max_eobrun) pw.flush_eobrun(act);
                     }
@@ -709,30 +748,38 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
             } else {
                 // ---- AC refinement
                 const HuffTable& act = ac_t[ta[cmp]];
+                const uint64_t band = (sc.to == 63 ? ~0ull : (1ull << (sc.to + 1)) - 1) & ~((1ull << sc.from) - 1);
                 while (sta == 0) {
-                    int blk[64];
-                    for (int bpos = sc.from; bpos <= sc.to; ++bpos) blk[bpos] = fdiv2(coef(bpos), sc.sal);
-                    int eob = sc.from;
-                    for (int bpos = sc.to; bpos >= sc.from; --bpos)
-                        if (blk[bpos] == 1 || blk[bpos] == -1) { eob = bpos + 1; break; }
+                    // sig: non-zero at this bit plane; old: significant before this scan (|v| >> sal >= 2);
+                    // the remaining sig positions turn significant here (|v| >> sal == 1)
+                    const int16_t* blkp = planes[cmp] + (size_t)dpos * 64;
+                    uint64_t sig = magnitude_mask_zigzag(blkp, 1 << sc.sal) & band;
+                    const uint64_t old = magnitude_mask_zigzag(blkp, 2 << sc.sal) & band;
+                    const uint64_t fresh = sig & ~old;
+                    const int eob = fresh ? 64 - __builtin_clzll(fresh) : sc.from;
                     if (eob > sc.from && pw.eobrun > 0) { pw.flush_eobrun(act); pw.flush_crbits(); }
-                    int z = 0, bpos = sc.from;
-                    for (; bpos < eob; ++bpos) {
-                        const int tmp = blk[bpos];
-                        if (tmp == 0) {
-                            if (++z == 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); pw.flush_crbits(); z = 0; }
-                        } else if (tmp == 1 || tmp == -1) {
+                    int z = 0, prev = sc.from - 1;
+                    while (sig) {
+                        const int bpos = __builtin_ctzll(sig);
+                        sig &= sig - 1;
+                        const int v = coef(bpos);
+                        if (bpos >= eob) {                 // behind the last new coefficient: correction bits only
+                            pw.push_crbit((uint32_t)(((v < 0 ? -v : v) >> sc.sal) & 1));
+                            continue;
+                        }
+                        z += bpos - prev - 1;
+                        prev = bpos;
+                        while (z >= 16) { bw.put(act.ecode[0xF0], act.elen[0xF0]); pw.flush_crbits(); z -= 16; }
+                        if ((fresh >> bpos) & 1) {
                             const int hc = (z << 4) + 1;
                             bw.put(act.ecode[hc], act.elen[hc]);
-                            bw.put(tmp > 0 ? 1u : 0u, 1);
+                            bw.put(v > 0 ? 1u : 0u, 1);
                             pw.flush_crbits();
                             z = 0;
                         } else {
-                            pw.crbits.push_back((uint8_t)(tmp & 1));
+                            pw.push_crbit((uint32_t)(((v < 0 ? -v : v) >> sc.sal) & 1));
                         }
                     }
-                    for (; bpos <= sc.to; ++bpos)
-                        if (blk[bpos] != 0) pw.crbits.push_back((uint8_t)(blk[bpos] & 1));
                     if (eob <= sc.to) {
                         ++pw.eobrun;
                         if (pw.eobrun == (unsigned)act.max_eobrun) { pw.flush_eobrun(act); pw.flush_crbits(); }
@@ -761,6 +808,7 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
     }
     bw.finish();
     if (scan == 0) { err = "no scan found"; return false; }
+    if (pw.bad) { err = "coefficients not expressible with the scan's huffman tables"; return false; }
     if (lf.jpeg_size >= j.grb.size() && out.size() > lf.jpeg_size - j.grb.size()) out.resize(lf.jpeg_size - j.grb.size());
     out.insert(out.end(), j.grb.begin(), j.grb.end());
     if (out.size() != lf.jpeg_size) { err = "re-created JPEG has the wrong size"; return false; }

@@ -13,6 +13,11 @@ the multi-megabyte dumps).  The reference repo's own golden .lep vectors are exe
 tests/test_oracle_golden.py (iphone16.lep, test_suite/test_16threads.sh); narrowrst.lep (version 4, brotli
 header) and gold-legacy.lep (pre-handoff legacy header) need the brotli / legacy container readers, which are
 outside the hot path.
+
+prog8x8.jpg is the one fixture that is not a reference image: a single 8x8 block of noise saved by Pillow as an
+optimised progressive JPEG (quality 92), whose AC tables hold no end-of-band code; prog8x8.lep is the reference
+CLI's output for it (make_prog8x8 below; kept as committed, not regenerated, because the bytes depend on the
+Pillow/libjpeg build).
 """
 import hashlib
 import json
@@ -52,7 +57,22 @@ def md5(b):
     return hashlib.md5(b).hexdigest()
 
 
+def make_prog8x8():
+    """One-block progressive JPEG with optimised tables + the reference's .lep for it (only when absent)."""
+    dst = os.path.join(HERE, "prog8x8.jpg")
+    if os.path.exists(dst):
+        return
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    a = np.clip(128 + rng.normal(0, 40, (8, 8, 3)), 0, 255).astype(np.uint8)
+    Image.fromarray(a).save(dst, "JPEG", quality=92, progressive=True, optimize=True, subsampling=0)
+    rc = subprocess.run([LEPTON, "-skipverify", "-allowprogressive", dst, dst[:-4] + ".lep"], capture_output=True).returncode
+    assert rc == 0, rc
+
+
 def main():
+    make_prog8x8()
     manifest = {}
     with tempfile.TemporaryDirectory() as td:
         for name in FIXTURES:

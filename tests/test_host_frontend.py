@@ -105,3 +105,24 @@ def test_device_reencode_layout_and_assembly(name):
     sos = jpg.rfind(b"\xff\xda", 0, off)
     assert sos >= 0 and off == sos + 2 + int.from_bytes(jpg[sos + 2:sos + 4], "big")     # right behind the SOS segment
     assert hl.assemble(jpg[off:off + n]) == jpg
+
+
+@pytest.mark.timeout(60)
+def test_progressive_reencode_rejects_coefficients_its_tables_cannot_express():
+    """prog8x8.jpg (one 8x8 block, optimised progressive tables) has AC tables without any end-of-band code.  The real
+    coefficients re-encode to the original bytes; coefficients that would need an end-of-band run must come back as an
+    error, not spin in the run-length flush (EOB run handling: jpgcoder.cc encode_eobrun :5345-5377)."""
+    from lepton_b200 import HostJpeg, HostLep, LeptonB200Error
+    jpg = open(os.path.join(GOLDEN, "prog8x8.jpg"), "rb").read()
+    hj = HostJpeg(jpg)
+    assert hj.status == 0, hj.error
+    planes = hj.coef_image().planes
+    hl = HostLep(open(os.path.join(GOLDEN, "prog8x8.lep"), "rb").read())
+    assert hl.status == 0, hl.error
+    assert hl.recode(planes) == jpg
+    flat = [np.full_like(np.asarray(p), i + 1) for i, p in enumerate(planes)]
+    try:
+        out = hl.recode(flat)
+    except LeptonB200Error:
+        return
+    assert out != jpg
