@@ -15,6 +15,7 @@
 #include "lep_encode.cu"
 #include "lep_decode.cu"
 #include "lep_decode_thread.cu"
+#include "lep_decode_lockstep.cu"
 #include "lep_huff.cu"
 #include "lep_huffenc.cu"
 
@@ -258,7 +259,7 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
     CK(ctx->d_counter.reserve(256));
-    if (!encode && ctx->dec_mode == 1) {
+    if (!encode && ctx->dec_mode >= 1) {
         ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)ctx->dec_threads * row_stride));
@@ -827,12 +828,15 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->dec_mode == 1) {
+    if (ctx->dec_mode >= 1) {
         // one thread per segment, largest segments first; a launch covers as many segments as there are model slots
+        // (mode 1: free-running lanes, mode 2: lanes in lock step)
+        const auto kernel = ctx->dec_mode == 2 ? lep_decode_lockstep_kernel : lep_decode_thread_kernel;
+        static_assert(DECT_THREADS == DECL_THREADS, "both thread-per-segment kernels use one warp per CTA");
         for (int first = 0; first < nseg; first += ctx->dec_threads) {
             const int count = std::min(ctx->dec_threads, nseg - first);
             CK(cudaMemsetAsync(ctx->d_models.p, 0, (size_t)count * MODEL_BYTES, ctx->stream));       // identity prior = zero fill
-            lep_decode_thread_kernel<<<(count + DECT_THREADS - 1) / DECT_THREADS, DECT_THREADS, 0, ctx->stream>>>(
+            kernel<<<(count + DECT_THREADS - 1) / DECT_THREADS, DECT_THREADS, 0, ctx->stream>>>(
                 static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), first, count, static_cast<const int*>(ctx->d_order.p),
                 static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
             CK(cudaGetLastError());
