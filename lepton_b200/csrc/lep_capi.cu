@@ -100,7 +100,8 @@ struct lepb200_ctx {
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
     int dec_mode = 0;                     // decode kernel: 0 = one warp per segment (default), 1 = one thread per segment (wins only when
-                                          // tens of thousands of segments are in flight)
+                                          // tens of thousands of segments are in flight), 2 = one thread per segment with
+                                          // the lanes of a warp in lock step (lep_decode_lockstep.cu)
     int dec_threads_max = 16384;          // thread mode: segments per launch (one 1.58 MB model each)
     int dec_threads = 0;                  // thread mode: model / row-buffer slots of the current batch
     bool tokens_known = false;            // token streams laid out on the host from caller-supplied bounds (no counting pre-pass)
