@@ -1,5 +1,7 @@
 """GPU parity: the sm_100a kernels, called through the C ABI, against the pinned oracle and the reference's own
 .lep files.  Bit-exact (integer / byte work): streams must be identical, decoded planes identical."""
+import os
+
 import numpy as np
 import pytest
 
@@ -53,6 +55,20 @@ def test_golden_batch_decode_thread_per_segment_kernel(monkeypatch):
     """The alternative decode kernel (one thread per segment, LEPB200_DEC_MODE=1) must give the same planes."""
     from lepton_b200 import LeptonB200Codec
     monkeypatch.setenv("LEPB200_DEC_MODE", "1")
+    c = LeptonB200Codec(0)
+    try:
+        test_golden_batch_decode_matches_reference_planes(c)
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(os.environ.get("LEPB200_TEST_LOCKSTEP") != "1",
+                    reason="lock-step decode kernel: pinned on the CPU (tests/test_emu_decode.py), first GPU run pending; "
+                           "set LEPB200_TEST_LOCKSTEP=1 (and run under `timeout`) to include it")
+def test_golden_batch_decode_lockstep_kernel(monkeypatch):
+    """The lock-step thread-per-segment decode kernel (LEPB200_DEC_MODE=2) must give the same planes."""
+    from lepton_b200 import LeptonB200Codec
+    monkeypatch.setenv("LEPB200_DEC_MODE", "2")
     c = LeptonB200Codec(0)
     try:
         test_golden_batch_decode_matches_reference_planes(c)
