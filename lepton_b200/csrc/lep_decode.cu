@@ -54,6 +54,10 @@ struct Decoder {
 // VPXBoolReader::get (vpx_bool_reader.hh:45-57) = vpx_read + Branch::record_obs_and_update
 __device__ __forceinline__ uint32_t dec_get(Decoder& d, uint32_t addr) {
     uint32_t w = d.model[addr];
+#ifdef LEPB200_EMU
+    __syncwarp();      // CPU warp emulator (tests/emu) only: lanes run one after the other there, so every lane must have
+                       // read the count before the first one writes it back; on the device the converged warp does that anyway
+#endif
     uint32_t prob = branch_prob(w, d.rcp);
     BoolReader& r = d.br;
     uint32_t split = (r.range * prob + (256 - prob)) >> 8;

@@ -1,9 +1,10 @@
-"""CPU emulation of the thread-per-segment decode kernels (test infrastructure).
+"""CPU emulation of the decode kernels (test infrastructure).
 
-`lep_decode_thread.cu` and `lep_decode_lockstep.cu` give every lane its own segment and exchange nothing between lanes
-but votes, so their source compiles as host C++ through `cuda_shim.h` and runs one lane at a time (emu_decode.cc).  That
-pins the per-lane arithmetic -- bool decoder, token state machine, predictors, IDCT, block stores -- to the oracle without
-a GPU; the GPU parity tests then only have to confirm the same source under real warps.
+The kernel sources compile as host C++ through `cuda_shim.h`, which runs every CUDA thread of a CTA as a fiber and
+implements the warp collectives and `__syncthreads` among them, so `lep_decode.cu` (warp per segment),
+`lep_decode_thread.cu` and `lep_decode_lockstep.cu` (thread per segment) execute with real 32-lane warps, divergence,
+votes and shuffles included, and can be pinned to the oracle bit for bit without a GPU.  The GPU parity tests then
+confirm the same sources on the device; what the emulator cannot show is timing and memory-system behaviour.
 """
 import ctypes
 import os
@@ -16,9 +17,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_decode.so")
 SOURCES = [os.path.join(HERE, "emu_decode.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
-           os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"),
+           os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"),
            os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
+KERNEL_WARP = 0
 KERNEL_THREAD = 1
 KERNEL_LOCKSTEP = 2
 
@@ -42,7 +44,7 @@ def lib():
     return _LIB
 
 
-def decode_images(kernel, images, streams):
+def decode_images(kernel, images, streams, grid_cap=0):
     """Same contract as LeptonB200Codec.decode_images: decodes into images[i].planes, returns (status, ndecisions) per segment."""
     from lepton_b200.codec import _Image, _Stream
     n = sum(im.nseg for im in images)
@@ -59,7 +61,7 @@ def decode_images(kernel, images, streams):
     cim = (_Image * len(images))(*[im.to_c() for im in images])
     st = (ctypes.c_int32 * n)()
     nd = (ctypes.c_uint64 * n)()
-    rc = lib().emu_decode_images(int(kernel), cim, len(images), arr, st, nd)
+    rc = lib().emu_decode_images(int(kernel), int(grid_cap), cim, len(images), arr, st, nd)
     if rc != 0:
         raise RuntimeError("emu_decode_images failed with %d" % rc)
     return list(st), list(nd)

@@ -1,14 +1,15 @@
-// emu_decode.cc -- runs the thread-per-segment decode kernels on the CPU, one lane at a time (test infrastructure).
+// emu_decode.cc -- runs the three decode kernels on the CPU under the warp emulator of cuda_shim.h (test infrastructure).
 //
-// The kernel sources are compiled as host C++ through cuda_shim.h; this file builds the same job descriptors
-// lep_capi.cu's build_batch / lepb200_decode_upload build for the device (ImageDesc, SegDesc, order, zeroed model and row
-// pools, zeroed planes) with host addresses in place of device addresses, then calls the kernel body once per lane.
+// The kernel sources are compiled as host C++; this file builds the same job descriptors lep_capi.cu's build_batch /
+// lepb200_decode_upload build for the device (ImageDesc, SegDesc, order, work counter, zeroed model and row pools, zeroed
+// planes) with host addresses in place of device addresses and launches the kernel with its device launch shape.
 // Entry point mirrors lepb200_decode_images (include/lepton_b200.h) plus a kernel selector.
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
 
 #include "cuda_shim.h"
+#include "../../lepton_b200/csrc/lep_decode.cu"
 #include "../../lepton_b200/csrc/lep_decode_thread.cu"
 #include "../../lepton_b200/csrc/lep_decode_lockstep.cu"
 #include "../../include/lepton_b200.h"
@@ -50,13 +51,27 @@ int fill_quant(ImageDesc& d, int c, const uint16_t zz[64]) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+struct LaunchArgs {
+    int kernel;
+    const ImageDesc* images; SegDesc* segs; int nseg; const int* order; int* counter;
+    uint16_t* models; uint8_t* rows; size_t row_stride;
+};
+
+void kernel_body(void* p) {
+    const LaunchArgs& a = *static_cast<const LaunchArgs*>(p);
+    if (a.kernel == 0) lep_decode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 1) lep_decode_thread_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
+    else lep_decode_lockstep_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
+}
+
 }  // namespace
 
-// kernel: 1 = lep_decode_thread_kernel, 2 = lep_decode_lockstep_kernel.  Decodes into images[i].planes (zeroed first,
+// kernel: 0 = lep_decode_kernel (warp per segment, persistent CTAs; `grid_cap` > 0 limits the CTAs so that warps take
+// several segments from the queue), 1 = lep_decode_thread_kernel, 2 = lep_decode_lockstep_kernel.  Decodes into images[i].planes (zeroed first,
 // like the device arena); per-segment status and decision counts come back like lepb200_decode_fetch reports them.
-extern "C" int emu_decode_images(int kernel, const lepb200_image* images, int nimages, const lepb200_stream* in,
+extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, const lepb200_stream* in,
                                  int32_t* status_out, uint64_t* ndecisions_out) {
-    if (nimages <= 0 || !images || !in || (kernel != 1 && kernel != 2)) return LEPB200_ERR_INVALID;
+    if (nimages <= 0 || !images || !in || kernel < 0 || kernel > 2) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
     std::vector<SegDesc> segs;
     std::vector<size_t> seg_blocks;
@@ -110,20 +125,24 @@ extern "C" int emu_decode_images(int kernel, const lepb200_image* images, int ni
     for (int i = 0; i < nseg; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg_blocks[a] > seg_blocks[b]; });
 
-    std::vector<uint16_t> models((size_t)nseg * M_TOTAL, 0);       // identity prior = zero fill
-    std::vector<uint8_t> rows((size_t)nseg * row_stride, 0);
-    const int lanes = 32;
-    blockDim.x = lanes; gridDim.x = (unsigned)((nseg + lanes - 1) / lanes);
-    // every lane of every launched warp runs, idle ones included (they fill their stripe of the shared tables and must
-    // not touch any job)
-    for (unsigned b = 0; b < gridDim.x; ++b)
-        for (int pass = 0; pass < 2; ++pass)               // pass 0: all lanes with no work (shared-memory tables filled), pass 1: the real run
-            for (int l = 0; l < lanes; ++l) {
-                blockIdx.x = b; threadIdx.x = (unsigned)l;
-                const int count = pass == 0 ? 0 : nseg;
-                if (kernel == 1) lep_decode_thread_kernel(descs.data(), segs.data(), 0, count, order.data(), models.data(), rows.data(), row_stride);
-                else lep_decode_lockstep_kernel(descs.data(), segs.data(), 0, count, order.data(), models.data(), rows.data(), row_stride);
-            }
+    LaunchArgs a;
+    a.kernel = kernel; a.images = descs.data(); a.segs = segs.data(); a.nseg = nseg; a.order = order.data(); a.row_stride = row_stride;
+    int counter = 0;
+    a.counter = &counter;
+    unsigned grid, block;
+    if (kernel == 0) {
+        grid = (unsigned)((nseg + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA);
+        if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
+        block = DEC_WARPS_PER_CTA * 32;
+    } else {
+        grid = (unsigned)((nseg + 31) / 32);
+        block = 32;
+    }
+    const size_t slots = kernel == 0 ? (size_t)grid * DEC_WARPS_PER_CTA : (size_t)nseg;
+    std::vector<uint16_t> models(slots * M_TOTAL, kernel == 0 ? 0x5a5a : 0);       // thread kernels: zero fill before the launch; the warp kernel clears its own
+    std::vector<uint8_t> rows(slots * row_stride, 0);
+    a.models = models.data(); a.rows = rows.data();
+    emu::launch(grid, block, kernel_body, &a);
     for (int s = 0; s < nseg; ++s) {
         if (status_out) status_out[s] = segs[s].status;
         if (ndecisions_out) ndecisions_out[s] = (uint64_t)segs[s].ndecisions_lo | ((uint64_t)segs[s].ndecisions_hi << 32);

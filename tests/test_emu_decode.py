@@ -1,8 +1,9 @@
-"""Thread-per-segment decode kernels, compiled as host C++ and run one lane at a time (tests/emu), against the oracle.
+"""The decode kernels, compiled as host C++ and run with real 32-lane warps by the CPU warp emulator (tests/emu), against
+the oracle.
 
-Both `lep_decode_thread.cu` (LEPB200_DEC_MODE=1) and `lep_decode_lockstep.cu` (LEPB200_DEC_MODE=2) give every lane its
-own segment and exchange only votes between lanes, so the per-lane arithmetic can be pinned here without a GPU; the
-GPU parity tests run the same sources under real warps.
+`lep_decode.cu` (warp per segment, the default), `lep_decode_thread.cu` (LEPB200_DEC_MODE=1) and `lep_decode_lockstep.cu`
+(LEPB200_DEC_MODE=2) run here exactly as written -- divergence, votes, shuffles, shared memory and the persistent work
+queue included -- so their logic is pinned without a GPU; the GPU parity tests run the same sources on the device.
 """
 import os
 import sys
@@ -16,7 +17,7 @@ import oracle  # noqa: E402
 from helpers import (coef_image_from_lep, geometry_of, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image,
                      random_coef_image, segments_of)
 
-KERNELS = [emu.KERNEL_THREAD, emu.KERNEL_LOCKSTEP]
+KERNELS = [emu.KERNEL_WARP, emu.KERNEL_THREAD, emu.KERNEL_LOCKSTEP]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -42,7 +43,7 @@ def test_one_launch_with_more_segments_than_a_warp(kernel):
         streams_all.append(streams[:lf.nseg])
         want.append(planes)
     assert sum(im.nseg for im in imgs) > 32
-    st, _ = emu.decode_images(kernel, imgs, streams_all)
+    st, _ = emu.decode_images(kernel, imgs, streams_all, grid_cap=3)      # warp kernel: 12 persistent warps share the queue
     assert all(s == 0 for s in st), st
     for name, img, planes in zip(golden_leps(), imgs, want):
         for c in range(img.ncmp):
@@ -103,11 +104,13 @@ def test_damaged_streams_end_the_same_way_in_both_kernels_and_the_oracle():
             img = coef_image_from_lep(lf, [np.full_like(p, 11) for p in planes])
             st, nd = emu.decode_images(kernel, [img], [bad])
             got[kernel] = (st, nd, [p.copy() for p in img.planes])
-        a, b = got[emu.KERNEL_THREAD], got[emu.KERNEL_LOCKSTEP]
-        assert a[0] == b[0] == want_rc and a[1] == b[1]
+        a = got[emu.KERNEL_THREAD]
+        for b in (got[emu.KERNEL_WARP], got[emu.KERNEL_LOCKSTEP]):
+            assert a[0] == b[0] == want_rc and a[1] == b[1]
+            for c in range(len(planes)):
+                assert np.array_equal(a[2][c], b[2][c])
         seen_bad += sum(1 for s in a[0] if s != 0)
-        for c in range(len(planes)):
-            assert np.array_equal(a[2][c], b[2][c])
-            if all(s == 0 for s in want_rc):
+        if all(s == 0 for s in want_rc):
+            for c in range(len(planes)):
                 assert np.array_equal(a[2][c], want[c])
     assert seen_bad > 0       # the damage was enough to hit the inconsistent-stream exit at least once
