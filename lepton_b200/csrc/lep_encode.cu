@@ -95,7 +95,9 @@ __device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, int base_b, 
         const uint32_t e = e_next;
         if (base + 32 < n) {
             e_next = decision_at(i + 32);
+#ifndef LEPB200_EMU      // (the CPU warp emulator of tests/emu has no use for a prefetch)
             if (i + 32 < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(model + (e_next & 0xfffffu)));
+#endif
         }
         const uint32_t addr = e & 0xfffffu, bit = e >> 31;
         const uint32_t peers = __match_any_sync(FULL, active ? addr : (0x100000u + lane));
@@ -249,8 +251,12 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
     int lane, warp_in_cta;
     {
         unsigned l, t;
+#ifndef LEPB200_EMU
         asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
         asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+#else                    // CPU warp emulator (tests/emu)
+        t = threadIdx.x; l = t & 31u;
+#endif
         lane = (int)l; warp_in_cta = (int)(t >> 5);
     }
     const int gwarp = blockIdx.x * ENC_WARPS_PER_CTA + warp_in_cta;
@@ -570,7 +576,11 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
 struct RcState { unsigned long long acc; uint32_t range; int U; uint32_t mpos, cap; uint8_t* buf; int cache; uint32_t run; };
 
 __device__ __forceinline__ void rc_store(RcState& w, uint32_t byte) {
+#ifndef LEPB200_EMU
     if (w.mpos < w.cap) asm volatile("st.global.u8 [%0], %1;" ::"l"(w.buf + w.mpos), "r"(byte) : "memory");
+#else                    // CPU warp emulator (tests/emu)
+    if (w.mpos < w.cap) w.buf[w.mpos] = (uint8_t)byte;
+#endif
     w.mpos++;
 }
 // rare path: pending 0xff run, a 0xff byte arriving, or a carry into a pending 0xff

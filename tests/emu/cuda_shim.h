@@ -180,7 +180,7 @@ inline void cta_barrier() {
     while (c.sync_gen == g) { yield(); wait_check(seen, spins, "__syncthreads"); }
 }
 
-constexpr size_t STACK_BYTES = 256 * 1024;
+constexpr size_t STACK_BYTES = 128 * 1024;
 
 // Runs grid x block CUDA threads of `body(arg)`; CTAs one after the other.
 inline void launch(unsigned grid, unsigned block, void (*body)(void*), void* arg) {

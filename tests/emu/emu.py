@@ -15,9 +15,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
-OUT = os.path.join(HERE, "_build", "libemu_decode.so")
-SOURCES = [os.path.join(HERE, "emu_decode.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
-           os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"),
+OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
+SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
+           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"),
            os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
@@ -32,7 +32,7 @@ def build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(HERE, "fake"),
-                           "-Wno-unknown-pragmas", "-o", OUT, os.path.join(HERE, "emu_decode.cc")])
+                           "-Wno-unknown-pragmas", "-o", OUT, os.path.join(HERE, "emu_kernels.cc")])
     return OUT
 
 
@@ -41,6 +41,7 @@ def lib():
     if _LIB is None:
         _LIB = ctypes.CDLL(build())
         _LIB.emu_decode_images.restype = ctypes.c_int
+        _LIB.emu_encode_images.restype = ctypes.c_int
     return _LIB
 
 
@@ -65,3 +66,25 @@ def decode_images(kernel, images, streams, grid_cap=0):
     if rc != 0:
         raise RuntimeError("emu_decode_images failed with %d" % rc)
     return list(st), list(nd)
+
+
+def encode_images(images, grid_cap=0):
+    """Same contract as LeptonB200Codec.encode_images: per image a list of (status, bytes, ndecisions) per segment."""
+    from lepton_b200.codec import _Image, _Stream
+    n = sum(im.nseg for im in images)
+    cim = (_Image * len(images))(*[im.to_c() for im in images])
+    out = (_Stream * n)()
+    cap = sum(im.blocks() for im in images) * 64 + 8192 * n
+    arena = (ctypes.c_uint8 * cap)()
+    rc = lib().emu_encode_images(int(grid_cap), cim, len(images), out, arena, ctypes.c_size_t(cap))
+    if rc != 0:
+        raise RuntimeError("emu_encode_images failed with %d" % rc)
+    res, k = [], 0
+    for im in images:
+        segs = []
+        for _ in range(im.nseg):
+            o = out[k]
+            segs.append((o.status, ctypes.string_at(o.data, o.len) if o.len else b"", int(o.ndecisions)))
+            k += 1
+        res.append(segs)
+    return res

@@ -1,14 +1,15 @@
-// emu_decode.cc -- runs the three decode kernels on the CPU under the warp emulator of cuda_shim.h (test infrastructure).
+// emu_kernels.cc -- runs the coder kernels on the CPU under the warp emulator of cuda_shim.h (test infrastructure).
 //
 // The kernel sources are compiled as host C++; this file builds the same job descriptors lep_capi.cu's build_batch /
 // lepb200_decode_upload build for the device (ImageDesc, SegDesc, order, work counter, zeroed model and row pools, zeroed
 // planes) with host addresses in place of device addresses and launches the kernel with its device launch shape.
-// Entry point mirrors lepb200_decode_images (include/lepton_b200.h) plus a kernel selector.
+// Entry points mirror lepb200_decode_images / lepb200_encode_images (include/lepton_b200.h).
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
 
 #include "cuda_shim.h"
+#include "../../lepton_b200/csrc/lep_encode.cu"
 #include "../../lepton_b200/csrc/lep_decode.cu"
 #include "../../lepton_b200/csrc/lep_decode_thread.cu"
 #include "../../lepton_b200/csrc/lep_decode_lockstep.cu"
@@ -146,6 +147,112 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
     for (int s = 0; s < nseg; ++s) {
         if (status_out) status_out[s] = segs[s].status;
         if (ndecisions_out) ndecisions_out[s] = (uint64_t)segs[s].ndecisions_lo | ((uint64_t)segs[s].ndecisions_hi << 32);
+    }
+    return 0;
+}
+
+namespace {
+
+struct EncArgs {
+    int stage;                       // 0 count, 1 offsets, 2 symbolise (kernel A), 3 range coder (kernel B)
+    const ImageDesc* images; SegDesc* segs; int nseg; const int* order; int* counter;
+    uint16_t* models; uint8_t* rows; size_t row_stride; uint16_t* tokens; unsigned long long* total;
+};
+
+void enc_body(void* p) {
+    const EncArgs& a = *static_cast<const EncArgs*>(p);
+    if (a.stage == 0) lep_count_kernel(a.images, a.segs, a.nseg);
+    else if (a.stage == 1) lep_token_offsets_kernel(a.segs, a.nseg, a.total);
+    else if (a.stage == 2) lep_encode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride, a.tokens);
+    else lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
+}
+
+}  // namespace
+
+// lepb200_encode_images on the emulator: count pre-pass -> token offsets -> kernel A (symbolise + model) -> kernel B
+// (range coder), with the launch shapes of lep_capi.cu.  `out` must hold sum(nseg) entries; the bytes of every stream are
+// copied into `arena` (capacity arena_cap) back to back and out[i].data points there.  grid_cap > 0 limits kernel A's
+// CTAs (persistent warps then take several segments each).
+extern "C" int emu_encode_images(int grid_cap, const lepb200_image* images, int nimages, lepb200_stream* out, uint8_t* arena, size_t arena_cap) {
+    if (nimages <= 0 || !images || !out || !arena) return LEPB200_ERR_INVALID;
+    std::vector<ImageDesc> descs(nimages);
+    std::vector<SegDesc> segs;
+    std::vector<size_t> seg_blocks;
+    size_t row_stride = 0, stream_total = 0;
+    for (int i = 0; i < nimages; ++i) {
+        const lepb200_image& im = images[i];
+        if (im.ncmp < 1 || im.ncmp > 3 || im.mcuv <= 0 || im.nseg < 1 || im.nseg > LEPB200_MAX_SEGMENTS) return LEPB200_ERR_INVALID;
+        ImageDesc& d = descs[i];
+        memset(&d, 0, sizeof(d));
+        d.ncmp = im.ncmp; d.mcuv = im.mcuv;
+        int qstatus = 0;
+        size_t rs = 0;
+        for (int c = 0; c < im.ncmp; ++c) {
+            d.bch[c] = im.bch[c]; d.bcv[c] = im.bcv[c]; d.trunc_bcv[c] = im.trunc_bcv[c]; d.trunc_bc[c] = im.trunc_bc[c];
+            d.mult[c] = im.bcv[c] / im.mcuv;
+            const int qs = fill_quant(d, c, im.qtable_zigzag[c]);
+            if (qs) qstatus = qs;
+            d.plane[c] = (unsigned long long)(uintptr_t)im.planes[c];
+            rs += (size_t)im.bch[c] * 16 + align_up((size_t)im.bch[c], 16);
+        }
+        row_stride = std::max(row_stride, align_up(rs, 256));
+        for (int s = 0; s < im.nseg; ++s) {
+            SegDesc sd;
+            memset(&sd, 0, sizeof(sd));
+            sd.image = i;
+            sd.min_y = im.luma_y_start[s];
+            sd.is_last = s + 1 == im.nseg;
+            sd.max_y = sd.is_last ? im.bcv[0] : im.luma_y_start[s + 1];
+            sd.status = qstatus;
+            size_t nb = 0;
+            const int v0 = std::max(im.bcv[0] / im.mcuv, 1);
+            for (int c = 0; c < im.ncmp; ++c) {
+                const int mult = im.bcv[c] / im.mcuv;
+                long y0 = (long)(sd.min_y / v0) * mult, y1 = sd.is_last ? im.trunc_bcv[c] : (long)((sd.max_y + v0 - 1) / v0) * mult;
+                y1 = std::min<long>(y1, im.trunc_bcv[c]);
+                if (y1 > y0) nb += (size_t)(y1 - y0) * im.bch[c];
+            }
+            seg_blocks.push_back(nb);
+            const size_t cap = align_up(nb * 64 + 4096, 256);
+            sd.stream = stream_total; sd.cap = (uint32_t)cap;
+            stream_total += cap;
+            segs.push_back(sd);
+        }
+    }
+    const int nseg = (int)segs.size();
+    std::vector<uint8_t> streams(stream_total + 256, 0);
+    for (auto& sd : segs) sd.stream += (unsigned long long)(uintptr_t)streams.data();
+    std::vector<int> order(nseg);
+    for (int i = 0; i < nseg; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg_blocks[a] > seg_blocks[b]; });
+
+    EncArgs a;
+    a.images = descs.data(); a.segs = segs.data(); a.nseg = nseg; a.order = order.data(); a.row_stride = row_stride;
+    int counter = 0;
+    unsigned long long total_tokens = 0;
+    a.counter = &counter; a.total = &total_tokens; a.models = nullptr; a.rows = nullptr; a.tokens = nullptr;
+    a.stage = 0; emu::launch((unsigned)nseg, CNT_THREADS, enc_body, &a);
+    a.stage = 1; emu::launch(1, 1024, enc_body, &a);
+    std::vector<uint16_t> tokens((size_t)total_tokens + 128, 0);
+    a.tokens = tokens.data();
+    unsigned grid = (unsigned)((nseg + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA);
+    if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
+    std::vector<uint16_t> models((size_t)grid * ENC_WARPS_PER_CTA * M_TOTAL, 0x5a5a);      // the kernel clears its own
+    std::vector<uint8_t> rows((size_t)grid * ENC_WARPS_PER_CTA * row_stride, 0);
+    a.models = models.data(); a.rows = rows.data();
+    a.stage = 2; emu::launch(grid, ENC_WARPS_PER_CTA * 32, enc_body, &a);
+    a.stage = 3; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+    size_t used = 0;
+    for (int s = 0; s < nseg; ++s) {
+        const size_t n = segs[s].status == 0 ? segs[s].len : 0;
+        if (used + n > arena_cap) return LEPB200_ERR_NOMEM;
+        memcpy(arena + used, reinterpret_cast<const uint8_t*>(segs[s].stream), n);
+        out[s].data = arena + used;
+        out[s].len = n;
+        out[s].status = segs[s].status;
+        out[s].reserved = 0;
+        out[s].ndecisions = (uint64_t)segs[s].ndecisions_lo | ((uint64_t)segs[s].ndecisions_hi << 32);
+        used += n;
     }
     return 0;
 }
