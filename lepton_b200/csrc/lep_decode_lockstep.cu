@@ -27,22 +27,27 @@ namespace lepb200 {
 constexpr int DECL_THREADS = 32;          // one warp per CTA
 
 struct LBool {                            // vpx_reader (boolreader.hh:184-258), per lane
-    unsigned long long value;
+    unsigned long long value;             // stream bits, left aligned
     uint32_t range;
-    int count;
-    const uint8_t* p;
+    int valid;                            // bits of `value` that come from the stream (the rest are zero)
+    const uint8_t* p;                     // next 32-bit word of the stream (streams start 16-byte aligned)
     const uint8_t* end;
 };
 
-__device__ __forceinline__ void l_fill(LBool& r) {
-    int shift = 64 - 8 - (r.count + 8);
-    while (shift >= 0) {
-        const unsigned long long byte = (r.p < r.end) ? (unsigned long long)__ldg(r.p) : 0ull;
-        r.p++;
-        r.value |= byte << shift;
-        r.count += 8;
-        shift -= 8;
+// The reference tops its window up byte by byte whenever fewer than 8 bits are left (vpx_reader_fill); what a decision
+// sees is only the top byte of the window, and bits past the end of the stream read as zero.  Here the window takes one
+// aligned big-endian 32-bit word whenever fewer than 32 bits are left: same bits in the same positions, and a refill is a
+// handful of instructions -- it matters because in a lock-step warp ANY lane's refill is paid by all 32.
+__device__ __forceinline__ void l_refill(LBool& r) {
+    uint32_t w = 0;
+    const long long rem = r.end - r.p;
+    if (rem > 0) {
+        w = __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(r.p)), 0u, 0x0123u);
+        if (rem < 4) w &= 0xffffffffu << (8 * (4 - (int)rem));        // the padding behind a stream is readable but not zero
     }
+    r.value |= (unsigned long long)w << (32 - r.valid);
+    r.valid += 32;
+    r.p += 4;
 }
 
 // VPXBoolReader::get (vpx_bool_reader.hh:45-57) = vpx_read + Branch::record_obs_and_update
@@ -50,7 +55,7 @@ __device__ __forceinline__ uint32_t l_get(LBool& r, uint16_t* model, const uint3
     const uint32_t w = model[addr];
     const uint32_t prob = branch_prob(w, rcp);
     const uint32_t split = (r.range * prob + (256 - prob)) >> 8;
-    if (r.count < 0) l_fill(r);
+    if (r.valid < 32) l_refill(r);
     const uint32_t top = (uint32_t)(r.value >> 56);               // value >= split << 56  <=>  top byte >= split
     const uint32_t bit = top >= split;
     const uint32_t range = bit ? r.range - split : split;
@@ -58,7 +63,7 @@ __device__ __forceinline__ uint32_t l_get(LBool& r, uint16_t* model, const uint3
     const int shift = __clz(range) - 24;
     r.range = range << shift;
     r.value <<= shift;
-    r.count -= shift;
+    r.valid -= shift;
     const bool plain = (w & 0xffu) < 254u && (w >> 8) < 254u;       // no count about to saturate, not the special state
     model[addr] = (uint16_t)(plain ? w + (bit ? 0x100u : 1u) : branch_update(w, bit));
     return bit;
@@ -173,18 +178,18 @@ lep_decode_lockstep_kernel(const ImageDesc* __restrict__ images, SegDesc* __rest
     uint16_t* model = model_pool + (size_t)(t < count ? t : 0) * M_TOTAL;       // zero-filled before the launch
 
     LBool br;
-    br.value = 0; br.count = -8; br.range = 255; br.p = nullptr; br.end = nullptr;
+    br.value = 0; br.valid = 0; br.range = 255; br.p = nullptr; br.end = nullptr;
     unsigned long long ndec = 0;
     if (alive) {
         br.p = reinterpret_cast<const uint8_t*>(sdp->stream); br.end = br.p + sdp->cap;
-        l_fill(br);
+        l_refill(br);
         // marker bit at p = 128 (boolreader.cc:26-35); no model involved
         const uint32_t split = (br.range * 128u + 128u) >> 8;
         const uint32_t bit = (uint32_t)(br.value >> 56) >= split;
         const uint32_t range = bit ? br.range - split : split;
         if (bit) br.value -= (unsigned long long)split << 56;
         const int shift = __clz(range) - 24;
-        br.range = range << shift; br.value <<= shift; br.count -= shift;
+        br.range = range << shift; br.value <<= shift; br.valid -= shift;
     }
 
     const int bw0 = g.bch[0], bw1 = g.ncmp > 1 ? g.bch[1] : 0, bw2 = g.ncmp > 2 ? g.bch[2] : 0;
@@ -498,7 +503,7 @@ lep_decode_lockstep_kernel(const ImageDesc* __restrict__ images, SegDesc* __rest
     }
     if (report) {
         sdp->status = status;
-        sdp->len = (uint32_t)(br.p - reinterpret_cast<const uint8_t*>(sdp->stream));
+        sdp->len = (uint32_t)(br.p - reinterpret_cast<const uint8_t*>(sdp->stream));        // whole words, so up to 7 bytes past the other kernels' figure
         sdp->ndecisions_lo = (uint32_t)ndec;
         sdp->ndecisions_hi = (uint32_t)(ndec >> 32);
     }

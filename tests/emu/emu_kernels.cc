@@ -105,7 +105,7 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
             sd.max_y = sd.is_last ? im.bcv[0] : im.luma_y_start[s + 1];
             sd.status = qstatus;
             const lepb200_stream& st = in[segs.size()];
-            padded.emplace_back((size_t)st.len + 16, 0);
+            padded.emplace_back((size_t)st.len + 16, 0xA5);      // the device arena is not cleared: whatever is behind a stream must not matter
             if (st.len) memcpy(padded.back().data(), st.data, (size_t)st.len);
             sd.cap = (uint32_t)st.len;
             size_t nb = 0;                                  // segment_blocks of lep_capi.cu: only the launch order depends on it
