@@ -53,6 +53,9 @@ __device__ __forceinline__ void l_refill(LBool& r) {
 // VPXBoolReader::get (vpx_bool_reader.hh:45-57) = vpx_read + Branch::record_obs_and_update
 __device__ __forceinline__ uint32_t l_get(LBool& r, uint16_t* model, const uint32_t* rcp, uint32_t addr) {
     const uint32_t w = model[addr];
+#ifdef LEPB200_EMU_TRACE                 // tests/tools_model_reuse.py: cache footprint of a lane's model accesses
+    emu_trace_model_access(model, addr);
+#endif
     const uint32_t prob = branch_prob(w, rcp);
     const uint32_t split = (r.range * prob + (256 - prob)) >> 8;
     if (r.valid < 32) l_refill(r);
