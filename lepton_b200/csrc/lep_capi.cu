@@ -74,9 +74,12 @@ struct lepb200_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+    cudaStream_t stream2 = nullptr;        // decode mode 3: the lock-step kernel's share runs beside the warp kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_images, d_segs, d_order, d_counter, d_models, d_rows;
     DevBuf d_henc_out, d_henc_imgs, d_henc_segs, d_henc_tabs;
+    DevBuf d_models2, d_rows2;             // decode mode 3: models / row buffers of the lock-step share
     HostBuf h_henc_out, h_henc_segs;
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
     std::vector<int> henc_seg_first;      // per image: index of its first segment record
@@ -101,7 +104,11 @@ struct lepb200_ctx {
     int host_threads = 1;                 // host threads this context may use for staging copies
     int dec_mode = 0;                     // decode kernel: 0 = one warp per segment (default), 1 = one thread per segment (wins only when
                                           // tens of thousands of segments are in flight), 2 = one thread per segment with
-                                          // the lanes of a warp in lock step (lep_decode_lockstep.cu)
+                                          // the lanes of a warp in lock step (lep_decode_lockstep.cu), 3 = both at once: the largest
+                                          // dec_split_pct % of the segments on the lock-step kernel (latency bound, few issue slots),
+                                          // the rest on the warp kernel (issue bound)
+    int dec_split_pct = 50;
+    int dec_lock = 0;                     // mode 3: segments of the current batch that go to the lock-step kernel
     int dec_threads_max = 16384;          // thread mode: segments per launch (one 1.58 MB model each)
     int dec_threads = 0;                  // thread mode: model / row-buffer slots of the current batch
     bool tokens_known = false;            // token streams laid out on the host from caller-supplied bounds (no counting pre-pass)
@@ -260,13 +267,23 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
     CK(ctx->d_counter.reserve(256));
-    if (!encode && ctx->dec_mode >= 1) {
+    ctx->dec_lock = 0;
+    if (!encode && (ctx->dec_mode == 1 || ctx->dec_mode == 2)) {
         ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)ctx->dec_threads * row_stride));
     } else {
         CK(ctx->d_models.reserve((size_t)grid * wpc * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
+        if (!encode && ctx->dec_mode == 3) {
+            // whole warps of the largest segments for the lock-step kernel
+            const int want = (int)((long long)nseg * ctx->dec_split_pct / 100);
+            ctx->dec_lock = std::min(std::min(want, ctx->dec_threads_max), nseg) / 32 * 32;
+            if (ctx->dec_lock > 0) {
+                CK(ctx->d_models2.reserve((size_t)ctx->dec_lock * MODEL_BYTES));
+                CK(ctx->d_rows2.reserve((size_t)ctx->dec_lock * row_stride));
+            }
+        }
     }
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < ctx->images[i].ncmp; ++c) ctx->images[i].plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
@@ -325,6 +342,13 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
+    if (const char* e = getenv("LEPB200_DEC_SPLIT")) ctx->dec_split_pct = std::min(100, std::max(0, atoi(e)));
+    if (ctx->dec_mode == 3 && (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+                               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                               cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+        lepb200_destroy(ctx);
+        return LEPB200_ERR_CUDA;
+    }
     *out = ctx;
     return LEPB200_OK;
 }
@@ -337,12 +361,15 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
+    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_models2, &ctx->d_rows2})
         b->release();
     for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs}) b->release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_mid);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -829,7 +856,7 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->dec_mode >= 1) {
+    if (ctx->dec_mode == 1 || ctx->dec_mode == 2) {
         // one thread per segment, largest segments first; a launch covers as many segments as there are model slots
         // (mode 1: free-running lanes, mode 2: lanes in lock step)
         const auto kernel = ctx->dec_mode == 2 ? lep_decode_lockstep_kernel : lep_decode_thread_kernel;
@@ -844,6 +871,25 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
             ctx->launches += 1;
         }
         ctx->launches -= 1;
+    } else if (ctx->dec_mode == 3 && ctx->dec_lock > 0) {
+        // both kernels at once: order[0, k) -> lock-step kernel on the second stream, order[k, nseg) -> warp kernel
+        const int k = ctx->dec_lock;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        CK(cudaMemsetAsync(ctx->d_models2.p, 0, (size_t)k * MODEL_BYTES, ctx->stream2));
+        lep_decode_lockstep_kernel<<<(k + DECL_THREADS - 1) / DECL_THREADS, DECL_THREADS, 0, ctx->stream2>>>(
+            static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), 0, k, static_cast<const int*>(ctx->d_order.p),
+            static_cast<uint16_t*>(ctx->d_models2.p), static_cast<uint8_t*>(ctx->d_rows2.p), ctx->row_stride);
+        CK(cudaGetLastError());
+        if (nseg > k) {
+            lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
+                static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg - k, static_cast<const int*>(ctx->d_order.p) + k,
+                static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+        }
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else {
         lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
             static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),

@@ -65,10 +65,13 @@ def test_golden_batch_decode_thread_per_segment_kernel(monkeypatch):
 @pytest.mark.skipif(os.environ.get("LEPB200_TEST_LOCKSTEP") != "1",
                     reason="lock-step decode kernel: pinned on the CPU (tests/test_emu_decode.py), first GPU run pending; "
                            "set LEPB200_TEST_LOCKSTEP=1 (and run under `timeout`) to include it")
-def test_golden_batch_decode_lockstep_kernel(monkeypatch):
-    """The lock-step thread-per-segment decode kernel (LEPB200_DEC_MODE=2) must give the same planes."""
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_golden_batch_decode_lockstep_kernel(monkeypatch, mode):
+    """The lock-step thread-per-segment decode kernel must give the same planes: alone (LEPB200_DEC_MODE=2) and sharing
+    the batch with the warp kernel on a second stream (mode 3: the largest half of the segments on the lock-step kernel)."""
     from lepton_b200 import LeptonB200Codec
-    monkeypatch.setenv("LEPB200_DEC_MODE", "2")
+    monkeypatch.setenv("LEPB200_DEC_MODE", mode)
+    monkeypatch.setenv("LEPB200_DEC_SPLIT", "90")          # mode 3: one full warp of segments for the lock-step kernel, the rest for the warp kernel
     c = LeptonB200Codec(0)
     try:
         test_golden_batch_decode_matches_reference_planes(c)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Decode kernel comparison on the GPU box (diagnostic): parity of the lock-step kernel first, then the decode leg of
-# bench.py for the three kernels, then a launch list and one full ncu capture of the lock-step kernel.
+# bench.py for the kernels (0 warp per segment, 1 thread per segment, 2 lock step, 3 lock step + warp kernel side by side), then a launch list and one full ncu capture of the lock-step kernel.
 #   gpurun --timeout 1500 -- 'bash tests/tools_decode_modes.sh'
 # Everything runs under `timeout` so that a kernel that does not terminate costs one step, not the box.
 mkdir -p gpurun_out
@@ -8,12 +8,13 @@ echo "== parity, LEPB200_DEC_MODE=2"
 LEPB200_TEST_LOCKSTEP=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "lockstep or thread_per_segment" 2>&1 | tail -3
 echo "== decode leg, 1024 and 4096 images"
 for images in 1024 4096; do
-  for mode in 0 1 2; do
-    for thr in 16384; do
-      LEPB200_DEC_MODE=$mode LEPB200_DEC_THREADS=$thr timeout 600 python bench.py --images $images --no-e2e --no-cpu-baseline --steps 2 --warmup 3 2>/dev/null | tail -1 | python -c "
+  for cfg in "0 16384 50" "1 16384 50" "2 16384 50" "2 8192 50" "3 16384 50" "3 16384 25" "3 16384 75"; do
+    set -- $cfg; mode=$1; thr=$2; split=$3
+    for once in 1; do
+      LEPB200_DEC_MODE=$mode LEPB200_DEC_THREADS=$thr LEPB200_DEC_SPLIT=$split timeout 600 python bench.py --images $images --no-e2e --no-cpu-baseline --steps 2 --warmup 3 2>/dev/null | tail -1 | python -c "
 import json,sys
 try:
-    d=json.loads(sys.stdin.read()); print('images $images mode $mode threads $thr  decode ms', round(d['decode']['ms_per_step'],1), ' MB/s', round(d['decode']['value'],1), ' round trip', d.get('roundtrip_pass_rate'))
+    d=json.loads(sys.stdin.read()); print('images $images mode $mode threads $thr split $split  decode ms', round(d['decode']['ms_per_step'],1), ' MB/s', round(d['decode']['value'],1), ' round trip', d.get('roundtrip_pass_rate'))
 except Exception as e: print('images $images mode $mode: no result', e)"
     done
   done
