@@ -13,6 +13,7 @@
 #include "lep_common.cuh"
 #include "lep_predict.cuh"
 #include "lep_encode.cu"
+#include "lep_encode_lockstep.cu"
 #include "lep_decode.cu"
 #include "lep_decode_thread.cu"
 #include "lep_decode_lockstep.cu"
@@ -107,6 +108,9 @@ struct lepb200_ctx {
                                           // the lanes of a warp in lock step (lep_decode_lockstep.cu), 3 = both at once: the largest
                                           // dec_split_pct % of the segments on the lock-step kernel (latency bound, few issue slots),
                                           // the rest on the warp kernel (issue bound)
+    int enc_mode = 0;                     // kernel A: 0 = one warp per segment (default), 1 = one thread per segment, lanes in lock step
+                                          // (lep_encode_lockstep.cu); model / row-buffer slots as in the decode thread modes
+    int enc_threads = 0;
     int dec_split_pct = 50;
     int dec_lock = 0;                     // mode 3: segments of the current batch that go to the lock-step kernel
     int dec_threads_max = 16384;          // thread mode: segments per launch (one 1.58 MB model each)
@@ -268,7 +272,11 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
     CK(ctx->d_counter.reserve(256));
     ctx->dec_lock = 0;
-    if (!encode && (ctx->dec_mode == 1 || ctx->dec_mode == 2)) {
+    if (encode && ctx->enc_mode == 1) {
+        ctx->enc_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
+        CK(ctx->d_models.reserve((size_t)ctx->enc_threads * MODEL_BYTES));
+        CK(ctx->d_rows.reserve((size_t)ctx->enc_threads * row_stride));
+    } else if (!encode && (ctx->dec_mode == 1 || ctx->dec_mode == 2)) {
         ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)ctx->dec_threads * row_stride));
@@ -342,6 +350,7 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
+    if (const char* e = getenv("LEPB200_ENC_MODE")) ctx->enc_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_SPLIT")) ctx->dec_split_pct = std::min(100, std::max(0, atoi(e)));
     if (ctx->dec_mode == 3 && (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
                                cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -638,11 +647,25 @@ int lepb200_encode_launch_symbolise(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    lep_encode_kernel<<<ctx->grid, ENC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
-        static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
-        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride,
-        static_cast<uint16_t*>(ctx->d_tokens.p));
-    CK(cudaGetLastError());
+    if (ctx->enc_mode == 1) {
+        // one thread per segment, lanes in lock step; a launch covers as many segments as there are model slots
+        for (int first = 0; first < nseg; first += ctx->enc_threads) {
+            const int count = std::min(ctx->enc_threads, nseg - first);
+            CK(cudaMemsetAsync(ctx->d_models.p, 0, (size_t)count * MODEL_BYTES, ctx->stream));       // identity prior = zero fill
+            lep_encode_lockstep_kernel<<<(count + ENCL_THREADS - 1) / ENCL_THREADS, ENCL_THREADS, 0, ctx->stream>>>(
+                static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), first, count, static_cast<const int*>(ctx->d_order.p),
+                static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride, static_cast<uint16_t*>(ctx->d_tokens.p));
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+        }
+        ctx->launches -= 1;
+    } else {
+        lep_encode_kernel<<<ctx->grid, ENC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
+            static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
+            static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride,
+            static_cast<uint16_t*>(ctx->d_tokens.p));
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
     ctx->launches += 1;
     ctx->symbolised = true;

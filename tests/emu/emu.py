@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
 SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
-           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"),
+           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_encode_lockstep.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"),
            os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
@@ -68,7 +68,11 @@ def decode_images(kernel, images, streams, grid_cap=0):
     return list(st), list(nd)
 
 
-def encode_images(images, grid_cap=0):
+ENC_KERNEL_A = 0
+ENC_KERNEL_LOCKSTEP = 1
+
+
+def encode_images(images, grid_cap=0, kernel=0):
     """Same contract as LeptonB200Codec.encode_images: per image a list of (status, bytes, ndecisions) per segment."""
     from lepton_b200.codec import _Image, _Stream
     n = sum(im.nseg for im in images)
@@ -76,7 +80,7 @@ def encode_images(images, grid_cap=0):
     out = (_Stream * n)()
     cap = sum(im.blocks() for im in images) * 64 + 8192 * n
     arena = (ctypes.c_uint8 * cap)()
-    rc = lib().emu_encode_images(int(grid_cap), cim, len(images), out, arena, ctypes.c_size_t(cap))
+    rc = lib().emu_encode_images(int(kernel), int(grid_cap), cim, len(images), out, arena, ctypes.c_size_t(cap))
     if rc != 0:
         raise RuntimeError("emu_encode_images failed with %d" % rc)
     res, k = [], 0

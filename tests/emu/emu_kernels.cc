@@ -10,6 +10,7 @@
 
 #include "cuda_shim.h"
 #include "../../lepton_b200/csrc/lep_encode.cu"
+#include "../../lepton_b200/csrc/lep_encode_lockstep.cu"
 #include "../../lepton_b200/csrc/lep_decode.cu"
 #include "../../lepton_b200/csrc/lep_decode_thread.cu"
 #include "../../lepton_b200/csrc/lep_decode_lockstep.cu"
@@ -154,7 +155,7 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
 namespace {
 
 struct EncArgs {
-    int stage;                       // 0 count, 1 offsets, 2 symbolise (kernel A), 3 range coder (kernel B)
+    int stage;                       // 0 count, 1 offsets, 2 symbolise (kernel A), 3 range coder (kernel B), 4 symbolise (lock-step kernel)
     const ImageDesc* images; SegDesc* segs; int nseg; const int* order; int* counter;
     uint16_t* models; uint8_t* rows; size_t row_stride; uint16_t* tokens; unsigned long long* total;
 };
@@ -164,7 +165,8 @@ void enc_body(void* p) {
     if (a.stage == 0) lep_count_kernel(a.images, a.segs, a.nseg);
     else if (a.stage == 1) lep_token_offsets_kernel(a.segs, a.nseg, a.total);
     else if (a.stage == 2) lep_encode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride, a.tokens);
-    else lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
+    else if (a.stage == 3) lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
+    else lep_encode_lockstep_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride, a.tokens);
 }
 
 }  // namespace
@@ -172,8 +174,8 @@ void enc_body(void* p) {
 // lepb200_encode_images on the emulator: count pre-pass -> token offsets -> kernel A (symbolise + model) -> kernel B
 // (range coder), with the launch shapes of lep_capi.cu.  `out` must hold sum(nseg) entries; the bytes of every stream are
 // copied into `arena` (capacity arena_cap) back to back and out[i].data points there.  grid_cap > 0 limits kernel A's
-// CTAs (persistent warps then take several segments each).
-extern "C" int emu_encode_images(int grid_cap, const lepb200_image* images, int nimages, lepb200_stream* out, uint8_t* arena, size_t arena_cap) {
+// CTAs (persistent warps then take several segments each).  kernel: 0 = lep_encode_kernel, 1 = lep_encode_lockstep_kernel.
+extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, lepb200_stream* out, uint8_t* arena, size_t arena_cap) {
     if (nimages <= 0 || !images || !out || !arena) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
     std::vector<SegDesc> segs;
@@ -235,12 +237,21 @@ extern "C" int emu_encode_images(int grid_cap, const lepb200_image* images, int 
     a.stage = 1; emu::launch(1, 1024, enc_body, &a);
     std::vector<uint16_t> tokens((size_t)total_tokens + 128, 0);
     a.tokens = tokens.data();
-    unsigned grid = (unsigned)((nseg + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA);
-    if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
-    std::vector<uint16_t> models((size_t)grid * ENC_WARPS_PER_CTA * M_TOTAL, 0x5a5a);      // the kernel clears its own
-    std::vector<uint8_t> rows((size_t)grid * ENC_WARPS_PER_CTA * row_stride, 0);
-    a.models = models.data(); a.rows = rows.data();
-    a.stage = 2; emu::launch(grid, ENC_WARPS_PER_CTA * 32, enc_body, &a);
+    std::vector<uint16_t> models;
+    std::vector<uint8_t> rows;
+    if (kernel == 0) {
+        unsigned grid = (unsigned)((nseg + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA);
+        if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
+        models.assign((size_t)grid * ENC_WARPS_PER_CTA * M_TOTAL, 0x5a5a);      // the kernel clears its own
+        rows.assign((size_t)grid * ENC_WARPS_PER_CTA * row_stride, 0);
+        a.models = models.data(); a.rows = rows.data();
+        a.stage = 2; emu::launch(grid, ENC_WARPS_PER_CTA * 32, enc_body, &a);
+    } else {
+        models.assign((size_t)nseg * M_TOTAL, 0);                               // zero fill before the launch
+        rows.assign((size_t)nseg * row_stride, 0);
+        a.models = models.data(); a.rows = rows.data();
+        a.stage = 4; emu::launch((unsigned)((nseg + ENCL_THREADS - 1) / ENCL_THREADS), ENCL_THREADS, enc_body, &a);
+    }
     a.stage = 3; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
     size_t used = 0;
     for (int s = 0; s < nseg; ++s) {

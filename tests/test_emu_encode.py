@@ -1,7 +1,7 @@
-"""The encode kernels -- count pre-pass, token offsets, kernel A (symbolise + adaptive model), kernel B (range coder) --
-compiled as host C++ and run with real 32-lane warps by the CPU warp emulator (tests/emu), against the reference's
-streams and the oracle.  Same cases as the GPU parity tests of the encoder; the GPU tests run the same sources on the
-device."""
+"""The encode kernels -- count pre-pass, token offsets, kernel A (symbolise + adaptive model) or its lock-step
+thread-per-segment counterpart (lep_encode_lockstep.cu, LEPB200_ENC_MODE=1), kernel B (range coder) -- compiled as host
+C++ and run with real 32-lane warps by the CPU warp emulator (tests/emu), against the reference's streams and the
+oracle.  Same cases as the GPU parity tests of the encoder; the GPU tests run the same sources on the device."""
 import os
 import sys
 
@@ -13,7 +13,11 @@ import emu  # noqa: E402
 from helpers import coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image, random_coef_image
 
 
-def test_golden_batch_encode_matches_reference_streams():
+KERNELS = [emu.ENC_KERNEL_A, emu.ENC_KERNEL_LOCKSTEP]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_batch_encode_matches_reference_streams(kernel):
     """All committed reference-written .lep files in ONE batch, three persistent CTAs sharing the work queue: emulated GPU
     streams == the reference's streams."""
     imgs, want = [], []
@@ -22,7 +26,7 @@ def test_golden_batch_encode_matches_reference_streams():
         planes, streams = oracle_decode_planes(lf)
         imgs.append(coef_image_from_lep(lf, planes))
         want.append(streams[:lf.nseg])
-    got = emu.encode_images(imgs, grid_cap=3)
+    got = emu.encode_images(imgs, grid_cap=3, kernel=kernel)
     for name, g, w in zip(golden_leps(), got, want):
         assert [x[0] for x in g] == [0] * len(w), name
         assert [x[1] for x in g] == list(w), name
@@ -40,12 +44,13 @@ def test_golden_batch_encode_matches_reference_streams():
     dict(ncmp=3, mcuh=12, mcuv=8, sf=((2, 2), (1, 1), (1, 1)), nseg=8, density=0.9, amp=100, qscale=0.3),   # dense, large coefficients
     dict(ncmp=3, mcuh=8, mcuv=8, sf=((2, 2), (1, 1), (1, 1)), nseg=1, density=0.0, amp=1),     # (almost) empty blocks
 ])
-def test_random_planes_encode_vs_oracle_and_decode_back(cfg):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_random_planes_encode_vs_oracle_and_decode_back(kernel, cfg):
     from lepton_b200 import CoefImage
     rng = np.random.default_rng(1234)
     img = random_coef_image(rng, **cfg)
     ref = oracle_encode_image(img)
-    got = emu.encode_images([img])[0]
+    got = emu.encode_images([img], kernel=kernel)[0]
     assert [(g[0], g[1], g[2]) for g in got] == [(rc, s, nd) for rc, s, nd in ref]
     out = CoefImage(ncmp=img.ncmp, mcuv=img.mcuv, bch=img.bch, bcv=img.bcv, qtables_zigzag=img.qtables_zigzag,
                     planes=[np.full_like(p, -5) for p in img.planes], luma_y_start=img.luma_y_start)
@@ -55,18 +60,20 @@ def test_random_planes_encode_vs_oracle_and_decode_back(cfg):
         assert np.array_equal(out.planes[c], img.planes[c])
 
 
-def test_out_of_range_coefficient_status():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_out_of_range_coefficient_status(kernel):
     """COEFFICIENT_OUT_OF_RANGE (reference exit code 6, src/vp8/encoder/encoder.cc:124,265,343)."""
     rng = np.random.default_rng(5)
     img = random_coef_image(rng, ncmp=1, mcuh=4, mcuv=4, sf=((1, 1),), nseg=2)
     img.planes[0][3, 7] = 4096          # 13-bit magnitude in the first segment only
     ref = oracle_encode_image(img)
-    got = emu.encode_images([img])[0]
+    got = emu.encode_images([img], kernel=kernel)[0]
     assert [g[0] for g in got] == [r[0] for r in ref] == [6, 0]
     assert got[1][1] == ref[1][1]
 
 
-def test_branch_saturation_long_run():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_branch_saturation_long_run(kernel):
     """Long constant runs drive branch counts through the 255 overflow / 'neverseen' paths (branch.hh:82-100): the
     closed-form conflict resolution of kernel A has to fall back to its rank loop there."""
     from lepton_b200 import CoefImage
@@ -77,11 +84,12 @@ def test_branch_saturation_long_run():
     p[:, 49] = 5
     img = CoefImage(ncmp=1, mcuv=40, bch=[40], bcv=[40], qtables_zigzag=[[8] * 64], planes=[p], luma_y_start=[0])
     (rc, s, nd), = oracle_encode_image(img)
-    got = emu.encode_images([img])[0][0]
+    got = emu.encode_images([img], kernel=kernel)[0][0]
     assert rc == 0 and got == (0, s, nd)
 
 
-def test_mixed_batch_many_images():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_mixed_batch_many_images(kernel):
     """A batch of different geometries in one launch: per-image results must not depend on batching."""
     rng = np.random.default_rng(99)
     imgs = []
@@ -89,7 +97,7 @@ def test_mixed_batch_many_images():
         ncmp = 1 if k % 5 == 0 else 3
         sf = ((1, 1),) if ncmp == 1 else (((2, 2), (1, 1), (1, 1)) if k % 2 else ((1, 1), (1, 1), (1, 1)))
         imgs.append(random_coef_image(rng, ncmp=ncmp, mcuh=2 + k % 7, mcuv=2 + (k * 3) % 5, sf=sf, nseg=1 + k % 3))
-    got = emu.encode_images(imgs, grid_cap=2)
+    got = emu.encode_images(imgs, grid_cap=2, kernel=kernel)
     for img, g in zip(imgs, got):
         ref = oracle_encode_image(img)
         assert [x[1] for x in g] == [r[1] for r in ref]

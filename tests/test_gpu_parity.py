@@ -63,6 +63,20 @@ def test_golden_batch_decode_thread_per_segment_kernel(monkeypatch):
 
 
 @pytest.mark.skipif(os.environ.get("LEPB200_TEST_LOCKSTEP") != "1",
+                    reason="lock-step encode kernel: pinned on the CPU (tests/test_emu_encode.py), first GPU run pending; "
+                           "set LEPB200_TEST_LOCKSTEP=1 (and run under `timeout`) to include it")
+def test_golden_batch_encode_lockstep_kernel(monkeypatch):
+    """The lock-step thread-per-segment kernel A (LEPB200_ENC_MODE=1) must give the reference's streams."""
+    from lepton_b200 import LeptonB200Codec
+    monkeypatch.setenv("LEPB200_ENC_MODE", "1")
+    c = LeptonB200Codec(0)
+    try:
+        test_golden_batch_encode_matches_reference_streams(c)
+    finally:
+        c.close()
+
+
+@pytest.mark.skipif(os.environ.get("LEPB200_TEST_LOCKSTEP") != "1",
                     reason="lock-step decode kernel: pinned on the CPU (tests/test_emu_decode.py), first GPU run pending; "
                            "set LEPB200_TEST_LOCKSTEP=1 (and run under `timeout`) to include it")
 @pytest.mark.parametrize("mode", ["2", "3"])
