@@ -27,13 +27,26 @@ KERNEL_LOCKSTEP = 2
 _LIB = None
 
 
-def build():
-    if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in SOURCES):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+def build(out=OUT, defines=()):
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in SOURCES):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(HERE, "fake"),
-                           "-Wno-unknown-pragmas", "-o", OUT, os.path.join(HERE, "emu_kernels.cc")])
-    return OUT
+                           "-Wno-unknown-pragmas"] + ["-D" + d for d in defines] + ["-o", out, os.path.join(HERE, "emu_kernels.cc")])
+    return out
+
+
+def use_variant(name, defines):
+    """Switches this module to a build of the harness with extra -D defines (e.g. another model layout)."""
+    global _LIB
+    _LIB = ctypes.CDLL(build(os.path.join(HERE, "_build", "libemu_kernels_%s.so" % name), defines))
+    _LIB.emu_decode_images.restype = ctypes.c_int
+    _LIB.emu_encode_images.restype = ctypes.c_int
+
+
+def use_default():
+    global _LIB
+    _LIB = None
 
 
 def lib():

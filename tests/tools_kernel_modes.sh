@@ -29,6 +29,7 @@ try:
 except Exception as e: print('images $images enc mode $mode: no result', e)"
   done
 done
+echo "== (rebuild with LEPB200_MODEL_LAYOUT=1 python -m lepton_b200.build --force and repeat the sweep for the cache-friendlier table layout)"
 echo "== lock-step kernel: launch list + full capture (256 images)"
 LEPB200_DEC_MODE=2 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_dec_mode2.csv \
   python bench.py --images 256 --no-e2e --no-cpu-baseline --steps 1 --warmup 1 > /dev/null 2>&1
