@@ -26,6 +26,7 @@ enum Status : int32_t {
     STREAM_INCONSISTENT = 7,
     PROGRESSIVE_UNSUPPORTED = 8,
     SAMPLING_BEYOND_TWO_UNSUPPORTED = 10,
+    THREADING_PARTIAL_MCU = 12,
     VERSION_UNSUPPORTED = 13,
     UNSUPPORTED_JPEG = 42,
     UNSUPPORTED_JPEG_WITH_ZERO_IDCT_0 = 43,
@@ -155,6 +156,7 @@ struct LepFile {
     std::vector<Handoff> handoffs;   // as serialised (luma_y_start, segment_size, overhang, last_dc)
     bool has_eee = false;
     bool rst_cnt_set = false;        // CRS section present (jpgcoder.cc:4241)
+    bool legacy = false;             // no handoff table: segment rows read from the payload (vp8_decoder.cc:337-369)
     uint32_t eee[7] = {0};
     std::vector<std::vector<uint8_t>> streams;   // demuxed per-segment bool-coder streams
     int status = OK;

@@ -67,8 +67,17 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
     j.hdr.assign(blob.begin() + p, blob.begin() + p + hdrs);
     p += hdrs;
     if (!parse_frame(j)) { lf.status = j.status; lf.error = j.error; return false; }
-    if (!need(4) || memcmp(&blob[p], "P0D", 3)) return lfail(lf, NOT_HANDLED, "P0D marker not found (legacy PAD not handled)");
-    j.padbit = (int8_t)blob[p + 3];
+    if (!need(4)) return lfail(lf, SHORT_READ, "short pad section");
+    if (!memcmp(&blob[p], "P0D", 3)) {
+        j.padbit = (int8_t)blob[p + 3];
+    } else if (!memcmp(&blob[p], "PAD", 3)) {
+        // legacy: one pad bit that stands for all of them (jpgcoder.cc:4228-4242)
+        const int8_t pb = (int8_t)blob[p + 3];
+        if (!(pb == 0 || pb == 1 || pb == -1)) return lfail(lf, STREAM_INCONSISTENT, "Legacy Padbit must be 0, 1 or -1");
+        j.padbit = pb == 1 ? 0x7f : pb;
+    } else {
+        return lfail(lf, UNSUPPORTED_JPEG, "PAD marker not found");
+    }
     p += 4;
     j.grb.clear();
     bool have_grb = false;
@@ -135,7 +144,33 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
         }
     }
     if (!have_grb) { j.grb = {0xFF, 0xD9}; }          // "if we don't have any garbage, assume FFD9 EOI" (jpgcoder.cc:4194)
-    if (lf.handoffs.empty() || (int)lf.handoffs.size() != lf.nseg) return lfail(lf, VERSION_UNSUPPORTED, "handoff table missing or inconsistent");
+    size_t q = 28 + (size_t)zlen;
+    if (memcmp(d + q, "CMP", 3)) return lfail(lf, UNSUPPORTED_JPEG, "CMP marker missing");
+    q += 3;
+    const size_t end = n - 4;
+    if (lf.handoffs.empty()) {
+        // Legacy files (before the handoff table existed): the payload opens with the number of thread-segments and
+        // the luma rows where they end (VP8ComponentDecoder::initialize_baseline_decoder, vp8_decoder.cc:337-369).
+        // Their handoffs carry no Huffman state (ThreadHandoff::LEGACY_OVERHANG_BITS), so the scan can only be
+        // re-created front to back -- which is what the host re-encoder does anyway.
+        if (q + 1 > end) return lfail(lf, SHORT_READ, "legacy segment table missing");
+        const int k = d[q];
+        if (k == 0) return lfail(lf, THREADING_PARTIAL_MCU, "legacy segment count is zero");
+        if (q + 1 + 2 * (size_t)(k - 1) > end) return lfail(lf, SHORT_READ, "short legacy segment table");
+        const int luma_mul = j.cmp[0].bcv / j.mcuv;
+        for (int i = 0; i < k; ++i) {
+            Handoff h;
+            h.num_overhang_bits = 0xff;
+            h.luma_y_end = i + 1 < k ? (uint16_t)(d[q + 1 + 2 * i] | (d[q + 2 + 2 * i] << 8)) : (uint16_t)j.cmp[0].bcv;
+            if (i + 1 < k && h.luma_y_end % luma_mul) return lfail(lf, THREADING_PARTIAL_MCU, "legacy split inside an MCU row");
+            h.luma_y_start = i ? lf.handoffs[i - 1].luma_y_end : 0;
+            lf.handoffs.push_back(h);
+        }
+        q += 1 + 2 * (size_t)(k - 1);
+        lf.nseg = k;
+        lf.legacy = true;
+    }
+    if ((int)lf.handoffs.size() != lf.nseg) return lfail(lf, VERSION_UNSUPPORTED, "handoff table inconsistent with the thread count");
     if (lf.nseg > 16) return lfail(lf, NOT_HANDLED, "more than 16 thread-segments");             // MAX_NUM_THREADS of this build
     // a corrupt handoff table must fail this file only, not the batch it travels in
     if (lf.handoffs[0].luma_y_start != 0) return lfail(lf, STREAM_INCONSISTENT, "first thread-segment does not start at row 0");
@@ -143,12 +178,7 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
         if ((int)lf.handoffs[i].luma_y_start > j.cmp[0].bcv || (i + 1 < lf.nseg && lf.handoffs[i].luma_y_start > lf.handoffs[i + 1].luma_y_start))
             return lfail(lf, STREAM_INCONSISTENT, "thread-segment rows out of order or beyond the image");
     }
-    if (lf.handoffs[0].num_overhang_bits == 0xff) return lfail(lf, NOT_HANDLED, "legacy single-thread container");
     // demux (src/io/MuxReader.hh:230-283); the last 4 bytes are the file-size trailer
-    size_t q = 28 + (size_t)zlen;
-    if (memcmp(d + q, "CMP", 3)) return lfail(lf, UNSUPPORTED_JPEG, "CMP marker missing");
-    q += 3;
-    const size_t end = n - 4;
     lf.streams.assign(16, std::vector<uint8_t>());
     while (q + 3 <= end) {
         const uint8_t hd = d[q];

@@ -110,12 +110,37 @@ class LepFile:
     frame: Frame
 
 
-def parse_container(data: bytes) -> LepFile:
+def jpeg_header_of(jpeg: bytes) -> bytes:
+    """The bytes the reference stores in HDR for a JPEG file: everything after SOI up to and including the first SOS
+    segment (src/lepton/jpgcoder.cc:2270-2300 read_jpeg collects the header segments the same way)."""
+    pos = 2
+    while True:
+        assert jpeg[pos] == 0xFF, "marker expected at %d" % pos
+        m = jpeg[pos + 1]
+        ln = struct.unpack(">H", jpeg[pos + 2:pos + 4])[0]
+        pos += 2 + ln
+        if m == 0xDA:
+            return jpeg[2:pos]
+
+
+def parse_container(data: bytes, jpeg_for_header: bytes = None) -> LepFile:
+    """``jpeg_for_header``: for container versions whose header blob is brotli-coded (2..4; no brotli decoder in this
+    image) the blob is skipped by its length field and the frame geometry / quantisation tables are taken from the
+    JPEG file the container is known to decode to.  Only valid when the fixed header says one thread-segment (the
+    handoff table inside the blob is then (luma_y_start 0) and nothing else on the coefficient path lives there)."""
     magic = data[:2]
     version, flag, nseg = data[2], data[3], data[4]
     jpeg_size, zlen = struct.unpack("<II", data[20:28])
-    blob = zlib.decompress(data[28:28 + zlen])
     assert data[28 + zlen:31 + zlen] == b"CMP", "CMP marker missing"
+    if version != 1:
+        assert jpeg_for_header is not None and nseg == 1, "brotli header blob: need the JPEG and a single segment"
+        jpeg_header = jpeg_header_of(jpeg_for_header)
+        frame = parse_jpeg_header(jpeg_header)
+        off = 31 + zlen
+        return LepFile(magic, version, flag, nseg, jpeg_size, b"", jpeg_header, 0,
+                       [Handoff(0, 0, 0, 0, (0, 0, 0, 0), frame.bcv[0])], {}, off, data[off:-4],
+                       struct.unpack("<I", data[-4:])[0], frame)
+    blob = zlib.decompress(data[28:28 + zlen])
     p = 0
     assert blob[:3] == b"HDR"
     n = struct.unpack("<I", blob[3:7])[0]
@@ -126,7 +151,7 @@ def parse_container(data: bytes) -> LepFile:
     handoffs = []
     while p < len(blob):
         tag = blob[p:p + 3]
-        if tag == b"P0D":
+        if tag in (b"P0D", b"PAD"):
             pad_bit = blob[p + 3]
             p += 4
         elif blob[p:p + 1] == b"H" and tag not in (b"HDR",):
@@ -163,6 +188,16 @@ def parse_container(data: bytes) -> LepFile:
     is_lep = magic == b"\xcf\x84"
     payload = data[off:-4] if is_lep else data[off:]
     trailer = struct.unpack("<I", data[-4:])[0] if is_lep else 0
+    if is_lep and not handoffs:
+        # legacy files carry no handoff table: the payload opens with the segment count and the luma split rows
+        # (src/lepton/vp8_decoder.cc:337-369), then the mux packets
+        k = payload[0]
+        assert k >= 1
+        ends = list(struct.unpack("<%dH" % (k - 1), payload[1:1 + 2 * (k - 1)])) + [frame.bcv[0]]
+        starts = [0] + ends[:-1]
+        handoffs = [Handoff(starts[i], 0, 0, 0xFF, (0, 0, 0, 0), ends[i]) for i in range(k)]
+        payload = payload[1 + 2 * (k - 1):]
+        off += 1 + 2 * (k - 1)
     return LepFile(magic, version, flag, nseg, jpeg_size, blob, jpeg_header, pad_bit, handoffs, sections, off,
                    payload, trailer, frame)
 

@@ -343,3 +343,20 @@ def test_corrupt_files_fail_alone_inside_a_batch():
         for j, (st, out) in zip(src, fc.decompress(again)):
             assert st == 0 and out == j
     fc.close()
+
+
+def test_reference_legacy_golden_vector_decompress():
+    """The reference repository's golden vector images/gold-legacy.lep (tests/golden/legacy/; test_suite/test_legacy.sh
+    pins the md5 of its decoding): a legacy container without a handoff table, four thread-segments.  The product's
+    file-level decode must produce the golden md5, and compressing the result again must round-trip."""
+    import hashlib
+    from lepton_b200 import LeptonB200FileCodec
+    data = open(os.path.join(GOLDEN, "legacy", "gold-legacy.lep"), "rb").read()
+    fc = LeptonB200FileCodec(0, host_threads=4)
+    (st, jpg), = fc.decompress([data])
+    assert st == 0 and hashlib.md5(jpg).hexdigest() == "9ffbfc24d1157d0b1ed7a9b53bef4c23"
+    (st, lep), = fc.compress([jpg])
+    assert st == 0
+    (st, back), = fc.decompress([lep])
+    assert st == 0 and back == jpg
+    fc.close()

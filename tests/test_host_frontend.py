@@ -126,3 +126,32 @@ def test_progressive_reencode_rejects_coefficients_its_tables_cannot_express():
     except LeptonB200Error:
         return
     assert out != jpg
+
+
+def test_legacy_container_golden_vector():
+    """images/gold-legacy.lep of the reference repository (committed under tests/golden/legacy/): its test
+    test_suite/test_legacy.sh expects md5 9ffbfc24d1157d0b1ed7a9b53bef4c23 after decoding.  A version-1 file from
+    before the handoff table existed: segment rows come from the payload (vp8_decoder.cc:337-369) and the scan can
+    only be re-created front to back.  Host halves: reader demuxes the four streams, the oracle decodes them, the
+    re-encoder must produce the golden md5."""
+    from lepton_b200 import HostLep
+    from helpers import oracle_decode_planes
+    data = open(os.path.join(GOLDEN, "legacy", "gold-legacy.lep"), "rb").read()
+    hl = HostLep(data)
+    assert hl.status == 0, hl.error
+    lf = lepfmt.parse_container(data)
+    img = hl.coef_image()
+    assert img.nseg == 4 and list(img.luma_y_start) == [h.luma_y_start for h in lf.handoffs] == [0, 94, 182, 284]
+    assert hl.streams(img.nseg) == lepfmt.demux(lf.payload)[:4]
+    planes, _ = oracle_decode_planes(lf)
+    jpg = hl.recode(planes)
+    assert len(jpg) == lf.jpeg_size and hashlib.md5(jpg).hexdigest() == "9ffbfc24d1157d0b1ed7a9b53bef4c23"
+
+
+def test_brotli_header_containers_are_refused():
+    """Container versions 2..4 carry a brotli-coded header blob: refused with the 'not handled' status."""
+    from lepton_b200 import HostLep
+    data = bytearray(open(os.path.join(GOLDEN, "android.lep"), "rb").read())
+    data[2] = 4
+    hl = HostLep(bytes(data))
+    assert hl.status == 200 and hl.error
