@@ -5,7 +5,8 @@
 # Everything runs under `timeout` so that a kernel that does not terminate costs one step, not the box.
 mkdir -p gpurun_out
 echo "== parity, LEPB200_DEC_MODE=2"
-LEPB200_TEST_LOCKSTEP=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "lockstep or thread_per_segment"   # decode modes 2 and 3, encode mode 1 2>&1 | tail -3
+# decode modes 2 and 3, encode mode 1
+LEPB200_TEST_LOCKSTEP=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "lockstep or thread_per_segment" 2>&1 | tail -3
 echo "== decode leg, 1024 and 4096 images"
 for images in 1024 4096; do
   for cfg in "0 16384 50" "1 16384 50" "2 16384 50" "2 8192 50" "3 16384 50" "3 16384 25" "3 16384 75"; do
