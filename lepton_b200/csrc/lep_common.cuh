@@ -14,6 +14,21 @@ namespace lepb200 {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Cache hints for data that streams through (build-time option LEPB200_STREAM_HINTS=1; results are unchanged, only the
+// eviction priority in L1 / L2): the coefficient planes, the token streams and the model zero fill add up to several
+// times the 126 MB L2 per launch, while the lines that ARE reused -- the touched part of each resident model, ~49 KB per
+// segment -- are what the kernels wait for.  LEP_LD_LAST = last use of a line (the row above, read a second time),
+// LEP_ST_STREAM = written once and read by a later kernel.  Off by default until it is measured on the GPU.
+// (macros, not functions: a pointer passed through a function parameter loses its __restrict__ and the default build
+// must keep the SASS that was validated on the GPU)
+#if defined(LEPB200_STREAM_HINTS) && LEPB200_STREAM_HINTS && !defined(LEPB200_EMU)
+#define LEP_LD_LAST(p, i) __ldcs((p) + (i))
+#define LEP_ST_STREAM(p, i, v) __stcs((p) + (i), (v))
+#else
+#define LEP_LD_LAST(p, i) p[i]
+#define LEP_ST_STREAM(p, i, v) p[i] = v
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // Probability model layout.
 //

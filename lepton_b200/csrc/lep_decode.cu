@@ -118,7 +118,7 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
         {
             uint4* m4 = reinterpret_cast<uint4*>(model);
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = lane; i < M_TOTAL / 8; i += 32) m4[i] = z;
+            for (uint32_t i = lane; i < M_TOTAL / 8; i += 32) LEP_ST_STREAM(m4, i, z);
         }
         __syncwarp();
 
@@ -165,13 +165,13 @@ lep_decode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             int16_t* redge = reinterpret_cast<int16_t*>(rowbuf + (size_t)(c == 0 ? 0 : (c == 1 ? bw0 : bw0 + bw1)) * 16);
             uint8_t* rnz = rowbuf + nz_base + (c == 0 ? 0 : (c == 1 ? nzs0 : nzs0 + nzs1));
 
-            uint32_t abv = has_above ? abovep[lane] : 0u;
+            uint32_t abv = has_above ? LEP_LD_LAST(abovep, lane) : 0u;
             uint32_t left = 0, aleft = 0;
             int left_v = 0, nz_left = 0, pp = 0;
             for (int x = 0; x < w; ++x) {
                 const bool has_left = x > 0;
                 uint32_t nabv = 0;
-                if (has_above && x + 1 < w) nabv = abovep[(size_t)(x + 1) * 32 + lane];
+                if (has_above && x + 1 < w) nabv = LEP_LD_LAST(abovep, (size_t)(x + 1) * 32 + lane);
                 ws.rast[2][r0] = (int16_t)h_lo(abv); ws.rast[2][r1] = (int16_t)h_hi(abv);
                 int16_t* rcur = ws.rast[pp];
                 const int16_t* rleft = ws.rast[pp ^ 1];

@@ -131,7 +131,7 @@ __device__ __forceinline__ void flush_queue(EncWarpSmem& ws, int n, int base_b, 
         }
         const uint32_t pb = branch_prob(w, s_rcp) | (bit << 8);
         if (active && (peers >> lane) == 1u) model[addr] = (uint16_t)neww;                    // last decision of its branch
-        if (active && ntok + i < tok_cap) tokens[ntok + i] = (uint16_t)pb;                    // coalesced 2-byte stores
+        if (active && ntok + i < tok_cap) LEP_ST_STREAM(tokens, ntok + i, (uint16_t)pb);                    // coalesced 2-byte stores
         __syncwarp();                                                                         // order this batch's model stores before the next batch's loads
     }
     ntok += (uint32_t)n;
@@ -283,7 +283,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
         {
             uint4* m4 = reinterpret_cast<uint4*>(model);
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = lane; i < M_TOTAL / 8; i += 32) m4[i] = z;
+            for (uint32_t i = lane; i < M_TOTAL / 8; i += 32) LEP_ST_STREAM(m4, i, z);
             uint32_t* mk4 = reinterpret_cast<uint32_t*>(ws.mark);        // the flush leaves the marks zero; a segment that ended on an error does not
             for (int i = lane; i < QCAP / 4; i += 32) mk4[i] = 0u;
         }
@@ -327,7 +327,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             const int l = lane & 15;
             const uint32_t trunc_bc = (uint32_t)g.trunc_bc[c];
             uint32_t curA = rowp[lane], curB = w > 1 ? rowp[32 + lane] : 0u;
-            uint32_t abvA = has_above ? abovep[lane] : 0u, abvB = (has_above && w > 1) ? abovep[32 + lane] : 0u;
+            uint32_t abvA = has_above ? LEP_LD_LAST(abovep, lane) : 0u, abvB = (has_above && w > 1) ? LEP_LD_LAST(abovep, 32 + lane) : 0u;
             uint32_t left = 0, aleft = 0;                    // left / above-left neighbours of A
             int left_v = 0;                                  // lanes 0..7: right-column edge prediction of A's left neighbour
             int nz_left = 0;
@@ -339,8 +339,8 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 const bool more = has_b && x + 2 < w && (uint32_t)((size_t)y * w + x + 2) < trunc_bc;
                 // prefetch the next pair of this row and of the row above
                 uint32_t ncurA = 0, ncurB = 0, nabvA = 0, nabvB = 0;
-                if (x + 2 < w) { ncurA = rowp[(size_t)(x + 2) * 32 + lane]; if (has_above) nabvA = abovep[(size_t)(x + 2) * 32 + lane]; }
-                if (x + 3 < w) { ncurB = rowp[(size_t)(x + 3) * 32 + lane]; if (has_above) nabvB = abovep[(size_t)(x + 3) * 32 + lane]; }
+                if (x + 2 < w) { ncurA = rowp[(size_t)(x + 2) * 32 + lane]; if (has_above) nabvA = LEP_LD_LAST(abovep, (size_t)(x + 2) * 32 + lane); }
+                if (x + 3 < w) { ncurB = rowp[(size_t)(x + 3) * 32 + lane]; if (has_above) nabvB = LEP_LD_LAST(abovep, (size_t)(x + 3) * 32 + lane); }
                 // ---------------- raster copies for the gathers (IDCT, Lakhani edge predictor)
                 ws.rast[ra * 64 + r0] = (int16_t)h_lo(curA); ws.rast[ra * 64 + r1] = (int16_t)h_hi(curA);
                 ws.rast[3 * 64 + r0] = (int16_t)h_lo(abvA); ws.rast[3 * 64 + r1] = (int16_t)h_hi(abvA);

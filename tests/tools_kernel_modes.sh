@@ -30,7 +30,16 @@ try:
 except Exception as e: print('images $images enc mode $mode: no result', e)"
   done
 done
-echo "== (rebuild with LEPB200_MODEL_LAYOUT=1 python -m lepton_b200.build --force and repeat the sweep for the cache-friendlier table layout)"
+echo "== build-time options on the default kernels: streaming cache hints, position-innermost model layout (rebuilds the library in place)"
+for opt in "LEPB200_STREAM_HINTS=1" "LEPB200_MODEL_LAYOUT=1" "LEPB200_STREAM_HINTS=1 LEPB200_MODEL_LAYOUT=1"; do
+  env $opt python -m lepton_b200.build --force > /dev/null 2>&1 || { echo "build failed: $opt"; continue; }
+  timeout 600 python bench.py --images 4096 --no-e2e --no-cpu-baseline --steps 3 --warmup 3 2>/dev/null | tail -1 | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); print('$opt  value MB/s', round(d['value'],1), ' kernel A ms', round(d['roofline']['kernel_ms'],1), ' decode ms', round(d['decode']['ms_per_step'],1), ' round trip', d.get('roundtrip_pass_rate'))
+except Exception as e: print('$opt: no result', e)"
+done
+python -m lepton_b200.build --force > /dev/null 2>&1    # back to the default build
 echo "== lock-step kernel: launch list + full capture (256 images)"
 LEPB200_DEC_MODE=2 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_dec_mode2.csv \
   python bench.py --images 256 --no-e2e --no-cpu-baseline --steps 1 --warmup 1 > /dev/null 2>&1
