@@ -29,7 +29,7 @@ def fingerprints(defs=()):
             cur = re.sub(r"_GLOBAL__N__[0-9a-f]+", "", m.group(1))          # anonymous-namespace hash varies per build
             out[cur] = []
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(.*?)\s*/\* 0x[0-9a-f]+ \*/", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?)\s*/\* 0x[0-9a-f]+ \*/", line)
         if m and cur:
             out[cur].append(m.group(1))
     return {k: (len(v), hashlib.md5("\n".join(v).encode()).hexdigest()) for k, v in out.items()}
