@@ -8,6 +8,13 @@
 // -maxencodethreads=) are accepted and ignored: the GPU coder always produces the reference's default .lep bytes and
 // every file is verified by construction in the test-suite, not at run time.  Service modes (-socket, -listen, -fork,
 // -benchmark, -lepcat) are not part of the hot path and are refused.
+//
+// Batch mode (no reference counterpart; a GPU wants thousands of files per call, the reference one per process):
+//   lepton-b200 -outdir=DIR a.jpg b.lep c.jpg ...
+// every positional argument is an input, the direction is chosen per file, all JPEGs go through ONE
+// lepb200_compress_jpegs call and all .lep files through ONE lepb200_decompress_leps call; outputs are DIR/<name>.lep /
+// DIR/<name>.jpg.  A file that fails reports its ExitCode on stderr and does not stop the others; the exit status is
+// the first non-zero one.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,13 +30,75 @@ static bool read_all(FILE* f, std::vector<uint8_t>& out) {
     return !ferror(f);
 }
 
+static std::string base_name(const std::string& path) {
+    size_t slash = path.find_last_of('/');
+    std::string b = slash == std::string::npos ? path : path.substr(slash + 1);
+    size_t dot = b.rfind('.');
+    if (dot != std::string::npos && dot > 0) b.resize(dot);
+    return b;
+}
+
+// -outdir=DIR: all inputs in two library calls (one per direction)
+static int run_batch(const std::vector<std::string>& files, const std::string& outdir, int device) {
+    struct Item { std::string name; std::vector<uint8_t> data; bool is_jpeg = false; int status = 0; };
+    std::vector<Item> items(files.size());
+    int first_err = 0;
+    for (size_t i = 0; i < files.size(); ++i) {
+        Item& it = items[i];
+        it.name = files[i];
+        FILE* f = fopen(files[i].c_str(), "rb");
+        if (!f) { it.status = 9; }                                                               // FILE_NOT_FOUND
+        else {
+            if (!read_all(f, it.data)) it.status = 33;
+            fclose(f);
+            if (!it.status && it.data.size() < 2) it.status = 3;                                     // SHORT_READ
+        }
+        if (!it.status) {
+            it.is_jpeg = it.data[0] == 0xFF && it.data[1] == 0xD8;
+            if (!it.is_jpeg && !(it.data[0] == 0xCF && it.data[1] == 0x84)) it.status = 42;          // UNSUPPORTED_JPEG
+        }
+    }
+    lepb200_codec* codec = nullptr;
+    int rc = lepb200_codec_create(&codec, device, 0);
+    if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device (%d); this build has no CPU coder\n", rc); return 33; }
+    for (int dir = 0; dir < 2; ++dir) {                      // 0: JPEG -> .lep, 1: .lep -> JPEG
+        std::vector<size_t> idx;
+        std::vector<lepb200_buffer> in;
+        for (size_t i = 0; i < items.size(); ++i)
+            if (!items[i].status && items[i].is_jpeg == (dir == 0)) { idx.push_back(i); in.push_back({items[i].data.data(), items[i].data.size()}); }
+        if (idx.empty()) continue;
+        std::vector<lepb200_result> res(idx.size(), lepb200_result{nullptr, 0, 0});
+        rc = dir == 0 ? lepb200_compress_jpegs(codec, in.data(), (int)in.size(), res.data())
+                      : lepb200_decompress_leps(codec, in.data(), (int)in.size(), res.data());
+        if (rc) { fprintf(stderr, "lepton-b200: %s\n", lepb200_codec_last_error(codec)); lepb200_codec_destroy(codec); return 33; }
+        for (size_t k = 0; k < idx.size(); ++k) {            // results stay valid until the next call on the codec: write now
+            Item& it = items[idx[k]];
+            it.status = res[k].status == LEPB200_ST_NOT_HANDLED ? 42 : res[k].status;
+            if (it.status) continue;
+            const std::string out = outdir + "/" + base_name(it.name) + (dir == 0 ? ".lep" : ".jpg");
+            FILE* fo = fopen(out.c_str(), "wb");
+            if (!fo || fwrite(res[k].data, 1, res[k].len, fo) != res[k].len) it.status = 33;
+            if (fo) fclose(fo);
+        }
+    }
+    lepb200_codec_destroy(codec);
+    for (const Item& it : items) {
+        if (!it.status) continue;
+        fprintf(stderr, "lepton-b200: %s: exit code %d\n", it.name.c_str(), it.status);
+        if (!first_err) first_err = it.status;
+    }
+    return first_err;
+}
+
 int main(int argc, char** argv) {
     std::vector<std::string> files;
+    std::string outdir;
     int device = 0;
     for (int i = 1; i < argc; ++i) {
         const char* a = argv[i];
         if (a[0] == '-' && a[1] != 0) {
             if (!strncmp(a, "-device=", 8)) { device = atoi(a + 8); continue; }
+            if (!strncmp(a, "-outdir=", 8)) { outdir = a + 8; continue; }
             if (!strcmp(a, "-socket") || !strncmp(a, "-socket=", 8) || !strncmp(a, "-listen", 7) || !strcmp(a, "-fork") ||
                 !strcmp(a, "-benchmark") || !strcmp(a, "-lepcat") || !strncmp(a, "-startbyte", 10) || !strncmp(a, "-trunc=", 7) ||
                 !strcmp(a, "-ujg") || !strcmp(a, "-brotliheader") || !strncmp(a, "-embedding", 10)) {
@@ -41,9 +110,11 @@ int main(int argc, char** argv) {
         files.push_back(a);
     }
     if (files.empty()) {
-        fprintf(stderr, "usage: lepton-b200 [flags] <input.jpg|input.lep|-> [output|-]\n");
+        fprintf(stderr, "usage: lepton-b200 [flags] <input.jpg|input.lep|-> [output|-]\n"
+                        "       lepton-b200 [flags] -outdir=DIR <inputs...>      (one batch per direction)\n");
         return 1;
     }
+    if (!outdir.empty()) return run_batch(files, outdir, device);
     std::vector<uint8_t> in;
     FILE* fi = files[0] == "-" ? stdin : fopen(files[0].c_str(), "rb");
     if (!fi) { fprintf(stderr, "lepton-b200: cannot open %s\n", files[0].c_str()); return 9; }   // FILE_NOT_FOUND

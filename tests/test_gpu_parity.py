@@ -360,3 +360,27 @@ def test_reference_legacy_golden_vector_decompress():
     (st, back), = fc.decompress([lep])
     assert st == 0 and back == jpg
     fc.close()
+
+
+def test_cli_batch_mode(tmp_path):
+    """`lepton-b200 -outdir=DIR inputs...`: JPEGs and .lep files in one invocation, one library call per direction;
+    outputs equal the reference's files, a damaged input fails alone with its exit code."""
+    import subprocess
+    from helpers import GOLDEN
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "lepton_b200", "bin", "lepton-b200")
+    names = ["androidcrop.jpg", "grayscale.jpg", "iphoneprogressive.jpg", "trailingrst.jpg"]
+    leps = ["android.lep", "gray2sf.lep", "iphonecrop2_t8.lep"]
+    bad = tmp_path / "broken.lep"
+    bad.write_bytes(open(os.path.join(GOLDEN, "android.lep"), "rb").read()[:40])          # cut inside the header: SHORT_READ
+    out = tmp_path / "out"
+    out.mkdir()
+    args = [os.path.join(GOLDEN, n) for n in names + leps] + [str(bad)]
+    r = subprocess.run([exe, "-outdir=" + str(out)] + args, capture_output=True)
+    assert r.returncode != 0 and b"broken.lep" in r.stderr, r.stderr            # the damaged file reports, the rest is written
+    for n in names:
+        assert (out / (n[:-4] + ".lep")).read_bytes() == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
+    from helpers import MANIFEST
+    for n in leps:
+        src = MANIFEST[n]["source"] if "source" in MANIFEST.get(n, {}) else n[:-4] + ".jpg"
+        assert (out / (n[:-4] + ".jpg")).read_bytes() == open(os.path.join(GOLDEN, src), "rb").read(), n
+    assert not (out / "broken.jpg").exists()

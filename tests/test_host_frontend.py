@@ -155,3 +155,20 @@ def test_brotli_header_containers_are_refused():
     data[2] = 4
     hl = HostLep(bytes(data))
     assert hl.status == 200 and hl.error
+
+
+def test_cli_without_a_device_fails_loudly(tmp_path):
+    """The CLI (single-file and batch mode) has no CPU coder to fall back to."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "lepton_b200", "bin", "lepton-b200")
+    assert os.path.exists(exe), "build() did not produce the CLI"
+    src = os.path.join(GOLDEN, "androidcrop.jpg")
+    for args in ([src, str(tmp_path / "o.lep")], ["-outdir=" + str(tmp_path), src]):
+        r = subprocess.run([exe] + args, capture_output=True)
+        assert r.returncode == 33 and b"no CPU coder" in r.stderr
+        assert not (tmp_path / "o.lep").exists() and not (tmp_path / "androidcrop.lep").exists()
+    assert subprocess.run([exe], capture_output=True).returncode == 1            # usage
+    assert subprocess.run([exe, "-socket", src], capture_output=True).returncode == 13
