@@ -224,6 +224,10 @@ void lepb200_codec_set_chunk_images(lepb200_codec* codec, int n);
 /* 1 (default): Huffman-decode on the GPU when every file of a chunk is a complete single-scan baseline JPEG;
  * 0: always Huffman-decode on host threads */
 void lepb200_codec_set_gpu_huffman(lepb200_codec* codec, int on);
+/* 1 (default, the reference built with DEFAULT_ALLOW_PROGRESSIVE / run with -allowprogressive): progressive and
+ * non-interleaved JPEGs are coded; 0 (-rejectprogressive): they fail with the reference's exit code 8
+ * (PROGRESSIVE_UNSUPPORTED, src/lepton/jpgcoder.cc:2911-2925) */
+void lepb200_codec_set_allow_progressive(lepb200_codec* codec, int on);
 /* device milliseconds of the last chunk's GPU Huffman-decode kernel (diagnostic) */
 double lepb200_codec_last_huffman_ms(const lepb200_codec* codec);
 /* files of the last lepb200_decompress_leps call whose scan was Huffman-encoded on the device (the rest went through the host re-encoder) */

@@ -29,6 +29,7 @@ struct lepb200_codec {
     int chunk_images = 4096;
     size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk (device memory budget: two contexts in flight)
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
+    bool allow_progressive = true; // false: -rejectprogressive (files that are not single-scan-interleaved baseline exit with code 8)
     void* arena[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
     size_t arena_cap[4] = {0, 0, 0, 0};
     std::vector<std::vector<uint8_t>> outputs;
@@ -125,6 +126,7 @@ uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
 }
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
+void lepb200_codec_set_allow_progressive(lepb200_codec* c, int on) { if (c) c->allow_progressive = on != 0; }
 double lepb200_codec_last_huffman_ms(const lepb200_codec* c) { return c ? c->t_huff_ms : -1.0; }
 int lepb200_codec_last_gpu_recoded(const lepb200_codec* c) { return c ? c->n_gpu_recoded.load() : 0; }
 
@@ -264,7 +266,12 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 memset(p, 0, pb);
                 p += (pb + 255) & ~size_t(255);
             }
-            if (decode_scans(j, s.planes[i].data())) { s.splits[i] = select_splits(j); s.host_decoded[i] = 1; }
+            if (decode_scans(j, s.planes[i].data())) {
+                // -rejectprogressive: the reference leaves with PROGRESSIVE_UNSUPPORTED at the first scan that is progressive
+                // or does not interleave all components (jpgcoder.cc:2911-2925)
+                if (!c->allow_progressive && !j.is_baseline) { j.status = PROGRESSIVE_UNSUPPORTED; j.error = "progressive / non-interleaved JPEG rejected (-rejectprogressive)"; return; }
+                s.splits[i] = select_splits(j); s.host_decoded[i] = 1;
+            }
         });
         // batch = every file that is still fine, in file order
         for (int i = 0; i < m; ++i) {

@@ -39,7 +39,7 @@ static std::string base_name(const std::string& path) {
 }
 
 // -outdir=DIR: all inputs in two library calls (one per direction)
-static int run_batch(const std::vector<std::string>& files, const std::string& outdir, int device) {
+static int run_batch(const std::vector<std::string>& files, const std::string& outdir, int device, int allow_progressive) {
     struct Item { std::string name; std::vector<uint8_t> data; bool is_jpeg = false; int status = 0; };
     std::vector<Item> items(files.size());
     int first_err = 0;
@@ -61,6 +61,7 @@ static int run_batch(const std::vector<std::string>& files, const std::string& o
     lepb200_codec* codec = nullptr;
     int rc = lepb200_codec_create(&codec, device, 0);
     if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device (%d); this build has no CPU coder\n", rc); return 33; }
+    lepb200_codec_set_allow_progressive(codec, allow_progressive);
     for (int dir = 0; dir < 2; ++dir) {                      // 0: JPEG -> .lep, 1: .lep -> JPEG
         std::vector<size_t> idx;
         std::vector<lepb200_buffer> in;
@@ -94,11 +95,14 @@ int main(int argc, char** argv) {
     std::vector<std::string> files;
     std::string outdir;
     int device = 0;
+    int allow_progressive = 1;   // this build follows the reference compiled with DEFAULT_ALLOW_PROGRESSIVE (CMakeLists.txt:293)
     for (int i = 1; i < argc; ++i) {
         const char* a = argv[i];
         if (a[0] == '-' && a[1] != 0) {
             if (!strncmp(a, "-device=", 8)) { device = atoi(a + 8); continue; }
             if (!strncmp(a, "-outdir=", 8)) { outdir = a + 8; continue; }
+            if (!strcmp(a, "-rejectprogressive")) { allow_progressive = 0; continue; }
+            if (!strcmp(a, "-allowprogressive") || !strcmp(a, "-forceprogressive")) { allow_progressive = 1; continue; }
             if (!strcmp(a, "-socket") || !strncmp(a, "-socket=", 8) || !strncmp(a, "-listen", 7) || !strcmp(a, "-fork") ||
                 !strcmp(a, "-benchmark") || !strcmp(a, "-lepcat") || !strncmp(a, "-startbyte", 10) || !strncmp(a, "-trunc=", 7) ||
                 !strcmp(a, "-ujg") || !strcmp(a, "-brotliheader") || !strncmp(a, "-embedding", 10)) {
@@ -114,7 +118,7 @@ int main(int argc, char** argv) {
                         "       lepton-b200 [flags] -outdir=DIR <inputs...>      (one batch per direction)\n");
         return 1;
     }
-    if (!outdir.empty()) return run_batch(files, outdir, device);
+    if (!outdir.empty()) return run_batch(files, outdir, device, allow_progressive);
     std::vector<uint8_t> in;
     FILE* fi = files[0] == "-" ? stdin : fopen(files[0].c_str(), "rb");
     if (!fi) { fprintf(stderr, "lepton-b200: cannot open %s\n", files[0].c_str()); return 9; }   // FILE_NOT_FOUND
@@ -135,6 +139,7 @@ int main(int argc, char** argv) {
     lepb200_codec* codec = nullptr;
     int rc = lepb200_codec_create(&codec, device, 0);
     if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device (%d); this build has no CPU coder\n", rc); return 33; }
+    lepb200_codec_set_allow_progressive(codec, allow_progressive);
     lepb200_buffer ib = {in.data(), in.size()};
     lepb200_result res = {nullptr, 0, 0};
     rc = is_jpeg ? lepb200_compress_jpegs(codec, &ib, 1, &res) : lepb200_decompress_leps(codec, &ib, 1, &res);

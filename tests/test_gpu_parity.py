@@ -384,3 +384,18 @@ def test_cli_batch_mode(tmp_path):
         src = MANIFEST[n]["source"] if "source" in MANIFEST.get(n, {}) else n[:-4] + ".jpg"
         assert (out / (n[:-4] + ".jpg")).read_bytes() == open(os.path.join(GOLDEN, src), "rb").read(), n
     assert not (out / "broken.jpg").exists()
+
+
+def test_rejectprogressive_exit_code():
+    """-rejectprogressive (src/lepton/jpgcoder.cc:1056-1058, :2911-2925): progressive files leave with the reference's
+    exit code 8 (PROGRESSIVE_UNSUPPORTED); baseline files of the same batch are coded as usual."""
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200FileCodec
+    names = ["androidcrop.jpg", "iphoneprogressive.jpg", "grayscale.jpg", "androidprogressive.jpg"]
+    fc = LeptonB200FileCodec(0, host_threads=2, allow_progressive=False)
+    res = fc.compress([open(os.path.join(GOLDEN, n), "rb").read() for n in names])
+    fc.close()
+    assert [st for st, _ in res] == [0, 8, 0, 8]
+    for n, (st, lep) in zip(names, res):
+        if st == 0:
+            assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
