@@ -20,16 +20,16 @@ inline void put(std::vector<uint8_t>& v, const char* s, size_t n) { v.insert(v.e
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// write_ujpg thread-segment selection (jpgcoder.cc:3860-3934), NUM_THREADS = MAX_NUM_THREADS = 8,
-// min_encode_threads = 1, no -evensplit.
+// write_ujpg thread-segment selection (jpgcoder.cc:3860-3934): NUM_THREADS = min(MAX_NUM_THREADS = 8,
+// -maxencodethreads) (:2196, :3862), min_encode_threads from -minencodethreads (default 1), no -evensplit.
 // ------------------------------------------------------------------------------------------------
-Splits select_splits(const Jpeg& j) {
+Splits select_splits(const Jpeg& j, unsigned max_threads, unsigned min_threads) {
     const std::vector<Handoff>& rows = j.rows;
     Splits sp;
     const uint32_t byte_size = rows.back().segment_size - rows.front().segment_size;
     const uint32_t num_rows = (uint32_t)rows.size();
-    unsigned nthreads = 8;
-    const unsigned min_threads = 1;
+    unsigned nthreads = std::min(8u, std::max(1u, max_threads));
+    min_threads = std::min(std::max(min_threads, 1u), 8u);
     if (num_rows / 2 < nthreads) {
         unsigned desired = std::max(num_rows / 2, min_threads);
         nthreads = std::min(std::max(desired, 1u), nthreads);

@@ -29,6 +29,7 @@ struct lepb200_codec {
     int chunk_images = 4096;
     size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk (device memory budget: two contexts in flight)
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
+    unsigned max_encode_threads = 8, min_encode_threads = 1;   // -maxencodethreads= / -minencodethreads= (jpgcoder.cc:1080-1089)
     bool allow_progressive = true; // false: -rejectprogressive (files that are not single-scan-interleaved baseline exit with code 8)
     void* arena[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
     size_t arena_cap[4] = {0, 0, 0, 0};
@@ -127,6 +128,11 @@ uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
 void lepb200_codec_set_allow_progressive(lepb200_codec* c, int on) { if (c) c->allow_progressive = on != 0; }
+void lepb200_codec_set_encode_threads(lepb200_codec* c, int min_threads, int max_threads) {
+    if (!c) return;
+    c->min_encode_threads = (unsigned)std::min(std::max(min_threads, 1), 8);
+    c->max_encode_threads = (unsigned)std::min(std::max(max_threads, 1), 8);
+}
 double lepb200_codec_last_huffman_ms(const lepb200_codec* c) { return c ? c->t_huff_ms : -1.0; }
 int lepb200_codec_last_gpu_recoded(const lepb200_codec* c) { return c ? c->n_gpu_recoded.load() : 0; }
 
@@ -270,7 +276,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 // -rejectprogressive: the reference leaves with PROGRESSIVE_UNSUPPORTED at the first scan that is progressive
                 // or does not interleave all components (jpgcoder.cc:2911-2925)
                 if (!c->allow_progressive && !j.is_baseline) { j.status = PROGRESSIVE_UNSUPPORTED; j.error = "progressive / non-interleaved JPEG rejected (-rejectprogressive)"; return; }
-                s.splits[i] = select_splits(j); s.host_decoded[i] = 1;
+                s.splits[i] = select_splits(j, c->max_encode_threads, c->min_encode_threads); s.host_decoded[i] = 1;
             }
         });
         // batch = every file that is still fine, in file order
@@ -335,7 +341,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                             for (size_t r = 1; r < j.rows.size(); ++r)
                                 if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
                             for (int t = 0; t < j.ncmp; ++t) { j.trunc_bcv[t] = j.cmp[t].bcv; j.trunc_bc[t] = j.cmp[t].bc; }
-                            s.splits[i] = select_splits(j);
+                            s.splits[i] = select_splits(j, c->max_encode_threads, c->min_encode_threads);
                         } else {
                             j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
                             j.error = "GPU Huffman decoder refused the scan";
@@ -739,6 +745,10 @@ struct lepb200_jpeg {
 };
 
 int lepb200_host_jpeg_open(const uint8_t* data, size_t len, lepb200_jpeg** out, int32_t* status) {
+    return lepb200_host_jpeg_open_threads(data, len, 1, 8, out, status);
+}
+
+int lepb200_host_jpeg_open_threads(const uint8_t* data, size_t len, int min_threads, int max_threads, lepb200_jpeg** out, int32_t* status) {
     if (!out || !data) return LEPB200_ERR_INVALID;
     lepb200_jpeg* h = new lepb200_jpeg();
     *out = h;
@@ -748,7 +758,7 @@ int lepb200_host_jpeg_open(const uint8_t* data, size_t len, lepb200_jpeg** out, 
             h->store[c].assign((size_t)h->j.cmp[c].bc * 64, 0);
             h->planes[c] = h->store[c].data();
         }
-        if (decode_scans(h->j, h->planes)) h->sp = select_splits(h->j);
+        if (decode_scans(h->j, h->planes)) h->sp = select_splits(h->j, (unsigned)std::max(max_threads, 1), (unsigned)std::max(min_threads, 1));
     }
     if (status) *status = h->j.status;
     return LEPB200_OK;

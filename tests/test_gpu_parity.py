@@ -399,3 +399,14 @@ def test_rejectprogressive_exit_code():
     for n, (st, lep) in zip(names, res):
         if st == 0:
             assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
+
+
+def test_minencodethreads_files_match_reference():
+    """-minencodethreads=N through the file API: the .lep bytes of the reference CLI run with the same flag."""
+    from helpers import GOLDEN, MANIFEST
+    from lepton_b200 import LeptonB200FileCodec
+    for lep_name, n in (("android_t4.lep", 4), ("androidcrop_t2.lep", 2), ("iphonecrop2_t8.lep", 8)):
+        fc = LeptonB200FileCodec(0, host_threads=2, min_encode_threads=n)
+        (st, lep), = fc.compress([open(os.path.join(GOLDEN, MANIFEST[lep_name]["source"]), "rb").read()])
+        fc.close()
+        assert st == 0 and lep == open(os.path.join(GOLDEN, lep_name), "rb").read(), lep_name

@@ -172,3 +172,40 @@ def test_cli_without_a_device_fails_loudly(tmp_path):
         assert not (tmp_path / "o.lep").exists() and not (tmp_path / "androidcrop.lep").exists()
     assert subprocess.run([exe], capture_output=True).returncode == 1            # usage
     assert subprocess.run([exe, "-socket", src], capture_output=True).returncode == 13
+
+
+@pytest.mark.parametrize("lep_name,min_threads", [("android_t4.lep", 4), ("androidcrop_t2.lep", 2), ("iphonecrop2_t8.lep", 8)])
+def test_minencodethreads_reproduces_reference_containers(lep_name, min_threads):
+    """-minencodethreads=N (src/lepton/jpgcoder.cc:1086-1089, :3862-3874): the thread-segment selection with a lower bound
+    must give the splits -- and, fed the reference's streams, the container bytes -- of the files the reference wrote
+    with that flag."""
+    from lepton_b200 import HostJpeg
+    src = MANIFEST[lep_name]["source"]
+    hj = HostJpeg(open(os.path.join(GOLDEN, src), "rb").read(), min_threads=min_threads)
+    assert hj.status == 0, hj.error
+    lf = load_lep(lep_name)
+    assert list(hj.coef_image().luma_y_start) == [h.luma_y_start for h in lf.handoffs]
+    assert lf.nseg >= min(min_threads, 2)
+    ref = open(os.path.join(GOLDEN, lep_name), "rb").read()
+    assert hj.write_lep(lepfmt.demux(lf.payload)[:lf.nseg]) == ref
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/images"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("flags", [["-maxencodethreads=1"], ["-maxencodethreads=2"], ["-maxencodethreads=3", "-minencodethreads=3"],
+                                   ["-minencodethreads=8"], ["-minencodethreads=5", "-maxencodethreads=6"]])
+def test_encode_thread_flags_against_live_reference(flags, tmp_path):
+    """Splits chosen under -minencodethreads / -maxencodethreads == the unmodified reference CLI's, on files of three sizes."""
+    import subprocess
+    from conftest import REF_LEPTON
+    from lepton_b200 import HostJpeg
+    lo = max([int(f.split("=")[1]) for f in flags if f.startswith("-min")] + [1])
+    hi = min([int(f.split("=")[1]) for f in flags if f.startswith("-max")] + [8])
+    for name in ("iphonecrop.jpg", "androidcrop.jpg", "slrcity.jpg"):
+        jpg = os.path.join("/root/reference/images", name)
+        lep = str(tmp_path / (name + ".lep"))
+        assert subprocess.run([REF_LEPTON, "-skipverify", "-unjailed"] + flags + [jpg, lep], capture_output=True).returncode == 0
+        lf = lepfmt.parse_container(open(lep, "rb").read())
+        hj = HostJpeg(open(jpg, "rb").read(), min_threads=lo, max_threads=hi)
+        assert hj.status == 0, hj.error
+        assert list(hj.coef_image().luma_y_start) == [h.luma_y_start for h in lf.handoffs], (name, flags)
+        assert hj.write_lep(lepfmt.demux(lf.payload)[:lf.nseg]) == open(lep, "rb").read(), (name, flags)
