@@ -232,6 +232,8 @@ void lepb200_codec_set_allow_progressive(lepb200_codec* codec, int on);
  * thread-segment count write_ujpg selects (:3862-3874); both clamp to 1..8, defaults 1 and 8.  They change the .lep
  * bytes exactly as they do in the reference. */
 void lepb200_codec_set_encode_threads(lepb200_codec* codec, int min_threads, int max_threads);
+/* -evensplit (jpgcoder.cc:1063-1064, :3898-3900): thread-segments cover equal numbers of MCU rows instead of equal bytes */
+void lepb200_codec_set_even_split(lepb200_codec* codec, int on);
 /* device milliseconds of the last chunk's GPU Huffman-decode kernel (diagnostic) */
 double lepb200_codec_last_huffman_ms(const lepb200_codec* codec);
 /* files of the last lepb200_decompress_leps call whose scan was Huffman-encoded on the device (the rest went through the host re-encoder) */
@@ -250,6 +252,7 @@ int lepb200_decompress_leps(lepb200_codec* codec, const lepb200_buffer* leps, in
 typedef struct lepb200_jpeg lepb200_jpeg;
 int lepb200_host_jpeg_open(const uint8_t* data, size_t len, lepb200_jpeg** out, int32_t* status);
 int lepb200_host_jpeg_open_threads(const uint8_t* data, size_t len, int min_threads, int max_threads, lepb200_jpeg** out, int32_t* status);
+int lepb200_host_jpeg_open_split(const uint8_t* data, size_t len, int min_threads, int max_threads, int even_split, lepb200_jpeg** out, int32_t* status);
 const char* lepb200_host_jpeg_error(const lepb200_jpeg* h);
 int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img);
 int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, int nseg, const uint8_t** data, size_t* len);

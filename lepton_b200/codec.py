@@ -57,7 +57,7 @@ _EXPORTS = [
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
     "lepb200_device_available", "lepb200_sync", "lepb200_last_symbolise_ms", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
     "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_codec_kernel_launches", "lepb200_codec_set_chunk_images",
-    "lepb200_codec_set_gpu_huffman", "lepb200_codec_set_allow_progressive", "lepb200_codec_set_encode_threads", "lepb200_host_jpeg_open_threads", "lepb200_huffman_decode_to_device", "lepb200_encode_upload_resident", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
+    "lepb200_codec_set_gpu_huffman", "lepb200_codec_set_allow_progressive", "lepb200_codec_set_encode_threads", "lepb200_host_jpeg_open_threads", "lepb200_host_jpeg_open_split", "lepb200_codec_set_even_split", "lepb200_huffman_decode_to_device", "lepb200_encode_upload_resident", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
     "lepb200_decompress_leps", "lepb200_host_lep_open", "lepb200_host_lep_error", "lepb200_host_lep_image",
     "lepb200_host_lep_stream", "lepb200_host_lep_recode", "lepb200_host_lep_close", "lepb200_host_frontend_seconds",
@@ -328,6 +328,10 @@ def _bind_file_api(L):
     L.lepb200_host_jpeg_open.restype = ctypes.c_int
     L.lepb200_host_jpeg_open_threads.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
     L.lepb200_host_jpeg_open_threads.restype = ctypes.c_int
+    L.lepb200_host_jpeg_open_split.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int32)]
+    L.lepb200_host_jpeg_open_split.restype = ctypes.c_int
+    L.lepb200_codec_set_even_split.argtypes = [vp, ctypes.c_int]
+    L.lepb200_codec_set_even_split.restype = None
     L.lepb200_host_jpeg_error.argtypes = [vp]
     L.lepb200_host_jpeg_error.restype = ctypes.c_char_p
     L.lepb200_host_jpeg_image.argtypes = [vp, ctypes.POINTER(_Image)]
@@ -356,13 +360,13 @@ def _bind_file_api(L):
 class HostJpeg:
     """Host stages only (no GPU): parse + Huffman-decode a JPEG, expose it as a CoefImage, assemble a .lep."""
 
-    def __init__(self, data: bytes, min_threads: int = 1, max_threads: int = 8):
+    def __init__(self, data: bytes, min_threads: int = 1, max_threads: int = 8, even_split: bool = False):
         self._L = lib()
         _bind_file_api(self._L)
         self._h = ctypes.c_void_p()
         st = ctypes.c_int32()
         self._data = data
-        self._L.lepb200_host_jpeg_open_threads(data, len(data), min_threads, max_threads, ctypes.byref(self._h), ctypes.byref(st))
+        self._L.lepb200_host_jpeg_open_split(data, len(data), min_threads, max_threads, 1 if even_split else 0, ctypes.byref(self._h), ctypes.byref(st))
         self.status = st.value
         self.error = self._L.lepb200_host_jpeg_error(self._h).decode()
 
@@ -486,7 +490,8 @@ class LeptonB200FileCodec:
     """JPEG bytes -> .lep bytes for a batch of files; host threads + one GPU."""
 
     def __init__(self, device: int = 0, host_threads: int = 0, chunk_images: int = 0, gpu_huffman: bool = True,
-                 allow_progressive: bool = True, min_encode_threads: int = 1, max_encode_threads: int = 8):
+                 allow_progressive: bool = True, min_encode_threads: int = 1, max_encode_threads: int = 8,
+                 even_split: bool = False):
         self._L = lib()
         _bind_file_api(self._L)
         self._c = ctypes.c_void_p()
@@ -498,6 +503,7 @@ class LeptonB200FileCodec:
         self._L.lepb200_codec_set_gpu_huffman(self._c, 1 if gpu_huffman else 0)
         self._L.lepb200_codec_set_allow_progressive(self._c, 1 if allow_progressive else 0)      # False = -rejectprogressive
         self._L.lepb200_codec_set_encode_threads(self._c, min_encode_threads, max_encode_threads)   # -minencodethreads= / -maxencodethreads=
+        self._L.lepb200_codec_set_even_split(self._c, 1 if even_split else 0)                      # -evensplit
 
     def close(self):
         if self._c:

@@ -21,9 +21,9 @@ inline void put(std::vector<uint8_t>& v, const char* s, size_t n) { v.insert(v.e
 
 // ------------------------------------------------------------------------------------------------
 // write_ujpg thread-segment selection (jpgcoder.cc:3860-3934): NUM_THREADS = min(MAX_NUM_THREADS = 8,
-// -maxencodethreads) (:2196, :3862), min_encode_threads from -minencodethreads (default 1), no -evensplit.
+// -maxencodethreads) (:2196, :3862), min_encode_threads from -minencodethreads (default 1), -evensplit = rows divided evenly instead of bytes.
 // ------------------------------------------------------------------------------------------------
-Splits select_splits(const Jpeg& j, unsigned max_threads, unsigned min_threads) {
+Splits select_splits(const Jpeg& j, unsigned max_threads, unsigned min_threads, bool even_split) {
     const std::vector<Handoff>& rows = j.rows;
     Splits sp;
     const uint32_t byte_size = rows.back().segment_size - rows.front().segment_size;
@@ -39,7 +39,7 @@ Splits select_splits(const Jpeg& j, unsigned max_threads, unsigned min_threads) 
     else if (byte_size < 500000) nthreads = std::min(std::max(min_threads, 4u), nthreads);
 
     std::vector<int> idx(nthreads, 0);
-    for (unsigned i = 0; i + 1 < nthreads; ++i) {
+    for (unsigned i = 0; !even_split && i + 1 < nthreads; ++i) {
         uint32_t desired = rows.back().segment_size;
         desired -= rows.front().segment_size;
         desired *= (i + 1);
@@ -53,6 +53,7 @@ Splits select_splits(const Jpeg& j, unsigned max_threads, unsigned min_threads) 
         }
         idx[i] = (int)(split - rows.begin());
     }
+    for (unsigned i = 0; even_split && i + 1 < nthreads; ++i) idx[i] = (int)(rows.size() * (i + 1) / nthreads);   // -evensplit (:3898-3900)
     for (unsigned k = 0; k + 1 < nthreads; ++k) {
         if (idx[k] == idx[k + 1]) {      // note: compares against the still-zero last entry for k == nthreads-2, as the reference does
             for (unsigned i = 0; i + 1 < nthreads; ++i) idx[i] = (int)((i + 1) * rows.size() / nthreads);

@@ -29,6 +29,7 @@ struct lepb200_codec {
     int chunk_images = 4096;
     size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk (device memory budget: two contexts in flight)
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
+    bool even_split = false;       // -evensplit (jpgcoder.cc:1063-1064)
     unsigned max_encode_threads = 8, min_encode_threads = 1;   // -maxencodethreads= / -minencodethreads= (jpgcoder.cc:1080-1089)
     bool allow_progressive = true; // false: -rejectprogressive (files that are not single-scan-interleaved baseline exit with code 8)
     void* arena[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
@@ -128,6 +129,7 @@ uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
 void lepb200_codec_set_allow_progressive(lepb200_codec* c, int on) { if (c) c->allow_progressive = on != 0; }
+void lepb200_codec_set_even_split(lepb200_codec* c, int on) { if (c) c->even_split = on != 0; }
 void lepb200_codec_set_encode_threads(lepb200_codec* c, int min_threads, int max_threads) {
     if (!c) return;
     c->min_encode_threads = (unsigned)std::min(std::max(min_threads, 1), 8);
@@ -276,7 +278,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 // -rejectprogressive: the reference leaves with PROGRESSIVE_UNSUPPORTED at the first scan that is progressive
                 // or does not interleave all components (jpgcoder.cc:2911-2925)
                 if (!c->allow_progressive && !j.is_baseline) { j.status = PROGRESSIVE_UNSUPPORTED; j.error = "progressive / non-interleaved JPEG rejected (-rejectprogressive)"; return; }
-                s.splits[i] = select_splits(j, c->max_encode_threads, c->min_encode_threads); s.host_decoded[i] = 1;
+                s.splits[i] = select_splits(j, c->max_encode_threads, c->min_encode_threads, c->even_split); s.host_decoded[i] = 1;
             }
         });
         // batch = every file that is still fine, in file order
@@ -341,7 +343,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                             for (size_t r = 1; r < j.rows.size(); ++r)
                                 if (j.rows[r].luma_y_start < j.rows[r - 1].luma_y_end) j.rows[r].luma_y_start = j.rows[r - 1].luma_y_end;
                             for (int t = 0; t < j.ncmp; ++t) { j.trunc_bcv[t] = j.cmp[t].bcv; j.trunc_bc[t] = j.cmp[t].bc; }
-                            s.splits[i] = select_splits(j, c->max_encode_threads, c->min_encode_threads);
+                            s.splits[i] = select_splits(j, c->max_encode_threads, c->min_encode_threads, c->even_split);
                         } else {
                             j.status = sc.status ? sc.status : (int)UNSUPPORTED_JPEG;
                             j.error = "GPU Huffman decoder refused the scan";
@@ -749,6 +751,10 @@ int lepb200_host_jpeg_open(const uint8_t* data, size_t len, lepb200_jpeg** out, 
 }
 
 int lepb200_host_jpeg_open_threads(const uint8_t* data, size_t len, int min_threads, int max_threads, lepb200_jpeg** out, int32_t* status) {
+    return lepb200_host_jpeg_open_split(data, len, min_threads, max_threads, 0, out, status);
+}
+
+int lepb200_host_jpeg_open_split(const uint8_t* data, size_t len, int min_threads, int max_threads, int even_split, lepb200_jpeg** out, int32_t* status) {
     if (!out || !data) return LEPB200_ERR_INVALID;
     lepb200_jpeg* h = new lepb200_jpeg();
     *out = h;
@@ -758,7 +764,7 @@ int lepb200_host_jpeg_open_threads(const uint8_t* data, size_t len, int min_thre
             h->store[c].assign((size_t)h->j.cmp[c].bc * 64, 0);
             h->planes[c] = h->store[c].data();
         }
-        if (decode_scans(h->j, h->planes)) h->sp = select_splits(h->j, (unsigned)std::max(max_threads, 1), (unsigned)std::max(min_threads, 1));
+        if (decode_scans(h->j, h->planes)) h->sp = select_splits(h->j, (unsigned)std::max(max_threads, 1), (unsigned)std::max(min_threads, 1), even_split != 0);
     }
     if (status) *status = h->j.status;
     return LEPB200_OK;

@@ -138,7 +138,7 @@ struct Splits {
     std::vector<Handoff> selected;   // what gets serialised into the header ('H' 'H' nseg ...)
 };
 // Thread-segment selection of write_ujpg (jpgcoder.cc:3860-3934) with the reference's default options.
-Splits select_splits(const Jpeg& j, unsigned max_threads = 8, unsigned min_threads = 1);
+Splits select_splits(const Jpeg& j, unsigned max_threads = 8, unsigned min_threads = 1, bool even_split = false);
 
 // MuxWriter + vp8_full_encoder interleave schedule (src/io/MuxReader.hh:336-522, src/lepton/vp8_encoder.cc:573-600).
 void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, std::vector<uint8_t>& out);

@@ -8,7 +8,7 @@
 // are accepted and ignored: the GPU coder always produces the reference's default .lep bytes and
 // every file is verified by construction in the test-suite, not at run time.  Service modes (-socket, -listen, -fork,
 // -benchmark, -lepcat) are not part of the hot path and are refused.  Flags that change the bytes are honoured:
-// -minencodethreads= / -maxencodethreads= (thread-segment count), -rejectprogressive / -allowprogressive.
+// -minencodethreads= / -maxencodethreads= / -evensplit (thread-segment selection), -rejectprogressive / -allowprogressive.
 //
 // Batch mode (no reference counterpart; a GPU wants thousands of files per call, the reference one per process):
 //   lepton-b200 -outdir=DIR a.jpg b.lep c.jpg ...
@@ -40,7 +40,7 @@ static std::string base_name(const std::string& path) {
 }
 
 // -outdir=DIR: all inputs in two library calls (one per direction)
-static int run_batch(const std::vector<std::string>& files, const std::string& outdir, int device, int allow_progressive, int min_threads, int max_threads) {
+static int run_batch(const std::vector<std::string>& files, const std::string& outdir, int device, int allow_progressive, int min_threads, int max_threads, int even_split) {
     struct Item { std::string name; std::vector<uint8_t> data; bool is_jpeg = false; int status = 0; };
     std::vector<Item> items(files.size());
     int first_err = 0;
@@ -64,6 +64,7 @@ static int run_batch(const std::vector<std::string>& files, const std::string& o
     if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device (%d); this build has no CPU coder\n", rc); return 33; }
     lepb200_codec_set_allow_progressive(codec, allow_progressive);
     lepb200_codec_set_encode_threads(codec, min_threads, max_threads);
+    lepb200_codec_set_even_split(codec, even_split);
     for (int dir = 0; dir < 2; ++dir) {                      // 0: JPEG -> .lep, 1: .lep -> JPEG
         std::vector<size_t> idx;
         std::vector<lepb200_buffer> in;
@@ -97,6 +98,7 @@ int main(int argc, char** argv) {
     std::vector<std::string> files;
     std::string outdir;
     int device = 0;
+    int even_split = 0;
     int min_threads = 1, max_threads = 8;   // -minencodethreads= / -maxencodethreads=: bounds of the thread-segment count (change the .lep bytes)
     int allow_progressive = 1;   // this build follows the reference compiled with DEFAULT_ALLOW_PROGRESSIVE (CMakeLists.txt:293)
     for (int i = 1; i < argc; ++i) {
@@ -106,6 +108,7 @@ int main(int argc, char** argv) {
             if (!strncmp(a, "-outdir=", 8)) { outdir = a + 8; continue; }
             if (!strncmp(a, "-minencodethreads=", 18)) { min_threads = atoi(a + 18); continue; }
             if (!strncmp(a, "-maxencodethreads=", 18)) { max_threads = atoi(a + 18); continue; }
+            if (!strcmp(a, "-evensplit")) { even_split = 1; continue; }
             if (!strcmp(a, "-rejectprogressive")) { allow_progressive = 0; continue; }
             if (!strcmp(a, "-allowprogressive") || !strcmp(a, "-forceprogressive")) { allow_progressive = 1; continue; }
             if (!strcmp(a, "-socket") || !strncmp(a, "-socket=", 8) || !strncmp(a, "-listen", 7) || !strcmp(a, "-fork") ||
@@ -123,7 +126,7 @@ int main(int argc, char** argv) {
                         "       lepton-b200 [flags] -outdir=DIR <inputs...>      (one batch per direction)\n");
         return 1;
     }
-    if (!outdir.empty()) return run_batch(files, outdir, device, allow_progressive, min_threads, max_threads);
+    if (!outdir.empty()) return run_batch(files, outdir, device, allow_progressive, min_threads, max_threads, even_split);
     std::vector<uint8_t> in;
     FILE* fi = files[0] == "-" ? stdin : fopen(files[0].c_str(), "rb");
     if (!fi) { fprintf(stderr, "lepton-b200: cannot open %s\n", files[0].c_str()); return 9; }   // FILE_NOT_FOUND
@@ -146,6 +149,7 @@ int main(int argc, char** argv) {
     if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device (%d); this build has no CPU coder\n", rc); return 33; }
     lepb200_codec_set_allow_progressive(codec, allow_progressive);
     lepb200_codec_set_encode_threads(codec, min_threads, max_threads);
+    lepb200_codec_set_even_split(codec, even_split);
     lepb200_buffer ib = {in.data(), in.size()};
     lepb200_result res = {nullptr, 0, 0};
     rc = is_jpeg ? lepb200_compress_jpegs(codec, &ib, 1, &res) : lepb200_decompress_leps(codec, &ib, 1, &res);

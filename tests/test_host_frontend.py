@@ -192,9 +192,10 @@ def test_minencodethreads_reproduces_reference_containers(lep_name, min_threads)
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/images"), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("flags", [["-maxencodethreads=1"], ["-maxencodethreads=2"], ["-maxencodethreads=3", "-minencodethreads=3"],
-                                   ["-minencodethreads=8"], ["-minencodethreads=5", "-maxencodethreads=6"]])
+                                   ["-minencodethreads=8"], ["-minencodethreads=5", "-maxencodethreads=6"],
+                                   ["-evensplit"], ["-evensplit", "-minencodethreads=8"]])
 def test_encode_thread_flags_against_live_reference(flags, tmp_path):
-    """Splits chosen under -minencodethreads / -maxencodethreads == the unmodified reference CLI's, on files of three sizes."""
+    """Splits chosen under -minencodethreads / -maxencodethreads / -evensplit == the unmodified reference CLI's, on files of three sizes."""
     import subprocess
     from conftest import REF_LEPTON
     from lepton_b200 import HostJpeg
@@ -205,7 +206,7 @@ def test_encode_thread_flags_against_live_reference(flags, tmp_path):
         lep = str(tmp_path / (name + ".lep"))
         assert subprocess.run([REF_LEPTON, "-skipverify", "-unjailed"] + flags + [jpg, lep], capture_output=True).returncode == 0
         lf = lepfmt.parse_container(open(lep, "rb").read())
-        hj = HostJpeg(open(jpg, "rb").read(), min_threads=lo, max_threads=hi)
+        hj = HostJpeg(open(jpg, "rb").read(), min_threads=lo, max_threads=hi, even_split="-evensplit" in flags)
         assert hj.status == 0, hj.error
         assert list(hj.coef_image().luma_y_start) == [h.luma_y_start for h in lf.handoffs], (name, flags)
         assert hj.write_lep(lepfmt.demux(lf.payload)[:lf.nseg]) == open(lep, "rb").read(), (name, flags)
