@@ -7,7 +7,8 @@
 // CPU runtime (-singlethread, -unjailed, -skipverify/-verify, -preload, -memory=, -threadmemory=, -timebound=)
 // are accepted and ignored: the GPU coder always produces the reference's default .lep bytes and
 // every file is verified by construction in the test-suite, not at run time.  Service modes (-socket, -listen, -fork,
-// -benchmark, -lepcat) are not part of the hot path and are refused.  Flags that change the bytes are honoured:
+// -benchmark, -lepcat) and output variants this build does not write (-brotliheader, -ans, -zlib0, -ujg, -startbyte /
+// -trunc slices, -embedding) are refused, never silently ignored.  Flags that change the bytes are honoured:
 // -minencodethreads= / -maxencodethreads= / -evensplit (thread-segment selection), -rejectprogressive / -allowprogressive.
 //
 // Batch mode (no reference counterpart; a GPU wants thousands of files per call, the reference one per process):
@@ -113,7 +114,7 @@ int main(int argc, char** argv) {
             if (!strcmp(a, "-allowprogressive") || !strcmp(a, "-forceprogressive")) { allow_progressive = 1; continue; }
             if (!strcmp(a, "-socket") || !strncmp(a, "-socket=", 8) || !strncmp(a, "-listen", 7) || !strcmp(a, "-fork") ||
                 !strcmp(a, "-benchmark") || !strcmp(a, "-lepcat") || !strncmp(a, "-startbyte", 10) || !strncmp(a, "-trunc=", 7) ||
-                !strcmp(a, "-ujg") || !strcmp(a, "-brotliheader") || !strncmp(a, "-embedding", 10)) {
+                !strcmp(a, "-ujg") || !strcmp(a, "-brotliheader") || !strncmp(a, "-embedding", 10) || !strcmp(a, "-zlib0") || !strcmp(a, "-ans")) {
                 fprintf(stderr, "lepton-b200: option %s is outside the B200 hot path build\n", a);
                 return 13;   // VERSION_UNSUPPORTED
             }
