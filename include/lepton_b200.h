@@ -245,6 +245,14 @@ int lepb200_compress_jpegs(lepb200_codec* codec, const lepb200_buffer* jpegs, in
 /* n .lep files in, n JPEG files out (byte-identical to the originals) */
 int lepb200_decompress_leps(lepb200_codec* codec, const lepb200_buffer* leps, int n, lepb200_result* out);
 
+/* ---- several GPUs from one process: codecs[k] was created on its own device.  The files are dealt to the codecs
+ * longest-first by size (lepb200_shard_by_size: owner[i] = codec of file i, balanced by bytes to within one file), each
+ * codec codes its share through its own pipeline on its own host thread; nothing crosses between GPUs.
+ * out[i].data is owned by the codec that coded file i and stays valid until that codec's next call. */
+void lepb200_shard_by_size(const size_t* sizes, int n, int world, int* owner);
+int lepb200_compress_jpegs_multi(lepb200_codec* const* codecs, int ncodecs, const lepb200_buffer* jpegs, int n, lepb200_result* out);
+int lepb200_decompress_leps_multi(lepb200_codec* const* codecs, int ncodecs, const lepb200_buffer* leps, int n, lepb200_result* out);
+
 /* ---- the host stages on their own (no GPU): JPEG front end and .lep assembly around an external coder.
  * lepb200_host_jpeg_open parses + Huffman-decodes one JPEG (read_jpeg + decode_jpeg, jpgcoder.cc:2270,2799) and
  * selects the thread-segments (write_ujpg :3860-3934); *_image exposes planes/geometry/splits as a lepb200_image

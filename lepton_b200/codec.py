@@ -57,7 +57,7 @@ _EXPORTS = [
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
     "lepb200_device_available", "lepb200_sync", "lepb200_last_symbolise_ms", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
     "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_codec_kernel_launches", "lepb200_codec_set_chunk_images",
-    "lepb200_codec_set_gpu_huffman", "lepb200_codec_set_allow_progressive", "lepb200_codec_set_encode_threads", "lepb200_host_jpeg_open_threads", "lepb200_host_jpeg_open_split", "lepb200_codec_set_even_split", "lepb200_huffman_decode_to_device", "lepb200_encode_upload_resident", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
+    "lepb200_codec_set_gpu_huffman", "lepb200_codec_set_allow_progressive", "lepb200_codec_set_encode_threads", "lepb200_host_jpeg_open_threads", "lepb200_host_jpeg_open_split", "lepb200_codec_set_even_split", "lepb200_shard_by_size", "lepb200_compress_jpegs_multi", "lepb200_decompress_leps_multi", "lepb200_huffman_decode_to_device", "lepb200_encode_upload_resident", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
     "lepb200_decompress_leps", "lepb200_host_lep_open", "lepb200_host_lep_error", "lepb200_host_lep_image",
     "lepb200_host_lep_stream", "lepb200_host_lep_recode", "lepb200_host_lep_close", "lepb200_host_frontend_seconds",
@@ -564,3 +564,47 @@ class LeptonB200FileCodec:
     @property
     def kernel_launches(self) -> int:
         return int(self._L.lepb200_codec_kernel_launches(self._c))
+
+
+def shard_by_size_native(sizes, world):
+    """lepb200_shard_by_size: owner (codec / GPU index) of every file, longest-first by size -- the native twin of
+    lepton_b200.sharding.shard_by_size."""
+    L = lib()
+    n = len(sizes)
+    arr = (ctypes.c_size_t * n)(*sizes)
+    owner = (ctypes.c_int * n)()
+    L.lepb200_shard_by_size.argtypes = [ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.lepb200_shard_by_size.restype = None
+    L.lepb200_shard_by_size(arr, n, world, owner)
+    return list(owner)
+
+
+class LeptonB200MultiGpuFileCodec:
+    """One process, several GPUs: a LeptonB200FileCodec per device, files dealt to them balanced by bytes
+    (lepb200_compress_jpegs_multi / lepb200_decompress_leps_multi); no data crosses between GPUs."""
+
+    def __init__(self, devices, host_threads_per_gpu: int = 0, **kw):
+        self.codecs = [LeptonB200FileCodec(d, host_threads=host_threads_per_gpu, **kw) for d in devices]
+        self._L = self.codecs[0]._L
+        vp = ctypes.c_void_p
+        self._arr = (vp * len(self.codecs))(*[c._c for c in self.codecs])
+        for f in (self._L.lepb200_compress_jpegs_multi, self._L.lepb200_decompress_leps_multi):
+            f.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+            f.restype = ctypes.c_int
+
+    def _run(self, fn, files):
+        bufs, n, _keep, res = self.codecs[0].prepare(files)
+        rc = fn(self._arr, len(self.codecs), ctypes.cast(bufs, ctypes.c_void_p), n, ctypes.cast(res, ctypes.c_void_p))
+        if rc != 0:
+            raise LeptonB200Error("multi-GPU call failed (%d)" % rc)
+        return [(res[i].status, ctypes.string_at(res[i].data, res[i].len) if res[i].len else b"") for i in range(n)]
+
+    def compress(self, jpegs):
+        return self._run(self._L.lepb200_compress_jpegs_multi, jpegs)
+
+    def decompress(self, leps):
+        return self._run(self._L.lepb200_decompress_leps_multi, leps)
+
+    def close(self):
+        for c in self.codecs:
+            c.close()

@@ -736,6 +736,62 @@ double lepb200_host_frontend_seconds(const lepb200_buffer* jpegs, int n, int thr
     return dt;
 }
 
+// ---- several GPUs from one process (per-GPU work queues, no collective, no peer traffic) ----------------
+// Files are independent, so the batch is dealt to the codecs (one per GPU) longest-first by size -- every GPU gets
+// the same number of bytes to within one file -- and every codec runs its share through its own chunk pipeline on its
+// own host thread.  A chunk has to stay large (the Huffman and range-coder kernels are latency-bound chains whose
+// duration hardly depends on the number of files), which is why the split is static per call and not file by file.
+void lepb200_shard_by_size(const size_t* sizes, int n, int world, int* owner) {
+    if (!sizes || !owner || n <= 0 || world <= 0) return;
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sizes[a] > sizes[b]; });
+    std::vector<unsigned long long> load(world, 0);
+    for (int i : order) {
+        int r = 0;
+        for (int k = 1; k < world; ++k) if (load[k] < load[r]) r = k;
+        owner[i] = r;
+        load[r] += sizes[i];
+    }
+}
+
+namespace {
+int run_multi(lepb200_codec* const* codecs, int ncodecs, const lepb200_buffer* in, int n, lepb200_result* out, bool compress) {
+    if (!codecs || ncodecs <= 0 || !in || !out || n <= 0) return LEPB200_ERR_INVALID;
+    for (int k = 0; k < ncodecs; ++k) if (!codecs[k]) return LEPB200_ERR_INVALID;
+    std::vector<size_t> sizes(n);
+    for (int i = 0; i < n; ++i) sizes[i] = in[i].len;
+    std::vector<int> owner(n, 0);
+    lepb200_shard_by_size(sizes.data(), n, ncodecs, owner.data());
+    std::vector<std::vector<int>> share(ncodecs);
+    for (int i = 0; i < n; ++i) share[owner[i]].push_back(i);                       // file order inside a share
+    std::vector<int> rcs(ncodecs, LEPB200_OK);
+    std::vector<std::thread> th;
+    for (int k = 0; k < ncodecs; ++k) {
+        if (share[k].empty()) continue;
+        th.emplace_back([&, k]() {
+            const std::vector<int>& idx = share[k];
+            std::vector<lepb200_buffer> sub(idx.size());
+            std::vector<lepb200_result> res(idx.size(), lepb200_result{nullptr, 0, 0});
+            for (size_t q = 0; q < idx.size(); ++q) sub[q] = in[idx[q]];
+            rcs[k] = compress ? lepb200_compress_jpegs(codecs[k], sub.data(), (int)sub.size(), res.data())
+                              : lepb200_decompress_leps(codecs[k], sub.data(), (int)sub.size(), res.data());
+            for (size_t q = 0; q < idx.size(); ++q) out[idx[q]] = res[q];        // data stays owned by codec k
+        });
+    }
+    for (std::thread& t : th) t.join();
+    for (int k = 0; k < ncodecs; ++k) if (rcs[k] != LEPB200_OK) return rcs[k];
+    return LEPB200_OK;
+}
+}  // namespace
+
+int lepb200_compress_jpegs_multi(lepb200_codec* const* codecs, int ncodecs, const lepb200_buffer* jpegs, int n, lepb200_result* out) {
+    return run_multi(codecs, ncodecs, jpegs, n, out, true);
+}
+int lepb200_decompress_leps_multi(lepb200_codec* const* codecs, int ncodecs, const lepb200_buffer* leps, int n, lepb200_result* out) {
+    return run_multi(codecs, ncodecs, leps, n, out, false);
+}
+
 // ---- staged host-only entry points (no GPU involved): parse + Huffman-decode one JPEG, expose its planes and
 // thread-segment split as a lepb200_image, and assemble the .lep from externally coded segment streams.
 struct lepb200_jpeg {

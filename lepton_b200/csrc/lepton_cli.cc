@@ -12,15 +12,17 @@
 // -minencodethreads= / -maxencodethreads= / -evensplit (thread-segment selection), -rejectprogressive / -allowprogressive.
 //
 // Batch mode (no reference counterpart; a GPU wants thousands of files per call, the reference one per process):
-//   lepton-b200 -outdir=DIR a.jpg b.lep c.jpg ...
+//   lepton-b200 -outdir=DIR [-devices=0,1,...] a.jpg b.lep c.jpg ...
 // every positional argument is an input, the direction is chosen per file, all JPEGs go through ONE
 // lepb200_compress_jpegs call and all .lep files through ONE lepb200_decompress_leps call; outputs are DIR/<name>.lep /
-// DIR/<name>.jpg.  A file that fails reports its ExitCode on stderr and does not stop the others; the exit status is
+// DIR/<name>.jpg.  With -devices= the files are dealt to one codec per GPU, balanced by bytes (lepb200_*_multi).  A file that fails reports its ExitCode on stderr and does not stop the others; the exit status is
 // the first non-zero one.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lepton_b200.h"
@@ -41,7 +43,7 @@ static std::string base_name(const std::string& path) {
 }
 
 // -outdir=DIR: all inputs in two library calls (one per direction)
-static int run_batch(const std::vector<std::string>& files, const std::string& outdir, int device, int allow_progressive, int min_threads, int max_threads, int even_split) {
+static int run_batch(const std::vector<std::string>& files, const std::string& outdir, const std::vector<int>& devices, int allow_progressive, int min_threads, int max_threads, int even_split) {
     struct Item { std::string name; std::vector<uint8_t> data; bool is_jpeg = false; int status = 0; };
     std::vector<Item> items(files.size());
     int first_err = 0;
@@ -60,12 +62,20 @@ static int run_batch(const std::vector<std::string>& files, const std::string& o
             if (!it.is_jpeg && !(it.data[0] == 0xCF && it.data[1] == 0x84)) it.status = 42;          // UNSUPPORTED_JPEG
         }
     }
-    lepb200_codec* codec = nullptr;
-    int rc = lepb200_codec_create(&codec, device, 0);
-    if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device (%d); this build has no CPU coder\n", rc); return 33; }
-    lepb200_codec_set_allow_progressive(codec, allow_progressive);
-    lepb200_codec_set_encode_threads(codec, min_threads, max_threads);
-    lepb200_codec_set_even_split(codec, even_split);
+    // one codec per GPU; the host threads are divided between them
+    std::vector<lepb200_codec*> codecs;
+    auto destroy_all = [&]() { for (lepb200_codec* c : codecs) lepb200_codec_destroy(c); };
+    const int host_threads = devices.size() > 1 ? (int)std::max<size_t>(1, std::thread::hardware_concurrency() / devices.size()) : 0;
+    int rc = 0;
+    for (int dev : devices) {
+        lepb200_codec* c = nullptr;
+        rc = lepb200_codec_create(&c, dev, host_threads);
+        if (rc) { fprintf(stderr, "lepton-b200: no usable CUDA device %d (%d); this build has no CPU coder\n", dev, rc); destroy_all(); return 33; }
+        lepb200_codec_set_allow_progressive(c, allow_progressive);
+        lepb200_codec_set_encode_threads(c, min_threads, max_threads);
+        lepb200_codec_set_even_split(c, even_split);
+        codecs.push_back(c);
+    }
     for (int dir = 0; dir < 2; ++dir) {                      // 0: JPEG -> .lep, 1: .lep -> JPEG
         std::vector<size_t> idx;
         std::vector<lepb200_buffer> in;
@@ -73,9 +83,13 @@ static int run_batch(const std::vector<std::string>& files, const std::string& o
             if (!items[i].status && items[i].is_jpeg == (dir == 0)) { idx.push_back(i); in.push_back({items[i].data.data(), items[i].data.size()}); }
         if (idx.empty()) continue;
         std::vector<lepb200_result> res(idx.size(), lepb200_result{nullptr, 0, 0});
-        rc = dir == 0 ? lepb200_compress_jpegs(codec, in.data(), (int)in.size(), res.data())
-                      : lepb200_decompress_leps(codec, in.data(), (int)in.size(), res.data());
-        if (rc) { fprintf(stderr, "lepton-b200: %s\n", lepb200_codec_last_error(codec)); lepb200_codec_destroy(codec); return 33; }
+        rc = dir == 0 ? lepb200_compress_jpegs_multi(codecs.data(), (int)codecs.size(), in.data(), (int)in.size(), res.data())
+                      : lepb200_decompress_leps_multi(codecs.data(), (int)codecs.size(), in.data(), (int)in.size(), res.data());
+        if (rc) {
+            for (lepb200_codec* c : codecs) { const char* e = lepb200_codec_last_error(c); if (e && *e) fprintf(stderr, "lepton-b200: %s\n", e); }
+            destroy_all();
+            return 33;
+        }
         for (size_t k = 0; k < idx.size(); ++k) {            // results stay valid until the next call on the codec: write now
             Item& it = items[idx[k]];
             it.status = res[k].status == LEPB200_ST_NOT_HANDLED ? 42 : res[k].status;
@@ -86,7 +100,7 @@ static int run_batch(const std::vector<std::string>& files, const std::string& o
             if (fo) fclose(fo);
         }
     }
-    lepb200_codec_destroy(codec);
+    destroy_all();
     for (const Item& it : items) {
         if (!it.status) continue;
         fprintf(stderr, "lepton-b200: %s: exit code %d\n", it.name.c_str(), it.status);
@@ -99,6 +113,7 @@ int main(int argc, char** argv) {
     std::vector<std::string> files;
     std::string outdir;
     int device = 0;
+    std::vector<int> devices;
     int even_split = 0;
     int min_threads = 1, max_threads = 8;   // -minencodethreads= / -maxencodethreads=: bounds of the thread-segment count (change the .lep bytes)
     int allow_progressive = 1;   // this build follows the reference compiled with DEFAULT_ALLOW_PROGRESSIVE (CMakeLists.txt:293)
@@ -106,6 +121,10 @@ int main(int argc, char** argv) {
         const char* a = argv[i];
         if (a[0] == '-' && a[1] != 0) {
             if (!strncmp(a, "-device=", 8)) { device = atoi(a + 8); continue; }
+            if (!strncmp(a, "-devices=", 9)) {                       // batch mode on several GPUs: -devices=0,1,2,3
+                for (const char* q = a + 9; *q;) { devices.push_back(atoi(q)); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+                continue;
+            }
             if (!strncmp(a, "-outdir=", 8)) { outdir = a + 8; continue; }
             if (!strncmp(a, "-minencodethreads=", 18)) { min_threads = atoi(a + 18); continue; }
             if (!strncmp(a, "-maxencodethreads=", 18)) { max_threads = atoi(a + 18); continue; }
@@ -127,7 +146,8 @@ int main(int argc, char** argv) {
                         "       lepton-b200 [flags] -outdir=DIR <inputs...>      (one batch per direction)\n");
         return 1;
     }
-    if (!outdir.empty()) return run_batch(files, outdir, device, allow_progressive, min_threads, max_threads, even_split);
+    if (devices.empty()) devices.push_back(device);
+    if (!outdir.empty()) return run_batch(files, outdir, devices, allow_progressive, min_threads, max_threads, even_split);
     std::vector<uint8_t> in;
     FILE* fi = files[0] == "-" ? stdin : fopen(files[0].c_str(), "rb");
     if (!fi) { fprintf(stderr, "lepton-b200: cannot open %s\n", files[0].c_str()); return 9; }   // FILE_NOT_FOUND

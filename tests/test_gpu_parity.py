@@ -345,6 +345,7 @@ def test_corrupt_files_fail_alone_inside_a_batch():
     fc.close()
 
 
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
 def test_reference_legacy_golden_vector_decompress():
     """The reference repository's golden vector images/gold-legacy.lep (tests/golden/legacy/; test_suite/test_legacy.sh
     pins the md5 of its decoding): a legacy container without a handoff table, four thread-segments.  The product's
@@ -362,6 +363,7 @@ def test_reference_legacy_golden_vector_decompress():
     fc.close()
 
 
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
 def test_cli_batch_mode(tmp_path):
     """`lepton-b200 -outdir=DIR inputs...`: JPEGs and .lep files in one invocation, one library call per direction;
     outputs equal the reference's files, a damaged input fails alone with its exit code."""
@@ -386,6 +388,7 @@ def test_cli_batch_mode(tmp_path):
     assert not (out / "broken.jpg").exists()
 
 
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
 def test_rejectprogressive_exit_code():
     """-rejectprogressive (src/lepton/jpgcoder.cc:1056-1058, :2911-2925): progressive files leave with the reference's
     exit code 8 (PROGRESSIVE_UNSUPPORTED); baseline files of the same batch are coded as usual."""
@@ -401,6 +404,7 @@ def test_rejectprogressive_exit_code():
             assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
 
 
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
 def test_minencodethreads_files_match_reference():
     """-minencodethreads=N through the file API: the .lep bytes of the reference CLI run with the same flag."""
     from helpers import GOLDEN, MANIFEST
@@ -410,3 +414,25 @@ def test_minencodethreads_files_match_reference():
         (st, lep), = fc.compress([open(os.path.join(GOLDEN, MANIFEST[lep_name]["source"]), "rb").read()])
         fc.close()
         assert st == 0 and lep == open(os.path.join(GOLDEN, lep_name), "rb").read(), lep_name
+
+
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
+def test_multi_gpu_single_process_codec():
+    """lepb200_compress_jpegs_multi / _decompress_leps_multi: one process, every visible GPU (the same GPU twice when
+    there is only one -- two codecs, two pipelines, same device), files dealt by size; bytes == the reference's."""
+    import torch
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200MultiGpuFileCodec
+    ngpu = torch.cuda.device_count()
+    devices = list(range(ngpu)) if ngpu > 1 else [0, 0]
+    names = ["android.jpg", "androidcrop.jpg", "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "iphoneprogressive.jpg",
+             "gray2sf.jpg", "colorswap.jpg", "androidtrail.jpg"]
+    jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
+    mc = LeptonB200MultiGpuFileCodec(devices, host_threads_per_gpu=2)
+    leps = mc.compress(jpegs)
+    for n, (st, lep) in zip(names, leps):
+        assert st == 0 and lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
+    back = mc.decompress([l for _, l in leps])
+    for n, j, (st, out) in zip(names, jpegs, back):
+        assert st == 0 and out == j, n
+    mc.close()

@@ -51,3 +51,19 @@ def test_two_rank_sharding_and_max_over_ranks(tmp_path):
 def test_shard_by_size_single_rank():
     from lepton_b200.sharding import shard_by_size
     assert shard_by_size([5, 1, 3], 1) == [[0, 1, 2]]
+
+
+def test_native_sharding_matches_python():
+    """lepb200_shard_by_size (the in-process multi-GPU split of lepb200_compress_jpegs_multi) == lepton_b200.sharding's."""
+    import random
+    from lepton_b200 import shard_by_size_native
+    from lepton_b200.sharding import shard_by_size
+    rnd = random.Random(5)
+    for world in (1, 2, 3, 8):
+        for n in (1, 7, 100, 1000):
+            sizes = [rnd.choice((rnd.randrange(1, 50), rnd.randrange(1000, 5_000_000))) for _ in range(n)]
+            owner = shard_by_size_native(sizes, world)
+            shards = [[i for i in range(n) if owner[i] == r] for r in range(world)]
+            assert shards == shard_by_size(sizes, world)
+            loads = [sum(sizes[i] for i in s) for s in shards]
+            assert max(loads) - min(loads) <= max(sizes)                        # balanced to within one file
