@@ -232,6 +232,11 @@ void lepb200_codec_set_allow_progressive(lepb200_codec* codec, int on);
  * thread-segment count write_ujpg selects (:3862-3874); both clamp to 1..8, defaults 1 and 8.  They change the .lep
  * bytes exactly as they do in the reference. */
 void lepb200_codec_set_encode_threads(lepb200_codec* codec, int min_threads, int max_threads);
+/* -verify / -roundtrip of the reference CLI (its default; src/lepton/jpgcoder.cc:1095-1110, validation.cc): 1 = every
+ * .lep produced by lepb200_compress_jpegs is decoded again on the GPU and compared with the input; a file that does not
+ * come back byte for byte is withheld with status 41 (ROUNDTRIP_FAILURE), e.g. the reference's images/roundtripfail.jpg.
+ * 0 (default) = -skipverify. */
+void lepb200_codec_set_verify(lepb200_codec* codec, int on);
 /* -evensplit (jpgcoder.cc:1063-1064, :3898-3900): thread-segments cover equal numbers of MCU rows instead of equal bytes */
 void lepb200_codec_set_even_split(lepb200_codec* codec, int on);
 /* device milliseconds of the last chunk's GPU Huffman-decode kernel (diagnostic) */

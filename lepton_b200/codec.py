@@ -57,7 +57,7 @@ _EXPORTS = [
     "lepb200_last_kernel_ms", "lepb200_kernel_launches", "lepb200_last_algorithmic_bytes", "lepb200_model_bytes",
     "lepb200_device_available", "lepb200_sync", "lepb200_last_symbolise_ms", "lepb200_codec_create", "lepb200_codec_destroy", "lepb200_codec_last_error",
     "lepb200_codec_ctx", "lepb200_codec_last_timing", "lepb200_codec_kernel_launches", "lepb200_codec_set_chunk_images",
-    "lepb200_codec_set_gpu_huffman", "lepb200_codec_set_allow_progressive", "lepb200_codec_set_encode_threads", "lepb200_host_jpeg_open_threads", "lepb200_host_jpeg_open_split", "lepb200_codec_set_even_split", "lepb200_shard_by_size", "lepb200_compress_jpegs_multi", "lepb200_decompress_leps_multi", "lepb200_huffman_decode_to_device", "lepb200_encode_upload_resident", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
+    "lepb200_codec_set_gpu_huffman", "lepb200_codec_set_allow_progressive", "lepb200_codec_set_encode_threads", "lepb200_host_jpeg_open_threads", "lepb200_host_jpeg_open_split", "lepb200_codec_set_even_split", "lepb200_codec_set_verify", "lepb200_shard_by_size", "lepb200_compress_jpegs_multi", "lepb200_decompress_leps_multi", "lepb200_huffman_decode_to_device", "lepb200_encode_upload_resident", "lepb200_compress_jpegs", "lepb200_host_jpeg_open",
     "lepb200_host_jpeg_error", "lepb200_host_jpeg_image", "lepb200_host_jpeg_write_lep", "lepb200_host_jpeg_close",
     "lepb200_decompress_leps", "lepb200_host_lep_open", "lepb200_host_lep_error", "lepb200_host_lep_image",
     "lepb200_host_lep_stream", "lepb200_host_lep_recode", "lepb200_host_lep_close", "lepb200_host_frontend_seconds",
@@ -332,6 +332,8 @@ def _bind_file_api(L):
     L.lepb200_host_jpeg_open_split.restype = ctypes.c_int
     L.lepb200_codec_set_even_split.argtypes = [vp, ctypes.c_int]
     L.lepb200_codec_set_even_split.restype = None
+    L.lepb200_codec_set_verify.argtypes = [vp, ctypes.c_int]
+    L.lepb200_codec_set_verify.restype = None
     L.lepb200_host_jpeg_error.argtypes = [vp]
     L.lepb200_host_jpeg_error.restype = ctypes.c_char_p
     L.lepb200_host_jpeg_image.argtypes = [vp, ctypes.POINTER(_Image)]
@@ -491,7 +493,7 @@ class LeptonB200FileCodec:
 
     def __init__(self, device: int = 0, host_threads: int = 0, chunk_images: int = 0, gpu_huffman: bool = True,
                  allow_progressive: bool = True, min_encode_threads: int = 1, max_encode_threads: int = 8,
-                 even_split: bool = False):
+                 even_split: bool = False, verify: bool = False):
         self._L = lib()
         _bind_file_api(self._L)
         self._c = ctypes.c_void_p()
@@ -504,6 +506,7 @@ class LeptonB200FileCodec:
         self._L.lepb200_codec_set_allow_progressive(self._c, 1 if allow_progressive else 0)      # False = -rejectprogressive
         self._L.lepb200_codec_set_encode_threads(self._c, min_encode_threads, max_encode_threads)   # -minencodethreads= / -maxencodethreads=
         self._L.lepb200_codec_set_even_split(self._c, 1 if even_split else 0)                      # -evensplit
+        self._L.lepb200_codec_set_verify(self._c, 1 if verify else 0)                              # -verify (reference default) / -skipverify
 
     def close(self):
         if self._c:

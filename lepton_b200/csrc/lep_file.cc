@@ -31,6 +31,7 @@ struct lepb200_codec {
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
     bool even_split = false;       // -evensplit (jpgcoder.cc:1063-1064)
     unsigned max_encode_threads = 8, min_encode_threads = 1;   // -maxencodethreads= / -minencodethreads= (jpgcoder.cc:1080-1089)
+    bool verify = false;           // -verify: decode every .lep again and compare with the input before handing it out
     bool allow_progressive = true; // false: -rejectprogressive (files that are not single-scan-interleaved baseline exit with code 8)
     void* arena[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host memory for coefficient planes, one per in-flight chunk
     size_t arena_cap[4] = {0, 0, 0, 0};
@@ -130,6 +131,7 @@ void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
 void lepb200_codec_set_allow_progressive(lepb200_codec* c, int on) { if (c) c->allow_progressive = on != 0; }
 void lepb200_codec_set_even_split(lepb200_codec* c, int on) { if (c) c->even_split = on != 0; }
+void lepb200_codec_set_verify(lepb200_codec* c, int on) { if (c) c->verify = on != 0; }
 void lepb200_codec_set_encode_threads(lepb200_codec* c, int min_threads, int max_threads) {
     if (!c) return;
     c->min_encode_threads = (unsigned)std::min(std::max(min_threads, 1), 8);
@@ -424,6 +426,27 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 2]);
             for (int i = ranges[k].first; i < ranges[k].second; ++i) if (!status[i]) status[i] = 33;       // ExitCode::OS_ERROR
         }
+    // -verify / -roundtrip (the reference CLI's default, jpgcoder.cc:1095-1110, validation.cc): every .lep is decoded
+    // again and must give back the input byte for byte; a file that does not is withheld with ROUNDTRIP_FAILURE (41)
+    if (c->verify && ret == LEPB200_OK) {
+        std::vector<std::vector<uint8_t>> leps;
+        leps.swap(c->outputs);
+        std::vector<int> idx;
+        std::vector<lepb200_buffer> vin;
+        for (int i = 0; i < n; ++i) if (!status[i]) { idx.push_back(i); vin.push_back({leps[i].data(), leps[i].size()}); }
+        if (!idx.empty()) {
+            const double tf = c->t_front, tg = c->t_gpu, tb = c->t_back;
+            std::vector<lepb200_result> back(idx.size(), lepb200_result{nullptr, 0, 0});
+            const int vrc = lepb200_decompress_leps(c, vin.data(), (int)vin.size(), back.data());
+            for (size_t q = 0; q < idx.size(); ++q) {
+                const lepb200_buffer& src = jpegs[idx[q]];
+                const bool same = vrc == LEPB200_OK && back[q].status == 0 && back[q].len == src.len && !memcmp(back[q].data, src.data, src.len);
+                if (!same) status[idx[q]] = 41;                                    // ExitCode::ROUNDTRIP_FAILURE
+            }
+            c->t_front += tf; c->t_gpu += tg; c->t_back += tb;                   // the verification pass is part of the call
+        }
+        c->outputs.swap(leps);
+    }
     for (int i = 0; i < n; ++i) {
         if (status[i]) c->outputs[i].clear();
         out[i].status = status[i];

@@ -4,9 +4,9 @@
 // initialize_options :988-1219, process_file :1528): `lepton [flags] <in.jpg|in.lep> [out]`, direction chosen from
 // the first two bytes of the input (FF D8 -> compress, CF 84 -> decompress; check_file :2178), `-` for stdin/stdout,
 // exit status = the reference's ExitCode (src/vp8/util/memory.hh:13-39).  Flags that only configure the reference's
-// CPU runtime (-singlethread, -unjailed, -skipverify/-verify, -preload, -memory=, -threadmemory=, -timebound=)
-// are accepted and ignored: the GPU coder always produces the reference's default .lep bytes and
-// every file is verified by construction in the test-suite, not at run time.  Service modes (-socket, -listen, -fork,
+// CPU runtime (-singlethread, -unjailed, -preload, -memory=, -threadmemory=, -timebound=) are accepted and ignored.
+// Like the reference, the CLI verifies every .lep it writes by decoding it again (exit code 41, ROUNDTRIP_FAILURE, and no
+// output when the input does not come back byte for byte) unless -skipverify is given.  Service modes (-socket, -listen, -fork,
 // -benchmark, -lepcat) and output variants this build does not write (-brotliheader, -ans, -zlib0, -ujg, -startbyte /
 // -trunc slices, -embedding) are refused, never silently ignored.  Flags that change the bytes are honoured:
 // -minencodethreads= / -maxencodethreads= / -evensplit (thread-segment selection), -rejectprogressive / -allowprogressive.
@@ -43,7 +43,7 @@ static std::string base_name(const std::string& path) {
 }
 
 // -outdir=DIR: all inputs in two library calls (one per direction)
-static int run_batch(const std::vector<std::string>& files, const std::string& outdir, const std::vector<int>& devices, int allow_progressive, int min_threads, int max_threads, int even_split) {
+static int run_batch(const std::vector<std::string>& files, const std::string& outdir, const std::vector<int>& devices, int allow_progressive, int min_threads, int max_threads, int even_split, int verify) {
     struct Item { std::string name; std::vector<uint8_t> data; bool is_jpeg = false; int status = 0; };
     std::vector<Item> items(files.size());
     int first_err = 0;
@@ -74,6 +74,7 @@ static int run_batch(const std::vector<std::string>& files, const std::string& o
         lepb200_codec_set_allow_progressive(c, allow_progressive);
         lepb200_codec_set_encode_threads(c, min_threads, max_threads);
         lepb200_codec_set_even_split(c, even_split);
+        lepb200_codec_set_verify(c, verify);
         codecs.push_back(c);
     }
     for (int dir = 0; dir < 2; ++dir) {                      // 0: JPEG -> .lep, 1: .lep -> JPEG
@@ -115,6 +116,7 @@ int main(int argc, char** argv) {
     int device = 0;
     std::vector<int> devices;
     int even_split = 0;
+    int verify = 1;              // the reference verifies every file it writes unless told -skipverify (jpgcoder.cc:107-112, 1095-1110)
     int min_threads = 1, max_threads = 8;   // -minencodethreads= / -maxencodethreads=: bounds of the thread-segment count (change the .lep bytes)
     int allow_progressive = 1;   // this build follows the reference compiled with DEFAULT_ALLOW_PROGRESSIVE (CMakeLists.txt:293)
     for (int i = 1; i < argc; ++i) {
@@ -129,6 +131,9 @@ int main(int argc, char** argv) {
             if (!strncmp(a, "-minencodethreads=", 18)) { min_threads = atoi(a + 18); continue; }
             if (!strncmp(a, "-maxencodethreads=", 18)) { max_threads = atoi(a + 18); continue; }
             if (!strcmp(a, "-evensplit")) { even_split = 1; continue; }
+            if (!strcmp(a, "-skipverify") || !strcmp(a, "-skipverification") || !strcmp(a, "-skiproundtrip")) { verify = 0; continue; }
+            if (!strcmp(a, "-verify") || !strcmp(a, "-verification") || !strcmp(a, "-roundtrip") || !strcmp(a, "-validate") ||
+                !strcmp(a, "-validation")) { verify = 1; continue; }
             if (!strcmp(a, "-rejectprogressive")) { allow_progressive = 0; continue; }
             if (!strcmp(a, "-allowprogressive") || !strcmp(a, "-forceprogressive")) { allow_progressive = 1; continue; }
             if (!strcmp(a, "-socket") || !strncmp(a, "-socket=", 8) || !strncmp(a, "-listen", 7) || !strcmp(a, "-fork") ||
@@ -147,7 +152,7 @@ int main(int argc, char** argv) {
         return 1;
     }
     if (devices.empty()) devices.push_back(device);
-    if (!outdir.empty()) return run_batch(files, outdir, devices, allow_progressive, min_threads, max_threads, even_split);
+    if (!outdir.empty()) return run_batch(files, outdir, devices, allow_progressive, min_threads, max_threads, even_split, verify);
     std::vector<uint8_t> in;
     FILE* fi = files[0] == "-" ? stdin : fopen(files[0].c_str(), "rb");
     if (!fi) { fprintf(stderr, "lepton-b200: cannot open %s\n", files[0].c_str()); return 9; }   // FILE_NOT_FOUND
@@ -171,6 +176,7 @@ int main(int argc, char** argv) {
     lepb200_codec_set_allow_progressive(codec, allow_progressive);
     lepb200_codec_set_encode_threads(codec, min_threads, max_threads);
     lepb200_codec_set_even_split(codec, even_split);
+    lepb200_codec_set_verify(codec, verify);
     lepb200_buffer ib = {in.data(), in.size()};
     lepb200_result res = {nullptr, 0, 0};
     rc = is_jpeg ? lepb200_compress_jpegs(codec, &ib, 1, &res) : lepb200_decompress_leps(codec, &ib, 1, &res);

@@ -377,7 +377,7 @@ def test_cli_batch_mode(tmp_path):
     out = tmp_path / "out"
     out.mkdir()
     args = [os.path.join(GOLDEN, n) for n in names + leps] + [str(bad)]
-    r = subprocess.run([exe, "-outdir=" + str(out)] + args, capture_output=True)
+    r = subprocess.run([exe, "-skipverify", "-outdir=" + str(out)] + args, capture_output=True)
     assert r.returncode != 0 and b"broken.lep" in r.stderr, r.stderr            # the damaged file reports, the rest is written
     for n in names:
         assert (out / (n[:-4] + ".lep")).read_bytes() == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
@@ -436,3 +436,34 @@ def test_multi_gpu_single_process_codec():
     for n, j, (st, out) in zip(names, jpegs, back):
         assert st == 0 and out == j, n
     mc.close()
+
+
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
+def test_verify_mode_withholds_files_that_do_not_round_trip(tmp_path):
+    """-verify (the reference CLI's default): the reference's images/roundtripfail.jpg (tests/golden/legacy/) is coded by
+    the reference only with -skipverify -- its .lep decodes to a JPEG that differs from the input -- and exits with
+    41 (ROUNDTRIP_FAILURE) otherwise.  Same here: with verify on the file is withheld with status 41 while the other
+    files of the batch are written as usual; with verify off the bytes equal what the reference writes under -skipverify."""
+    import subprocess
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200FileCodec
+    bad = open(os.path.join(GOLDEN, "legacy", "roundtripfail.jpg"), "rb").read()
+    names = ["androidcrop.jpg", "grayscale.jpg", "iphoneprogressive.jpg", "gray2sf.jpg"]
+    jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
+    fc = LeptonB200FileCodec(0, host_threads=2, verify=True)
+    res = fc.compress(jpegs[:2] + [bad] + jpegs[2:])
+    fc.close()
+    assert [st for st, _ in res] == [0, 0, 41, 0, 0] and res[2][1] == b""
+    for n, (st, lep) in zip(names, res[:2] + res[3:]):
+        assert lep == open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read(), n
+    fc = LeptonB200FileCodec(0, host_threads=2)
+    (st, lep), = fc.compress([bad])
+    (st2, back), = fc.decompress([lep])
+    fc.close()
+    assert st == 0 and lep == open(os.path.join(GOLDEN, "legacy", "roundtripfail_skipverify.lep"), "rb").read()
+    assert st2 == 0 and back != bad and len(back) == len(bad)
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "lepton_b200", "bin", "lepton-b200")
+    r = subprocess.run([exe, os.path.join(GOLDEN, "legacy", "roundtripfail.jpg"), str(tmp_path / "o.lep")], capture_output=True)
+    assert r.returncode == 41 and not (tmp_path / "o.lep").exists()
+    r = subprocess.run([exe, os.path.join(GOLDEN, "androidcrop.jpg"), str(tmp_path / "a.lep")], capture_output=True)
+    assert r.returncode == 0 and (tmp_path / "a.lep").read_bytes() == open(os.path.join(GOLDEN, "androidcrop.lep"), "rb").read()

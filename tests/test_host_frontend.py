@@ -210,3 +210,24 @@ def test_encode_thread_flags_against_live_reference(flags, tmp_path):
         assert hj.status == 0, hj.error
         assert list(hj.coef_image().luma_y_start) == [h.luma_y_start for h in lf.handoffs], (name, flags)
         assert hj.write_lep(lepfmt.demux(lf.payload)[:lf.nseg]) == open(lep, "rb").read(), (name, flags)
+
+
+def test_roundtripfail_fixture_host_halves():
+    """images/roundtripfail.jpg of the reference repository (tests/golden/legacy/): the reference codes it only under
+    -skipverify (exit code 41, ROUNDTRIP_FAILURE, otherwise) because the .lep does not decode back to the input.  The
+    host halves reproduce both facts: the container equals the reference's -skipverify output, and re-creating the JPEG
+    from the decoded planes gives a file of the same length that differs from the input -- what lepb200_codec_set_verify
+    catches on the GPU path."""
+    from lepton_b200 import HostJpeg, HostLep
+    from helpers import oracle_decode_planes
+    d = open(os.path.join(GOLDEN, "legacy", "roundtripfail.jpg"), "rb").read()
+    ref = open(os.path.join(GOLDEN, "legacy", "roundtripfail_skipverify.lep"), "rb").read()
+    hj = HostJpeg(d)
+    assert hj.status == 0, hj.error
+    lf = lepfmt.parse_container(ref)
+    assert hj.write_lep(lepfmt.demux(lf.payload)[:lf.nseg]) == ref
+    hl = HostLep(ref)
+    assert hl.status == 0, hl.error
+    planes, _ = oracle_decode_planes(lf)
+    back = hl.recode(planes)
+    assert len(back) == len(d) and back != d
