@@ -19,7 +19,9 @@
 #include <vector>
 
 #include "base_coders.hh"                 // src/lepton
+#ifndef LEPB200_HAVE_UNCOMPRESSED_COMPONENTS  // (that header has no include guard: a file that already included it says so)
 #include "uncompressed_components.hh"     // src/lepton
+#endif
 #include "../io/MuxReader.hh"
 #include "../io/ioutil.hh"
 #include "../vp8/util/memory.hh"

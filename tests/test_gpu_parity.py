@@ -467,3 +467,27 @@ def test_verify_mode_withholds_files_that_do_not_round_trip(tmp_path):
     assert r.returncode == 41 and not (tmp_path / "o.lep").exists()
     r = subprocess.run([exe, os.path.join(GOLDEN, "androidcrop.jpg"), str(tmp_path / "a.lep")], capture_output=True)
     assert r.returncode == 0 and (tmp_path / "a.lep").read_bytes() == open(os.path.join(GOLDEN, "androidcrop.lep"), "rb").read()
+
+
+@pytest.mark.skipif(os.environ.get("LEPB200_TEST_PLUG") != "1",
+                    reason="reference CLI with the adapters plugged in: not yet tried on a GPU (the reference replaces "
+                           "operator new with a bounded arena, INTEGRATION.md section 1); set LEPB200_TEST_PLUG=1 to include it")
+@pytest.mark.timeout(600, method="thread")
+def test_reference_cli_with_b200_adapters(tmp_path):
+    """oracle/_ref/lepton-b200plug = the reference's own CLI, built from its sources with B200ComponentEncoder /
+    B200ComponentDecoder (lepton_b200/adapter/) in its two factory lines: `lepton in.jpg out.lep` must write the bytes
+    the unmodified reference writes, and `lepton -forceprogressive out.lep back.jpg` must restore the input."""
+    import subprocess
+    from helpers import GOLDEN
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "lepton-b200plug")
+    if not os.path.exists(exe):
+        pytest.skip("plug binary not built (needs the reference tree at build time)")
+    for name in ("androidcrop.jpg", "grayscale.jpg", "iphonecrop2.jpg"):
+        src = os.path.join(GOLDEN, name)
+        lep, back = str(tmp_path / "o.lep"), str(tmp_path / "o.jpg")
+        r = subprocess.run([exe, "-unjailed", "-skipverify", src, lep], capture_output=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert open(lep, "rb").read() == open(os.path.join(GOLDEN, name[:-4] + ".lep"), "rb").read(), name
+        r = subprocess.run([exe, "-unjailed", "-forceprogressive", lep, back], capture_output=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert open(back, "rb").read() == open(src, "rb").read(), name
