@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import lepfmt
-from helpers import (coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image,
+from helpers import (GOLDEN, MANIFEST, coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image,
                      random_coef_image)
 
 pytestmark = pytest.mark.gpu
