@@ -148,7 +148,8 @@ public:
     unsigned int getNumWorkers() const { return 0; }
     size_t get_model_memory_usage() const { return 0; }
     size_t get_model_worker_memory_usage() const { return 0; }
-    // Row-by-row baseline entry (recoder.cc:516, up to 8 host threads pulling rows): not wired -- a batch-of-rows
+    // Row-by-row baseline entry (recoder.cc:516, up to 8 host threads pulling rows): not wired, exactly like the
+    // reference's own second plug-in (SimpleComponentDecoder::decode_row, simple_decoder.cc:24-32) -- a batch-of-rows
     // pull would serialise the GPU behind the host Huffman encoder.  Deployments run the decoder with
     // -forceprogressive (full planes, then recode_jpeg), or use lepb200_decompress_leps which keeps the planes on
     // the device and re-creates the scan there.
