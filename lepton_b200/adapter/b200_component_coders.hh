@@ -8,6 +8,8 @@
 //   B200ComponentDecoder::decode_chunk  replaces VP8ComponentDecoder::decode_chunk (src/lepton/vp8_decoder.cc:387-490)
 //                                       on the full-plane path the reference takes for progressive files and with
 //                                       -forceprogressive (jpgcoder.cc:1052-1055, :4359-4360)
+//   B200ComponentDecoder::initialize_baseline_decoder + decode_row  replace the row-by-row baseline entry
+//                                       (vp8_decoder.cc:314-371, lepton_codec.cc:7-47; caller recoder.cc:472-545, :728)
 //
 // This file includes the reference's headers, so it is compiled only where they exist: tests/test_adapter_compiles.py
 // checks it against /root/reference with the reference's own flags (-std=c++11 -fno-exceptions -fno-rtti).
@@ -107,26 +109,22 @@ class B200ComponentDecoder : public BaseDecoder {
     lepb200_ctx* ctx_;
     Sirikata::DecoderReader* in_;
     std::vector<ThreadHandoff> handoffs_;
-    static void unsupported() { custom_exit(ExitCode::ASSERTION_FAILURE); }
-public:
-    B200ComponentDecoder() : ctx_(NULL), in_(NULL) { lepb200_adapter::exit_on(lepb200_create(&ctx_, 0)); }
-    ~B200ComponentDecoder() { lepb200_destroy(ctx_); }
-    void initialize(Sirikata::DecoderReader* input, const std::vector<ThreadHandoff>& thread_transition_info) {
-        in_ = input;
-        handoffs_ = thread_transition_info;
-    }
-    // Full-plane entry: every thread-segment of the image in one launch.
-    CodingReturnValue decode_chunk(UncompressedComponents* dst) {
+    std::vector<int16_t> rows_[4];          // baseline entry: the decoded planes rows are served from
+    uint32_t rows_bch_[4];
+    std::vector<NeighborSummary> dummy_;     // off_y() wants a neighbour-summary iterator; only the block pointer is used
+    GenericWorker* workers_;
+    unsigned int num_workers_;
+
+    // All thread-segments of the image in one launch: demux with the reference's own MuxReader
+    // (src/io/MuxReader.hh:230-331; it stops at the EOF marker or, for version 1, when the bounded reader runs dry,
+    // jpgcoder.cc:2176), then lepb200_decode_images into im.planes.
+    void decode_all(lepb200_image& im) {
         const int nseg = (int)handoffs_.size();
-        if (nseg == 0 || nseg > LEPB200_MAX_SEGMENTS) custom_exit(ExitCode::VERSION_UNSUPPORTED);
-        // demux with the reference's own MuxReader (src/io/MuxReader.hh:230-331); it stops at the EOF marker or,
-        // for version 1, when the reader runs dry (the trailer is cut off by the bounded reader, jpgcoder.cc:2176)
+        if (nseg == 0 || nseg > LEPB200_MAX_SEGMENTS) custom_exit(ExitCode::VERSION_UNSUPPORTED);   // legacy files: no handoff table
         Sirikata::MuxReader mux(Sirikata::JpegAllocator<uint8_t>(), nseg, 0, in_);
         std::pair<Sirikata::MuxReader::ResizableByteBuffer::const_iterator,
                   Sirikata::MuxReader::ResizableByteBuffer::const_iterator> seg[Sirikata::MuxReader::MAX_STREAM_ID];
         mux.fillBufferEntirely(seg);
-        lepb200_image im;
-        lepb200_adapter::fill_image(im, dst, true);
         im.nseg = nseg;
         lepb200_stream s[LEPB200_MAX_SEGMENTS];
         memset(s, 0, sizeof(s));
@@ -140,23 +138,70 @@ public:
         for (int i = 0; i < nseg; ++i) {
             if (st[i]) custom_exit((ExitCode)st[i]);
         }
+    }
+public:
+    B200ComponentDecoder() : ctx_(NULL), in_(NULL), workers_(NULL), num_workers_(0) { lepb200_adapter::exit_on(lepb200_create(&ctx_, 0)); }
+    ~B200ComponentDecoder() { lepb200_destroy(ctx_); }
+    void initialize(Sirikata::DecoderReader* input, const std::vector<ThreadHandoff>& thread_transition_info) {
+        in_ = input;
+        handoffs_ = thread_transition_info;
+    }
+    // Full-plane entry (progressive files, -forceprogressive): planes go straight into the reference's own buffers.
+    CodingReturnValue decode_chunk(UncompressedComponents* dst) {
+        lepb200_image im;
+        lepb200_adapter::fill_image(im, dst, true);
+        decode_all(im);
         for (int k = 0; k < im.ncmp; ++k) dst->worker_mark_cmp_finished((BlockType)k);
         return CODING_DONE;
     }
-    void registerWorkers(GenericWorker*, unsigned int) {}
-    GenericWorker* getWorker(unsigned int) { return NULL; }
-    unsigned int getNumWorkers() const { return 0; }
+    // Baseline entry (recode_baseline_jpeg, recoder.cc:694-889): the reference keeps only a 2-row framebuffer per
+    // worker and pulls rows with decode_row from up to 8 threads while it Huffman-encodes.  Here the whole image is
+    // decoded on the GPU when the decoder is set up -- a row-at-a-time launch would leave the device idle -- and
+    // decode_row copies the requested row into the caller's ring (read-only on shared planes: safe from any thread).
+    std::vector<ThreadHandoff> initialize_baseline_decoder(const UncompressedComponents* const colldata,
+            Sirikata::Array1d<BlockBasedImagePerChannel<true>, MAX_NUM_THREADS>&) {
+        lepb200_image im;
+        memset(&im, 0, sizeof(im));
+        im.ncmp = colldata->get_num_components();
+        im.mcuv = colldata->get_mcu_count_vertical();
+        Sirikata::Array1d<uint32_t, (size_t)ColorChannel::NumBlockTypes> maxh = colldata->get_max_coded_heights();
+        uint32_t widest = 0;
+        for (int k = 0; k < im.ncmp; ++k) {
+            im.bch[k] = colldata->block_width(k);
+            im.bcv[k] = colldata->block_height(k);
+            im.trunc_bcv[k] = (int32_t)maxh[k];
+            im.trunc_bc[k] = (int32_t)colldata->component_size_in_blocks(k);
+            memcpy(im.qtable_zigzag[k], colldata->get_quantization_tables((BlockType)k), 64 * sizeof(uint16_t));
+            rows_[k].assign((size_t)im.bch[k] * im.bcv[k] * 64, 0);
+            rows_bch_[k] = (uint32_t)im.bch[k];
+            im.planes[k] = rows_[k].data();
+            widest = std::max(widest, rows_bch_[k]);
+        }
+        dummy_.resize((size_t)widest * 2 + 2);
+        decode_all(im);
+        if (!handoffs_.empty()) handoffs_.back().luma_y_end = colldata->block_height(0);          // vp8_decoder.cc:367-369
+        for (size_t i = 0; i + 1 < handoffs_.size(); ++i) {
+            if (handoffs_[i].luma_y_end == 0) handoffs_[i].luma_y_end = handoffs_[i + 1].luma_y_start;
+        }
+        return handoffs_;
+    }
+    void decode_row(int, BlockBasedImagePerChannel<true>& image_data,
+                    Sirikata::Array1d<uint32_t, (uint32_t)ColorChannel::NumBlockTypes> component_size_in_blocks,
+                    int component, int curr_y) {
+        const uint32_t w = rows_bch_[component];
+        const size_t first = (size_t)curr_y * w;
+        if (first >= (size_t)component_size_in_blocks[component]) return;                  // truncated image (lepton_codec.cc:21-24)
+        const size_t n = std::min<size_t>(w, (size_t)component_size_in_blocks[component] - first);
+        AlignedBlock* dst = image_data[component]->off_y(curr_y, dummy_.begin()).cur;          // row slot of the 2-row ring
+        memcpy(dst->raw_data(), rows_[component].data() + first * 64, n * 64 * sizeof(int16_t));
+    }
+    // The spin workers belong to the caller's Huffman re-encoder (recoder.cc:765-815 hands them the per-thread recode
+    // jobs through getWorker); the decoder only keeps them, as LeptonCodec does (lepton_codec.hh:182-185).
+    void registerWorkers(GenericWorker* workers, unsigned int num_workers) { workers_ = workers; num_workers_ = num_workers; }
+    GenericWorker* getWorker(unsigned int i) { return workers_ ? &workers_[i] : NULL; }
+    unsigned int getNumWorkers() const { return num_workers_; }
     size_t get_model_memory_usage() const { return 0; }
     size_t get_model_worker_memory_usage() const { return 0; }
-    // Row-by-row baseline entry (recoder.cc:516, up to 8 host threads pulling rows): not wired, exactly like the
-    // reference's own second plug-in (SimpleComponentDecoder::decode_row, simple_decoder.cc:24-32) -- a batch-of-rows
-    // pull would serialise the GPU behind the host Huffman encoder.  Deployments run the decoder with
-    // -forceprogressive (full planes, then recode_jpeg), or use lepb200_decompress_leps which keeps the planes on
-    // the device and re-creates the scan there.
-    std::vector<ThreadHandoff> initialize_baseline_decoder(const UncompressedComponents* const,
-            Sirikata::Array1d<BlockBasedImagePerChannel<true>, MAX_NUM_THREADS>&) { unsupported(); return handoffs_; }
-    void decode_row(int, BlockBasedImagePerChannel<true>&,
-                    Sirikata::Array1d<uint32_t, (uint32_t)ColorChannel::NumBlockTypes>, int, int) { unsupported(); }
     void flush() {}
     void map_logical_thread_to_physical_thread(int, int) {}
     void clear_thread_state(int, int, BlockBasedImagePerChannel<true>&) {}
@@ -166,5 +211,6 @@ public:
 // The two lines that change in the reference (src/lepton/jpgcoder.cc):
 //   :1710   g_encoder.reset(makeEncoder<VPXBoolReader>(g_threaded, g_threaded));   ->  g_encoder.reset(new B200ComponentEncoder);
 //   :1727   g_decoder = makeDecoder(g_threaded, g_threaded, ujgversion == 3);       ->  g_decoder = new B200ComponentDecoder;
+//           followed, as in makeBoth (:440-452), by  if (g_threaded) g_decoder->registerWorkers(get_worker_threads(NUM_THREADS), NUM_THREADS);
 // and the process that owns the CUDA context runs with -unjailed (seccomp filter, src/io/Seccomp.cc:94-97).
 #endif

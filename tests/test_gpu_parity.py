@@ -476,7 +476,7 @@ def test_verify_mode_withholds_files_that_do_not_round_trip(tmp_path):
 def test_reference_cli_with_b200_adapters(tmp_path):
     """oracle/_ref/lepton-b200plug = the reference's own CLI, built from its sources with B200ComponentEncoder /
     B200ComponentDecoder (lepton_b200/adapter/) in its two factory lines: `lepton in.jpg out.lep` must write the bytes
-    the unmodified reference writes, and `lepton -forceprogressive out.lep back.jpg` must restore the input."""
+    the unmodified reference writes, and `lepton out.lep back.jpg` must restore the input through both decoder entries."""
     import subprocess
     from helpers import GOLDEN
     exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "lepton-b200plug")
@@ -488,6 +488,7 @@ def test_reference_cli_with_b200_adapters(tmp_path):
         r = subprocess.run([exe, "-unjailed", "-skipverify", src, lep], capture_output=True)
         assert r.returncode == 0, r.stderr[-2000:]
         assert open(lep, "rb").read() == open(os.path.join(GOLDEN, name[:-4] + ".lep"), "rb").read(), name
-        r = subprocess.run([exe, "-unjailed", "-forceprogressive", lep, back], capture_output=True)
-        assert r.returncode == 0, r.stderr[-2000:]
-        assert open(back, "rb").read() == open(src, "rb").read(), name
+        for flags in (["-forceprogressive"], [], ["-singlethread"]):        # full-plane entry, row entry threaded / single-threaded
+            r = subprocess.run([exe, "-unjailed"] + flags + [lep, back], capture_output=True)
+            assert r.returncode == 0, (flags, r.stderr[-2000:])
+            assert open(back, "rb").read() == open(src, "rb").read(), (name, flags)
