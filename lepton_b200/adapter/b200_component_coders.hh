@@ -178,6 +178,26 @@ public:
             widest = std::max(widest, rows_bch_[k]);
         }
         dummy_.resize((size_t)widest * 2 + 2);
+        if (handoffs_.empty()) {
+            // legacy container: segment count and luma split rows open the payload (vp8_decoder.cc:337-366); such
+            // handoffs carry no Huffman state, so the caller re-encodes single-threaded (recoder.cc:731-733)
+            unsigned char mark = 0;
+            if (in_->Read(&mark, 1).second != Sirikata::JpegError::nil()) return handoffs_;
+            if (mark == 0) custom_exit(ExitCode::THREADING_PARTIAL_MCU);
+            ThreadHandoff th;
+            memset(&th, 0, sizeof(th));
+            th.num_overhang_bits = ThreadHandoff::LEGACY_OVERHANG_BITS;
+            th.luma_y_end = colldata->block_height(0);
+            handoffs_.insert(handoffs_.end(), mark, th);
+            std::vector<uint16_t> ends(mark - 1);
+            IOUtil::ReadFull(in_, ends.data(), sizeof(uint16_t) * (mark - 1));
+            const int mul = colldata->min_vertical_luma_multiple();
+            for (int i = 0; i + 1 < mark; ++i) {
+                handoffs_[i].luma_y_end = htole16(ends[i]);
+                if (handoffs_[i].luma_y_end % mul) custom_exit(ExitCode::THREADING_PARTIAL_MCU);
+            }
+            for (int i = 1; i < mark; ++i) handoffs_[i].luma_y_start = handoffs_[i - 1].luma_y_end;
+        }
         decode_all(im);
         if (!handoffs_.empty()) handoffs_.back().luma_y_end = colldata->block_height(0);          // vp8_decoder.cc:367-369
         for (size_t i = 0; i + 1 < handoffs_.size(); ++i) {
