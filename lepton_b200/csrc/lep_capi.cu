@@ -499,11 +499,14 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     std::vector<HuffJob> jobs(n);
     std::vector<HuffTableDev> tabs;
     std::vector<std::pair<const lepb200_hufftable*, int>> seen;     // dedupe identical tables (most files share the standard ones)
+    std::vector<char> tab_ok;                                       // build result per table: a cache hit on a table that failed to build fails too
     auto table_index = [&](const lepb200_hufftable& t, bool& ok) -> int {
-        for (auto& s : seen) if (!memcmp(s.first, &t, sizeof(t))) return s.second;
+        for (auto& s : seen) if (!memcmp(s.first, &t, sizeof(t))) { if (!tab_ok[s.second]) ok = false; return s.second; }
         HuffTableDev d;
-        ok = build_table_dev(t, d);
+        const bool built = build_table_dev(t, d);
+        if (!built) ok = false;
         tabs.push_back(d);
+        tab_ok.push_back(built ? 1 : 0);
         seen.emplace_back(&t, (int)tabs.size() - 1);
         return (int)tabs.size() - 1;
     };
@@ -763,11 +766,14 @@ int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* imgs, 
     std::vector<HEncSeg> hs;
     std::vector<HEncTable> tabs;
     std::vector<const lepb200_hufftable*> seen;
+    std::vector<char> tab_ok;                     // build result per table (a cache hit on a table that failed to build fails too)
     auto table_index = [&](const lepb200_hufftable& t, bool& ok) -> int {
-        for (size_t q = 0; q < seen.size(); ++q) if (!memcmp(seen[q], &t, sizeof(t))) return (int)q;
+        for (size_t q = 0; q < seen.size(); ++q) if (!memcmp(seen[q], &t, sizeof(t))) { if (!tab_ok[q]) ok = false; return (int)q; }
         HEncTable e;
-        ok = build_enc_table(t, e) && ok;
+        const bool built = build_enc_table(t, e);
+        if (!built) ok = false;
         tabs.push_back(e);
+        tab_ok.push_back(built ? 1 : 0);
         seen.push_back(&t);
         return (int)tabs.size() - 1;
     };

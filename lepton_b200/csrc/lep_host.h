@@ -52,12 +52,12 @@ struct HuffTable {
     uint8_t bits[17] = {0};
     uint8_t vals[256] = {0};
     // decode acceleration
-    uint16_t fast[512];        // (len << 8) | symbol for codes of <= 9 bits, 0 = slow path
-    int32_t maxcode[18];       // canonical decode
-    int32_t valoff[18];
+    uint16_t fast[512] = {0};  // (len << 8) | symbol for codes of <= 9 bits, 0 = slow path
+    int32_t maxcode[18] = {0}; // canonical decode
+    int32_t valoff[18] = {0};
     // encode side
-    uint16_t ecode[256];
-    uint8_t elen[256];
+    uint16_t ecode[256] = {0};
+    uint8_t elen[256] = {0};
     int max_eobrun = 0;        // progressive: longest end-of-band run with a code in this table
     bool build();
 };

@@ -159,6 +159,7 @@ bool parse_frame(Jpeg& j) {
     while (hpos + 4 <= h.size()) {
         const uint8_t type = h[hpos + 1];
         const size_t len = 2 + be16(&h[hpos + 2]);
+        if (hpos + len > h.size()) return fail(j, UNSUPPORTED_JPEG, "truncated header segment");      // the header of a .lep is untrusted input
         const uint8_t* seg = &h[hpos];
         if (type == 0xDB) {
             size_t p = 4;
@@ -698,6 +699,7 @@ bool gpu_scan_setup(const Jpeg& j, GpuScanSetup& out) {
             if (p != len) return false;
         } else if (type == 0xDD) {
             if (nsos) return false;
+            if (len < 6) return false;
             out.rsti = be16(seg + 4);
         } else if (type == 0xDA) {
             if (++nsos > 1) return false;
@@ -756,8 +758,9 @@ bool decode_scans(Jpeg& j, int16_t* const planes[4]) {
                 }
                 if (p != len) return fail(j, UNSUPPORTED_JPEG, "size mismatch in dht marker");
             } else if (type == 0xDD) {
-                rsti = be16(seg + 4);
+                if (len >= 6) rsti = be16(seg + 4);
             } else if (type == 0xDA) {
+                if (len < 5) return fail(j, UNSUPPORTED_JPEG, "bad SOS");
                 sc.ncomp = seg[4];
                 if (sc.ncomp > j.ncmp || sc.ncomp < 1 || len < (size_t)(8 + 2 * sc.ncomp)) return fail(j, UNSUPPORTED_JPEG, "bad SOS");
                 for (int i = 0; i < sc.ncomp; ++i) {

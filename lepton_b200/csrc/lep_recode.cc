@@ -48,7 +48,13 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
         size_t have = 0;
         int ret;
         do {
-            if (have == blob.size()) blob.resize(blob.size() * 2);
+            if (have == blob.size()) {
+                // untrusted input: a few KB of zlib can expand to gigabytes.  The blob holds the JPEG header, garbage and
+                // per-restart bookkeeping -- all bounded by the JPEG it describes (the reference bounds it through its
+                // memory limit); 256 MB is far beyond any file the 4-byte size fields can describe sensibly
+                if (blob.size() >= (size_t(256) << 20)) { inflateEnd(&zs); return lfail(lf, 38 /*TOO_MUCH_MEMORY_NEEDED, memory.hh:34*/, "header blob too large"); }
+                blob.resize(blob.size() * 2);
+            }
             zs.next_out = blob.data() + have; zs.avail_out = (uInt)(blob.size() - have);
             ret = inflate(&zs, Z_NO_FLUSH);
             have = blob.size() - zs.avail_out;
@@ -223,6 +229,7 @@ struct FastWriter {
     inline void raw(uint8_t b) { room(1); *p++ = b; }
     inline void raw_bytes(const uint8_t* src, size_t n) { room(n); memcpy(p, src, n); p += n; }
     inline void put(uint32_t v, int n) {          // n <= 32, v < 2^n
+        if (n > 32) n = 32;                       // tables are validated by HuffTable::build(); never shift by >= 64
         acc = (acc << n) | v;
         nbits += n;
         if (nbits >= 32) {
@@ -242,7 +249,7 @@ struct FastWriter {
         }
     }
     inline void flush_bytes() {
-        room(16);
+        room(16 + (size_t)(nbits / 8) * 2);
         while (nbits >= 8) {
             const uint8_t b = (uint8_t)(acc >> (nbits - 8));
             *p++ = b;
@@ -349,6 +356,7 @@ bool gpu_recode_setup(const LepFile& lf, GpuRecodeSetup& out) {
             }
         } else if (type == 0xDD) {
             if (nsos) return false;
+            if (len < 6) return false;
             out.rsti = be16(seg + 4);
         } else if (type == 0xDA) {
             if (++nsos > 1) return false;
@@ -428,15 +436,19 @@ bool recode_baseline(const LepFile& lf, const int16_t* const planes[4], std::vec
                 p += 16 + total;
             }
         } else if (type == 0xDD) {
+            if (len < 6) { err = "bad DRI"; return false; }
             rsti = be16(seg + 4);
         } else if (type == 0xDA) {
+            if (len < 5) { err = "bad SOS"; return false; }
             ncomp = seg[4];
-            if (ncomp < 1 || ncomp > j.ncmp) { err = "bad SOS"; return false; }
+            if (ncomp < 1 || ncomp > j.ncmp || len < (size_t)(8 + 2 * ncomp)) { err = "bad SOS"; return false; }
             for (int i = 0; i < ncomp; ++i) {
                 int c = 0;
                 while (c < j.ncmp && j.cmp[c].jid != seg[5 + 2 * i]) ++c;
                 if (c == j.ncmp) { err = "component id mismatch"; return false; }
                 scmp[i] = c; td[c] = seg[6 + 2 * i] >> 4; ta[c] = seg[6 + 2 * i] & 15;
+                // the .lep header is untrusted input: table selectors in range and the tables present (as recode_scans does)
+                if (td[c] >= 4 || ta[c] >= 4 || !dc_t[td[c]].set || !ac_t[ta[c]].set) { err = "scan refers to a missing huffman table"; return false; }
             }
             hpos += len;
             found = true;
@@ -627,8 +639,9 @@ bool recode_scans(const LepFile& lf, const int16_t* const planes[4], std::vector
                     p += 16 + total;
                 }
             } else if (type == 0xDD) {
-                rsti = be16(seg + 4);
+                if (len >= 6) rsti = be16(seg + 4);
             } else if (type == 0xDA) {
+                if (len < 5) { err = "bad SOS"; return false; }
                 sc.ncomp = seg[4];
                 if (sc.ncomp < 1 || sc.ncomp > j.ncmp || len < (size_t)(8 + 2 * sc.ncomp)) { err = "bad SOS"; return false; }
                 for (int i = 0; i < sc.ncomp; ++i) {

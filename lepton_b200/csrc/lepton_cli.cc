@@ -188,8 +188,9 @@ int main(int argc, char** argv) {
     }
     FILE* fo = outname == "-" ? stdout : fopen(outname.c_str(), "wb");
     if (!fo) { lepb200_codec_destroy(codec); return 33; }
-    fwrite(res.data, 1, res.len, fo);
-    if (fo != stdout) fclose(fo);
+    bool wrote = fwrite(res.data, 1, res.len, fo) == res.len;
+    if (fo != stdout) wrote = (fclose(fo) == 0) && wrote; else wrote = (fflush(fo) == 0) && wrote;
+    if (!wrote) { fprintf(stderr, "lepton-b200: could not write %s\n", outname.c_str()); lepb200_codec_destroy(codec); return 33; }     // OS_ERROR
     if (is_jpeg) fprintf(stderr, "%zu %zu\n%.2f%%\n", res.len, in.size(), 100.0 * (double)res.len / (double)in.size());
     lepb200_codec_destroy(codec);
     return 0;
