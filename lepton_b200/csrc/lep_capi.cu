@@ -17,6 +17,7 @@
 #include "lep_decode.cu"
 #include "lep_decode_thread.cu"
 #include "lep_decode_lockstep.cu"
+#include "lep_decode_group.cu"
 #include "lep_huff.cu"
 #include "lep_huffenc.cu"
 
@@ -113,7 +114,9 @@ struct lepb200_ctx {
     int enc_threads = 0;
     int dec_split_pct = 50;
     int dec_lock = 0;                     // mode 3: segments of the current batch that go to the lock-step kernel
-    int dec_threads_max = 16384;          // thread mode: segments per launch (one 1.58 MB model each)
+    int dec_threads_max = 16384;          // thread / group modes: segments per launch (one 1.58 MB model each)
+    int dec_lanes = 8;                    // mode 4 (lep_decode_group.cu): lanes per thread-segment, 32 / dec_lanes segments per warp in lock step
+    int dec_group_grid = 0;               // mode 4: CTAs of the current batch
     int dec_threads = 0;                  // thread mode: model / row-buffer slots of the current batch
     bool tokens_known = false;            // token streams laid out on the host from caller-supplied bounds (no counting pre-pass)
     unsigned long long token_total = 0;
@@ -184,6 +187,28 @@ int validate_image(lepb200_ctx* ctx, const lepb200_image& im) {
     for (int s = 0; s + 1 < im.nseg; ++s)
         if (im.luma_y_start[s] > im.luma_y_start[s + 1]) { ctx->err = "segment starts must be non-decreasing"; return LEPB200_ERR_INVALID; }
     return 0;
+}
+
+// lep_decode_group_kernel<G>: launch shape (warps per CTA, thread-segments per warp) and resident CTAs per SM
+template <int G> int group_ctas_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_group_kernel<G>, GCfg<G>::THREADS, 0) != cudaSuccess) n = 1;
+    return std::max(n, 1);
+}
+void group_launch_shape(int lanes, int& warps, int& per_warp, int& ctas_per_sm) {
+    per_warp = 32 / lanes;
+    switch (lanes) {
+    case 1: warps = GCfg<1>::WARPS; ctas_per_sm = group_ctas_per_sm<1>(); break;
+    case 2: warps = GCfg<2>::WARPS; ctas_per_sm = group_ctas_per_sm<2>(); break;
+    case 4: warps = GCfg<4>::WARPS; ctas_per_sm = group_ctas_per_sm<4>(); break;
+    case 8: warps = GCfg<8>::WARPS; ctas_per_sm = group_ctas_per_sm<8>(); break;
+    case 16: warps = GCfg<16>::WARPS; ctas_per_sm = group_ctas_per_sm<16>(); break;
+    default: warps = GCfg<32>::WARPS; ctas_per_sm = group_ctas_per_sm<32>(); break;
+    }
+}
+template <int G> void launch_group_kernel(int grid, cudaStream_t st, const ImageDesc* images, SegDesc* segs, int first, int count, const int* order,
+                                          int* counter, uint16_t* models, uint8_t* rows, size_t row_stride) {
+    lep_decode_group_kernel<G><<<grid, GCfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
 }
 
 // Common part of encode/decode upload: job tables, pools, plane arena layout.
@@ -276,6 +301,15 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
         ctx->enc_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         CK(ctx->d_models.reserve((size_t)ctx->enc_threads * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)ctx->enc_threads * row_stride));
+    } else if (!encode && ctx->dec_mode == 4) {
+        // group kernel: one zero-filled model per segment of a launch, one row buffer per resident group
+        ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
+        int warps = 0, per_warp = 0, gsm = 0;
+        group_launch_shape(ctx->dec_lanes, warps, per_warp, gsm);
+        const int per_cta = warps * per_warp;
+        ctx->dec_group_grid = std::max(1, std::min(gsm * ctx->sm_count, (ctx->dec_threads + per_cta - 1) / per_cta));
+        CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
+        CK(ctx->d_rows.reserve((size_t)ctx->dec_group_grid * per_cta * row_stride));
     } else if (!encode && (ctx->dec_mode == 1 || ctx->dec_mode == 2)) {
         ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
@@ -352,6 +386,10 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
     if (const char* e = getenv("LEPB200_ENC_MODE")) ctx->enc_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_SPLIT")) ctx->dec_split_pct = std::min(100, std::max(0, atoi(e)));
+    if (const char* e = getenv("LEPB200_DEC_LANES")) {
+        const int g = atoi(e);
+        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ctx->dec_lanes = g;
+    }
     if (ctx->dec_mode == 3 && (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
                                cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
                                cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
@@ -885,7 +923,36 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->dec_mode == 1 || ctx->dec_mode == 2) {
+    if (ctx->dec_mode == 4) {
+        // G lanes per segment, 32 / G segments per warp in lock step; the groups of a launch share a queue of at most
+        // dec_threads segments (one zero-filled model each), largest first
+        int warps = 0, per_warp = 0, gsm = 0;
+        group_launch_shape(ctx->dec_lanes, warps, per_warp, gsm);
+        const int per_cta = warps * per_warp;
+        for (int first = 0; first < nseg; first += ctx->dec_threads) {
+            const int count = std::min(ctx->dec_threads, nseg - first);
+            const int grid = std::max(1, std::min(ctx->dec_group_grid, (count + per_cta - 1) / per_cta));
+            CK(cudaMemsetAsync(ctx->d_models.p, 0, (size_t)count * MODEL_BYTES, ctx->stream));       // identity prior = zero fill
+            CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
+            const ImageDesc* di = static_cast<const ImageDesc*>(ctx->d_images.p);
+            SegDesc* ds = static_cast<SegDesc*>(ctx->d_segs.p);
+            const int* dord = static_cast<const int*>(ctx->d_order.p);
+            int* dcnt = static_cast<int*>(ctx->d_counter.p);
+            uint16_t* dm = static_cast<uint16_t*>(ctx->d_models.p);
+            uint8_t* dr = static_cast<uint8_t*>(ctx->d_rows.p);
+            switch (ctx->dec_lanes) {
+            case 1: launch_group_kernel<1>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 2: launch_group_kernel<2>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 4: launch_group_kernel<4>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 8: launch_group_kernel<8>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 16: launch_group_kernel<16>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            default: launch_group_kernel<32>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            }
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+        }
+        ctx->launches -= 1;
+    } else if (ctx->dec_mode == 1 || ctx->dec_mode == 2) {
         // one thread per segment, largest segments first; a launch covers as many segments as there are model slots
         // (mode 1: free-running lanes, mode 2: lanes in lock step)
         const auto kernel = ctx->dec_mode == 2 ? lep_decode_lockstep_kernel : lep_decode_thread_kernel;

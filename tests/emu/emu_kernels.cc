@@ -14,6 +14,7 @@
 #include "../../lepton_b200/csrc/lep_decode.cu"
 #include "../../lepton_b200/csrc/lep_decode_thread.cu"
 #include "../../lepton_b200/csrc/lep_decode_lockstep.cu"
+#include "../../lepton_b200/csrc/lep_decode_group.cu"
 #include "../../include/lepton_b200.h"
 
 using namespace lepb200;
@@ -63,7 +64,19 @@ void kernel_body(void* p) {
     const LaunchArgs& a = *static_cast<const LaunchArgs*>(p);
     if (a.kernel == 0) lep_decode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
     else if (a.kernel == 1) lep_decode_thread_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
-    else lep_decode_lockstep_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 2) lep_decode_lockstep_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 101) lep_decode_group_kernel<1>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 102) lep_decode_group_kernel<2>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 104) lep_decode_group_kernel<4>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 108) lep_decode_group_kernel<8>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 116) lep_decode_group_kernel<16>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else lep_decode_group_kernel<32>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+}
+
+// launch shape of the group kernel: warps per CTA and thread-segments per warp for G lanes per segment
+void group_shape(int G, int& warps, int& per_warp) {
+    per_warp = 32 / G;
+    warps = G >= 4 ? 4 : G;
 }
 
 }  // namespace
@@ -73,7 +86,8 @@ void kernel_body(void* p) {
 // like the device arena); per-segment status and decision counts come back like lepb200_decode_fetch reports them.
 extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, const lepb200_stream* in,
                                  int32_t* status_out, uint64_t* ndecisions_out) {
-    if (nimages <= 0 || !images || !in || kernel < 0 || kernel > 2) return LEPB200_ERR_INVALID;
+    const bool group = kernel == 101 || kernel == 102 || kernel == 104 || kernel == 108 || kernel == 116 || kernel == 132;
+    if (nimages <= 0 || !images || !in || kernel < 0 || (kernel > 2 && !group)) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
     std::vector<SegDesc> segs;
     std::vector<size_t> seg_blocks;
@@ -132,7 +146,16 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
     int counter = 0;
     a.counter = &counter;
     unsigned grid, block;
-    if (kernel == 0) {
+    size_t group_slots = 0;
+    if (group) {
+        // 100 + G: lep_decode_group_kernel<G>; grid_cap > 0 limits the CTAs so that groups take several segments from the queue
+        int warps, per_warp;
+        group_shape(kernel - 100, warps, per_warp);
+        grid = (unsigned)((nseg + warps * per_warp - 1) / (warps * per_warp));
+        if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
+        block = (unsigned)warps * 32;
+        group_slots = (size_t)grid * warps * per_warp;
+    } else if (kernel == 0) {
         grid = (unsigned)((nseg + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA);
         if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
         block = DEC_WARPS_PER_CTA * 32;
@@ -141,8 +164,8 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
         block = 32;
     }
     const size_t slots = kernel == 0 ? (size_t)grid * DEC_WARPS_PER_CTA : (size_t)nseg;
-    std::vector<uint16_t> models(slots * M_TOTAL, kernel == 0 ? 0x5a5a : 0);       // thread kernels: zero fill before the launch; the warp kernel clears its own
-    std::vector<uint8_t> rows(slots * row_stride, 0);
+    std::vector<uint16_t> models(slots * M_TOTAL, kernel == 0 ? 0x5a5a : 0);       // thread / group kernels: zero fill before the launch; the warp kernel clears its own
+    std::vector<uint8_t> rows((group ? group_slots : slots) * row_stride, 0);
     a.models = models.data(); a.rows = rows.data();
     emu::launch(grid, block, kernel_body, &a);
     for (int s = 0; s < nseg; ++s) {

@@ -93,6 +93,22 @@ def test_golden_batch_decode_lockstep_kernel(monkeypatch, mode):
         c.close()
 
 
+@pytest.mark.parametrize("lanes", ["1", "4", "8", "32"])
+def test_golden_batch_decode_group_kernel(monkeypatch, lanes):
+    """lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4): G lanes per thread-segment, 32 / G segments per warp in lock step;
+    every group size must give the reference planes.  LEPB200_DEC_THREADS=32 forces several launches / a shared queue."""
+    from lepton_b200 import LeptonB200Codec
+    monkeypatch.setenv("LEPB200_DEC_MODE", "4")
+    monkeypatch.setenv("LEPB200_DEC_LANES", lanes)
+    if lanes == "4":
+        monkeypatch.setenv("LEPB200_DEC_THREADS", "32")
+    c = LeptonB200Codec(0)
+    try:
+        test_golden_batch_decode_matches_reference_planes(c)
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("cfg", [
     dict(ncmp=3, mcuh=5, mcuv=4, sf=((2, 2), (1, 1), (1, 1)), nseg=1),
     dict(ncmp=3, mcuh=7, mcuv=6, sf=((2, 2), (1, 1), (1, 1)), nseg=3),
