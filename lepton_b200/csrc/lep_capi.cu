@@ -18,6 +18,7 @@
 #include "lep_decode_thread.cu"
 #include "lep_decode_lockstep.cu"
 #include "lep_decode_group.cu"
+#include "lep_decode_g2.cu"
 #include "lep_huff.cu"
 #include "lep_huffenc.cu"
 
@@ -189,26 +190,31 @@ int validate_image(lepb200_ctx* ctx, const lepb200_image& im) {
     return 0;
 }
 
-// lep_decode_group_kernel<G>: launch shape (warps per CTA, thread-segments per warp) and resident CTAs per SM
-template <int G> int group_ctas_per_sm() {
+// lep_decode_group_kernel<G> / lep_decode_g2_kernel<G>: launch shape (warps per CTA, thread-segments per warp) and resident CTAs per SM
+template <int G, bool V2> int group_ctas_per_sm() {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_group_kernel<G>, GCfg<G>::THREADS, 0) != cudaSuccess) n = 1;
+    cudaError_t e = V2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_g2_kernel<G>, G2Cfg<G>::THREADS, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_group_kernel<G>, GCfg<G>::THREADS, 0);
+    if (e != cudaSuccess) n = 1;
     return std::max(n, 1);
 }
-void group_launch_shape(int lanes, int& warps, int& per_warp, int& ctas_per_sm) {
+static_assert(GCfg<1>::WARPS == G2Cfg<1>::WARPS && GCfg<2>::WARPS == G2Cfg<2>::WARPS && GCfg<4>::WARPS == G2Cfg<4>::WARPS &&
+              GCfg<8>::WARPS == G2Cfg<8>::WARPS && GCfg<16>::WARPS == G2Cfg<16>::WARPS && GCfg<32>::WARPS == G2Cfg<32>::WARPS, "same launch shape");
+void group_launch_shape(int lanes, bool v2, int& warps, int& per_warp, int& ctas_per_sm) {
     per_warp = 32 / lanes;
     switch (lanes) {
-    case 1: warps = GCfg<1>::WARPS; ctas_per_sm = group_ctas_per_sm<1>(); break;
-    case 2: warps = GCfg<2>::WARPS; ctas_per_sm = group_ctas_per_sm<2>(); break;
-    case 4: warps = GCfg<4>::WARPS; ctas_per_sm = group_ctas_per_sm<4>(); break;
-    case 8: warps = GCfg<8>::WARPS; ctas_per_sm = group_ctas_per_sm<8>(); break;
-    case 16: warps = GCfg<16>::WARPS; ctas_per_sm = group_ctas_per_sm<16>(); break;
-    default: warps = GCfg<32>::WARPS; ctas_per_sm = group_ctas_per_sm<32>(); break;
+    case 1: warps = GCfg<1>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<1, true>() : group_ctas_per_sm<1, false>(); break;
+    case 2: warps = GCfg<2>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<2, true>() : group_ctas_per_sm<2, false>(); break;
+    case 4: warps = GCfg<4>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<4, true>() : group_ctas_per_sm<4, false>(); break;
+    case 8: warps = GCfg<8>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<8, true>() : group_ctas_per_sm<8, false>(); break;
+    case 16: warps = GCfg<16>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<16, true>() : group_ctas_per_sm<16, false>(); break;
+    default: warps = GCfg<32>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<32, true>() : group_ctas_per_sm<32, false>(); break;
     }
 }
-template <int G> void launch_group_kernel(int grid, cudaStream_t st, const ImageDesc* images, SegDesc* segs, int first, int count, const int* order,
+template <int G> void launch_group_kernel(bool v2, int grid, cudaStream_t st, const ImageDesc* images, SegDesc* segs, int first, int count, const int* order,
                                           int* counter, uint16_t* models, uint8_t* rows, size_t row_stride) {
-    lep_decode_group_kernel<G><<<grid, GCfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
+    if (v2) lep_decode_g2_kernel<G><<<grid, G2Cfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
+    else lep_decode_group_kernel<G><<<grid, GCfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
 }
 
 // Common part of encode/decode upload: job tables, pools, plane arena layout.
@@ -301,11 +307,11 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
         ctx->enc_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         CK(ctx->d_models.reserve((size_t)ctx->enc_threads * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)ctx->enc_threads * row_stride));
-    } else if (!encode && ctx->dec_mode == 4) {
+    } else if (!encode && (ctx->dec_mode == 4 || ctx->dec_mode == 5)) {
         // group kernel: one zero-filled model per segment of a launch, one row buffer per resident group
         ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         int warps = 0, per_warp = 0, gsm = 0;
-        group_launch_shape(ctx->dec_lanes, warps, per_warp, gsm);
+        group_launch_shape(ctx->dec_lanes, ctx->dec_mode == 5, warps, per_warp, gsm);
         const int per_cta = warps * per_warp;
         ctx->dec_group_grid = std::max(1, std::min(gsm * ctx->sm_count, (ctx->dec_threads + per_cta - 1) / per_cta));
         CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
@@ -923,11 +929,12 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->dec_mode == 4) {
-        // G lanes per segment, 32 / G segments per warp in lock step; the groups of a launch share a queue of at most
+    if (ctx->dec_mode == 4 || ctx->dec_mode == 5) {
+        // (4: lep_decode_group.cu, 5: lep_decode_g2.cu) G lanes per segment, 32 / G segments per warp in lock step; the groups of a launch share a queue of at most
         // dec_threads segments (one zero-filled model each), largest first
         int warps = 0, per_warp = 0, gsm = 0;
-        group_launch_shape(ctx->dec_lanes, warps, per_warp, gsm);
+        const bool v2 = ctx->dec_mode == 5;
+        group_launch_shape(ctx->dec_lanes, v2, warps, per_warp, gsm);
         const int per_cta = warps * per_warp;
         for (int first = 0; first < nseg; first += ctx->dec_threads) {
             const int count = std::min(ctx->dec_threads, nseg - first);
@@ -941,12 +948,12 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
             uint16_t* dm = static_cast<uint16_t*>(ctx->d_models.p);
             uint8_t* dr = static_cast<uint8_t*>(ctx->d_rows.p);
             switch (ctx->dec_lanes) {
-            case 1: launch_group_kernel<1>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 2: launch_group_kernel<2>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 4: launch_group_kernel<4>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 8: launch_group_kernel<8>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 16: launch_group_kernel<16>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            default: launch_group_kernel<32>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 1: launch_group_kernel<1>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 2: launch_group_kernel<2>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 4: launch_group_kernel<4>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 8: launch_group_kernel<8>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 16: launch_group_kernel<16>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            default: launch_group_kernel<32>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
             }
             CK(cudaGetLastError());
             ctx->launches += 1;

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
 SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
-           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_encode_lockstep.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"), os.path.join(CSRC, "lep_decode_group.cu"),
+           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_encode_lockstep.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"), os.path.join(CSRC, "lep_decode_group.cu"), os.path.join(CSRC, "lep_decode_g2.cu"),
            os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
@@ -29,6 +29,12 @@ def KERNEL_GROUP(lanes):
     """lep_decode_group_kernel<lanes>: `lanes` lanes per thread-segment, 32 / lanes segments per warp in lock step."""
     assert lanes in (1, 2, 4, 8, 16, 32)
     return 100 + lanes
+
+
+def KERNEL_G2(lanes):
+    """lep_decode_g2_kernel<lanes>: the group kernel with the stripped-down step loop."""
+    assert lanes in (1, 2, 4, 8, 16, 32)
+    return 200 + lanes
 
 _LIB = None
 

@@ -15,6 +15,7 @@
 #include "../../lepton_b200/csrc/lep_decode_thread.cu"
 #include "../../lepton_b200/csrc/lep_decode_lockstep.cu"
 #include "../../lepton_b200/csrc/lep_decode_group.cu"
+#include "../../lepton_b200/csrc/lep_decode_g2.cu"
 #include "../../include/lepton_b200.h"
 
 using namespace lepb200;
@@ -70,7 +71,13 @@ void kernel_body(void* p) {
     else if (a.kernel == 104) lep_decode_group_kernel<4>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
     else if (a.kernel == 108) lep_decode_group_kernel<8>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
     else if (a.kernel == 116) lep_decode_group_kernel<16>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else lep_decode_group_kernel<32>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 132) lep_decode_group_kernel<32>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 201) lep_decode_g2_kernel<1>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 202) lep_decode_g2_kernel<2>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 204) lep_decode_g2_kernel<4>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 208) lep_decode_g2_kernel<8>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else if (a.kernel == 216) lep_decode_g2_kernel<16>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
+    else lep_decode_g2_kernel<32>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
 }
 
 // launch shape of the group kernel: warps per CTA and thread-segments per warp for G lanes per segment
@@ -86,7 +93,8 @@ void group_shape(int G, int& warps, int& per_warp) {
 // like the device arena); per-segment status and decision counts come back like lepb200_decode_fetch reports them.
 extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, const lepb200_stream* in,
                                  int32_t* status_out, uint64_t* ndecisions_out) {
-    const bool group = kernel == 101 || kernel == 102 || kernel == 104 || kernel == 108 || kernel == 116 || kernel == 132;
+    const int gl = kernel % 100;
+    const bool group = (kernel / 100 == 1 || kernel / 100 == 2) && (gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32);
     if (nimages <= 0 || !images || !in || kernel < 0 || (kernel > 2 && !group)) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
     std::vector<SegDesc> segs;
@@ -150,7 +158,7 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
     if (group) {
         // 100 + G: lep_decode_group_kernel<G>; grid_cap > 0 limits the CTAs so that groups take several segments from the queue
         int warps, per_warp;
-        group_shape(kernel - 100, warps, per_warp);
+        group_shape(kernel % 100, warps, per_warp);
         grid = (unsigned)((nseg + warps * per_warp - 1) / (warps * per_warp));
         if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
         block = (unsigned)warps * 32;

@@ -18,10 +18,10 @@ from helpers import (coef_image_from_lep, geometry_of, golden_leps, load_lep, or
                      random_coef_image, segments_of)
 
 KERNELS = [emu.KERNEL_WARP, emu.KERNEL_THREAD, emu.KERNEL_LOCKSTEP]
-GROUPS = [emu.KERNEL_GROUP(g) for g in (1, 2, 4, 8, 16, 32)]       # lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4)
+GROUPS = [emu.KERNEL_GROUP(g) for g in (1, 4, 32)] + [emu.KERNEL_G2(g) for g in (1, 2, 4, 8, 16, 32)]   # lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4), lep_decode_g2_kernel<G> (mode 5)
 
 
-@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_GROUP(8)])
+@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_G2(8)])
 def test_golden_files_decode_to_the_reference_planes(kernel):
     for name in golden_leps():
         lf = load_lep(name)
@@ -33,7 +33,7 @@ def test_golden_files_decode_to_the_reference_planes(kernel):
             assert np.array_equal(img.planes[c], planes[c]), "%s component %d" % (name, c)
 
 
-@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_GROUP(4)])
+@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_G2(4)])
 def test_one_launch_with_more_segments_than_a_warp(kernel):
     """All golden files in one batch: > 32 segments, so several warps and a partly filled last one."""
     imgs, streams_all, want = [], [], []
@@ -101,12 +101,12 @@ def test_damaged_streams_end_the_same_way_in_both_kernels_and_the_oracle():
             rc, _ = oracle.decode_segment(g, want, y0, y1, last, bad[i])
             want_rc.append(rc)
         got = {}
-        for kernel in KERNELS + [emu.KERNEL_GROUP(4), emu.KERNEL_GROUP(16)]:
+        for kernel in KERNELS + [emu.KERNEL_GROUP(4), emu.KERNEL_G2(4), emu.KERNEL_G2(16)]:
             img = coef_image_from_lep(lf, [np.full_like(p, 11) for p in planes])
             st, nd = emu.decode_images(kernel, [img], [bad])
             got[kernel] = (st, nd, [p.copy() for p in img.planes])
         a = got[emu.KERNEL_THREAD]
-        for b in (got[emu.KERNEL_WARP], got[emu.KERNEL_LOCKSTEP], got[emu.KERNEL_GROUP(4)], got[emu.KERNEL_GROUP(16)]):
+        for b in (got[emu.KERNEL_WARP], got[emu.KERNEL_LOCKSTEP], got[emu.KERNEL_GROUP(4)], got[emu.KERNEL_G2(4)], got[emu.KERNEL_G2(16)]):
             assert a[0] == b[0] == want_rc and a[1] == b[1]
             for c in range(len(planes)):
                 assert np.array_equal(a[2][c], b[2][c])

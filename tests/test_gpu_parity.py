@@ -93,12 +93,14 @@ def test_golden_batch_decode_lockstep_kernel(monkeypatch, mode):
         c.close()
 
 
+@pytest.mark.parametrize("mode", ["4", "5"])
 @pytest.mark.parametrize("lanes", ["1", "4", "8", "32"])
-def test_golden_batch_decode_group_kernel(monkeypatch, lanes):
-    """lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4): G lanes per thread-segment, 32 / G segments per warp in lock step;
-    every group size must give the reference planes.  LEPB200_DEC_THREADS=32 forces several launches / a shared queue."""
+def test_golden_batch_decode_group_kernel(monkeypatch, lanes, mode):
+    """lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4) and lep_decode_g2_kernel<G> (mode 5, the stripped-down step loop):
+    G lanes per thread-segment, 32 / G segments per warp in lock step; every group size must give the reference planes.
+    LEPB200_DEC_THREADS=32 forces several launches / a shared queue."""
     from lepton_b200 import LeptonB200Codec
-    monkeypatch.setenv("LEPB200_DEC_MODE", "4")
+    monkeypatch.setenv("LEPB200_DEC_MODE", mode)
     monkeypatch.setenv("LEPB200_DEC_LANES", lanes)
     if lanes == "4":
         monkeypatch.setenv("LEPB200_DEC_THREADS", "32")
