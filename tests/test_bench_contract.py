@@ -17,11 +17,12 @@ def test_reference_arm_line():
                         "--cpu-sample", "8", "--distinct", "2"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-500:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["impl"] == "reference" and line["metric"] == "JPEG MB/s encode" and line["unit"] == "MB/s"
+    assert line["impl"] == "reference" and line["metric"] == "JPEG MB/s encode+decode" and line["unit"] == "MB/s"
     assert line["higher_is_better"] is True and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+    assert line["encode"]["value"] > line["value"] and line["decode"]["value"] > line["value"]      # value = bytes / (encode s + decode s)
 
 
 def test_product_arm_needs_a_gpu():
