@@ -26,7 +26,7 @@ def build(force=False, verbose=False):
         return OUT
     cu = [os.path.join(SRC, "lep_capi.cu")]
     cc = sorted(os.path.join(SRC, f) for f in os.listdir(SRC) if f.endswith(".cc") and f != "lepton_cli.cc")
-    defs = ["-D%s=%s" % (k, os.environ[k]) for k in ("LEPB200_ENC_MINBLOCKS", "LEPB200_DEC_MINBLOCKS", "LEPB200_HUFF_MINBLOCKS", "LEPB200_MODEL_LAYOUT", "LEPB200_STREAM_HINTS") if k in os.environ]
+    defs = ["-D%s=%s" % (k, os.environ[k]) for k in ("LEPB200_ENC_MINBLOCKS", "LEPB200_DEC_MINBLOCKS", "LEPB200_HUFF_MINBLOCKS", "LEPB200_MODEL_LAYOUT", "LEPB200_STREAM_HINTS", "LEPB200_G2_PREFETCH", "LEPB200_G2_PF_DIST") if k in os.environ]
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared"] + defs + [
            "-Xcompiler", "-fPIC,-O3,-pthread", "-o", OUT] + cu + cc + ["-lz", "-lpthread"]
     if verbose:

@@ -94,7 +94,10 @@ __device__ __forceinline__ void g2_prefetch(const uint16_t* p) { asm volatile("p
 #else
 __device__ __forceinline__ void g2_prefetch(const uint16_t*) {}
 #endif
-constexpr int G2_PF_DIST = 3;
+#ifndef LEPB200_G2_PF_DIST
+#define LEPB200_G2_PF_DIST 3
+#endif
+constexpr int G2_PF_DIST = LEPB200_G2_PF_DIST;
 
 enum : int { G2_EXP = 0, G2_SIGN = 1, G2_THR = 2, G2_RES = 3 };
 
