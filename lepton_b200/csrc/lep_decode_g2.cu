@@ -57,22 +57,35 @@ __device__ __forceinline__ void g2_init(G2Bool& r, const uint8_t* p, uint32_t le
     r.range = range << shift; r.value <<= shift; r.valid -= shift;
 }
 
-// VPXBoolReader::get (vpx_bool_reader.hh:45-57) = vpx_read + Branch::record_obs_and_update, given the branch word `w`
-// the caller loaded from model[addr]
-__device__ __forceinline__ uint32_t g2_get(G2Bool& r, uint16_t* model, const uint32_t* rcp, uint32_t addr, uint32_t w) {
+// VPXBoolReader::get (vpx_bool_reader.hh:45-57) = vpx_read + Branch::record_obs_and_update, in three pieces so that the
+// step loops can put the NEXT decision's model load between the bit and the bookkeeping:
+//   g2_bit         the decision itself: probability of the branch word, split, window top-up, compare   (on the serial chain)
+//   g2_update      range / window renormalisation                                                      (off the chain)
+//   g2_model_word  the branch word after the observation                                                (off the chain)
+__device__ __forceinline__ uint32_t g2_bit(G2Bool& r, const uint32_t* rcp, uint32_t w, uint32_t& split) {
     const uint32_t prob = branch_prob(w, rcp);
-    const uint32_t split = (r.range * prob + (256 - prob)) >> 8;
+    split = (r.range * prob + (256 - prob)) >> 8;
     if (r.valid < 32) g2_refill(r);
-    const uint32_t top = (uint32_t)(r.value >> 56);               // value >= split << 56  <=>  top byte >= split
-    const uint32_t bit = top >= split;
+    return (uint32_t)(r.value >> 56) >= split;                     // value >= split << 56  <=>  top byte >= split
+}
+__device__ __forceinline__ void g2_update(G2Bool& r, uint32_t split, uint32_t bit) {
     const uint32_t range = bit ? r.range - split : split;
     if (bit) r.value -= (unsigned long long)split << 56;
     const int shift = __clz(range) - 24;
     r.range = range << shift;
     r.value <<= shift;
     r.valid -= shift;
+}
+__device__ __forceinline__ uint32_t g2_model_word(uint32_t w, uint32_t bit) {
     const bool plain = (w & 0xffu) < 254u && (w >> 8) < 254u;       // no count about to saturate, not the special state
-    model[addr] = (uint16_t)(plain ? w + (bit ? 0x100u : 1u) : branch_update(w, bit));     // all lanes of the group store the same value
+    return (plain ? w + (bit ? 0x100u : 1u) : branch_update(w, bit)) & 0xffffu;
+}
+// one whole decision where nothing is pipelined (fixed-length count loops use the pieces directly)
+__device__ __forceinline__ uint32_t g2_get(G2Bool& r, uint16_t* model, const uint32_t* rcp, uint32_t addr, uint32_t w) {
+    uint32_t split;
+    const uint32_t bit = g2_bit(r, rcp, w, split);
+    g2_update(r, split, bit);
+    model[addr] = (uint16_t)g2_model_word(w, bit);                 // all lanes of the group store the same value
     return bit;
 }
 #ifdef LEPB200_EMU
@@ -332,7 +345,12 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
         bool bad = false;                 // a stream that announces more than 49 coefficients ends its segment (decoder.cc:182-184)
         if (alive && nz > 49) { bad = true; alive = false; }
 
-        // ---- (2b) the 7x7 coefficients in zig-zag order (== aligned order 0..48) until the announced count is used up
+        // ---- (2b) the 7x7 coefficients in zig-zag order (== aligned order 0..48) until the announced count is used up.
+        //      One decision per live group and round.  The transition to the next decision is straight-line code (no
+        //      divergence between groups that stand in different states), and the next decision's branch word is
+        //      requested as soon as its address is known -- before this decision's write-back and bookkeeping, which
+        //      then run in the shadow of the load.  (Consecutive decisions never use the same branch, except for the
+        //      saturated threshold index of the edge loop; the forwarding line covers every such case.)
         {
             int zz = 0, left_nz = nz, st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
@@ -342,60 +360,55 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                 const uint32_t eb = s_eb[ci][left_nz];
                 addr = eb + eoff[0];
 #pragma unroll
-                for (int k = 0; k <= G2_PF_DIST; ++k) g2_prefetch(model + eb + eoff[k]);        // a block has >= 4 positions to go when nz > 0 ... positions 0..3 always exist
+                for (int k = 1; k <= G2_PF_DIST; ++k) g2_prefetch(model + eb + eoff[k]);        // positions 0..3 always exist
             }
             const uint32_t sign_addr = m_sign(ci, 0, 0);
+            uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
-                const uint32_t mw = busy ? model[addr] : 0u;
-                G2_EMU_BARRIER();
                 if (busy) {
-                    const uint32_t bit = g2_get(br, model, s_rcp, addr, mw);
+                    uint32_t split;
+                    const uint32_t bit = g2_bit(br, s_rcp, mw, split);
+                    // ---- transition
+                    const int isE = st == G2_EXP, isS = st == G2_SIGN, isR = st == G2_RES;
+                    const int cont = isE & (int)bit & (int)(len < 10);               // exponent goes on
+                    const int len1 = len + (isE & (int)bit);
+                    const int ev0 = isE & (cont ^ 1) & (int)(len1 == 0);              // zero coefficient
+                    const int toS = isE & (cont ^ 1) & (int)(len1 != 0);
+                    const int ris = len - 2;                                          // sign state: first residual bit
+                    const int evS = isS & (int)(ris < 0), toR = isS & (int)(ris >= 0);
+                    const int evR = isR & (int)(ri == 0), contR = isR & (int)(ri != 0);
+                    const int evN = evS | evR, ev = ev0 | evN;                        // a (non-zero) coefficient is complete
+                    const int nval = isS ? (1 << ((len - 1) & 31)) : (isR ? (val | ((int)bit << (ri & 31))) : val);
+                    const bool nneg = isS ? !bit : neg;
+                    const int coord = s_a2r[zz];
+                    const uint32_t rbase = m_resn(ci, coord, s_nzbin[left_nz]);
+                    const int nleft = left_nz - evN, nzz = zz + ev;
+                    const int done = ev & (int)((nleft == 0) | (nzz == 49));
+                    const uint32_t eb = s_eb[ci][nleft];
+                    const uint32_t naddr = cont ? addr + 1 : toS ? sign_addr : toR ? rbase + (uint32_t)ris : contR ? addr - 1 : eb + eoff[min(nzz, 48)];
+                    const bool nbusy = !done;
+                    // ---- the next decision's branch word
+                    uint32_t mwn = nbusy ? model[naddr] : 0u;
+                    // ---- in its shadow: write-back, window, the decoded value, requests for later positions
+                    const uint32_t neww = g2_model_word(mw, bit);
+                    model[addr] = (uint16_t)neww;                  // all lanes of the group store the same value
+                    if (naddr == addr) mwn = neww;
+                    g2_update(br, split, bit);
                     ++nd;
-                    bool ev = false;
-                    int v = 0;
-                    if (st == G2_EXP) {
-                        if (bit && len < 10) {
-                            if (len == 0) {       // non-zero: residual bits may follow, and the positions after it see one coefficient less
-                                g2_prefetch(model + m_resn(ci, s_a2r[zz], s_nzbin[left_nz]));
-                                const uint32_t eb = s_eb[ci][left_nz - 1];
-                                if (eb != s_eb[ci][left_nz] && left_nz > 1) {
+                    if (evN && sub == 0) rcur[coord] = (int16_t)(nneg ? -nval : nval);
+                    if (isE & (int)bit & (int)(len == 0)) {       // non-zero: residual bits may follow, and the positions after it see one coefficient less
+                        g2_prefetch(model + rbase);
+                        const uint32_t eb1 = s_eb[ci][left_nz - 1];
+                        if (eb1 != s_eb[ci][left_nz] && left_nz > 1) {
 #pragma unroll
-                                    for (int k = 1; k <= G2_PF_DIST; ++k) if (zz + k < 49) g2_prefetch(model + eb + eoff[zz + k]);
-                                }
-                            }
-                            ++len; ++addr;
-                        } else {
-                            len += (int)bit;
-                            if (len == 0) ev = true;
-                            else { st = G2_SIGN; addr = sign_addr; }
-                        }
-                    } else if (st == G2_SIGN) {
-                        neg = !bit;
-                        val = 1 << (len - 1);
-                        ri = len - 2;
-                        if (ri < 0) { ev = true; v = neg ? -val : val; }
-                        else {
-                            st = G2_RES;
-                            addr = m_resn(ci, s_a2r[zz], s_nzbin[left_nz]) + (uint32_t)ri;
-                        }
-                    } else {
-                        val |= (int)bit << ri;
-                        if (--ri < 0) { ev = true; v = neg ? -val : val; }
-                        else --addr;
-                    }
-                    if (ev) {
-                        if (v != 0) {
-                            --left_nz;
-                            if (sub == 0) rcur[s_a2r[zz]] = (int16_t)v;
-                        }
-                        ++zz;
-                        if (left_nz == 0 || zz == 49) busy = false;
-                        else {
-                            const uint32_t eb = s_eb[ci][left_nz];
-                            addr = eb + eoff[zz]; st = G2_EXP; len = 0;
-                            if (zz + G2_PF_DIST < 49) g2_prefetch(model + eb + eoff[zz + G2_PF_DIST]);
+                            for (int k = 1; k <= G2_PF_DIST; ++k) if (zz + k < 49) g2_prefetch(model + eb1 + eoff[zz + k]);
                         }
                     }
+                    if (ev && nzz + G2_PF_DIST < 49) g2_prefetch(model + eb + eoff[nzz + G2_PF_DIST]);
+                    st = toS ? G2_SIGN : toR ? G2_RES : ev ? G2_EXP : st;
+                    len = ev ? 0 : len1;
+                    ri = isS ? ris : ri - isR;
+                    val = nval; neg = nneg; left_nz = nleft; zz = nzz; addr = naddr; busy = nbusy; mw = mwn;
                 }
             }
         }
@@ -451,84 +464,68 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                 ne = (int)prefix;
                 if (alive) nd += 3;
             }
-            int ln = 0, st = G2_EXP, len = 0, ri = 0, val = 0, min_thr = 0;
+            int ln = 0, st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
             uint32_t addr = 0, e = 0, so = 1, thr_base = 0;
             const uint32_t expx_base = M_EXPX + (uint32_t)((ci * 8) * 15 * 12 * 16) + (uint32_t)(vert * 7 * 12 * 16);
             const uint32_t sign_base = M_SIGN + (uint32_t)(ci * 48);
+            const int cstep = vert ? 8 : 1;                       // raster distance between the coefficients of this edge
             bool busy = alive && ne > 0;
             if (busy) {
                 e = einfo[vert * 7];
                 addr = expx_base + (uint32_t)(ne * (15 * 12 * 16)) + ((e & 15u) << 4);
-                g2_prefetch(model + addr);
                 g2_prefetch(model + expx_base + (uint32_t)(ne * (15 * 12 * 16)) + (uint32_t)(12 * 16) + ((einfo[vert * 7 + 1] & 15u) << 4));
             }
+            uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
-                const uint32_t mw = busy ? model[addr] : 0u;
-                G2_EMU_BARRIER();
                 if (busy) {
-                    const uint32_t bit = g2_get(br, model, s_rcp, addr, mw);
+                    uint32_t split;
+                    const uint32_t bit = g2_bit(br, s_rcp, mw, split);
+                    // ---- transition (straight-line; see the 7x7 loop)
+                    const int isE = st == G2_EXP, isS = st == G2_SIGN, isT = st == G2_THR, isR = st == G2_RES;
+                    const int cont = isE & (int)bit & (int)(len < 10);
+                    const int len1 = len + (isE & (int)bit);
+                    const int ev0 = isE & (cont ^ 1) & (int)(len1 == 0);
+                    const int toS = isE & (cont ^ 1) & (int)(len1 != 0);
+                    const int mt = (int)((e >> 6) & 7u);                              // min_threshold of this position
+                    const int ris = len - 2;
+                    const int evS = isS & (int)(ris < 0);
+                    const int toT = isS & (int)(ris >= 0) & (int)(ris >= mt), toRs = isS & (int)(ris >= 0) & (int)(ris < mt);
+                    const int rit = ri - 1;                                           // threshold / residual states: next bit
+                    const int evT = isT & (int)(ri == 0), contT = isT & (int)(ri != 0) & (int)(rit >= mt), toRt = isT & (int)(ri != 0) & (int)(rit < mt);
+                    const int evR = isR & (int)(ri == 0), contR = isR & (int)(ri != 0);
+                    const int evN = evS | evT | evR, ev = ev0 | evN;
+                    const int nval = isS ? (1 << ((len - 1) & 31)) : ((isT | isR) ? (val | ((int)bit << (ri & 31))) : val);
+                    const bool nneg = isS ? !bit : neg;
+                    const uint32_t nso = isT ? min((so << 1) | bit, 127u) : 1u;
+                    const uint32_t nthr = isS ? m_thr(ci, (int)((e >> 9) & 255u), min(len - mt, 7)) : thr_base;
+                    const int coord = (ln + 1) * cstep;
+                    const uint32_t rbase = m_resn(ci, coord, ne);
+                    const uint32_t sa = sign_base + ((e >> 4) & 3u) * 12u + (e & 15u);
+                    const int nne = ne - evN, nln = ln + ev;
+                    const int done = ev & (int)((nne == 0) | (nln == 7));
+                    const uint32_t en = einfo[vert * 7 + min(nln, 6)];
+                    const uint32_t nexta = expx_base + (uint32_t)(nne * (15 * 12 * 16)) + (uint32_t)(nln * (12 * 16)) + ((en & 15u) << 4);
+                    const uint32_t naddr = cont ? addr + 1 : toS ? sa : toT ? nthr + 1 : toRs ? rbase + (uint32_t)ris : contT ? nthr + nso
+                                         : toRt ? rbase + (uint32_t)rit : contR ? addr - 1 : nexta;
+                    const bool nbusy = !done;
+                    // ---- the next decision's branch word, then everything that is off the chain
+                    uint32_t mwn = nbusy ? model[naddr] : 0u;
+                    const uint32_t neww = g2_model_word(mw, bit);
+                    model[addr] = (uint16_t)neww;
+                    if (naddr == addr) mwn = neww;                 // saturated threshold index: the same branch twice in a row
+                    g2_update(br, split, bit);
                     ++nd;
-                    bool ev = false;
-                    int v = 0;
-                    if (st == G2_EXP) {
-                        if (bit && len < 10) {
-                            if (len == 0 && ne > 1 && ln < 6) {       // non-zero: the next position sees one coefficient less
-                                g2_prefetch(model + expx_base + (uint32_t)((ne - 1) * (15 * 12 * 16)) + (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + ln + 1] & 15u) << 4));
-                            }
-                            ++len; ++addr;
-                        } else {
-                            len += (int)bit;
-                            if (len == 0) ev = true;
-                            else {
-                                st = G2_SIGN; addr = sign_base + ((e >> 4) & 3u) * 12u + (e & 15u);
-                                if (len >= 2) {       // value bits follow: through the threshold table first when the magnitude allows
-                                    const int mt = (int)((e >> 6) & 7u);
-                                    g2_prefetch(model + (len - 2 >= mt ? m_thr(ci, (int)((e >> 9) & 255u), min(len - mt, 7)) : m_resn(ci, vert ? 8 * (ln + 1) : ln + 1, ne)));
-                                }
-                            }
-                        }
-                    } else if (st == G2_SIGN) {
-                        neg = !bit;
-                        val = 1 << (len - 1);
-                        ri = len - 2;
-                        if (ri < 0) { ev = true; v = neg ? -val : val; }
-                        else {
-                            min_thr = (int)((e >> 6) & 7u);
-                            if (ri >= min_thr) {
-                                st = G2_THR; so = 1;
-                                thr_base = m_thr(ci, (int)((e >> 9) & 255u), min(len - min_thr, 7));
-                                addr = thr_base + 1;
-                            } else {
-                                st = G2_RES;
-                                addr = m_resn(ci, vert ? 8 * (ln + 1) : ln + 1, ne) + (uint32_t)ri;
-                            }
-                        }
-                    } else if (st == G2_THR) {
-                        val |= (int)bit << ri;
-                        so = min((so << 1) | bit, 127u);
-                        if (--ri < 0) { ev = true; v = neg ? -val : val; }
-                        else if (ri >= min_thr) addr = thr_base + so;
-                        else { st = G2_RES; addr = m_resn(ci, vert ? 8 * (ln + 1) : ln + 1, ne) + (uint32_t)ri; }
-                    } else {
-                        val |= (int)bit << ri;
-                        if (--ri < 0) { ev = true; v = neg ? -val : val; }
-                        else --addr;
-                    }
-                    if (ev) {
-                        if (v != 0) {
-                            if (sub == 0) rcur[vert ? 8 * (ln + 1) : ln + 1] = (int16_t)v;
-                            --ne;
-                        }
-                        ++ln;
-                        if (ne == 0 || ln == 7) busy = false;
-                        else {
-                            e = einfo[vert * 7 + ln];
-                            addr = expx_base + (uint32_t)(ne * (15 * 12 * 16)) + (uint32_t)(ln * (12 * 16)) + ((e & 15u) << 4);
-                            st = G2_EXP; len = 0;
-                            if (ln < 6) g2_prefetch(model + expx_base + (uint32_t)(ne * (15 * 12 * 16)) + (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + ln + 1] & 15u) << 4));
-                        }
-                    }
+                    if (evN && sub == 0) rcur[coord] = (int16_t)(nneg ? -nval : nval);
+                    if (isE & (int)bit & (int)(len == 0) & (int)(ne > 1) & (int)(ln < 6))      // non-zero: the next position sees one coefficient less
+                        g2_prefetch(model + expx_base + (uint32_t)((ne - 1) * (15 * 12 * 16)) + (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + ln + 1] & 15u) << 4));
+                    if (toS && len1 >= 2) g2_prefetch(model + (len1 - 2 >= mt ? m_thr(ci, (int)((e >> 9) & 255u), min(len1 - mt, 7)) : rbase));
+                    if (ev && !done && nln < 6) g2_prefetch(model + expx_base + (uint32_t)(nne * (15 * 12 * 16)) + (uint32_t)((nln + 1) * (12 * 16)) + ((einfo[vert * 7 + nln + 1] & 15u) << 4));
+                    st = toS ? G2_SIGN : toT ? G2_THR : (toRs | toRt) ? G2_RES : ev ? G2_EXP : st;
+                    len = ev ? 0 : len1;
+                    ri = isS ? ris : ri - (isT | isR);
+                    val = nval; neg = nneg; so = nso; thr_base = nthr; ne = nne; ln = nln; e = ev ? en : e;
+                    addr = naddr; busy = nbusy; mw = mwn;
                 }
             }
         }
@@ -607,37 +604,42 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
             }
         }
 
-        // ---- (6) the DC coefficient: exponent / sign / residual bits (decoder.cc:286-304)
+        // ---- (6) the DC coefficient: exponent / sign / residual bits (decoder.cc:286-304), pipelined like the loops above
         int dcv = 0;
         {
             int st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
             uint32_t addr = dc_exp;
             bool busy = alive;
+            uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
-                const uint32_t mw = busy ? model[addr] : 0u;
-                G2_EMU_BARRIER();
                 if (busy) {
-                    const uint32_t bit = g2_get(br, model, s_rcp, addr, mw);
+                    uint32_t split;
+                    const uint32_t bit = g2_bit(br, s_rcp, mw, split);
+                    const int isE = st == G2_EXP, isS = st == G2_SIGN, isR = st == G2_RES;
+                    const int cont = isE & (int)bit & (int)(len < 10);
+                    const int len1 = len + (isE & (int)bit);
+                    const int ev0 = isE & (cont ^ 1) & (int)(len1 == 0);
+                    const int toS = isE & (cont ^ 1) & (int)(len1 != 0);
+                    const int ris = len - 2;
+                    const int evS = isS & (int)(ris < 0), toR = isS & (int)(ris >= 0);
+                    const int evR = isR & (int)(ri == 0), contR = isR & (int)(ri != 0);
+                    const int evN = evS | evR, ev = ev0 | evN;
+                    const int nval = isS ? (1 << ((len - 1) & 31)) : (isR ? (val | ((int)bit << (ri & 31))) : val);
+                    const bool nneg = isS ? !bit : neg;
+                    const uint32_t naddr = cont ? addr + 1 : toS ? dc_sign : toR ? dc_res + (uint32_t)ris : contR ? addr - 1 : addr;
+                    const bool nbusy = !ev;
+                    uint32_t mwn = nbusy ? model[naddr] : 0u;
+                    const uint32_t neww = g2_model_word(mw, bit);
+                    model[addr] = (uint16_t)neww;
+                    if (naddr == addr) mwn = neww;
+                    g2_update(br, split, bit);
                     ++nd;
-                    if (st == G2_EXP) {
-                        if (bit && len < 10) { ++len; ++addr; }
-                        else {
-                            len += (int)bit;
-                            if (len == 0) busy = false;
-                            else { st = G2_SIGN; addr = dc_sign; }
-                        }
-                    } else if (st == G2_SIGN) {
-                        neg = !bit;
-                        val = 1 << (len - 1);
-                        ri = len - 2;
-                        if (ri < 0) { dcv = neg ? -val : val; busy = false; }
-                        else { st = G2_RES; addr = dc_res + (uint32_t)ri; }
-                    } else {
-                        val |= (int)bit << ri;
-                        if (--ri < 0) { dcv = neg ? -val : val; busy = false; }
-                        else --addr;
-                    }
+                    if (evN) dcv = nneg ? -nval : nval;
+                    st = toS ? G2_SIGN : toR ? G2_RES : st;
+                    len = len1;
+                    ri = isS ? ris : ri - isR;
+                    val = nval; neg = nneg; addr = naddr; busy = nbusy; mw = mwn;
                 }
             }
         }
