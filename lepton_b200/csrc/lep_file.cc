@@ -24,10 +24,12 @@ using namespace lephost;
 
 struct lepb200_codec {
     lepb200_ctx* ctx = nullptr;     // == ctx2[0]
-    lepb200_ctx* ctx2[3] = {nullptr, nullptr, nullptr};   // rotating contexts: chunk k on ctx2[k % 3]
+    static constexpr int NCTX = 4;
+    lepb200_ctx* ctx2[NCTX] = {nullptr, nullptr, nullptr, nullptr};   // one context (stream, device arenas) per chunk in flight
+    int concurrent = 4;             // chunks of one call that run at the same time (LEPB200_CHUNKS_IN_FLIGHT), 1..NCTX
     int nthreads = 1;
     int chunk_images = 4096;
-    size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk (device memory budget: two contexts in flight)
+    size_t plane_cap = size_t(28) << 30;   // coefficient-plane bytes per chunk when one chunk runs at a time; divided among the chunks in flight
     bool gpu_huffman = true;       // Huffman-decode eligible chunks on the GPU
     bool even_split = false;       // -evensplit (jpgcoder.cc:1063-1064)
     unsigned max_encode_threads = 8, min_encode_threads = 1;   // -maxencodethreads= / -minencodethreads= (jpgcoder.cc:1080-1089)
@@ -97,16 +99,16 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
     lepb200_ctx* ctx = nullptr;
     int r = lepb200_create(&ctx, device);
     if (r) return r;
-    lepb200_ctx *ctxb = nullptr, *ctxc = nullptr;
-    r = lepb200_create(&ctxb, device);
-    if (r) { lepb200_destroy(ctx); return r; }
-    r = lepb200_create(&ctxc, device);
-    if (r) { lepb200_destroy(ctx); lepb200_destroy(ctxb); return r; }
     lepb200_codec* c = new lepb200_codec();
     c->ctx = ctx;
-    c->ctx2[0] = ctx; c->ctx2[1] = ctxb; c->ctx2[2] = ctxc;
+    c->ctx2[0] = ctx;
+    for (int s = 1; s < lepb200_codec::NCTX; ++s) {
+        r = lepb200_create(&c->ctx2[s], device);
+        if (r) { for (int q = 0; q < s; ++q) lepb200_destroy(c->ctx2[q]); delete c; return r; }
+    }
     c->nthreads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
-    for (int s = 0; s < 3; ++s) lepb200_set_host_threads(c->ctx2[s], c->nthreads);
+    for (int s = 0; s < lepb200_codec::NCTX; ++s) lepb200_set_host_threads(c->ctx2[s], c->nthreads);
+    if (const char* e = getenv("LEPB200_CHUNKS_IN_FLIGHT")) c->concurrent = std::min((int)lepb200_codec::NCTX, std::max(1, atoi(e)));
     *out = c;
     return LEPB200_OK;
 }
@@ -114,7 +116,7 @@ int lepb200_codec_create(lepb200_codec** out, int device, int host_threads) {
 void lepb200_codec_destroy(lepb200_codec* c) {
     if (!c) return;
     for (int s = 0; s < 4; ++s) if (c->arena[s]) lepb200_pinned_free(c->arena[s]);
-    for (int s = 0; s < 3; ++s) lepb200_destroy(c->ctx2[s]);
+    for (int s = 0; s < lepb200_codec::NCTX; ++s) lepb200_destroy(c->ctx2[s]);
     delete c;
 }
 
@@ -125,7 +127,9 @@ const char* lepb200_codec_last_error(const lepb200_codec* c) {
 
 lepb200_ctx* lepb200_codec_ctx(lepb200_codec* c) { return c ? c->ctx : nullptr; }
 uint64_t lepb200_codec_kernel_launches(const lepb200_codec* c) {
-    return c ? lepb200_kernel_launches(c->ctx2[0]) + lepb200_kernel_launches(c->ctx2[1]) + lepb200_kernel_launches(c->ctx2[2]) : 0;
+    uint64_t n = 0;
+    for (int s = 0; c && s < lepb200_codec::NCTX; ++s) n += lepb200_kernel_launches(c->ctx2[s]);
+    return n;
 }
 void lepb200_codec_set_chunk_images(lepb200_codec* c, int n) { if (c && n > 0) c->chunk_images = n; }
 void lepb200_codec_set_gpu_huffman(lepb200_codec* c, int on) { if (c) c->gpu_huffman = on != 0; }
@@ -191,17 +195,30 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     // ---- chunk boundaries
     std::vector<size_t> need(n);
     parallel_for(n, c->nthreads, [&](int i) { need[i] = peek_plane_bytes(jpegs[i].data, jpegs[i].len); });
+    // Chunks: up to `concurrent` of them run at the same time, each on its own context (stream + device arenas), so
+    // that the latency-bound kernels of one chunk (Huffman decode, range coder) and its host stages lie under the
+    // issue-bound kernel A of another.  A large call is cut into that many chunks of about equal plane bytes; the
+    // device memory budget `plane_cap` is shared by the chunks in flight.  Small calls stay in one piece.
     std::vector<std::pair<int, int>> ranges;
+    int W = 1;
     {
+        size_t total_need = 0;
+        for (int i = 0; i < n; ++i) total_need += need[i];
+        W = (n >= 64 && total_need >= (size_t(1) << 30)) ? std::max(1, c->concurrent) : 1;
+        const size_t cap = c->plane_cap / (size_t)W;
+        const size_t target = std::min(cap, std::max<size_t>(total_need / (size_t)W + 1, size_t(256) << 20));
         const int chunk = std::max(1, c->chunk_images);
         int b = 0;
         size_t acc = 0;
         for (int i = 0; i < n; ++i) {
-            if (i > b && (i - b >= chunk || acc + need[i] > c->plane_cap)) { ranges.emplace_back(b, i); b = i; acc = 0; }
+            if (i > b && (i - b >= chunk || acc + need[i] > target)) { ranges.emplace_back(b, i); b = i; acc = 0; }
             acc += need[i];
         }
         ranges.emplace_back(b, n);
+        if (c->chunk_images < 4096 && (int)ranges.size() > 1) W = std::max(W, std::min((int)ranges.size(), c->concurrent));   // caller-forced small chunks
+        W = std::max(1, std::min(W, (int)ranges.size()));
     }
+    const int pth = std::max(1, c->nthreads / W);          // host threads of one chunk's stages (W chunks share the cores)
     const int nchunks = (int)ranges.size();
     c->outputs.resize(n);
     std::vector<int> status(n, 0);
@@ -213,7 +230,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         ChunkState& s = cs[k];
         s.begin = ranges[k].first; s.end = ranges[k].second;
         const int m = s.end - s.begin;
-        lepb200_ctx* ctx = c->ctx2[k % 2];
+        lepb200_ctx* ctx = c->ctx2[k % W];
         s.js.resize(m); s.planes.resize(m); s.splits.resize(m); s.host_decoded.assign(m, 0);
         // staging layout for the de-stuffed scans (a scan is never longer than its file) and arena layout for planes
         // of files that turn out to need the host decoder
@@ -224,7 +241,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         }
         uint8_t* stage = c->gpu_huffman ? lepb200_huffman_stage_reserve(ctx, soff[m]) : nullptr;
         if (c->gpu_huffman && !stage) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
-        const int slot = k % 2;
+        const int slot = k % W;
         uint8_t* arena = nullptr;
         if (!c->gpu_huffman) {                       // every file takes the host decoder: one arena for the chunk
             if (!reserve_arena(c, slot, poff[m] + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
@@ -236,14 +253,14 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         // staged bytes are contiguous, so one asynchronous H2D per group pushes them while other groups are still being
         // parsed (a copy per file would spend more time in the CUDA runtime than in the parser)
         const int group = 32, ngroups = (m + group - 1) / group;
-        parallel_for(ngroups, c->nthreads, [&](int gi) {
+        parallel_for(ngroups, pth, [&](int gi) {
             const int g0 = gi * group, g1 = std::min(m, g0 + group);
             for (int i = g0; i < g1; ++i) {
                 s.js[i].reset(new Jpeg());
                 Jpeg& j = *s.js[i];
                 const lepb200_buffer& in = jpegs[s.begin + i];
                 if (stage) { j.huff.attach(stage + soff[i], soff[i + 1] - soff[i] - 16); memset(stage + soff[i], 0, 16); }
-                if (need[s.begin + i] > c->plane_cap) { j.status = NOT_HANDLED; j.error = "image larger than the per-chunk device memory budget"; continue; }
+                if (need[s.begin + i] > c->plane_cap / (size_t)W) { j.status = NOT_HANDLED; j.error = "image larger than the per-chunk device memory budget"; continue; }
                 const bool parsed = parse_jpeg(in.data, in.len, j);
                 if (stage) memset(stage + soff[i] + j.huff.size(), 0, 16);          // the decoder reads whole words past the end
                 if (parsed && stage && gpu_scan_setup(j, setups[i])) eligible[i] = 1;
@@ -262,7 +279,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             for (int i = 0; i < m; ++i) poff[i] = off[i];
         }
         // pass 2: host Huffman decode where needed
-        parallel_for(m, c->nthreads, [&](int i) {
+        parallel_for(m, pth, [&](int i) {
             Jpeg& j = *s.js[i];
             for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
             if (j.status || eligible[i]) return;
@@ -317,7 +334,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     auto gpu = [&](int k) {
         double t0 = now_s();
         ChunkState& s = cs[k];
-        lepb200_ctx* ctx = c->ctx2[k % 2];
+        lepb200_ctx* ctx = c->ctx2[k % W];
         const int nb = (int)s.idx.size();
         if (s.gpu_rc == 0 && nb > 0) {
             if (s.any_gpu_huffman) {
@@ -330,7 +347,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             s.imgs.resize(nb);
             if (s.gpu_rc == 0) {
                 // thread-segment selection from the Huffman states at the MCU-row starts (write_ujpg, jpgcoder.cc:3860-3934)
-                parallel_for(nb, c->nthreads, [&](int q) {
+                parallel_for(nb, pth, [&](int q) {
                     const int i = s.idx[q];
                     Jpeg& j = *s.js[i];
                     const lepb200_jpeg_scan& sc = s.scans[q];
@@ -391,7 +408,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         double t0 = now_s();
         ChunkState& s = cs[k];
         if (s.gpu_rc == 0) {
-            parallel_for((int)s.idx.size(), c->nthreads, [&](int q) {
+            parallel_for((int)s.idx.size(), pth, [&](int q) {
                 const int i = s.begin + s.idx[q];
                 if (status[i]) return;
                 std::vector<std::pair<const uint8_t*, size_t>> ss;
@@ -404,26 +421,27 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 if (!write_lep(*s.js[s.idx[q]], s.splits[s.idx[q]], ss, c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
             });
         }
-        parallel_for((int)s.js.size(), c->nthreads, [&](int i) { s.js[i].reset(); });     // release per-chunk host state early
+        parallel_for((int)s.js.size(), pth, [&](int i) { s.js[i].reset(); });     // release per-chunk host state early
         s.js.clear(); s.planes.clear(); s.splits.clear();
         mark("back", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_back += now_s() - t0;
     };
 
-    // 3-stage lock-step pipeline, chunk k on context k % 2
-    for (int step = 0; step < nchunks + 2; ++step) {
-        std::thread th[3];
-        auto in = [&](int k) { return k >= 0 && k < nchunks; };
-        if (in(step)) th[0] = std::thread(front, step);
-        if (in(step - 1)) th[1] = std::thread(gpu, step - 1);
-        if (in(step - 2)) th[2] = std::thread(back, step - 2);
-        for (auto& t : th) if (t.joinable()) t.join();
+    // W workers; worker w takes the chunks w, w + W, ... through front -> gpu -> back on context w.  Chunks of different
+    // workers overlap freely: host stages with device stages, and on the device the kernels of different streams
+    {
+        std::vector<std::thread> workers;
+        for (int w = 0; w < W; ++w)
+            workers.emplace_back([&, w]() {
+                for (int k = w; k < nchunks; k += W) { front(k); gpu(k); back(k); }
+            });
+        for (auto& t : workers) t.join();
     }
     int ret = LEPB200_OK;
     for (int k = 0; k < nchunks; ++k)
         if (cs[k].gpu_rc) {               // the chunk's device work failed (e.g. out of memory): none of its files has an output
-            ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 2]);
+            ret = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % W]);
             for (int i = ranges[k].first; i < ranges[k].second; ++i) if (!status[i]) status[i] = 33;       // ExitCode::OS_ERROR
         }
     // -verify / -roundtrip (the reference CLI's default, jpgcoder.cc:1095-1110, validation.cc): every .lep is decoded
@@ -472,26 +490,34 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         all[i].reset(new LepFile());
         if (read_lep(leps[i].data, leps[i].len, *all[i])) {
             for (int q = 0; q < all[i]->j.ncmp; ++q) pbytes[i] += (plane_bytes(all[i]->j, q) + 255) & ~size_t(255);
-            if (pbytes[i] > c->plane_cap) { all[i]->status = NOT_HANDLED; all[i]->error = "image larger than the per-chunk device memory budget"; pbytes[i] = 0; }
+            if (pbytes[i] > c->plane_cap / (size_t)std::max(1, c->concurrent)) { all[i]->status = NOT_HANDLED; all[i]->error = "image larger than the per-chunk device memory budget"; pbytes[i] = 0; }
         }
     });
     c->t_front += now_s() - t_parse;
     // chunks of up to `plane_cap` bytes of coefficient planes (device memory: three contexts in flight).  The planes stay on the device
     // for every file whose scan the GPU can re-encode; only the others need a pinned host arena (128 B per block over PCIe)
     std::vector<std::pair<int, int>> ranges;
+    int W = 1;
     {
-        // one launch of the decode kernel should cover as many segments as possible (each chunk ends in a partly filled wave);
-        // without the device re-encoder every plane needs pinned host memory too, so those chunks stay small
-        const size_t cap = c->gpu_huffman ? c->plane_cap : (size_t(6) << 30);
+        // as in lepb200_compress_jpegs: up to `concurrent` chunks of about equal plane bytes run at the same time, each on
+        // its own context; without the device re-encoder every plane needs pinned host memory too, so those chunks stay small
+        size_t total = 0;
+        for (int i = 0; i < n; ++i) total += pbytes[i];
+        W = (n >= 64 && total >= (size_t(1) << 30)) ? std::max(1, c->concurrent) : 1;
+        const size_t cap = (c->gpu_huffman ? c->plane_cap : (size_t(6) << 30)) / (size_t)W;
+        const size_t target = std::min(cap, std::max<size_t>(total / (size_t)W + 1, size_t(256) << 20));
         const int chunk_max = std::max(1, c->chunk_images);
         int b0 = 0;
         size_t acc = 0;
         for (int i = 0; i < n; ++i) {
-            if (i > b0 && (i - b0 >= chunk_max || acc + pbytes[i] > cap)) { ranges.emplace_back(b0, i); b0 = i; acc = 0; }
+            if (i > b0 && (i - b0 >= chunk_max || acc + pbytes[i] > target)) { ranges.emplace_back(b0, i); b0 = i; acc = 0; }
             acc += pbytes[i];
         }
         ranges.emplace_back(b0, n);
+        if (c->chunk_images < 4096 && (int)ranges.size() > 1) W = std::max(W, std::min((int)ranges.size(), c->concurrent));
+        W = std::max(1, std::min(W, (int)ranges.size()));
     }
+    const int pth = std::max(1, c->nthreads / W);
     const int nchunks = (int)ranges.size();
     c->outputs.assign(n, std::vector<uint8_t>());
     std::vector<int> status(n, 0);
@@ -528,7 +554,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         s.henc.assign(nb, lepb200_henc_image());
         s.gsetup.assign(nb, GpuRecodeSetup());
         s.fallback.resize(nb);
-        parallel_for(nb, c->nthreads, [&](int q) {
+        parallel_for(nb, pth, [&](int q) {
             const LepFile& lf = *s.lf[s.idx[q]];
             lepb200_henc_image& he = s.henc[q];
             memset(&he, 0, sizeof(he));
@@ -562,8 +588,8 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         for (int q = 0; q < nb; ++q) if (s.henc[q].scan_bytes == 0) { base[q] = total; total += pbytes[s.begin + s.idx[q]]; }
         uint8_t* arena = nullptr;
         if (total) {
-            if (!reserve_arena(c, k % 4, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
-            arena = static_cast<uint8_t*>(c->arena[k % 4]);
+            if (!reserve_arena(c, k % W, total + 256)) { s.gpu_rc = LEPB200_ERR_NOMEM; return; }
+            arena = static_cast<uint8_t*>(c->arena[k % W]);
         }
         int nseg_total = 0;
         s.imgs.resize(nb);
@@ -596,7 +622,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     auto gpu = [&](int k) {               // H2D of the streams + decode kernel
         double t0 = now_s();
         DChunk& s = cs[k];
-        lepb200_ctx* ctx = c->ctx2[k % 3];
+        lepb200_ctx* ctx = c->ctx2[k % W];
         if (s.gpu_rc == 0 && !s.imgs.empty()) {
             s.gpu_rc = lepb200_decode_upload(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data());
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_launch(ctx);
@@ -610,7 +636,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         double t0 = now_s();
         DChunk& s = cs[k];
         if (s.gpu_rc == 0 && !s.imgs.empty()) {
-            lepb200_ctx* ctx = c->ctx2[k % 3];
+            lepb200_ctx* ctx = c->ctx2[k % W];
             s.gpu_rc = lepb200_huffman_encode_fetch(ctx, s.henc.data(), (int)s.henc.size());
             // planes come back only for the files the host has to re-encode
             std::vector<lepb200_image> need(s.imgs);
@@ -636,7 +662,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         double t0 = now_s();
         DChunk& s = cs[k];
         if (s.gpu_rc == 0) {
-            parallel_for((int)s.imgs.size(), c->nthreads, [&](int q) {
+            parallel_for((int)s.imgs.size(), pth, [&](int q) {
                 const int li = s.idx[q], i = s.begin + li;
                 for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t)
                     if (s.seg_status[t]) { status[i] = s.seg_status[t]; return; }
@@ -654,20 +680,19 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         std::lock_guard<std::mutex> g(tmu);
         c->t_back += now_s() - t0;
     };
-    // 4-stage lock-step pipeline: chunk k on context k % 3 (kernel, D2H) and pinned plane arena k % 4 (front .. back)
-    for (int step = 0; step < nchunks + 3; ++step) {
-        std::thread th[4];
-        auto in = [&](int k) { return k >= 0 && k < nchunks; };
-        if (in(step)) th[0] = std::thread(front, step);
-        if (in(step - 1)) th[1] = std::thread(gpu, step - 1);
-        if (in(step - 2)) th[2] = std::thread(fetch, step - 2);
-        if (in(step - 3)) th[3] = std::thread(back, step - 3);
-        for (auto& t : th) if (t.joinable()) t.join();
+    // W workers; worker w takes the chunks w, w + W, ... through front -> gpu -> fetch -> back on context / arena w
+    {
+        std::vector<std::thread> workers;
+        for (int w = 0; w < W; ++w)
+            workers.emplace_back([&, w]() {
+                for (int k = w; k < nchunks; k += W) { front(k); gpu(k); fetch(k); back(k); }
+            });
+        for (auto& t : workers) t.join();
     }
     int rc = LEPB200_OK;
     for (int k = 0; k < nchunks; ++k)
         if (cs[k].gpu_rc) {
-            rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % 3]);
+            rc = cs[k].gpu_rc; c->err = lepb200_last_error(c->ctx2[k % W]);
             for (int i = ranges[k].first; i < ranges[k].second; ++i) if (!status[i]) status[i] = 33;       // ExitCode::OS_ERROR
         }
     for (int i = 0; i < n; ++i) {
