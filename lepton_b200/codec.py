@@ -27,7 +27,9 @@ class LeptonB200Error(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "liblepton_b200.so")
+    """The C-ABI library.  LEPB200_LIBRARY selects another build of the same sources (tuning variants built with
+    `python -m lepton_b200.build --variant NAME` land in lepton_b200/variants/)."""
+    return os.environ.get("LEPB200_LIBRARY") or os.path.join(HERE, "liblepton_b200.so")
 
 
 class _Image(ctypes.Structure):

@@ -13,11 +13,7 @@
 #include "lep_common.cuh"
 #include "lep_predict.cuh"
 #include "lep_encode.cu"
-#include "lep_encode_lockstep.cu"
 #include "lep_decode.cu"
-#include "lep_decode_thread.cu"
-#include "lep_decode_lockstep.cu"
-#include "lep_decode_group.cu"
 #include "lep_decode_g2.cu"
 #include "lep_huff.cu"
 #include "lep_huffenc.cu"
@@ -77,12 +73,9 @@ struct lepb200_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
-    cudaStream_t stream2 = nullptr;        // decode mode 3: the lock-step kernel's share runs beside the warp kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_images, d_segs, d_order, d_counter, d_models, d_rows;
     DevBuf d_henc_out, d_henc_imgs, d_henc_segs, d_henc_tabs;
-    DevBuf d_models2, d_rows2;             // decode mode 3: models / row buffers of the lock-step share
     HostBuf h_henc_out, h_henc_segs;
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
     std::vector<int> henc_seg_first;      // per image: index of its first segment record
@@ -105,20 +98,16 @@ struct lepb200_ctx {
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
-    int dec_mode = 0;                     // decode kernel: 0 = one warp per segment (default), 1 = one thread per segment (wins only when
-                                          // tens of thousands of segments are in flight), 2 = one thread per segment with
-                                          // the lanes of a warp in lock step (lep_decode_lockstep.cu), 3 = both at once: the largest
-                                          // dec_split_pct % of the segments on the lock-step kernel (latency bound, few issue slots),
-                                          // the rest on the warp kernel (issue bound)
-    int enc_mode = 0;                     // kernel A: 0 = one warp per segment (default), 1 = one thread per segment, lanes in lock step
-                                          // (lep_encode_lockstep.cu); model / row-buffer slots as in the decode thread modes
-    int enc_threads = 0;
-    int dec_split_pct = 50;
-    int dec_lock = 0;                     // mode 3: segments of the current batch that go to the lock-step kernel
-    int dec_threads_max = 16384;          // thread / group modes: segments per launch (one 1.58 MB model each)
-    int dec_lanes = 8;                    // mode 4 (lep_decode_group.cu): lanes per thread-segment, 32 / dec_lanes segments per warp in lock step
-    int dec_group_grid = 0;               // mode 4: CTAs of the current batch
-    int dec_threads = 0;                  // thread mode: model / row-buffer slots of the current batch
+    int dec_mode = 0;                     // decode kernel: 0 = by batch size (group kernel when at least dec_group_min segments are in the
+                                          // batch, else one warp per segment), 1 = always one warp per segment (lep_decode.cu),
+                                          // 2 = always the group kernel (lep_decode_g2.cu)
+    int dec_group_min = 12288;            // the group kernel carries 8 serial chains per warp: fewer instructions per decision, but a
+                                          // longer latency per chain -- it wins when the chains alone fill the machine (measured: 16 384
+                                          // segments 1043 ms against 1620 ms; 4 096 segments 1000 ms against 510 ms)
+    int dec_threads_max = 16384;          // group kernel: segments per launch (one zero-filled 1.58 MB model each)
+    int dec_lanes = 4;                    // group kernel: lanes per thread-segment, 32 / dec_lanes segments per warp in lock step
+    int dec_group_grid = 0;               // group kernel: CTAs of the current batch
+    int dec_threads = 0;                  // group kernel: model slots of the current batch (0: the batch uses the warp kernel)
     bool tokens_known = false;            // token streams laid out on the host from caller-supplied bounds (no counting pre-pass)
     unsigned long long token_total = 0;
     bool stage_preuploaded = false;       // the caller pushed the staged scans itself (lepb200_huffman_stage_upload)
@@ -190,31 +179,23 @@ int validate_image(lepb200_ctx* ctx, const lepb200_image& im) {
     return 0;
 }
 
-// lep_decode_group_kernel<G> / lep_decode_g2_kernel<G>: launch shape (warps per CTA, thread-segments per warp) and resident CTAs per SM
-template <int G, bool V2> int group_ctas_per_sm() {
+// lep_decode_g2_kernel<G>: launch shape (warps per CTA, thread-segments per warp) and resident CTAs per SM
+template <int G> int group_ctas_per_sm() {
     int n = 0;
-    cudaError_t e = V2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_g2_kernel<G>, G2Cfg<G>::THREADS, 0)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_group_kernel<G>, GCfg<G>::THREADS, 0);
-    if (e != cudaSuccess) n = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lep_decode_g2_kernel<G>, G2Cfg<G>::THREADS, 0) != cudaSuccess) n = 1;
     return std::max(n, 1);
 }
-static_assert(GCfg<1>::WARPS == G2Cfg<1>::WARPS && GCfg<2>::WARPS == G2Cfg<2>::WARPS && GCfg<4>::WARPS == G2Cfg<4>::WARPS &&
-              GCfg<8>::WARPS == G2Cfg<8>::WARPS && GCfg<16>::WARPS == G2Cfg<16>::WARPS && GCfg<32>::WARPS == G2Cfg<32>::WARPS, "same launch shape");
-void group_launch_shape(int lanes, bool v2, int& warps, int& per_warp, int& ctas_per_sm) {
+void group_launch_shape(int lanes, int& warps, int& per_warp, int& ctas_per_sm) {
     per_warp = 32 / lanes;
     switch (lanes) {
-    case 1: warps = GCfg<1>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<1, true>() : group_ctas_per_sm<1, false>(); break;
-    case 2: warps = GCfg<2>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<2, true>() : group_ctas_per_sm<2, false>(); break;
-    case 4: warps = GCfg<4>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<4, true>() : group_ctas_per_sm<4, false>(); break;
-    case 8: warps = GCfg<8>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<8, true>() : group_ctas_per_sm<8, false>(); break;
-    case 16: warps = GCfg<16>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<16, true>() : group_ctas_per_sm<16, false>(); break;
-    default: warps = GCfg<32>::WARPS; ctas_per_sm = v2 ? group_ctas_per_sm<32, true>() : group_ctas_per_sm<32, false>(); break;
+    case 8: warps = G2Cfg<8>::WARPS; ctas_per_sm = group_ctas_per_sm<8>(); break;
+    case 32: warps = G2Cfg<32>::WARPS; ctas_per_sm = group_ctas_per_sm<32>(); break;
+    default: warps = G2Cfg<4>::WARPS; ctas_per_sm = group_ctas_per_sm<4>(); break;
     }
 }
-template <int G> void launch_group_kernel(bool v2, int grid, cudaStream_t st, const ImageDesc* images, SegDesc* segs, int first, int count, const int* order,
+template <int G> void launch_group_kernel(int grid, cudaStream_t st, const ImageDesc* images, SegDesc* segs, int first, int count, const int* order,
                                           int* counter, uint16_t* models, uint8_t* rows, size_t row_stride) {
-    if (v2) lep_decode_g2_kernel<G><<<grid, G2Cfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
-    else lep_decode_group_kernel<G><<<grid, GCfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
+    lep_decode_g2_kernel<G><<<grid, G2Cfg<G>::THREADS, 0, st>>>(images, segs, first, count, order, counter, models, rows, row_stride);
 }
 
 // Common part of encode/decode upload: job tables, pools, plane arena layout.
@@ -302,36 +283,20 @@ int build_batch(lepb200_ctx* ctx, const lepb200_image* images, int nimages, bool
     CK(ctx->d_segs.reserve(sizeof(SegDesc) * nseg));
     CK(ctx->d_order.reserve(sizeof(int) * nseg));
     CK(ctx->d_counter.reserve(256));
-    ctx->dec_lock = 0;
-    if (encode && ctx->enc_mode == 1) {
-        ctx->enc_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
-        CK(ctx->d_models.reserve((size_t)ctx->enc_threads * MODEL_BYTES));
-        CK(ctx->d_rows.reserve((size_t)ctx->enc_threads * row_stride));
-    } else if (!encode && (ctx->dec_mode == 4 || ctx->dec_mode == 5)) {
+    ctx->dec_threads = 0;
+    const bool use_group = !encode && (ctx->dec_mode == 2 || (ctx->dec_mode == 0 && nseg >= ctx->dec_group_min));
+    if (use_group) {
         // group kernel: one zero-filled model per segment of a launch, one row buffer per resident group
         ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
         int warps = 0, per_warp = 0, gsm = 0;
-        group_launch_shape(ctx->dec_lanes, ctx->dec_mode == 5, warps, per_warp, gsm);
+        group_launch_shape(ctx->dec_lanes, warps, per_warp, gsm);
         const int per_cta = warps * per_warp;
         ctx->dec_group_grid = std::max(1, std::min(gsm * ctx->sm_count, (ctx->dec_threads + per_cta - 1) / per_cta));
         CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)ctx->dec_group_grid * per_cta * row_stride));
-    } else if (!encode && (ctx->dec_mode == 1 || ctx->dec_mode == 2)) {
-        ctx->dec_threads = std::max(1, std::min(nseg, ctx->dec_threads_max));
-        CK(ctx->d_models.reserve((size_t)ctx->dec_threads * MODEL_BYTES));
-        CK(ctx->d_rows.reserve((size_t)ctx->dec_threads * row_stride));
     } else {
         CK(ctx->d_models.reserve((size_t)grid * wpc * MODEL_BYTES));
         CK(ctx->d_rows.reserve((size_t)grid * wpc * row_stride));
-        if (!encode && ctx->dec_mode == 3) {
-            // whole warps of the largest segments for the lock-step kernel
-            const int want = (int)((long long)nseg * ctx->dec_split_pct / 100);
-            ctx->dec_lock = std::min(std::min(want, ctx->dec_threads_max), nseg) / 32 * 32;
-            if (ctx->dec_lock > 0) {
-                CK(ctx->d_models2.reserve((size_t)ctx->dec_lock * MODEL_BYTES));
-                CK(ctx->d_rows2.reserve((size_t)ctx->dec_lock * row_stride));
-            }
-        }
     }
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < ctx->images[i].ncmp; ++c) ctx->images[i].plane[c] += (unsigned long long)(uintptr_t)ctx->d_planes.p;
@@ -390,17 +355,10 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
-    if (const char* e = getenv("LEPB200_ENC_MODE")) ctx->enc_mode = atoi(e);
-    if (const char* e = getenv("LEPB200_DEC_SPLIT")) ctx->dec_split_pct = std::min(100, std::max(0, atoi(e)));
+    if (const char* e = getenv("LEPB200_DEC_GROUP_MIN")) ctx->dec_group_min = std::max(1, atoi(e));
     if (const char* e = getenv("LEPB200_DEC_LANES")) {
         const int g = atoi(e);
-        if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ctx->dec_lanes = g;
-    }
-    if (ctx->dec_mode == 3 && (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-                               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-                               cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
-        lepb200_destroy(ctx);
-        return LEPB200_ERR_CUDA;
+        if (g == 4 || g == 8 || g == 32) ctx->dec_lanes = g;
     }
     *out = ctx;
     return LEPB200_OK;
@@ -414,15 +372,12 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_models2, &ctx->d_rows2})
+    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
         b->release();
     for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs}) b->release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_mid);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -694,25 +649,11 @@ int lepb200_encode_launch_symbolise(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->enc_mode == 1) {
-        // one thread per segment, lanes in lock step; a launch covers as many segments as there are model slots
-        for (int first = 0; first < nseg; first += ctx->enc_threads) {
-            const int count = std::min(ctx->enc_threads, nseg - first);
-            CK(cudaMemsetAsync(ctx->d_models.p, 0, (size_t)count * MODEL_BYTES, ctx->stream));       // identity prior = zero fill
-            lep_encode_lockstep_kernel<<<(count + ENCL_THREADS - 1) / ENCL_THREADS, ENCL_THREADS, 0, ctx->stream>>>(
-                static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), first, count, static_cast<const int*>(ctx->d_order.p),
-                static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride, static_cast<uint16_t*>(ctx->d_tokens.p));
-            CK(cudaGetLastError());
-            ctx->launches += 1;
-        }
-        ctx->launches -= 1;
-    } else {
-        lep_encode_kernel<<<ctx->grid, ENC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
-            static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
-            static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride,
-            static_cast<uint16_t*>(ctx->d_tokens.p));
-        CK(cudaGetLastError());
-    }
+    lep_encode_kernel<<<ctx->grid, ENC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
+        static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),
+        static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride,
+        static_cast<uint16_t*>(ctx->d_tokens.p));
+    CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_mid, ctx->stream));
     ctx->launches += 1;
     ctx->symbolised = true;
@@ -929,12 +870,11 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
     const int nseg = (int)ctx->segs.size();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, sizeof(int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->dec_mode == 4 || ctx->dec_mode == 5) {
-        // (4: lep_decode_group.cu, 5: lep_decode_g2.cu) G lanes per segment, 32 / G segments per warp in lock step; the groups of a launch share a queue of at most
-        // dec_threads segments (one zero-filled model each), largest first
+    if (ctx->dec_threads > 0) {
+        // group kernel (lep_decode_g2.cu): G lanes per segment, 32 / G segments per warp in lock step; the groups of a
+        // launch share a queue of at most dec_threads segments (one zero-filled model each), largest first
         int warps = 0, per_warp = 0, gsm = 0;
-        const bool v2 = ctx->dec_mode == 5;
-        group_launch_shape(ctx->dec_lanes, v2, warps, per_warp, gsm);
+        group_launch_shape(ctx->dec_lanes, warps, per_warp, gsm);
         const int per_cta = warps * per_warp;
         for (int first = 0; first < nseg; first += ctx->dec_threads) {
             const int count = std::min(ctx->dec_threads, nseg - first);
@@ -948,51 +888,14 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
             uint16_t* dm = static_cast<uint16_t*>(ctx->d_models.p);
             uint8_t* dr = static_cast<uint8_t*>(ctx->d_rows.p);
             switch (ctx->dec_lanes) {
-            case 1: launch_group_kernel<1>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 2: launch_group_kernel<2>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 4: launch_group_kernel<4>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 8: launch_group_kernel<8>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            case 16: launch_group_kernel<16>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
-            default: launch_group_kernel<32>(v2, grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 8: launch_group_kernel<8>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            case 32: launch_group_kernel<32>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
+            default: launch_group_kernel<4>(grid, ctx->stream, di, ds, first, count, dord, dcnt, dm, dr, ctx->row_stride); break;
             }
             CK(cudaGetLastError());
             ctx->launches += 1;
         }
         ctx->launches -= 1;
-    } else if (ctx->dec_mode == 1 || ctx->dec_mode == 2) {
-        // one thread per segment, largest segments first; a launch covers as many segments as there are model slots
-        // (mode 1: free-running lanes, mode 2: lanes in lock step)
-        const auto kernel = ctx->dec_mode == 2 ? lep_decode_lockstep_kernel : lep_decode_thread_kernel;
-        static_assert(DECT_THREADS == DECL_THREADS, "both thread-per-segment kernels use one warp per CTA");
-        for (int first = 0; first < nseg; first += ctx->dec_threads) {
-            const int count = std::min(ctx->dec_threads, nseg - first);
-            CK(cudaMemsetAsync(ctx->d_models.p, 0, (size_t)count * MODEL_BYTES, ctx->stream));       // identity prior = zero fill
-            kernel<<<(count + DECT_THREADS - 1) / DECT_THREADS, DECT_THREADS, 0, ctx->stream>>>(
-                static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), first, count, static_cast<const int*>(ctx->d_order.p),
-                static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
-            CK(cudaGetLastError());
-            ctx->launches += 1;
-        }
-        ctx->launches -= 1;
-    } else if (ctx->dec_mode == 3 && ctx->dec_lock > 0) {
-        // both kernels at once: order[0, k) -> lock-step kernel on the second stream, order[k, nseg) -> warp kernel
-        const int k = ctx->dec_lock;
-        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-        CK(cudaMemsetAsync(ctx->d_models2.p, 0, (size_t)k * MODEL_BYTES, ctx->stream2));
-        lep_decode_lockstep_kernel<<<(k + DECL_THREADS - 1) / DECL_THREADS, DECL_THREADS, 0, ctx->stream2>>>(
-            static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), 0, k, static_cast<const int*>(ctx->d_order.p),
-            static_cast<uint16_t*>(ctx->d_models2.p), static_cast<uint8_t*>(ctx->d_rows2.p), ctx->row_stride);
-        CK(cudaGetLastError());
-        if (nseg > k) {
-            lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
-                static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg - k, static_cast<const int*>(ctx->d_order.p) + k,
-                static_cast<int*>(ctx->d_counter.p), static_cast<uint16_t*>(ctx->d_models.p), static_cast<uint8_t*>(ctx->d_rows.p), ctx->row_stride);
-            CK(cudaGetLastError());
-            ctx->launches += 1;
-        }
-        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     } else {
         lep_decode_kernel<<<ctx->grid, DEC_WARPS_PER_CTA * 32, 0, ctx->stream>>>(
             static_cast<const ImageDesc*>(ctx->d_images.p), static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p),

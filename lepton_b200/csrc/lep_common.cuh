@@ -61,22 +61,11 @@ __host__ __device__ inline uint32_t m_nz7(int ci, int bin, int idx, int prefix) 
 __host__ __device__ inline uint32_t m_nze(int vertical, int ci, int eob, int nzb, int idx, int prefix) {
     return M_NZE + (((((vertical * 2 + ci) * 8 + eob) * 8 + nzb) * 3 + idx) << 2) + prefix;
 }
-// LEPB200_MODEL_LAYOUT: 0 (default) = position-major tables as declared above; 1 = the three big tables with the position
-// innermost ([ci][bin][bsr][zz], [ci][ne][bsr][zig15], [ci][bin][coord]): the contexts a segment keeps hitting differ in
-// the position much more than in bsr / bin, so they share 128-byte lines (tests/tools_model_reuse.py: a quarter fewer
-// misses with 64 lines of cache per segment).  Same entries, same sizes; only where an entry lives changes.
-#ifndef LEPB200_MODEL_LAYOUT
-#define LEPB200_MODEL_LAYOUT 0
-#endif
-#if LEPB200_MODEL_LAYOUT == 0
+// (a position-innermost variant of the three big tables was measured in rounds 1 and 2 -- kernel A 305 ms against 290 ms,
+// decode 1632 ms against 1620 ms -- and dropped)
 __host__ __device__ inline uint32_t m_resn(int ci, int coord, int bin) { return M_RESN + (((ci * 64 + coord) * 10 + bin) << 4); }
 __host__ __device__ inline uint32_t m_exp7(int ci, int bin, int zz, int bsr) { return M_EXP7 + ((((ci * 10 + bin) * 49 + zz) * 12 + bsr) << 4); }
 __host__ __device__ inline uint32_t m_expx(int ci, int ne, int zig15, int bsr) { return M_EXPX + ((((ci * 8 + ne) * 15 + zig15) * 12 + bsr) << 4); }
-#else
-__host__ __device__ inline uint32_t m_resn(int ci, int coord, int bin) { return M_RESN + (((ci * 10 + bin) * 64 + coord) << 4); }
-__host__ __device__ inline uint32_t m_exp7(int ci, int bin, int zz, int bsr) { return M_EXP7 + ((((ci * 10 + bin) * 12 + bsr) * 49 + zz) << 4); }
-__host__ __device__ inline uint32_t m_expx(int ci, int ne, int zig15, int bsr) { return M_EXPX + ((((ci * 8 + ne) * 12 + bsr) * 15 + zig15) << 4); }
-#endif
 __host__ __device__ inline uint32_t m_resdc(int lenmxm) { return M_RESDC + (lenmxm << 4); }
 __host__ __device__ inline uint32_t m_expdc(int a, int b) { return M_EXPDC + ((a * 17 + b) << 4); }
 __host__ __device__ inline uint32_t m_sign(int ci, int a, int b) { return M_SIGN + (ci * 4 + a) * 12 + b; }

@@ -1,8 +1,8 @@
 """CPU emulation of the decode kernels (test infrastructure).
 
 The kernel sources compile as host C++ through `cuda_shim.h`, which runs every CUDA thread of a CTA as a fiber and
-implements the warp collectives and `__syncthreads` among them, so `lep_decode.cu` (warp per segment),
-`lep_decode_thread.cu` and `lep_decode_lockstep.cu` (thread per segment) execute with real 32-lane warps, divergence,
+implements the warp collectives and `__syncthreads` among them, so `lep_decode.cu` (warp per segment) and
+`lep_decode_g2.cu` (G lanes per segment, 32 / G segments per warp in lock step) execute with real 32-lane warps, divergence,
 votes and shuffles included, and can be pinned to the oracle bit for bit without a GPU.  The GPU parity tests then
 confirm the same sources on the device; what the emulator cannot show is timing and memory-system behaviour.
 """
@@ -17,24 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
 SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
-           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_encode_lockstep.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_thread.cu"), os.path.join(CSRC, "lep_decode_lockstep.cu"), os.path.join(CSRC, "lep_decode_group.cu"), os.path.join(CSRC, "lep_decode_g2.cu"),
+           os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_g2.cu"),
            os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
-KERNEL_THREAD = 1
-KERNEL_LOCKSTEP = 2
-
-
-def KERNEL_GROUP(lanes):
-    """lep_decode_group_kernel<lanes>: `lanes` lanes per thread-segment, 32 / lanes segments per warp in lock step."""
-    assert lanes in (1, 2, 4, 8, 16, 32)
-    return 100 + lanes
 
 
 def KERNEL_G2(lanes):
-    """lep_decode_g2_kernel<lanes>: the group kernel with the stripped-down step loop."""
+    """lep_decode_g2_kernel<lanes>: `lanes` lanes per thread-segment, 32 / lanes segments per warp in lock step."""
     assert lanes in (1, 2, 4, 8, 16, 32)
     return 200 + lanes
+
 
 _LIB = None
 
@@ -94,7 +87,6 @@ def decode_images(kernel, images, streams, grid_cap=0):
 
 
 ENC_KERNEL_A = 0
-ENC_KERNEL_LOCKSTEP = 1
 
 
 def encode_images(images, grid_cap=0, kernel=0):

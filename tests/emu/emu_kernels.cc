@@ -10,11 +10,7 @@
 
 #include "cuda_shim.h"
 #include "../../lepton_b200/csrc/lep_encode.cu"
-#include "../../lepton_b200/csrc/lep_encode_lockstep.cu"
 #include "../../lepton_b200/csrc/lep_decode.cu"
-#include "../../lepton_b200/csrc/lep_decode_thread.cu"
-#include "../../lepton_b200/csrc/lep_decode_lockstep.cu"
-#include "../../lepton_b200/csrc/lep_decode_group.cu"
 #include "../../lepton_b200/csrc/lep_decode_g2.cu"
 #include "../../include/lepton_b200.h"
 
@@ -64,14 +60,6 @@ struct LaunchArgs {
 void kernel_body(void* p) {
     const LaunchArgs& a = *static_cast<const LaunchArgs*>(p);
     if (a.kernel == 0) lep_decode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 1) lep_decode_thread_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 2) lep_decode_lockstep_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 101) lep_decode_group_kernel<1>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 102) lep_decode_group_kernel<2>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 104) lep_decode_group_kernel<4>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 108) lep_decode_group_kernel<8>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 116) lep_decode_group_kernel<16>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
-    else if (a.kernel == 132) lep_decode_group_kernel<32>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
     else if (a.kernel == 201) lep_decode_g2_kernel<1>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
     else if (a.kernel == 202) lep_decode_g2_kernel<2>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
     else if (a.kernel == 204) lep_decode_g2_kernel<4>(a.images, a.segs, 0, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride);
@@ -89,13 +77,13 @@ void group_shape(int G, int& warps, int& per_warp) {
 }  // namespace
 
 // kernel: 0 = lep_decode_kernel (warp per segment, persistent CTAs; `grid_cap` > 0 limits the CTAs so that warps take
-// several segments from the queue), 1 = lep_decode_thread_kernel, 2 = lep_decode_lockstep_kernel.  Decodes into images[i].planes (zeroed first,
+// several segments from the queue), 200 + G = lep_decode_g2_kernel<G> (G lanes per segment).  Decodes into images[i].planes (zeroed first,
 // like the device arena); per-segment status and decision counts come back like lepb200_decode_fetch reports them.
 extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, const lepb200_stream* in,
                                  int32_t* status_out, uint64_t* ndecisions_out) {
     const int gl = kernel % 100;
-    const bool group = (kernel / 100 == 1 || kernel / 100 == 2) && (gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32);
-    if (nimages <= 0 || !images || !in || kernel < 0 || (kernel > 2 && !group)) return LEPB200_ERR_INVALID;
+    const bool group = kernel / 100 == 2 && (gl == 1 || gl == 2 || gl == 4 || gl == 8 || gl == 16 || gl == 32);
+    if (nimages <= 0 || !images || !in || (kernel != 0 && !group)) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
     std::vector<SegDesc> segs;
     std::vector<size_t> seg_blocks;
@@ -163,13 +151,10 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
         if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
         block = (unsigned)warps * 32;
         group_slots = (size_t)grid * warps * per_warp;
-    } else if (kernel == 0) {
+    } else {
         grid = (unsigned)((nseg + DEC_WARPS_PER_CTA - 1) / DEC_WARPS_PER_CTA);
         if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
         block = DEC_WARPS_PER_CTA * 32;
-    } else {
-        grid = (unsigned)((nseg + 31) / 32);
-        block = 32;
     }
     const size_t slots = kernel == 0 ? (size_t)grid * DEC_WARPS_PER_CTA : (size_t)nseg;
     std::vector<uint16_t> models(slots * M_TOTAL, kernel == 0 ? 0x5a5a : 0);       // thread / group kernels: zero fill before the launch; the warp kernel clears its own
@@ -186,7 +171,7 @@ extern "C" int emu_decode_images(int kernel, int grid_cap, const lepb200_image* 
 namespace {
 
 struct EncArgs {
-    int stage;                       // 0 count, 1 offsets, 2 symbolise (kernel A), 3 range coder (kernel B), 4 symbolise (lock-step kernel)
+    int stage;                       // 0 count, 1 offsets, 2 symbolise (kernel A), 3 range coder (kernel B)
     const ImageDesc* images; SegDesc* segs; int nseg; const int* order; int* counter;
     uint16_t* models; uint8_t* rows; size_t row_stride; uint16_t* tokens; unsigned long long* total;
 };
@@ -196,8 +181,7 @@ void enc_body(void* p) {
     if (a.stage == 0) lep_count_kernel(a.images, a.segs, a.nseg);
     else if (a.stage == 1) lep_token_offsets_kernel(a.segs, a.nseg, a.total);
     else if (a.stage == 2) lep_encode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride, a.tokens);
-    else if (a.stage == 3) lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
-    else lep_encode_lockstep_kernel(a.images, a.segs, 0, a.nseg, a.order, a.models, a.rows, a.row_stride, a.tokens);
+    else lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
 }
 
 }  // namespace
@@ -205,7 +189,7 @@ void enc_body(void* p) {
 // lepb200_encode_images on the emulator: count pre-pass -> token offsets -> kernel A (symbolise + model) -> kernel B
 // (range coder), with the launch shapes of lep_capi.cu.  `out` must hold sum(nseg) entries; the bytes of every stream are
 // copied into `arena` (capacity arena_cap) back to back and out[i].data points there.  grid_cap > 0 limits kernel A's
-// CTAs (persistent warps then take several segments each).  kernel: 0 = lep_encode_kernel, 1 = lep_encode_lockstep_kernel.
+// CTAs (persistent warps then take several segments each).  `kernel` is kept for the ABI of the harness (0).
 extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, lepb200_stream* out, uint8_t* arena, size_t arena_cap) {
     if (nimages <= 0 || !images || !out || !arena) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
@@ -270,18 +254,13 @@ extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* 
     a.tokens = tokens.data();
     std::vector<uint16_t> models;
     std::vector<uint8_t> rows;
-    if (kernel == 0) {
+    {
         unsigned grid = (unsigned)((nseg + ENC_WARPS_PER_CTA - 1) / ENC_WARPS_PER_CTA);
         if (grid_cap > 0) grid = std::min(grid, (unsigned)grid_cap);
         models.assign((size_t)grid * ENC_WARPS_PER_CTA * M_TOTAL, 0x5a5a);      // the kernel clears its own
         rows.assign((size_t)grid * ENC_WARPS_PER_CTA * row_stride, 0);
         a.models = models.data(); a.rows = rows.data();
         a.stage = 2; emu::launch(grid, ENC_WARPS_PER_CTA * 32, enc_body, &a);
-    } else {
-        models.assign((size_t)nseg * M_TOTAL, 0);                               // zero fill before the launch
-        rows.assign((size_t)nseg * row_stride, 0);
-        a.models = models.data(); a.rows = rows.data();
-        a.stage = 4; emu::launch((unsigned)((nseg + ENCL_THREADS - 1) / ENCL_THREADS), ENCL_THREADS, enc_body, &a);
     }
     a.stage = 3; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
     size_t used = 0;

@@ -1,9 +1,10 @@
 """The decode kernels, compiled as host C++ and run with real 32-lane warps by the CPU warp emulator (tests/emu), against
 the oracle.
 
-`lep_decode.cu` (warp per segment, the default), `lep_decode_thread.cu` (LEPB200_DEC_MODE=1) and `lep_decode_lockstep.cu`
-(LEPB200_DEC_MODE=2) run here exactly as written -- divergence, votes, shuffles, shared memory and the persistent work
-queue included -- so their logic is pinned without a GPU; the GPU parity tests run the same sources on the device.
+`lep_decode.cu` (one warp per thread-segment; small batches) and `lep_decode_g2.cu` (G lanes per segment, 32 / G segments
+per warp in lock step; large batches) run here exactly as written -- divergence, votes, shuffles, shared memory and the
+persistent work queues included -- so their logic is pinned without a GPU; the GPU parity tests run the same sources on
+the device.
 """
 import os
 import sys
@@ -17,11 +18,11 @@ import oracle  # noqa: E402
 from helpers import (coef_image_from_lep, geometry_of, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image,
                      random_coef_image, segments_of)
 
-KERNELS = [emu.KERNEL_WARP, emu.KERNEL_THREAD, emu.KERNEL_LOCKSTEP]
-GROUPS = [emu.KERNEL_GROUP(g) for g in (1, 4, 32)] + [emu.KERNEL_G2(g) for g in (1, 2, 4, 8, 16, 32)]   # lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4), lep_decode_g2_kernel<G> (mode 5)
+KERNELS = [emu.KERNEL_WARP]
+GROUPS = [emu.KERNEL_G2(g) for g in (1, 2, 4, 8, 16, 32)]       # lep_decode_g2_kernel<G>; the library ships G = 4, 8, 32
 
 
-@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_G2(8)])
+@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_G2(4)])
 def test_golden_files_decode_to_the_reference_planes(kernel):
     for name in golden_leps():
         lf = load_lep(name)
@@ -33,7 +34,7 @@ def test_golden_files_decode_to_the_reference_planes(kernel):
             assert np.array_equal(img.planes[c], planes[c]), "%s component %d" % (name, c)
 
 
-@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_G2(4)])
+@pytest.mark.parametrize("kernel", KERNELS + [emu.KERNEL_G2(8)])
 def test_one_launch_with_more_segments_than_a_warp(kernel):
     """All golden files in one batch: > 32 segments, so several warps and a partly filled last one."""
     imgs, streams_all, want = [], [], []
@@ -79,7 +80,7 @@ def test_random_planes_oracle_streams_decode_back(kernel, cfg):
         assert np.array_equal(out.planes[c], img.planes[c])
 
 
-def test_damaged_streams_end_the_same_way_in_both_kernels_and_the_oracle():
+def test_damaged_streams_end_the_same_way_in_all_kernels_and_the_oracle():
     """Truncated / bit-flipped streams: whatever comes out (status 7 for an impossible non-zero count, or garbage
     coefficients), the two kernels and the oracle must agree on status, decision count and every stored block."""
     rng = np.random.default_rng(99)
@@ -101,12 +102,12 @@ def test_damaged_streams_end_the_same_way_in_both_kernels_and_the_oracle():
             rc, _ = oracle.decode_segment(g, want, y0, y1, last, bad[i])
             want_rc.append(rc)
         got = {}
-        for kernel in KERNELS + [emu.KERNEL_GROUP(4), emu.KERNEL_G2(4), emu.KERNEL_G2(16)]:
+        for kernel in KERNELS + [emu.KERNEL_G2(4), emu.KERNEL_G2(8), emu.KERNEL_G2(32)]:
             img = coef_image_from_lep(lf, [np.full_like(p, 11) for p in planes])
             st, nd = emu.decode_images(kernel, [img], [bad])
             got[kernel] = (st, nd, [p.copy() for p in img.planes])
-        a = got[emu.KERNEL_THREAD]
-        for b in (got[emu.KERNEL_WARP], got[emu.KERNEL_LOCKSTEP], got[emu.KERNEL_GROUP(4)], got[emu.KERNEL_G2(4)], got[emu.KERNEL_G2(16)]):
+        a = got[emu.KERNEL_WARP]
+        for b in (got[emu.KERNEL_G2(4)], got[emu.KERNEL_G2(8)], got[emu.KERNEL_G2(32)]):
             assert a[0] == b[0] == want_rc and a[1] == b[1]
             for c in range(len(planes)):
                 assert np.array_equal(a[2][c], b[2][c])

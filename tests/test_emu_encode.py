@@ -1,6 +1,5 @@
-"""The encode kernels -- count pre-pass, token offsets, kernel A (symbolise + adaptive model) or its lock-step
-thread-per-segment counterpart (lep_encode_lockstep.cu, LEPB200_ENC_MODE=1), kernel B (range coder) -- compiled as host
-C++ and run with real 32-lane warps by the CPU warp emulator (tests/emu), against the reference's streams and the
+"""The encode kernels -- count pre-pass, token offsets, kernel A (symbolise + adaptive model), kernel B (range coder) --
+compiled as host C++ and run with real 32-lane warps by the CPU warp emulator (tests/emu), against the reference's streams and the
 oracle.  Same cases as the GPU parity tests of the encoder; the GPU tests run the same sources on the device."""
 import os
 import sys
@@ -13,7 +12,7 @@ import emu  # noqa: E402
 from helpers import coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image, random_coef_image
 
 
-KERNELS = [emu.ENC_KERNEL_A, emu.ENC_KERNEL_LOCKSTEP]
+KERNELS = [emu.ENC_KERNEL_A]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -101,25 +100,3 @@ def test_mixed_batch_many_images(kernel):
     for img, g in zip(imgs, got):
         ref = oracle_encode_image(img)
         assert [x[1] for x in g] == [r[1] for r in ref]
-
-
-def test_position_innermost_model_layout_is_bit_exact():
-    """LEPB200_MODEL_LAYOUT=1 only moves entries of the exponent / residual tables (cache locality); every kernel must
-    produce and consume the same streams with it."""
-    names = ["androidcrop_t2.lep", "iphoneprogressive2.lep", "truncatedzerorun.lep", "gray2sf.lep"]
-    emu.use_variant("layout1", ["LEPB200_MODEL_LAYOUT=1"])
-    try:
-        for name in names:
-            lf = load_lep(name)
-            planes, streams = oracle_decode_planes(lf)
-            img = coef_image_from_lep(lf, planes)
-            for kernel in KERNELS:
-                got = emu.encode_images([img], kernel=kernel)[0]
-                assert [g[1] for g in got] == list(streams[:lf.nseg]), (name, kernel)
-            for kernel in (emu.KERNEL_WARP, emu.KERNEL_THREAD, emu.KERNEL_LOCKSTEP):
-                out = coef_image_from_lep(lf, [np.full_like(p, 9) for p in planes])
-                st, _ = emu.decode_images(kernel, [out], [streams[:lf.nseg]])
-                assert all(s == 0 for s in st)
-                assert all(np.array_equal(a, b) for a, b in zip(out.planes, planes)), (name, kernel)
-    finally:
-        emu.use_default()

@@ -51,56 +51,13 @@ def test_golden_batch_decode_matches_reference_planes(codec):
             assert np.array_equal(img.planes[c], planes[c]), "%s component %d" % (name, c)
 
 
-def test_golden_batch_decode_thread_per_segment_kernel(monkeypatch):
-    """The alternative decode kernel (one thread per segment, LEPB200_DEC_MODE=1) must give the same planes."""
+@pytest.mark.parametrize("lanes", ["4", "8", "32"])
+def test_golden_batch_decode_group_kernel(monkeypatch, lanes):
+    """lep_decode_g2_kernel<G> (the decode kernel of large batches; forced here with LEPB200_DEC_MODE=2): G lanes per
+    thread-segment, 32 / G segments per warp in lock step; every group size the library ships must give the reference
+    planes.  LEPB200_DEC_THREADS=32 forces several launches / a shared queue."""
     from lepton_b200 import LeptonB200Codec
-    monkeypatch.setenv("LEPB200_DEC_MODE", "1")
-    c = LeptonB200Codec(0)
-    try:
-        test_golden_batch_decode_matches_reference_planes(c)
-    finally:
-        c.close()
-
-
-@pytest.mark.skipif(os.environ.get("LEPB200_TEST_LOCKSTEP") != "1",
-                    reason="lock-step encode kernel: pinned on the CPU (tests/test_emu_encode.py), first GPU run pending; "
-                           "set LEPB200_TEST_LOCKSTEP=1 (and run under `timeout`) to include it")
-def test_golden_batch_encode_lockstep_kernel(monkeypatch):
-    """The lock-step thread-per-segment kernel A (LEPB200_ENC_MODE=1) must give the reference's streams."""
-    from lepton_b200 import LeptonB200Codec
-    monkeypatch.setenv("LEPB200_ENC_MODE", "1")
-    c = LeptonB200Codec(0)
-    try:
-        test_golden_batch_encode_matches_reference_streams(c)
-    finally:
-        c.close()
-
-
-@pytest.mark.skipif(os.environ.get("LEPB200_TEST_LOCKSTEP") != "1",
-                    reason="lock-step decode kernel: pinned on the CPU (tests/test_emu_decode.py), first GPU run pending; "
-                           "set LEPB200_TEST_LOCKSTEP=1 (and run under `timeout`) to include it")
-@pytest.mark.parametrize("mode", ["2", "3"])
-def test_golden_batch_decode_lockstep_kernel(monkeypatch, mode):
-    """The lock-step thread-per-segment decode kernel must give the same planes: alone (LEPB200_DEC_MODE=2) and sharing
-    the batch with the warp kernel on a second stream (mode 3: the largest half of the segments on the lock-step kernel)."""
-    from lepton_b200 import LeptonB200Codec
-    monkeypatch.setenv("LEPB200_DEC_MODE", mode)
-    monkeypatch.setenv("LEPB200_DEC_SPLIT", "90")          # mode 3: one full warp of segments for the lock-step kernel, the rest for the warp kernel
-    c = LeptonB200Codec(0)
-    try:
-        test_golden_batch_decode_matches_reference_planes(c)
-    finally:
-        c.close()
-
-
-@pytest.mark.parametrize("mode", ["4", "5"])
-@pytest.mark.parametrize("lanes", ["1", "4", "8", "32"])
-def test_golden_batch_decode_group_kernel(monkeypatch, lanes, mode):
-    """lep_decode_group_kernel<G> (LEPB200_DEC_MODE=4) and lep_decode_g2_kernel<G> (mode 5, the stripped-down step loop):
-    G lanes per thread-segment, 32 / G segments per warp in lock step; every group size must give the reference planes.
-    LEPB200_DEC_THREADS=32 forces several launches / a shared queue."""
-    from lepton_b200 import LeptonB200Codec
-    monkeypatch.setenv("LEPB200_DEC_MODE", mode)
+    monkeypatch.setenv("LEPB200_DEC_MODE", "2")
     monkeypatch.setenv("LEPB200_DEC_LANES", lanes)
     if lanes == "4":
         monkeypatch.setenv("LEPB200_DEC_THREADS", "32")
@@ -109,6 +66,29 @@ def test_golden_batch_decode_group_kernel(monkeypatch, lanes, mode):
         test_golden_batch_decode_matches_reference_planes(c)
     finally:
         c.close()
+
+
+def test_random_planes_through_both_decode_kernels(monkeypatch):
+    """The same coded batch through the warp-per-segment kernel (LEPB200_DEC_MODE=1) and the group kernel (mode 2): both
+    must return the planes that were encoded."""
+    from lepton_b200 import CoefImage, LeptonB200Codec
+    rng = np.random.default_rng(4242)
+    imgs = [random_coef_image(rng, ncmp=3, mcuh=3 + k % 5, mcuv=3 + k % 4, sf=((2, 2), (1, 1), (1, 1)) if k % 2 else ((1, 1), (1, 1), (1, 1)), nseg=1 + k % 4)
+            for k in range(40)]
+    for mode in ("1", "2"):
+        monkeypatch.setenv("LEPB200_DEC_MODE", mode)
+        c = LeptonB200Codec(0)
+        try:
+            got = c.encode_images(imgs)
+            outs = [CoefImage(ncmp=im.ncmp, mcuv=im.mcuv, bch=im.bch, bcv=im.bcv, qtables_zigzag=im.qtables_zigzag,
+                              planes=[np.full_like(p, 3) for p in im.planes], luma_y_start=im.luma_y_start) for im in imgs]
+            st = c.decode_images(outs, [[g.data for g in r] for r in got])
+            assert all(s == 0 for s in st), (mode, st)
+            for im, o in zip(imgs, outs):
+                for a, b in zip(im.planes, o.planes):
+                    assert np.array_equal(a, b), mode
+        finally:
+            c.close()
 
 
 @pytest.mark.parametrize("cfg", [
@@ -487,9 +467,6 @@ def test_verify_mode_withholds_files_that_do_not_round_trip(tmp_path):
     assert r.returncode == 0 and (tmp_path / "a.lep").read_bytes() == open(os.path.join(GOLDEN, "androidcrop.lep"), "rb").read()
 
 
-@pytest.mark.skipif(os.environ.get("LEPB200_TEST_PLUG") != "1",
-                    reason="reference CLI with the adapters plugged in: not yet tried on a GPU (the reference replaces "
-                           "operator new with a bounded arena, INTEGRATION.md section 1); set LEPB200_TEST_PLUG=1 to include it")
 @pytest.mark.timeout(600, method="thread")
 def test_reference_cli_with_b200_adapters(tmp_path):
     """oracle/_ref/lepton-b200plug = the reference's own CLI, built from its sources with B200ComponentEncoder /
@@ -498,8 +475,7 @@ def test_reference_cli_with_b200_adapters(tmp_path):
     import subprocess
     from helpers import GOLDEN
     exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "lepton-b200plug")
-    if not os.path.exists(exe):
-        pytest.skip("plug binary not built (needs the reference tree at build time)")
+    assert os.path.exists(exe), "oracle/_ref/lepton-b200plug missing: __graft_entry__.build() makes it where /root/reference exists (it travels with the snapshot)"
     for name in ("androidcrop.jpg", "grayscale.jpg", "iphonecrop2.jpg"):
         src = os.path.join(GOLDEN, name)
         lep, back = str(tmp_path / "o.lep"), str(tmp_path / "o.jpg")
