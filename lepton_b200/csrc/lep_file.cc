@@ -490,7 +490,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         all[i].reset(new LepFile());
         if (read_lep(leps[i].data, leps[i].len, *all[i])) {
             for (int q = 0; q < all[i]->j.ncmp; ++q) pbytes[i] += (plane_bytes(all[i]->j, q) + 255) & ~size_t(255);
-            if (pbytes[i] > c->plane_cap / (size_t)std::max(1, c->concurrent)) { all[i]->status = NOT_HANDLED; all[i]->error = "image larger than the per-chunk device memory budget"; pbytes[i] = 0; }
+            if (pbytes[i] > c->plane_cap) { all[i]->status = NOT_HANDLED; all[i]->error = "image larger than the per-chunk device memory budget"; pbytes[i] = 0; }
         }
     });
     c->t_front += now_s() - t_parse;
@@ -499,23 +499,22 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     std::vector<std::pair<int, int>> ranges;
     int W = 1;
     {
-        // as in lepb200_compress_jpegs: up to `concurrent` chunks of about equal plane bytes run at the same time, each on
-        // its own context; without the device re-encoder every plane needs pinned host memory too, so those chunks stay small
-        size_t total = 0;
-        for (int i = 0; i < n; ++i) total += pbytes[i];
-        W = (n >= 64 && total >= (size_t(1) << 30)) ? std::max(1, c->concurrent) : 1;
-        const size_t cap = (c->gpu_huffman ? c->plane_cap : (size_t(6) << 30)) / (size_t)W;
-        const size_t target = std::min(cap, std::max<size_t>(total / (size_t)W + 1, size_t(256) << 20));
+        // Unlike the way in, the way back wants LARGE chunks: the decode kernel of large batches (lep_decode_g2.cu, eight
+        // serial chains per warp) is bound by the latency of a chain, so its duration hardly depends on how many
+        // segments a launch covers -- cutting a call into four chunks costs four times that latency (measured: 4096
+        // files 1.48 s in one chunk, 1.90 s in four).  A chunk therefore takes as much as the device memory budget
+        // allows; when a call needs several, two are in flight (the second one's host stages and copies under the
+        // first one's kernel).  Without the device re-encoder every plane needs pinned host memory too: small chunks.
+        const size_t cap = c->gpu_huffman ? c->plane_cap : (size_t(6) << 30);
         const int chunk_max = std::max(1, c->chunk_images);
         int b0 = 0;
         size_t acc = 0;
         for (int i = 0; i < n; ++i) {
-            if (i > b0 && (i - b0 >= chunk_max || acc + pbytes[i] > target)) { ranges.emplace_back(b0, i); b0 = i; acc = 0; }
+            if (i > b0 && (i - b0 >= chunk_max || acc + pbytes[i] > cap)) { ranges.emplace_back(b0, i); b0 = i; acc = 0; }
             acc += pbytes[i];
         }
         ranges.emplace_back(b0, n);
-        if (c->chunk_images < 4096 && (int)ranges.size() > 1) W = std::max(W, std::min((int)ranges.size(), c->concurrent));
-        W = std::max(1, std::min(W, (int)ranges.size()));
+        W = std::max(1, std::min(std::min(2, c->concurrent), (int)ranges.size()));
     }
     const int pth = std::max(1, c->nthreads / W);
     const int nchunks = (int)ranges.size();

