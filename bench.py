@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic images replicated to --images (0 = per config)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-only", action="store_true", help="diagnostic: skip the device-resident legs (the line then has no `value`)")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads for the e2e stage (0 = effective cores / ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -351,7 +352,7 @@ def main():
 
     # ================================================================== device-resident legs (config 2 only)
     sampler = ClockSampler(local_rank)
-    if cfg == 2:
+    if cfg == 2 and not args.e2e_only:
         hjs = [HostJpeg(j) for j in distinct]
         for h in hjs:
             assert h.status == 0, h.error
@@ -494,7 +495,7 @@ def main():
             leps = [b for _, b in r]
             lep_bytes = sum(len(b) for b in leps)
             barrier()
-            if cfg != 2:
+            if cfg != 2 or args.e2e_only:
                 sampler.start()
             l0 = fc.kernel_launches
             t0 = time.perf_counter()
@@ -529,7 +530,7 @@ def main():
                                  "roundtrip_pass_rate": exact / len(jpegs), "roundtrip_files": len(jpegs), "stage_seconds_last_step": fc.last_timing()}
             e2e["value"] = total_jpeg * args.e2e_steps / (e_s + (d_s or 0.0)) / 1e6
             line["e2e"] = e2e
-            if cfg != 2:
+            if cfg != 2 or args.e2e_only:
                 line.update(value=e2e["value"], ms_per_step=1e3 * (e_s + (d_s or 0.0)) / args.e2e_steps, clocks=sampler.stop(),
                             gpu_launches=int(e2e["gpu_launches"]), value_note="file-level API only for this config (value == e2e.value)")
                 if "decode" in e2e:
