@@ -848,18 +848,43 @@ int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
     int r = build_batch(ctx, images, nimages, false, in);
     if (r) return r;
     const int nseg = (int)ctx->segs.size();
-    // pack the streams into one pinned staging buffer -> one H2D copy
-    size_t total = 0;
-    for (int s = 0; s < nseg; ++s) total = std::max(total, (size_t)(ctx->segs[s].stream - (unsigned long long)(uintptr_t)ctx->d_streams.p) + in[s].len);
-    CK(ctx->h_stage.reserve(total + 16));
-    for (int s = 0; s < nseg; ++s)
-        if (in[s].len) memcpy(static_cast<uint8_t*>(ctx->h_stage.p) + (ctx->segs[s].stream - (unsigned long long)(uintptr_t)ctx->d_streams.p), in[s].data, in[s].len);
-    if (total) CK(cudaMemcpyAsync(ctx->d_streams.p, ctx->h_stage.p, total, cudaMemcpyHostToDevice, ctx->stream));
-    // planes start zeroed: blocks outside the coded range (truncated images) stay zero like the reference's calloc
+    // planes start zeroed: blocks outside the coded range (truncated images) stay zero like the reference's calloc.
+    // Issued first: the device clears them while the host packs the streams.
     size_t plane_total = 0;
     for (int i = 0; i < nimages; ++i)
         for (int c = 0; c < images[i].ncmp; ++c) plane_total = std::max(plane_total, (size_t)(ctx->images[i].plane[c] - (unsigned long long)(uintptr_t)ctx->d_planes.p) + ctx->plane_bytes[(size_t)i * 3 + c]);
     CK(cudaMemsetAsync(ctx->d_planes.p, 0, plane_total, ctx->stream));
+    // pack the streams into the pinned staging buffer (over a gigabyte for a 4096-image batch: a single-threaded copy
+    // loop took longer than the H2D itself) in a few slices of consecutive segments; every slice is packed by the
+    // context's host threads and its H2D copy runs while the next one is packed
+    const unsigned long long base = (unsigned long long)(uintptr_t)ctx->d_streams.p;
+    size_t total = 0;
+    for (int s = 0; s < nseg; ++s) total = std::max(total, (size_t)(ctx->segs[s].stream - base) + in[s].len);
+    CK(ctx->h_stage.reserve(total + 16));
+    uint8_t* hs = static_cast<uint8_t*>(ctx->h_stage.p);
+    const int nslices = total > (size_t(64) << 20) ? 8 : 1;
+    int s0 = 0;
+    for (int k = 0; k < nslices && s0 < nseg; ++k) {
+        // segments are laid out in order, so a slice is a contiguous byte range of the staging buffer
+        const size_t want_end = total / nslices * (k + 1);
+        int s1 = s0;
+        while (s1 < nseg && (k + 1 == nslices || (size_t)(ctx->segs[s1].stream - base) < want_end)) ++s1;
+        const int nt = std::max(1, std::min(ctx->host_threads, s1 - s0));
+        auto pack = [&](int t) {
+            for (int s = s0 + t; s < s1; s += nt)
+                if (in[s].len) memcpy(hs + (ctx->segs[s].stream - base), in[s].data, in[s].len);
+        };
+        if (nt == 1) pack(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(pack, t);
+            for (auto& t : th) t.join();
+        }
+        const size_t b0 = (size_t)(ctx->segs[s0].stream - base);
+        const size_t b1 = s1 < nseg ? (size_t)(ctx->segs[s1].stream - base) : total;
+        if (b1 > b0) CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_streams.p) + b0, hs + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->stream));
+        s0 = s1;
+    }
     ctx->have_batch = true;
     return LEPB200_OK;
 }
