@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--batch", type=int, default=1024, help="config 5: files per decode call (latency = time of a call)")
+    ap.add_argument("--streams", type=int, default=4, help="config 5: decode calls in flight (one codec + one submitting thread each), like a server that keeps several requests going")
     args = ap.parse_args()
     cfg = args.config
     if args.images <= 0:
@@ -468,22 +469,51 @@ def main():
             barrier()
             if not sampler.samples and sampler.proc is None:
                 sampler.start()
+            # K calls in flight: K codecs (own contexts / streams), K submitting threads taking calls from one queue.  A call
+            # of 1024 one-segment thumbnails is 1024 serial chains -- a fraction of the machine -- so calls overlap on the
+            # device; ctypes releases the GIL for the duration of a call
+            K = max(1, min(args.streams, len(handles)))
+            codecs = [fc] + [LeptonB200FileCodec(local_rank, host_threads=max(1, threads // K)) for _ in range(K - 1)]
+            for cdc in codecs[1:]:
+                cdc.decompress(handles[0], copy=False)           # warm-up of every codec (arenas)
+            barrier()
             lat = []
-            l0 = fc.kernel_launches
-            t0 = time.perf_counter()
+            l0 = sum(cdc.kernel_launches for cdc in codecs)
+            import queue
+            q = queue.Queue()
             for h in handles:
-                t1 = time.perf_counter()
-                fc.decompress(h, copy=False)
-                lat.append(time.perf_counter() - t1)
+                q.put(h)
+            lock = threading.Lock()
+
+            def serve(cdc):
+                while True:
+                    try:
+                        h = q.get_nowait()
+                    except queue.Empty:
+                        return
+                    t1 = time.perf_counter()
+                    cdc.decompress(h, copy=False)
+                    d1 = time.perf_counter() - t1
+                    with lock:
+                        lat.append(d1)
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=serve, args=(cdc,)) for cdc in codecs]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
             barrier()
             dt = rmax(time.perf_counter() - t0)
+            nlaunch = sum(cdc.kernel_launches for cdc in codecs) - l0
+            for cdc in codecs[1:]:
+                cdc.close()
             lat.sort()
             total_jpeg = rsum(jpeg_bytes)
             v = total_jpeg / dt / 1e6
-            line.update(value=v, ms_per_step=1e3 * dt, clocks=sampler.stop(), gpu_launches=int(fc.kernel_launches - l0),
+            line.update(value=v, ms_per_step=1e3 * dt, clocks=sampler.stop(), gpu_launches=int(nlaunch),
                         images_per_s=rsum(args.images) / dt,
                         latency={"p50_ms": 1e3 * lat[len(lat) // 2], "p90_ms": 1e3 * lat[(len(lat) * 9) // 10], "max_ms": 1e3 * lat[-1],
-                                 "files_per_call": nb, "calls": len(lat),
+                                 "files_per_call": nb, "calls": len(lat), "calls_in_flight": K,
                                  "note": "per-image latency = latency of the call that carries the image (one serial chain per thumbnail)"},
                         e2e={"value": v, "unit": "MB/s", "h2d_bytes_per_step": int(sum(len(b) for b in leps)), "d2h_bytes_per_step": int(jpeg_bytes),
                              "api": "lepb200_decompress_leps (.lep bytes -> JPEG bytes, host memory)", "host_threads": threads},
