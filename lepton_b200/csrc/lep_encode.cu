@@ -49,6 +49,12 @@ struct EncWarpSmem {
     int16_t rast[5 * 64];     // raster-order copies: three rotating buffers (A, B, left neighbour of A) + above A, above B
     int32_t tmp[2 * 64];      // IDCT intermediates of A and B
     int16_t pix[2 * 64];      // IDCT outputs (pixels sans DC) of A and B
+    // per-component tables of the image, copied at every row start: the IDCT, the Lakhani predictors and the threshold
+    // contexts read them per block, and as loads from the image descriptor in global memory they accounted for a tenth of
+    // the kernel's stall samples (profiles/r02_shipped_kernelA_by_line.txt: lep_encode.cu lines 154, 230, 513)
+    int32_t icx[64], icy[64]; // model.hh:254-255
+    uint16_t qtab[64];        // quantisation table, raster order
+    uint8_t mthr[64];         // model.hh:277-289
 };
 
 // (the CTA's shared memory is declared as separate arrays inside the kernel: members of one struct reached through a
@@ -317,7 +323,17 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
             const uint32_t* plane = reinterpret_cast<const uint32_t*>(g.plane[c]);
             const uint32_t* rowp = plane + (size_t)y * w * 32;
             const uint32_t* abovep = rowp - (size_t)w * 32;
-            const uint16_t* q = g.q[c];
+            {
+                const uint32_t* gq = reinterpret_cast<const uint32_t*>(g.q[c]);
+                const uint32_t* gm = reinterpret_cast<const uint32_t*>(g.min_thr[c]);
+                __syncwarp();
+                reinterpret_cast<uint32_t*>(ws.qtab)[lane] = gq[lane];
+                if (lane < 16) reinterpret_cast<uint32_t*>(ws.mthr)[lane] = gm[lane];
+                ws.icx[lane] = g.icos_x[c][lane]; ws.icx[32 + lane] = g.icos_x[c][32 + lane];
+                ws.icy[lane] = g.icos_y[c][lane]; ws.icy[32 + lane] = g.icos_y[c][32 + lane];
+                __syncwarp();
+            }
+            const uint16_t* q = ws.qtab;
             const int q0 = q[0];
             int16_t* redge = reinterpret_cast<int16_t*>(rowbuf + (size_t)(c == 0 ? 0 : (c == 1 ? bw0 : bw0 + bw1)) * 16);
             uint8_t* rnz = rowbuf + nz_base + (c == 0 ? 0 : (c == 1 ? nzs0 : nzs0 + nzs1));
@@ -405,7 +421,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                 const int ne_h = __popc(hm), ne_v = __popc(vm);
                 int eprior = 0;
                 if (act_h && ((is_h && has_above) || (is_v && has_left_h)))        // one pass for both edges of both blocks
-                    eprior = lak_pred_at(ws, rcur, is_h ? rabove : rleft, (is_h ? g.icos_x[c] : g.icos_y[c]) + ek * 8, ecoord, is_h ? 8 : 1);
+                    eprior = lak_pred_at(ws, rcur, is_h ? rabove : rleft, (is_h ? ws.icx : ws.icy) + ek * 8, ecoord, is_h ? 8 : 1);
                 const uint32_t lt16 = (1u << l) - 1;
                 const int ne_rem = is_h ? ne_h - __popc(hm & lt16) : ne_v - __popc(vm & ((lt16 >> 8) & 0x7f));
                 const bool ecoded = (is_h || is_v) && ne_rem > 0;
@@ -508,7 +524,7 @@ lep_encode_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__ se
                         const int bsr = bitlen((uint32_t)min(iabs(eprior), 1023));
                         const int p16 = (int)(int16_t)eprior;                           // sign_array_8: int16 truncation (model.hh:1116)
                         const int sctx = p16 == 0 ? 0 : (p16 > 0 ? 1 : 2);
-                        const int min_thr = g.min_thr[c][ecoord];
+                        const int min_thr = ws.mthr[ecoord];
                         uint32_t w3 = 15u << 20;
                         if (elen - 2 >= min_thr) {
                             const int ctx_abs = iabs(eprior) & 0xffff;                  // uint16_t ctx_abs (model.hh:1079)
