@@ -429,7 +429,7 @@ def main():
         dec_s = rmax(sum(dms) / 1e3)
         avg_d_s = (sum(dms) / len(dms)) / 1e3
         dmode = int(os.environ.get("LEPB200_DEC_MODE", "0"))
-        group = dmode == 2 or (dmode == 0 and nseg >= int(os.environ.get("LEPB200_DEC_GROUP_MIN", "12288")))
+        group = dmode == 2 or (dmode == 0 and nseg >= int(os.environ.get("LEPB200_DEC_GROUP_MIN", "10240")))
         dec_kernel = ("lep_decode_g2_kernel<%s> (group kernel: %s lanes per thread-segment, lock step)" % ((os.environ.get("LEPB200_DEC_LANES", "4"),) * 2)
                       if group else "lep_decode_kernel (one warp per thread-segment)")
         dec = {"value": total_jpeg * args.steps / dec_s / 1e6, "unit": "MB/s", "ms_per_step": 1e3 * dec_s / args.steps,

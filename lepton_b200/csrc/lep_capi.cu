@@ -101,7 +101,7 @@ struct lepb200_ctx {
     int dec_mode = 0;                     // decode kernel: 0 = by batch size (group kernel when at least dec_group_min segments are in the
                                           // batch, else one warp per segment), 1 = always one warp per segment (lep_decode.cu),
                                           // 2 = always the group kernel (lep_decode_g2.cu)
-    int dec_group_min = 12288;            // the group kernel carries 8 serial chains per warp: fewer instructions per decision, but a
+    int dec_group_min = 10240;            // the group kernel carries 8 serial chains per warp: fewer instructions per decision, but a
                                           // longer latency per chain -- it wins when the chains alone fill the machine (measured: 16 384
                                           // segments 1043 ms against 1620 ms; 4 096 segments 1000 ms against 510 ms)
     int dec_threads_max = 16384;          // group kernel: segments per launch (one zero-filled 1.58 MB model each)

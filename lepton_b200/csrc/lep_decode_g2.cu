@@ -89,7 +89,9 @@ __device__ __forceinline__ uint32_t g2_get(G2Bool& r, uint16_t* model, const uin
     return bit;
 }
 #ifdef LEPB200_EMU
-#define G2_EMU_BARRIER() __syncwarp()      // CPU warp emulator: lanes run one after the other, reads of a group before its first write-back
+#define G2_EMU_BARRIER() __syncwarp()      // CPU warp emulator only: lanes run one after the other there, so the lanes of a group must
+                                           // all have read a branch word before the first of them writes it back (fixed-length count loops;
+                                           // the coefficient loops vote once per decision, which orders them the same way)
 #else
 #define G2_EMU_BARRIER()
 #endif
@@ -326,15 +328,25 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
         }
         __syncwarp();
 
-        // ---- (2a) the 7x7 non-zero count: six decisions, every live group in step (decoder.cc:175-184)
+        // ---- (2a) the 7x7 non-zero count: six decisions, every live group in step (decoder.cc:175-184).  The branch word of
+        //      the next level is requested as soon as this level's bit is known, before the write-back.
         {
-            uint32_t prefix = 0;
+            uint32_t prefix = 0, a = cnt_addr + (5u << 5);
+            uint32_t mw = alive ? model[a] : 0u;
+            G2_EMU_BARRIER();
 #pragma unroll 1
             for (int idx = 5; idx >= 0; --idx) {
-                const uint32_t a = cnt_addr + ((uint32_t)idx << 5) + prefix;
-                const uint32_t mw = alive ? model[a] : 0u;
+                uint32_t split = 0, bit = 0;
+                if (alive) bit = g2_bit(br, s_rcp, mw, split);
+                const uint32_t na = cnt_addr + ((uint32_t)max(idx - 1, 0) << 5) + ((prefix << 1) | bit);
+                const uint32_t mwn = (alive && idx > 0) ? model[na] : 0u;
                 G2_EMU_BARRIER();
-                if (alive) prefix = (prefix << 1) | g2_get(br, model, s_rcp, a, mw);
+                if (alive) {
+                    model[a] = (uint16_t)g2_model_word(mw, bit);
+                    g2_update(br, split, bit);
+                    prefix = (prefix << 1) | bit;
+                }
+                a = na; mw = mwn;
             }
             nz = (int)prefix;
             if (alive) nd += 6;
@@ -343,29 +355,38 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
         if (alive && nz > 49) { bad = true; alive = false; }
 
         // ---- (2b) the 7x7 coefficients in zig-zag order (== aligned order 0..48) until the announced count is used up.
-        //      One decision per live group and round.  The transition to the next decision is straight-line code (no
-        //      divergence between groups that stand in different states), and the next decision's branch word is
-        //      requested as soon as its address is known -- before this decision's write-back and bookkeeping, which
-        //      then run in the shadow of the load.  (Consecutive decisions never use the same branch, except for the
-        //      saturated threshold index of the edge loop; the forwarding line covers every such case.)
+        //      One decision per live group and round.  What sits on the serial chain of a group is only: branch word ->
+        //      probability -> split -> compare -> SELECT of the next branch address -> load.  The two candidate addresses
+        //      (next decision if this bit is 0 / if it is 1) are prepared from the grammar state BEFORE the bit is known,
+        //      in the shadow of the previous load, together with the write-back, the window update and the state update
+        //      (straight-line code: groups in different states share every instruction).  Consecutive decisions never use
+        //      the same branch, except for the saturated threshold index of the edge loop; the forwarding line covers it.
         {
             int zz = 0, left_nz = nz, st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
-            uint32_t addr = 0;
-            bool busy = alive && nz > 0;
+            uint32_t addr = 0, a0 = 0, a1 = 0;
+            bool busy = alive && nz > 0, b0 = busy, b1 = busy;
+            const uint32_t sign_addr = m_sign(ci, 0, 0);
             if (busy) {
                 const uint32_t eb = s_eb[ci][left_nz];
                 addr = eb + eoff[0];
-#pragma unroll
-                for (int k = 1; k <= G2_PF_DIST; ++k) g2_prefetch(model + eb + eoff[k]);        // positions 0..3 always exist
+                a1 = addr + 1; a0 = eb + eoff[1];          // after the first exponent bit of position 0
             }
-            const uint32_t sign_addr = m_sign(ci, 0, 0);
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
                 if (busy) {
+                    // ---- on the chain
                     uint32_t split;
                     const uint32_t bit = g2_bit(br, s_rcp, mw, split);
-                    // ---- transition
+                    const uint32_t naddr = bit ? a1 : a0;
+                    const bool nbusy = bit ? b1 : b0;
+                    uint32_t mwn = nbusy ? model[naddr] : 0u;
+                    // ---- in the shadow of that load: write-back, window, grammar state, decoded value
+                    const uint32_t neww = g2_model_word(mw, bit);
+                    model[addr] = (uint16_t)neww;                  // all lanes of the group store the same value
+                    if (naddr == addr) mwn = neww;
+                    g2_update(br, split, bit);
+                    ++nd;
                     const int isE = st == G2_EXP, isS = st == G2_SIGN, isR = st == G2_RES;
                     const int cont = isE & (int)bit & (int)(len < 10);               // exponent goes on
                     const int len1 = len + (isE & (int)bit);
@@ -373,39 +394,32 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                     const int toS = isE & (cont ^ 1) & (int)(len1 != 0);
                     const int ris = len - 2;                                          // sign state: first residual bit
                     const int evS = isS & (int)(ris < 0), toR = isS & (int)(ris >= 0);
-                    const int evR = isR & (int)(ri == 0), contR = isR & (int)(ri != 0);
+                    const int evR = isR & (int)(ri == 0);
                     const int evN = evS | evR, ev = ev0 | evN;                        // a (non-zero) coefficient is complete
                     const int nval = isS ? (1 << ((len - 1) & 31)) : (isR ? (val | ((int)bit << (ri & 31))) : val);
                     const bool nneg = isS ? !bit : neg;
-                    const int coord = s_a2r[zz];
-                    const uint32_t rbase = m_resn(ci, coord, s_nzbin[left_nz]);
-                    const int nleft = left_nz - evN, nzz = zz + ev;
-                    const int done = ev & (int)((nleft == 0) | (nzz == 49));
-                    const uint32_t eb = s_eb[ci][nleft];
-                    const uint32_t naddr = cont ? addr + 1 : toS ? sign_addr : toR ? rbase + (uint32_t)ris : contR ? addr - 1 : eb + eoff[min(nzz, 48)];
-                    const bool nbusy = !done;
-                    // ---- the next decision's branch word
-                    uint32_t mwn = nbusy ? model[naddr] : 0u;
-                    // ---- in its shadow: write-back, window, the decoded value, requests for later positions
-                    const uint32_t neww = g2_model_word(mw, bit);
-                    model[addr] = (uint16_t)neww;                  // all lanes of the group store the same value
-                    if (naddr == addr) mwn = neww;
-                    g2_update(br, split, bit);
-                    ++nd;
-                    if (evN && sub == 0) rcur[coord] = (int16_t)(nneg ? -nval : nval);
-                    if (isE & (int)bit & (int)(len == 0)) {       // non-zero: residual bits may follow, and the positions after it see one coefficient less
-                        g2_prefetch(model + rbase);
-                        const uint32_t eb1 = s_eb[ci][left_nz - 1];
-                        if (eb1 != s_eb[ci][left_nz] && left_nz > 1) {
-#pragma unroll
-                            for (int k = 1; k <= G2_PF_DIST; ++k) if (zz + k < 49) g2_prefetch(model + eb1 + eoff[zz + k]);
-                        }
-                    }
-                    if (ev && nzz + G2_PF_DIST < 49) g2_prefetch(model + eb + eoff[nzz + G2_PF_DIST]);
+                    if (evN && sub == 0) rcur[s_a2r[zz]] = (int16_t)(nneg ? -nval : nval);
+                    left_nz -= evN; zz += ev;
                     st = toS ? G2_SIGN : toR ? G2_RES : ev ? G2_EXP : st;
                     len = ev ? 0 : len1;
                     ri = isS ? ris : ri - isR;
-                    val = nval; neg = nneg; left_nz = nleft; zz = nzz; addr = naddr; busy = nbusy; mw = mwn;
+                    val = nval; neg = nneg; addr = naddr; busy = nbusy; mw = mwn;
+                    // ---- candidates of the decision after the one just requested
+                    if (busy) {
+                        const int zn = min(zz + 1, 48);
+                        const bool lastpos = zz == 48;
+                        const bool doneN = left_nz == 1 || lastpos;              // after the non-zero coefficient in progress
+                        const uint32_t nextN = s_eb[ci][left_nz - 1] + eoff[zn];
+                        const bool inE = st == G2_EXP, inS = st == G2_SIGN;
+                        const bool fin = inS ? len < 2 : ri == 0;                // the coming decision completes the coefficient
+                        const uint32_t cont_a = inS ? m_resn(ci, s_a2r[zz], s_nzbin[left_nz]) + (uint32_t)(len - 2) : addr - 1;
+                        const uint32_t common = fin ? nextN : cont_a;
+                        const bool commonB = fin ? !doneN : true;
+                        a1 = inE ? (len < 10 ? addr + 1 : sign_addr) : common;
+                        a0 = inE ? (len == 0 ? s_eb[ci][left_nz] + eoff[zn] : sign_addr) : common;
+                        b1 = inE ? true : commonB;
+                        b0 = inE ? (len == 0 ? !lastpos : true) : commonB;
+                    }
                 }
             }
         }
@@ -450,35 +464,55 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
             int ne = 0;
             {
                 const uint32_t base = m_nze(vert, ci, vert ? eoby : eobx, (nz + 3) / 7, 0, 0);
-                uint32_t prefix = 0;
+                uint32_t prefix = 0, a = base + (2u << 2);
+                uint32_t mw = alive ? model[a] : 0u;
+                G2_EMU_BARRIER();
 #pragma unroll 1
                 for (int idx = 2; idx >= 0; --idx) {
-                    const uint32_t a = base + ((uint32_t)idx << 2) + prefix;
-                    const uint32_t mw = alive ? model[a] : 0u;
+                    uint32_t split = 0, bit = 0;
+                    if (alive) bit = g2_bit(br, s_rcp, mw, split);
+                    const uint32_t na = base + ((uint32_t)max(idx - 1, 0) << 2) + ((prefix << 1) | bit);
+                    const uint32_t mwn = (alive && idx > 0) ? model[na] : 0u;
                     G2_EMU_BARRIER();
-                    if (alive) prefix = (prefix << 1) | g2_get(br, model, s_rcp, a, mw);
+                    if (alive) {
+                        model[a] = (uint16_t)g2_model_word(mw, bit);
+                        g2_update(br, split, bit);
+                        prefix = (prefix << 1) | bit;
+                    }
+                    a = na; mw = mwn;
                 }
                 ne = (int)prefix;
                 if (alive) nd += 3;
             }
             int ln = 0, st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
-            uint32_t addr = 0, e = 0, so = 1, thr_base = 0;
+            uint32_t addr = 0, e = 0, so = 1, thr_base = 0, a0 = 0, a1 = 0;
             const uint32_t expx_base = M_EXPX + (uint32_t)((ci * 8) * 15 * 12 * 16) + (uint32_t)(vert * 7 * 12 * 16);
             const uint32_t sign_base = M_SIGN + (uint32_t)(ci * 48);
             const int cstep = vert ? 8 : 1;                       // raster distance between the coefficients of this edge
-            bool busy = alive && ne > 0;
+            constexpr uint32_t NE_STRIDE = 15 * 12 * 16;          // exponent contexts of one remaining-count value
+            bool busy = alive && ne > 0, b0 = busy, b1 = busy;
             if (busy) {
                 e = einfo[vert * 7];
-                addr = expx_base + (uint32_t)(ne * (15 * 12 * 16)) + ((e & 15u) << 4);
-                g2_prefetch(model + expx_base + (uint32_t)(ne * (15 * 12 * 16)) + (uint32_t)(12 * 16) + ((einfo[vert * 7 + 1] & 15u) << 4));
+                addr = expx_base + (uint32_t)ne * NE_STRIDE + ((e & 15u) << 4);
+                a1 = addr + 1;
+                a0 = expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(12 * 16) + ((einfo[vert * 7 + 1] & 15u) << 4);
             }
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
                 if (busy) {
+                    // ---- on the chain (see the 7x7 loop)
                     uint32_t split;
                     const uint32_t bit = g2_bit(br, s_rcp, mw, split);
-                    // ---- transition (straight-line; see the 7x7 loop)
+                    const uint32_t naddr = bit ? a1 : a0;
+                    const bool nbusy = bit ? b1 : b0;
+                    uint32_t mwn = nbusy ? model[naddr] : 0u;
+                    // ---- in the shadow of that load
+                    const uint32_t neww = g2_model_word(mw, bit);
+                    model[addr] = (uint16_t)neww;
+                    if (naddr == addr) mwn = neww;                 // saturated threshold index: the same branch twice in a row
+                    g2_update(br, split, bit);
+                    ++nd;
                     const int isE = st == G2_EXP, isS = st == G2_SIGN, isT = st == G2_THR, isR = st == G2_RES;
                     const int cont = isE & (int)bit & (int)(len < 10);
                     const int len1 = len + (isE & (int)bit);
@@ -489,40 +523,44 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                     const int evS = isS & (int)(ris < 0);
                     const int toT = isS & (int)(ris >= 0) & (int)(ris >= mt), toRs = isS & (int)(ris >= 0) & (int)(ris < mt);
                     const int rit = ri - 1;                                           // threshold / residual states: next bit
-                    const int evT = isT & (int)(ri == 0), contT = isT & (int)(ri != 0) & (int)(rit >= mt), toRt = isT & (int)(ri != 0) & (int)(rit < mt);
-                    const int evR = isR & (int)(ri == 0), contR = isR & (int)(ri != 0);
+                    const int evT = isT & (int)(ri == 0), toRt = isT & (int)(ri != 0) & (int)(rit < mt);
+                    const int evR = isR & (int)(ri == 0);
                     const int evN = evS | evT | evR, ev = ev0 | evN;
                     const int nval = isS ? (1 << ((len - 1) & 31)) : ((isT | isR) ? (val | ((int)bit << (ri & 31))) : val);
                     const bool nneg = isS ? !bit : neg;
-                    const uint32_t nso = isT ? min((so << 1) | bit, 127u) : 1u;
-                    const uint32_t nthr = isS ? m_thr(ci, (int)((e >> 9) & 255u), min(len - mt, 7)) : thr_base;
-                    const int coord = (ln + 1) * cstep;
-                    const uint32_t rbase = m_resn(ci, coord, ne);
-                    const uint32_t sa = sign_base + ((e >> 4) & 3u) * 12u + (e & 15u);
-                    const int nne = ne - evN, nln = ln + ev;
-                    const int done = ev & (int)((nne == 0) | (nln == 7));
-                    const uint32_t en = einfo[vert * 7 + min(nln, 6)];
-                    const uint32_t nexta = expx_base + (uint32_t)(nne * (15 * 12 * 16)) + (uint32_t)(nln * (12 * 16)) + ((en & 15u) << 4);
-                    const uint32_t naddr = cont ? addr + 1 : toS ? sa : toT ? nthr + 1 : toRs ? rbase + (uint32_t)ris : contT ? nthr + nso
-                                         : toRt ? rbase + (uint32_t)rit : contR ? addr - 1 : nexta;
-                    const bool nbusy = !done;
-                    // ---- the next decision's branch word, then everything that is off the chain
-                    uint32_t mwn = nbusy ? model[naddr] : 0u;
-                    const uint32_t neww = g2_model_word(mw, bit);
-                    model[addr] = (uint16_t)neww;
-                    if (naddr == addr) mwn = neww;                 // saturated threshold index: the same branch twice in a row
-                    g2_update(br, split, bit);
-                    ++nd;
-                    if (evN && sub == 0) rcur[coord] = (int16_t)(nneg ? -nval : nval);
-                    if (isE & (int)bit & (int)(len == 0) & (int)(ne > 1) & (int)(ln < 6))      // non-zero: the next position sees one coefficient less
-                        g2_prefetch(model + expx_base + (uint32_t)((ne - 1) * (15 * 12 * 16)) + (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + ln + 1] & 15u) << 4));
-                    if (toS && len1 >= 2) g2_prefetch(model + (len1 - 2 >= mt ? m_thr(ci, (int)((e >> 9) & 255u), min(len1 - mt, 7)) : rbase));
-                    if (ev && !done && nln < 6) g2_prefetch(model + expx_base + (uint32_t)(nne * (15 * 12 * 16)) + (uint32_t)((nln + 1) * (12 * 16)) + ((einfo[vert * 7 + nln + 1] & 15u) << 4));
+                    if (evN && sub == 0) rcur[(ln + 1) * cstep] = (int16_t)(nneg ? -nval : nval);
+                    so = isT ? min((so << 1) | bit, 127u) : 1u;
+                    thr_base = isS ? m_thr(ci, (int)((e >> 9) & 255u), min(len - mt, 7)) : thr_base;
+                    ne -= evN; ln += ev;
+                    if (ev) e = einfo[vert * 7 + min(ln, 6)];
                     st = toS ? G2_SIGN : toT ? G2_THR : (toRs | toRt) ? G2_RES : ev ? G2_EXP : st;
                     len = ev ? 0 : len1;
                     ri = isS ? ris : ri - (isT | isR);
-                    val = nval; neg = nneg; so = nso; thr_base = nthr; ne = nne; ln = nln; e = ev ? en : e;
-                    addr = naddr; busy = nbusy; mw = mwn;
+                    val = nval; neg = nneg; addr = naddr; busy = nbusy; mw = mwn;
+                    // ---- candidates of the decision after the one just requested
+                    if (busy) {
+                        const int mt2 = (int)((e >> 6) & 7u);
+                        const bool lastpos = ln == 6;
+                        const bool doneN = ne == 1 || lastpos;                   // after the non-zero coefficient in progress
+                        const uint32_t nxt = (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + min(ln + 1, 6)] & 15u) << 4);
+                        const uint32_t nextN = expx_base + (uint32_t)(ne - 1) * NE_STRIDE + nxt;
+                        const uint32_t rb = m_resn(ci, (ln + 1) * cstep, ne);
+                        const bool inE = st == G2_EXP, inS = st == G2_SIGN, inT = st == G2_THR;
+                        const int r2 = inS ? len - 2 : ri - 1;                   // bit index of the decision after the coming one
+                        const bool fin = r2 < 0;                                 // the coming decision completes the coefficient
+                        const bool thr = r2 >= mt2 && (inS || inT);              // ... or it is followed by a threshold bit
+                        const uint32_t tb = inS ? m_thr(ci, (int)((e >> 9) & 255u), min(len - mt2, 7)) : thr_base;
+                        const uint32_t so0 = inS ? 1u : min(so << 1, 127u), so1 = inS ? 1u : min((so << 1) | 1u, 127u);
+                        const uint32_t rest = (inS || inT) ? rb + (uint32_t)r2 : addr - 1;        // residual bit after sign / threshold, or the next one down
+                        const uint32_t c0 = fin ? nextN : thr ? tb + so0 : rest;
+                        const uint32_t c1 = fin ? nextN : thr ? tb + so1 : rest;
+                        const bool cb = fin ? !doneN : true;
+                        const uint32_t sa = sign_base + ((e >> 4) & 3u) * 12u + (e & 15u);
+                        a1 = inE ? (len < 10 ? addr + 1 : sa) : c1;
+                        a0 = inE ? (len == 0 ? expx_base + (uint32_t)ne * NE_STRIDE + nxt : sa) : c0;
+                        b1 = inE ? true : cb;
+                        b0 = inE ? (len == 0 ? !lastpos : true) : cb;
+                    }
                 }
             }
         }
@@ -601,42 +639,49 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
             }
         }
 
-        // ---- (6) the DC coefficient: exponent / sign / residual bits (decoder.cc:286-304), pipelined like the loops above
+        // ---- (6) the DC coefficient: exponent / sign / residual bits (decoder.cc:286-304), same scheme
         int dcv = 0;
         {
             int st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
-            uint32_t addr = dc_exp;
-            bool busy = alive;
+            uint32_t addr = dc_exp, a0 = dc_exp, a1 = dc_exp + 1;
+            bool busy = alive, b0 = false, b1 = busy;
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
                 if (busy) {
                     uint32_t split;
                     const uint32_t bit = g2_bit(br, s_rcp, mw, split);
-                    const int isE = st == G2_EXP, isS = st == G2_SIGN, isR = st == G2_RES;
-                    const int cont = isE & (int)bit & (int)(len < 10);
-                    const int len1 = len + (isE & (int)bit);
-                    const int ev0 = isE & (cont ^ 1) & (int)(len1 == 0);
-                    const int toS = isE & (cont ^ 1) & (int)(len1 != 0);
-                    const int ris = len - 2;
-                    const int evS = isS & (int)(ris < 0), toR = isS & (int)(ris >= 0);
-                    const int evR = isR & (int)(ri == 0), contR = isR & (int)(ri != 0);
-                    const int evN = evS | evR, ev = ev0 | evN;
-                    const int nval = isS ? (1 << ((len - 1) & 31)) : (isR ? (val | ((int)bit << (ri & 31))) : val);
-                    const bool nneg = isS ? !bit : neg;
-                    const uint32_t naddr = cont ? addr + 1 : toS ? dc_sign : toR ? dc_res + (uint32_t)ris : contR ? addr - 1 : addr;
-                    const bool nbusy = !ev;
+                    const uint32_t naddr = bit ? a1 : a0;
+                    const bool nbusy = bit ? b1 : b0;
                     uint32_t mwn = nbusy ? model[naddr] : 0u;
                     const uint32_t neww = g2_model_word(mw, bit);
                     model[addr] = (uint16_t)neww;
                     if (naddr == addr) mwn = neww;
                     g2_update(br, split, bit);
                     ++nd;
-                    if (evN) dcv = nneg ? -nval : nval;
+                    const int isE = st == G2_EXP, isS = st == G2_SIGN, isR = st == G2_RES;
+                    const int cont = isE & (int)bit & (int)(len < 10);
+                    const int len1 = len + (isE & (int)bit);
+                    const int toS = isE & (cont ^ 1) & (int)(len1 != 0);
+                    const int ris = len - 2;
+                    const int evS = isS & (int)(ris < 0), toR = isS & (int)(ris >= 0);
+                    const int evR = isR & (int)(ri == 0);
+                    const int nval = isS ? (1 << ((len - 1) & 31)) : (isR ? (val | ((int)bit << (ri & 31))) : val);
+                    const bool nneg = isS ? !bit : neg;
+                    if (evS | evR) dcv = nneg ? -nval : nval;
                     st = toS ? G2_SIGN : toR ? G2_RES : st;
                     len = len1;
                     ri = isS ? ris : ri - isR;
                     val = nval; neg = nneg; addr = naddr; busy = nbusy; mw = mwn;
+                    if (busy) {
+                        const bool inE = st == G2_EXP, inS = st == G2_SIGN;
+                        const bool fin = inS ? len < 2 : ri == 0;
+                        const uint32_t common = inS ? dc_res + (uint32_t)(len - 2) : addr - 1;
+                        a1 = inE ? (len < 10 ? addr + 1 : dc_sign) : common;
+                        a0 = inE ? dc_sign : common;
+                        b1 = inE ? true : !fin;
+                        b0 = inE ? len != 0 : !fin;
+                    }
                 }
             }
         }
