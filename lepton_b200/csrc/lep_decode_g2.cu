@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t g2_get(G2Bool& r, uint16_t* model, const uin
 // model lines alive, far more than the L2 holds, so a demand load is a DRAM round trip on the serial chain).
 // G2_PF_DIST: how many coefficients ahead of the one being decoded.
 #ifndef LEPB200_G2_PREFETCH
-#define LEPB200_G2_PREFETCH 0        // measured on the 4096-image batch: 1043 ms without, 1054 ms with L1 or L2 requests
+#define LEPB200_G2_PREFETCH 0
 #endif
 #if LEPB200_G2_PREFETCH == 1 && !defined(LEPB200_EMU)
 __device__ __forceinline__ void g2_prefetch(const uint16_t* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -371,6 +371,8 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                 const uint32_t eb = s_eb[ci][left_nz];
                 addr = eb + eoff[0];
                 a1 = addr + 1; a0 = eb + eoff[1];          // after the first exponent bit of position 0
+#pragma unroll
+                for (int k = 1; k <= G2_PF_DIST; ++k) g2_prefetch(model + eb + eoff[k]);        // positions 0..5 always exist
             }
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
@@ -399,6 +401,17 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                     const int nval = isS ? (1 << ((len - 1) & 31)) : (isR ? (val | ((int)bit << (ri & 31))) : val);
                     const bool nneg = isS ? !bit : neg;
                     if (evN && sub == 0) rcur[s_a2r[zz]] = (int16_t)(nneg ? -nval : nval);
+#if LEPB200_G2_PREFETCH
+                    if (isE & (int)bit & (int)(len == 0)) {       // non-zero: residual bits may follow, and the positions after it see one coefficient less
+                        g2_prefetch(model + m_resn(ci, s_a2r[zz], s_nzbin[left_nz]));
+                        const uint32_t eb1 = s_eb[ci][left_nz - 1];
+                        if (eb1 != s_eb[ci][left_nz] && left_nz > 1) {
+#pragma unroll
+                            for (int k = 1; k <= G2_PF_DIST; ++k) if (zz + k < 49) g2_prefetch(model + eb1 + eoff[zz + k]);
+                        }
+                    }
+                    if (ev && zz + 1 + G2_PF_DIST < 49) g2_prefetch(model + s_eb[ci][left_nz - evN] + eoff[zz + 1 + G2_PF_DIST]);
+#endif
                     left_nz -= evN; zz += ev;
                     st = toS ? G2_SIGN : toR ? G2_RES : ev ? G2_EXP : st;
                     len = ev ? 0 : len1;
@@ -497,6 +510,8 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                 addr = expx_base + (uint32_t)ne * NE_STRIDE + ((e & 15u) << 4);
                 a1 = addr + 1;
                 a0 = expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(12 * 16) + ((einfo[vert * 7 + 1] & 15u) << 4);
+                g2_prefetch(model + a0);
+                g2_prefetch(model + expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(2 * 12 * 16) + ((einfo[vert * 7 + 2] & 15u) << 4));
             }
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
@@ -529,6 +544,14 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                     const int nval = isS ? (1 << ((len - 1) & 31)) : ((isT | isR) ? (val | ((int)bit << (ri & 31))) : val);
                     const bool nneg = isS ? !bit : neg;
                     if (evN && sub == 0) rcur[(ln + 1) * cstep] = (int16_t)(nneg ? -nval : nval);
+#if LEPB200_G2_PREFETCH
+                    if (isE & (int)bit & (int)(len == 0) & (int)(ne > 1)) {      // non-zero: the next positions see one coefficient less
+                        if (ln < 6) g2_prefetch(model + expx_base + (uint32_t)(ne - 1) * NE_STRIDE + (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + ln + 1] & 15u) << 4));
+                        if (ln < 5) g2_prefetch(model + expx_base + (uint32_t)(ne - 1) * NE_STRIDE + (uint32_t)((ln + 2) * (12 * 16)) + ((einfo[vert * 7 + ln + 2] & 15u) << 4));
+                    }
+                    if (toS && len1 >= 2) g2_prefetch(model + (len1 - 2 >= mt ? m_thr(ci, (int)((e >> 9) & 255u), min(len1 - mt, 7)) : m_resn(ci, (ln + 1) * cstep, ne)));
+                    if (ev && ln + 3 < 7 && ne - evN > 0) g2_prefetch(model + expx_base + (uint32_t)(ne - evN) * NE_STRIDE + (uint32_t)((ln + 3) * (12 * 16)) + ((einfo[vert * 7 + ln + 3] & 15u) << 4));
+#endif
                     so = isT ? min((so << 1) | bit, 127u) : 1u;
                     thr_base = isS ? m_thr(ci, (int)((e >> 9) & 255u), min(len - mt, 7)) : thr_base;
                     ne -= evN; ln += ev;
