@@ -52,14 +52,7 @@ constexpr uint32_t M_EXPX = M_EXP7 + 2 * 10 * 49 * 12 * 16;          // [2][8][1
 constexpr uint32_t M_EXPDC = M_EXPX + 2 * 8 * 15 * 12 * 16;          // [12][17][16]
 constexpr uint32_t M_SIGN = M_EXPDC + 12 * 17 * 16;                  // [2][4][12] (+pad)
 constexpr uint32_t M_THR = M_SIGN + 128;                             // [2][256][8][128]
-// First exponent bit ("is the coefficient non-zero") of EVERY exponent context, packed densely: one word per context, in
-// the order of the contexts of M_EXP7 | M_EXPX | M_EXPDC (which are contiguous).  Two thirds of the coded coefficients are
-// zero and take exactly this one decision; with the bit inside its context's 32-byte row every visited position costs a
-// row of its own (~55 distinct sectors per block), while here the 12 prior classes of a position share 24 bytes and five
-// neighbouring positions a 128-byte line.  Entry 0 of the rows themselves is unused.
-constexpr uint32_t M_E0 = M_THR + 2 * 256 * 8 * 128;                 // [(M_SIGN - M_EXP7) / 16]
-constexpr uint32_t M_E0_COUNT = (M_SIGN - M_EXP7) / 16;
-constexpr uint32_t M_TOTAL = (M_E0 + M_E0_COUNT + 7) & ~7u;          // u16 entries
+constexpr uint32_t M_TOTAL = M_THR + 2 * 256 * 8 * 128;              // u16 entries
 static_assert(M_TOTAL < (1u << 20), "branch index must fit in 20 bits");
 static_assert((M_TOTAL % 8) == 0, "model zero fill uses 16-byte stores");
 constexpr size_t MODEL_BYTES = size_t(M_TOTAL) * 2;
@@ -73,9 +66,6 @@ __host__ __device__ inline uint32_t m_nze(int vertical, int ci, int eob, int nzb
 __host__ __device__ inline uint32_t m_resn(int ci, int coord, int bin) { return M_RESN + (((ci * 64 + coord) * 10 + bin) << 4); }
 __host__ __device__ inline uint32_t m_exp7(int ci, int bin, int zz, int bsr) { return M_EXP7 + ((((ci * 10 + bin) * 49 + zz) * 12 + bsr) << 4); }
 __host__ __device__ inline uint32_t m_expx(int ci, int ne, int zig15, int bsr) { return M_EXPX + ((((ci * 8 + ne) * 15 + zig15) * 12 + bsr) << 4); }
-// branch of exponent bit k of the context whose row starts at `base` (m_exp7 / m_expx / m_expdc)
-__host__ __device__ inline uint32_t m_exp_first(uint32_t base) { return M_E0 + ((base - M_EXP7) >> 4); }
-__host__ __device__ inline uint32_t m_exp_bit(uint32_t base, int k) { return k == 0 ? m_exp_first(base) : base + (uint32_t)k; }
 __host__ __device__ inline uint32_t m_resdc(int lenmxm) { return M_RESDC + (lenmxm << 4); }
 __host__ __device__ inline uint32_t m_expdc(int a, int b) { return M_EXPDC + ((a * 17 + b) << 4); }
 __host__ __device__ inline uint32_t m_sign(int ci, int a, int b) { return M_SIGN + (ci * 4 + a) * 12 + b; }

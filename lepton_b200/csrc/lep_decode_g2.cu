@@ -369,10 +369,10 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
             const uint32_t sign_addr = m_sign(ci, 0, 0);
             if (busy) {
                 const uint32_t eb = s_eb[ci][left_nz];
-                addr = m_exp_first(eb + eoff[0]);          // first exponent bit: the dense table (lep_common.cuh)
-                a1 = eb + eoff[0] + 1; a0 = m_exp_first(eb + eoff[1]);          // after the first exponent bit of position 0
+                addr = eb + eoff[0];
+                a1 = addr + 1; a0 = eb + eoff[1];          // after the first exponent bit of position 0
 #pragma unroll
-                for (int k = 1; k <= G2_PF_DIST; ++k) g2_prefetch(model + m_exp_first(eb + eoff[k]));        // positions 0..5 always exist
+                for (int k = 1; k <= G2_PF_DIST; ++k) g2_prefetch(model + eb + eoff[k]);        // positions 0..5 always exist
             }
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
@@ -422,14 +422,14 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                         const int zn = min(zz + 1, 48);
                         const bool lastpos = zz == 48;
                         const bool doneN = left_nz == 1 || lastpos;              // after the non-zero coefficient in progress
-                        const uint32_t nextN = m_exp_first(s_eb[ci][left_nz - 1] + eoff[zn]);
+                        const uint32_t nextN = s_eb[ci][left_nz - 1] + eoff[zn];
                         const bool inE = st == G2_EXP, inS = st == G2_SIGN;
                         const bool fin = inS ? len < 2 : ri == 0;                // the coming decision completes the coefficient
                         const uint32_t cont_a = inS ? m_resn(ci, s_a2r[zz], s_nzbin[left_nz]) + (uint32_t)(len - 2) : addr - 1;
                         const uint32_t common = fin ? nextN : cont_a;
                         const bool commonB = fin ? !doneN : true;
-                        a1 = inE ? (len == 0 ? s_eb[ci][left_nz] + eoff[zz] + 1 : len < 10 ? addr + 1 : sign_addr) : common;
-                        a0 = inE ? (len == 0 ? m_exp_first(s_eb[ci][left_nz] + eoff[zn]) : sign_addr) : common;
+                        a1 = inE ? (len < 10 ? addr + 1 : sign_addr) : common;
+                        a0 = inE ? (len == 0 ? s_eb[ci][left_nz] + eoff[zn] : sign_addr) : common;
                         b1 = inE ? true : commonB;
                         b0 = inE ? (len == 0 ? !lastpos : true) : commonB;
                     }
@@ -507,10 +507,9 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
             bool busy = alive && ne > 0, b0 = busy, b1 = busy;
             if (busy) {
                 e = einfo[vert * 7];
-                const uint32_t base0 = expx_base + (uint32_t)ne * NE_STRIDE + ((e & 15u) << 4);
-                addr = m_exp_first(base0);
-                a1 = base0 + 1;
-                a0 = m_exp_first(expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(12 * 16) + ((einfo[vert * 7 + 1] & 15u) << 4));
+                addr = expx_base + (uint32_t)ne * NE_STRIDE + ((e & 15u) << 4);
+                a1 = addr + 1;
+                a0 = expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(12 * 16) + ((einfo[vert * 7 + 1] & 15u) << 4);
                 g2_prefetch(model + a0);
                 g2_prefetch(model + expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(2 * 12 * 16) + ((einfo[vert * 7 + 2] & 15u) << 4));
             }
@@ -567,7 +566,7 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                         const bool lastpos = ln == 6;
                         const bool doneN = ne == 1 || lastpos;                   // after the non-zero coefficient in progress
                         const uint32_t nxt = (uint32_t)((ln + 1) * (12 * 16)) + ((einfo[vert * 7 + min(ln + 1, 6)] & 15u) << 4);
-                        const uint32_t nextN = m_exp_first(expx_base + (uint32_t)(ne - 1) * NE_STRIDE + nxt);
+                        const uint32_t nextN = expx_base + (uint32_t)(ne - 1) * NE_STRIDE + nxt;
                         const uint32_t rb = m_resn(ci, (ln + 1) * cstep, ne);
                         const bool inE = st == G2_EXP, inS = st == G2_SIGN, inT = st == G2_THR;
                         const int r2 = inS ? len - 2 : ri - 1;                   // bit index of the decision after the coming one
@@ -580,8 +579,8 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                         const uint32_t c1 = fin ? nextN : thr ? tb + so1 : rest;
                         const bool cb = fin ? !doneN : true;
                         const uint32_t sa = sign_base + ((e >> 4) & 3u) * 12u + (e & 15u);
-                        a1 = inE ? (len == 0 ? expx_base + (uint32_t)ne * NE_STRIDE + (uint32_t)(ln * (12 * 16)) + ((e & 15u) << 4) + 1 : len < 10 ? addr + 1 : sa) : c1;
-                        a0 = inE ? (len == 0 ? m_exp_first(expx_base + (uint32_t)ne * NE_STRIDE + nxt) : sa) : c0;
+                        a1 = inE ? (len < 10 ? addr + 1 : sa) : c1;
+                        a0 = inE ? (len == 0 ? expx_base + (uint32_t)ne * NE_STRIDE + nxt : sa) : c0;
                         b1 = inE ? true : cb;
                         b0 = inE ? (len == 0 ? !lastpos : true) : cb;
                     }
@@ -659,7 +658,7 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                 const int lm = min(bitlen((uint32_t)iabs(unc) & 0xffff), 11), lo16 = min(bitlen((uint32_t)iabs(unc2) & 0xffff), 16);
                 const int sctx = unc2 >= 0 ? (unc2 == 0 ? 3 : 2) : 1;
                 dc_exp = m_expdc(lm, lo16); dc_sign = m_sign(ci, 0, sctx); dc_res = m_resdc(lm);
-                g2_prefetch(model + m_exp_first(dc_exp)); g2_prefetch(model + dc_res);
+                g2_prefetch(model + dc_exp); g2_prefetch(model + dc_res);
             }
         }
 
@@ -668,7 +667,7 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
         {
             int st = G2_EXP, len = 0, ri = 0, val = 0;
             bool neg = false;
-            uint32_t addr = m_exp_first(dc_exp), a0 = dc_exp, a1 = dc_exp + 1;
+            uint32_t addr = dc_exp, a0 = dc_exp, a1 = dc_exp + 1;
             bool busy = alive, b0 = false, b1 = busy;
             uint32_t mw = busy ? model[addr] : 0u;
             while (__any_sync(FULL, busy)) {
@@ -701,7 +700,7 @@ lep_decode_g2_kernel(const ImageDesc* __restrict__ images, SegDesc* __restrict__
                         const bool inE = st == G2_EXP, inS = st == G2_SIGN;
                         const bool fin = inS ? len < 2 : ri == 0;
                         const uint32_t common = inS ? dc_res + (uint32_t)(len - 2) : addr - 1;
-                        a1 = inE ? (len == 0 ? dc_exp + 1 : len < 10 ? addr + 1 : dc_sign) : common;
+                        a1 = inE ? (len < 10 ? addr + 1 : dc_sign) : common;
                         a0 = inE ? dc_sign : common;
                         b1 = inE ? true : !fin;
                         b0 = inE ? len != 0 : !fin;

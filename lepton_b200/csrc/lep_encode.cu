@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t expand_item(const uint4 d, int pos) {      /
     if (d.x >> 31) return d.y;
     const int len = (int)((d.x >> 20) & 15u), nexp = min(len + 1, 11);
     const int k = pos - (int)(d.z >> 20);
-    if (k < nexp) return m_exp_bit(d.x & 0xfffffu, k) | ((uint32_t)(len != k) << 31);
+    if (k < nexp) return ((d.x & 0xfffffu) + (uint32_t)k) | ((uint32_t)(len != k) << 31);
     if (k == nexp) return (d.y & 0xfffffu) | (((d.x >> 24) & 1u) << 31);
     const int ib = len - 2 - (k - nexp - 1);                  // residual bit index, MSB first
     const uint32_t av = d.y >> 20;
