@@ -76,6 +76,7 @@ struct lepb200_ctx {
     std::string err;
     DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_images, d_segs, d_order, d_counter, d_models, d_rows;
     DevBuf d_henc_out, d_henc_imgs, d_henc_segs, d_henc_tabs;
+    DevBuf d_rc_ck, d_rc_digits;           // parallel range coder: checkpoints of the range-only pass, deferred-carry digits
     HostBuf h_henc_out, h_henc_segs;
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
     std::vector<int> henc_seg_first;      // per image: index of its first segment record
@@ -98,6 +99,8 @@ struct lepb200_ctx {
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
+    int rc_mode = 1;                      // range coder: 1 = range-only pass + parallel pieces + carry pass (lep_rangepass / piece / norm kernels),
+                                          // 0 = one serial chain per segment (lep_rangecode_kernel); LEPB200_RC_MODE
     int dec_mode = 0;                     // decode kernel: 0 = by batch size (group kernel when at least dec_group_min segments are in the
                                           // batch, else one warp per segment), 1 = always one warp per segment (lep_decode.cu),
                                           // 2 = always the group kernel (lep_decode_g2.cu)
@@ -354,6 +357,7 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (const char* e = getenv("LEPB200_ENC_CTA_CAP")) ctx->enc_cta_cap = atoi(e);          // tuning overrides
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
+    if (const char* e = getenv("LEPB200_RC_MODE")) ctx->rc_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
     if (const char* e = getenv("LEPB200_DEC_GROUP_MIN")) ctx->dec_group_min = std::max(1, atoi(e));
     if (const char* e = getenv("LEPB200_DEC_LANES")) {
@@ -372,7 +376,7 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows})
+    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_rc_ck, &ctx->d_rc_digits})
         b->release();
     for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs}) b->release();
     cudaEventDestroy(ctx->ev0);
@@ -445,6 +449,7 @@ static int encode_prepass(lepb200_ctx* ctx) {
     CK(cudaMemcpyAsync(&total_tokens, d_total, sizeof(total_tokens), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(ctx->d_tokens.reserve((size_t)total_tokens * 2 + 256));
+    ctx->token_total = total_tokens;
     ctx->have_batch = true;
     return LEPB200_OK;
 }
@@ -664,9 +669,34 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
     if (!ctx || !ctx->symbolised || !ctx->is_encode) { if (ctx) ctx->err = "encode_launch_rangecode without encode_launch_symbolise"; return LEPB200_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     const int nseg = (int)ctx->segs.size();
-    lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(
-        static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p), static_cast<const uint16_t*>(ctx->d_tokens.p));
-    CK(cudaGetLastError());
+    if (ctx->rc_mode == 1) {
+        // range-only pass -> digit layout (one small D2H + sync: the arena size depends on the data) -> parallel pieces -> carries
+        SegDesc* ds = static_cast<SegDesc*>(ctx->d_segs.p);
+        const int* dord = static_cast<const int*>(ctx->d_order.p);
+        const uint16_t* dtok = static_cast<const uint16_t*>(ctx->d_tokens.p);
+        CK(ctx->d_rc_ck.reserve((((size_t)ctx->token_total >> 10) + 2 * (size_t)nseg + 8) * sizeof(unsigned long long)));
+        unsigned long long* dck = static_cast<unsigned long long*>(ctx->d_rc_ck.p);
+        lep_rangepass_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(ds, nseg, dord, dtok, dck);
+        CK(cudaGetLastError());
+        unsigned long long* d_total = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_counter.p) + 128);
+        lep_digit_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(ds, nseg, d_total);
+        CK(cudaGetLastError());
+        unsigned long long total_digits = 0;
+        CK(cudaMemcpyAsync(&total_digits, d_total, sizeof(total_digits), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx->d_rc_digits.reserve((size_t)total_digits * 4 + 256));
+        CK(cudaMemsetAsync(ctx->d_rc_digits.p, 0, (size_t)total_digits * 4, ctx->stream));
+        uint32_t* ddig = static_cast<uint32_t*>(ctx->d_rc_digits.p);
+        lep_rangepiece_kernel<<<dim3(8, (unsigned)nseg), RCP_THREADS, 0, ctx->stream>>>(ds, nseg, dtok, dck, ddig);
+        CK(cudaGetLastError());
+        lep_rangenorm_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(ds, nseg, dord, ddig);
+        CK(cudaGetLastError());
+        ctx->launches += 3;
+    } else {
+        lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(
+            static_cast<SegDesc*>(ctx->d_segs.p), nseg, static_cast<const int*>(ctx->d_order.p), static_cast<const uint16_t*>(ctx->d_tokens.p));
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches += 1;
     ctx->symbolised = false;

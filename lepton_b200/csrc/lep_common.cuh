@@ -109,7 +109,9 @@ struct SegDesc {
     uint32_t ndecisions_lo, ndecisions_hi;
     uint32_t ntok;                   // encode: (probability, bit) tokens produced by kernel A
     unsigned long long tokens;       // encode: device address of the segment's token stream (uint16 each)
-    uint32_t tok_cap, pad_;
+    uint32_t tok_cap;
+    uint32_t total_shift;            // encode, parallel range coder: bits the coder shifted out over the whole segment (incl. marker and stop bits)
+    unsigned long long digits;       // encode, parallel range coder: offset of the segment's 16-bit digits in the digit arena
 };
 
 enum : int32_t { ST_OK = 0, ST_ASSERT = 1, ST_COEF_RANGE = 6, ST_STREAM_INCONSISTENT = 7, ST_OUT_OVERFLOW = 100 };

@@ -702,6 +702,185 @@ lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     if (w.mpos >= w.cap) sd.status = ST_OUT_OVERFLOW;
 }
 
+// ---- kernel B, parallel form -----------------------------------------------------------------------------
+// The serial kernel above is a 53 ms floor whatever the batch size (125 cycles per token on one thread per segment).
+// Two facts break the chain up (boolwriter.hh:48-118 read as arithmetic):
+//   * `range` and the number of bits shifted out depend only on the (probability, bit) sequence, never on `lowvalue`;
+//   * `lowvalue` is a plain sum: a 1-decision adds its `split` at the current bit position, and the byte stream is that
+//     sum written out from the top (the carry walk of boolwriter.hh:96-105 is the carry of this addition).
+// So: (1) lep_rangepass_kernel, still one thread per segment but with the short chain split -> select -> normalise only
+// (no window, no bytes), records (range, bits shifted so far) every RC_PIECE tokens and the total; (2)
+// lep_rangepiece_kernel gives every piece of RC_PIECE tokens to its own thread, which replays the range evolution from
+// its checkpoint and ADDS its splits -- as 16-bit digits with room for deferred carries -- into the segment's digit array
+// (pieces overlap by a digit or two at their borders: atomic adds); (3) lep_rangenorm_kernel resolves the carries from
+// the last digit to the first and writes the bytes, the stop rule of vpx_stop_encode (boolwriter.cc:32-34) included.
+// Depth of a bit = its distance from the top of the code value: the coder starts with an 8-bit window (depths 1..8); a
+// split added after S shifted bits covers depths S+1..S+8; byte k of the stream is depths 8k+1..8k+8, digit d the bytes
+// 2d, 2d+1; of the 8+T bits the last 24..31 never leave the window (vpx_stop_encode pushes 32 zero decisions through).
+constexpr int RC_PIECE = 1024;
+
+struct RcRange { uint32_t range; uint32_t S; };
+__device__ __forceinline__ void rr_put(RcRange& r, uint32_t bit, uint32_t prob, uint32_t& split_out, int& shift_out) {
+    const uint32_t split = 1 + (((r.range - 1) * prob) >> 8);
+    const uint32_t range = bit ? r.range - split : split;
+    const int shift = __clz(range) - 24;
+    r.range = range << shift;
+    r.S += (uint32_t)shift;
+    split_out = split; shift_out = shift;
+}
+
+// (1) range-only pass: checkpoints ck[(tokens >> 10) + 2 * segment + piece] = S << 8 | range, total shift per segment
+__global__ void __launch_bounds__(RC_THREADS)
+lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order, const uint16_t* __restrict__ token_base,
+                     unsigned long long* __restrict__ ck) {
+    const int t = blockIdx.x * RC_THREADS + threadIdx.x;
+    if (t >= nseg) return;
+    const int sidx = order[t];
+    SegDesc& sd = segs[sidx];
+    if (sd.status != ST_OK) { sd.total_shift = 0; return; }
+    unsigned long long* myck = ck + (sd.tokens >> 10) + 2ull * (unsigned long long)sidx;
+    RcRange r; r.range = 255; r.S = 0;
+    uint32_t sp; int sh;
+    myck[0] = 255ull;                                                   // piece 0 starts before the marker bit
+    rr_put(r, 0, 128, sp, sh);                                          // vpx_start_encode marker bit (boolwriter.cc:17-24)
+    const uint16_t* tok = token_base + sd.tokens;
+    const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
+    const uint32_t ntok = sd.ntok;
+    const uint32_t nfull = ntok / 8;
+    uint4 r0 = nfull > 0 ? __ldg(tok4 + 0) : make_uint4(0, 0, 0, 0);
+    uint4 r1 = nfull > 1 ? __ldg(tok4 + 1) : make_uint4(0, 0, 0, 0);
+    uint4 r2 = nfull > 2 ? __ldg(tok4 + 2) : make_uint4(0, 0, 0, 0);
+    uint4 r3 = nfull > 3 ? __ldg(tok4 + 3) : make_uint4(0, 0, 0, 0);
+    for (uint32_t i = 0; i < nfull; ++i) {
+        const uint4 cur = r0;
+        r0 = r1; r1 = r2; r2 = r3;
+        r3 = i + 4 < nfull ? __ldg(tok4 + i + 4) : make_uint4(0, 0, 0, 0);
+        if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)r.S << 8) | r.range;
+        rr_put(r, (cur.x >> 8) & 1, cur.x & 0xff, sp, sh);
+        rr_put(r, (cur.x >> 24) & 1, (cur.x >> 16) & 0xff, sp, sh);
+        rr_put(r, (cur.y >> 8) & 1, cur.y & 0xff, sp, sh);
+        rr_put(r, (cur.y >> 24) & 1, (cur.y >> 16) & 0xff, sp, sh);
+        rr_put(r, (cur.z >> 8) & 1, cur.z & 0xff, sp, sh);
+        rr_put(r, (cur.z >> 24) & 1, (cur.z >> 16) & 0xff, sp, sh);
+        rr_put(r, (cur.w >> 8) & 1, cur.w & 0xff, sp, sh);
+        rr_put(r, (cur.w >> 24) & 1, (cur.w >> 16) & 0xff, sp, sh);
+    }
+#pragma unroll 1
+    for (uint32_t i = nfull * 8; i < ntok; ++i) {
+        if (i != 0 && (i & (RC_PIECE - 1)) == 0) myck[i / RC_PIECE] = ((unsigned long long)r.S << 8) | r.range;
+        const uint32_t v = tok[i];
+        rr_put(r, (v >> 8) & 1, v & 0xff, sp, sh);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) rr_put(r, 0, 128, sp, sh);            // vpx_stop_encode (boolwriter.cc:26-35)
+    sd.total_shift = r.S;
+}
+
+// exclusive scan of the digit counts -> digit offsets; total in *total_out.  Single CTA (cf. lep_token_offsets_kernel).
+__global__ void lep_digit_offsets_kernel(SegDesc* __restrict__ segs, int nseg, unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long sums[1024];
+    const int t = threadIdx.x, per = (nseg + 1023) / 1024;
+    const int b = t * per, e = min(nseg, b + per);
+    unsigned long long s = 0;
+    for (int i = b; i < e; ++i) s += ((unsigned long long)segs[i].total_shift + 8 + 15) / 16 + 2;
+    sums[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; ++i) { unsigned long long v = sums[i]; sums[i] = run; run += v; }
+        *total_out = run;
+    }
+    __syncthreads();
+    unsigned long long off = sums[t];
+    for (int i = b; i < e; ++i) { segs[i].digits = off; off += ((unsigned long long)segs[i].total_shift + 8 + 15) / 16 + 2; }
+}
+
+// adds the window `acc` (bit 0 at depth 8 + S) into the digits
+__device__ __forceinline__ void rc_flush_digits(uint32_t* __restrict__ dig, unsigned long long acc, uint32_t S) {
+    if (acc == 0) return;
+    const uint32_t d0 = 8 + S - 1;                                      // depth - 1 of bit 0
+    const uint32_t dl = d0 >> 4, pos = 15 - (d0 & 15);
+    const unsigned long long x = acc << pos;
+    const uint32_t p0 = (uint32_t)(x & 0xffff), p1 = (uint32_t)((x >> 16) & 0xffff), p2 = (uint32_t)((x >> 32) & 0xffff), p3 = (uint32_t)(x >> 48);
+    if (p0) atomicAdd(dig + dl, p0);
+    if (p1) atomicAdd(dig + dl - 1, p1);
+    if (p2) atomicAdd(dig + dl - 2, p2);
+    if (p3) atomicAdd(dig + dl - 3, p3);
+}
+
+// (2) one thread per piece of RC_PIECE tokens: grid.y = segment, pieces strided over grid.x * blockDim.x threads
+constexpr int RCP_THREADS = 128;
+__global__ void __launch_bounds__(RCP_THREADS)
+lep_rangepiece_kernel(const SegDesc* __restrict__ segs, int nseg, const uint16_t* __restrict__ token_base, const unsigned long long* __restrict__ ck,
+                      uint32_t* __restrict__ digit_base) {
+    const int sidx = blockIdx.y;
+    if (sidx >= nseg) return;
+    const SegDesc& sd = segs[sidx];
+    if (sd.status != ST_OK) return;
+    const uint32_t ntok = sd.ntok;
+    const uint32_t npieces = max(1u, (ntok + RC_PIECE - 1) / RC_PIECE);
+    const unsigned long long* myck = ck + (sd.tokens >> 10) + 2ull * (unsigned long long)sidx;
+    uint32_t* dig = digit_base + sd.digits;
+    const uint16_t* tok = token_base + sd.tokens;
+    for (uint32_t p = blockIdx.x * RCP_THREADS + threadIdx.x; p < npieces; p += gridDim.x * RCP_THREADS) {
+        const unsigned long long c = myck[p];
+        RcRange r; r.range = (uint32_t)(c & 0xff); r.S = (uint32_t)(c >> 8);
+        unsigned long long acc = 0;
+        uint32_t pending = 0;                                           // bits shifted since the last flush
+        uint32_t sp; int sh;
+        auto put = [&](uint32_t bit, uint32_t prob) {
+            rr_put(r, bit, prob, sp, sh);
+            acc += bit ? sp : 0u;
+            acc <<= sh;
+            pending += (uint32_t)sh;
+            if (pending >= 32) { rc_flush_digits(dig, acc, r.S); acc = 0; pending = 0; }
+        };
+        if (p == 0) put(0, 128);                                        // marker bit
+        const uint32_t t0 = p * RC_PIECE, t1 = min(ntok, t0 + RC_PIECE);
+        uint32_t i = t0;
+        for (; i + 8 <= t1; i += 8) {                                   // pieces start at multiples of 1024 tokens: 16-byte aligned
+            const uint4 cur = __ldg(reinterpret_cast<const uint4*>(tok + i));
+            put((cur.x >> 8) & 1, cur.x & 0xff); put((cur.x >> 24) & 1, (cur.x >> 16) & 0xff);
+            put((cur.y >> 8) & 1, cur.y & 0xff); put((cur.y >> 24) & 1, (cur.y >> 16) & 0xff);
+            put((cur.z >> 8) & 1, cur.z & 0xff); put((cur.z >> 24) & 1, (cur.z >> 16) & 0xff);
+            put((cur.w >> 8) & 1, cur.w & 0xff); put((cur.w >> 24) & 1, (cur.w >> 16) & 0xff);
+        }
+        for (; i < t1; ++i) { const uint32_t v = tok[i]; put((v >> 8) & 1, v & 0xff); }
+        if (p + 1 == npieces) for (int k = 0; k < 32; ++k) put(0, 128); // stop bits: zeros, they only move the position
+        rc_flush_digits(dig, acc, r.S);
+    }
+}
+
+// (3) carries from the last digit to the first, bytes out; one thread per segment
+__global__ void __launch_bounds__(RC_THREADS)
+lep_rangenorm_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order, const uint32_t* __restrict__ digit_base) {
+    const int t = blockIdx.x * RC_THREADS + threadIdx.x;
+    if (t >= nseg) return;
+    SegDesc& sd = segs[order[t]];
+    if (sd.status != ST_OK) return;
+    const uint32_t T = sd.total_shift;
+    const uint32_t L = T >= 16 ? (T - 16) >> 3 : 0;                    // bytes that leave the window (boolwriter.hh:88)
+    const uint32_t nd = (T + 8 + 15) / 16;
+    const uint32_t* dig = digit_base + sd.digits;
+    uint8_t* buf = reinterpret_cast<uint8_t*>(sd.stream);
+    const uint32_t cap = sd.cap;
+    uint32_t carry = 0, last = 0;
+    for (int d = (int)nd - 1; d >= 0; --d) {
+        const uint32_t v = dig[d] + carry;
+        carry = v >> 16;
+        const uint32_t hi = (v >> 8) & 0xff, lo = v & 0xff;
+        const uint32_t k = 2u * (uint32_t)d;
+        if (k + 1 < L && k + 1 < cap) buf[k + 1] = (uint8_t)lo;
+        if (k < L && k < cap) buf[k] = (uint8_t)hi;
+        if (k + 1 == L - 1) last = lo;
+        if (k == L - 1) last = hi;
+    }
+    uint32_t len = L;
+    if (L > 0 && (last & 0xe0) == 0xc0) { if (len < cap) buf[len] = 0; ++len; }     // boolwriter.cc:32-34
+    sd.len = len;
+    if (len >= cap) sd.status = ST_OUT_OVERFLOW;
+}
+
 // ---- pre-pass: upper bound of the number of tokens each segment will produce -------------------------------
 // Exact for the 7x7 and edge coefficients (their decision counts depend only on the block itself), 22 for the DC
 // (its value depends on the prediction), 12 for the three count fields.  One CTA per segment, one warp per block.

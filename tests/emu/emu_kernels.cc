@@ -174,6 +174,7 @@ struct EncArgs {
     int stage;                       // 0 count, 1 offsets, 2 symbolise (kernel A), 3 range coder (kernel B)
     const ImageDesc* images; SegDesc* segs; int nseg; const int* order; int* counter;
     uint16_t* models; uint8_t* rows; size_t row_stride; uint16_t* tokens; unsigned long long* total;
+    unsigned long long* ck; uint32_t* digits;
 };
 
 void enc_body(void* p) {
@@ -181,7 +182,11 @@ void enc_body(void* p) {
     if (a.stage == 0) lep_count_kernel(a.images, a.segs, a.nseg);
     else if (a.stage == 1) lep_token_offsets_kernel(a.segs, a.nseg, a.total);
     else if (a.stage == 2) lep_encode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride, a.tokens);
-    else lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
+    else if (a.stage == 3) lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
+    else if (a.stage == 5) lep_rangepass_kernel(a.segs, a.nseg, a.order, a.tokens, a.ck);
+    else if (a.stage == 6) lep_digit_offsets_kernel(a.segs, a.nseg, a.total);
+    else if (a.stage == 7) lep_rangepiece_kernel(a.segs, a.nseg, a.tokens, a.ck, a.digits);
+    else lep_rangenorm_kernel(a.segs, a.nseg, a.order, a.digits);
 }
 
 }  // namespace
@@ -189,7 +194,7 @@ void enc_body(void* p) {
 // lepb200_encode_images on the emulator: count pre-pass -> token offsets -> kernel A (symbolise + model) -> kernel B
 // (range coder), with the launch shapes of lep_capi.cu.  `out` must hold sum(nseg) entries; the bytes of every stream are
 // copied into `arena` (capacity arena_cap) back to back and out[i].data points there.  grid_cap > 0 limits kernel A's
-// CTAs (persistent warps then take several segments each).  `kernel` is kept for the ABI of the harness (0).
+// CTAs (persistent warps then take several segments each).  kernel: 0 = parallel range coder, 1 = serial range coder.
 extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, lepb200_stream* out, uint8_t* arena, size_t arena_cap) {
     if (nimages <= 0 || !images || !out || !arena) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
@@ -262,7 +267,24 @@ extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* 
         a.models = models.data(); a.rows = rows.data();
         a.stage = 2; emu::launch(grid, ENC_WARPS_PER_CTA * 32, enc_body, &a);
     }
-    a.stage = 3; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+    std::vector<unsigned long long> ck;
+    std::vector<uint32_t> digits;
+    if (kernel == 0) {        // parallel range coder: range-only pass, digit layout, pieces, carries (lep_capi.cu: rc_mode 1)
+        ck.assign(((size_t)total_tokens >> 10) + 2 * (size_t)nseg + 8, 0);
+        a.ck = ck.data();
+        a.stage = 5; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+        unsigned long long total_digits = 0;
+        a.total = &total_digits;
+        a.stage = 6; emu::launch(1, 1024, enc_body, &a);
+        digits.assign((size_t)total_digits + 64, 0);
+        a.digits = digits.data();
+        a.stage = 7;
+        for (int y = 0; y < nseg; ++y) { emu::g_block_idx.y = (unsigned)y; emu::launch(8, RCP_THREADS, enc_body, &a); }      // grid (8, nseg)
+        emu::g_block_idx.y = 0;
+        a.stage = 8; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+    } else {                  // kernel 1: the serial range coder (rc_mode 0)
+        a.stage = 3; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+    }
     size_t used = 0;
     for (int s = 0; s < nseg; ++s) {
         const size_t n = segs[s].status == 0 ? segs[s].len : 0;

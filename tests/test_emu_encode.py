@@ -12,7 +12,7 @@ import emu  # noqa: E402
 from helpers import coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image, random_coef_image
 
 
-KERNELS = [emu.ENC_KERNEL_A]
+KERNELS = [0, 1]        # range coder: 0 = range-only pass + parallel pieces + carry pass (the default), 1 = one serial chain per segment
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
