@@ -184,6 +184,8 @@ float lepb200_last_kernel_ms(lepb200_ctx* ctx);
 float lepb200_last_symbolise_ms(lepb200_ctx* ctx);
 /* Device time of the Huffman-decode kernel of the last lepb200_huffman_decode_to_device call, milliseconds. */
 float lepb200_last_huffman_ms(lepb200_ctx* ctx);
+/* Synchronisation iterations the sub-sequence Huffman kernels (lep_huffpar.cu) needed in that call; 0 = serial kernel only. */
+int lepb200_last_huffman_iterations(lepb200_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx);
 /* Sum over the last uploaded batch of 128 * coded blocks + stream bytes (SURVEY.md section 8(d) algorithmic bytes);
@@ -268,6 +270,9 @@ int lepb200_host_jpeg_open_threads(const uint8_t* data, size_t len, int min_thre
 int lepb200_host_jpeg_open_split(const uint8_t* data, size_t len, int min_threads, int max_threads, int even_split, lepb200_jpeg** out, int32_t* status);
 const char* lepb200_host_jpeg_error(const lepb200_jpeg* h);
 int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img);
+/* the scan as lepb200_huffman_decode_to_device takes it (de-stuffed entropy bytes, tables, geometry; pointers valid until
+ * *_close; `rows` and the outputs are left alone); LEPB200_ERR_INVALID when the file needs the host Huffman decoder */
+int lepb200_host_jpeg_scan(lepb200_jpeg* h, lepb200_jpeg_scan* scan);
 int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, int nseg, const uint8_t** data, size_t* len);
 void lepb200_host_jpeg_close(lepb200_jpeg* h);
 /* decode-side host stages: container parse + demux (read_ujpg, jpgcoder.cc:4117), geometry/splits, segment streams, and

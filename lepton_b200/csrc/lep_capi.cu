@@ -15,7 +15,7 @@
 #include "lep_encode.cu"
 #include "lep_decode.cu"
 #include "lep_decode_g2.cu"
-#include "lep_huff.cu"
+#include "lep_huffpar.cu"
 #include "lep_huffenc.cu"
 
 using namespace lepb200;
@@ -74,14 +74,14 @@ struct lepb200_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
     std::string err;
-    DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_images, d_segs, d_order, d_counter, d_models, d_rows;
+    DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_hpar, d_images, d_segs, d_order, d_counter, d_models, d_rows;
     DevBuf d_henc_out, d_henc_imgs, d_henc_segs, d_henc_tabs;
     DevBuf d_rc_ck, d_rc_digits;           // parallel range coder: checkpoints of the range-only pass, deferred-carry digits
     HostBuf h_henc_out, h_henc_segs;
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
     std::vector<int> henc_seg_first;      // per image: index of its first segment record
     int henc_nseg = 0;
-    HostBuf h_segs, h_dense, h_stage, h_hjobs;
+    HostBuf h_segs, h_dense, h_stage, h_hjobs, h_hpar;
     size_t resident_plane_total = 0;
     int resident_images = 0;
     std::vector<ImageDesc> images;
@@ -97,6 +97,9 @@ struct lepb200_ctx {
     uint64_t alg_bytes = 0;
     uint64_t coded_blocks = 0;
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
+    int huff_par = 1;                     // 1: images with enough entropy bytes take the many-threads-per-image kernels (lep_huffpar.cu)
+    int huff_sub_bits = 4096;             // bits per sub-sequence (one thread each)
+    int huff_par_iters = 0;               // synchronisation iterations of the last batch (diagnostic)
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
     int rc_mode = 1;                      // range coder: 1 = range-only pass + parallel pieces + carry pass (lep_rangepass / piece / norm kernels),
@@ -356,6 +359,8 @@ int lepb200_create(lepb200_ctx** out, int device) {
     }
     if (const char* e = getenv("LEPB200_ENC_CTA_CAP")) ctx->enc_cta_cap = atoi(e);          // tuning overrides
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
+    if (const char* e = getenv("LEPB200_HUFF_PAR")) ctx->huff_par = atoi(e);
+    if (const char* e = getenv("LEPB200_HUFF_SUBSEQ_BITS")) ctx->huff_sub_bits = std::max(256, std::min(1 << 20, atoi(e))) & ~31;
     if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
     if (const char* e = getenv("LEPB200_RC_MODE")) ctx->rc_mode = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
@@ -376,9 +381,9 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_rc_ck, &ctx->d_rc_digits})
+    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_hpar, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_rc_ck, &ctx->d_rc_digits})
         b->release();
-    for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs}) b->release();
+    for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs, &ctx->h_hpar}) b->release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_mid);
@@ -409,6 +414,7 @@ float lepb200_last_symbolise_ms(lepb200_ctx* ctx) {
     return ctx->last_ms_a;
 }
 float lepb200_last_huffman_ms(lepb200_ctx* ctx) { return ctx ? ctx->last_ms_huff : -1.f; }
+int lepb200_last_huffman_iterations(lepb200_ctx* ctx) { return ctx ? ctx->huff_par_iters : 0; }
 uint64_t lepb200_kernel_launches(const lepb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t lepb200_last_algorithmic_bytes(const lepb200_ctx* ctx) { return ctx ? ctx->alg_bytes : 0; }
 
@@ -455,26 +461,7 @@ static int encode_prepass(lepb200_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------------ GPU Huffman decode
-static bool build_table_dev(const lepb200_hufftable& in, HuffTableDev& t) {
-    memset(&t, 0, sizeof(t));
-    int code = 0, k = 0;
-    for (int len = 1; len <= 16; ++len) {
-        t.valoff[len] = k - code;
-        for (int i = 0; i < in.bits[len]; ++i, ++k, ++code) {
-            if (k >= 256 || code >= (1 << len)) return false;        // over-subscribed table
-            t.vals[k] = in.vals[k];
-            if (len <= 9) {
-                const int shift = 9 - len;
-                for (int f = 0; f < (1 << shift); ++f) t.fast[(code << shift) | f] = (uint16_t)((len << 8) | in.vals[k]);
-            }
-        }
-        t.maxcode[len] = in.bits[len] ? code - 1 : -1;
-        if (code > (1 << len)) return false;
-        code <<= 1;
-    }
-    t.maxcode[17] = 0x7fffffff;
-    return true;
-}
+static bool build_table_dev(const lepb200_hufftable& in, HuffTableDev& t) { return huff_build_table(in.bits, in.vals, t); }
 
 uint8_t* lepb200_huffman_stage_reserve(lepb200_ctx* ctx, size_t bytes) {
     if (!ctx) return nullptr;
@@ -515,6 +502,8 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         return (int)tabs.size() - 1;
     };
     size_t plane_total = 0, huff_total = 0, rows_total = 0;
+    uint32_t sub_total = 0;
+    std::vector<uint32_t> sub_base((size_t)n + 1, 0);
     // in-place mode: the caller de-stuffed straight into this context's pinned staging buffer
     // (lepb200_huffman_stage_reserve), 16-byte aligned with >= 16 spare bytes after each scan -> no gather copy
     const uint8_t* stage0 = static_cast<const uint8_t*>(ctx->h_stage.p);
@@ -553,7 +542,15 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         }
         jb.rows = rows_total;
         rows_total += (size_t)(sc.mcuv + 1) * sizeof(HuffRow);
+        // interleaved scans without restart intervals and with enough data take the many-threads-per-image kernels
+        const uint64_t bits = (uint64_t)sc.nbytes * 8;
+        jb.sub_base = sub_total;
+        if (ctx->huff_par && jb.status == 0 && sc.ncmp > 1 && sc.rsti == 0 && bits >= 4ull * (uint64_t)ctx->huff_sub_bits && bits < (1ull << 32))
+            jb.nsub = (uint32_t)((bits + (uint64_t)ctx->huff_sub_bits - 1) / (uint64_t)ctx->huff_sub_bits);
+        sub_total += jb.nsub;
+        sub_base[i] = jb.sub_base;
     }
+    sub_base[n] = sub_total;
     CK(ctx->d_planes.reserve(plane_total + 256));
     CK(ctx->d_huff.reserve(huff_total + 256));
     CK(ctx->d_hrows.reserve(rows_total + 256));
@@ -600,6 +597,49 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     // CTA width: 7 images per CTA puts a 1024-image chunk on one CTA per SM, whose registers fit next to the encode
     // kernel of the previous chunk when that one is capped (lepb200_set_encode_ctas_per_sm), so the two overlap
+    ctx->huff_par_iters = 0;
+    if (sub_total > 0) {
+        // sub-sequence kernels (lep_huffpar.cu): arrays of 32 bytes per sub-sequence, then sub_base and the dirty counters
+        constexpr int ITER_CAP = 62;
+        const size_t o_exit = 0, o_cnt = align_up((size_t)sub_total * 8, 256), o_tok = o_cnt + align_up((size_t)sub_total * 16, 256),
+                     o_epoch = o_tok + align_up((size_t)sub_total * 4, 256), o_dirty = o_epoch + align_up((size_t)sub_total * 4, 256),
+                     o_base = o_dirty + 256, o_end = o_base + align_up(((size_t)n + 1) * 4, 256);
+        CK(ctx->d_hpar.reserve(o_end));
+        uint8_t* hp = static_cast<uint8_t*>(ctx->d_hpar.p);
+        CK(cudaMemsetAsync(hp + o_epoch, 0, o_base - o_epoch, ctx->stream));
+        CK(ctx->h_hpar.reserve(align_up(((size_t)n + 1) * 4, 256) + 256));
+        uint32_t* h_base = static_cast<uint32_t*>(ctx->h_hpar.p);
+        unsigned int* h_dirty = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(ctx->h_hpar.p) + align_up(((size_t)n + 1) * 4, 256));
+        memcpy(h_base, sub_base.data(), ((size_t)n + 1) * 4);
+        CK(cudaMemcpyAsync(hp + o_base, h_base, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        HpArrays a;
+        a.exit = reinterpret_cast<unsigned long long*>(hp + o_exit); a.cnt = reinterpret_cast<uint4*>(hp + o_cnt);
+        a.tok = reinterpret_cast<uint32_t*>(hp + o_tok); a.epoch = reinterpret_cast<uint32_t*>(hp + o_epoch);
+        a.sub_base = reinterpret_cast<const uint32_t*>(hp + o_base); a.total = sub_total; a.sub_bits = (uint32_t)ctx->huff_sub_bits;
+        unsigned int* d_dirty = reinterpret_cast<unsigned int*>(hp + o_dirty);
+        HuffJob* dj = static_cast<HuffJob*>(ctx->d_hjobs.p);
+        const HuffTableDev* dt = static_cast<const HuffTableDev*>(ctx->d_htabs.p);
+        const unsigned grid = (sub_total + HP_THREADS - 1) / HP_THREADS;
+        int iter = 0;
+        auto sync_iter = [&]() {
+            lep_huffpar_sync_kernel<<<grid, HP_THREADS, 0, ctx->stream>>>(dj, n, dt, (int)tabs.size(), a, iter, ITER_CAP, d_dirty);
+            ++iter; ctx->launches += 1;
+        };
+        sync_iter(); sync_iter(); sync_iter();
+        for (;;) {              // until no sub-sequence has to run again (dirty[k] = sub-sequences that iteration k has to decode)
+            CK(cudaMemcpyAsync(h_dirty, d_dirty, 64 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (iter > ITER_CAP || h_dirty[iter] == 0) break;
+            sync_iter();
+            if (iter <= ITER_CAP) sync_iter();
+        }
+        ctx->huff_par_iters = iter;
+        lep_huffpar_prefix_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(dj, n, a);
+        lep_huffpar_write_kernel<<<grid, HP_THREADS, 0, ctx->stream>>>(dj, n, dt, (int)tabs.size(), a);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+    }
+    // the serial walk: every image the kernels above did not take or did not finish cleanly
     const int hw = std::max(1, std::min(HUFF_MAX_WARPS, ctx->huff_warps));
     lep_huffdecode_kernel<<<(n + hw - 1) / hw, hw * 32, 0, ctx->stream>>>(
         static_cast<HuffJob*>(ctx->d_hjobs.p), n, static_cast<const HuffTableDev*>(ctx->d_htabs.p), (int)tabs.size());
@@ -676,6 +716,9 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
         const uint16_t* dtok = static_cast<const uint16_t*>(ctx->d_tokens.p);
         CK(ctx->d_rc_ck.reserve((((size_t)ctx->token_total >> 10) + 2 * (size_t)nseg + 8) * sizeof(unsigned long long)));
         unsigned long long* dck = static_cast<unsigned long long*>(ctx->d_rc_ck.p);
+        const bool trace = getenv("LEPB200_TRACE") != nullptr;           // per-kernel times on stderr (diagnostics; adds a sync)
+        cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (trace) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->stream); }
         lep_rangepass_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(ds, nseg, dord, dtok, dck);
         CK(cudaGetLastError());
         unsigned long long* d_total = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_counter.p) + 128);
@@ -684,13 +727,23 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
         unsigned long long total_digits = 0;
         CK(cudaMemcpyAsync(&total_digits, d_total, sizeof(total_digits), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (trace) cudaEventRecord(te[1], ctx->stream);
         CK(ctx->d_rc_digits.reserve((size_t)total_digits * 4 + 256));
         CK(cudaMemsetAsync(ctx->d_rc_digits.p, 0, (size_t)total_digits * 4, ctx->stream));
         uint32_t* ddig = static_cast<uint32_t*>(ctx->d_rc_digits.p);
         lep_rangepiece_kernel<<<dim3(8, (unsigned)nseg), RCP_THREADS, 0, ctx->stream>>>(ds, nseg, dtok, dck, ddig);
         CK(cudaGetLastError());
+        if (trace) cudaEventRecord(te[2], ctx->stream);
         lep_rangenorm_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(ds, nseg, dord, ddig);
         CK(cudaGetLastError());
+        if (trace) {
+            cudaEventRecord(te[3], ctx->stream);
+            cudaEventSynchronize(te[3]);
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, te[0], te[1]); cudaEventElapsedTime(&b, te[1], te[2]); cudaEventElapsedTime(&c, te[2], te[3]);
+            fprintf(stderr, "[trace]   range coder: range pass + offsets %.1f ms, pieces (incl. digit zero fill) %.1f ms, carries %.1f ms, %d segments\n", a, b, c, nseg);
+            for (auto& e : te) cudaEventDestroy(e);
+        }
         ctx->launches += 3;
     } else {
         lep_rangecode_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(

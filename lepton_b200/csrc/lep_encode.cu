@@ -795,21 +795,29 @@ __global__ void lep_digit_offsets_kernel(SegDesc* __restrict__ segs, int nseg, u
     for (int i = b; i < e; ++i) { segs[i].digits = off; off += ((unsigned long long)segs[i].total_shift + 8 + 15) / 16 + 2; }
 }
 
-// adds the window `acc` (bit 0 at depth 8 + S) into the digits
-__device__ __forceinline__ void rc_flush_digits(uint32_t* __restrict__ dig, unsigned long long acc, uint32_t S) {
-    if (acc == 0) return;
-    const uint32_t d0 = 8 + S - 1;                                      // depth - 1 of bit 0
-    const uint32_t dl = d0 >> 4, pos = 15 - (d0 & 15);
-    const unsigned long long x = acc << pos;
-    const uint32_t p0 = (uint32_t)(x & 0xffff), p1 = (uint32_t)((x >> 16) & 0xffff), p2 = (uint32_t)((x >> 32) & 0xffff), p3 = (uint32_t)(x >> 48);
-    if (p0) atomicAdd(dig + dl, p0);
-    if (p1) atomicAdd(dig + dl - 1, p1);
-    if (p2) atomicAdd(dig + dl - 2, p2);
-    if (p3) atomicAdd(dig + dl - 3, p3);
-}
-
-// (2) one thread per piece of RC_PIECE tokens: grid.y = segment, pieces strided over grid.x * blockDim.x threads
+// (2) one thread per piece of RC_PIECE tokens: grid.y = segment, pieces strided over grid.x * blockDim.x threads.
+// A thread carries five digits in registers: `top` = digit dn with room for carries, `win` = digits dn+1 .. dn+4 (bit 63 =
+// depth 16 (dn + 1) + 1).  A split decided after S shifted bits lands with its bit 0 at depth S + 8 = bit `off` of win; when
+// the position has moved on, the finished top digit leaves: with a plain store when no other piece can touch it (its 16
+// depths lie strictly inside this piece's range), else with an atomic add.  The digits are checked every four tokens
+// (<= 28 bits of movement), the same instruction for all lanes, so the lanes of a warp do not diverge per token.
 constexpr int RCP_THREADS = 128;
+struct RcDigits {
+    uint32_t* dig; unsigned long long win; uint32_t top; int dn, off; uint32_t own_lo, own_hi;
+    __device__ __forceinline__ void emit(int d, uint32_t v) {
+        if (v == 0 || d < 0) return;
+        const uint32_t first = 16u * (uint32_t)d + 1u;
+        if (first > own_lo && first + 15u < own_hi) dig[d] = v; else atomicAdd(dig + d, v);
+    }
+    __device__ __forceinline__ void advance() {               // keeps off in [28, 44): room for four more tokens
+        while (off < 28) { emit(dn, top); top = (uint32_t)(win >> 48); win <<= 16; ++dn; off += 16; }
+    }
+    __device__ __forceinline__ void flush() {
+        emit(dn, top);
+        emit(dn + 1, (uint32_t)(win >> 48)); emit(dn + 2, (uint32_t)(win >> 32) & 0xffffu);
+        emit(dn + 3, (uint32_t)(win >> 16) & 0xffffu); emit(dn + 4, (uint32_t)win & 0xffffu);
+    }
+};
 __global__ void __launch_bounds__(RCP_THREADS)
 lep_rangepiece_kernel(const SegDesc* __restrict__ segs, int nseg, const uint16_t* __restrict__ token_base, const unsigned long long* __restrict__ ck,
                       uint32_t* __restrict__ digit_base) {
@@ -820,34 +828,42 @@ lep_rangepiece_kernel(const SegDesc* __restrict__ segs, int nseg, const uint16_t
     const uint32_t ntok = sd.ntok;
     const uint32_t npieces = max(1u, (ntok + RC_PIECE - 1) / RC_PIECE);
     const unsigned long long* myck = ck + (sd.tokens >> 10) + 2ull * (unsigned long long)sidx;
-    uint32_t* dig = digit_base + sd.digits;
     const uint16_t* tok = token_base + sd.tokens;
     for (uint32_t p = blockIdx.x * RCP_THREADS + threadIdx.x; p < npieces; p += gridDim.x * RCP_THREADS) {
         const unsigned long long c = myck[p];
         RcRange r; r.range = (uint32_t)(c & 0xff); r.S = (uint32_t)(c >> 8);
-        unsigned long long acc = 0;
-        uint32_t pending = 0;                                           // bits shifted since the last flush
+        RcDigits g;
+        g.dig = digit_base + sd.digits;
+        g.win = 0; g.top = 0;
+        g.dn = (int)((r.S + 36 + 15) / 16) - 5;
+        g.off = 16 * (g.dn + 5) - (int)(r.S + 8);
+        g.own_lo = r.S + 8;                                                // the previous piece reaches down to this depth
+        g.own_hi = p + 1 < npieces ? (uint32_t)(myck[p + 1] >> 8) + 1 : 0xffffffffu;   // the next one starts here
         uint32_t sp; int sh;
         auto put = [&](uint32_t bit, uint32_t prob) {
             rr_put(r, bit, prob, sp, sh);
-            acc += bit ? sp : 0u;
-            acc <<= sh;
-            pending += (uint32_t)sh;
-            if (pending >= 32) { rc_flush_digits(dig, acc, r.S); acc = 0; pending = 0; }
+            if (bit) {
+                const unsigned long long x = (unsigned long long)sp << g.off;
+                g.win += x;
+                g.top += g.win < x ? 1u : 0u;
+            }
+            g.off -= sh;
         };
-        if (p == 0) put(0, 128);                                        // marker bit
+        if (p == 0) { put(0, 128); g.advance(); }                          // marker bit
         const uint32_t t0 = p * RC_PIECE, t1 = min(ntok, t0 + RC_PIECE);
         uint32_t i = t0;
-        for (; i + 8 <= t1; i += 8) {                                   // pieces start at multiples of 1024 tokens: 16-byte aligned
+        for (; i + 8 <= t1; i += 8) {                                      // pieces start at multiples of 1024 tokens: 16-byte aligned
             const uint4 cur = __ldg(reinterpret_cast<const uint4*>(tok + i));
             put((cur.x >> 8) & 1, cur.x & 0xff); put((cur.x >> 24) & 1, (cur.x >> 16) & 0xff);
             put((cur.y >> 8) & 1, cur.y & 0xff); put((cur.y >> 24) & 1, (cur.y >> 16) & 0xff);
+            g.advance();
             put((cur.z >> 8) & 1, cur.z & 0xff); put((cur.z >> 24) & 1, (cur.z >> 16) & 0xff);
             put((cur.w >> 8) & 1, cur.w & 0xff); put((cur.w >> 24) & 1, (cur.w >> 16) & 0xff);
+            g.advance();
         }
-        for (; i < t1; ++i) { const uint32_t v = tok[i]; put((v >> 8) & 1, v & 0xff); }
-        if (p + 1 == npieces) for (int k = 0; k < 32; ++k) put(0, 128); // stop bits: zeros, they only move the position
-        rc_flush_digits(dig, acc, r.S);
+        for (; i < t1; ++i) { const uint32_t v = tok[i]; put((v >> 8) & 1, v & 0xff); g.advance(); }
+        if (p + 1 == npieces) for (int k = 0; k < 32; ++k) { put(0, 128); g.advance(); }   // stop bits: zeros, they only move the position
+        g.flush();
     }
 }
 

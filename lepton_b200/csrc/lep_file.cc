@@ -341,7 +341,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 s.gpu_rc = lepb200_huffman_decode_to_device(ctx, s.scans.data(), nb);
                 c->t_huff_ms = lepb200_last_huffman_ms(ctx);
                 mark("huffman", k, t0);
-                if (trace) fprintf(stderr, "[trace]   huffman kernel %.1f ms\n", c->t_huff_ms);
+                if (trace) fprintf(stderr, "[trace]   huffman kernels %.1f ms, %d synchronisation iterations\n", c->t_huff_ms, lepb200_last_huffman_iterations(ctx));
             }
             double t1 = now_s();
             s.imgs.resize(nb);
@@ -878,6 +878,24 @@ const char* lepb200_host_jpeg_error(const lepb200_jpeg* h) { return h ? h->j.err
 int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img) {
     if (!h || !img || h->j.status) return LEPB200_ERR_INVALID;
     fill_image(*img, h->j, h->planes, h->sp.selected);
+    return LEPB200_OK;
+}
+
+int lepb200_host_jpeg_scan(lepb200_jpeg* h, lepb200_jpeg_scan* sc) {
+    if (!h || !sc || h->j.status) return LEPB200_ERR_INVALID;
+    const Jpeg& j = h->j;
+    GpuScanSetup gs;
+    if (!gpu_scan_setup(j, gs)) return LEPB200_ERR_INVALID;
+    lepb200_huffrow* rows = sc->rows;
+    memset(sc, 0, sizeof(*sc));
+    sc->rows = rows;
+    sc->ncmp = j.ncmp; sc->mcuh = j.mcuh; sc->mcuv = j.mcuv; sc->rsti = gs.rsti;
+    for (int t = 0; t < j.ncmp && t < 3; ++t) {
+        sc->H[t] = j.cmp[t].H; sc->V[t] = j.cmp[t].V; sc->nch[t] = j.cmp[t].nch; sc->ncv[t] = j.cmp[t].ncv;
+        memcpy(sc->dc[t].bits, gs.dc_bits[t], 17); memcpy(sc->dc[t].vals, gs.dc_vals[t], 256);
+        memcpy(sc->ac[t].bits, gs.ac_bits[t], 17); memcpy(sc->ac[t].vals, gs.ac_vals[t], 256);
+    }
+    sc->entropy = j.huff.data(); sc->nbytes = (uint32_t)j.huff.size();
     return LEPB200_OK;
 }
 

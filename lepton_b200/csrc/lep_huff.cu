@@ -13,6 +13,9 @@
 // decisions the Lepton coder will take, so the encoder's token streams can be laid out without a counting pass.
 // Semantics follow decode_jpeg / decode_block_seq (jpgcoder.cc:2799-3302, :4893-4961) exactly like the host decoder in
 // lep_jpeg.cc, against which it is tested.
+#pragma once
+#include <cstring>
+
 #include "lep_common.cuh"
 
 namespace lepb200 {
@@ -23,6 +26,28 @@ struct HuffTableDev {
     int32_t valoff[18];
     uint8_t vals[256];
 };
+
+// host side: the decode tables of one DHT table (counts per code length, values in code order)
+static inline bool huff_build_table(const uint8_t bits[17], const uint8_t vals[256], HuffTableDev& t) {
+    memset(&t, 0, sizeof(t));
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        t.valoff[len] = k - code;
+        for (int i = 0; i < bits[len]; ++i, ++k, ++code) {
+            if (k >= 256 || code >= (1 << len)) return false;        // over-subscribed table
+            t.vals[k] = vals[k];
+            if (len <= 9) {
+                const int shift = 9 - len;
+                for (int f = 0; f < (1 << shift); ++f) t.fast[(code << shift) | f] = (uint16_t)((len << 8) | vals[k]);
+            }
+        }
+        t.maxcode[len] = bits[len] ? code - 1 : -1;
+        if (code > (1 << len)) return false;
+        code <<= 1;
+    }
+    t.maxcode[17] = 0x7fffffff;
+    return true;
+}
 
 struct HuffRow {             // state at the start of an MCU row
     uint32_t bitpos;         // bits consumed of the de-stuffed entropy stream
@@ -46,6 +71,11 @@ struct HuffJob {
     int32_t padbit;
     uint32_t end_bitpos;
     int32_t nrows;
+    // many-threads-per-image path (lep_huffpar.cu): first sub-sequence and their number (0 = this kernel decodes the image)
+    uint32_t sub_base, nsub;
+    int32_t par_done;                // the sub-sequence pass completed the image
+    int32_t par_redo;                // it met something only the serial walk below classifies (an error, trailing data, no
+                                     // convergence): decode the image again here, over freshly zeroed planes
 };
 
 static __constant__ uint8_t c_zigzag_to_aligned[64] = {
@@ -131,6 +161,15 @@ lep_huffdecode_kernel(HuffJob* __restrict__ jobs, int njobs, const HuffTableDev*
     if (job >= njobs) return;
     HuffJob& jb = jobs[job];
     if (jb.status != 0) return;
+    if (jb.nsub != 0) {                              // the image went through the sub-sequence kernels first
+        if (jb.par_done && !jb.par_redo) return;
+        for (int q = 0; q < jb.ncmp; ++q) {          // rare: start over from zeroed planes
+            uint4* pl = reinterpret_cast<uint4*>(jb.plane[q]);
+            const size_t n16 = (size_t)jb.bch[q] * jb.bcv[q] * 8;
+            for (size_t i = lane; i < n16; i += 32) pl[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+    }
 
     const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(jb.huff);
     const uint32_t nwords = (jb.nbytes + 3) / 4;

@@ -18,7 +18,7 @@ CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
 SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
            os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_g2.cu"),
-           os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
+           os.path.join(CSRC, "lep_huff.cu"), os.path.join(CSRC, "lep_huffpar.cu"), os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
 
@@ -109,3 +109,80 @@ def encode_images(images, grid_cap=0, kernel=0):
             k += 1
         res.append(segs)
     return res
+
+
+# ---- baseline Huffman decode kernels (lep_huff.cu, lep_huffpar.cu)
+class _HuffTable(ctypes.Structure):
+    _fields_ = [("bits", ctypes.c_uint8 * 17), ("vals", ctypes.c_uint8 * 256)]
+
+
+class _HuffRow(ctypes.Structure):
+    _fields_ = [("bitpos", ctypes.c_uint32), ("lastdc", ctypes.c_int16 * 3), ("mcu_y", ctypes.c_int16), ("tokens", ctypes.c_uint32)]
+
+
+class _Scan(ctypes.Structure):
+    _fields_ = [("entropy", ctypes.c_void_p), ("nbytes", ctypes.c_uint32), ("ncmp", ctypes.c_int32), ("mcuh", ctypes.c_int32),
+                ("mcuv", ctypes.c_int32), ("rsti", ctypes.c_int32), ("H", ctypes.c_int32 * 3), ("V", ctypes.c_int32 * 3),
+                ("nch", ctypes.c_int32 * 3), ("ncv", ctypes.c_int32 * 3), ("dc", _HuffTable * 3), ("ac", _HuffTable * 3),
+                ("status", ctypes.c_int32), ("padbit", ctypes.c_int32), ("end_bitpos", ctypes.c_uint32), ("nrows", ctypes.c_int32),
+                ("rows", ctypes.POINTER(_HuffRow))]
+
+
+HUFF_SERIAL, HUFF_SUBSEQ = 0, 1
+
+
+def huffman_decode(mode, jpegs, sub_bits=4096, iter_cap=62, mutate=None):
+    """Huffman-decodes whole JPEG files with the emulated kernels.  mode HUFF_SERIAL: lep_huffdecode_kernel (one warp per
+    image); HUFF_SUBSEQ: the sub-sequence kernels of lep_huffpar.cu, then lep_huffdecode_kernel for what they left.
+    Returns (results, info): per file None when the host front end does not hand the file to the GPU decoder, else a dict
+    with status, padbit, end_bitpos, rows [(bitpos, lastdc, mcu_y, tokens)], planes [ndarray(blocks, 64)], host_planes;
+    info = (synchronisation iterations, images the serial kernel had to redo).  `mutate(i, bytearray)` may damage the
+    de-stuffed entropy bytes of file i before decoding."""
+    from lepton_b200.codec import HostJpeg, lib as product_lib
+    L = product_lib()
+    L.lepb200_host_jpeg_scan.argtypes = [ctypes.c_void_p, ctypes.POINTER(_Scan)]
+    L.lepb200_host_jpeg_scan.restype = ctypes.c_int
+    hjs, scans, idx, keep = [], [], [], []
+    for i, data in enumerate(jpegs):
+        hj = HostJpeg(data)
+        hjs.append(hj)
+        sc = _Scan()
+        if hj.status != 0 or L.lepb200_host_jpeg_scan(hj._h, ctypes.byref(sc)) != 0:
+            continue
+        if mutate is not None:
+            buf = bytearray(ctypes.string_at(sc.entropy, sc.nbytes))
+            mutate(i, buf)
+            arr = (ctypes.c_uint8 * len(buf)).from_buffer(buf)
+            keep.append((buf, arr))
+            sc.entropy = ctypes.addressof(arr)
+            sc.nbytes = len(buf)
+        rows = (_HuffRow * (sc.mcuv + 1))()
+        keep.append(rows)
+        sc.rows = ctypes.cast(rows, ctypes.POINTER(_HuffRow))
+        scans.append(sc)
+        idx.append(i)
+    n = len(scans)
+    res = [None] * len(jpegs)
+    if n == 0:
+        return res, (0, 0)
+    arr = (_Scan * n)(*scans)
+    planes, pp = [], (ctypes.POINTER(ctypes.c_int16) * (3 * n))()
+    for k, sc in enumerate(scans):
+        ps = []
+        for c in range(sc.ncmp):
+            a = np.zeros((sc.mcuh * sc.H[c] * sc.mcuv * sc.V[c], 64), np.int16)
+            ps.append(a)
+            pp[3 * k + c] = a.ctypes.data_as(ctypes.POINTER(ctypes.c_int16))
+        planes.append(ps)
+    info = (ctypes.c_int * 2)()
+    f = lib().emu_huffman_decode
+    f.restype = ctypes.c_int
+    rc = f(int(mode), int(sub_bits), int(iter_cap), arr, n, pp, info)
+    if rc != 0:
+        raise RuntimeError("emu_huffman_decode failed with %d" % rc)
+    for k, i in enumerate(idx):
+        sc = arr[k]
+        rows = [(sc.rows[r].bitpos, tuple(sc.rows[r].lastdc), sc.rows[r].mcu_y, sc.rows[r].tokens) for r in range(max(0, min(sc.nrows, sc.mcuv + 1)))]
+        host = [np.array(p) for p in hjs[i].coef_image().planes] if mutate is None else None
+        res[i] = dict(status=sc.status, padbit=sc.padbit, end_bitpos=sc.end_bitpos, nrows=sc.nrows, rows=rows, planes=planes[k], host_planes=host)
+    return res, (info[0], info[1])

@@ -12,6 +12,7 @@
 #include "../../lepton_b200/csrc/lep_encode.cu"
 #include "../../lepton_b200/csrc/lep_decode.cu"
 #include "../../lepton_b200/csrc/lep_decode_g2.cu"
+#include "../../lepton_b200/csrc/lep_huffpar.cu"
 #include "../../include/lepton_b200.h"
 
 using namespace lepb200;
@@ -297,5 +298,101 @@ extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* 
         out[s].ndecisions = (uint64_t)segs[s].ndecisions_lo | ((uint64_t)segs[s].ndecisions_hi << 32);
         used += n;
     }
+    return 0;
+}
+
+
+// ---- baseline Huffman decode: lep_huffdecode_kernel alone (mode 0) or the sub-sequence kernels of lep_huffpar.cu followed
+// by it (mode 1), with the job set-up and the iteration loop of lepb200_huffman_decode_to_device (lep_capi.cu).
+// planes[3 * i + c] = host plane of component c of scan i (zeroed by the caller); scans[i] outputs are filled like the
+// device call fills them.  info[0] = synchronisation iterations, info[1] = images the serial kernel had to redo.
+namespace {
+struct HuffArgs { HuffJob* jobs; int n; const HuffTableDev* tabs; int ntabs; HpArrays a; int iter; int last_iter; unsigned int* dirty; int which; };
+void huff_body(void* p) {
+    const HuffArgs& h = *static_cast<const HuffArgs*>(p);
+    if (h.which == 0) lep_huffdecode_kernel(h.jobs, h.n, h.tabs, h.ntabs);
+    else if (h.which == 1) lep_huffpar_sync_kernel(h.jobs, h.n, h.tabs, h.ntabs, h.a, h.iter, h.last_iter, h.dirty);
+    else if (h.which == 2) lep_huffpar_prefix_kernel(h.jobs, h.n, h.a);
+    else lep_huffpar_write_kernel(h.jobs, h.n, h.tabs, h.ntabs, h.a);
+}
+}  // namespace
+
+extern "C" int emu_huffman_decode(int mode, int sub_bits, int iter_cap, lepb200_jpeg_scan* scans, int n, int16_t** planes, int* info) {
+    std::vector<HuffJob> jobs(n);
+    std::vector<HuffTableDev> tabs;
+    std::vector<std::vector<HuffRow>> rows(n);
+    std::vector<uint32_t> sub_base((size_t)n + 1, 0);
+    uint32_t sub_total = 0;
+    auto table_index = [&](const lepb200_hufftable& t, bool& ok) -> int {
+        HuffTableDev d;
+        if (!huff_build_table(t.bits, t.vals, d)) ok = false;
+        for (size_t k = 0; k < tabs.size(); ++k) if (!memcmp(&tabs[k], &d, sizeof(d))) return (int)k;
+        tabs.push_back(d);
+        return (int)tabs.size() - 1;
+    };
+    std::vector<std::vector<uint8_t>> padded(n);
+    for (int i = 0; i < n; ++i) {
+        lepb200_jpeg_scan& sc = scans[i];
+        HuffJob& jb = jobs[i];
+        memset(&jb, 0, sizeof(jb));
+        bool ok = sc.ncmp >= 1 && sc.ncmp <= 3 && sc.mcuh > 0 && sc.mcuv > 0 && sc.entropy;
+        jb.ncmp = sc.ncmp; jb.mcuh = sc.mcuh; jb.mcuv = sc.mcuv; jb.rsti = sc.rsti; jb.nbytes = sc.nbytes;
+        for (int c = 0; ok && c < sc.ncmp; ++c) {
+            jb.H[c] = sc.H[c]; jb.V[c] = sc.V[c];
+            ok = ok && sc.H[c] >= 1 && sc.H[c] <= 2 && sc.V[c] >= 1 && sc.V[c] <= 2;
+            jb.bch[c] = sc.mcuh * sc.H[c]; jb.bcv[c] = sc.mcuv * sc.V[c];
+            jb.nch[c] = sc.nch[c]; jb.ncv[c] = sc.ncv[c];
+            jb.dc_tab[c] = table_index(sc.dc[c], ok); jb.ac_tab[c] = table_index(sc.ac[c], ok);
+            jb.plane[c] = (unsigned long long)(uintptr_t)planes[3 * i + c];
+        }
+        jb.status = ok ? 0 : LEPB200_ST_NOT_HANDLED;
+        padded[i].assign((size_t)sc.nbytes + 32, 0);                 // the kernels read whole words past the end
+        if (sc.entropy) memcpy(padded[i].data(), sc.entropy, sc.nbytes);
+        jb.huff = (unsigned long long)(uintptr_t)padded[i].data();
+        rows[i].assign((size_t)sc.mcuv + 1, HuffRow());
+        jb.rows = (unsigned long long)(uintptr_t)rows[i].data();
+        const uint64_t bits = (uint64_t)sc.nbytes * 8;
+        jb.sub_base = sub_total;
+        if (mode == 1 && jb.status == 0 && sc.ncmp > 1 && sc.rsti == 0 && bits >= 4ull * (uint64_t)sub_bits)
+            jb.nsub = (uint32_t)((bits + (uint64_t)sub_bits - 1) / (uint64_t)sub_bits);
+        sub_total += jb.nsub;
+        sub_base[i] = jb.sub_base;
+    }
+    sub_base[n] = sub_total;
+    HuffArgs h;
+    memset(&h, 0, sizeof(h));
+    h.jobs = jobs.data(); h.n = n; h.tabs = tabs.data(); h.ntabs = (int)tabs.size();
+    int iters = 0;
+    std::vector<unsigned long long> ex(sub_total + 1);
+    std::vector<uint32_t> epoch(sub_total + 1, 0), tok(sub_total + 1, 0);
+    std::vector<uint4> cnt(sub_total + 1);
+    std::vector<unsigned int> dirty(iter_cap + 4, 0);
+    if (sub_total > 0) {
+        h.a.exit = ex.data(); h.a.epoch = epoch.data(); h.a.cnt = cnt.data(); h.a.tok = tok.data();
+        h.a.sub_base = sub_base.data(); h.a.total = sub_total; h.a.sub_bits = (uint32_t)sub_bits;
+        h.dirty = dirty.data(); h.last_iter = iter_cap;
+        const unsigned grid = (sub_total + HP_THREADS - 1) / HP_THREADS;
+        h.which = 1;
+        for (;;) {
+            h.iter = iters;
+            emu::launch(grid, HP_THREADS, huff_body, &h);
+            ++iters;
+            if (iters > iter_cap || dirty[iters] == 0) break;
+        }
+        h.which = 2; emu::launch((n + 127) / 128, 128, huff_body, &h);
+        h.which = 3; emu::launch(grid, HP_THREADS, huff_body, &h);
+    }
+    int redo = 0;
+    for (int i = 0; i < n; ++i) if (jobs[i].nsub && !(jobs[i].par_done && !jobs[i].par_redo)) ++redo;
+    h.which = 0;
+    emu::launch((n + 3) / 4, 4 * 32, huff_body, &h);
+    for (int i = 0; i < n; ++i) {
+        scans[i].status = jobs[i].status;
+        scans[i].padbit = jobs[i].padbit;
+        scans[i].end_bitpos = jobs[i].end_bitpos;
+        scans[i].nrows = jobs[i].nrows;
+        if (scans[i].rows && jobs[i].nrows > 0) memcpy(scans[i].rows, rows[i].data(), sizeof(HuffRow) * (size_t)std::min(jobs[i].nrows, scans[i].mcuv + 1));
+    }
+    if (info) { info[0] = iters; info[1] = redo; }
     return 0;
 }

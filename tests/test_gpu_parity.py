@@ -231,6 +231,44 @@ def test_file_level_compress_both_huffman_paths(gpu_huffman):
     fc.close()
 
 
+@pytest.mark.parametrize("par,bits", [("0", "4096"), ("1", "4096"), ("1", "512")])
+def test_huffman_decode_kernels_serial_and_subsequence(par, bits, monkeypatch):
+    """lep_huffdecode_kernel alone (LEPB200_HUFF_PAR=0) and the sub-sequence kernels of lep_huffpar.cu in front of it must
+    both lead to the reference's .lep bytes; synthetic 4:2:0 / 4:4:4 files large enough for hundreds of sub-sequences
+    are checked against each other and by a round trip."""
+    import io
+    import os
+    import numpy as np
+    from PIL import Image
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200FileCodec
+    monkeypatch.setenv("LEPB200_HUFF_PAR", par)
+    monkeypatch.setenv("LEPB200_HUFF_SUBSEQ_BITS", bits)
+    names = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg"]
+    jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
+    rng = np.random.default_rng(11)
+    for k, (w, h, q, sub) in enumerate([(1920, 1080, 85, 2), (801, 603, 95, 0), (2048, 64, 70, 1), (1280, 720, 85, 2)]):
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.stack([128 + 70 * np.sin(xx / (9.0 + c) + yy / (17.0 - c) + k) for c in range(3)], -1) + rng.normal(0, 16, (h, w, 3))
+        b = io.BytesIO()
+        Image.fromarray(np.clip(img, 0, 255).astype(np.uint8), "RGB").save(b, "JPEG", quality=q, subsampling=sub)
+        jpegs.append(b.getvalue())
+    fc = LeptonB200FileCodec(0, host_threads=4)
+    res = fc.compress(jpegs)
+    host = LeptonB200FileCodec(0, host_threads=4, gpu_huffman=False)
+    want = host.compress(jpegs)
+    host.close()
+    for k, ((st, lep), (st2, lep2)) in enumerate(zip(res, want)):
+        assert st == 0 and st2 == 0, k
+        assert lep == lep2, "file %d: GPU Huffman decode and host Huffman decode lead to different .lep bytes" % k
+        if k < len(names):
+            assert lep == open(os.path.join(GOLDEN, names[k][:-4] + ".lep"), "rb").read(), names[k]
+    back = fc.decompress([lep for _, lep in res])
+    fc.close()
+    for k, (j, (st, out)) in enumerate(zip(jpegs, back)):
+        assert st == 0 and out == j, k
+
+
 def test_cli_jpg_to_lep_and_back(tmp_path):
     """`lepton-b200 in.jpg out.lep` writes the reference CLI's bytes; `lepton-b200 out.lep back.jpg` restores the input
     (the north_star's `lepton` command-line surface, src/lepton/jpgcoder.cc:988-1219,1528)."""
