@@ -357,6 +357,10 @@ int lepb200_create(lepb200_ctx** out, int device) {
         delete ctx;
         return LEPB200_ERR_CUDA;
     }
+    if (cudaFuncSetAttribute(lep_rangepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCT_SMEM_BYTES) != cudaSuccess) {
+        delete ctx;
+        return LEPB200_ERR_CUDA;
+    }
     if (const char* e = getenv("LEPB200_ENC_CTA_CAP")) ctx->enc_cta_cap = atoi(e);          // tuning overrides
     if (const char* e = getenv("LEPB200_HUFF_WARPS")) ctx->huff_warps = atoi(e);
     if (const char* e = getenv("LEPB200_HUFF_PAR")) ctx->huff_par = atoi(e);
@@ -719,7 +723,7 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
         const bool trace = getenv("LEPB200_TRACE") != nullptr;           // per-kernel times on stderr (diagnostics; adds a sync)
         cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
         if (trace) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->stream); }
-        lep_rangepass_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(ds, nseg, dord, dtok, dck);
+        lep_rangepass_kernel<<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
         CK(cudaGetLastError());
         unsigned long long* d_total = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_counter.p) + 128);
         lep_digit_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(ds, nseg, d_total);
@@ -734,7 +738,7 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
         lep_rangepiece_kernel<<<dim3(8, (unsigned)nseg), RCP_THREADS, 0, ctx->stream>>>(ds, nseg, dtok, dck, ddig);
         CK(cudaGetLastError());
         if (trace) cudaEventRecord(te[2], ctx->stream);
-        lep_rangenorm_kernel<<<(nseg + RC_THREADS - 1) / RC_THREADS, RC_THREADS, 0, ctx->stream>>>(ds, nseg, dord, ddig);
+        lep_rangenorm_kernel<<<(nseg + RCN_WARPS - 1) / RCN_WARPS, RCN_WARPS * 32, 0, ctx->stream>>>(ds, nseg, dord, ddig);
         CK(cudaGetLastError());
         if (trace) {
             cudaEventRecord(te[3], ctx->stream);

@@ -729,20 +729,52 @@ __device__ __forceinline__ void rr_put(RcRange& r, uint32_t bit, uint32_t prob, 
     split_out = split; shift_out = shift;
 }
 
-// (1) range-only pass: checkpoints ck[(tokens >> 10) + 2 * segment + piece] = S << 8 | range, total shift per segment
-__global__ void __launch_bounds__(RC_THREADS)
+// (1) range-only pass: checkpoints ck[(tokens >> 10) + 2 * segment + piece] = S << 8 | range, total shift per segment.
+// Still one thread per segment, so what counts is the dependent chain per token.  split -> select -> count leading
+// zeros -> shift is seven dependent instructions (78 cycles per token measured, 34 ms per 832 K tokens); but a normalised
+// range has only 128 values and a token 512, so the whole transition fits a 128 KB table in shared memory:
+// entry[token * 128 + (range - 128)] = (new range - 128) << 1 | shift << 8, and the chain per token is one LOP3 (next byte
+// offset = token row | state) and one 16-bit shared-memory load.  One CTA of 128 threads per SM holds the table.
+constexpr int RCT_THREADS = 128;
+constexpr int RCT_ENTRIES = 512 * 128;
+constexpr size_t RCT_SMEM_BYTES = (size_t)RCT_ENTRIES * 2;
+__device__ __forceinline__ uint32_t rct_entry(uint32_t tok9, uint32_t range) {
+    const uint32_t prob = tok9 & 0xff, bit = tok9 >> 8;
+    const uint32_t split = 1 + (((range - 1) * prob) >> 8);
+    uint32_t r = bit ? range - split : split;
+    if (r == 0) return 0;                                   // probability 0 with bit 1: never produced by kernel A
+    const int shift = __clz(r) - 24;
+    r <<= shift;
+    return ((r - 128) << 1) | ((uint32_t)shift << 8);
+}
+__global__ void __launch_bounds__(RCT_THREADS, 1)
 lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order, const uint16_t* __restrict__ token_base,
                      unsigned long long* __restrict__ ck) {
-    const int t = blockIdx.x * RC_THREADS + threadIdx.x;
+#ifndef LEPB200_EMU
+    extern __shared__ uint16_t s_rct[];
+#else
+    static uint16_t s_rct[RCT_ENTRIES];
+#endif
+    for (int e = threadIdx.x; e < RCT_ENTRIES; e += RCT_THREADS) s_rct[e] = (uint16_t)rct_entry((uint32_t)e >> 7, 128u + ((uint32_t)e & 127u));
+    __syncthreads();
+    const int t = blockIdx.x * RCT_THREADS + threadIdx.x;
     if (t >= nseg) return;
     const int sidx = order[t];
     SegDesc& sd = segs[sidx];
     if (sd.status != ST_OK) { sd.total_shift = 0; return; }
     unsigned long long* myck = ck + (sd.tokens >> 10) + 2ull * (unsigned long long)sidx;
-    RcRange r; r.range = 255; r.S = 0;
-    uint32_t sp; int sh;
+    const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_rct);
+    uint32_t e = (255u - 128u) << 1;                        // last entry read; e & 0xfe = (range - 128) << 1 = byte offset inside a token's row
+    uint32_t S = 0;
+    // one transition: address = row of the token (token << 8 bytes) | state, as ONE lop3 (the token row is ready long before)
+#ifndef LEPB200_EMU
+#define RCT_ADDR(dst, row) asm("lop3.b32 %0, %1, 0xfe, %2, 0xf8;" : "=r"(dst) : "r"(e), "r"(row))
+#else
+#define RCT_ADDR(dst, row) dst = (e & 0xfeu) | (row)
+#endif
+#define RCT_STEP(tok9) { const uint32_t row = (uint32_t)(tok9) << 8; uint32_t ad; RCT_ADDR(ad, row); e = *reinterpret_cast<const uint16_t*>(tab + ad); S += e >> 8; }
     myck[0] = 255ull;                                                   // piece 0 starts before the marker bit
-    rr_put(r, 0, 128, sp, sh);                                          // vpx_start_encode marker bit (boolwriter.cc:17-24)
+    RCT_STEP(128u);                                                     // vpx_start_encode marker bit (boolwriter.cc:17-24)
     const uint16_t* tok = token_base + sd.tokens;
     const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
@@ -755,25 +787,23 @@ lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
         const uint4 cur = r0;
         r0 = r1; r1 = r2; r2 = r3;
         r3 = i + 4 < nfull ? __ldg(tok4 + i + 4) : make_uint4(0, 0, 0, 0);
-        if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)r.S << 8) | r.range;
-        rr_put(r, (cur.x >> 8) & 1, cur.x & 0xff, sp, sh);
-        rr_put(r, (cur.x >> 24) & 1, (cur.x >> 16) & 0xff, sp, sh);
-        rr_put(r, (cur.y >> 8) & 1, cur.y & 0xff, sp, sh);
-        rr_put(r, (cur.y >> 24) & 1, (cur.y >> 16) & 0xff, sp, sh);
-        rr_put(r, (cur.z >> 8) & 1, cur.z & 0xff, sp, sh);
-        rr_put(r, (cur.z >> 24) & 1, (cur.z >> 16) & 0xff, sp, sh);
-        rr_put(r, (cur.w >> 8) & 1, cur.w & 0xff, sp, sh);
-        rr_put(r, (cur.w >> 24) & 1, (cur.w >> 16) & 0xff, sp, sh);
+        if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
+        RCT_STEP(cur.x & 0x1ffu); RCT_STEP((cur.x >> 16) & 0x1ffu);
+        RCT_STEP(cur.y & 0x1ffu); RCT_STEP((cur.y >> 16) & 0x1ffu);
+        RCT_STEP(cur.z & 0x1ffu); RCT_STEP((cur.z >> 16) & 0x1ffu);
+        RCT_STEP(cur.w & 0x1ffu); RCT_STEP((cur.w >> 16) & 0x1ffu);
     }
 #pragma unroll 1
     for (uint32_t i = nfull * 8; i < ntok; ++i) {
-        if (i != 0 && (i & (RC_PIECE - 1)) == 0) myck[i / RC_PIECE] = ((unsigned long long)r.S << 8) | r.range;
+        if (i != 0 && (i & (RC_PIECE - 1)) == 0) myck[i / RC_PIECE] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
         const uint32_t v = tok[i];
-        rr_put(r, (v >> 8) & 1, v & 0xff, sp, sh);
+        RCT_STEP(v & 0x1ffu);
     }
 #pragma unroll 1
-    for (int i = 0; i < 32; ++i) rr_put(r, 0, 128, sp, sh);            // vpx_stop_encode (boolwriter.cc:26-35)
-    sd.total_shift = r.S;
+    for (int i = 0; i < 32; ++i) RCT_STEP(128u);                        // vpx_stop_encode (boolwriter.cc:26-35)
+#undef RCT_STEP
+#undef RCT_ADDR
+    sd.total_shift = S;
 }
 
 // exclusive scan of the digit counts -> digit offsets; total in *total_out.  Single CTA (cf. lep_token_offsets_kernel).
@@ -867,10 +897,16 @@ lep_rangepiece_kernel(const SegDesc* __restrict__ segs, int nseg, const uint16_t
     }
 }
 
-// (3) carries from the last digit to the first, bytes out; one thread per segment
-__global__ void __launch_bounds__(RC_THREADS)
+// (3) carries from the last digit to the first, bytes out; ONE WARP PER SEGMENT, 32 digits per step.
+// A digit holds 16 bits plus whatever the pieces left above them.  Step one adds every digit's excess to its shallower
+// neighbour; after that each digit owes at most one carry and the classical generate / propagate rule applies, which a
+// warp resolves for 32 digits at once with two ballots and one 64-bit addition (bit j of (a + b + c) ^ a ^ b is the carry into
+// position j when a = generate | propagate, b = generate).  Lane l holds digit base + l; carries run from lane 31 to lane 0.
+constexpr int RCN_WARPS = 4;
+__global__ void __launch_bounds__(RCN_WARPS * 32)
 lep_rangenorm_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order, const uint32_t* __restrict__ digit_base) {
-    const int t = blockIdx.x * RC_THREADS + threadIdx.x;
+    const int t = blockIdx.x * RCN_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (t >= nseg) return;
     SegDesc& sd = segs[order[t]];
     if (sd.status != ST_OK) return;
@@ -880,21 +916,40 @@ lep_rangenorm_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     const uint32_t* dig = digit_base + sd.digits;
     uint8_t* buf = reinterpret_cast<uint8_t*>(sd.stream);
     const uint32_t cap = sd.cap;
-    uint32_t carry = 0, last = 0;
-    for (int d = (int)nd - 1; d >= 0; --d) {
-        const uint32_t v = dig[d] + carry;
-        carry = v >> 16;
-        const uint32_t hi = (v >> 8) & 0xff, lo = v & 0xff;
-        const uint32_t k = 2u * (uint32_t)d;
-        if (k + 1 < L && k + 1 < cap) buf[k + 1] = (uint8_t)lo;
-        if (k < L && k < cap) buf[k] = (uint8_t)hi;
-        if (k + 1 == L - 1) last = lo;
-        if (k == L - 1) last = hi;
+    uint32_t g_prev = 0, c_prev = 0, last = 0;
+    const int nbatch = (int)((nd + 31) / 32);
+    uint32_t v_next = nbatch > 0 && (uint32_t)(nbatch - 1) * 32 + lane < nd ? dig[(uint32_t)(nbatch - 1) * 32 + lane] : 0u;
+    for (int bt = nbatch - 1; bt >= 0; --bt) {
+        const uint32_t d = (uint32_t)bt * 32 + (uint32_t)lane;
+        const uint32_t v = v_next;
+        if (bt > 0) v_next = dig[d - 32];                              // next step's digits are on their way while this one resolves
+        const uint32_t r = v & 0xffffu, g = v >> 16;
+        uint32_t g_in = __shfl_down_sync(FULL, g, 1);
+        if (lane == 31) g_in = g_prev;
+        const uint32_t u = r + g_in;
+        const uint32_t r1 = u & 0xffffu;
+        const uint32_t gm = __brev(__ballot_sync(FULL, (u >> 16) != 0)), pm = __brev(__ballot_sync(FULL, r1 == 0xffffu));
+        const unsigned long long a = gm | pm, b = gm;
+        const unsigned long long sum = a + b + c_prev;
+        const uint32_t cin = (uint32_t)(sum ^ a ^ b);                  // bit 31 - lane: carry into this lane's digit
+        const uint32_t fin = (r1 + ((cin >> (31 - lane)) & 1u)) & 0xffffu;
+        c_prev = (uint32_t)(sum >> 32) & 1u;
+        g_prev = __shfl_sync(FULL, g, 0);
+        const uint32_t hi = fin >> 8, lo = fin & 0xffu, k = 2u * d;
+        if (d < nd) {
+            if (k + 1 < L && k + 1 < cap) *reinterpret_cast<uint16_t*>(buf + k) = (uint16_t)(hi | (lo << 8));
+            else if (k < L && k < cap) buf[k] = (uint8_t)hi;
+            if (L > 0 && k + 1 == L - 1) last = 0x100u | lo;
+            if (L > 0 && k == L - 1) last = 0x100u | hi;
+        }
     }
+    last = __reduce_max_sync(FULL, last) & 0xffu;
     uint32_t len = L;
-    if (L > 0 && (last & 0xe0) == 0xc0) { if (len < cap) buf[len] = 0; ++len; }     // boolwriter.cc:32-34
-    sd.len = len;
-    if (len >= cap) sd.status = ST_OUT_OVERFLOW;
+    if (L > 0 && (last & 0xe0) == 0xc0) { if (lane == 0 && len < cap) buf[len] = 0; ++len; }     // boolwriter.cc:32-34
+    if (lane == 0) {
+        sd.len = len;
+        if (len >= cap) sd.status = ST_OUT_OVERFLOW;
+    }
 }
 
 // ---- pre-pass: upper bound of the number of tokens each segment will produce -------------------------------

@@ -268,12 +268,17 @@ extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* 
         a.models = models.data(); a.rows = rows.data();
         a.stage = 2; emu::launch(grid, ENC_WARPS_PER_CTA * 32, enc_body, &a);
     }
+    if (const char* dump = getenv("EMU_DUMP_TOKENS")) {          // diagnostics: the (probability, bit) tokens of every segment
+        FILE* f = fopen(dump, "wb");
+        for (int s = 0; f && s < nseg; ++s) { const uint32_t nt = segs[s].ntok; fwrite(&nt, 4, 1, f); fwrite(tokens.data() + segs[s].tokens, 2, nt, f); }
+        if (f) fclose(f);
+    }
     std::vector<unsigned long long> ck;
     std::vector<uint32_t> digits;
     if (kernel == 0) {        // parallel range coder: range-only pass, digit layout, pieces, carries (lep_capi.cu: rc_mode 1)
         ck.assign(((size_t)total_tokens >> 10) + 2 * (size_t)nseg + 8, 0);
         a.ck = ck.data();
-        a.stage = 5; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+        a.stage = 5; emu::launch((unsigned)((nseg + RCT_THREADS - 1) / RCT_THREADS), RCT_THREADS, enc_body, &a);
         unsigned long long total_digits = 0;
         a.total = &total_digits;
         a.stage = 6; emu::launch(1, 1024, enc_body, &a);
@@ -282,7 +287,7 @@ extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* 
         a.stage = 7;
         for (int y = 0; y < nseg; ++y) { emu::g_block_idx.y = (unsigned)y; emu::launch(8, RCP_THREADS, enc_body, &a); }      // grid (8, nseg)
         emu::g_block_idx.y = 0;
-        a.stage = 8; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
+        a.stage = 8; emu::launch((unsigned)((nseg + RCN_WARPS - 1) / RCN_WARPS), RCN_WARPS * 32, enc_body, &a);
     } else {                  // kernel 1: the serial range coder (rc_mode 0)
         a.stage = 3; emu::launch((unsigned)((nseg + RC_THREADS - 1) / RC_THREADS), RC_THREADS, enc_body, &a);
     }
