@@ -98,7 +98,7 @@ struct lepb200_ctx {
     uint64_t coded_blocks = 0;
     int enc_cta_cap = 0;                  // 0 = as many encode CTAs per SM as fit
     int huff_par = 1;                     // 1: images with enough entropy bytes take the many-threads-per-image kernels (lep_huffpar.cu)
-    int huff_sub_bits = 4096;             // bits per sub-sequence (one thread each)
+    int huff_sub_bits = 0;                // bits per sub-sequence (one thread each); 0 = by batch size (LEPB200_HUFF_SUBSEQ_BITS overrides)
     int huff_par_iters = 0;               // synchronisation iterations of the last batch (diagnostic)
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
@@ -518,6 +518,15 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
     if (inside != 0 && inside != n - placeholders) { ctx->err = "huffman_decode_to_device: scans partly inside the staging buffer"; return LEPB200_ERR_INVALID; }
     const bool in_place = inside > 0 && inside == n - placeholders;
     for (int i = 0; i < n; ++i) if (in_place && scans[i].entropy && ((scans[i].entropy - stage0) & 15)) { ctx->err = "huffman_decode_to_device: staged scan not 16-byte aligned"; return LEPB200_ERR_INVALID; }
+    // sub-sequence length of the many-threads-per-image kernels: longer sub-sequences need fewer synchronisation passes
+    // (8192 bits: 3, 4096: 5, 2048: 9 on 1080p files), as long as the batch still gives every SM its 2048 threads
+    int sub_bits = ctx->huff_sub_bits;
+    if (sub_bits <= 0) {
+        uint64_t bits = 0;
+        for (int i = 0; i < n; ++i) if (scans[i].entropy && scans[i].ncmp > 1 && scans[i].rsti == 0) bits += (uint64_t)scans[i].nbytes * 8;
+        sub_bits = 2048;
+        for (int cand : {16384, 8192, 4096}) if (bits / (uint64_t)cand >= (uint64_t)ctx->sm_count * 2048) { sub_bits = cand; break; }
+    }
     for (int i = 0; i < n; ++i) {
         lepb200_jpeg_scan& sc = scans[i];
         HuffJob& jb = jobs[i];
@@ -549,8 +558,8 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         // interleaved scans without restart intervals and with enough data take the many-threads-per-image kernels
         const uint64_t bits = (uint64_t)sc.nbytes * 8;
         jb.sub_base = sub_total;
-        if (ctx->huff_par && jb.status == 0 && sc.ncmp > 1 && sc.rsti == 0 && bits >= 4ull * (uint64_t)ctx->huff_sub_bits && bits < (1ull << 32))
-            jb.nsub = (uint32_t)((bits + (uint64_t)ctx->huff_sub_bits - 1) / (uint64_t)ctx->huff_sub_bits);
+        if (ctx->huff_par && jb.status == 0 && sc.ncmp > 1 && sc.rsti == 0 && bits >= 4ull * (uint64_t)sub_bits && bits < (1ull << 32))
+            jb.nsub = (uint32_t)((bits + (uint64_t)sub_bits - 1) / (uint64_t)sub_bits);
         sub_total += jb.nsub;
         sub_base[i] = jb.sub_base;
     }
@@ -619,7 +628,7 @@ int lepb200_huffman_decode_to_device(lepb200_ctx* ctx, lepb200_jpeg_scan* scans,
         HpArrays a;
         a.exit = reinterpret_cast<unsigned long long*>(hp + o_exit); a.cnt = reinterpret_cast<uint4*>(hp + o_cnt);
         a.tok = reinterpret_cast<uint32_t*>(hp + o_tok); a.epoch = reinterpret_cast<uint32_t*>(hp + o_epoch);
-        a.sub_base = reinterpret_cast<const uint32_t*>(hp + o_base); a.total = sub_total; a.sub_bits = (uint32_t)ctx->huff_sub_bits;
+        a.sub_base = reinterpret_cast<const uint32_t*>(hp + o_base); a.total = sub_total; a.sub_bits = (uint32_t)sub_bits;
         unsigned int* d_dirty = reinterpret_cast<unsigned int*>(hp + o_dirty);
         HuffJob* dj = static_cast<HuffJob*>(ctx->d_hjobs.p);
         const HuffTableDev* dt = static_cast<const HuffTableDev*>(ctx->d_htabs.p);

@@ -62,8 +62,8 @@ __device__ __forceinline__ void hp_span(HuffJob& jb, const HuffTableDev* __restr
     uint32_t p = (uint32_t)start;
     int z = (int)(start >> 32) & 63, cl = (int)(start >> 38) & 63, lnz = (int)(start >> 44) & 1, b = (int)(start >> 48) & 255;
     int cmp = b < nb0 ? 0 : (b < nb1 ? 1 : 2);
-    const HuffTableDev* dct = tb + jb.dc_tab[cmp];
-    const HuffTableDev* act = tb + jb.ac_tab[cmp];
+    const HuffTableDev* dct;
+    const HuffTableDev* act;
     uint32_t nblk = 0, tok = 0;
     int s0 = 0, s1 = 0, s2 = 0, blk_sum = 0, blk_last = 0;
     o.anomaly = 0;
@@ -85,6 +85,10 @@ __device__ __forceinline__ void hp_span(HuffJob& jb, const HuffTableDev* __restr
         mx = (int)(mcu % (uint32_t)mcuh); my = (int)(mcu / (uint32_t)mcuh);
         blk = block_ptr();
     }
+    // table of the current block: indices of the three components kept in registers (no global load per block)
+    const int dct0 = jb.dc_tab[0], dct1 = jb.dc_tab[1], dct2 = jb.dc_tab[2], act0 = jb.ac_tab[0], act1 = jb.ac_tab[1], act2 = jb.ac_tab[2];
+    dct = tb + (cmp == 0 ? dct0 : (cmp == 1 ? dct1 : dct2));
+    act = tb + (cmp == 0 ? act0 : (cmp == 1 ? act1 : act2));
     uint32_t ck = 0xffffffffu, w0 = 0, w1 = 0;
     while (p < end_bit) {
         const uint32_t k = p >> 5, sh = p & 31;
@@ -94,61 +98,46 @@ __device__ __forceinline__ void hp_span(HuffJob& jb, const HuffTableDev* __restr
             ck = k;
         }
         const uint32_t hi = __funnelshift_l(w1, w0, sh);       // 32 bits from p: a code (<= 16 bits) and its magnitude bits (<= 16)
-        bool block_done = false;
+        // DC and AC symbols take the same instructions (the lanes of a warp are at different places of their blocks)
+        const bool isdc = z == 0;
+        if (WRITE && isdc && b == 0 && mx == 0) {              // first block of an MCU row: the resumable state (HuffRow)
+            HuffRow r;
+            r.bitpos = p; r.mcu_y = (int16_t)my;
+            r.lastdc[0] = (int16_t)(pdc0 + s0); r.lastdc[1] = (int16_t)(pdc1 + s1); r.lastdc[2] = (int16_t)(pdc2 + s2);
+            r.tokens = tok0 + tok;
+            rows[my] = r;
+        }
         int len, sym;
-        if (z == 0) {
-            if (WRITE && b == 0 && mx == 0) {                  // first block of an MCU row: the resumable state (HuffRow)
-                HuffRow r;
-                r.bitpos = p; r.mcu_y = (int16_t)my;
-                r.lastdc[0] = (int16_t)(pdc0 + s0); r.lastdc[1] = (int16_t)(pdc1 + s1); r.lastdc[2] = (int16_t)(pdc2 + s2);
-                r.tokens = tok0 + tok;
-                rows[my] = r;
-            }
-            hp_lookup(dct, hi, len, sym);
-            const int sz = sym;
-            if (len == 0 || sz > 16) {
-                if (WRITE) { o.anomaly = 1; return; }
-                p += 1; continue;
-            }
-            int val = 0;
-            if (sz) {
-                const int nb = (int)((hi << len) >> (32 - sz));
-                val = nb >= (1 << (sz - 1)) ? nb : nb + 1 - (1 << sz);
-            }
+        hp_lookup(isdc ? dct : act, hi, len, sym);
+        const int sz = isdc ? sym : (sym & 15), run = isdc ? 0 : (sym >> 4);
+        if (len == 0 || sz > 16) {                             // no such code
+            if (WRITE) { o.anomaly = 1; return; }
+            p += 1; continue;
+        }
+        int val = 0;
+        if (sz) {
+            const int nb = (int)((hi << len) >> (32 - sz));
+            val = nb >= (1 << (sz - 1)) ? nb : nb + 1 - (1 << sz);
+        }
+        p += (uint32_t)(len + sz);
+        bool block_done = false;
+        if (isdc) {
             if (cmp == 0) s0 += val; else if (cmp == 1) s1 += val; else s2 += val;
             if (WRITE) blk[49] = (int16_t)((cmp == 0 ? pdc0 + s0 : (cmp == 1 ? pdc1 + s1 : pdc2 + s2)));
-            p += (uint32_t)(len + sz);
             z = 1; lnz = 1;
+        } else if (sym == 0) {                                 // EOB
+            if (WRITE && z > 1 && !lnz) { o.anomaly = 1; return; }           // "eob after last 0" (jpgcoder.cc:2953)
+            block_done = true;
+        } else if (run + z >= 64) {                            // the truncated-file fix-up path of the reference: serial kernel
+            if (WRITE) { o.anomaly = 1; return; }
+            block_done = true;
         } else {
-            hp_lookup(act, hi, len, sym);
-            if (len == 0) {
-                if (WRITE) { o.anomaly = 1; return; }
-                p += 1; continue;
-            }
-            const int run = sym >> 4, sz = sym & 15;
-            if (sym == 0) {                                    // EOB
-                if (WRITE && z > 1 && !lnz) { o.anomaly = 1; return; }       // "eob after last 0" (jpgcoder.cc:2953)
-                p += (uint32_t)len;
-                block_done = true;
-            } else if (run + z >= 64) {                        // the truncated-file fix-up path of the reference: serial kernel
-                if (WRITE) { o.anomaly = 1; return; }
-                p += (uint32_t)(len + sz);
-                block_done = true;
-            } else {
-                z += run;
-                int val = 0;
-                if (sz) {
-                    const int nb = (int)((hi << len) >> (32 - sz));
-                    val = nb >= (1 << (sz - 1)) ? nb : nb + 1 - (1 << sz);
-                    blk_sum += min(sz + 1, 11) + sz - 1;
-                    blk_last = z;
-                }
-                if (WRITE) blk[zz[z]] = (int16_t)val;
-                lnz = sz != 0;
-                ++z;
-                p += (uint32_t)(len + sz);
-                if (z >= 64) block_done = true;
-            }
+            z += run;
+            if (sz) { blk_sum += min(sz + 1, 11) + sz - 1; blk_last = z; }
+            if (WRITE) blk[zz[z]] = (int16_t)val;
+            lnz = sz != 0;
+            ++z;
+            if (z >= 64) block_done = true;
         }
         if (!block_done) continue;
         tok += (uint32_t)(blk_sum + (blk_last ? blk_last - cl : 0) + 34);
@@ -160,8 +149,8 @@ __device__ __forceinline__ void hp_span(HuffJob& jb, const HuffTableDev* __restr
             if (WRITE && ++mx == mcuh) { mx = 0; ++my; }
         }
         cmp = b < nb0 ? 0 : (b < nb1 ? 1 : 2);
-        dct = tb + jb.dc_tab[cmp];
-        act = tb + jb.ac_tab[cmp];
+        dct = tb + (cmp == 0 ? dct0 : (cmp == 1 ? dct1 : dct2));
+        act = tb + (cmp == 0 ? act0 : (cmp == 1 ? act1 : act2));
         z = 0; lnz = 1;
         if (WRITE) {
             if (n0 + nblk == N) { finished = true; break; }
