@@ -668,25 +668,31 @@ lep_rangecode_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
     const uint32_t nfull = ntok / 8;
-    // 4-deep software prefetch (32 tokens ahead) so that the chain never waits on memory
-    uint4 r0 = nfull > 0 ? __ldg(tok4 + 0) : make_uint4(0, 0, 0, 0);
-    uint4 r1 = nfull > 1 ? __ldg(tok4 + 1) : make_uint4(0, 0, 0, 0);
-    uint4 r2 = nfull > 2 ? __ldg(tok4 + 2) : make_uint4(0, 0, 0, 0);
-    uint4 r3 = nfull > 3 ? __ldg(tok4 + 3) : make_uint4(0, 0, 0, 0);
-    for (uint32_t i = 0; i < nfull; ++i) {
-        const uint4 cur = r0;
-        r0 = r1; r1 = r2; r2 = r3;
-        r3 = i + 4 < nfull ? __ldg(tok4 + i + 4) : make_uint4(0, 0, 0, 0);
-        rc_drain(w);
-        rc_put(w, (cur.x >> 8) & 1, cur.x & 0xff);
-        rc_put(w, (cur.x >> 24) & 1, (cur.x >> 16) & 0xff);
-        rc_put(w, (cur.y >> 8) & 1, cur.y & 0xff);
-        rc_put(w, (cur.y >> 24) & 1, (cur.y >> 16) & 0xff);
-        rc_drain(w);
-        rc_put(w, (cur.z >> 8) & 1, cur.z & 0xff);
-        rc_put(w, (cur.z >> 24) & 1, (cur.z >> 16) & 0xff);
-        rc_put(w, (cur.w >> 8) & 1, cur.w & 0xff);
-        rc_put(w, (cur.w >> 24) & 1, (cur.w >> 16) & 0xff);
+    // RC_DEPTH loads of 16 bytes in flight per thread (a register ring, 8 tokens each): one thread per segment leaves
+    // few loads in flight per SM, and the token streams (27 GB per 4096-image batch) have to arrive at 0.5-1 TB/s
+    constexpr int RC_DEPTH = 10;
+    uint4 q[RC_DEPTH];
+#pragma unroll
+    for (int j = 0; j < RC_DEPTH; ++j) q[j] = (uint32_t)j < nfull ? __ldg(tok4 + j) : make_uint4(0, 0, 0, 0);
+    for (uint32_t base = 0; base < nfull; base += RC_DEPTH) {
+#pragma unroll
+        for (int j = 0; j < RC_DEPTH; ++j) {
+            const uint32_t i = base + (uint32_t)j;
+            if (i < nfull) {
+                const uint4 cur = q[j];
+                q[j] = i + RC_DEPTH < nfull ? __ldg(tok4 + i + RC_DEPTH) : make_uint4(0, 0, 0, 0);
+                rc_drain(w);
+                rc_put(w, (cur.x >> 8) & 1, cur.x & 0xff);
+                rc_put(w, (cur.x >> 24) & 1, (cur.x >> 16) & 0xff);
+                rc_put(w, (cur.y >> 8) & 1, cur.y & 0xff);
+                rc_put(w, (cur.y >> 24) & 1, (cur.y >> 16) & 0xff);
+                rc_drain(w);
+                rc_put(w, (cur.z >> 8) & 1, cur.z & 0xff);
+                rc_put(w, (cur.z >> 24) & 1, (cur.z >> 16) & 0xff);
+                rc_put(w, (cur.w >> 8) & 1, cur.w & 0xff);
+                rc_put(w, (cur.w >> 24) & 1, (cur.w >> 16) & 0xff);
+            }
+        }
     }
 #pragma unroll 1
     for (uint32_t i = nfull * 8; i < ntok; ++i) { const uint32_t v = tok[i]; rc_drain(w); rc_put(w, (v >> 8) & 1, v & 0xff); }
@@ -768,7 +774,7 @@ lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     uint32_t S = 0;
     // one transition: address = row of the token (token << 8 bytes) | state, as ONE lop3 (the token row is ready long before)
 #ifndef LEPB200_EMU
-#define RCT_ADDR(dst, row) asm("lop3.b32 %0, %1, 0xfe, %2, 0xf8;" : "=r"(dst) : "r"(e), "r"(row))
+#define RCT_ADDR(dst, row) asm("lop3.b32 %0, %1, 0xfe, %2, 0xea;" : "=r"(dst) : "r"(e), "r"(row))      /* (e & 0xfe) | row */
 #else
 #define RCT_ADDR(dst, row) dst = (e & 0xfeu) | (row)
 #endif
@@ -779,19 +785,26 @@ lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
     const uint32_t nfull = ntok / 8;
-    uint4 r0 = nfull > 0 ? __ldg(tok4 + 0) : make_uint4(0, 0, 0, 0);
-    uint4 r1 = nfull > 1 ? __ldg(tok4 + 1) : make_uint4(0, 0, 0, 0);
-    uint4 r2 = nfull > 2 ? __ldg(tok4 + 2) : make_uint4(0, 0, 0, 0);
-    uint4 r3 = nfull > 3 ? __ldg(tok4 + 3) : make_uint4(0, 0, 0, 0);
-    for (uint32_t i = 0; i < nfull; ++i) {
-        const uint4 cur = r0;
-        r0 = r1; r1 = r2; r2 = r3;
-        r3 = i + 4 < nfull ? __ldg(tok4 + i + 4) : make_uint4(0, 0, 0, 0);
-        if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
-        RCT_STEP(cur.x & 0x1ffu); RCT_STEP((cur.x >> 16) & 0x1ffu);
-        RCT_STEP(cur.y & 0x1ffu); RCT_STEP((cur.y >> 16) & 0x1ffu);
-        RCT_STEP(cur.z & 0x1ffu); RCT_STEP((cur.z >> 16) & 0x1ffu);
-        RCT_STEP(cur.w & 0x1ffu); RCT_STEP((cur.w >> 16) & 0x1ffu);
+    // RCT_DEPTH loads of 16 bytes in flight per thread (a register ring): with one CTA per SM the token streams
+    // (27 GB per 4096-image batch) only arrive in time when about 1.5 KB per thread is on its way
+    constexpr int RCT_DEPTH = 12;
+    uint4 q[RCT_DEPTH];
+#pragma unroll
+    for (int j = 0; j < RCT_DEPTH; ++j) q[j] = (uint32_t)j < nfull ? __ldg(tok4 + j) : make_uint4(0, 0, 0, 0);
+    for (uint32_t base = 0; base < nfull; base += RCT_DEPTH) {
+#pragma unroll
+        for (int j = 0; j < RCT_DEPTH; ++j) {
+            const uint32_t i = base + (uint32_t)j;
+            if (i < nfull) {
+                const uint4 cur = q[j];
+                q[j] = i + RCT_DEPTH < nfull ? __ldg(tok4 + i + RCT_DEPTH) : make_uint4(0, 0, 0, 0);
+                if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
+                RCT_STEP(cur.x & 0x1ffu); RCT_STEP((cur.x >> 16) & 0x1ffu);
+                RCT_STEP(cur.y & 0x1ffu); RCT_STEP((cur.y >> 16) & 0x1ffu);
+                RCT_STEP(cur.z & 0x1ffu); RCT_STEP((cur.z >> 16) & 0x1ffu);
+                RCT_STEP(cur.w & 0x1ffu); RCT_STEP((cur.w >> 16) & 0x1ffu);
+            }
+        }
     }
 #pragma unroll 1
     for (uint32_t i = nfull * 8; i < ntok; ++i) {

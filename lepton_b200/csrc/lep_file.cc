@@ -479,6 +479,11 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
 //   back (host: Huffman re-encode + byte stuffing + header/garbage re-assembly)
 int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n, lepb200_result* out) {
     if (!c || !leps || !out || n <= 0) return LEPB200_ERR_INVALID;
+    const bool trace = getenv("LEPB200_TRACE") != nullptr;           // stage timeline on stderr (diagnostics)
+    const double t_origin = now_s();
+    auto mark = [&](const char* what, int k, double t_begin) {
+        if (trace) fprintf(stderr, "[trace] %-16s chunk %d  %8.1f -> %8.1f ms\n", what, k, (t_begin - t_origin) * 1e3, (now_s() - t_origin) * 1e3);
+    };
     c->err.clear();
     c->t_front = c->t_gpu = c->t_back = 0;
     c->n_gpu_recoded = 0;
@@ -494,6 +499,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         }
     });
     c->t_front += now_s() - t_parse;
+    mark("containers", -1, t_parse);
     // chunks of up to `plane_cap` bytes of coefficient planes (device memory: three contexts in flight).  The planes stay on the device
     // for every file whose scan the GPU can re-encode; only the others need a pinned host arena (128 B per block over PCIe)
     std::vector<std::pair<int, int>> ranges;
@@ -615,6 +621,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         s.seg_status.assign(nseg_total, 0);
         s.seg_base.assign(nb + 1, 0);
         for (int q = 0; q < nb; ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
+        mark("front", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_front += now_s() - t0;
     };
@@ -624,9 +631,13 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         lepb200_ctx* ctx = c->ctx2[k % W];
         if (s.gpu_rc == 0 && !s.imgs.empty()) {
             s.gpu_rc = lepb200_decode_upload(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data());
+            mark("pack+upload", k, t0);
+            double t1 = now_s();
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_launch(ctx);
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_huffman_encode_resident(ctx, s.henc.data(), (int)s.henc.size());   // scans re-encoded from the resident planes
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_sync(ctx);
+            mark("decode+huffenc", k, t1);
+            if (trace) fprintf(stderr, "[trace]   decode kernel %.1f ms\n", lepb200_last_kernel_ms(ctx));
         }
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
@@ -654,6 +665,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             }
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_fetch(ctx, need.data(), (int)need.size(), s.seg_status.data());
         }
+        mark("fetch", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
@@ -676,6 +688,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             });
         }
         s.lf.clear();
+        mark("back", k, t0);
         std::lock_guard<std::mutex> g(tmu);
         c->t_back += now_s() - t0;
     };

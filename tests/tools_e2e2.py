@@ -42,6 +42,9 @@ for combo in combos:
     sys.stderr.flush()
     os.environ["LEPB200_TRACE"] = "1"
     fc.compress(handle, copy=False)
+    if os.environ.get("E2E_DECOMPRESS", "1") == "1":
+        sys.stderr.write("[trace] -- decompress\n")
+        fc.decompress(lhandle, copy=False)
     del os.environ["LEPB200_TRACE"]
     sys.stderr.flush()
     fc.close()
