@@ -64,7 +64,11 @@ def test_expected_failure_exit_codes(expected, compressed):
     st = {n: s for n, (s, _) in zip(names, res)}
     assert st["arithmetic.jpg"] == 42
     assert st["badzerorun.jpg"] == 1
-    assert expected["arithmetic.jpg"]["rc_skipverify"] == 42        # what the live reference CLI returned in the build container
+    # what the live reference CLI said in the build container.  Its process status is not a stable witness (custom_exit
+    # ends ONE thread with SYS_exit, memory.cc:246-247: 42 or 0 depending on which thread leaves last), the name it
+    # writes first (memory.cc:238-245) and the empty output are
+    assert expected["arithmetic.jpg"]["exit_name"] == "UNSUPPORTED_JPEG" and "lep_md5" not in expected["arithmetic.jpg"]
+    assert expected["badzerorun.jpg"]["rc_skipverify"] != 0 and "lep_md5" not in expected["badzerorun.jpg"]
 
 
 def test_every_reference_image_round_trips(expected, compressed):
@@ -86,7 +90,7 @@ def test_every_reference_image_round_trips(expected, compressed):
 def test_roundtripfail_with_verify_is_withheld(expected):
     """test_suite/test_roundtrip.sh territory: with validation on (the reference CLI's default) the file exits 41."""
     from lepton_b200 import LeptonB200FileCodec
-    assert expected["roundtripfail.jpg"]["rc_verify"] == 41
+    assert expected["roundtripfail.jpg"]["rc_verify"] == 41 or expected["roundtripfail.jpg"]["exit_name_verify"] == "ROUNDTRIP_FAILURE"
     fc = LeptonB200FileCodec(0, host_threads=4, verify=True)
     data = [open(os.path.join(REFIMG, n), "rb").read() for n in ("iphonecrop.jpg", "roundtripfail.jpg", "trunc.jpg")]
     res = fc.compress(data)
