@@ -102,6 +102,7 @@ struct lepb200_ctx {
     int huff_par_iters = 0;               // synchronisation iterations of the last batch (diagnostic)
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
+    int rc_feed = 1;                      // range pass token feed: 1 = cp.async ring in shared memory, 0 = register ring of plain loads; LEPB200_RC_FEED
     int rc_mode = 1;                      // range coder: 1 = range-only pass + parallel pieces + carry pass (lep_rangepass / piece / norm kernels),
                                           // 0 = one serial chain per segment (lep_rangecode_kernel); LEPB200_RC_MODE
     int dec_mode = 0;                     // decode kernel: 0 = by batch size (group kernel when at least dec_group_min segments are in the
@@ -357,7 +358,8 @@ int lepb200_create(lepb200_ctx** out, int device) {
         delete ctx;
         return LEPB200_ERR_CUDA;
     }
-    if (cudaFuncSetAttribute(lep_rangepass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCT_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(lep_rangepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(lep_rangepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RCT_SMEM_TABLE_BYTES) != cudaSuccess) {
         delete ctx;
         return LEPB200_ERR_CUDA;
     }
@@ -367,6 +369,7 @@ int lepb200_create(lepb200_ctx** out, int device) {
     if (const char* e = getenv("LEPB200_HUFF_SUBSEQ_BITS")) ctx->huff_sub_bits = std::max(256, std::min(1 << 20, atoi(e))) & ~31;
     if (const char* e = getenv("LEPB200_DEC_MODE")) ctx->dec_mode = atoi(e);
     if (const char* e = getenv("LEPB200_RC_MODE")) ctx->rc_mode = atoi(e);
+    if (const char* e = getenv("LEPB200_RC_FEED")) ctx->rc_feed = atoi(e);
     if (const char* e = getenv("LEPB200_DEC_THREADS")) ctx->dec_threads_max = std::max(32, atoi(e));
     if (const char* e = getenv("LEPB200_DEC_GROUP_MIN")) ctx->dec_group_min = std::max(1, atoi(e));
     if (const char* e = getenv("LEPB200_DEC_LANES")) {
@@ -732,7 +735,8 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
         const bool trace = getenv("LEPB200_TRACE") != nullptr;           // per-kernel times on stderr (diagnostics; adds a sync)
         cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
         if (trace) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->stream); }
-        lep_rangepass_kernel<<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
+        if (ctx->rc_feed) lep_rangepass_kernel<true><<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
+        else lep_rangepass_kernel<false><<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_TABLE_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
         CK(cudaGetLastError());
         unsigned long long* d_total = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_counter.p) + 128);
         lep_digit_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(ds, nseg, d_total);

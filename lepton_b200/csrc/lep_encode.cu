@@ -743,7 +743,28 @@ __device__ __forceinline__ void rr_put(RcRange& r, uint32_t bit, uint32_t prob, 
 // offset = token row | state) and one 16-bit shared-memory load.  One CTA of 128 threads per SM holds the table.
 constexpr int RCT_THREADS = 128;
 constexpr int RCT_ENTRIES = 512 * 128;
-constexpr size_t RCT_SMEM_BYTES = (size_t)RCT_ENTRIES * 2;
+constexpr int RCT_RING = 32;                                   // 16-byte token slots per thread in flight (power of two)
+constexpr size_t RCT_SMEM_TABLE_BYTES = (size_t)RCT_ENTRIES * 2;
+constexpr size_t RCT_SMEM_BYTES = RCT_SMEM_TABLE_BYTES + (size_t)RCT_RING * RCT_THREADS * 16;      // 128 KB table + 64 KB ring
+// asynchronous 16-byte copy global -> shared (LDGSTS), commit / wait of the per-thread copy groups
+__device__ __forceinline__ void rct_async16(uint4* dst_shared, const uint4* src_global) {
+#ifndef LEPB200_EMU
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_shared);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(src_global) : "memory");
+#else
+    *dst_shared = *src_global;
+#endif
+}
+__device__ __forceinline__ void rct_commit() {
+#ifndef LEPB200_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void rct_wait_ring() {               // at most RCT_RING - 1 groups still pending: the oldest slot has arrived
+#ifndef LEPB200_EMU
+    asm volatile("cp.async.wait_group %0;" :: "n"(RCT_RING - 1) : "memory");
+#endif
+}
 __device__ __forceinline__ uint32_t rct_entry(uint32_t tok9, uint32_t range) {
     const uint32_t prob = tok9 & 0xff, bit = tok9 >> 8;
     const uint32_t split = 1 + (((range - 1) * prob) >> 8);
@@ -753,13 +774,14 @@ __device__ __forceinline__ uint32_t rct_entry(uint32_t tok9, uint32_t range) {
     r <<= shift;
     return ((r - 128) << 1) | ((uint32_t)shift << 8);
 }
+template <bool kAsyncFeed>
 __global__ void __launch_bounds__(RCT_THREADS, 1)
 lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict__ order, const uint16_t* __restrict__ token_base,
                      unsigned long long* __restrict__ ck) {
 #ifndef LEPB200_EMU
     extern __shared__ uint16_t s_rct[];
 #else
-    static uint16_t s_rct[RCT_ENTRIES];
+    static uint16_t s_rct[RCT_SMEM_BYTES / 2];
 #endif
     for (int e = threadIdx.x; e < RCT_ENTRIES; e += RCT_THREADS) s_rct[e] = (uint16_t)rct_entry((uint32_t)e >> 7, 128u + ((uint32_t)e & 127u));
     __syncthreads();
@@ -785,24 +807,51 @@ lep_rangepass_kernel(SegDesc* __restrict__ segs, int nseg, const int* __restrict
     const uint4* tok4 = reinterpret_cast<const uint4*>(tok);
     const uint32_t ntok = sd.ntok;
     const uint32_t nfull = ntok / 8;
-    // RCT_DEPTH loads of 16 bytes in flight per thread (a register ring): with one CTA per SM the token streams
-    // (27 GB per 4096-image batch) only arrive in time when about 1.5 KB per thread is on its way
-    constexpr int RCT_DEPTH = 12;
-    uint4 q[RCT_DEPTH];
+    // Token feed: every thread streams its own 1.7 MB of tokens, 16 bytes (8 tokens) per 300 cycles of chain.  With plain
+    // loads into a register ring the kernel spent 55 % of its stall samples waiting for tokens (profiles/r02_round_k.log:
+    // a warp has six scoreboards, so of twelve loads in flight a wait also covers the younger load sharing the
+    // scoreboard -- half the nominal distance).  The ring therefore lives in shared memory next to the table and is filled
+    // with asynchronous copies (cp.async, LDGSTS: global -> shared without a register or a scoreboard in between):
+    // RCT_RING slots of 16 bytes per thread, slot k of thread t at (k * RCT_THREADS + t) * 16 (a warp's 32 slots are 512
+    // contiguous bytes), one commit group per slot, `cp.async.wait_group RCT_RING - 1` before a slot is read -- 256 tokens,
+    // about 5 us of chain, between a request and its use.
+    if (kAsyncFeed) {
+        uint4* ring = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(s_rct) + RCT_SMEM_TABLE_BYTES) + threadIdx.x;
+#pragma unroll 1
+        for (uint32_t j = 0; j < (uint32_t)RCT_RING; ++j) { if (j < nfull) rct_async16(ring + j * RCT_THREADS, tok4 + j); rct_commit(); }
+#pragma unroll 1
+        for (uint32_t i = 0; i < nfull; ++i) {
+            rct_wait_ring();
+            uint4* slot = ring + (i & (uint32_t)(RCT_RING - 1)) * RCT_THREADS;
+            const uint4 cur = *slot;
+            if (i + RCT_RING < nfull) rct_async16(slot, tok4 + i + RCT_RING);
+            rct_commit();
+            if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
+            RCT_STEP(cur.x & 0x1ffu); RCT_STEP((cur.x >> 16) & 0x1ffu);
+            RCT_STEP(cur.y & 0x1ffu); RCT_STEP((cur.y >> 16) & 0x1ffu);
+            RCT_STEP(cur.z & 0x1ffu); RCT_STEP((cur.z >> 16) & 0x1ffu);
+            RCT_STEP(cur.w & 0x1ffu); RCT_STEP((cur.w >> 16) & 0x1ffu);
+        }
+    } else {
+        // the round-2 feed before the ring (kept selectable for the A/B, LEPB200_RC_FEED=0): twelve plain 16-byte loads in
+        // flight per thread in registers
+        constexpr int RCT_DEPTH = 12;
+        uint4 q[RCT_DEPTH];
 #pragma unroll
-    for (int j = 0; j < RCT_DEPTH; ++j) q[j] = (uint32_t)j < nfull ? __ldg(tok4 + j) : make_uint4(0, 0, 0, 0);
-    for (uint32_t base = 0; base < nfull; base += RCT_DEPTH) {
+        for (int j = 0; j < RCT_DEPTH; ++j) q[j] = (uint32_t)j < nfull ? __ldg(tok4 + j) : make_uint4(0, 0, 0, 0);
+        for (uint32_t base = 0; base < nfull; base += RCT_DEPTH) {
 #pragma unroll
-        for (int j = 0; j < RCT_DEPTH; ++j) {
-            const uint32_t i = base + (uint32_t)j;
-            if (i < nfull) {
-                const uint4 cur = q[j];
-                q[j] = i + RCT_DEPTH < nfull ? __ldg(tok4 + i + RCT_DEPTH) : make_uint4(0, 0, 0, 0);
-                if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
-                RCT_STEP(cur.x & 0x1ffu); RCT_STEP((cur.x >> 16) & 0x1ffu);
-                RCT_STEP(cur.y & 0x1ffu); RCT_STEP((cur.y >> 16) & 0x1ffu);
-                RCT_STEP(cur.z & 0x1ffu); RCT_STEP((cur.z >> 16) & 0x1ffu);
-                RCT_STEP(cur.w & 0x1ffu); RCT_STEP((cur.w >> 16) & 0x1ffu);
+            for (int j = 0; j < RCT_DEPTH; ++j) {
+                const uint32_t i = base + (uint32_t)j;
+                if (i < nfull) {
+                    const uint4 cur = q[j];
+                    q[j] = i + RCT_DEPTH < nfull ? __ldg(tok4 + i + RCT_DEPTH) : make_uint4(0, 0, 0, 0);
+                    if (i != 0 && (i & (RC_PIECE / 8 - 1)) == 0) myck[i / (RC_PIECE / 8)] = ((unsigned long long)S << 8) | (128u + ((e & 0xfeu) >> 1));
+                    RCT_STEP(cur.x & 0x1ffu); RCT_STEP((cur.x >> 16) & 0x1ffu);
+                    RCT_STEP(cur.y & 0x1ffu); RCT_STEP((cur.y >> 16) & 0x1ffu);
+                    RCT_STEP(cur.z & 0x1ffu); RCT_STEP((cur.z >> 16) & 0x1ffu);
+                    RCT_STEP(cur.w & 0x1ffu); RCT_STEP((cur.w >> 16) & 0x1ffu);
+                }
             }
         }
     }

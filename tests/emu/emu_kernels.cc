@@ -184,7 +184,8 @@ void enc_body(void* p) {
     else if (a.stage == 1) lep_token_offsets_kernel(a.segs, a.nseg, a.total);
     else if (a.stage == 2) lep_encode_kernel(a.images, a.segs, a.nseg, a.order, a.counter, a.models, a.rows, a.row_stride, a.tokens);
     else if (a.stage == 3) lep_rangecode_kernel(a.segs, a.nseg, a.order, a.tokens);
-    else if (a.stage == 5) lep_rangepass_kernel(a.segs, a.nseg, a.order, a.tokens, a.ck);
+    else if (a.stage == 5) lep_rangepass_kernel<true>(a.segs, a.nseg, a.order, a.tokens, a.ck);
+    else if (a.stage == 4) lep_rangepass_kernel<false>(a.segs, a.nseg, a.order, a.tokens, a.ck);
     else if (a.stage == 6) lep_digit_offsets_kernel(a.segs, a.nseg, a.total);
     else if (a.stage == 7) lep_rangepiece_kernel(a.segs, a.nseg, a.tokens, a.ck, a.digits);
     else lep_rangenorm_kernel(a.segs, a.nseg, a.order, a.digits);
@@ -195,7 +196,8 @@ void enc_body(void* p) {
 // lepb200_encode_images on the emulator: count pre-pass -> token offsets -> kernel A (symbolise + model) -> kernel B
 // (range coder), with the launch shapes of lep_capi.cu.  `out` must hold sum(nseg) entries; the bytes of every stream are
 // copied into `arena` (capacity arena_cap) back to back and out[i].data points there.  grid_cap > 0 limits kernel A's
-// CTAs (persistent warps then take several segments each).  kernel: 0 = parallel range coder, 1 = serial range coder.
+// CTAs (persistent warps then take several segments each).  kernel: 0 = parallel range coder, 1 = serial range coder,
+// 2 = parallel range coder whose range pass feeds tokens through registers (LEPB200_RC_FEED=0).
 extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* images, int nimages, lepb200_stream* out, uint8_t* arena, size_t arena_cap) {
     if (nimages <= 0 || !images || !out || !arena) return LEPB200_ERR_INVALID;
     std::vector<ImageDesc> descs(nimages);
@@ -275,10 +277,10 @@ extern "C" int emu_encode_images(int kernel, int grid_cap, const lepb200_image* 
     }
     std::vector<unsigned long long> ck;
     std::vector<uint32_t> digits;
-    if (kernel == 0) {        // parallel range coder: range-only pass, digit layout, pieces, carries (lep_capi.cu: rc_mode 1)
+    if (kernel == 0 || kernel == 2) {   // parallel range coder: range-only pass, digit layout, pieces, carries (lep_capi.cu: rc_mode 1; 2 = register-ring token feed)
         ck.assign(((size_t)total_tokens >> 10) + 2 * (size_t)nseg + 8, 0);
         a.ck = ck.data();
-        a.stage = 5; emu::launch((unsigned)((nseg + RCT_THREADS - 1) / RCT_THREADS), RCT_THREADS, enc_body, &a);
+        a.stage = kernel == 0 ? 5 : 4; emu::launch((unsigned)((nseg + RCT_THREADS - 1) / RCT_THREADS), RCT_THREADS, enc_body, &a);
         unsigned long long total_digits = 0;
         a.total = &total_digits;
         a.stage = 6; emu::launch(1, 1024, enc_body, &a);

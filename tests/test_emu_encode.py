@@ -12,7 +12,9 @@ import emu  # noqa: E402
 from helpers import coef_image_from_lep, golden_leps, load_lep, oracle_decode_planes, oracle_encode_image, random_coef_image
 
 
-KERNELS = [0, 1]        # range coder: 0 = range-only pass + parallel pieces + carry pass (the default), 1 = one serial chain per segment
+# range coder: 0 = range-only pass + parallel pieces + carry pass (the default), 1 = one serial chain per segment,
+# 2 = as 0 with the range pass's tokens fed through registers instead of the cp.async ring (LEPB200_RC_FEED=0)
+KERNELS = [0, 1, 2]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
