@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <array>
@@ -206,7 +207,10 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         for (int i = 0; i < n; ++i) total_need += need[i];
         W = (n >= 64 && total_need >= (size_t(1) << 30)) ? std::max(1, c->concurrent) : 1;
         const size_t cap = c->plane_cap / (size_t)W;
-        const size_t target = std::min(cap, std::max<size_t>(total_need / (size_t)W + 1, size_t(256) << 20));
+        // LEPB200_CHUNK_SPLIT=s (tuning): s chunks per worker instead of one -- a shorter head (first kernel A) and tail (last
+        // range coder + containers) against smaller launches of kernel A
+        const int split = getenv("LEPB200_CHUNK_SPLIT") ? std::max(1, std::min(8, atoi(getenv("LEPB200_CHUNK_SPLIT")))) : 1;
+        const size_t target = std::min(cap, std::max<size_t>(total_need / (size_t)(W * split) + 1, size_t(256) << 20));
         const int chunk = std::max(1, c->chunk_images);
         int b = 0;
         size_t acc = 0;
@@ -219,6 +223,17 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         W = std::max(1, std::min(W, (int)ranges.size()));
     }
     const int pth = std::max(1, c->nthreads / W);          // host threads of one chunk's stages (W chunks share the cores)
+    // Front stages take turns (LEPB200_FRONT_TURNS=0: all W at once, a W-th of the threads each): chunk 0's parse +
+    // de-stuff + H2D with ALL host threads is done after a W-th of the time, so its Huffman kernels and kernel A start
+    // while the other chunks are still being parsed, and the chunks reach the device one after the other instead of
+    // all at the same moment (measured before: four fronts end together at 36 ms, four Huffman launches share the
+    // device until 85-148 ms, the first kernel A starts at 88 ms -- profiles/r02_round_k.log).
+    const bool front_turns = W > 1 && !(getenv("LEPB200_FRONT_TURNS") && atoi(getenv("LEPB200_FRONT_TURNS")) == 0);
+    const int fth = front_turns ? std::max(1, c->nthreads) : pth;
+    std::mutex turn_mu;
+    std::condition_variable turn_cv;
+    int front_turn = 0;
+    std::atomic<int> alive(W);                               // workers that still have a chunk to finish
     const int nchunks = (int)ranges.size();
     c->outputs.resize(n);
     std::vector<int> status(n, 0);
@@ -253,7 +268,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         // staged bytes are contiguous, so one asynchronous H2D per group pushes them while other groups are still being
         // parsed (a copy per file would spend more time in the CUDA runtime than in the parser)
         const int group = 32, ngroups = (m + group - 1) / group;
-        parallel_for(ngroups, pth, [&](int gi) {
+        parallel_for(ngroups, fth, [&](int gi) {
             const int g0 = gi * group, g1 = std::min(m, g0 + group);
             for (int i = g0; i < g1; ++i) {
                 s.js[i].reset(new Jpeg());
@@ -279,7 +294,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             for (int i = 0; i < m; ++i) poff[i] = off[i];
         }
         // pass 2: host Huffman decode where needed
-        parallel_for(m, pth, [&](int i) {
+        parallel_for(m, fth, [&](int i) {
             Jpeg& j = *s.js[i];
             for (int q = 0; q < 4; ++q) s.planes[i][q] = nullptr;
             if (j.status || eligible[i]) return;
@@ -407,8 +422,10 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     auto back = [&](int k) {
         double t0 = now_s();
         ChunkState& s = cs[k];
+        // the workers that have no chunk left leave their share of the host threads to the ones still writing containers
+        const int bth = std::max(pth, c->nthreads / std::max(1, alive.load()));
         if (s.gpu_rc == 0) {
-            parallel_for((int)s.idx.size(), pth, [&](int q) {
+            parallel_for((int)s.idx.size(), bth, [&](int q) {
                 const int i = s.begin + s.idx[q];
                 if (status[i]) return;
                 std::vector<std::pair<const uint8_t*, size_t>> ss;
@@ -421,7 +438,7 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 if (!write_lep(*s.js[s.idx[q]], s.splits[s.idx[q]], ss, c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
             });
         }
-        parallel_for((int)s.js.size(), pth, [&](int i) { s.js[i].reset(); });     // release per-chunk host state early
+        parallel_for((int)s.js.size(), bth, [&](int i) { s.js[i].reset(); });     // release per-chunk host state early
         s.js.clear(); s.planes.clear(); s.splits.clear();
         mark("back", k, t0);
         std::lock_guard<std::mutex> g(tmu);
@@ -434,7 +451,20 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
         std::vector<std::thread> workers;
         for (int w = 0; w < W; ++w)
             workers.emplace_back([&, w]() {
-                for (int k = w; k < nchunks; k += W) { front(k); gpu(k); back(k); }
+                for (int k = w; k < nchunks; k += W) {
+                    if (front_turns) {
+                        std::unique_lock<std::mutex> lk(turn_mu);
+                        turn_cv.wait(lk, [&] { return front_turn == k; });
+                    }
+                    front(k);
+                    if (front_turns) {
+                        { std::lock_guard<std::mutex> lk(turn_mu); ++front_turn; }
+                        turn_cv.notify_all();
+                    }
+                    gpu(k);
+                    if (k + W >= nchunks) --alive;           // this worker's last chunk: only its container stage is left
+                    back(k);
+                }
             });
         for (auto& t : workers) t.join();
     }
