@@ -176,6 +176,16 @@ typedef struct lepb200_henc_image {
 } lepb200_henc_image;
 int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* images, int nimages);   /* queues the kernel (async) */
 int lepb200_huffman_encode_fetch(lepb200_ctx* ctx, lepb200_henc_image* images, int nimages);      /* waits, D2H of the scan bytes */
+/* The same in `nparts` launches over consecutive images (about equal output bytes each), every launch followed by the D2H
+ * of its scan bytes on a second stream: part k travels, and the caller assembles its files, while part k + 1 is encoded.
+ * lepb200_huffman_encode_parts = parts actually queued; lepb200_huffman_encode_wait_part blocks until part `part` is on the
+ * host, fills data / status of its images and returns their index range [*first, *last). */
+int lepb200_huffman_encode_resident_parts(lepb200_ctx* ctx, lepb200_henc_image* images, int nimages, int nparts);
+int lepb200_huffman_encode_parts(const lepb200_ctx* ctx);
+int lepb200_huffman_encode_wait_part(lepb200_ctx* ctx, lepb200_henc_image* images, int nimages, int part, int* first, int* last);
+/* Per-segment status of the decode batch as soon as the decode kernel has finished (a second stream: work queued behind
+ * the kernel -- the Huffman encode above -- is not waited for).  lepb200_decode_fetch reports the same later. */
+int lepb200_decode_fetch_status(lepb200_ctx* ctx, int32_t* status_out);
 
 /* Device time of the most recent *_launch (CUDA events on the context's stream), milliseconds; <0 if none. */
 float lepb200_last_kernel_ms(lepb200_ctx* ctx);

@@ -81,6 +81,12 @@ struct lepb200_ctx {
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
     std::vector<int> henc_seg_first;      // per image: index of its first segment record
     int henc_nseg = 0;
+    // parts of the last lepb200_huffman_encode_resident_parts call: image range, segment range, byte range of the output,
+    // the event behind the part's D2H copies on copy_stream
+    struct HEncPart { int i0, i1, s0, s1; size_t b0, b1; cudaEvent_t done; };
+    std::vector<HEncPart> henc_parts;
+    std::vector<cudaEvent_t> part_events;      // pool: [2k] = part k's kernel, [2k + 1] = part k's copies
+    cudaStream_t copy_stream = nullptr;        // D2H copies that run under the kernels of `stream`
     HostBuf h_segs, h_dense, h_stage, h_hjobs, h_hpar;
     size_t resident_plane_total = 0;
     int resident_images = 0;
@@ -353,7 +359,8 @@ int lepb200_create(lepb200_ctx** out, int device) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return LEPB200_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess ||
         cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->ev_mid) != cudaSuccess) {
         delete ctx;
         return LEPB200_ERR_CUDA;
@@ -394,6 +401,8 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_mid);
+    for (cudaEvent_t e : ctx->part_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -843,8 +852,9 @@ static bool build_enc_table(const lepb200_hufftable& in, HEncTable& t) {
     return true;
 }
 
-int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n) {
+static int henc_launch(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n, int nparts) {
     if (!ctx || !imgs || n <= 0) return LEPB200_ERR_INVALID;
+    ctx->henc_parts.clear();
     if (!ctx->launched || ctx->is_encode || n != (int)ctx->images.size()) { ctx->err = "huffman_encode_resident: needs the decode batch just launched on this context"; return LEPB200_ERR_INVALID; }
     CK(cudaSetDevice(ctx->device));
     std::vector<HEncImage> hi(n);
@@ -911,10 +921,79 @@ int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* imgs, 
     CK(cudaMemcpyAsync(ctx->d_henc_segs.p, hs.data(), sizeof(HEncSeg) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_henc_tabs.p, tabs.data(), sizeof(HEncTable) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
     const int nseg = (int)hs.size();
-    lep_huffencode_kernel<<<(nseg + HENC_WARPS - 1) / HENC_WARPS, HENC_WARPS * 32, 0, ctx->stream>>>(
-        static_cast<const HEncImage*>(ctx->d_henc_imgs.p), static_cast<HEncSeg*>(ctx->d_henc_segs.p), nseg, static_cast<const HEncTable*>(ctx->d_henc_tabs.p));
-    CK(cudaGetLastError());
-    ctx->launches += 1;
+    if (nparts <= 0) {                    // one launch, the caller fetches everything with lepb200_huffman_encode_fetch
+        lep_huffencode_kernel<<<(nseg + HENC_WARPS - 1) / HENC_WARPS, HENC_WARPS * 32, 0, ctx->stream>>>(
+            static_cast<const HEncImage*>(ctx->d_henc_imgs.p), static_cast<HEncSeg*>(ctx->d_henc_segs.p), nseg, static_cast<const HEncTable*>(ctx->d_henc_tabs.p));
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+        return LEPB200_OK;
+    }
+    // parts of consecutive images with about equal output bytes: one launch each, and behind each launch the D2H of its
+    // scan bytes and segment records on the copy stream -- part k travels (and the host assembles its files) while
+    // part k + 1 is encoded
+    CK(ctx->h_henc_out.reserve(total + 256));
+    CK(ctx->h_henc_segs.reserve(sizeof(HEncSeg) * hs.size()));
+    while (ctx->part_events.size() < 2 * (size_t)nparts) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->part_events.push_back(e);
+    }
+    int i0 = 0;
+    for (int k = 0; k < nparts && i0 < n; ++k) {
+        const size_t want_end = k + 1 == nparts ? total : total / nparts * (k + 1);
+        int i1 = i0;
+        size_t bend = 0;
+        auto end_of = [&](int i) { return ctx->henc_off[i] == SIZE_MAX ? (size_t)0 : ctx->henc_off[i] + align_up((size_t)imgs[i].scan_bytes + 16, 256); };
+        while (i1 < n && (k + 1 == nparts || std::max(bend, end_of(i1)) <= want_end || i1 == i0)) { bend = std::max(bend, end_of(i1)); ++i1; }
+        lepb200_ctx::HEncPart pt;
+        pt.i0 = i0; pt.i1 = i1; pt.s0 = -1; pt.s1 = -1; pt.b0 = SIZE_MAX; pt.b1 = 0; pt.done = ctx->part_events[2 * k + 1];
+        for (int i = i0; i < i1; ++i) {
+            if (ctx->henc_off[i] == SIZE_MAX) continue;
+            if (pt.s0 < 0) pt.s0 = ctx->henc_seg_first[i];
+            pt.s1 = ctx->henc_seg_first[i] + imgs[i].nseg;
+            pt.b0 = std::min(pt.b0, ctx->henc_off[i]);
+            pt.b1 = std::max(pt.b1, ctx->henc_off[i] + (size_t)imgs[i].scan_bytes);
+        }
+        if (pt.s0 >= 0) {
+            const int ns = pt.s1 - pt.s0;
+            lep_huffencode_kernel<<<(ns + HENC_WARPS - 1) / HENC_WARPS, HENC_WARPS * 32, 0, ctx->stream>>>(
+                static_cast<const HEncImage*>(ctx->d_henc_imgs.p), static_cast<HEncSeg*>(ctx->d_henc_segs.p) + pt.s0, ns, static_cast<const HEncTable*>(ctx->d_henc_tabs.p));
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+            CK(cudaEventRecord(ctx->part_events[2 * k], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->part_events[2 * k], 0));
+            CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->h_henc_out.p) + pt.b0, static_cast<const uint8_t*>(ctx->d_henc_out.p) + pt.b0, pt.b1 - pt.b0, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaMemcpyAsync(static_cast<HEncSeg*>(ctx->h_henc_segs.p) + pt.s0, static_cast<const HEncSeg*>(ctx->d_henc_segs.p) + pt.s0, sizeof(HEncSeg) * (size_t)ns, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        CK(cudaEventRecord(pt.done, ctx->copy_stream));
+        ctx->henc_parts.push_back(pt);
+        i0 = i1;
+    }
+    return LEPB200_OK;
+}
+
+int lepb200_huffman_encode_resident(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n) { return henc_launch(ctx, imgs, n, 0); }
+
+int lepb200_huffman_encode_resident_parts(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n, int nparts) {
+    return henc_launch(ctx, imgs, n, std::max(1, std::min(16, nparts)));
+}
+
+int lepb200_huffman_encode_parts(const lepb200_ctx* ctx) { return ctx ? (int)ctx->henc_parts.size() : 0; }
+
+int lepb200_huffman_encode_wait_part(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n, int part, int* first, int* last) {
+    if (!ctx || !imgs || !first || !last || n != (int)ctx->henc_off.size() || part < 0 || part >= (int)ctx->henc_parts.size()) return LEPB200_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const lepb200_ctx::HEncPart& pt = ctx->henc_parts[part];
+    CK(cudaEventSynchronize(pt.done));
+    const HEncSeg* hs = static_cast<const HEncSeg*>(ctx->h_henc_segs.p);
+    for (int i = pt.i0; i < pt.i1; ++i) {
+        if (ctx->henc_off[i] == SIZE_MAX) continue;
+        imgs[i].data = static_cast<const uint8_t*>(ctx->h_henc_out.p) + ctx->henc_off[i];
+        int st = 0;
+        for (int k = 0; k < imgs[i].nseg; ++k) if (hs[ctx->henc_seg_first[i] + k].status) st = 1;
+        imgs[i].status = st;
+    }
+    *first = pt.i0; *last = pt.i1;
     return LEPB200_OK;
 }
 
@@ -1054,6 +1133,19 @@ int lepb200_decode_fetch(lepb200_ctx* ctx, const lepb200_image* images, int nima
         alg += (uint64_t)ctx->seg_blocks[s] * 128 + ctx->segs[s].cap;
     }
     ctx->alg_bytes = alg;
+    return LEPB200_OK;
+}
+
+int lepb200_decode_fetch_status(lepb200_ctx* ctx, int32_t* status_out) {
+    if (!ctx || !status_out || !ctx->launched || ctx->is_encode) { if (ctx) ctx->err = "decode_fetch_status without decode_launch"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size();
+    CK(ctx->h_segs.reserve(sizeof(SegDesc) * nseg));
+    SegDesc* hs = static_cast<SegDesc*>(ctx->h_segs.p);
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));              // the decode kernel, not what was queued behind it
+    CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    for (int s = 0; s < nseg; ++s) status_out[s] = hs[s].status;
     return LEPB200_OK;
 }
 

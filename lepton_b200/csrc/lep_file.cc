@@ -658,37 +658,70 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         std::lock_guard<std::mutex> g(tmu);
         c->t_front += now_s() - t0;
     };
-    auto gpu = [&](int k) {               // H2D of the streams + decode kernel
+    // parts of the device Huffman encode whose D2H and JPEG assembly run under the encode of the next part
+    // (LEPB200_HENC_PARTS, 1 = one launch, everything after it as before round 2's last change)
+    const int henc_parts_want = getenv("LEPB200_HENC_PARTS") ? std::max(1, std::min(16, atoi(getenv("LEPB200_HENC_PARTS")))) : 4;
+    auto gpu = [&](int k) {               // H2D of the streams + decode kernel + Huffman encode of the resident planes, all queued
         double t0 = now_s();
         DChunk& s = cs[k];
         lepb200_ctx* ctx = c->ctx2[k % W];
         if (s.gpu_rc == 0 && !s.imgs.empty()) {
             s.gpu_rc = lepb200_decode_upload(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data());
             mark("pack+upload", k, t0);
-            double t1 = now_s();
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_launch(ctx);
-            if (s.gpu_rc == 0) s.gpu_rc = lepb200_huffman_encode_resident(ctx, s.henc.data(), (int)s.henc.size());   // scans re-encoded from the resident planes
-            if (s.gpu_rc == 0) s.gpu_rc = lepb200_sync(ctx);
-            mark("decode+huffenc", k, t1);
-            if (trace) fprintf(stderr, "[trace]   decode kernel %.1f ms\n", lepb200_last_kernel_ms(ctx));
+            const int parts = s.imgs.size() >= 256 ? henc_parts_want : 1;
+            if (s.gpu_rc == 0) s.gpu_rc = lepb200_huffman_encode_resident_parts(ctx, s.henc.data(), (int)s.henc.size(), parts);   // scans re-encoded from the resident planes
         }
         std::lock_guard<std::mutex> g(tmu);
         c->t_gpu += now_s() - t0;
     };
-    auto fetch = [&](int k) {             // D2H of the planes (128 B per block), overlapping the next chunk's kernel
+    // JPEG of one batch image from the scan the device produced
+    auto assemble = [&](DChunk& s, int q) {
+        const int li = s.idx[q], i = s.begin + li;
+        for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t)
+            if (s.seg_status[t]) { status[i] = s.seg_status[t]; return; }
+        std::string err;
+        c->n_gpu_recoded++;
+        if (!assemble_baseline(*s.lf[li], s.gsetup[q], s.henc[q].data, c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
+    };
+    auto fetch_back = [&](int k) {
         double t0 = now_s();
         DChunk& s = cs[k];
-        if (s.gpu_rc == 0 && !s.imgs.empty()) {
-            lepb200_ctx* ctx = c->ctx2[k % W];
-            s.gpu_rc = lepb200_huffman_encode_fetch(ctx, s.henc.data(), (int)s.henc.size());
+        const int nb = (int)s.imgs.size();
+        std::vector<uint8_t> done(nb, 0);
+        lepb200_ctx* ctx = nb ? c->ctx2[k % W] : nullptr;
+        if (s.gpu_rc == 0 && nb) {
+            // decode status as soon as the decode kernel is through, then the parts of the device re-encode as they arrive
+            s.gpu_rc = lepb200_decode_fetch_status(ctx, s.seg_status.data());
+            mark("decode", k, t0);
+            const int parts = s.gpu_rc == 0 ? lepb200_huffman_encode_parts(ctx) : 0;
+            for (int p = 0; p < parts && s.gpu_rc == 0; ++p) {
+                double tp = now_s();
+                int q0 = 0, q1 = 0;
+                s.gpu_rc = lepb200_huffman_encode_wait_part(ctx, s.henc.data(), nb, p, &q0, &q1);
+                if (s.gpu_rc) break;
+                mark("huffenc part", k, tp);
+                tp = now_s();
+                parallel_for(q1 - q0, pth, [&](int d) {
+                    const int q = q0 + d;
+                    const lepb200_henc_image& he = s.henc[q];
+                    if (!(he.scan_bytes && he.status == 0 && he.data)) return;
+                    assemble(s, q);
+                    done[q] = 1;
+                });
+                mark("assemble part", k, tp);
+            }
+        }
+        double t1 = now_s();
+        if (s.gpu_rc == 0 && nb) {
             // planes come back only for the files the host has to re-encode
             std::vector<lepb200_image> need(s.imgs);
-            for (size_t q = 0; q < need.size(); ++q) {
+            for (int q = 0; q < nb; ++q) {
                 const lepb200_henc_image& he = s.henc[q];
-                if (he.scan_bytes == 0) continue;                                  // planned for the host: arena pointers are in place
                 const int li = s.idx[q];
                 const Jpeg& j = s.lf[li]->j;
-                if (he.status == 0 && he.data) { for (int t = 0; t < 3; ++t) need[q].planes[t] = nullptr; continue; }
+                if (done[q]) { for (int t = 0; t < 3; ++t) need[q].planes[t] = nullptr; continue; }
+                if (he.scan_bytes == 0) continue;                                  // planned for the host: arena pointers are in place
                 // the device re-encode did not produce the byte counts the handoffs promise: fetch the planes after all
                 size_t tot = 0;
                 for (int t = 0; t < j.ncmp; ++t) tot += plane_bytes(j, t) / 2;
@@ -696,41 +729,33 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
                 int16_t* p = s.fallback[q].data();
                 for (int t = 0; t < j.ncmp; ++t) { s.planes[li][t] = p; need[q].planes[t] = p; p += plane_bytes(j, t) / 2; }
             }
-            if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_fetch(ctx, need.data(), (int)need.size(), s.seg_status.data());
+            s.gpu_rc = lepb200_decode_fetch(ctx, need.data(), nb, s.seg_status.data());
+            if (trace) fprintf(stderr, "[trace]   decode kernel %.1f ms\n", lepb200_last_kernel_ms(ctx));
         }
-        mark("fetch", k, t0);
-        std::lock_guard<std::mutex> g(tmu);
-        c->t_gpu += now_s() - t0;
-    };
-    auto back = [&](int k) {
-        double t0 = now_s();
-        DChunk& s = cs[k];
+        mark("fetch", k, t1);
+        t1 = now_s();
         if (s.gpu_rc == 0) {
-            parallel_for((int)s.imgs.size(), pth, [&](int q) {
+            parallel_for(nb, pth, [&](int q) {
+                if (done[q]) return;
                 const int li = s.idx[q], i = s.begin + li;
                 for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t)
                     if (s.seg_status[t]) { status[i] = s.seg_status[t]; return; }
                 std::string err;
-                const lepb200_henc_image& he = s.henc[q];
-                const bool on_gpu = he.scan_bytes && he.status == 0 && he.data;
-                if (on_gpu) c->n_gpu_recoded++;
-                const bool ok = on_gpu
-                                    ? assemble_baseline(*s.lf[li], s.gsetup[q], he.data, c->outputs[i], err)
-                                    : recode_baseline(*s.lf[li], s.planes[li].data(), c->outputs[i], err);
-                if (!ok) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
+                if (!recode_baseline(*s.lf[li], s.planes[li].data(), c->outputs[i], err)) { status[i] = NOT_HANDLED; c->outputs[i].clear(); }
             });
         }
         s.lf.clear();
-        mark("back", k, t0);
+        mark("back", k, t1);
         std::lock_guard<std::mutex> g(tmu);
-        c->t_back += now_s() - t0;
+        c->t_gpu += t1 - t0;
+        c->t_back += now_s() - t1;
     };
     // W workers; worker w takes the chunks w, w + W, ... through front -> gpu -> fetch -> back on context / arena w
     {
         std::vector<std::thread> workers;
         for (int w = 0; w < W; ++w)
             workers.emplace_back([&, w]() {
-                for (int k = w; k < nchunks; k += W) { front(k); gpu(k); fetch(k); back(k); }
+                for (int k = w; k < nchunks; k += W) { front(k); gpu(k); fetch_back(k); }
             });
         for (auto& t : workers) t.join();
     }
