@@ -224,6 +224,11 @@ int lepb200_device_available(void);
 typedef struct lepb200_codec lepb200_codec;
 typedef struct lepb200_buffer { const uint8_t* data; size_t len; } lepb200_buffer;
 typedef struct lepb200_result { const uint8_t* data; size_t len; int32_t status; } lepb200_result; /* data owned by the codec */
+/* lepb200_decode_upload for streams that lie in pieces (the mux packets of a .lep file, src/io/MuxReader.hh:230-283): in[s].len
+ * is the length of segment s's stream, its bytes are the pieces spans[span_first[s] .. span_first[s + 1]) in order; in[s].data
+ * is not read.  The pieces are gathered straight into the context's pinned staging buffer (no intermediate copy). */
+int lepb200_decode_upload_gather(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in,
+                                 const lepb200_buffer* spans, const uint32_t* span_first);
 
 int lepb200_codec_create(lepb200_codec** out, int device, int host_threads /* 0 = all cores */);
 void lepb200_codec_destroy(lepb200_codec* codec);

@@ -1020,7 +1020,8 @@ int lepb200_huffman_encode_fetch(lepb200_ctx* ctx, lepb200_henc_image* imgs, int
 }
 
 // ------------------------------------------------------------------------------------------------ decode
-int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in) {
+static int decode_upload_impl(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in,
+                              const lepb200_buffer* spans, const uint32_t* span_first) {
     if (!ctx || !in) return LEPB200_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->d_tokens.release();              // the encoder's token arena (the largest buffer of that direction) is not needed on the way back
@@ -1050,8 +1051,16 @@ int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
         while (s1 < nseg && (k + 1 == nslices || (size_t)(ctx->segs[s1].stream - base) < want_end)) ++s1;
         const int nt = std::max(1, std::min(ctx->host_threads, s1 - s0));
         auto pack = [&](int t) {
-            for (int s = s0 + t; s < s1; s += nt)
-                if (in[s].len) memcpy(hs + (ctx->segs[s].stream - base), in[s].data, in[s].len);
+            for (int s = s0 + t; s < s1; s += nt) {
+                uint8_t* dst = hs + (ctx->segs[s].stream - base);
+                if (!spans) { if (in[s].len) memcpy(dst, in[s].data, in[s].len); continue; }
+                size_t room = in[s].len;                       // the pieces of a stream as they lie in the caller's file
+                for (uint32_t q = span_first[s]; q < span_first[s + 1] && room; ++q) {
+                    const size_t n = std::min(room, spans[q].len);
+                    memcpy(dst, spans[q].data, n);
+                    dst += n; room -= n;
+                }
+            }
         };
         if (nt == 1) pack(0);
         else {
@@ -1066,6 +1075,16 @@ int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nim
     }
     ctx->have_batch = true;
     return LEPB200_OK;
+}
+
+int lepb200_decode_upload(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in) {
+    return decode_upload_impl(ctx, images, nimages, in, nullptr, nullptr);
+}
+
+int lepb200_decode_upload_gather(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in,
+                                 const lepb200_buffer* spans, const uint32_t* span_first) {
+    if (!spans || !span_first) return LEPB200_ERR_INVALID;
+    return decode_upload_impl(ctx, images, nimages, in, spans, span_first);
 }
 
 int lepb200_decode_launch(lepb200_ctx* ctx) {

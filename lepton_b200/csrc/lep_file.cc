@@ -523,7 +523,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
     std::vector<size_t> pbytes(n, 0);
     parallel_for(n, c->nthreads, [&](int i) {
         all[i].reset(new LepFile());
-        if (read_lep(leps[i].data, leps[i].len, *all[i])) {
+        if (read_lep(leps[i].data, leps[i].len, *all[i], /*lazy=*/true)) {    // mux packets stay where they are: gathered into the staging buffer
             for (int q = 0; q < all[i]->j.ncmp; ++q) pbytes[i] += (plane_bytes(all[i]->j, q) + 255) & ~size_t(255);
             if (pbytes[i] > c->plane_cap) { all[i]->status = NOT_HANDLED; all[i]->error = "image larger than the per-chunk device memory budget"; pbytes[i] = 0; }
         }
@@ -566,6 +566,8 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         std::vector<lepb200_image> imgs;
         std::vector<int> idx;
         std::vector<lepb200_stream> streams;
+        std::vector<lepb200_buffer> spans;          // mux packets of all streams of the chunk, in stream order
+        std::vector<uint32_t> span_first;           // per stream: its first packet in `spans` (+ one past the end)
         std::vector<int32_t> seg_status;
         std::vector<int> seg_base;
         std::vector<lepb200_henc_image> henc;       // per batch image: scan re-encoded on the device when scan_bytes != 0
@@ -645,12 +647,15 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             for (int t = 0; t < lf.nseg; ++t) {
                 lepb200_stream st;
                 memset(&st, 0, sizeof(st));
-                st.data = lf.streams[t].data();
-                st.len = lf.streams[t].size();
+                st.data = nullptr;
+                st.len = lf.stream_len[t];
+                s.span_first.push_back((uint32_t)s.spans.size());
+                for (const auto& sp : lf.spans[t]) s.spans.push_back(lepb200_buffer{sp.first, sp.second});
                 s.streams.push_back(st);
             }
             nseg_total += lf.nseg;
         }
+        s.span_first.push_back((uint32_t)s.spans.size());
         s.seg_status.assign(nseg_total, 0);
         s.seg_base.assign(nb + 1, 0);
         for (int q = 0; q < nb; ++q) s.seg_base[q + 1] = s.seg_base[q] + s.imgs[q].nseg;
@@ -666,7 +671,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
         DChunk& s = cs[k];
         lepb200_ctx* ctx = c->ctx2[k % W];
         if (s.gpu_rc == 0 && !s.imgs.empty()) {
-            s.gpu_rc = lepb200_decode_upload(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data());
+            s.gpu_rc = lepb200_decode_upload_gather(ctx, s.imgs.data(), (int)s.imgs.size(), s.streams.data(), s.spans.data(), s.span_first.data());
             mark("pack+upload", k, t0);
             if (s.gpu_rc == 0) s.gpu_rc = lepb200_decode_launch(ctx);
             const int parts = s.imgs.size() >= 256 ? henc_parts_want : 1;

@@ -159,10 +159,14 @@ struct LepFile {
     bool legacy = false;             // no handoff table: segment rows read from the payload (vp8_decoder.cc:337-369)
     uint32_t eee[7] = {0};
     std::vector<std::vector<uint8_t>> streams;   // demuxed per-segment bool-coder streams
+    // read_lep(..., lazy = true): the mux packets of every stream as (pointer into the caller's file, length) instead of a
+    // copy -- the batch decoder gathers them straight into its pinned staging buffer; `streams` then stays empty
+    std::vector<std::vector<std::pair<const uint8_t*, uint32_t>>> spans;
+    std::vector<size_t> stream_len;
     int status = OK;
     std::string error;
 };
-bool read_lep(const uint8_t* data, size_t n, LepFile& lf);
+bool read_lep(const uint8_t* data, size_t n, LepFile& lf, bool lazy = false);
 // Set-up for re-encoding the scan on the GPU (lepb200_huffman_encode_resident): false when the file needs the host
 // re-encoder (progressive, truncated, several scans, scan order != frame order, restart-marker budget).
 struct GpuRecodeSetup {

@@ -29,7 +29,7 @@ const uint8_t k_zigzag_to_aligned[64] = {
     33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48};
 }  // namespace
 
-bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
+bool read_lep(const uint8_t* d, size_t n, LepFile& lf, bool lazy) {
     if (n < 28 + 3 + 4 || d[0] != 0xCF || d[1] != 0x84) return lfail(lf, VERSION_UNSUPPORTED, "not a .lep file");
     lf.version = d[2]; lf.flag = d[3]; lf.nseg = d[4];
     if (lf.version != 1) return lfail(lf, NOT_HANDLED, "only version 1 (zlib header) containers are handled");
@@ -185,7 +185,8 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
             return lfail(lf, STREAM_INCONSISTENT, "thread-segment rows out of order or beyond the image");
     }
     // demux (src/io/MuxReader.hh:230-283); the last 4 bytes are the file-size trailer
-    lf.streams.assign(16, std::vector<uint8_t>());
+    if (lazy) { lf.spans.assign(16, {}); lf.stream_len.assign(16, 0); }
+    else lf.streams.assign(16, std::vector<uint8_t>());
     while (q + 3 <= end) {
         const uint8_t hd = d[q];
         const int sid = hd & 15, flags = (hd >> 4) & 3;
@@ -193,10 +194,12 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf) {
         if (flags == 0) { len = (size_t)d[q + 1] + 256 * (size_t)d[q + 2] + 1; skip = 3; }
         else { len = (size_t)1024 << (2 * flags); skip = 1; }
         if (q + skip + len > end) return lfail(lf, SHORT_READ, "mux packet runs past the end of the file");
-        lf.streams[sid].insert(lf.streams[sid].end(), d + q + skip, d + q + skip + len);
+        if (lazy) { lf.spans[sid].emplace_back(d + q + skip, (uint32_t)len); lf.stream_len[sid] += len; }
+        else lf.streams[sid].insert(lf.streams[sid].end(), d + q + skip, d + q + skip + len);
         q += skip + len;
     }
-    lf.streams.resize(lf.nseg);
+    if (lazy) { lf.spans.resize(lf.nseg); lf.stream_len.resize(lf.nseg); }
+    else lf.streams.resize(lf.nseg);
     return true;
 }
 
