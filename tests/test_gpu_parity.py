@@ -212,6 +212,39 @@ def test_file_level_roundtrip_jpeg_lep_jpeg():
     fc.close()
 
 
+@pytest.mark.timeout(600, method="thread")        # added without a GPU at hand: a hang must cost this test, not the box
+@pytest.mark.parametrize("parts", ["", "1", "7"])
+def test_decompress_large_batch_device_reencode_in_parts(parts, monkeypatch):
+    """A batch large enough (>= 256 files) for the device Huffman encode to run in several launches whose D2H copies and
+    JPEG assembly overlap the next launch (lepb200_huffman_encode_resident_parts): device-re-encoded files, files the host
+    re-encodes (truncated / progressive) and a damaged .lep in ONE call; 1 part and an odd number of parts give the same bytes."""
+    import os
+    from helpers import GOLDEN
+    from lepton_b200 import LeptonB200FileCodec
+    if parts:
+        monkeypatch.setenv("LEPB200_HENC_PARTS", parts)
+    names = ["android.jpg", "androidcrop.jpg", "grayscale.jpg", "iphonecrop2.jpg", "trailingrst.jpg", "colorswap.jpg",
+             "gray2sf.jpg", "iphoneprogressive.jpg", "androidtrail.jpg", "narrowrst.jpg"]
+    jpegs = [open(os.path.join(GOLDEN, n), "rb").read() for n in names]
+    leps = [open(os.path.join(GOLDEN, n[:-4] + ".lep"), "rb").read() for n in names]
+    order = [(7 * k + k // 10) % len(names) for k in range(300)]
+    batch = [leps[i] for i in order]
+    bad = bytearray(leps[0])
+    for q in range(len(bad) // 2, len(bad) // 2 + 40):
+        bad[q] ^= 0x5a
+    batch[123] = bytes(bad)
+    fc = LeptonB200FileCodec(0, host_threads=8)
+    back = fc.decompress(batch)
+    n_dev = fc.last_gpu_recoded
+    fc.close()
+    for k, (i, (st, out)) in enumerate(zip(order, back)):
+        if k == 123:
+            assert st != 0 or out != jpegs[i]
+            continue
+        assert st == 0 and out == jpegs[i], (k, names[i], st)
+    assert n_dev >= 150, n_dev
+
+
 @pytest.mark.parametrize("gpu_huffman", [True, False])
 def test_file_level_compress_both_huffman_paths(gpu_huffman):
     """Huffman decode on the GPU (one thread per image) and on host threads must give the same, reference-identical

@@ -1,7 +1,7 @@
 """Diagnostic (not a test): one 4096-file compress / decompress through the file API for several environment settings, with
 the stage timeline (LEPB200_TRACE) of one call each.
 
-    python tests/tools_e2e2.py [files] "K=V,K=V" "K=V" ...
+    python tests/tools_e2e2.py [files] "K=V,K=V" "K=V" ...        (E2E_CHUNK_IMAGES=n as one of the K=V: files per chunk)
 """
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,7 +20,8 @@ for combo in combos:
     kv = dict(x.split("=") for x in combo.split(",") if x)
     for k, v in kv.items():
         os.environ[k] = v
-    fc = LeptonB200FileCodec(0, host_threads=16)
+    ci = int(os.environ.get("E2E_CHUNK_IMAGES", "0"))
+    fc = LeptonB200FileCodec(0, host_threads=16, chunk_images=ci) if ci else LeptonB200FileCodec(0, host_threads=16)
     r = fc.compress(handle, copy=leps is None)
     assert all(st == 0 for st, _ in r)
     if leps is None:
