@@ -77,30 +77,38 @@ Splits select_splits(const Jpeg& j, unsigned max_threads, unsigned min_threads, 
 // ------------------------------------------------------------------------------------------------
 // MuxWriter (src/io/MuxReader.hh:336-522), version 1 (no EOF marker)
 // ------------------------------------------------------------------------------------------------
+// The writer's decisions -- when a stream is flushed, as packets of which kind -- depend only on how many bytes each
+// stream has been given so far, never on the bytes.  So the writer is kept data-free: it is driven with lengths and
+// emits the packet list (stream id, header bytes, offset and length inside the stream); mux_streams copies by that
+// list on the host, the device gather kernel (lep_capi.cu, lepb200_encode_fetch_files) by the same list on the GPU.
 namespace {
 struct Mux {
-    enum { NS = 16, MIN_OFFSET = 3, MAX_BUFFER_LAG = 65537 };
-    std::vector<uint8_t>& out;
-    std::vector<uint8_t> buf[NS];
-    uint32_t off[NS], flushed[NS], low_water[NS];
+    enum { NS = 16, MAX_BUFFER_LAG = 65537 };
+    std::vector<MuxPacket>& out;
+    uint32_t pending[NS];            // bytes written to the stream's buffer and not yet flushed
+    uint32_t consumed[NS];           // offset inside the stream of the first pending byte
+    uint32_t flushed[NS], low_water[NS];
+    bool opened[NS];
     uint32_t total_written = 0;
-    explicit Mux(std::vector<uint8_t>& o) : out(o) { for (int i = 0; i < NS; ++i) off[i] = flushed[i] = low_water[i] = 0; }
+    explicit Mux(std::vector<MuxPacket>& o) : out(o) { for (int i = 0; i < NS; ++i) { pending[i] = consumed[i] = flushed[i] = low_water[i] = 0; opened[i] = false; } }
 
     static uint32_t high_water(uint32_t f) { return (f & 0xffffc000u) ? 65536 : ((f & 0xfffff000u) ? 16384 : 4096); }
 
+    void emit(int id, uint8_t nhdr, uint8_t h0, uint8_t h1, uint8_t h2, uint32_t len) {
+        MuxPacket p;
+        p.id = (uint8_t)id; p.nhdr = nhdr; p.hdr[0] = h0; p.hdr[1] = h1; p.hdr[2] = h2;
+        p.src_off = consumed[id]; p.len = len;
+        out.push_back(p);
+        consumed[id] += len; pending[id] -= len;
+        total_written += len; flushed[id] += len;
+    }
     void flush_full(int id, uint32_t n) {
         if (!n) return;
         do {
-            uint32_t o = off[id];
-            uint32_t w = std::min(n, 65536u);
-            buf[id][o - 3] = (uint8_t)id;
-            buf[id][o - 2] = (uint8_t)((w - 1) & 0xff);
-            buf[id][o - 1] = (uint8_t)(((w - 1) >> 8) & 0xff);
-            out.insert(out.end(), buf[id].begin() + (o - 3), buf[id].begin() + o + w);
-            total_written += w; flushed[id] += w; off[id] += w; n -= w;
+            const uint32_t w = std::min(n, 65536u);
+            emit(id, 3, (uint8_t)id, (uint8_t)((w - 1) & 0xff), (uint8_t)(((w - 1) >> 8) & 0xff), w);
+            n -= w;
         } while (n > 0);
-        off[id] = MIN_OFFSET;
-        buf[id].resize(MIN_OFFSET);
         low_water[id] = total_written;
     }
     void flush_partial(int id, uint32_t n) {
@@ -111,57 +119,51 @@ struct Mux {
         else if (n < 65536) { if (n > 32768) { flush_full(id, n); return; } len = 16384; code |= 2 << 4; }
         else { if (n > 131072) { flush_full(id, n); return; } len = 65536; code |= 3 << 4; }
         for (uint32_t w = 0; w + len <= n; w += len) {
-            uint32_t o = off[id];
-            if (o == buf[id].size()) continue;
-            buf[id][o - 1] = code;
-            out.insert(out.end(), buf[id].begin() + (o - 1), buf[id].begin() + o + len);
-            total_written += len; flushed[id] += len; off[id] += len;
-            if (off[id] > 65539) {
-                buf[id].erase(buf[id].begin() + MIN_OFFSET, buf[id].begin() + off[id]);
-                off[id] = MIN_OFFSET;
-            }
+            if (pending[id] == 0) continue;
+            emit(id, 1, code, 0, 0, len);
         }
-        uint32_t delta = (uint32_t)buf[id].size() - off[id];
+        const uint32_t delta = pending[id];
         low_water[id] = delta > total_written ? 0 : total_written - delta;
     }
     void flush(int id) {
         for (int i = 0; i < NS; ++i) {
-            uint32_t n = (uint32_t)buf[i].size() - off[i];
+            const uint32_t n = pending[i];
             if (i == id || !n) continue;
-            bool urgent = total_written - low_water[i] > MAX_BUFFER_LAG;
+            const bool urgent = total_written - low_water[i] > MAX_BUFFER_LAG;
             if (n < 4096) { if (urgent) flush_full(i, n); }
             else if (urgent && n < 16384) flush_full(i, n);
             else flush_partial(i, n);
         }
-        flush_partial(id, (uint32_t)buf[id].size() - off[id]);
+        flush_partial(id, pending[id]);
     }
-    void write(int id, const uint8_t* d, uint32_t n) {
-        if (buf[id].empty()) { buf[id].reserve(16387); buf[id].resize(MIN_OFFSET); off[id] = MIN_OFFSET; }
-        buf[id].insert(buf[id].end(), d, d + n);
-        if (buf[id].size() >= off[id] + high_water(flushed[id])) flush(id);
+    void write(int id, uint32_t n) {
+        opened[id] = true;
+        pending[id] += n;
+        if (pending[id] >= high_water(flushed[id])) flush(id);
     }
     void close() {
         for (int i = 0; i < NS; ++i)
-            if (off[i] != buf[i].size()) flush_full(i, (uint32_t)buf[i].size() - off[i]);
+            if (pending[i]) flush_full(i, pending[i]);
     }
 };
 }  // namespace
 
-void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, std::vector<uint8_t>& out) {
+void plan_mux(const size_t* lens, int nseg, std::vector<MuxPacket>& out) {
     // interleave schedule of vp8_full_encoder (vp8_encoder.cc:575-594): 256 bytes, then 4096, then 65536 per turn
+    out.clear();
     Mux mux(out);
-    std::vector<size_t> done(streams.size(), 0);
+    std::vector<size_t> done((size_t)std::max(nseg, 0), 0);
     bool any = true;
     while (any) {
         any = false;
-        for (size_t i = 0; i < streams.size() && i < 16; ++i) {
-            if (streams[i].second > done[i]) {
+        for (int i = 0; i < nseg && i < 16; ++i) {
+            if (lens[i] > done[i]) {
                 any = true;
                 size_t maxw = 65536;
                 if (done[i] == 0) maxw = 256;
                 else if (done[i] == 256) maxw = 4096;
-                size_t w = std::min(maxw, streams[i].second - done[i]);
-                mux.write((int)i, streams[i].first + done[i], (uint32_t)w);
+                const size_t w = std::min(maxw, lens[i] - done[i]);
+                mux.write(i, (uint32_t)w);
                 done[i] += w;
             }
         }
@@ -169,11 +171,21 @@ void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, 
     mux.close();
 }
 
+void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, std::vector<uint8_t>& out) {
+    std::vector<size_t> lens(streams.size());
+    for (size_t i = 0; i < streams.size(); ++i) lens[i] = streams[i].second;
+    std::vector<MuxPacket> plan;
+    plan_mux(lens.data(), (int)streams.size(), plan);
+    for (const MuxPacket& p : plan) {
+        out.insert(out.end(), p.hdr, p.hdr + p.nhdr);
+        out.insert(out.end(), streams[p.id].first + p.src_off, streams[p.id].first + p.src_off + p.len);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // write_ujpg header + trailer
 // ------------------------------------------------------------------------------------------------
-bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<const uint8_t*, size_t>>& streams,
-               std::vector<uint8_t>& out, std::string& err) {
+bool build_lep_header(const Jpeg& j, const Splits& sp, std::vector<uint8_t>& out, std::string& err) {
     std::vector<uint8_t> blob;
     blob.reserve(j.hdr.size() + j.grb.size() + 512);
     put(blob, "HDR", 3);
@@ -229,9 +241,7 @@ bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<cons
     deflateEnd(&strm);
 
     out.clear();
-    size_t total_stream = 0;
-    for (auto& s : streams) total_stream += s.second;
-    out.reserve(28 + z.size() + 3 + total_stream + total_stream / 1024 + 64);
+    out.reserve(28 + z.size() + 3);
     out.push_back(0xCF); out.push_back(0x84);              // lepton_header (jpgcoder.cc:551)
     out.push_back(1);                                      // ujgversion
     out.push_back(j.is_baseline ? 'Z' : 'X');              // 'Z': g_allow_progressive cleared for baseline files (:3298-3300, :4044-4052)
@@ -242,6 +252,18 @@ bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<cons
     le32(out, (uint32_t)z.size());
     out.insert(out.end(), z.begin(), z.end());
     put(out, "CMP", 3);
+    return true;
+}
+
+bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<const uint8_t*, size_t>>& streams,
+               std::vector<uint8_t>& out, std::string& err) {
+    std::vector<uint8_t> hdr;
+    if (!build_lep_header(j, sp, hdr, err)) return false;
+    size_t total_stream = 0;
+    for (auto& s : streams) total_stream += s.second;
+    out.clear();
+    out.reserve(hdr.size() + total_stream + total_stream / 1024 + 64);
+    out.insert(out.end(), hdr.begin(), hdr.end());
     mux_streams(streams, out);
     le32(out, (uint32_t)out.size() + 4);                   // vp8_encoder.cc:603-614
     return true;

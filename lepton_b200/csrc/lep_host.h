@@ -141,7 +141,13 @@ struct Splits {
 Splits select_splits(const Jpeg& j, unsigned max_threads = 8, unsigned min_threads = 1, bool even_split = false);
 
 // MuxWriter + vp8_full_encoder interleave schedule (src/io/MuxReader.hh:336-522, src/lepton/vp8_encoder.cc:573-600).
+// One packet of the mux: `nhdr` header bytes, then `len` bytes of stream `id` from offset `src_off`.  plan_mux runs the
+// writer on stream LENGTHS only (its decisions never depend on the data); mux_streams copies by the plan.
+struct MuxPacket { uint8_t id, nhdr, hdr[3]; uint32_t src_off, len; };
+void plan_mux(const size_t* lens, int nseg, std::vector<MuxPacket>& out);
 void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, std::vector<uint8_t>& out);
+// fixed header + zlib'd header blob + "CMP": everything of a .lep in front of the mux packets
+bool build_lep_header(const Jpeg& j, const Splits& sp, std::vector<uint8_t>& out, std::string& err);
 
 // Whole .lep file: fixed header, zlib'd header blob, "CMP", muxed streams, LE32 size trailer.
 bool write_lep(const Jpeg& j, const Splits& sp, const std::vector<std::pair<const uint8_t*, size_t>>& streams,
