@@ -227,6 +227,13 @@ typedef struct lepb200_result { const uint8_t* data; size_t len; int32_t status;
 /* lepb200_decode_upload for streams that lie in pieces (the mux packets of a .lep file, src/io/MuxReader.hh:230-283): in[s].len
  * is the length of segment s's stream, its bytes are the pieces spans[span_first[s] .. span_first[s + 1]) in order; in[s].data
  * is not read.  The pieces are gathered straight into the context's pinned staging buffer (no intermediate copy). */
+/* Instead of lepb200_encode_fetch: one complete .lep file per image of the batch, ASSEMBLED ON THE DEVICE.  headers[i] =
+ * everything in front of the mux packets (fixed header, compressed JPEG header, "CMP" -- jpgcoder.cc:3779-4076; the host
+ * stages build it, lepb200_host_jpeg_header); the MuxWriter packet schedule (src/io/MuxReader.hh:336-522) is planned
+ * from the stream lengths and a gather kernel writes header, packets and the LE32 size trailer (vp8_encoder.cc:573-614) into
+ * one dense buffer that comes back in a single copy.  files[i].data: pinned host memory owned by the context (valid until its
+ * next fetch); files[i].status: the first non-zero segment status of the image (then no file). */
+int lepb200_encode_fetch_files(lepb200_ctx* ctx, const lepb200_buffer* headers, lepb200_result* files);
 int lepb200_decode_upload_gather(lepb200_ctx* ctx, const lepb200_image* images, int nimages, const lepb200_stream* in,
                                  const lepb200_buffer* spans, const uint32_t* span_first);
 
@@ -289,6 +296,13 @@ int lepb200_host_jpeg_image(lepb200_jpeg* h, lepb200_image* img);
  * *_close; `rows` and the outputs are left alone); LEPB200_ERR_INVALID when the file needs the host Huffman decoder */
 int lepb200_host_jpeg_scan(lepb200_jpeg* h, lepb200_jpeg_scan* scan);
 int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, int nseg, const uint8_t** data, size_t* len);
+/* everything of the .lep in front of the mux packets (what lepb200_encode_fetch_files wants as headers[i]) */
+int lepb200_host_jpeg_header(lepb200_jpeg* h, const uint8_t** data, size_t* len);
+/* The MuxWriter schedule (src/io/MuxReader.hh:336-522 driven by vp8_encoder.cc:575-594) for nseg streams of the given
+ * lengths -- it depends on the lengths only: packet k = `nhdr` header bytes, then `len` bytes of stream `id` from offset
+ * `src_off`.  Returns the number of packets (writes at most `cap` of them). */
+typedef struct lepb200_mux_packet { uint8_t id, nhdr, hdr[3]; uint32_t src_off, len; } lepb200_mux_packet;
+int lepb200_host_mux_plan(const size_t* lens, int nseg, lepb200_mux_packet* out, int cap);
 void lepb200_host_jpeg_close(lepb200_jpeg* h);
 /* decode-side host stages: container parse + demux (read_ujpg, jpgcoder.cc:4117), geometry/splits, segment streams, and
  * JPEG re-creation from caller-provided planes (recode_baseline_jpeg, recoder.cc:694) */

@@ -17,6 +17,8 @@
 #include "lep_decode_g2.cu"
 #include "lep_huffpar.cu"
 #include "lep_huffenc.cu"
+#include "lep_mux.cu"
+#include "lep_host.h"
 
 using namespace lepb200;
 
@@ -76,6 +78,8 @@ struct lepb200_ctx {
     std::string err;
     DevBuf d_planes, d_streams, d_tokens, d_dense, d_huff, d_hjobs, d_htabs, d_hrows, d_hpar, d_images, d_segs, d_order, d_counter, d_models, d_rows;
     DevBuf d_henc_out, d_henc_imgs, d_henc_segs, d_henc_tabs;
+    DevBuf d_gather, d_lit;                // device container assembly: piece list, literal bytes (file headers + trailers)
+    HostBuf h_lit;
     DevBuf d_rc_ck, d_rc_digits;           // parallel range coder: checkpoints of the range-only pass, deferred-carry digits
     HostBuf h_henc_out, h_henc_segs;
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
@@ -395,7 +399,7 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_hpar, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_rc_ck, &ctx->d_rc_digits})
+    for (DevBuf* b : {&ctx->d_henc_out, &ctx->d_henc_imgs, &ctx->d_henc_segs, &ctx->d_henc_tabs, &ctx->d_huff, &ctx->d_hjobs, &ctx->d_htabs, &ctx->d_hrows, &ctx->d_hpar, &ctx->d_planes, &ctx->d_streams, &ctx->d_tokens, &ctx->d_dense, &ctx->d_images, &ctx->d_segs, &ctx->d_order, &ctx->d_counter, &ctx->d_models, &ctx->d_rows, &ctx->d_rc_ck, &ctx->d_rc_digits, &ctx->d_gather, &ctx->d_lit})
         b->release();
     for (HostBuf* b : {&ctx->h_segs, &ctx->h_dense, &ctx->h_stage, &ctx->h_hjobs, &ctx->h_hpar}) b->release();
     cudaEventDestroy(ctx->ev0);
@@ -825,6 +829,77 @@ int lepb200_encode_fetch(lepb200_ctx* ctx, lepb200_stream* out) {
         out[s].reserved = 0;
         out[s].ndecisions = (uint64_t)hs[s].ndecisions_lo | ((uint64_t)hs[s].ndecisions_hi << 32);
     }
+    return LEPB200_OK;
+}
+
+// Final .lep files from the device: headers[i] = everything in front of the mux packets
+// of image i (fixed header + zlib'd JPEG header + "CMP", built on the host: lephost::build_lep_header); the MuxWriter
+// schedule is planned on the host from the stream lengths the range coder reports (lephost::plan_mux, data-free), the
+// bytes are moved by lep_gather_kernel, the LE32 size trailer (vp8_encoder.cc:603-614) is a literal.
+int lepb200_encode_fetch_files(lepb200_ctx* ctx, const lepb200_buffer* headers, lepb200_result* files) {
+    if (!ctx || !ctx->launched || !ctx->is_encode || !headers || !files) { if (ctx) ctx->err = "encode_fetch_files without encode_launch"; return LEPB200_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const int nseg = (int)ctx->segs.size(), nimg = (int)ctx->images.size();
+    CK(ctx->h_segs.reserve(sizeof(SegDesc) * nseg));
+    SegDesc* hs = static_cast<SegDesc*>(ctx->h_segs.p);
+    CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    // literals: header + 4 trailer bytes per image, 16-byte aligned
+    size_t lit_total = 0;
+    std::vector<size_t> lit_off(nimg);
+    for (int i = 0; i < nimg; ++i) { lit_off[i] = lit_total; lit_total += align_up(headers[i].len + 4, 16); }
+    CK(ctx->h_lit.reserve(lit_total + 64));
+    CK(ctx->d_lit.reserve(lit_total + 256));
+    uint8_t* hl = static_cast<uint8_t*>(ctx->h_lit.p);
+    const unsigned long long dl = (unsigned long long)(uintptr_t)ctx->d_lit.p;
+    std::vector<GatherPiece> pieces;
+    pieces.reserve((size_t)nseg * 32 + 2 * (size_t)nimg);
+    std::vector<size_t> file_off(nimg, 0);
+    std::vector<lephost::MuxPacket> plan;
+    size_t total = 0;
+    uint64_t alg = 0;
+    int s0 = 0;
+    for (int i = 0; i < nimg; ++i) {
+        int s1 = s0;
+        while (s1 < nseg && hs[s1].image == i) ++s1;
+        int st = 0;
+        size_t lens[LEPB200_MAX_SEGMENTS];
+        const int ns = s1 - s0;
+        for (int s = s0; s < s1; ++s) {
+            if (hs[s].status && !st) st = hs[s].status;
+            if (s - s0 < LEPB200_MAX_SEGMENTS) lens[s - s0] = hs[s].len;
+            alg += (uint64_t)ctx->seg_blocks[s] * 128 + (hs[s].status == 0 ? hs[s].len : 0);
+        }
+        files[i].data = nullptr; files[i].len = 0; files[i].status = st;
+        if (st == 0 && (ns < 1 || ns > LEPB200_MAX_SEGMENTS || !headers[i].data || headers[i].len == 0)) files[i].status = st = LEPB200_ST_NOT_HANDLED;
+        if (st == 0) {
+            lephost::plan_mux(lens, ns, plan);
+            total = align_up(total, 16);
+            file_off[i] = total;
+            memcpy(hl + lit_off[i], headers[i].data, headers[i].len);
+            unsigned long long saddr[LEPB200_MAX_SEGMENTS];
+            for (int k = 0; k < ns; ++k) saddr[k] = hs[s0 + k].stream;
+            const uint32_t fsz = gather_file_pieces(plan.data(), plan.size(), saddr, dl + lit_off[i], hl + lit_off[i], headers[i].len, total, pieces);
+            files[i].len = fsz;
+            total += fsz;
+        }
+        s0 = s1;
+    }
+    ctx->alg_bytes = alg;
+    if (pieces.empty()) return LEPB200_OK;
+    CK(ctx->d_dense.reserve(total + 256));
+    CK(ctx->h_dense.reserve(total + 16));
+    CK(ctx->d_gather.reserve(sizeof(GatherPiece) * pieces.size()));
+    CK(cudaMemcpyAsync(ctx->d_lit.p, hl, lit_total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_gather.p, pieces.data(), sizeof(GatherPiece) * pieces.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = (unsigned)std::min<size_t>((pieces.size() + GATHER_WARPS - 1) / GATHER_WARPS, (size_t)ctx->sm_count * 8);
+    lep_gather_kernel<<<grid, GATHER_WARPS * 32, 0, ctx->stream>>>(static_cast<const GatherPiece*>(ctx->d_gather.p), (uint32_t)pieces.size(), static_cast<uint8_t*>(ctx->d_dense.p));
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_dense.p, ctx->d_dense.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < nimg; ++i) if (files[i].status == 0) files[i].data = static_cast<const uint8_t*>(ctx->h_dense.p) + file_off[i];
     return LEPB200_OK;
 }
 

@@ -180,6 +180,8 @@ struct ChunkState {
     std::vector<std::vector<lepb200_huffrow>> rowbuf;
     int gpu_rc = 0;
     bool any_gpu_huffman = false;
+    std::vector<std::vector<uint8_t>> headers;   // device container assembly: per batch image everything in front of the mux packets
+    std::vector<lepb200_result> files;           // ... and the finished files (pinned memory of the chunk's context)
 };
 
 }  // namespace
@@ -228,6 +230,8 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     // while the other chunks are still being parsed, and the chunks reach the device one after the other instead of
     // all at the same moment (measured before: four fronts end together at 36 ms, four Huffman launches share the
     // device until 85-148 ms, the first kernel A starts at 88 ms -- profiles/r02_round_k.log).
+    // containers assembled on the device (lepb200_encode_fetch_files) unless LEPB200_DEVICE_MUX=0 (host MuxWriter)
+    const bool device_mux = !(getenv("LEPB200_DEVICE_MUX") && atoi(getenv("LEPB200_DEVICE_MUX")) == 0);
     const bool front_turns = W > 1 && !(getenv("LEPB200_FRONT_TURNS") && atoi(getenv("LEPB200_FRONT_TURNS")) == 0);
     const int fth = front_turns ? std::max(1, c->nthreads) : pth;
     std::mutex turn_mu;
@@ -410,7 +414,20 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
                 mark("upload+prepass", k, t1);
                 t1 = now_s();
                 if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_launch(ctx);
-                if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
+                if (device_mux) {
+                    // while the kernels run: the part of every container that does not depend on the coded bytes (fixed
+                    // header, zlib'd JPEG header, "CMP"); then the files themselves come back assembled by the device
+                    s.headers.assign(nb, std::vector<uint8_t>());
+                    std::vector<lepb200_buffer> hb(nb, lepb200_buffer{nullptr, 0});
+                    parallel_for(nb, pth, [&](int q) {
+                        const int i = s.idx[q];
+                        if (status[s.begin + i]) return;
+                        std::string err;
+                        if (build_lep_header(*s.js[i], s.splits[i], s.headers[q], err)) hb[q] = lepb200_buffer{s.headers[q].data(), s.headers[q].size()};
+                    });
+                    s.files.assign(nb, lepb200_result{nullptr, 0, 0});
+                    if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_fetch_files(ctx, hb.data(), s.files.data());
+                } else if (s.gpu_rc == 0) s.gpu_rc = lepb200_encode_fetch(ctx, s.streams.data());
                 mark("encode+fetch", k, t1);
                 if (trace) fprintf(stderr, "[trace]   kernel A %.1f ms, A+B %.1f ms\n", lepb200_last_symbolise_ms(ctx), lepb200_last_kernel_ms(ctx));
             }
@@ -428,6 +445,12 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
             parallel_for((int)s.idx.size(), bth, [&](int q) {
                 const int i = s.begin + s.idx[q];
                 if (status[i]) return;
+                if (device_mux) {                     // the file is complete: it only moves into the codec's output buffer
+                    const lepb200_result& f = s.files[q];
+                    if (f.status) { status[i] = f.status; return; }
+                    c->outputs[i].assign(f.data, f.data + f.len);
+                    return;
+                }
                 std::vector<std::pair<const uint8_t*, size_t>> ss;
                 for (int t = s.seg_base[q]; t < s.seg_base[q + 1]; ++t) {
                     if (s.streams[t].status) { status[i] = s.streams[t].status; return; }
@@ -922,7 +945,7 @@ struct lepb200_jpeg {
     Splits sp;
     std::vector<std::vector<int16_t>> store;
     int16_t* planes[4] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<uint8_t> out;
+    std::vector<uint8_t> out, hdr;
 };
 
 int lepb200_host_jpeg_open(const uint8_t* data, size_t len, lepb200_jpeg** out, int32_t* status) {
@@ -983,6 +1006,23 @@ int lepb200_host_jpeg_write_lep(lepb200_jpeg* h, const lepb200_stream* streams, 
     if (!write_lep(h->j, h->sp, ss, h->out, err)) { h->j.error = err; return LEPB200_ERR_INVALID; }
     *data = h->out.data();
     *len = h->out.size();
+    return LEPB200_OK;
+}
+
+int lepb200_host_mux_plan(const size_t* lens, int nseg, lepb200_mux_packet* out, int cap) {
+    if (!lens || nseg < 0 || nseg > 16 || (cap > 0 && !out)) return LEPB200_ERR_INVALID;
+    std::vector<MuxPacket> plan;
+    plan_mux(lens, nseg, plan);
+    for (size_t k = 0; k < plan.size() && (int)k < cap; ++k) out[k] = plan[k];
+    return (int)plan.size();
+}
+
+int lepb200_host_jpeg_header(lepb200_jpeg* h, const uint8_t** data, size_t* len) {
+    if (!h || !data || !len || h->j.status) return LEPB200_ERR_INVALID;
+    std::string err;
+    if (!build_lep_header(h->j, h->sp, h->hdr, err)) { h->j.error = err; return LEPB200_ERR_INVALID; }
+    *data = h->hdr.data();
+    *len = h->hdr.size();
     return LEPB200_OK;
 }
 

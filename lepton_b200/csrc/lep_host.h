@@ -8,6 +8,7 @@
 // and the inverse for decode.  Everything here must be byte-exact with the reference; citations are to
 // /root/reference/src/lepton/jpgcoder.cc unless stated otherwise.
 #pragma once
+#include "../../include/lepton_b200.h"
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -143,7 +144,7 @@ Splits select_splits(const Jpeg& j, unsigned max_threads = 8, unsigned min_threa
 // MuxWriter + vp8_full_encoder interleave schedule (src/io/MuxReader.hh:336-522, src/lepton/vp8_encoder.cc:573-600).
 // One packet of the mux: `nhdr` header bytes, then `len` bytes of stream `id` from offset `src_off`.  plan_mux runs the
 // writer on stream LENGTHS only (its decisions never depend on the data); mux_streams copies by the plan.
-struct MuxPacket { uint8_t id, nhdr, hdr[3]; uint32_t src_off, len; };
+typedef lepb200_mux_packet MuxPacket;            // include/lepton_b200.h
 void plan_mux(const size_t* lens, int nseg, std::vector<MuxPacket>& out);
 void mux_streams(const std::vector<std::pair<const uint8_t*, size_t>>& streams, std::vector<uint8_t>& out);
 // fixed header + zlib'd header blob + "CMP": everything of a .lep in front of the mux packets

@@ -18,7 +18,7 @@ CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
 SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
            os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_g2.cu"),
-           os.path.join(CSRC, "lep_huff.cu"), os.path.join(CSRC, "lep_huffpar.cu"), os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
+           os.path.join(CSRC, "lep_huff.cu"), os.path.join(CSRC, "lep_huffpar.cu"), os.path.join(CSRC, "lep_mux.cu"), os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
 
@@ -186,3 +186,57 @@ def huffman_decode(mode, jpegs, sub_bits=4096, iter_cap=62, mutate=None):
         host = [np.array(p) for p in hjs[i].coef_image().planes] if mutate is None else None
         res[i] = dict(status=sc.status, padbit=sc.padbit, end_bitpos=sc.end_bitpos, nrows=sc.nrows, rows=rows, planes=planes[k], host_planes=host)
     return res, (info[0], info[1])
+
+
+# ---- device container assembly (lep_mux.cu)
+class _MuxPacket(ctypes.Structure):
+    _fields_ = [("id", ctypes.c_uint8), ("nhdr", ctypes.c_uint8), ("hdr", ctypes.c_uint8 * 3), ("src_off", ctypes.c_uint32), ("len", ctypes.c_uint32)]
+
+
+def mux_plan(lens):
+    """lepb200_host_mux_plan of the PRODUCT library (host code, no GPU): the MuxWriter schedule for streams of these lengths."""
+    import lepton_b200
+    L = lepton_b200.lib()
+    L.lepb200_host_mux_plan.restype = ctypes.c_int
+    L.lepb200_host_mux_plan.argtypes = [ctypes.POINTER(ctypes.c_size_t), ctypes.c_int, ctypes.POINTER(_MuxPacket), ctypes.c_int]
+    arr = (ctypes.c_size_t * len(lens))(*lens)
+    n = L.lepb200_host_mux_plan(arr, len(lens), None, 0)
+    assert n >= 0
+    out = (_MuxPacket * max(n, 1))()
+    assert L.lepb200_host_mux_plan(arr, len(lens), out, n) == n
+    return out, n
+
+
+def mux_files(files, grid=3):
+    """files: list of (header bytes, [stream bytes per segment]).  Returns the assembled .lep files (lep_gather_kernel on the
+    emulator over the pieces the C ABI would build)."""
+    from lepton_b200.codec import _Stream
+    nf = len(files)
+    hdrs = [ctypes.create_string_buffer(h, len(h)) for h, _ in files]
+    hdr_p = (ctypes.c_void_p * nf)(*[ctypes.cast(h, ctypes.c_void_p) for h in hdrs])
+    hlen = (ctypes.c_size_t * nf)(*[len(h) for h, _ in files])
+    nseg = (ctypes.c_int * nf)(*[len(ss) for _, ss in files])
+    flat = [s for _, ss in files for s in ss]
+    keep = [ctypes.create_string_buffer(s, max(len(s), 1)) for s in flat]
+    st = (_Stream * max(len(flat), 1))()
+    for k, (s, b) in enumerate(zip(flat, keep)):
+        st[k].data = ctypes.cast(b, ctypes.c_void_p).value
+        st[k].len = len(s)
+    plans, first = [], [0]
+    for _, ss in files:
+        p, n = mux_plan([len(s) for s in ss])
+        plans.extend(p[i] for i in range(n))
+        first.append(first[-1] + n)
+    plan = (_MuxPacket * max(len(plans), 1))(*plans)
+    pf = (ctypes.c_uint32 * (nf + 1))(*first)
+    cap = sum(len(h) + sum(len(s) for s in ss) for h, ss in files) * 2 + 4096 * nf
+    out = (ctypes.c_uint8 * cap)()
+    off = (ctypes.c_size_t * nf)()
+    ln = (ctypes.c_size_t * nf)()
+    L = lib()
+    L.emu_mux_files.restype = ctypes.c_int
+    rc = L.emu_mux_files(nf, hdr_p, hlen, nseg, st, plan, pf, int(grid), out, ctypes.c_size_t(cap), off, ln)
+    if rc != 0:
+        raise RuntimeError("emu_mux_files failed with %d" % rc)
+    raw = bytes(out)
+    return [raw[off[f]:off[f] + ln[f]] for f in range(nf)]

@@ -13,6 +13,7 @@
 #include "../../lepton_b200/csrc/lep_decode.cu"
 #include "../../lepton_b200/csrc/lep_decode_g2.cu"
 #include "../../lepton_b200/csrc/lep_huffpar.cu"
+#include "../../lepton_b200/csrc/lep_mux.cu"
 #include "../../include/lepton_b200.h"
 
 using namespace lepb200;
@@ -401,5 +402,55 @@ extern "C" int emu_huffman_decode(int mode, int sub_bits, int iter_cap, lepb200_
         if (scans[i].rows && jobs[i].nrows > 0) memcpy(scans[i].rows, rows[i].data(), sizeof(HuffRow) * (size_t)std::min(jobs[i].nrows, scans[i].mcuv + 1));
     }
     if (info) { info[0] = iters; info[1] = redo; }
+    return 0;
+}
+
+
+// ---- device container assembly: lep_gather_kernel over the pieces lepb200_encode_fetch_files builds (gather_file_pieces,
+// lep_mux.cu) for `nfiles` files at once.  File f has header hdr[f] (hlen[f] bytes), nseg[f] streams (streams[] holds them file
+// after file) and the MuxWriter plan plan[plan_first[f] .. plan_first[f + 1]) (from lepb200_host_mux_plan).  The files are
+// written back to back (16-byte aligned starts, like the device buffer) into out; off[f] / len[f] say where.
+namespace {
+struct GatherArgs { const GatherPiece* pieces; uint32_t n; uint8_t* out; };
+void gather_body(void* p) { const GatherArgs& a = *static_cast<const GatherArgs*>(p); lep_gather_kernel(a.pieces, a.n, a.out); }
+}  // namespace
+
+extern "C" int emu_mux_files(int nfiles, const uint8_t* const* hdr, const size_t* hlen, const int* nseg, const lepb200_stream* streams,
+                             const lepb200_mux_packet* plan, const uint32_t* plan_first, int grid, uint8_t* out, size_t cap, size_t* off, size_t* len) {
+    if (nfiles <= 0 || !hdr || !hlen || !nseg || !streams || !plan || !plan_first || !out) return LEPB200_ERR_INVALID;
+    // stream arena: 256-byte aligned starts and 256 bytes of slack like d_streams; poisoned so that a byte taken from outside a
+    // stream shows
+    size_t arena = 256, nstreams = 0;
+    for (int f = 0; f < nfiles; ++f) for (int k = 0; k < nseg[f]; ++k) arena += align_up((size_t)streams[nstreams++].len + 16, 256);
+    std::vector<uint8_t> sbuf(arena + 512, 0xEE);
+    uint8_t* sbase = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)sbuf.data(), 256));
+    size_t lit_total = 0;
+    for (int f = 0; f < nfiles; ++f) lit_total += align_up(hlen[f] + 4, 16);
+    std::vector<uint8_t> lit(lit_total + 512, 0xDD);
+    uint8_t* lbase = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)lit.data(), 256));
+    std::vector<GatherPiece> pieces;
+    size_t spos = 0, lpos = 0, total = 0, si = 0;
+    for (int f = 0; f < nfiles; ++f) {
+        unsigned long long saddr[LEPB200_MAX_SEGMENTS];
+        if (nseg[f] < 1 || nseg[f] > LEPB200_MAX_SEGMENTS) return LEPB200_ERR_INVALID;
+        for (int k = 0; k < nseg[f]; ++k, ++si) {
+            if (streams[si].len) memcpy(sbase + spos, streams[si].data, (size_t)streams[si].len);
+            saddr[k] = (unsigned long long)(uintptr_t)(sbase + spos);
+            spos += align_up((size_t)streams[si].len + 16, 256);
+        }
+        memcpy(lbase + lpos, hdr[f], hlen[f]);
+        total = align_up(total, 16);
+        off[f] = total;
+        len[f] = gather_file_pieces(plan + plan_first[f], plan_first[f + 1] - plan_first[f], saddr, (unsigned long long)(uintptr_t)(lbase + lpos),
+                                    lbase + lpos, hlen[f], total, pieces);
+        total += len[f];
+        lpos += align_up(hlen[f] + 4, 16);
+    }
+    if (total > cap) return LEPB200_ERR_NOMEM;
+    std::vector<uint8_t> dense(total + 512, 0xCC);
+    uint8_t* dbase = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)dense.data(), 256));
+    GatherArgs a{pieces.data(), (uint32_t)pieces.size(), dbase};
+    emu::launch((unsigned)std::max(1, grid), GATHER_WARPS * 32, gather_body, &a);
+    memcpy(out, dbase, total);
     return 0;
 }
