@@ -81,7 +81,9 @@ struct lepb200_ctx {
     DevBuf d_gather, d_lit;                // device container assembly: piece list, literal bytes (file headers + trailers)
     HostBuf h_lit;
     DevBuf d_rc_ck, d_rc_digits;           // parallel range coder: checkpoints of the range-only pass, deferred-carry digits
-    HostBuf h_henc_out, h_henc_segs;
+    HostBuf h_henc_out, h_henc_segs, h_henc_desc;
+    cudaEvent_t status_ev = nullptr;       // parts mode: the D2H of the decode batch's segment records, queued ahead of the part copies
+    bool status_queued = false;
     std::vector<size_t> henc_off;         // per image: offset of its scan bytes in the output buffers (SIZE_MAX = skipped)
     std::vector<int> henc_seg_first;      // per image: index of its first segment record
     int henc_nseg = 0;
@@ -112,7 +114,9 @@ struct lepb200_ctx {
     int huff_par_iters = 0;               // synchronisation iterations of the last batch (diagnostic)
     int huff_warps = 4;                   // images per CTA of the Huffman kernel
     int host_threads = 1;                 // host threads this context may use for staging copies
-    int rc_feed = 1;                      // range pass token feed: 1 = cp.async ring in shared memory, 0 = register ring of plain loads; LEPB200_RC_FEED
+    int rc_feed = -1;                     // range pass token feed: 1 = cp.async ring in shared memory, 0 = register ring of plain loads, -1 = by
+                                          // batch size (measured, profiles/r02_round_l.log: 4096 segments 26.3 ms against 40 ms, 16384
+                                          // segments 37.5 against 35.2 ms -- with every SM streaming, the feed is no longer what bounds it); LEPB200_RC_FEED
     int rc_mode = 1;                      // range coder: 1 = range-only pass + parallel pieces + carry pass (lep_rangepass / piece / norm kernels),
                                           // 0 = one serial chain per segment (lep_rangecode_kernel); LEPB200_RC_MODE
     int dec_mode = 0;                     // decode kernel: 0 = by batch size (group kernel when at least dec_group_min segments are in the
@@ -406,6 +410,7 @@ void lepb200_destroy(lepb200_ctx* ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_mid);
     for (cudaEvent_t e : ctx->part_events) cudaEventDestroy(e);
+    if (ctx->status_ev) cudaEventDestroy(ctx->status_ev);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -748,7 +753,8 @@ int lepb200_encode_launch_rangecode(lepb200_ctx* ctx) {
         const bool trace = getenv("LEPB200_TRACE") != nullptr;           // per-kernel times on stderr (diagnostics; adds a sync)
         cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
         if (trace) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->stream); }
-        if (ctx->rc_feed) lep_rangepass_kernel<true><<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
+        const bool async_feed = ctx->rc_feed < 0 ? nseg <= 8192 : ctx->rc_feed != 0;
+        if (async_feed) lep_rangepass_kernel<true><<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
         else lep_rangepass_kernel<false><<<(nseg + RCT_THREADS - 1) / RCT_THREADS, RCT_THREADS, RCT_SMEM_TABLE_BYTES, ctx->stream>>>(ds, nseg, dord, dtok, dck);
         CK(cudaGetLastError());
         unsigned long long* d_total = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ctx->d_counter.p) + 128);
@@ -991,10 +997,19 @@ static int henc_launch(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n, int np
     CK(ctx->d_henc_segs.reserve(sizeof(HEncSeg) * hs.size()));
     CK(ctx->d_henc_tabs.reserve(sizeof(HEncTable) * std::max<size_t>(1, tabs.size())));
     for (int i = 0; i < n; ++i) if (ctx->henc_off[i] != SIZE_MAX) hi[i].out = (unsigned long long)(uintptr_t)ctx->d_henc_out.p + ctx->henc_off[i];
-    // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may go out of scope
-    CK(cudaMemcpyAsync(ctx->d_henc_imgs.p, hi.data(), sizeof(HEncImage) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_henc_segs.p, hs.data(), sizeof(HEncSeg) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_henc_tabs.p, tabs.data(), sizeof(HEncTable) * tabs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    // the records travel from pinned memory: a copy from pageable memory of this size would hold the calling thread
+    // until the stream has reached it, i.e. for the whole decode kernel queued in front
+    {
+        const size_t b_img = align_up(sizeof(HEncImage) * (size_t)n, 256), b_seg = align_up(sizeof(HEncSeg) * hs.size(), 256), b_tab = sizeof(HEncTable) * tabs.size();
+        CK(ctx->h_henc_desc.reserve(b_img + b_seg + b_tab + 256));
+        uint8_t* hd = static_cast<uint8_t*>(ctx->h_henc_desc.p);
+        memcpy(hd, hi.data(), sizeof(HEncImage) * (size_t)n);
+        memcpy(hd + b_img, hs.data(), sizeof(HEncSeg) * hs.size());
+        memcpy(hd + b_img + b_seg, tabs.data(), b_tab);
+        CK(cudaMemcpyAsync(ctx->d_henc_imgs.p, hd, sizeof(HEncImage) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_henc_segs.p, hd + b_img, sizeof(HEncSeg) * hs.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_henc_tabs.p, hd + b_img + b_seg, b_tab, cudaMemcpyHostToDevice, ctx->stream));
+    }
     const int nseg = (int)hs.size();
     if (nparts <= 0) {                    // one launch, the caller fetches everything with lepb200_huffman_encode_fetch
         lep_huffencode_kernel<<<(nseg + HENC_WARPS - 1) / HENC_WARPS, HENC_WARPS * 32, 0, ctx->stream>>>(
@@ -1012,6 +1027,16 @@ static int henc_launch(lepb200_ctx* ctx, lepb200_henc_image* imgs, int n, int np
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->part_events.push_back(e);
+    }
+    // the decode batch's segment records first: they must not queue behind the part copies on the copy stream
+    {
+        const int nseg_dec = (int)ctx->segs.size();
+        CK(ctx->h_segs.reserve(sizeof(SegDesc) * nseg_dec));
+        if (!ctx->status_ev) CK(cudaEventCreateWithFlags(&ctx->status_ev, cudaEventDisableTiming));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));
+        CK(cudaMemcpyAsync(ctx->h_segs.p, ctx->d_segs.p, sizeof(SegDesc) * nseg_dec, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->status_ev, ctx->copy_stream));
+        ctx->status_queued = true;
     }
     int i0 = 0;
     for (int k = 0; k < nparts && i0 < n; ++k) {
@@ -1201,6 +1226,7 @@ int lepb200_decode_launch(lepb200_ctx* ctx) {
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->status_queued = false;
     ctx->launches += 1;
     ctx->launched = true;
     return LEPB200_OK;
@@ -1236,9 +1262,13 @@ int lepb200_decode_fetch_status(lepb200_ctx* ctx, int32_t* status_out) {
     const int nseg = (int)ctx->segs.size();
     CK(ctx->h_segs.reserve(sizeof(SegDesc) * nseg));
     SegDesc* hs = static_cast<SegDesc*>(ctx->h_segs.p);
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));              // the decode kernel, not what was queued behind it
-    CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->status_queued) {                                            // queued by lepb200_huffman_encode_resident_parts ahead of its copies
+        CK(cudaEventSynchronize(ctx->status_ev));
+    } else {
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev1, 0));          // the decode kernel, not what was queued behind it
+        CK(cudaMemcpyAsync(hs, ctx->d_segs.p, sizeof(SegDesc) * nseg, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+    }
     for (int s = 0; s < nseg; ++s) status_out[s] = hs[s].status;
     return LEPB200_OK;
 }

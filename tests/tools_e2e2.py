@@ -22,11 +22,13 @@ for combo in combos:
         os.environ[k] = v
     ci = int(os.environ.get("E2E_CHUNK_IMAGES", "0"))
     fc = LeptonB200FileCodec(0, host_threads=16, chunk_images=ci) if ci else LeptonB200FileCodec(0, host_threads=16)
-    r = fc.compress(handle, copy=leps is None)
+    r = fc.compress(handle, copy=True)
     assert all(st == 0 for st, _ in r)
     if leps is None:
         leps = [b for _, b in r]
         lhandle = LeptonB200FileCodec.prepare(leps)
+    else:                     # every setting must write the bytes of the first one
+        assert [b for _, b in r] == leps, "setting %r changes the .lep bytes" % combo
     best = 1e9
     for _ in range(3):
         t0 = time.perf_counter()
