@@ -315,6 +315,8 @@ int lepb200_host_lep_recode(lepb200_lep* h, const int16_t* const planes[3], cons
 /* host half of the device re-encode path (lepb200_huffman_encode_resident): offset and length of the scan in the original
  * file (both 0 when the file needs the host re-encoder), and the JPEG assembled around scan bytes produced elsewhere */
 int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t* scan_bytes);
+/* the job lepb200_huffman_encode_resident wants for this file (scan_bytes == 0: the file needs the host re-encoder) */
+int lepb200_host_lep_henc_image(lepb200_lep* h, lepb200_henc_image* out);
 int lepb200_host_lep_assemble(lepb200_lep* h, const uint8_t* scan, size_t scan_len, const uint8_t** data, size_t* len);
 void lepb200_host_lep_close(lepb200_lep* h);
 /* diagnostic: wall-clock seconds of the host front end alone over a batch with `threads` workers */

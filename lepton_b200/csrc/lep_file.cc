@@ -527,6 +527,35 @@ int lepb200_compress_jpegs(lepb200_codec* c, const lepb200_buffer* jpegs, int n,
     return ret;
 }
 
+// The job the device Huffman encoder gets for one .lep file (lepb200_huffman_encode_resident): tables selected by the SOS,
+// sampling factors, and per thread-segment the MCU-row range, DC predictors, pending bits and byte count its ThreadHandoff
+// carries (recode_row_range, src/lepton/recoder.cc:472-545).  he.scan_bytes stays 0 when the file needs the host re-encoder.
+static void fill_henc_image(const LepFile& lf, GpuRecodeSetup& gs, lepb200_henc_image& he) {
+    memset(&he, 0, sizeof(he));
+    if (!gpu_recode_setup(lf, gs)) return;
+    const Jpeg& j = lf.j;
+    he.rsti = gs.rsti; he.padbit = (uint8_t)j.padbit;
+    for (int t = 0; t < j.ncmp; ++t) {
+        he.H[t] = j.cmp[t].H; he.V[t] = j.cmp[t].V;
+        memcpy(he.dc[t].bits, gs.dc_bits[t], 17); memcpy(he.dc[t].vals, gs.dc_vals[t], 256);
+        memcpy(he.ac[t].bits, gs.ac_bits[t], 17); memcpy(he.ac[t].vals, gs.ac_vals[t], 256);
+    }
+    const int luma_mul = j.cmp[0].bcv / j.mcuv;
+    he.nseg = lf.nseg;
+    bool ok = lf.nseg >= 1 && lf.nseg <= LEPB200_MAX_SEGMENTS;
+    for (int t = 0; ok && t < lf.nseg; ++t) {
+        const Handoff& hd = lf.handoffs[t];
+        lepb200_henc_segment& sg = he.seg[t];
+        ok = hd.luma_y_start % luma_mul == 0 && hd.num_overhang_bits < 8;
+        sg.mcu_row_start = hd.luma_y_start / luma_mul;
+        sg.mcu_row_end = t + 1 < lf.nseg ? lf.handoffs[t + 1].luma_y_start / luma_mul : j.mcuv;
+        for (int q3 = 0; q3 < 3; ++q3) sg.last_dc[q3] = hd.last_dc[q3];
+        sg.overhang_bits = hd.num_overhang_bits; sg.overhang_byte = hd.overhang_byte;
+        sg.expect_bytes = hd.segment_size;
+    }
+    if (ok) he.scan_bytes = gs.scan_bytes;
+}
+
 // .lep files -> JPEG files (inverse of lepb200_compress_jpegs), same 3-stage chunk pipeline:
 //   front (host: container parse, zlib inflate, demux)  |  gpu (H2D streams, decode kernel, D2H planes)  |
 //   back (host: Huffman re-encode + byte stuffing + header/garbage re-assembly)
@@ -621,29 +650,7 @@ int lepb200_decompress_leps(lepb200_codec* c, const lepb200_buffer* leps, int n,
             const LepFile& lf = *s.lf[s.idx[q]];
             lepb200_henc_image& he = s.henc[q];
             memset(&he, 0, sizeof(he));
-            GpuRecodeSetup& gs = s.gsetup[q];
-            if (!c->gpu_huffman || !gpu_recode_setup(lf, gs)) return;
-            const Jpeg& j = lf.j;
-            he.rsti = gs.rsti; he.padbit = (uint8_t)j.padbit;
-            for (int t = 0; t < j.ncmp; ++t) {
-                he.H[t] = j.cmp[t].H; he.V[t] = j.cmp[t].V;
-                memcpy(he.dc[t].bits, gs.dc_bits[t], 17); memcpy(he.dc[t].vals, gs.dc_vals[t], 256);
-                memcpy(he.ac[t].bits, gs.ac_bits[t], 17); memcpy(he.ac[t].vals, gs.ac_vals[t], 256);
-            }
-            const int luma_mul = j.cmp[0].bcv / j.mcuv;
-            he.nseg = lf.nseg;
-            bool ok = lf.nseg >= 1 && lf.nseg <= LEPB200_MAX_SEGMENTS;
-            for (int t = 0; ok && t < lf.nseg; ++t) {
-                const Handoff& hd = lf.handoffs[t];
-                lepb200_henc_segment& sg = he.seg[t];
-                ok = hd.luma_y_start % luma_mul == 0 && hd.num_overhang_bits < 8;
-                sg.mcu_row_start = hd.luma_y_start / luma_mul;
-                sg.mcu_row_end = t + 1 < lf.nseg ? lf.handoffs[t + 1].luma_y_start / luma_mul : j.mcuv;
-                for (int q3 = 0; q3 < 3; ++q3) sg.last_dc[q3] = hd.last_dc[q3];
-                sg.overhang_bits = hd.num_overhang_bits; sg.overhang_byte = hd.overhang_byte;
-                sg.expect_bytes = hd.segment_size;
-            }
-            if (ok) he.scan_bytes = gs.scan_bytes;
+            if (c->gpu_huffman) fill_henc_image(lf, s.gsetup[q], he);
         });
         // pinned arena for the planes of the files the host re-encodes
         size_t total = 0;
@@ -845,6 +852,12 @@ int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t
     if (!gpu_recode_setup(h->lf, gs)) { *scan_offset = 0; *scan_bytes = 0; return LEPB200_OK; }
     *scan_offset = (uint32_t)(2 + gs.hpos);
     *scan_bytes = gs.scan_bytes;
+    return LEPB200_OK;
+}
+int lepb200_host_lep_henc_image(lepb200_lep* h, lepb200_henc_image* out) {
+    if (!h || h->lf.status || !out) return LEPB200_ERR_INVALID;
+    GpuRecodeSetup gs;
+    fill_henc_image(h->lf, gs, *out);
     return LEPB200_OK;
 }
 int lepb200_host_lep_assemble(lepb200_lep* h, const uint8_t* scan, size_t scan_len, const uint8_t** data, size_t* len) {

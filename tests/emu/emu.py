@@ -18,7 +18,7 @@ CSRC = os.path.join(ROOT, "lepton_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libemu_kernels.so")
 SOURCES = [os.path.join(HERE, "emu_kernels.cc"), os.path.join(HERE, "cuda_shim.h"), os.path.join(HERE, "fake", "cuda_runtime.h"),
            os.path.join(CSRC, "lep_encode.cu"), os.path.join(CSRC, "lep_decode.cu"), os.path.join(CSRC, "lep_decode_g2.cu"),
-           os.path.join(CSRC, "lep_huff.cu"), os.path.join(CSRC, "lep_huffpar.cu"), os.path.join(CSRC, "lep_mux.cu"), os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
+           os.path.join(CSRC, "lep_huff.cu"), os.path.join(CSRC, "lep_huffpar.cu"), os.path.join(CSRC, "lep_mux.cu"), os.path.join(CSRC, "lep_huffenc.cu"), os.path.join(CSRC, "lep_common.cuh"), os.path.join(CSRC, "lep_predict.cuh"), os.path.join(ROOT, "include", "lepton_b200.h")]
 
 KERNEL_WARP = 0
 
@@ -240,3 +240,42 @@ def mux_files(files, grid=3):
         raise RuntimeError("emu_mux_files failed with %d" % rc)
     raw = bytes(out)
     return [raw[off[f]:off[f] + ln[f]] for f in range(nf)]
+
+
+# ---- baseline Huffman encode for the way back (lep_huffenc.cu)
+class _HEncSegment(ctypes.Structure):
+    _fields_ = [("mcu_row_start", ctypes.c_int32), ("mcu_row_end", ctypes.c_int32), ("last_dc", ctypes.c_int16 * 3),
+                ("overhang_bits", ctypes.c_uint8), ("overhang_byte", ctypes.c_uint8), ("expect_bytes", ctypes.c_uint32)]
+
+
+class _HEncImage(ctypes.Structure):
+    _fields_ = [("rsti", ctypes.c_int32), ("padbit", ctypes.c_int32), ("H", ctypes.c_int32 * 3), ("V", ctypes.c_int32 * 3),
+                ("dc", _HuffTable * 3), ("ac", _HuffTable * 3), ("nseg", ctypes.c_int32), ("seg", _HEncSegment * 16),
+                ("scan_bytes", ctypes.c_uint32), ("data", ctypes.c_void_p), ("status", ctypes.c_int32)]
+
+
+def henc_job(host_lep):
+    """lepb200_host_lep_henc_image of the PRODUCT library (host code): the job the device Huffman encoder gets for this .lep."""
+    L = host_lep._L
+    L.lepb200_host_lep_henc_image.restype = ctypes.c_int
+    L.lepb200_host_lep_henc_image.argtypes = [ctypes.c_void_p, ctypes.POINTER(_HEncImage)]
+    job = _HEncImage()
+    assert L.lepb200_host_lep_henc_image(host_lep._h, ctypes.byref(job)) == 0
+    return job
+
+
+def huffman_encode(job, img):
+    """lep_huffencode_kernel on the emulator: scan bytes, per-segment (status, bytes produced).  img: CoefImage with the planes."""
+    assert job.scan_bytes > 0
+    planes = [np.ascontiguousarray(p, dtype=np.int16) for p in img.planes]
+    pp = (ctypes.c_void_p * 3)(*[p.ctypes.data for p in planes] + [None] * (3 - len(planes)))
+    bch = (ctypes.c_int * 3)(*list(img.bch) + [0] * (3 - len(img.bch)))
+    out = (ctypes.c_uint8 * job.scan_bytes)()
+    st = (ctypes.c_int32 * 16)()
+    prod = (ctypes.c_uint32 * 16)()
+    L = lib()
+    L.emu_huffman_encode.restype = ctypes.c_int
+    rc = L.emu_huffman_encode(ctypes.byref(job), img.ncmp, img.mcuv, pp, bch, out, st, prod)
+    if rc != 0:
+        raise RuntimeError("emu_huffman_encode failed with %d" % rc)
+    return bytes(out), [(st[k], prod[k]) for k in range(job.nseg)]

@@ -14,6 +14,7 @@
 #include "../../lepton_b200/csrc/lep_decode_g2.cu"
 #include "../../lepton_b200/csrc/lep_huffpar.cu"
 #include "../../lepton_b200/csrc/lep_mux.cu"
+#include "../../lepton_b200/csrc/lep_huffenc.cu"
 #include "../../include/lepton_b200.h"
 
 using namespace lepb200;
@@ -452,5 +453,68 @@ extern "C" int emu_mux_files(int nfiles, const uint8_t* const* hdr, const size_t
     GatherArgs a{pieces.data(), (uint32_t)pieces.size(), dbase};
     emu::launch((unsigned)std::max(1, grid), GATHER_WARPS * 32, gather_body, &a);
     memcpy(out, dbase, total);
+    return 0;
+}
+
+
+// ---- baseline Huffman ENCODE for the way back (lep_huffenc.cu): the job set-up of lepb200_huffman_encode_resident (henc_launch,
+// lep_capi.cu) with host addresses, one launch over all thread-segments.  planes[c] = coefficient plane of component c
+// (AlignedBlock layout), bch[c] = blocks per row; out receives im->scan_bytes bytes; seg_status[k] / seg_produced[k] what each
+// segment reported.
+namespace {
+struct HEncArgs { const HEncImage* images; HEncSeg* segs; int nseg; const HEncTable* tables; };
+void henc_body(void* p) { const HEncArgs& a = *static_cast<const HEncArgs*>(p); lep_huffencode_kernel(a.images, a.segs, a.nseg, a.tables); }
+bool emu_build_enc_table(const lepb200_hufftable& in, HEncTable& t) {      // build_enc_table of lep_capi.cu (build_huffcodes, jpgcoder.cc:5508-5540)
+    memset(&t, 0, sizeof(t));
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        for (int i = 0; i < in.bits[len]; ++i, ++k, ++code) {
+            if (k >= 256 || code >= (1 << len)) return false;
+            t.code[in.vals[k]] = (uint16_t)code;
+            t.len[in.vals[k]] = (uint8_t)len;
+        }
+        if (code > (1 << len)) return false;
+        code <<= 1;
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" int emu_huffman_encode(const lepb200_henc_image* im, int ncmp, int mcuv, const int16_t* const* planes, const int* bch,
+                                  uint8_t* out, int32_t* seg_status, uint32_t* seg_produced) {
+    if (!im || !planes || !bch || !out || im->scan_bytes == 0 || im->nseg < 1 || im->nseg > LEPB200_MAX_SEGMENTS) return LEPB200_ERR_INVALID;
+    HEncImage d;
+    memset(&d, 0, sizeof(d));
+    std::vector<HEncTable> tabs;
+    d.ncmp = ncmp; d.mcuv = mcuv; d.rsti = im->rsti; d.padbit = im->padbit; d.scan_len = im->scan_bytes;
+    for (int c = 0; c < ncmp; ++c) {
+        d.H[c] = im->H[c]; d.V[c] = im->V[c]; d.bch[c] = bch[c];
+        d.plane[c] = (unsigned long long)(uintptr_t)planes[c];
+        HEncTable t;
+        if (!emu_build_enc_table(im->dc[c], t)) return LEPB200_ERR_INVALID;
+        d.dc_tab[c] = (int)tabs.size(); tabs.push_back(t);
+        if (!emu_build_enc_table(im->ac[c], t)) return LEPB200_ERR_INVALID;
+        d.ac_tab[c] = (int)tabs.size(); tabs.push_back(t);
+    }
+    d.mcuh = bch[0] / im->H[0];
+    std::vector<uint8_t> obuf((size_t)im->scan_bytes + 256 + 512, 0xA5);
+    uint8_t* obase = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)obuf.data(), 256));
+    d.out = (unsigned long long)(uintptr_t)obase;
+    std::vector<HEncSeg> segs;
+    uint32_t off = 0;
+    for (int k = 0; k < im->nseg; ++k) {
+        HEncSeg sg;
+        memset(&sg, 0, sizeof(sg));
+        sg.image = 0; sg.my0 = im->seg[k].mcu_row_start; sg.my1 = im->seg[k].mcu_row_end;
+        for (int c = 0; c < 3; ++c) sg.lastdc[c] = im->seg[k].last_dc[c];
+        sg.ov_bits = im->seg[k].overhang_bits; sg.ov_byte = im->seg[k].overhang_byte;
+        sg.out_off = off; sg.expect = im->seg[k].expect_bytes; sg.is_last = k + 1 == im->nseg;
+        off += im->seg[k].expect_bytes;
+        segs.push_back(sg);
+    }
+    HEncArgs a{&d, segs.data(), (int)segs.size(), tabs.data()};
+    emu::launch((unsigned)((segs.size() + HENC_WARPS - 1) / HENC_WARPS), HENC_WARPS * 32, henc_body, &a);
+    memcpy(out, obase, im->scan_bytes);
+    for (int k = 0; k < im->nseg; ++k) { if (seg_status) seg_status[k] = segs[k].status; if (seg_produced) seg_produced[k] = segs[k].produced; }
     return 0;
 }

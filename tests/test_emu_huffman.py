@@ -103,3 +103,47 @@ def test_no_convergence_within_the_budget_is_handed_to_the_serial_kernel():
     par, (iters, redo) = emu.huffman_decode(emu.HUFF_SUBSEQ, jpegs, sub_bits=256, iter_cap=1)
     assert redo == 1
     check_equal(par[0], ser[0], "iteration budget 1")
+
+
+# ---- the way back: lep_huffencode_kernel (one warp per thread-segment) on the emulator
+HENC_FILES = ["android.jpg", "androidcrop.jpg", "androidcropoptions.jpg", "androidtrail.jpg", "grayscale.jpg", "iphonecrop2.jpg",
+              "trailingrst.jpg", "trailingrst2.jpg"]
+
+
+@pytest.mark.parametrize("name", HENC_FILES)
+def test_huffman_encode_kernel_recreates_the_original_scan(name):
+    """Planes of the JPEG (host Huffman decoder, pinned against the reference's -ujg dump) + the job the product builds from the
+    reference-written .lep (tables, per-segment MCU rows, DC predictors, pending bits, byte counts of the ThreadHandoffs)
+    -> lep_huffencode_kernel on the emulator -> exactly the entropy-coded bytes of the original file's scan, every segment
+    reporting the byte count its handoff promises (recode_row_range, src/lepton/recoder.cc:472-545; restart markers and
+    0xFF stuffing included)."""
+    from lepton_b200 import HostJpeg, HostLep
+    jpg = open(os.path.join(GOLDEN, name), "rb").read()
+    hl = HostLep(open(os.path.join(GOLDEN, name[:-4] + ".lep"), "rb").read())
+    assert hl.status == 0, hl.error
+    off, n = hl.scan_layout()
+    assert n > 0
+    job = emu.henc_job(hl)
+    assert job.scan_bytes == n
+    img = HostJpeg(jpg).coef_image()
+    scan, segs = emu.huffman_encode(job, img)
+    assert [st for st, _ in segs] == [0] * job.nseg, segs
+    assert scan == jpg[off:off + n]
+    assert hl.assemble(scan) == jpg
+
+
+def test_huffman_encode_kernel_multi_segment_reference_files():
+    """Reference-written .lep files with 2 / 4 / 8 thread-segments (-minencodethreads): every segment starts from its own
+    handoff (bits pending in its first byte, DC predictors) and the pieces meet byte for byte."""
+    from helpers import MANIFEST
+    from lepton_b200 import HostJpeg, HostLep
+    for lep_name in ["androidcrop_t2.lep", "android_t4.lep", "iphonecrop2_t8.lep"]:
+        jpg = open(os.path.join(GOLDEN, MANIFEST[lep_name]["source"]), "rb").read()
+        hl = HostLep(open(os.path.join(GOLDEN, lep_name), "rb").read())
+        assert hl.status == 0, hl.error
+        off, n = hl.scan_layout()
+        job = emu.henc_job(hl)
+        assert n > 0 and job.nseg == int(lep_name.split("_t")[1].split(".")[0])
+        scan, segs = emu.huffman_encode(job, HostJpeg(jpg).coef_image())
+        assert [st for st, _ in segs] == [0] * job.nseg, (lep_name, segs)
+        assert scan == jpg[off:off + n], lep_name
