@@ -102,3 +102,26 @@ def test_mixed_batch_many_images(kernel):
     for img, g in zip(imgs, got):
         ref = oracle_encode_image(img)
         assert [x[1] for x in g] == [r[1] for r in ref]
+
+
+def test_zero_quantiser_status_both_directions():
+    """UNSUPPORTED_JPEG_WITH_ZERO_IDCT_0 (reference exit code 43): set_quantization_table refuses a table whose first row /
+    column entries make an IDCT base of zero (src/vp8/model/model.hh:257-262).  Every segment of such an image reports 43 in
+    the oracle, in kernel A and in both decode kernels; nothing is coded."""
+    from lepton_b200 import CoefImage
+    rng = np.random.default_rng(3)
+    img = random_coef_image(rng, ncmp=3, mcuh=4, mcuv=4, sf=((2, 2), (1, 1), (1, 1)), nseg=2)
+    q = [list(t) for t in img.qtables_zigzag]
+    q[1][0] = 0                                  # chroma DC quantiser 0
+    bad = CoefImage(ncmp=img.ncmp, mcuv=img.mcuv, bch=img.bch, bcv=img.bcv, qtables_zigzag=q, planes=img.planes, luma_y_start=img.luma_y_start)
+    ref = oracle_encode_image(bad)
+    assert [r[0] for r in ref] == [43, 43]
+    for kernel in KERNELS:
+        got = emu.encode_images([bad], kernel=kernel)[0]
+        assert [g[0] for g in got] == [43, 43] and all(g[1] == b"" for g in got), kernel
+    good = oracle_encode_image(img)
+    for dk in (emu.KERNEL_WARP, emu.KERNEL_G2(4)):
+        out = CoefImage(ncmp=bad.ncmp, mcuv=bad.mcuv, bch=bad.bch, bcv=bad.bcv, qtables_zigzag=q,
+                        planes=[np.zeros_like(p) for p in bad.planes], luma_y_start=bad.luma_y_start)
+        st, _ = emu.decode_images(dk, [out], [[s for _, s, _ in good]])
+        assert list(st) == [43, 43], (dk, st)
