@@ -98,6 +98,30 @@ def make_corpus(config, distinct, seed0=0):
         return list(ex.map(synth_jpeg, [(config, s) for s in range(seed0, seed0 + distinct)]))
 
 
+def pin_to_gpu_numa_node(local_rank, want_threads):
+    """Ranks of a multi-GPU run: keep this rank's threads (and the pinned staging buffers they first touch) on the NUMA node
+    its GPU hangs on (/sys/bus/pci/devices/<id>/local_cpulist).  Returns the note that goes into the JSON line.  Does nothing
+    when the node cannot be read, is the whole machine, or would leave the rank fewer cores than it wants threads."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cl = open("/sys/bus/pci/devices/%s/local_cpulist" % dev).read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        now = os.sched_getaffinity(0)
+        use = cpus & now
+        if not use or use == now or len(use) < max(1, want_threads):
+            return "not pinned (GPU %s: local cpus %s, %d usable of %d allowed)" % (dev, cl or "?", len(use), len(now))
+        os.sched_setaffinity(0, use)
+        return "pinned to the %d cores of GPU %s's NUMA node (%s)" % (len(use), dev, cl)
+    except Exception as ex:          # no sysfs entry, no permission: run unpinned
+        return "not pinned (%s)" % type(ex).__name__
+
+
 def effective_cores():
     """CPU cores this process may actually use: affinity mask and cgroup quota, whichever is smaller."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -346,6 +370,7 @@ def main():
     jpegs = [distinct[i % len(distinct)] for i in range(args.images)]
     jpeg_bytes = sum(len(j) for j in jpegs)
     threads = args.host_threads or max(1, effective_cores() // max(world, 1))
+    numa_note = pin_to_gpu_numa_node(local_rank, threads) if world > 1 and not os.environ.get("LEPB200_BENCH_NO_PIN") else None
 
     line = {"metric": metric, "unit": "MB/s", "n_gpus": max(world, 1), "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -536,7 +561,7 @@ def main():
             total_jpeg = rsum(jpeg_bytes)
             e2e = {"unit": "MB/s", "h2d_bytes_per_step": int(jpeg_bytes), "d2h_bytes_per_step": int(lep_bytes),
                    "h2d_note": "entropy-coded scan bytes (Huffman decode happens on the GPU); files the host has to decode upload 128 B per block instead",
-                   "steps": args.e2e_steps, "host_threads": threads, "gpu_launches": fc.kernel_launches - l0,
+                   "steps": args.e2e_steps, "host_threads": threads, "host_affinity": numa_note, "gpu_launches": fc.kernel_launches - l0,
                    "encode": {"value": total_jpeg * args.e2e_steps / e_s / 1e6, "unit": "MB/s", "ms_per_step": 1e3 * e_s / args.e2e_steps,
                               "api": "lepb200_compress_jpegs (JPEG bytes -> .lep bytes, host memory)", "stage_seconds_last_step": fc.last_timing()}}
             d_s = None
