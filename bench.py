@@ -98,15 +98,21 @@ def make_corpus(config, distinct, seed0=0):
         return list(ex.map(synth_jpeg, [(config, s) for s in range(seed0, seed0 + distinct)]))
 
 
-def pin_to_gpu_numa_node(local_rank, want_threads):
+def pin_to_gpu_numa_node(local_rank, world, want_threads):
     """Ranks of a multi-GPU run: keep this rank's threads (and the pinned staging buffers they first touch) on the NUMA node
     its GPU hangs on (/sys/bus/pci/devices/<id>/local_cpulist).  Returns the note that goes into the JSON line.  Does nothing
-    when the node cannot be read, is the whole machine, or would leave the rank fewer cores than it wants threads."""
+    when the node cannot be read, is the whole machine, or is too small for the threads of all the ranks whose GPUs share it
+    (2 or 4 ranks on the GPUs of one socket keep the whole machine)."""
     try:
         import torch
-        pr = torch.cuda.get_device_properties(local_rank)
-        dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        cl = open("/sys/bus/pci/devices/%s/local_cpulist" % dev).read().strip()
+
+        def cpulist(i):
+            pr = torch.cuda.get_device_properties(i)
+            dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return dev, open("/sys/bus/pci/devices/%s/local_cpulist" % dev).read().strip()
+
+        dev, cl = cpulist(local_rank)
+        sharing = sum(1 for i in range(world) if cpulist(i)[1] == cl)
         cpus = set()
         for part in cl.split(","):
             if part:
@@ -114,10 +120,10 @@ def pin_to_gpu_numa_node(local_rank, want_threads):
                 cpus.update(range(int(a), int(b or a) + 1))
         now = os.sched_getaffinity(0)
         use = cpus & now
-        if not use or use == now or len(use) < max(1, want_threads):
-            return "not pinned (GPU %s: local cpus %s, %d usable of %d allowed)" % (dev, cl or "?", len(use), len(now))
+        if not use or use == now or len(use) < max(1, want_threads) * sharing:
+            return "not pinned (GPU %s: local cpus %s, %d usable of %d allowed, %d ranks on this node)" % (dev, cl or "?", len(use), len(now), sharing)
         os.sched_setaffinity(0, use)
-        return "pinned to the %d cores of GPU %s's NUMA node (%s)" % (len(use), dev, cl)
+        return "pinned to the %d cores of GPU %s's NUMA node (%s), shared by %d ranks" % (len(use), dev, cl, sharing)
     except Exception as ex:          # no sysfs entry, no permission: run unpinned
         return "not pinned (%s)" % type(ex).__name__
 
@@ -370,7 +376,7 @@ def main():
     jpegs = [distinct[i % len(distinct)] for i in range(args.images)]
     jpeg_bytes = sum(len(j) for j in jpegs)
     threads = args.host_threads or max(1, effective_cores() // max(world, 1))
-    numa_note = pin_to_gpu_numa_node(local_rank, threads) if world > 1 and not os.environ.get("LEPB200_BENCH_NO_PIN") else None
+    numa_note = pin_to_gpu_numa_node(local_rank, world, threads) if world > 1 and not os.environ.get("LEPB200_BENCH_NO_PIN") else None
 
     line = {"metric": metric, "unit": "MB/s", "n_gpus": max(world, 1), "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
