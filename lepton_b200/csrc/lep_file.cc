@@ -854,6 +854,7 @@ int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t
     *scan_bytes = gs.scan_bytes;
     return LEPB200_OK;
 }
+int lepb200_host_brotli_available(void) { return brotli_available() ? 1 : 0; }
 int lepb200_host_lep_henc_image(lepb200_lep* h, lepb200_henc_image* out) {
     if (!h || h->lf.status || !out) return LEPB200_ERR_INVALID;
     GpuRecodeSetup gs;

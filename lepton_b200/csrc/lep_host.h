@@ -174,6 +174,7 @@ struct LepFile {
     std::string error;
 };
 bool read_lep(const uint8_t* data, size_t n, LepFile& lf, bool lazy = false);
+bool brotli_available();          // libbrotlidec could be loaded: container versions 2 / 4 (brotli header blob) are read
 // Set-up for re-encoding the scan on the GPU (lepb200_huffman_encode_resident): false when the file needs the host
 // re-encoder (progressive, truncated, several scans, scan order != frame order, restart-marker budget).
 struct GpuRecodeSetup {

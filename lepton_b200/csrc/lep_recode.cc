@@ -7,11 +7,13 @@
 // concatenates; encoding the scan front to back from the complete planes yields the same bytes, so that is what
 // is done here (one host thread per file; files are processed in parallel by the caller).
 #include <zlib.h>
+#include <dlfcn.h>
 
 #include <emmintrin.h>
 
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 #include "lep_host.h"
 
@@ -22,6 +24,55 @@ inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16
 inline int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 bool lfail(LepFile& lf, int st, const char* msg) { lf.status = st; lf.error = msg; return false; }
 
+// Header blobs of container versions 2 and 4 are brotli streams (write_ujpg, jpgcoder.cc:4032-4041; read_ujpg :4168-4175;
+// the reference vendors the brotli sources).  Brotli needs the 122 KB static dictionary of RFC 7932, which is third-party
+// DATA, so no decoder is written here: the system's libbrotlidec (the same kind of dependency as -lz for version 1) is
+// loaded at run time through its stable streaming C API.  Without the library such files are refused (status 200) as before.
+struct BrotliApi {
+    void* (*create)(void*, void*, void*) = nullptr;
+    int (*stream)(void*, size_t*, const uint8_t**, size_t*, uint8_t**, size_t*) = nullptr;
+    void (*destroy)(void*) = nullptr;
+    bool ok = false;
+};
+const BrotliApi& brotli_api() {
+    static BrotliApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        for (const char* name : {"libbrotlidec.so.1", "libbrotlidec.so"}) { h = dlopen(name, RTLD_NOW | RTLD_LOCAL); if (h) break; }
+        if (!h) return;
+        api.create = reinterpret_cast<void* (*)(void*, void*, void*)>(dlsym(h, "BrotliDecoderCreateInstance"));
+        api.stream = reinterpret_cast<int (*)(void*, size_t*, const uint8_t**, size_t*, uint8_t**, size_t*)>(dlsym(h, "BrotliDecoderDecompressStream"));
+        api.destroy = reinterpret_cast<void (*)(void*)>(dlsym(h, "BrotliDecoderDestroyInstance"));
+        api.ok = api.create && api.stream && api.destroy;
+    });
+    return api;
+}
+// 0 ok, 1 no library, 2 corrupt stream, 3 larger than `cap`
+int brotli_decompress(const uint8_t* in, size_t n, std::vector<uint8_t>& out, size_t cap) {
+    const BrotliApi& b = brotli_api();
+    if (!b.ok) return 1;
+    void* st = b.create(nullptr, nullptr, nullptr);
+    if (!st) return 1;
+    out.resize(std::max<size_t>(4096, n * 6));
+    size_t avail_in = n, have = 0;
+    const uint8_t* next_in = in;
+    int rc = 2;
+    for (;;) {
+        size_t avail_out = out.size() - have;
+        uint8_t* next_out = out.data() + have;
+        const int r = b.stream(st, &avail_in, &next_in, &avail_out, &next_out, nullptr);
+        have = out.size() - avail_out;
+        if (r == 1) { rc = 0; break; }                     // BROTLI_DECODER_RESULT_SUCCESS
+        if (r != 3) { rc = 2; break; }                     // error, or more input wanted than the blob has
+        if (out.size() >= cap) { rc = 3; break; }          // BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT
+        out.resize(std::min(cap, out.size() * 2));
+    }
+    b.destroy(st);
+    out.resize(rc == 0 ? have : 0);
+    return rc;
+}
+
 // AlignedBlock index of each zig-zag position (src/vp8/util/aligned_block.hh:56-65)
 const uint8_t k_zigzag_to_aligned[64] = {
     49, 50, 57, 58, 0, 51, 52, 1, 2, 59, 60, 3, 4, 5, 53, 54, 6, 7, 8, 9, 61, 62, 10, 11,
@@ -29,17 +80,26 @@ const uint8_t k_zigzag_to_aligned[64] = {
     33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48};
 }  // namespace
 
+bool brotli_available() { return brotli_api().ok; }
+
 bool read_lep(const uint8_t* d, size_t n, LepFile& lf, bool lazy) {
     if (n < 28 + 3 + 4 || d[0] != 0xCF || d[1] != 0x84) return lfail(lf, VERSION_UNSUPPORTED, "not a .lep file");
     lf.version = d[2]; lf.flag = d[3]; lf.nseg = d[4];
-    if (lf.version != 1) return lfail(lf, NOT_HANDLED, "only version 1 (zlib header) containers are handled");
+    // version 1: zlib header blob; 2 and 4: brotli header blob (and an EOF marker behind the mux packets); 3: brotli header AND the
+    // ANS coder instead of the bool coder (makeDecoder(..., ujgversion == 3), jpgcoder.cc:1727) -- another codec, refused
+    if (lf.version != 1 && lf.version != 2 && lf.version != 4) return lfail(lf, NOT_HANDLED, "container version not handled (3 = ANS coder)");
     if (lf.flag == 'Y') return lfail(lf, NOT_HANDLED, "-startbyte slices are not handled");
     lf.jpeg_size = rd32(d + 20);
     const uint32_t zlen = rd32(d + 24);
     if ((size_t)28 + zlen + 3 + 4 > n) return lfail(lf, SHORT_READ, "truncated .lep");
     // inflate the header blob
     std::vector<uint8_t> blob;
-    {
+    if (lf.version != 1) {
+        const int rc = brotli_decompress(d + 28, zlen, blob, size_t(256) << 20);
+        if (rc == 1) return lfail(lf, NOT_HANDLED, "brotli header blob (container version 2 / 4) and no libbrotlidec on this system");
+        if (rc == 3) return lfail(lf, 38 /*TOO_MUCH_MEMORY_NEEDED*/, "header blob too large");
+        if (rc) return lfail(lf, ASSERTION_FAILURE, "Data not properly brotli coded");
+    } else {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit(&zs) != Z_OK) return lfail(lf, ASSERTION_FAILURE, "inflateInit failed");
@@ -188,6 +248,7 @@ bool read_lep(const uint8_t* d, size_t n, LepFile& lf, bool lazy) {
     if (lazy) { lf.spans.assign(16, {}); lf.stream_len.assign(16, 0); }
     else lf.streams.assign(16, std::vector<uint8_t>());
     while (q + 3 <= end) {
+        if (d[q] == 0xFF && d[q + 1] == 0xFE && d[q + 2] == 0xFF) break;      // MuxReader::getEofMarker (MuxReader.hh:131-139,240-243), written by versions > 1
         const uint8_t hd = d[q];
         const int sid = hd & 15, flags = (hd >> 4) & 3;
         size_t len, skip;

@@ -101,10 +101,11 @@ def test_roundtripfail_with_verify_is_withheld(expected):
 
 def test_reference_golden_lep_vectors_decode_to_the_pinned_md5(expected):
     """The reference repository's own golden vectors: iphone16.lep (16 thread-segments, test_suite/test_16threads.sh) and
-    gold-legacy.lep (test_suite/test_legacy.sh) must decode to the md5 those scripts pin.  narrowrst.lep
-    (test_suite/test_future_compat.sh) is a version-4 container whose header blob is brotli-coded; the product has no
-    brotli decoder and must REFUSE it with status 200 -- never produce bytes for it.  (Its
-    coefficient streams are pinned against the oracle in tests/test_oracle_golden.py.)"""
+    gold-legacy.lep (test_suite/test_legacy.sh) must decode to the md5 those scripts pin; so must narrowrst.lep
+    (test_suite/test_future_compat.sh), a version-4 container whose header blob is brotli-coded (read through the system's
+    libbrotlidec; where that library is missing the file must be REFUSED with status 200 -- never produce bytes for it)."""
+    import ctypes
+    from lepton_b200 import lib
     from lepton_b200 import LeptonB200FileCodec
     names = ["iphone16.lep", "gold-legacy.lep", "narrowrst.lep"]
     fc = LeptonB200FileCodec(0, host_threads=4)
@@ -113,4 +114,9 @@ def test_reference_golden_lep_vectors_decode_to_the_pinned_md5(expected):
     for n, (st, out) in zip(names[:2], back[:2]):
         assert st == 0, (n, st)
         assert md5(out) == expected[n]["decoded_md5"], n
-    assert back[2][0] == 200 and back[2][1] == b""
+    L = lib()
+    L.lepb200_host_brotli_available.restype = ctypes.c_int
+    if L.lepb200_host_brotli_available() == 1:
+        assert back[2][0] == 0 and md5(back[2][1]) == expected["narrowrst.lep"]["decoded_md5"] == "07e9021d35114bd69f44f5bc1c3788e3"
+    else:
+        assert back[2][0] == 200 and back[2][1] == b""
