@@ -318,6 +318,8 @@ int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t
 /* 1 when the system's libbrotlidec could be loaded: .lep container versions 2 and 4 (brotli-coded header blob, jpgcoder.cc:4168-4175)
  * are then read like version 1; 0: they are refused with status 200.  Version 3 (ANS coder) is always refused. */
 int lepb200_host_brotli_available(void);
+/* test hook: 0 when the container reader's two modes (streams copied out / mux packets recorded in place) agree on this file */
+int lepb200_host_lep_lazy_equal(const uint8_t* data, size_t len);
 /* the job lepb200_huffman_encode_resident wants for this file (scan_bytes == 0: the file needs the host re-encoder) */
 int lepb200_host_lep_henc_image(lepb200_lep* h, lepb200_henc_image* out);
 int lepb200_host_lep_assemble(lepb200_lep* h, const uint8_t* scan, size_t scan_len, const uint8_t** data, size_t* len);

@@ -854,6 +854,26 @@ int lepb200_host_lep_scan_layout(lepb200_lep* h, uint32_t* scan_offset, uint32_t
     *scan_bytes = gs.scan_bytes;
     return LEPB200_OK;
 }
+// Test hook (host only): the container parsed both ways -- streams copied out, and mux packets recorded in place (what
+// lepb200_decompress_leps hands to lepb200_decode_upload_gather) -- must agree on status, segment count and every stream byte.
+int lepb200_host_lep_lazy_equal(const uint8_t* data, size_t len) {
+    if (!data) return LEPB200_ERR_INVALID;
+    LepFile a, b;
+    const bool ra = read_lep(data, len, a, false), rb = read_lep(data, len, b, true);
+    if (ra != rb || a.status != b.status) return 1;
+    if (!ra) return 0;
+    if (a.nseg != b.nseg || (int)a.streams.size() != a.nseg || (int)b.spans.size() != b.nseg || !b.streams.empty()) return 2;
+    for (int t = 0; t < a.nseg; ++t) {
+        if (a.streams[t].size() != b.stream_len[t]) return 3;
+        size_t off = 0;
+        for (const auto& sp : b.spans[t]) {
+            if (off + sp.second > a.streams[t].size() || memcmp(a.streams[t].data() + off, sp.first, sp.second)) return 4;
+            off += sp.second;
+        }
+        if (off != a.streams[t].size()) return 5;
+    }
+    return 0;
+}
 int lepb200_host_brotli_available(void) { return brotli_available() ? 1 : 0; }
 int lepb200_host_lep_henc_image(lepb200_lep* h, lepb200_henc_image* out) {
     if (!h || h->lf.status || !out) return LEPB200_ERR_INVALID;

@@ -180,6 +180,32 @@ def test_future_compat_golden_vector_brotli_header():
     assert jpg == open(os.path.join(GOLDEN, "narrowrst.jpg"), "rb").read() == v1.recode(planes)
 
 
+def test_container_reader_modes_agree():
+    """The batch decoder reads containers with the mux packets recorded in place (gathered into the pinned staging buffer by
+    lepb200_decode_upload_gather); the host API copies the streams out.  Both modes must agree on every golden .lep (1 to 8
+    segments, legacy, version 4 with its EOF marker) and on damaged files (status, and streams where there are any)."""
+    import ctypes
+    import glob
+    import random
+    from lepton_b200 import lib
+    L = lib()
+    L.lepb200_host_lep_lazy_equal.restype = ctypes.c_int
+    L.lepb200_host_lep_lazy_equal.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    files = sorted(glob.glob(os.path.join(GOLDEN, "*.lep")) + glob.glob(os.path.join(GOLDEN, "legacy", "*.lep")) + glob.glob(os.path.join(GOLDEN, "future", "*.lep")))
+    assert len(files) >= 20
+    rnd = random.Random(5)
+    for f in files:
+        raw = open(f, "rb").read()
+        assert L.lepb200_host_lep_lazy_equal(raw, len(raw)) == 0, f
+        for _ in range(6):
+            bad = bytearray(raw)
+            for _ in range(rnd.randrange(1, 4)):
+                bad[rnd.randrange(2, len(bad))] = rnd.randrange(256)
+            if rnd.random() < 0.3:
+                bad = bad[:rnd.randrange(8, len(bad))]
+            assert L.lepb200_host_lep_lazy_equal(bytes(bad), len(bad)) == 0, f
+
+
 def test_container_versions():
     """Version 3 is the ANS coder (another codec behind the same boundary, jpgcoder.cc:1727): always refused with the 'not
     handled' status.  Versions 2 and 4 carry a brotli header blob: a zlib blob under that version byte is 'not properly brotli
