@@ -2,7 +2,7 @@
 // baseline re-encoder and through the JPEG front end.  Build and run:
 //   g++ -O1 -g -std=c++17 -fsanitize=address,undefined -fno-sanitize-recover=undefined -Ilepton_b200/csrc \
 //       tests/tools_fuzz_host.cc lepton_b200/csrc/lep_recode.cc lepton_b200/csrc/lep_jpeg.cc lepton_b200/csrc/lep_container.cc \
-//       -lz -lpthread -o /tmp/fuzz_host && /tmp/fuzz_host 400 tests/golden/*.lep tests/golden/legacy/*.lep tests/golden/*.jpg
+//       -lz -lpthread -ldl -o /tmp/fuzz_host && /tmp/fuzz_host 400 tests/golden/*.lep tests/golden/legacy/*.lep tests/golden/future/*.lep tests/golden/*.jpg
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +22,7 @@ static std::vector<uint8_t> slurp(const char* path) {
 
 static void one_lep(const std::vector<uint8_t>& d, long& ok, long& refused) {
     LepFile lf;
+    { LepFile lz; read_lep(d.data(), d.size(), lz, /*lazy=*/true); }      // the batch decoder's mode: packets recorded in place
     if (!read_lep(d.data(), d.size(), lf)) { ++refused; return; }
     ++ok;
     // re-create the JPEG from all-zero planes: exercises the handoff / restart / truncation bookkeeping
