@@ -57,7 +57,8 @@ def use_default():
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = ctypes.CDLL(build())
+        # LEPB200_EMU_LIB: another build of the harness, e.g. the AddressSanitizer one of tests/tools_emu_sanitize.py
+        _LIB = ctypes.CDLL(os.environ.get("LEPB200_EMU_LIB") or build())
         _LIB.emu_decode_images.restype = ctypes.c_int
         _LIB.emu_encode_images.restype = ctypes.c_int
     return _LIB
